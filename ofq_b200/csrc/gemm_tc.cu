@@ -1,0 +1,350 @@
+// Tensor-core GEMM engine of the OFQ hot path (sm_100a only).
+//
+//   D[z][m][n] (=|+=)  acc[z][m][n] * rs[m] * cs[n]  +  rt[m] * ct[n]
+//   acc[z][m][n] = sum_{k2,k} A[z][k2][m][k] * B[z][k2][n][k]        (both operands K-major)
+//
+// kind::i8  : int8 quantization codes x int8 codes -> exact int32 accumulators in TMEM (forward path:
+//             QLinear / qkx / attention-score / P.V GEMMs of reference qlinear.py:69, attention.py:180,200,210,219).
+// kind::f16 : bf16 x bf16 -> fp32 accumulators (backward dX / dW / attention gradients).
+//
+// One CTA = one 128 x BN output tile. Warp 0 streams 128-byte-swizzled operand tiles with TMA into a
+// multi-stage smem ring, warp 1 (one elected lane) issues tcgen05.mma into a TMEM accumulator, warps 2..5
+// read the accumulator back with tcgen05.ld and apply the rank-1 scale/offset epilogue straight to HBM.
+// Quantizer scales never touch the operands: per-row (token) scales, per-column (StatsQ channel) scales
+// and the affine "move_aft" shift all live in the epilogue vectors, so the MMA itself is exact.
+#include "ofq_b200.h"
+#include "ptx.cuh"
+#include "host_util.h"
+
+namespace ofq {
+
+constexpr int BM = 128;          // UMMA M
+constexpr int KBYTES = 128;      // one 128B swizzle atom of K per stage
+constexpr int NUM_THREADS = 192; // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+
+struct VecRef {
+    const float* p;   // nullptr -> 1.0
+    int period;       // row vectors only: index = i % period
+    long long bs1, bs2;
+};
+
+struct GemmParams {
+    int M, N;
+    int kblocks, k2, splits;
+    int nb1, nb2;
+    int a_b1, a_b2, b_b1, b_b2, c_b1, c_b2;
+    VecRef rs, cs, rt, ct;
+    int has_rank1;
+    int atomic;
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+    static constexpr uint32_t A_BYTES = BM * KBYTES;
+    static constexpr uint32_t B_BYTES = BN * KBYTES;
+    static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr uint32_t OUT_OFF = STAGES * STAGE_BYTES;          // 4 warps x 2 x (32 x 128 B), swizzled
+    static constexpr uint32_t OUT_BYTES = 4 * 2 * 4096;
+    static constexpr uint32_t VEC_OFF = OUT_OFF + OUT_BYTES;            // cs[BN], ct[BN]
+    static constexpr uint32_t BAR_OFF = VEC_OFF + 2 * BN * 4;
+    static constexpr uint32_t TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16;
+    static constexpr size_t DYN_BYTES = TOTAL + 1024;                   // slack for 1024 B alignment
+};
+
+template <int KIND, int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+    using L = SmemLayout<BN, STAGES>;
+    constexpr uint32_t A_BYTES = L::A_BYTES;
+    constexpr uint32_t STAGE_BYTES = L::STAGE_BYTES;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two");
+    constexpr uint32_t UMMA_K_BYTES = 32;  // 32 int8 or 16 bf16 per MMA
+    constexpr uint32_t IDESC = KIND == 0 ? umma_idesc(2u, 1u, BM, BN)   // S32 acc, signed int8
+                                         : umma_idesc(1u, 1u, BM, BN);  // F32 acc, bf16
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+    float* cs_s = reinterpret_cast<float*>(smem + L::VEC_OFF);
+    float* ct_s = cs_s + BN;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // batch / split decode
+    const int nbatch = p.nb1 * p.nb2;
+    const int z = blockIdx.z % nbatch;
+    const int split = blockIdx.z / nbatch;
+    const int b1 = z % p.nb1, b2 = z / p.nb1;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int total_it = p.k2 * p.kblocks;
+    const int it_begin = (int)((long long)total_it * split / p.splits);
+    const int it_end = (int)((long long)total_it * (split + 1) / p.splits);
+    const int nit = it_end - it_begin;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(acc_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            const int kelem = KIND == 0 ? KBYTES : KBYTES / 2;
+            for (int i = 0; i < nit; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                const int it = it_begin + i;
+                const int k2i = it / p.kblocks, kb = it % p.kblocks;
+                uint8_t* sa = smem + s * STAGE_BYTES;
+                uint8_t* sb = sa + A_BYTES;
+                mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                tma_load_5d(sa, &tmA, &full_bar[s], kb * kelem, m0, k2i, b1 * p.a_b1, b2 * p.a_b2);
+                tma_load_5d(sb, &tmB, &full_bar[s], kb * kelem, n0, k2i, b1 * p.b_b1, b2 * p.b_b2);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            for (int i = 0; i < nit; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                const uint64_t adesc = umma_desc_kmajor_sw128(sa);
+                const uint64_t bdesc = umma_desc_kmajor_sw128(sa + A_BYTES);
+#pragma unroll
+                for (uint32_t kk = 0; kk < KBYTES / UMMA_K_BYTES; ++kk) {
+                    const uint64_t adv = (kk * UMMA_K_BYTES) >> 4;
+                    if (KIND == 0)
+                        umma_i8(tmem_base, adesc + adv, bdesc + adv, IDESC, (i | kk) != 0);
+                    else
+                        umma_f16(tmem_base, adesc + adv, bdesc + adv, IDESC, (i | kk) != 0);
+                }
+                tc_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+            }
+            tc_commit(acc_bar);            // accumulator complete
+        }
+    } else {
+        // ---- epilogue: warps 2..5 own TMEM lane quarters (warp % 4)
+        const int q = warp & 3;
+        const int m = m0 + q * 32 + lane;
+        const bool rank1 = p.has_rank1 && split == 0;
+        {   // stage the column vectors of this tile once
+            const long long cs_off = (long long)b1 * p.cs.bs1 + (long long)b2 * p.cs.bs2;
+            const long long ct_off = (long long)b1 * p.ct.bs1 + (long long)b2 * p.ct.bs2;
+            for (int j = threadIdx.x - 64; j < BN; j += 128) {
+                const int n = n0 + j;
+                const bool ok = n < p.N;
+                cs_s[j] = ok ? (p.cs.p ? __ldg(p.cs.p + cs_off + n) : 1.0f) : 0.f;
+                ct_s[j] = (ok && rank1) ? (p.ct.p ? __ldg(p.ct.p + ct_off + n) : 1.0f) : 0.f;
+            }
+            named_bar_sync(1, 128);
+        }
+        const long long rs_off = (long long)b1 * p.rs.bs1 + (long long)b2 * p.rs.bs2;
+        const long long rt_off = (long long)b1 * p.rt.bs1 + (long long)b2 * p.rt.bs2;
+        const bool row_ok = m < p.M;
+        const float rsv = row_ok ? (p.rs.p ? __ldg(p.rs.p + rs_off + (m % p.rs.period)) : 1.0f) : 0.f;
+        const float rtv = (row_ok && rank1) ? (p.rt.p ? __ldg(p.rt.p + rt_off + (m % p.rt.period)) : 1.0f) : 0.f;
+        uint8_t* stage_base = smem + L::OUT_OFF + q * 2 * 4096;
+
+        if (nit > 0) {
+            mbar_wait(acc_bar, 0);
+            tc_fence_after();
+        }
+        int chunk = 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32, ++chunk) {
+            if (n0 + c0 >= p.N) break;  // warp-uniform
+            uint32_t r[32];
+            if (nit > 0) {
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0;
+            }
+            uint8_t* buf = stage_base + (chunk & 1) * 4096;
+            if (chunk >= 2) {  // the staging buffer used two chunks ago must have been read by TMA
+                if (lane == 0) tma_store_wait_read<1>();
+                __syncwarp();
+            }
+            // row `lane` of the 32x32 fp32 box, 128B-swizzled: 16-byte chunk j lands at j ^ (lane % 8)
+            float4* rowp = reinterpret_cast<float4*>(buf + lane * 128);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = 4 * j4 + e;
+                    const float acc = KIND == 0 ? static_cast<float>(static_cast<int32_t>(r[j]))
+                                                : __uint_as_float(r[j]);
+                    o[e] = acc * rsv * cs_s[c0 + j] + rtv * ct_s[c0 + j];
+                }
+                rowp[j4 ^ (lane & 7)] = make_float4(o[0], o[1], o[2], o[3]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if (p.atomic)
+                    tma_reduce_add_5d(&tmC, buf, n0 + c0, m0 + q * 32, 0, b1 * p.c_b1, b2 * p.c_b2);
+                else
+                    tma_store_5d(&tmC, buf, n0 + c0, m0 + q * 32, 0, b1 * p.c_b1, b2 * p.c_b2);
+                tma_store_commit();
+            }
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+template <int KIND, int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                       const GemmParams& p, cudaStream_t stream) {
+    constexpr size_t smem = SmemLayout<BN, STAGES>::DYN_BYTES;
+    auto kern = gemm_tc_kernel<KIND, BN, STAGES>;
+    static bool configured = false;  // per instantiation; attribute is per function, idempotent
+    if (!configured) {
+        OFQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, p.nb1 * p.nb2 * p.splits);
+    kern<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, tmC, p);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static VecRef make_vec(const ofq_vec_t* v) {
+    VecRef r;
+    r.p = v ? v->ptr : nullptr;
+    r.period = (v && v->period > 0) ? v->period : 0x7fffffff;
+    r.bs1 = v ? v->bstride1 : 0;
+    r.bs2 = v ? v->bstride2 : 0;
+    return r;
+}
+
+}  // namespace ofq
+
+using namespace ofq;
+
+// Build a 5-D tensor map {K, rows, k2, b1, b2} with a {128 bytes of K, box_rows, 1, 1, 1} box, 128B swizzle.
+static int make_operand_map(CUtensorMap* tm, const ofq_operand_t* op, int elem_bytes, int rows, int K,
+                            int k2, int nb1, int nb2, int box_rows) {
+    cuuint64_t dims[5] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)k2,
+                          (cuuint64_t)(op->bstride1 ? nb1 : 1), (cuuint64_t)(op->bstride2 ? nb2 : 1)};
+    const cuuint64_t row_b = (cuuint64_t)op->row_stride * elem_bytes;
+    cuuint64_t strides[4] = {row_b,
+                             (cuuint64_t)(op->k2_stride ? op->k2_stride * elem_bytes : row_b),
+                             (cuuint64_t)(op->bstride1 ? op->bstride1 * elem_bytes : row_b),
+                             (cuuint64_t)(op->bstride2 ? op->bstride2 * elem_bytes : row_b)};
+    for (int i = 0; i < 4; ++i)
+        if (strides[i] % 16) {
+            ofq_set_error("gemm operand stride %d (%llu bytes) is not a multiple of 16", i,
+                          (unsigned long long)strides[i]);
+            return OFQ_ERR_ARG;
+        }
+    if (reinterpret_cast<uintptr_t>(op->ptr) % 16) {
+        ofq_set_error("gemm operand pointer is not 16-byte aligned");
+        return OFQ_ERR_ARG;
+    }
+    cuuint32_t box[5] = {(cuuint32_t)(KBYTES / elem_bytes), (cuuint32_t)box_rows, 1, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return ofq_encode_tensor_map(tm, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                                     : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                                 5, const_cast<void*>(op->ptr), dims, strides, box, estr);
+}
+
+// Output map {N, M, 1, b1, b2}, fp32, 32 x 32 box (one epilogue warp's chunk), 128B swizzle.
+static int make_out_map(CUtensorMap* tm, const ofq_gemm_out_t* out, int M, int N, int nb1, int nb2) {
+    if (reinterpret_cast<uintptr_t>(out->ptr) % 16 || out->ld % 4 || out->bstride1 % 4 || out->bstride2 % 4) {
+        ofq_set_error("gemm output must be 16-byte aligned with ld / batch strides that are multiples of 4 floats");
+        return OFQ_ERR_ARG;
+    }
+    const cuuint64_t row_b = (cuuint64_t)out->ld * 4;
+    cuuint64_t dims[5] = {(cuuint64_t)N, (cuuint64_t)M, 1, (cuuint64_t)(out->bstride1 ? nb1 : 1),
+                          (cuuint64_t)(out->bstride2 ? nb2 : 1)};
+    cuuint64_t strides[4] = {row_b, row_b, (cuuint64_t)(out->bstride1 ? out->bstride1 * 4 : row_b),
+                             (cuuint64_t)(out->bstride2 ? out->bstride2 * 4 : row_b)};
+    cuuint32_t box[5] = {32, 32, 1, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return ofq_encode_tensor_map(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, out->ptr, dims, strides, box, estr);
+}
+
+extern "C" int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B, const ofq_gemm_out_t* out,
+                        int M, int N, int K, int k2, int nb1, int nb2, int splits, const ofq_vec_t* rs,
+                        const ofq_vec_t* cs, const ofq_vec_t* rt, const ofq_vec_t* ct, void* stream) {
+    if (kind != OFQ_GEMM_I8 && kind != OFQ_GEMM_BF16) {
+        ofq_set_error("ofq_gemm: unknown kind %d", kind);
+        return OFQ_ERR_ARG;
+    }
+    if (M <= 0 || N <= 0 || K <= 0 || k2 <= 0 || nb1 <= 0 || nb2 <= 0 || splits <= 0) {
+        ofq_set_error("ofq_gemm: non-positive extent");
+        return OFQ_ERR_ARG;
+    }
+    OFQ_CHECK_ARCH();
+    const int eb = kind == OFQ_GEMM_I8 ? 1 : 2;
+    const int kelem = KBYTES / eb;
+    GemmParams p;
+    p.M = M; p.N = N;
+    p.kblocks = (K + kelem - 1) / kelem;
+    p.k2 = k2; p.splits = splits;
+    p.nb1 = nb1; p.nb2 = nb2;
+    p.a_b1 = A->bstride1 != 0; p.a_b2 = A->bstride2 != 0;
+    p.b_b1 = B->bstride1 != 0; p.b_b2 = B->bstride2 != 0;
+    p.c_b1 = out->bstride1 != 0; p.c_b2 = out->bstride2 != 0;
+    p.rs = make_vec(rs); p.cs = make_vec(cs); p.rt = make_vec(rt); p.ct = make_vec(ct);
+    p.has_rank1 = (rt && rt->ptr) || (ct && ct->ptr);
+    p.atomic = out->accumulate;
+    if (splits > 1 && !p.atomic) {
+        ofq_set_error("ofq_gemm: split-K requires an accumulating (pre-zeroed) output");
+        return OFQ_ERR_ARG;
+    }
+    // tile width: widest tile that does not waste more than a quarter of its columns
+    int bn = N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
+    if (bn == 256 && (N % 256) != 0 && (N % 256) <= 128 && N < 512) bn = 128;
+    if (bn == 256 && (long long)((M + BM - 1) / BM) * ((N + 255) / 256) * nb1 * nb2 * splits < 148) bn = 128;
+    CUtensorMap tmA, tmB, tmC;
+    int rc = make_operand_map(&tmA, A, eb, M, K, k2, nb1, nb2, BM);
+    if (rc) return rc;
+    rc = make_operand_map(&tmB, B, eb, N, K, k2, nb1, nb2, bn);
+    if (rc) return rc;
+    rc = make_out_map(&tmC, out, M, N, nb1, nb2);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define OFQ_DISPATCH(KIND)                                                   \
+    switch (bn) {                                                            \
+        case 256: return launch_gemm<KIND, 256, 3>(tmA, tmB, tmC, p, st);    \
+        case 128: return launch_gemm<KIND, 128, 2>(tmA, tmB, tmC, p, st);    \
+        case 64:  return launch_gemm<KIND, 64, 4>(tmA, tmB, tmC, p, st);     \
+        default:  return launch_gemm<KIND, 32, 4>(tmA, tmB, tmC, p, st);     \
+    }
+    if (kind == OFQ_GEMM_I8) { OFQ_DISPATCH(0) } else { OFQ_DISPATCH(1) }
+#undef OFQ_DISPATCH
+}
