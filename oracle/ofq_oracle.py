@@ -289,7 +289,7 @@ def patch_embed_q(img: Tensor, P: Params, pre: str, state: dict) -> Tensor:
                     lambda: 2 * w.detach().abs().mean(dim=-1).mean(dim=-1).mean(dim=-1) / (hi ** 0.5))
     wq = _lsq_generic(w, sw.view(-1, 1, 1, 1), w.shape[1] * w.shape[2] * w.shape[3], lo, hi)
     x = img + P[pre + "move_b4.bias"].reshape(img.shape[-1], img.shape[-2]).expand_as(img)
-    if float(x.min()) < -1e-5:
+    if float(x.detach().min()) < -1e-5:
         state["signed"] = 1  # sticky, lsq.py:338-339
     ilo, ihi = (0, 255) if not state.get("signed", 0) else (-128, 127)
     sx = _get_scale(P, pre + "input_quant_fn.s",
