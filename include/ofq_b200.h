@@ -48,7 +48,8 @@ OFQ_API int ofq_device_ok(void);
 typedef struct {
     const void* ptr;
     long long row_stride; /* elements between consecutive rows (m or n) */
-    long long k2_stride;  /* elements between outer-K slices (0 if k2 == 1) */
+    long long k2_stride;  /* elements between outer-K slices; 0 = the operand is shared by all slices */
+    int k2_mod;           /* > 0: slice index used for this operand is (k2 index % k2_mod); 0: the k2 index itself */
     long long bstride1;   /* elements between batch-axis-1 entries, 0 = broadcast */
     long long bstride2;   /* elements between batch-axis-2 entries, 0 = broadcast */
 } ofq_operand_t;
@@ -72,6 +73,124 @@ OFQ_API int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B, c
              int M, int N, int K, int k2, int nb1, int nb2, int splits,
              const ofq_vec_t* rs, const ofq_vec_t* cs, const ofq_vec_t* rt, const ofq_vec_t* ct,
              void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  StatsQuantizer.forward as integer codes (reference statsq.py:133-150).
+ *   sf[r]       = 2 * mean_c |w[r][c]|                       (row sum accumulated in fp64, then fp32 ops)
+ *   k           = rint( clamp(w/sf, -1, 1-1e-6) * n - 0.5 ),  n = 2^(bits-1)       (IEEE div, no FMA)
+ *   codes[r][c] = 2k+1  (odd, |code| <= 2^bits - 1)  so that  w_q = sf/(2n) * code
+ *   colscale[r] = sf[r] / (2n)
+ *   colterm[r]  = colscale[r] * sum_c aft[c] * codes[r][c] + bias[r]   (optional: the move_aft shift of the
+ *                 layer input folded through the weights, qlinear.py:68-71; aft/bias may be NULL)
+ *   kminmax     = optional int32[2] {min k, max k} over the whole tensor, atomically updated (pre-set to
+ *                 {INT_MAX, INT_MIN}); cga.py:459-463 needs it.
+ */
+OFQ_API int ofq_statsq_codes(const float* w, int rows, int cols, long long ldw, int bits, int8_t* codes,
+                             long long ldq, float* colscale, float* sf, const float* aft, const float* bias,
+                             float* colterm, int* kminmax, void* stream);
+
+/* LSQ effective step size (lsq.py:593): out[i] = (a - a*g) + a*g with a = alpha[i] > 1e-5 ? alpha[i] : 1e-5,
+ * evaluated in fp32 exactly as grad_scale(clip(alpha)) does. */
+OFQ_API int ofq_lsq_effective_scale(const float* alpha, int n, float g, float* out, void* stream);
+
+/* K2  LearnableBias + LsqQuantizer / LsqQuantizer4v forward as integer codes
+ * (qbias.py:10-13, lsq.py:571-602, 757-790):   codes = rint( clamp( (x + b4[col]) / s_eff, qlo, qhi ) ).
+ *   x        [rows][cols] fp32, row stride ldx; a row is `nseg` segments of cols/nseg columns
+ *            (nseg = heads for the (B, N*H, C) view of qkx, attention.py:202-205; 1 otherwise)
+ *   b4       shift of length cols
+ *   s_eff    effective scales from ofq_lsq_effective_scale;
+ *            scale_mode OFQ_SCALE_PER_ROW: index (row % period) * nseg + segment   (per token [, head])
+ *            scale_mode OFQ_SCALE_PER_COL: index col                               (LsqQuantizer4v)
+ */
+#define OFQ_SCALE_PER_ROW 0
+#define OFQ_SCALE_PER_COL 1
+OFQ_API int ofq_lsq_quant(const float* x, long long rows, int cols, long long ldx, const float* b4,
+                          const float* s_eff, int scale_mode, int period, int nseg, int qlo, int qhi,
+                          int8_t* codes, long long ldq, void* stream);
+
+/* Backward of (LearnableBias -> LSQ -> LearnableBias) given dy = dL/d(x_hat) (autograd of lsq.py:571-602):
+ *   v = (x + b4)/s_eff;  inside = qlo <= v <= qhi;  q = rint(clamp(v))
+ *   dx = dy * inside;  d_aft[c] = sum dy;  d_b4[c] = sum dx;  d_s[idx] = g * sum dy * (q - inside * v)
+ * Partial sums go to `workspace` (float[ofq_lsq_bwd_workspace(...)], no atomics, deterministic) and are
+ * reduced by ofq_lsq_bwd_finalize. dx may alias dy.
+ */
+OFQ_API long long ofq_lsq_bwd_workspace(long long rows, int cols, int nseg);
+OFQ_API int ofq_lsq_bwd(const float* dy, long long lddy, const float* x, long long ldx, long long rows, int cols,
+                        const float* b4, const float* s_eff, int scale_mode, int period, int nseg,
+                        int qlo, int qhi, float* dx, long long lddx, float* workspace, void* stream);
+OFQ_API int ofq_lsq_bwd_finalize(const float* workspace, long long rows, int cols, int scale_mode, int period,
+                                 int nseg, float g, float* d_s, float* d_b4, float* d_aft, void* stream);
+
+/* Gradient operand preparation for the bf16 backward GEMMs: one pass over a fp32 gradient x[nb][R][C]:
+ *   out_rm[p][b][r][c] = bf16 plane p of ( x * cs[c] )              (row-major, ld = ld_rm; NULL to skip)
+ *   out_t [p][b][c][r] = bf16 plane p of ( x * rs[r % rs_period] )  (per-batch transpose, pitch r_pad; NULL to skip)
+ *     planes = 1: plane 0 = bf16(v).  planes = 2: plane 0 = hi = bf16(v), plane 1 = lo = bf16(v - hi); feeding both
+ *     planes to the GEMM as two outer-K slices gives ~16 mantissa bits (the integer-code operand is exact in bf16).
+ *   colsum[c]       = sum_{b,r} x                      (optional; pre-zeroed, atomically accumulated)
+ *   rowdot[b][g][r] = sum_{c in group g} x * u[c]      (optional; groups of `group` = 16, 32 or 64 consecutive columns)
+ */
+OFQ_API int ofq_grad_prep(const float* x, int nb, int R, int C, long long ldx, long long bstride_x,
+                          const float* cs, const float* rs, int rs_period, int planes, void* out_rm,
+                          long long ld_rm, void* out_t, int r_pad, float* colsum, const float* u, int group,
+                          float* rowdot, void* stream);
+
+/* int8 codes [nb][R][C] (row stride ld, batch stride bstride) -> bf16, optionally transposed per batch:
+ *   transpose = 0: out[b][r][c] (row stride ld_out);   transpose = 1: out[b][c][r] (row pitch ld_out >= R) */
+OFQ_API int ofq_codes_to_bf16(const int8_t* codes, int nb, int R, int C, long long ld, long long bstride,
+                              void* out, long long ld_out, long long bstride_out, int transpose, void* stream);
+/* out[row][seg] = sum_{c in segment seg} u[c] * codes[row][c]  (the move_aft shift of one attention operand
+ * folded through the other operand's codes; row has nseg segments of cols/nseg columns). */
+OFQ_API int ofq_codes_rowdot(const int8_t* codes, long long rows, int cols, long long ld, int nseg,
+                             const float* u, float* out, void* stream);
+/* int8 codes [nb][R][C] -> int8 transposed [nb][C][r_pad] (V operand of the P.V GEMM). */
+OFQ_API int ofq_codes_transpose(const int8_t* codes, int nb, int R, int C, long long ld, long long bstride,
+                                int8_t* out, long long ld_out, long long bstride_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Softmax + unsigned LSQ of the attention probabilities (attention.py:96-99 / 212-216,
+ * swin_attention_and_mlp.py:201-227):   P = softmax_d( S[z][n][:] + bias[h][n][:] + mask[w][n][:] ),
+ * codes = rint( clamp( P / s_eff[n], 0, qhi ) ),  rowsum[z][n] = s_eff[n] * sum_d codes.
+ *   S     [nz][N][ld] fp32 (already multiplied by head_dim^-0.5), z = (b*H + h); window index w = b % nW
+ *   P     optional fp32 output (saved for backward), same layout as S
+ *   codes [nz][N][ldq] int8, columns N..ldq-1 are zero-filled
+ */
+OFQ_API int ofq_softmax_quant(const float* S, int nz, int N, long long ld, int H, const float* bias,
+                              const float* mask, int nW, const float* s_eff, int qhi, float* P, int8_t* codes,
+                              long long ldq, float* rowsum, void* stream);
+
+/* Backward of softmax + LSQ given dPq = dL/dP_hat [nz][N][ld] and the saved P:
+ *   v = P/s;  inside = v <= qhi (v >= 0 always);  dP = dPq * inside
+ *   d_s[n] += g_s * sum_{z,d} dPq * (q - inside * v)                  (atomic; d_s pre-zeroed)
+ *   dS = alpha * P * (dP - sum_d P*dP)                                 (alpha = head_dim^-0.5 of the logits)
+ *   out_a [b][p][h][n][d] = bf16 plane p of ( dS * ca[d] )   ca index (h*N + d) if ca_per_head else d  (pitch ldo)
+ *   out_bt[b][p][h][d][n] = bf16 plane p of ( dS * rb[n] )   (transposed, pitch ldo);  planes as in ofq_grad_prep
+ *   colsum[z][d]   += sum_n dS              (optional, atomic, pre-zeroed)
+ *   dS32            = optional fp32 P * (dP - sum_d P*dP) WITHOUT alpha, layout of P: the gradient w.r.t. the
+ *                     additive pre-softmax bias (Swin relative-position bias)
+ */
+OFQ_API int ofq_softmax_quant_bwd(const float* dPq, const float* P, int nz, int N, long long ld, int H,
+                                  const float* s_eff, int qhi, float alpha, float g_s, const float* ca,
+                                  int ca_per_head, const float* rb, int planes, void* out_a, void* out_bt,
+                                  long long ldo, float* colsum, float* d_s, float* dS32, void* stream);
+
+/* K4  W_qk[h] = W_q[h]^T W_k[h] in fp32 (attention.py:190-194) and its backward. wq, wk: [H*hd][C]. */
+OFQ_API int ofq_wqk_compose(const float* wq, const float* wk, int H, int hd, int C, float* wqk, void* stream);
+OFQ_API int ofq_wqk_compose_bwd(const float* dwqk, const float* wq, const float* wk, int H, int hd, int C,
+                                float* dwq, float* dwk, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K7  CGA: freeze mask (cga.py:450-469) and the masked AdamW step (cga.py:953-1013 + torch.optim.AdamW).
+ * ofq_cga_mask writes 1 for frozen, 0 for trainable (the reference's `freeze_idx`).
+ * ofq_cga_adamw updates p, exp_avg, exp_avg_sq in place in ONE pass: frozen elements see a zero gradient
+ * (moments decay, weight untouched bit-for-bit); bits == 0 disables masking (plain AdamW for the other params).
+ * rowstat: float[rows] scratch for the per-row StatsQ scale; kminmax: int32[2] scratch.
+ */
+OFQ_API int ofq_cga_mask(const float* w, int rows, int cols, int bits, double boundary_range, uint8_t* mask,
+                         float* rowstat, int* kminmax, void* stream);
+OFQ_API int ofq_cga_adamw(float* p, const float* grad, float* exp_avg, float* exp_avg_sq, long long numel,
+                          int rows, int cols, int step, double lr, double beta1, double beta2, double eps,
+                          double weight_decay, int bits, double boundary_range, float* rowstat, int* kminmax,
+                          uint8_t* mask_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@ class OfqError(RuntimeError):
 
 
 class Operand(C.Structure):
-    _fields_ = [("ptr", C.c_void_p), ("row_stride", C.c_longlong), ("k2_stride", C.c_longlong),
+    _fields_ = [("ptr", C.c_void_p), ("row_stride", C.c_longlong), ("k2_stride", C.c_longlong), ("k2_mod", C.c_int),
                 ("bstride1", C.c_longlong), ("bstride2", C.c_longlong)]
 
 
@@ -31,6 +31,34 @@ class GemmOut(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("ld", C.c_longlong), ("bstride1", C.c_longlong),
                 ("bstride2", C.c_longlong), ("accumulate", C.c_int)]
 
+
+_p, _i, _ll, _f, _d = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
+
+# name -> (restype, argtypes); must list every symbol include/ofq_b200.h declares (tests/test_abi.py checks)
+SIGNATURES = {
+    "ofq_version": (_i, []),
+    "ofq_last_error": (C.c_char_p, []),
+    "ofq_device_ok": (_i, []),
+    "ofq_gemm": (_i, [_i, C.POINTER(Operand), C.POINTER(Operand), C.POINTER(GemmOut), _i, _i, _i, _i, _i, _i, _i,
+                      C.POINTER(Vec), C.POINTER(Vec), C.POINTER(Vec), C.POINTER(Vec), _p]),
+    "ofq_statsq_codes": (_i, [_p, _i, _i, _ll, _i, _p, _ll, _p, _p, _p, _p, _p, _p, _p]),
+    "ofq_lsq_effective_scale": (_i, [_p, _i, _f, _p, _p]),
+    "ofq_lsq_quant": (_i, [_p, _ll, _i, _ll, _p, _p, _i, _i, _i, _i, _i, _p, _ll, _p]),
+    "ofq_lsq_bwd_workspace": (_ll, [_ll, _i, _i]),
+    "ofq_lsq_bwd": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _i, _i, _i, _i, _i, _p, _ll, _p, _p]),
+    "ofq_lsq_bwd_finalize": (_i, [_p, _ll, _i, _i, _i, _i, _f, _p, _p, _p, _p]),
+    "ofq_grad_prep": (_i, [_p, _i, _i, _i, _ll, _ll, _p, _p, _i, _i, _p, _ll, _p, _i, _p, _p, _i, _p, _p]),
+    "ofq_codes_to_bf16": (_i, [_p, _i, _i, _i, _ll, _ll, _p, _ll, _ll, _i, _p]),
+    "ofq_codes_transpose": (_i, [_p, _i, _i, _i, _ll, _ll, _p, _ll, _ll, _p]),
+    "ofq_codes_rowdot": (_i, [_p, _ll, _i, _ll, _i, _p, _p, _p]),
+    "ofq_softmax_quant": (_i, [_p, _i, _i, _ll, _i, _p, _p, _i, _p, _i, _p, _p, _ll, _p, _p]),
+    "ofq_softmax_quant_bwd": (_i, [_p, _p, _i, _i, _ll, _i, _p, _i, _f, _f, _p, _i, _p, _i, _p, _p, _ll, _p, _p, _p, _p]),
+    "ofq_wqk_compose": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "ofq_wqk_compose_bwd": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
+    "ofq_cga_mask": (_i, [_p, _i, _i, _i, _d, _p, _p, _p, _p]),
+    "ofq_cga_adamw": (_i, [_p, _p, _p, _p, _ll, _i, _i, _i, _d, _d, _d, _d, _d, _i, _d, _p, _p, _p, _p]),
+}
+EXPORTS = list(SIGNATURES)
 
 _lib = None
 
@@ -49,25 +77,12 @@ def load(build_if_missing: bool = False):
                 f"{LIB_PATH} is missing: run `python -m ofq_b200.build` (or __graft_entry__.build()). "
                 "ofq_b200 has no CPU / PyTorch fallback.")
     lib = C.CDLL(str(LIB_PATH))
-    lib.ofq_last_error.restype = C.c_char_p
-    for name in EXPORTS:
-        getattr(lib, name)  # raises AttributeError if an export is missing
-    for name in EXPORTS:
-        if name not in ("ofq_last_error",):
-            getattr(lib, name).restype = C.c_int
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if an export is missing
+        fn.restype = res
+        fn.argtypes = args
     _lib = lib
     return lib
-
-
-# every symbol include/ofq_b200.h declares (tests/test_abi.py cross-checks this list against the header)
-EXPORTS = [
-    "ofq_version", "ofq_last_error", "ofq_device_ok", "ofq_gemm",
-    "ofq_statsq_codes", "ofq_lsq_effective_scale", "ofq_lsq_quant", "ofq_lsq_bwd", "ofq_lsq_bwd_finalize",
-    "ofq_cvt_bf16", "ofq_cvt_bf16_t", "ofq_codes_bf16_t", "ofq_colsum",
-    "ofq_softmax_quant", "ofq_softmax_quant_bwd",
-    "ofq_wqk_compose", "ofq_wqk_compose_bwd",
-    "ofq_cga_mask", "ofq_cga_adamw",
-]
 
 
 def check(rc: int) -> None:
@@ -76,10 +91,10 @@ def check(rc: int) -> None:
         raise OfqError(f"ofq_b200 C-ABI call failed ({rc}): {msg}")
 
 
-def stream_ptr() -> C.c_void_p:
+def stream_ptr() -> int:
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return torch.cuda.current_stream().cuda_stream
 
 
-def ptr(t) -> C.c_void_p:
-    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+def ptr(t) -> int:
+    return t.data_ptr() if t is not None else None

@@ -33,6 +33,8 @@ struct GemmParams {
     int kblocks, k2, splits;
     int nb1, nb2;
     int a_b1, a_b2, b_b1, b_b2, c_b1, c_b2;
+    int a_k2, b_k2;          // 0: operand shared by all outer-K slices
+    int a_k2mod, b_k2mod;    // slice index = k2 % mod
     VecRef rs, cs, rt, ct;
     int has_rank1;
     int atomic;
@@ -120,8 +122,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint8_t* sa = smem + s * STAGE_BYTES;
                 uint8_t* sb = sa + A_BYTES;
                 mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-                tma_load_5d(sa, &tmA, &full_bar[s], kb * kelem, m0, k2i, b1 * p.a_b1, b2 * p.a_b2);
-                tma_load_5d(sb, &tmB, &full_bar[s], kb * kelem, n0, k2i, b1 * p.b_b1, b2 * p.b_b2);
+                tma_load_5d(sa, &tmA, &full_bar[s], kb * kelem, m0, (k2i % p.a_k2mod) * p.a_k2, b1 * p.a_b1, b2 * p.a_b2);
+                tma_load_5d(sb, &tmB, &full_bar[s], kb * kelem, n0, (k2i % p.b_k2mod) * p.b_k2, b1 * p.b_b1, b2 * p.b_b2);
             }
         }
     } else if (warp == 1) {
@@ -257,7 +259,8 @@ using namespace ofq;
 // Build a 5-D tensor map {K, rows, k2, b1, b2} with a {128 bytes of K, box_rows, 1, 1, 1} box, 128B swizzle.
 static int make_operand_map(CUtensorMap* tm, const ofq_operand_t* op, int elem_bytes, int rows, int K,
                             int k2, int nb1, int nb2, int box_rows) {
-    cuuint64_t dims[5] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)k2,
+    const int k2_eff = op->k2_stride ? (op->k2_mod > 0 ? (op->k2_mod < k2 ? op->k2_mod : k2) : k2) : 1;
+    cuuint64_t dims[5] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)k2_eff,
                           (cuuint64_t)(op->bstride1 ? nb1 : 1), (cuuint64_t)(op->bstride2 ? nb2 : 1)};
     const cuuint64_t row_b = (cuuint64_t)op->row_stride * elem_bytes;
     cuuint64_t strides[4] = {row_b,
@@ -318,6 +321,9 @@ extern "C" int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B
     p.nb1 = nb1; p.nb2 = nb2;
     p.a_b1 = A->bstride1 != 0; p.a_b2 = A->bstride2 != 0;
     p.b_b1 = B->bstride1 != 0; p.b_b2 = B->bstride2 != 0;
+    p.a_k2 = A->k2_stride != 0; p.b_k2 = B->k2_stride != 0;
+    p.a_k2mod = A->k2_mod > 0 ? A->k2_mod : 0x7fffffff;
+    p.b_k2mod = B->k2_mod > 0 ? B->k2_mod : 0x7fffffff;
     p.c_b1 = out->bstride1 != 0; p.c_b2 = out->bstride2 != 0;
     p.rs = make_vec(rs); p.cs = make_vec(cs); p.rt = make_vec(rt); p.ct = make_vec(ct);
     p.has_rank1 = (rt && rt->ptr) || (ct && ct->ptr);

@@ -1,0 +1,202 @@
+// K7: confidence-guided-annealing freeze mask (cga.py:450-469) fused into the AdamW update
+// (cga.py:953-1013 around torch.optim.AdamW). One pre-pass computes the per-row StatsQ scale and the global
+// min/max rounding level; one pass then reads p, g, m, v and writes p, m, v (32 B/param in total).
+#include "host_util.h"
+#include "ofq_b200.h"
+#include <climits>
+#include <cmath>
+#include <cstdint>
+
+namespace {
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// statsq.py:137-147 restated: b4_round = clamp(w/sf, -1, 1-1e-6) * n - 0.5
+__device__ __forceinline__ float statsq_b4(float w, float sf, float n_levels) {
+    float v = __fdiv_rn(w, sf);
+    v = fminf(fmaxf(v, -1.0f), __fsub_rn(1.0f, 1e-6f));
+    return __fsub_rn(__fmul_rn(v, n_levels), 0.5f);
+}
+
+__global__ void cga_init_kernel(int* kminmax) {
+    kminmax[0] = INT_MAX;
+    kminmax[1] = INT_MIN;
+}
+
+__global__ void __launch_bounds__(256)
+cga_rowstat_kernel(const float* __restrict__ w, int rows, int cols, float n_levels, float* __restrict__ rowstat,
+                   int* __restrict__ kminmax) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + warp;
+    if (row >= rows) return;
+    const float* wr = w + (long long)row * cols;
+    double acc = 0.0;
+    for (int c = lane; c < cols; c += 32) acc += (double)fabsf(__ldg(wr + c));
+    acc = warp_sum_d(acc);
+    const float sf = __fmul_rn(2.0f, __fdiv_rn((float)acc, (float)cols));
+    int kmin = INT_MAX, kmax = INT_MIN;
+    for (int c = lane; c < cols; c += 32) {
+        const int k = (int)rintf(statsq_b4(__ldg(wr + c), sf, n_levels));
+        kmin = min(kmin, k);
+        kmax = max(kmax, k);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if (lane == 0) {
+        rowstat[row] = sf;
+        atomicMin(kminmax, kmin);
+        atomicMax(kminmax + 1, kmax);
+    }
+}
+
+// cga.py:465-469: trainable iff for some integer i in [kmin, kmax): 0.5-BR <= b4 - i <= 0.5+BR (fp32 compares).
+// Only i = floor(b4) can satisfy it.
+__device__ __forceinline__ bool cga_frozen(float w, float sf, float n_levels, int kmin, int kmax, float lo_thr,
+                                           float hi_thr) {
+    const float b4 = statsq_b4(w, sf, n_levels);
+    const float fi = floorf(b4);
+    const int i = (int)fi;
+    bool trainable = false;
+    if (i >= kmin && i < kmax) {
+        const float d = __fsub_rn(b4, fi);
+        trainable = (d <= hi_thr) && (d >= lo_thr);
+    }
+    return !trainable;
+}
+
+__global__ void __launch_bounds__(256)
+cga_mask_kernel(const float* __restrict__ w, long long numel, int cols, float n_levels,
+                const float* __restrict__ rowstat, const int* __restrict__ kminmax, float lo_thr, float hi_thr,
+                uint8_t* __restrict__ mask) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numel) return;
+    const int kmin = kminmax[0], kmax = kminmax[1];
+    mask[i] = cga_frozen(__ldg(w + i), __ldg(rowstat + i / cols), n_levels, kmin, kmax, lo_thr, hi_thr) ? 1 : 0;
+}
+
+struct AdamScalars {
+    float decay;        // 1 - lr * wd
+    float one_m_b1;     // 1 - beta1
+    float beta2;
+    float one_m_b2;
+    float step_size;    // lr / (1 - beta1^t)
+    float bc2_sqrt;     // sqrt(1 - beta2^t)
+    float eps;
+};
+
+// torch/optim/adamw.py::_single_tensor_adamw element-wise math.
+__device__ __forceinline__ void adamw_elem(float& p, float g, float& m, float& v, const AdamScalars& a, bool frozen) {
+    if (frozen) g = 0.f;                                    // cga.py:958 grad * freeze_idx * 0
+    const float p_new0 = p * a.decay;                       // param.mul_(1 - lr * wd)
+    m = fmaf(a.one_m_b1, g - m, m);                         // exp_avg.lerp_(grad, 1 - beta1)
+    v = fmaf(a.one_m_b2 * g, g, v * a.beta2);               // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+    const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+    const float p_new = p_new0 - a.step_size * (m / denom); // param.addcdiv_(exp_avg, denom, value=-step_size)
+    if (!frozen) p = p_new;                                 // cga.py:1002-1005 restores frozen weights bit-for-bit
+}
+
+template <bool MASKED>
+__global__ void __launch_bounds__(256)
+cga_adamw_kernel(float* __restrict__ p, const float* __restrict__ grad, float* __restrict__ m,
+                 float* __restrict__ v, long long numel, int cols, float n_levels,
+                 const float* __restrict__ rowstat, const int* __restrict__ kminmax, float lo_thr, float hi_thr,
+                 AdamScalars a, uint8_t* __restrict__ mask_out) {
+    const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= numel) return;
+    int kmin = 0, kmax = 0;
+    if (MASKED) { kmin = kminmax[0]; kmax = kminmax[1]; }
+    if (i4 + 4 <= numel && (cols % 4 == 0 || !MASKED)) {
+        float4 pp = *reinterpret_cast<float4*>(p + i4);
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(grad + i4));
+        float4 mm = *reinterpret_cast<float4*>(m + i4);
+        float4 vv = *reinterpret_cast<float4*>(v + i4);
+        float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+        const float sf = MASKED ? __ldg(rowstat + i4 / cols) : 1.f;
+        uint8_t fr[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const bool frozen = MASKED ? cga_frozen(pa[e], sf, n_levels, kmin, kmax, lo_thr, hi_thr) : false;
+            fr[e] = frozen;
+            adamw_elem(pa[e], ga[e], ma[e], va[e], a, frozen);
+        }
+        *reinterpret_cast<float4*>(p + i4) = pp;
+        *reinterpret_cast<float4*>(m + i4) = mm;
+        *reinterpret_cast<float4*>(v + i4) = vv;
+        if (MASKED && mask_out)
+            *reinterpret_cast<uint32_t*>(mask_out + i4) = fr[0] | (fr[1] << 8) | (fr[2] << 16) | ((uint32_t)fr[3] << 24);
+    } else {
+        for (long long i = i4; i < numel && i < i4 + 4; ++i) {
+            const bool frozen = MASKED ? cga_frozen(p[i], __ldg(rowstat + i / cols), n_levels, kmin, kmax, lo_thr, hi_thr) : false;
+            float pv = p[i], mv = m[i], vv = v[i];
+            adamw_elem(pv, grad[i], mv, vv, a, frozen);
+            p[i] = pv; m[i] = mv; v[i] = vv;
+            if (MASKED && mask_out) mask_out[i] = frozen;
+        }
+    }
+}
+
+}  // namespace
+
+static int cga_prepass(const float* w, int rows, int cols, int bits, float* rowstat, int* kminmax, cudaStream_t st) {
+    cga_init_kernel<<<1, 1, 0, st>>>(kminmax);
+    cga_rowstat_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w, rows, cols, (float)(1 << (bits - 1)), rowstat, kminmax);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ofq_cga_mask(const float* w, int rows, int cols, int bits, double boundary_range, uint8_t* mask,
+                            float* rowstat, int* kminmax, void* stream) {
+    OFQ_REQUIRE(w && mask && rowstat && kminmax && rows > 0 && cols > 0 && bits >= 2 && bits <= 7, "ofq_cga_mask: bad argument");
+    OFQ_CHECK_ARCH();
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = cga_prepass(w, rows, cols, bits, rowstat, kminmax, st);
+    if (rc) return rc;
+    const long long numel = (long long)rows * cols;
+    cga_mask_kernel<<<(unsigned)((numel + 255) / 256), 256, 0, st>>>(
+        w, numel, cols, (float)(1 << (bits - 1)), rowstat, kminmax, (float)(0.5 - boundary_range),
+        (float)(0.5 + boundary_range), mask);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ofq_cga_adamw(float* p, const float* grad, float* exp_avg, float* exp_avg_sq, long long numel,
+                             int rows, int cols, int step, double lr, double beta1, double beta2, double eps,
+                             double weight_decay, int bits, double boundary_range, float* rowstat, int* kminmax,
+                             uint8_t* mask_out, void* stream) {
+    OFQ_REQUIRE(p && grad && exp_avg && exp_avg_sq && numel > 0 && step >= 1, "ofq_cga_adamw: bad argument");
+    OFQ_REQUIRE((uintptr_t)p % 16 == 0 && (uintptr_t)grad % 16 == 0 && (uintptr_t)exp_avg % 16 == 0 &&
+                (uintptr_t)exp_avg_sq % 16 == 0, "ofq_cga_adamw: tensors must be 16-byte aligned");
+    OFQ_CHECK_ARCH();
+    cudaStream_t st = (cudaStream_t)stream;
+    AdamScalars a;
+    a.decay = (float)(1.0 - lr * weight_decay);
+    a.one_m_b1 = (float)(1.0 - beta1);
+    a.beta2 = (float)beta2;
+    a.one_m_b2 = (float)(1.0 - beta2);
+    a.step_size = (float)(lr / (1.0 - std::pow(beta1, (double)step)));
+    a.bc2_sqrt = (float)std::sqrt(1.0 - std::pow(beta2, (double)step));
+    a.eps = (float)eps;
+    const unsigned grid = (unsigned)((numel + 1023) / 1024);
+    if (bits > 0) {
+        OFQ_REQUIRE(rows > 0 && cols > 0 && (long long)rows * cols == numel && rowstat && kminmax && bits >= 2 && bits <= 7,
+                    "ofq_cga_adamw: masked update needs a 2-D weight (rows*cols == numel), rowstat and kminmax scratch");
+        OFQ_REQUIRE(!mask_out || (uintptr_t)mask_out % 4 == 0, "ofq_cga_adamw: mask_out alignment");
+        int rc = cga_prepass(p, rows, cols, bits, rowstat, kminmax, st);
+        if (rc) return rc;
+        cga_adamw_kernel<true><<<grid, 256, 0, st>>>(p, grad, exp_avg, exp_avg_sq, numel, cols, (float)(1 << (bits - 1)),
+                                                     rowstat, kminmax, (float)(0.5 - boundary_range),
+                                                     (float)(0.5 + boundary_range), a, mask_out);
+    } else {
+        cga_adamw_kernel<false><<<grid, 256, 0, st>>>(p, grad, exp_avg, exp_avg_sq, numel, 1, 1.f, nullptr, nullptr, 0.f,
+                                                      0.f, a, nullptr);
+    }
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}

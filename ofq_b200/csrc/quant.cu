@@ -1,0 +1,644 @@
+// Quantizer kernels of the OFQ hot path (HBM-bound byte/float work, sm_100a):
+//   K1 StatsQ codes, K2 LSQ codes, LSQ backward (STE mask + scale / shift gradients).
+// Every arithmetic step that decides an integer code uses explicit round-to-nearest intrinsics
+// (__fdiv_rn / __fmul_rn / __fsub_rn / __fadd_rn, rintf) so that nvcc cannot contract it into FMAs:
+// codes must be bit-identical to the reference's fp32 op sequence.
+#include "host_util.h"
+#include "ofq_b200.h"
+#include <climits>
+#include <cstdint>
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------- K1 StatsQ
+// One warp per weight row. statsq.py:137-147.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+statsq_codes_kernel(const float* __restrict__ w, int rows, int cols, long long ldw, float n_levels,
+                    int8_t* __restrict__ codes, long long ldq, float* __restrict__ colscale,
+                    float* __restrict__ sf_out, const float* __restrict__ aft, const float* __restrict__ bias,
+                    float* __restrict__ colterm, int* __restrict__ kminmax) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kWarpsPerBlock + warp;
+    if (row >= rows) return;
+    const float* wr = w + (long long)row * ldw;
+    double acc = 0.0;
+    for (int c = lane; c < cols; c += 32) acc += (double)fabsf(__ldg(wr + c));
+    acc = warp_sum(acc);
+    const float mean = __fdiv_rn((float)acc, (float)cols);   // torch.mean = sum / numel
+    const float sf = __fmul_rn(2.0f, mean);
+    const float upper = __fsub_rn(1.0f, 1e-6f);              // (clip_val / 2) - 1e-6 in fp32
+    float dot = 0.f;
+    int kmin = INT_MAX, kmax = INT_MIN;
+    int8_t* qr = codes + (long long)row * ldq;
+    for (int c = lane; c < cols; c += 32) {
+        float v = __fdiv_rn(__ldg(wr + c), sf);
+        v = fminf(fmaxf(v, -1.0f), upper);
+        const float k = rintf(__fsub_rn(__fmul_rn(v, n_levels), 0.5f));
+        const int ki = (int)k;
+        const int code = 2 * ki + 1;
+        qr[c] = (int8_t)code;
+        if (aft) dot = fmaf(__ldg(aft + c), (float)code, dot);
+        kmin = min(kmin, ki);
+        kmax = max(kmax, ki);
+    }
+    const float cs = __fdiv_rn(sf, 2.0f * n_levels);
+    if (colterm) {
+        dot = warp_sum(dot);
+        if (lane == 0) colterm[row] = cs * dot + (bias ? __ldg(bias + row) : 0.f);
+    }
+    if (kminmax) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+            kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+        }
+        if (lane == 0) {
+            atomicMin(kminmax, kmin);
+            atomicMax(kminmax + 1, kmax);
+        }
+    }
+    if (lane == 0) {
+        colscale[row] = cs;
+        if (sf_out) sf_out[row] = sf;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- LSQ scale
+__global__ void lsq_effective_scale_kernel(const float* __restrict__ alpha, int n, float g,
+                                           float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a = alpha[i];
+    const float ac = a > 1e-5f ? a : 1e-5f;          // clip(): where(x > eps, x, eps)
+    const float ag = __fmul_rn(ac, g);               // grad_scale(): (y - y*g) + y*g
+    out[i] = __fadd_rn(__fsub_rn(ac, ag), ag);
+}
+
+// ------------------------------------------------------------------------------------------- K2 LSQ codes
+__device__ __forceinline__ int lsq_code(float x, float b4, float s, float qlo, float qhi) {
+    float v = __fdiv_rn(__fadd_rn(x, b4), s);
+    v = fminf(fmaxf(v, qlo), qhi);
+    return (int)rintf(v);
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+lsq_quant_kernel(const float* __restrict__ x, long long rows, int cols, long long ldx,
+                 const float* __restrict__ b4, const float* __restrict__ s_eff, int scale_mode, int period,
+                 int nseg, int seg_len, float qlo, float qhi, int8_t* __restrict__ codes, long long ldq) {
+    constexpr int W = VEC ? 4 : 1;
+    const int cw = cols / W;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * cw) return;
+    const long long row = idx / cw;
+    const int col = (int)(idx - row * cw) * W;
+    float xv[W], bv[W], sv[W];
+    if (VEC) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(x + row * ldx + col));
+        xv[0] = t.x; xv[1 % W] = t.y; xv[2 % W] = t.z; xv[3 % W] = t.w;
+        const float4 b = __ldg(reinterpret_cast<const float4*>(b4 + col));
+        bv[0] = b.x; bv[1 % W] = b.y; bv[2 % W] = b.z; bv[3 % W] = b.w;
+    } else {
+        xv[0] = __ldg(x + row * ldx + col);
+        bv[0] = __ldg(b4 + col);
+    }
+    if (scale_mode == OFQ_SCALE_PER_ROW) {
+        const float s = __ldg(s_eff + (row % period) * nseg + col / seg_len);
+#pragma unroll
+        for (int e = 0; e < W; ++e) sv[e] = s;
+    } else {
+        if (VEC) {
+            const float4 s = __ldg(reinterpret_cast<const float4*>(s_eff + col));
+            sv[0] = s.x; sv[1 % W] = s.y; sv[2 % W] = s.z; sv[3 % W] = s.w;
+        } else {
+            sv[0] = __ldg(s_eff + col);
+        }
+    }
+    int q[W];
+#pragma unroll
+    for (int e = 0; e < W; ++e) q[e] = lsq_code(xv[e], bv[e], sv[e], qlo, qhi);
+    if (VEC) {
+        const uint32_t packed = (uint32_t)(q[0] & 0xff) | ((uint32_t)(q[1 % W] & 0xff) << 8) |
+                                ((uint32_t)(q[2 % W] & 0xff) << 16) | ((uint32_t)(q[3 % W] & 0xff) << 24);
+        *reinterpret_cast<uint32_t*>(codes + row * ldq + col) = packed;
+    } else {
+        codes[row * ldq + col] = (int8_t)q[0];
+    }
+}
+
+// ------------------------------------------------------------------------------------------- LSQ backward
+// Block = 8 warps, a contiguous range of rows; a warp walks its rows, lanes own fixed float4 columns of the
+// current 512-column chunk so that column partial sums stay in registers; per-(row,segment) partial sums
+// are reduced with shuffles. workspace = rowpart[rows*nseg] | colpart[nblk][3][cols].
+constexpr int kBwdChunk = 512;   // columns per register-resident chunk (4 float4 per lane)
+constexpr int kBwdRowsPerBlock = 64;
+
+__host__ __device__ inline long long lsq_bwd_nblk(long long rows) {
+    return (rows + kBwdRowsPerBlock - 1) / kBwdRowsPerBlock;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+lsq_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
+               long long rows, int cols, const float* __restrict__ b4, const float* __restrict__ s_eff,
+               int scale_mode, int period, int nseg, int seg_len, float qlo, float qhi,
+               float* __restrict__ dx, long long lddx, float* __restrict__ rowpart,
+               float* __restrict__ colpart) {
+    __shared__ float col_s[3][kBwdChunk];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long r0 = (long long)blockIdx.x * kBwdRowsPerBlock;
+    const long long r1 = min(rows, r0 + kBwdRowsPerBlock);
+    float* cp = colpart + (long long)blockIdx.x * 3 * cols;
+
+    for (int cbase = 0; cbase < cols; cbase += kBwdChunk) {
+        for (int i = threadIdx.x; i < 3 * kBwdChunk; i += blockDim.x) (&col_s[0][0])[i] = 0.f;
+        __syncthreads();
+        float a_aft[4][4], a_b4[4][4], a_s[4][4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) a_aft[p][e] = a_b4[p][e] = a_s[p][e] = 0.f;
+
+        for (long long row = r0 + warp; row < r1; row += kWarpsPerBlock) {
+            const float* dyr = dy + row * lddy;
+            const float* xr = x + row * ldx;
+            float* dxr = dx + row * lddx;
+            const long long srow = (row % period) * nseg;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int pass0 = cbase + p * 128;            // warp-uniform
+                if (pass0 >= cols) break;
+                const int col = pass0 + lane * 4;
+                const bool ok = col < cols;
+                float part = 0.f;
+                int myseg = ok ? col / seg_len : -1;
+                if (ok) {
+                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(dyr + col));
+                    const float4 x4 = __ldg(reinterpret_cast<const float4*>(xr + col));
+                    const float4 b4v = __ldg(reinterpret_cast<const float4*>(b4 + col));
+                    float sv[4];
+                    if (scale_mode == OFQ_SCALE_PER_ROW) {
+                        const float s = __ldg(s_eff + srow + myseg);
+                        sv[0] = sv[1] = sv[2] = sv[3] = s;
+                    } else {
+                        const float4 s4 = __ldg(reinterpret_cast<const float4*>(s_eff + col));
+                        sv[0] = s4.x; sv[1] = s4.y; sv[2] = s4.z; sv[3] = s4.w;
+                    }
+                    const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+                    const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
+                    const float bb[4] = {b4v.x, b4v.y, b4v.z, b4v.w};
+                    float o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float v = __fdiv_rn(__fadd_rn(xx[e], bb[e]), sv[e]);
+                        const bool inside = (v >= qlo) && (v <= qhi);
+                        const float q = rintf(fminf(fmaxf(v, qlo), qhi));
+                        const float t = gg[e] * (inside ? (q - v) : q);
+                        o[e] = inside ? gg[e] : 0.f;
+                        a_aft[p][e] += gg[e];
+                        a_b4[p][e] += o[e];
+                        if (scale_mode == OFQ_SCALE_PER_ROW) part += t; else a_s[p][e] += t;
+                    }
+                    *reinterpret_cast<float4*>(dxr + col) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                if (scale_mode == OFQ_SCALE_PER_ROW) {
+                    const int pass_end = min(pass0 + 128, cols) - 1;
+                    const int seg_first = pass0 / seg_len, seg_last = pass_end / seg_len;   // warp-uniform
+                    for (int sg = seg_first; sg <= seg_last; ++sg) {
+                        const float v = warp_sum(myseg == sg ? part : 0.f);
+                        if (lane == 0) {
+                            float* dst = rowpart + row * nseg + sg;
+                            // the first pass that touches (row, sg) initialises it, later ones accumulate
+                            const bool first = (pass0 <= sg * seg_len);
+                            *dst = first ? v : (*dst + v);
+                        }
+                    }
+                }
+            }
+        }
+        // fold the 8 warps' column partials
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int lc = p * 128 + lane * 4;
+            if (cbase + lc < cols) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    atomicAdd(&col_s[0][lc + e], a_aft[p][e]);
+                    atomicAdd(&col_s[1][lc + e], a_b4[p][e]);
+                    if (scale_mode == OFQ_SCALE_PER_COL) atomicAdd(&col_s[2][lc + e], a_s[p][e]);
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < kBwdChunk; i += blockDim.x) {
+            if (cbase + i < cols) {
+                cp[0 * cols + cbase + i] = col_s[0][i];
+                cp[1 * cols + cbase + i] = col_s[1][i];
+                cp[2 * cols + cbase + i] = col_s[2][i];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void lsq_bwd_finalize_kernel(const float* __restrict__ rowpart, const float* __restrict__ colpart,
+                                        long long rows, int cols, int scale_mode, int period, int nseg, float g,
+                                        long long nblk, float* __restrict__ d_s, float* __restrict__ d_b4,
+                                        float* __restrict__ d_aft) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cols) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        for (long long b = 0; b < nblk; ++b) {
+            const float* cp = colpart + b * 3 * cols;
+            s0 += cp[i];
+            s1 += cp[cols + i];
+            s2 += cp[2 * cols + i];
+        }
+        if (d_aft) d_aft[i] = s0;
+        if (d_b4) d_b4[i] = s1;
+        if (d_s && scale_mode == OFQ_SCALE_PER_COL) d_s[i] = g * s2;
+    }
+    if (d_s && scale_mode == OFQ_SCALE_PER_ROW) {
+        const long long nscale = (long long)min((long long)period, rows) * nseg;
+        if (i < nscale) {
+            float s = 0.f;
+            const long long stride = (long long)period * nseg;
+            for (long long j = i; j < rows * nseg; j += stride) s += rowpart[j];
+            d_s[i] = g * s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- gradient prep
+// 64x64 fp32 tile -> bf16 row-major (x*cs[c]) and/or bf16 transposed (x*rs[r]); column sums; per-group row dots.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+__device__ __forceinline__ float bf16_lo_to_float(uint32_t packed) { return __uint_as_float(packed << 16); }
+__device__ __forceinline__ float bf16_hi_to_float(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
+
+__global__ void __launch_bounds__(256)
+grad_prep_kernel(const float* __restrict__ x, int R, int C, long long ldx, long long bstride_x,
+                 const float* __restrict__ cs, const float* __restrict__ rs, int rs_period, int planes,
+                 long long plane_rm, long long plane_t,
+                 uint16_t* __restrict__ out_rm, long long ld_rm, uint16_t* __restrict__ out_t, int r_pad,
+                 float* __restrict__ colsum, const float* __restrict__ u, int group,
+                 float* __restrict__ rowdot) {
+    __shared__ float tile[64][65];
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    const int t = threadIdx.x;
+    const int tc = (t & 15) * 4, tr = t >> 4;   // 16 float4 per tile row, 16 rows per pass
+    const float* xb = x + (long long)b * bstride_x;
+    float colacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + tr + 16 * i, c = c0 + tc;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (r < R && c < C) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(xb + (long long)r * ldx + c));
+            v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        }
+        if (out_rm && r < R && c < C) {
+            float s[4] = {1.f, 1.f, 1.f, 1.f};
+            if (cs) {
+                const float4 f = __ldg(reinterpret_cast<const float4*>(cs + c));
+                s[0] = f.x; s[1] = f.y; s[2] = f.z; s[3] = f.w;
+            }
+            float sv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) sv[e] = v[e] * s[e];
+            uint2 pk;
+            pk.x = pack_bf16x2(sv[0], sv[1]);
+            pk.y = pack_bf16x2(sv[2], sv[3]);
+            uint16_t* dst = out_rm + ((long long)b * R + r) * ld_rm + c;
+            *reinterpret_cast<uint2*>(dst) = pk;
+            if (planes == 2) {
+                uint2 lo;
+                lo.x = pack_bf16x2(sv[0] - bf16_lo_to_float(pk.x), sv[1] - bf16_hi_to_float(pk.x));
+                lo.y = pack_bf16x2(sv[2] - bf16_lo_to_float(pk.y), sv[3] - bf16_hi_to_float(pk.y));
+                *reinterpret_cast<uint2*>(dst + plane_rm) = lo;
+            }
+        }
+        if (rowdot) {
+            float d = 0.f;
+            if (r < R && c < C) {
+                const float4 f = __ldg(reinterpret_cast<const float4*>(u + c));
+                d = v[0] * f.x + v[1] * f.y + v[2] * f.z + v[3] * f.w;
+            }
+            // threads sharing a row and a group are consecutive lanes: 16 (group 64), 8 (group 32) or 4 (group 16)
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            d += __shfl_xor_sync(0xffffffffu, d, 2);
+            if (group >= 32) d += __shfl_xor_sync(0xffffffffu, d, 4);
+            if (group == 64) d += __shfl_xor_sync(0xffffffffu, d, 8);
+            const int lanes = group / 4;
+            if (((t & 15) % lanes) == 0 && r < R && c < C)
+                rowdot[((long long)b * (C / group) + c / group) * R + r] = d;
+        }
+        const float rsv = (out_t && rs && r < R) ? __ldg(rs + (r % rs_period)) : 1.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            colacc[e] += v[e];
+            tile[tr + 16 * i][tc + e] = v[e] * rsv;
+        }
+    }
+    if (colsum) {
+        // reduce the 16 row-slots that share a column quad: lanes t and t^16 (same warp), then 8 warps via smem
+#pragma unroll
+        for (int e = 0; e < 4; ++e) colacc[e] += __shfl_xor_sync(0xffffffffu, colacc[e], 16);
+        const int warp = t >> 5;
+        __shared__ float cpart[8][64];
+        if ((t & 31) < 16) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) cpart[warp][tc + e] = colacc[e];
+        }
+        __syncthreads();
+        if (t < 64 && c0 + t < C) {
+            float s = 0.f;
+#pragma unroll
+            for (int w2 = 0; w2 < 8; ++w2) s += cpart[w2][t];
+            atomicAdd(colsum + c0 + t, s);
+        }
+    }
+    if (out_t) {
+        __syncthreads();
+        // write transposed: each thread emits 8 consecutive r (16 bytes) of one column
+        uint16_t* ob = out_t + (long long)b * C * r_pad;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int item = t + 256 * i;          // 64 columns x 8 row-octets
+            const int c = item >> 3, ro = (item & 7) * 8;
+            if (c0 + c < C && r0 + ro < r_pad) {
+                uint4 pk;
+                pk.x = pack_bf16x2(tile[ro + 0][c], tile[ro + 1][c]);
+                pk.y = pack_bf16x2(tile[ro + 2][c], tile[ro + 3][c]);
+                pk.z = pack_bf16x2(tile[ro + 4][c], tile[ro + 5][c]);
+                pk.w = pack_bf16x2(tile[ro + 6][c], tile[ro + 7][c]);
+                uint16_t* dst = ob + (long long)(c0 + c) * r_pad + r0 + ro;
+                *reinterpret_cast<uint4*>(dst) = pk;
+                if (planes == 2) {
+                    uint4 lo;
+                    lo.x = pack_bf16x2(tile[ro + 0][c] - bf16_lo_to_float(pk.x), tile[ro + 1][c] - bf16_hi_to_float(pk.x));
+                    lo.y = pack_bf16x2(tile[ro + 2][c] - bf16_lo_to_float(pk.y), tile[ro + 3][c] - bf16_hi_to_float(pk.y));
+                    lo.z = pack_bf16x2(tile[ro + 4][c] - bf16_lo_to_float(pk.z), tile[ro + 5][c] - bf16_hi_to_float(pk.z));
+                    lo.w = pack_bf16x2(tile[ro + 6][c] - bf16_lo_to_float(pk.w), tile[ro + 7][c] - bf16_hi_to_float(pk.w));
+                    *reinterpret_cast<uint4*>(dst + plane_t) = lo;
+                }
+            }
+        }
+    }
+}
+
+// int8 codes -> bf16 (exact), optional per-batch transpose, 64x64 tiles.
+template <bool TRANSPOSE, typename OutT>
+__global__ void __launch_bounds__(256)
+codes_convert_kernel(const int8_t* __restrict__ codes, int R, int C, long long ld, long long bstride,
+                     OutT* __restrict__ out, long long ld_out, long long bstride_out) {
+    __shared__ int8_t tile[64][68];
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    const int t = threadIdx.x;
+    const int8_t* cb = codes + (long long)b * bstride;
+    {   // 64 rows x 16 words
+        const int r = t >> 2, w4 = (t & 3) * 16;
+        for (int j = 0; j < 16; j += 4) {
+            const int c = c0 + w4 + j;
+            uint32_t word = 0;
+            if (r0 + r < R && c < C) word = *reinterpret_cast<const uint32_t*>(cb + (long long)(r0 + r) * ld + c);
+            *reinterpret_cast<uint32_t*>(&tile[r][w4 + j]) = word;
+        }
+    }
+    __syncthreads();
+    OutT* ob = out + (long long)b * bstride_out;
+    if (TRANSPOSE) {
+        // out[c][r]: thread -> (column c, 16 consecutive r)
+        const int c = t >> 2, ro = (t & 3) * 16;
+        if (c0 + c < C) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 8) {
+                const int r = r0 + ro + j;
+                if (r >= ld_out) continue;
+                if (sizeof(OutT) == 2) {
+                    uint4 pk;
+                    pk.x = pack_bf16x2((float)tile[ro + j + 0][c], (float)tile[ro + j + 1][c]);
+                    pk.y = pack_bf16x2((float)tile[ro + j + 2][c], (float)tile[ro + j + 3][c]);
+                    pk.z = pack_bf16x2((float)tile[ro + j + 4][c], (float)tile[ro + j + 5][c]);
+                    pk.w = pack_bf16x2((float)tile[ro + j + 6][c], (float)tile[ro + j + 7][c]);
+                    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ob) + (long long)(c0 + c) * ld_out + r) = pk;
+                } else {
+                    uint2 pk;
+                    uint8_t by[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) by[e] = (uint8_t)tile[ro + j + e][c];
+                    pk.x = by[0] | (by[1] << 8) | (by[2] << 16) | ((uint32_t)by[3] << 24);
+                    pk.y = by[4] | (by[5] << 8) | (by[6] << 16) | ((uint32_t)by[7] << 24);
+                    *reinterpret_cast<uint2*>(reinterpret_cast<int8_t*>(ob) + (long long)(c0 + c) * ld_out + r) = pk;
+                }
+            }
+        }
+    } else {
+        const int r = t >> 2, co = (t & 3) * 16;
+        if (r0 + r < R) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 8) {
+                const int c = c0 + co + j;
+                if (c >= C) continue;
+                uint4 pk;
+                pk.x = pack_bf16x2((float)tile[r][co + j + 0], (float)tile[r][co + j + 1]);
+                pk.y = pack_bf16x2((float)tile[r][co + j + 2], (float)tile[r][co + j + 3]);
+                pk.z = pack_bf16x2((float)tile[r][co + j + 4], (float)tile[r][co + j + 5]);
+                pk.w = pack_bf16x2((float)tile[r][co + j + 6], (float)tile[r][co + j + 7]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ob) + (long long)(r0 + r) * ld_out + c) = pk;
+            }
+        }
+    }
+}
+
+// out[row][seg] = sum_{c in seg} u[c] * codes[row][c]; one warp per (row, segment).
+__global__ void __launch_bounds__(256)
+codes_rowdot_kernel(const int8_t* __restrict__ codes, long long rows, int cols, long long ld, int nseg,
+                    const float* __restrict__ u, float* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * 8 + warp;
+    if (item >= rows * nseg) return;
+    const long long row = item / nseg;
+    const int seg = (int)(item - row * nseg);
+    const int seg_len = cols / nseg;
+    const int8_t* cr = codes + row * ld + (long long)seg * seg_len;
+    const float* us = u + (long long)seg * seg_len;
+    float acc = 0.f;
+    for (int c = lane * 4; c < seg_len; c += 128) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(cr + c);
+        const float4 uu = __ldg(reinterpret_cast<const float4*>(us + c));
+        acc = fmaf((float)(int8_t)(w & 0xff), uu.x, acc);
+        acc = fmaf((float)(int8_t)((w >> 8) & 0xff), uu.y, acc);
+        acc = fmaf((float)(int8_t)((w >> 16) & 0xff), uu.z, acc);
+        acc = fmaf((float)(int8_t)(w >> 24), uu.w, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[item] = acc;
+}
+
+}  // namespace
+
+// =============================================================================================== C-ABI
+extern "C" int ofq_codes_rowdot(const int8_t* codes, long long rows, int cols, long long ld, int nseg,
+                                const float* u, float* out, void* stream) {
+    OFQ_REQUIRE(codes && u && out && rows > 0 && cols > 0 && nseg > 0 && cols % nseg == 0, "ofq_codes_rowdot: bad argument");
+    OFQ_REQUIRE((cols / nseg) % 4 == 0 && ld % 4 == 0 && (uintptr_t)codes % 4 == 0 && (uintptr_t)u % 16 == 0,
+                "ofq_codes_rowdot: segment length and pitch must be multiples of 4");
+    OFQ_CHECK_ARCH();
+    const long long items = rows * nseg;
+    codes_rowdot_kernel<<<(unsigned)((items + 7) / 8), 256, 0, (cudaStream_t)stream>>>(codes, rows, cols, ld, nseg, u, out);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ofq_statsq_codes(const float* w, int rows, int cols, long long ldw, int bits, int8_t* codes,
+                                long long ldq, float* colscale, float* sf, const float* aft, const float* bias,
+                                float* colterm, int* kminmax, void* stream) {
+    OFQ_REQUIRE(w && codes && colscale, "ofq_statsq_codes: null pointer");
+    OFQ_REQUIRE(rows > 0 && cols > 0 && bits >= 2 && bits <= 7, "ofq_statsq_codes: bad shape or bits (2..7)");
+    OFQ_CHECK_ARCH();
+    const float n = (float)(1 << (bits - 1));
+    const int grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    statsq_codes_kernel<<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        w, rows, cols, ldw, n, codes, ldq, colscale, sf, aft, bias, colterm, kminmax);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ofq_lsq_effective_scale(const float* alpha, int n, float g, float* out, void* stream) {
+    OFQ_REQUIRE(alpha && out && n > 0, "ofq_lsq_effective_scale: bad argument");
+    OFQ_CHECK_ARCH();
+    lsq_effective_scale_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(alpha, n, g, out);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ofq_lsq_quant(const float* x, long long rows, int cols, long long ldx, const float* b4,
+                             const float* s_eff, int scale_mode, int period, int nseg, int qlo, int qhi,
+                             int8_t* codes, long long ldq, void* stream) {
+    OFQ_REQUIRE(x && b4 && s_eff && codes, "ofq_lsq_quant: null pointer");
+    OFQ_REQUIRE(rows > 0 && cols > 0 && nseg > 0 && cols % nseg == 0 && period > 0, "ofq_lsq_quant: bad shape");
+    OFQ_REQUIRE(qlo >= -128 && qhi <= 127 && qlo < qhi, "ofq_lsq_quant: codes must fit int8");
+    OFQ_CHECK_ARCH();
+    const int seg_len = cols / nseg;
+    const bool vec = (cols % 4 == 0) && (seg_len % 4 == 0) && (ldx % 4 == 0) && (ldq % 4 == 0) &&
+                     ((uintptr_t)x % 16 == 0) && ((uintptr_t)b4 % 16 == 0) && ((uintptr_t)s_eff % 16 == 0) &&
+                     ((uintptr_t)codes % 4 == 0);
+    const long long n = rows * (cols / (vec ? 4 : 1));
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (vec)
+        lsq_quant_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, b4, s_eff, scale_mode,
+                                                                      period, nseg, seg_len, (float)qlo, (float)qhi, codes, ldq);
+    else
+        lsq_quant_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, b4, s_eff, scale_mode,
+                                                                       period, nseg, seg_len, (float)qlo, (float)qhi, codes, ldq);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" long long ofq_lsq_bwd_workspace(long long rows, int cols, int nseg) {
+    return rows * nseg + lsq_bwd_nblk(rows) * 3 * cols;
+}
+
+extern "C" int ofq_lsq_bwd(const float* dy, long long lddy, const float* x, long long ldx, long long rows,
+                           int cols, const float* b4, const float* s_eff, int scale_mode, int period, int nseg,
+                           int qlo, int qhi, float* dx, long long lddx, float* workspace, void* stream) {
+    OFQ_REQUIRE(dy && x && b4 && s_eff && dx && workspace, "ofq_lsq_bwd: null pointer");
+    OFQ_REQUIRE(rows > 0 && cols > 0 && nseg > 0 && cols % nseg == 0 && period > 0, "ofq_lsq_bwd: bad shape");
+    const int seg_len = cols / nseg;
+    OFQ_REQUIRE(cols % 4 == 0 && seg_len % 4 == 0 && lddy % 4 == 0 && ldx % 4 == 0 && lddx % 4 == 0,
+                "ofq_lsq_bwd: columns, segment length and row strides must be multiples of 4");
+    OFQ_REQUIRE((uintptr_t)dy % 16 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)dx % 16 == 0 &&
+                (uintptr_t)b4 % 16 == 0 && (uintptr_t)s_eff % 16 == 0, "ofq_lsq_bwd: pointers must be 16-byte aligned");
+    OFQ_CHECK_ARCH();
+    float* rowpart = workspace;
+    float* colpart = workspace + rows * nseg;
+    lsq_bwd_kernel<<<(unsigned)lsq_bwd_nblk(rows), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        dy, lddy, x, ldx, rows, cols, b4, s_eff, scale_mode, period, nseg, seg_len, (float)qlo, (float)qhi, dx,
+        lddx, rowpart, colpart);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ofq_lsq_bwd_finalize(const float* workspace, long long rows, int cols, int scale_mode, int period,
+                                    int nseg, float g, float* d_s, float* d_b4, float* d_aft, void* stream) {
+    OFQ_REQUIRE(workspace && rows > 0 && cols > 0, "ofq_lsq_bwd_finalize: bad argument");
+    OFQ_CHECK_ARCH();
+    const float* rowpart = workspace;
+    const float* colpart = workspace + rows * nseg;
+    long long n = cols;
+    if (scale_mode == OFQ_SCALE_PER_ROW) n = n > (long long)period * nseg ? n : (long long)period * nseg;
+    lsq_bwd_finalize_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        rowpart, colpart, rows, cols, scale_mode, period, nseg, g, lsq_bwd_nblk(rows), d_s, d_b4, d_aft);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ofq_grad_prep(const float* x, int nb, int R, int C, long long ldx, long long bstride_x,
+                             const float* cs, const float* rs, int rs_period, int planes, void* out_rm,
+                             long long ld_rm, void* out_t, int r_pad, float* colsum, const float* u, int group,
+                             float* rowdot, void* stream) {
+    OFQ_REQUIRE(x && nb > 0 && R > 0 && C > 0, "ofq_grad_prep: bad argument");
+    OFQ_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && bstride_x % 4 == 0 && (uintptr_t)x % 16 == 0,
+                "ofq_grad_prep: C, ldx must be multiples of 4 and x 16-byte aligned");
+    OFQ_REQUIRE(!out_rm || (ld_rm % 4 == 0 && (uintptr_t)out_rm % 8 == 0), "ofq_grad_prep: out_rm alignment");
+    OFQ_REQUIRE(!out_t || (r_pad % 8 == 0 && r_pad >= R && (uintptr_t)out_t % 16 == 0), "ofq_grad_prep: out_t pitch must be a multiple of 8 and >= R");
+    OFQ_REQUIRE(!rowdot || (u && (group == 16 || group == 32 || group == 64) && C % group == 0), "ofq_grad_prep: rowdot needs u and group 16, 32 or 64");
+    OFQ_REQUIRE(planes == 1 || planes == 2, "ofq_grad_prep: planes must be 1 or 2");
+    OFQ_REQUIRE(!cs || (uintptr_t)cs % 16 == 0, "ofq_grad_prep: cs alignment");
+    OFQ_CHECK_ARCH();
+    if (rs_period <= 0) rs_period = 0x7fffffff;
+    dim3 grid((C + 63) / 64, (R + 63) / 64, nb);
+    grad_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, R, C, ldx, bstride_x, cs, rs, rs_period, planes,
+                                                             (long long)nb * R * ld_rm, (long long)nb * C * r_pad,
+                                                             (uint16_t*)out_rm, ld_rm, (uint16_t*)out_t, r_pad,
+                                                             colsum, u, group, rowdot);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ofq_codes_to_bf16(const int8_t* codes, int nb, int R, int C, long long ld, long long bstride,
+                                 void* out, long long ld_out, long long bstride_out, int transpose, void* stream) {
+    OFQ_REQUIRE(codes && out && nb > 0 && R > 0 && C > 0, "ofq_codes_to_bf16: bad argument");
+    OFQ_REQUIRE(C % 4 == 0 && ld % 4 == 0 && bstride % 4 == 0 && (uintptr_t)codes % 4 == 0, "ofq_codes_to_bf16: input alignment");
+    OFQ_REQUIRE(ld_out % 8 == 0 && bstride_out % 8 == 0 && (uintptr_t)out % 16 == 0, "ofq_codes_to_bf16: output alignment");
+    OFQ_REQUIRE(transpose ? ld_out >= R : (ld_out >= C && C % 8 == 0), "ofq_codes_to_bf16: output pitch too small");
+    OFQ_CHECK_ARCH();
+    dim3 grid((C + 63) / 64, (R + 63) / 64, nb);
+    if (transpose)
+        codes_convert_kernel<true, uint16_t><<<grid, 256, 0, (cudaStream_t)stream>>>(codes, R, C, ld, bstride, (uint16_t*)out, ld_out, bstride_out);
+    else
+        codes_convert_kernel<false, uint16_t><<<grid, 256, 0, (cudaStream_t)stream>>>(codes, R, C, ld, bstride, (uint16_t*)out, ld_out, bstride_out);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ofq_codes_transpose(const int8_t* codes, int nb, int R, int C, long long ld, long long bstride,
+                                   int8_t* out, long long ld_out, long long bstride_out, void* stream) {
+    OFQ_REQUIRE(codes && out && nb > 0 && R > 0 && C > 0, "ofq_codes_transpose: bad argument");
+    OFQ_REQUIRE(C % 4 == 0 && ld % 4 == 0 && bstride % 4 == 0 && (uintptr_t)codes % 4 == 0, "ofq_codes_transpose: input alignment");
+    OFQ_REQUIRE(ld_out % 16 == 0 && ld_out >= R && bstride_out % 16 == 0 && (uintptr_t)out % 16 == 0, "ofq_codes_transpose: output pitch must be a multiple of 16 and >= R");
+    OFQ_CHECK_ARCH();
+    dim3 grid((C + 63) / 64, (R + 63) / 64, nb);
+    codes_convert_kernel<true, int8_t><<<grid, 256, 0, (cudaStream_t)stream>>>(codes, R, C, ld, bstride, out, ld_out, bstride_out);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,230 @@
+// Softmax + unsigned LSQ quantization of attention probabilities, forward and backward
+// (reference attention.py:96-99 / 212-216, swin_attention_and_mlp.py:201-227). One warp owns one query row
+// (N <= 256 keys: DeiT 197/198, Swin 49), values live in registers, reductions are warp shuffles.
+#include "host_util.h"
+#include "ofq_b200.h"
+#include <cstdint>
+
+namespace {
+
+constexpr int kMaxPer = 8;  // keys per lane -> N <= 256
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float wmax(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint16_t to_bf16(float v) { return (uint16_t)(pack_bf16x2(v, 0.f) & 0xffff); }
+
+__global__ void __launch_bounds__(256)
+softmax_quant_kernel(const float* __restrict__ S, int nz, int N, long long ld, int H,
+                     const float* __restrict__ bias, const float* __restrict__ mask, int nW,
+                     const float* __restrict__ s_eff, float qhi, float* __restrict__ P,
+                     int8_t* __restrict__ codes, long long ldq, float* __restrict__ rowsum) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long gr = (long long)blockIdx.x * 8 + warp;   // global row = z * N + n
+    if (gr >= (long long)nz * N) return;
+    const int z = (int)(gr / N), n = (int)(gr - (long long)z * N);
+    const int h = z % H, b = z / H;
+    const float* srow = S + ((long long)z * N + n) * ld;
+    const float* brow = bias ? bias + ((long long)h * N + n) * N : nullptr;
+    const float* mrow = mask ? mask + ((long long)(b % nW) * N + n) * N : nullptr;
+    float v[kMaxPer];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kMaxPer; ++i) {
+        const int d = lane + 32 * i;
+        float t = -INFINITY;
+        if (d < N) {
+            t = __ldg(srow + d);
+            if (brow) t += __ldg(brow + d);
+            if (mrow) t += __ldg(mrow + d);
+        }
+        v[i] = t;
+        m = fmaxf(m, t);
+    }
+    m = wmax(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxPer; ++i) {
+        const int d = lane + 32 * i;
+        v[i] = d < N ? expf(v[i] - m) : 0.f;
+        sum += v[i];
+    }
+    sum = wsum(sum);
+    const float s = __ldg(s_eff + n);
+    float csum = 0.f;
+    float* prow = P ? P + ((long long)z * N + n) * ld : nullptr;
+    int8_t* crow = codes + ((long long)z * N + n) * ldq;
+#pragma unroll
+    for (int i = 0; i < kMaxPer; ++i) {
+        const int d = lane + 32 * i;
+        if (d < N) {
+            const float p = __fdiv_rn(v[i], sum);
+            const float q = rintf(fminf(fmaxf(__fdiv_rn(p, s), 0.f), qhi));
+            if (prow) prow[d] = p;
+            crow[d] = (int8_t)(int)q;
+            csum += q;
+        } else if (d < ldq) {
+            crow[d] = 0;
+        }
+    }
+    csum = wsum(csum);
+    if (lane == 0 && rowsum) rowsum[(long long)z * N + n] = s * csum;
+}
+
+// Backward: block = 32 query rows of one (b, h); 8 warps x 4 rows.
+__global__ void __launch_bounds__(256)
+softmax_quant_bwd_kernel(const float* __restrict__ dPq, const float* __restrict__ P, int N, long long ld, int H,
+                         const float* __restrict__ s_eff, float qhi, float alpha, float g_s,
+                         const float* __restrict__ ca, int ca_per_head, const float* __restrict__ rb, int planes,
+                         uint16_t* __restrict__ out_a, uint16_t* __restrict__ out_bt, long long ldo,
+                         float* __restrict__ colsum, float* __restrict__ d_s, float* __restrict__ dS32) {
+    extern __shared__ float tile[];           // [32][N + 1] dS * rb[n] for the transposed output
+    __shared__ float csum_s[kMaxPer * 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int z = blockIdx.y, h = z % H, b = z / H;
+    // output slab of (b, plane p, h): index ((b * planes + p) * H + h); plane stride = H slabs
+    const long long zo = ((long long)b * planes * H + h) * N;
+    const long long plane = (long long)H * N * ldo;
+    const int n0 = blockIdx.x * 32;
+    const int pitch = N + 1;
+    for (int i = threadIdx.x; i < kMaxPer * 32; i += blockDim.x) csum_s[i] = 0.f;
+    __syncthreads();
+    const float* cav = ca ? (ca_per_head ? ca + (long long)h * N : ca) : nullptr;
+    float colacc[kMaxPer];
+#pragma unroll
+    for (int i = 0; i < kMaxPer; ++i) colacc[i] = 0.f;
+
+    for (int rr = 0; rr < 4; ++rr) {
+        const int ln = warp * 4 + rr;
+        const int n = n0 + ln;
+        if (n >= N) {                                   // warp-uniform; keep the tile defined
+            for (int d = lane; d < N; d += 32) tile[ln * pitch + d] = 0.f;
+            continue;
+        }
+        const long long ro = ((long long)z * N + n) * ld;
+        const float s = __ldg(s_eff + n);
+        float p[kMaxPer], dp[kMaxPer];
+        float dot = 0.f, dsp = 0.f;
+#pragma unroll
+        for (int i = 0; i < kMaxPer; ++i) {
+            const int d = lane + 32 * i;
+            p[i] = 0.f; dp[i] = 0.f;
+            if (d < N) {
+                p[i] = __ldg(P + ro + d);
+                const float gq = __ldg(dPq + ro + d);
+                const float v = __fdiv_rn(p[i], s);
+                const bool inside = v <= qhi;           // v >= 0 always holds for probabilities
+                const float q = rintf(fminf(v, qhi));
+                dsp += gq * (inside ? (q - v) : q);
+                dp[i] = inside ? gq : 0.f;
+                dot += p[i] * dp[i];
+            }
+        }
+        dot = wsum(dot);
+        dsp = wsum(dsp);
+        if (lane == 0 && d_s) atomicAdd(d_s + n, g_s * dsp);
+        const float rbv = rb ? __ldg(rb + n) : 1.f;
+#pragma unroll
+        for (int i = 0; i < kMaxPer; ++i) {
+            const int d = lane + 32 * i;
+            if (d < N) {
+                const float ds_raw = p[i] * (dp[i] - dot);   // gradient w.r.t. the (scaled) logits / additive bias
+                const float ds = alpha * ds_raw;             // gradient w.r.t. the un-scaled q.k product
+                colacc[i] += ds;
+                if (out_a) {
+                    const float va = ds * (cav ? __ldg(cav + d) : 1.f);
+                    const uint16_t hi16 = to_bf16(va);
+                    uint16_t* dst = out_a + (zo + n) * ldo + d;
+                    *dst = hi16;
+                    if (planes == 2) dst[plane] = to_bf16(va - __uint_as_float((uint32_t)hi16 << 16));
+                }
+                if (dS32) dS32[ro + d] = ds_raw;
+                tile[ln * pitch + d] = ds * rbv;
+            } else if (out_a && d < ldo) {
+                out_a[(zo + n) * ldo + d] = 0;
+                if (planes == 2) out_a[(zo + n) * ldo + d + plane] = 0;
+            }
+        }
+    }
+    if (colsum) {
+#pragma unroll
+        for (int i = 0; i < kMaxPer; ++i)
+            if (lane + 32 * i < N) atomicAdd(&csum_s[lane + 32 * i], colacc[i]);
+    }
+    __syncthreads();
+    if (colsum)
+        for (int d = threadIdx.x; d < N; d += blockDim.x) atomicAdd(colsum + (long long)z * N + d, csum_s[d]);
+    if (out_bt) {
+        // out_bt[z][d][n0 .. n0+31]: 4 threads per key row d, 8 consecutive n each (16 bytes)
+        for (int item = threadIdx.x; item < N * 4; item += blockDim.x) {
+            const int d = item >> 2, no = (item & 3) * 8;
+            if (n0 + no >= ldo) continue;
+            float t8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) t8[e] = tile[(no + e) * pitch + d];
+            uint4 pk;
+            pk.x = pack_bf16x2(t8[0], t8[1]);
+            pk.y = pack_bf16x2(t8[2], t8[3]);
+            pk.z = pack_bf16x2(t8[4], t8[5]);
+            pk.w = pack_bf16x2(t8[6], t8[7]);
+            uint16_t* dst = out_bt + (zo + d) * ldo + n0 + no;
+            *reinterpret_cast<uint4*>(dst) = pk;
+            if (planes == 2) {
+                uint4 lo;
+                lo.x = pack_bf16x2(t8[0] - __uint_as_float(pk.x << 16), t8[1] - __uint_as_float(pk.x & 0xffff0000u));
+                lo.y = pack_bf16x2(t8[2] - __uint_as_float(pk.y << 16), t8[3] - __uint_as_float(pk.y & 0xffff0000u));
+                lo.z = pack_bf16x2(t8[4] - __uint_as_float(pk.z << 16), t8[5] - __uint_as_float(pk.z & 0xffff0000u));
+                lo.w = pack_bf16x2(t8[6] - __uint_as_float(pk.w << 16), t8[7] - __uint_as_float(pk.w & 0xffff0000u));
+                *reinterpret_cast<uint4*>(dst + plane) = lo;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int ofq_softmax_quant(const float* S, int nz, int N, long long ld, int H, const float* bias,
+                                 const float* mask, int nW, const float* s_eff, int qhi, float* P, int8_t* codes,
+                                 long long ldq, float* rowsum, void* stream) {
+    OFQ_REQUIRE(S && s_eff && codes && nz > 0 && N > 0 && H > 0, "ofq_softmax_quant: bad argument");
+    OFQ_REQUIRE(N <= kMaxPer * 32, "ofq_softmax_quant: at most 256 keys per row are supported");
+    OFQ_REQUIRE(ld >= N && ldq >= N && qhi > 0 && qhi <= 127, "ofq_softmax_quant: bad pitch or level count");
+    OFQ_REQUIRE(!mask || nW > 0, "ofq_softmax_quant: mask needs nW");
+    OFQ_CHECK_ARCH();
+    const long long rows = (long long)nz * N;
+    softmax_quant_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        S, nz, N, ld, H, bias, mask, nW > 0 ? nW : 1, s_eff, (float)qhi, P, codes, ldq, rowsum);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ofq_softmax_quant_bwd(const float* dPq, const float* P, int nz, int N, long long ld, int H,
+                                     const float* s_eff, int qhi, float alpha, float g_s, const float* ca,
+                                     int ca_per_head, const float* rb, int planes, void* out_a, void* out_bt,
+                                     long long ldo, float* colsum, float* d_s, float* dS32, void* stream) {
+    OFQ_REQUIRE(dPq && P && s_eff && nz > 0 && N > 0 && H > 0, "ofq_softmax_quant_bwd: bad argument");
+    OFQ_REQUIRE(N <= kMaxPer * 32, "ofq_softmax_quant_bwd: at most 256 keys per row are supported");
+    OFQ_REQUIRE((!out_a && !out_bt) || (ldo % 8 == 0 && ldo >= N), "ofq_softmax_quant_bwd: output pitch must be a multiple of 8 and >= N");
+    OFQ_REQUIRE(!out_bt || (uintptr_t)out_bt % 16 == 0, "ofq_softmax_quant_bwd: out_bt alignment");
+    OFQ_REQUIRE(planes == 1 || planes == 2, "ofq_softmax_quant_bwd: planes must be 1 or 2");
+    OFQ_CHECK_ARCH();
+    dim3 grid((N + 31) / 32, nz);
+    const size_t smem = (size_t)32 * (N + 1) * sizeof(float);
+    softmax_quant_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
+        dPq, P, N, ld, H, s_eff, (float)qhi, alpha, g_s, ca, ca_per_head, rb, planes, (uint16_t*)out_a,
+        (uint16_t*)out_bt, ldo, colsum, d_s, dS32);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}

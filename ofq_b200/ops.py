@@ -1,0 +1,262 @@
+"""Tensor-level wrappers over the C-ABI (include/ofq_b200.h).
+
+Each function checks device / dtype / contiguity, allocates outputs with torch (plumbing) and launches the
+sm_100a kernel on torch's current stream.  No function here computes anything itself.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import GemmOut, Operand, Vec, check
+
+GEMM_I8, GEMM_BF16 = 0, 1
+PER_ROW, PER_COL = 0, 1
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.OfqError("ofq_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def vec(t: Optional[torch.Tensor], period: int = 0, bs1: int = 0, bs2: int = 0):
+    if t is None:
+        return None
+    assert t.dtype == torch.float32
+    return C.byref(Vec(t.data_ptr(), period, bs1, bs2))
+
+
+def gemm(kind: int, a: torch.Tensor, a_strides, b: torch.Tensor, b_strides, out: torch.Tensor, out_strides,
+         M: int, N: int, K: int, *, k2: int = 1, nb1: int = 1, nb2: int = 1, splits: int = 1, accumulate: bool = False,
+         rs=None, cs=None, rt=None, ct=None, a_k2mod: int = 0, b_k2mod: int = 0) -> None:
+    """Raw ofq_gemm call. a_strides/b_strides = (row, k2, batch1, batch2) in elements; out_strides = (ld, b1, b2).
+    rs/cs/rt/ct are ctypes Vec references from `vec()` or None."""
+    _cuda(a, b, out)
+    A = Operand(a.data_ptr(), a_strides[0], a_strides[1], a_k2mod, a_strides[2], a_strides[3])
+    B = Operand(b.data_ptr(), b_strides[0], b_strides[1], b_k2mod, b_strides[2], b_strides[3])
+    O = GemmOut(out.data_ptr(), *out_strides, 1 if accumulate else 0)
+    check(_lib.load().ofq_gemm(kind, C.byref(A), C.byref(B), C.byref(O), M, N, K, k2, nb1, nb2, splits,
+                               rs, cs, rt, ct, _st()))
+
+
+# ------------------------------------------------------------------------------------------------ quantizers
+def statsq_codes(w: torch.Tensor, bits: int, aft: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+                 want_minmax: bool = False):
+    """StatsQ codes of a 2-D fp32 weight. Returns (codes int8 [R,C], colscale [R], sf [R], colterm [R] | None,
+    kminmax int32[2] | None)."""
+    _cuda(w)
+    assert w.dim() == 2 and w.dtype == torch.float32 and w.stride(1) == 1
+    R, Cc = w.shape
+    codes = torch.empty((R, Cc), dtype=torch.int8, device=w.device)
+    colscale = torch.empty(R, dtype=torch.float32, device=w.device)
+    sf = torch.empty(R, dtype=torch.float32, device=w.device)
+    colterm = torch.empty(R, dtype=torch.float32, device=w.device) if (aft is not None or bias is not None) else None
+    mm = None
+    if want_minmax:
+        mm = torch.tensor([2 ** 31 - 1, -2 ** 31], dtype=torch.int32, device=w.device)
+    if colterm is not None and aft is None:
+        aft = torch.zeros(Cc, dtype=torch.float32, device=w.device)
+    check(_lib.load().ofq_statsq_codes(w.data_ptr(), R, Cc, w.stride(0), bits, codes.data_ptr(), Cc,
+                                       colscale.data_ptr(), sf.data_ptr(), _ptr(aft), _ptr(bias), _ptr(colterm),
+                                       _ptr(mm), _st()))
+    return codes, colscale, sf, colterm, mm
+
+
+def lsq_effective_scale(alpha: torch.Tensor, g: float) -> torch.Tensor:
+    _cuda(alpha)
+    a = alpha.detach().contiguous()
+    out = torch.empty_like(a)
+    check(_lib.load().ofq_lsq_effective_scale(a.data_ptr(), a.numel(), float(g), out.data_ptr(), _st()))
+    return out
+
+
+def lsq_quant(x2d: torch.Tensor, b4: torch.Tensor, s_eff: torch.Tensor, mode: int, period: int, nseg: int,
+              qlo: int, qhi: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x2d: [rows, cols] fp32 view (last dim contiguous). Returns int8 codes [rows, cols]."""
+    _cuda(x2d, b4, s_eff)
+    assert x2d.dim() == 2 and x2d.stride(1) == 1 and x2d.dtype == torch.float32
+    rows, cols = x2d.shape
+    if out is None:
+        out = torch.empty((rows, cols), dtype=torch.int8, device=x2d.device)
+    check(_lib.load().ofq_lsq_quant(x2d.data_ptr(), rows, cols, x2d.stride(0), b4.data_ptr(), s_eff.data_ptr(),
+                                    mode, period, nseg, qlo, qhi, out.data_ptr(), out.stride(0), _st()))
+    return out
+
+
+def lsq_bwd(dy2d: torch.Tensor, x2d: torch.Tensor, b4: torch.Tensor, s_eff: torch.Tensor, mode: int, period: int,
+            nseg: int, qlo: int, qhi: int, g: float, want_ds: bool = True):
+    """Returns (dx [rows, cols], d_s, d_b4 [cols], d_aft [cols])."""
+    _cuda(dy2d, x2d)
+    assert dy2d.dim() == 2 and dy2d.stride(1) == 1 and x2d.stride(1) == 1
+    rows, cols = dy2d.shape
+    lib = _lib.load()
+    ws = torch.empty(lib.ofq_lsq_bwd_workspace(rows, cols, nseg), dtype=torch.float32, device=dy2d.device)
+    dx = torch.empty((rows, cols), dtype=torch.float32, device=dy2d.device)
+    check(lib.ofq_lsq_bwd(dy2d.data_ptr(), dy2d.stride(0), x2d.data_ptr(), x2d.stride(0), rows, cols, b4.data_ptr(),
+                          s_eff.data_ptr(), mode, period, nseg, qlo, qhi, dx.data_ptr(), dx.stride(0),
+                          ws.data_ptr(), _st()))
+    ns = cols if mode == PER_COL else min(period, rows) * nseg
+    d_s = torch.empty(ns, dtype=torch.float32, device=dy2d.device) if want_ds else None
+    d_b4 = torch.empty(cols, dtype=torch.float32, device=dy2d.device)
+    d_aft = torch.empty(cols, dtype=torch.float32, device=dy2d.device)
+    check(lib.ofq_lsq_bwd_finalize(ws.data_ptr(), rows, cols, mode, period, nseg, float(g), _ptr(d_s),
+                                   d_b4.data_ptr(), d_aft.data_ptr(), _st()))
+    return dx, d_s, d_b4, d_aft
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def grad_prep(x: torch.Tensor, nb: int, R: int, Cc: int, ldx: int, bstride: int, *, cs=None, rs=None, rs_period=0,
+              want_rm: bool = False, want_t: bool = False, want_colsum: bool = False, u=None, group: int = 64,
+              planes: int = 1):
+    """One pass over a fp32 gradient: returns dict(rm=bf16 [planes,nb,R,C], t=bf16 [planes,nb,C,r_pad], r_pad,
+    colsum [C], rowdot [nb,C/group,R])."""
+    _cuda(x)
+    dev = x.device
+    r_pad = round_up(R, 8)
+    out = {"r_pad": r_pad}
+    rm = torch.empty((planes, nb, R, Cc), dtype=torch.bfloat16, device=dev) if want_rm else None
+    t = torch.empty((planes, nb, Cc, r_pad), dtype=torch.bfloat16, device=dev) if want_t else None
+    colsum = torch.zeros(Cc, dtype=torch.float32, device=dev) if want_colsum else None
+    rowdot = torch.empty((nb, Cc // group, R), dtype=torch.float32, device=dev) if u is not None else None
+    check(_lib.load().ofq_grad_prep(x.data_ptr(), nb, R, Cc, ldx, bstride, _ptr(cs), _ptr(rs), rs_period, planes,
+                                    _ptr(rm), Cc, _ptr(t), r_pad, _ptr(colsum), _ptr(u), group, _ptr(rowdot), _st()))
+    out.update(rm=rm, t=t, colsum=colsum, rowdot=rowdot)
+    return out
+
+
+def codes_to_bf16(codes: torch.Tensor, nb: int, R: int, Cc: int, ld: int, bstride: int, transpose: bool):
+    """int8 codes [nb][R][C] -> bf16 [nb,R,C] or transposed [nb,C,r_pad]."""
+    _cuda(codes)
+    if transpose:
+        r_pad = round_up(R, 8)
+        out = torch.empty((nb, Cc, r_pad), dtype=torch.bfloat16, device=codes.device)
+        check(_lib.load().ofq_codes_to_bf16(codes.data_ptr(), nb, R, Cc, ld, bstride, out.data_ptr(), r_pad,
+                                            Cc * r_pad, 1, _st()))
+    else:
+        out = torch.empty((nb, R, Cc), dtype=torch.bfloat16, device=codes.device)
+        check(_lib.load().ofq_codes_to_bf16(codes.data_ptr(), nb, R, Cc, ld, bstride, out.data_ptr(), Cc, R * Cc, 0,
+                                            _st()))
+    return out
+
+
+def codes_transpose(codes: torch.Tensor, nb: int, R: int, Cc: int, ld: int, bstride: int):
+    """int8 codes [nb][R][C] -> int8 [nb, C, r_pad16] (zero padded)."""
+    _cuda(codes)
+    r_pad = round_up(R, 16)
+    out = torch.empty((nb, Cc, r_pad), dtype=torch.int8, device=codes.device)
+    check(_lib.load().ofq_codes_transpose(codes.data_ptr(), nb, R, Cc, ld, bstride, out.data_ptr(), r_pad, Cc * r_pad,
+                                          _st()))
+    return out
+
+
+def codes_rowdot(codes2d: torch.Tensor, nseg: int, u: torch.Tensor) -> torch.Tensor:
+    """[rows, cols] int8 codes x fp32 vector u[cols] -> [rows, nseg] segment-wise dot products."""
+    _cuda(codes2d, u)
+    rows, cols = codes2d.shape
+    out = torch.empty((rows, nseg), dtype=torch.float32, device=codes2d.device)
+    check(_lib.load().ofq_codes_rowdot(codes2d.data_ptr(), rows, cols, codes2d.stride(0), nseg, u.data_ptr(),
+                                       out.data_ptr(), _st()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ softmax
+def softmax_quant(S: torch.Tensor, N: int, H: int, s_eff: torch.Tensor, qhi: int, *, bias=None, mask=None, nW: int = 0,
+                  save_p: bool = True):
+    """S: [nz, N, ld] fp32 scaled logits. Returns (P fp32 [nz,N,ld] | None, codes int8 [nz,N,ldq], rowsum [nz,N])."""
+    _cuda(S, s_eff)
+    nz, _, ld = S.shape
+    ldq = round_up(N, 16)
+    P = torch.empty_like(S) if save_p else None
+    codes = torch.empty((nz, N, ldq), dtype=torch.int8, device=S.device)
+    rowsum = torch.empty((nz, N), dtype=torch.float32, device=S.device)
+    check(_lib.load().ofq_softmax_quant(S.data_ptr(), nz, N, ld, H, _ptr(bias), _ptr(mask), nW, s_eff.data_ptr(), qhi,
+                                        _ptr(P), codes.data_ptr(), ldq, rowsum.data_ptr(), _st()))
+    return P, codes, rowsum
+
+
+def softmax_quant_bwd(dPq: torch.Tensor, P: torch.Tensor, N: int, H: int, s_eff: torch.Tensor, qhi: int, alpha: float,
+                      g_s: float, ca: torch.Tensor, ca_per_head: bool, rb: torch.Tensor, want_ds32: bool = False,
+                      planes: int = 1):
+    """Returns (out_a bf16 [B,planes,H,N,ldo], out_bt bf16 [B,planes,H,N,ldo], ldo, colsum [nz,N], d_s [N], dS32 | None)."""
+    _cuda(dPq, P)
+    nz, _, ld = P.shape
+    ldo = round_up(N, 8)
+    dev = P.device
+    out_a = torch.empty((nz // H, planes, H, N, ldo), dtype=torch.bfloat16, device=dev)
+    out_bt = torch.empty((nz // H, planes, H, N, ldo), dtype=torch.bfloat16, device=dev)
+    colsum = torch.zeros((nz, N), dtype=torch.float32, device=dev)
+    d_s = torch.zeros(N, dtype=torch.float32, device=dev)
+    ds32 = torch.empty_like(P) if want_ds32 else None
+    check(_lib.load().ofq_softmax_quant_bwd(dPq.data_ptr(), P.data_ptr(), nz, N, ld, H, s_eff.data_ptr(), qhi,
+                                            float(alpha), float(g_s), _ptr(ca), 1 if ca_per_head else 0, _ptr(rb), planes,
+                                            out_a.data_ptr(), out_bt.data_ptr(), ldo, colsum.data_ptr(),
+                                            d_s.data_ptr(), _ptr(ds32), _st()))
+    return out_a, out_bt, ldo, colsum, d_s, ds32
+
+
+# ------------------------------------------------------------------------------------------------ W_qk
+def wqk_compose(wq: torch.Tensor, wk: torch.Tensor, H: int) -> torch.Tensor:
+    _cuda(wq, wk)
+    Cc = wq.shape[1]
+    hd = wq.shape[0] // H
+    out = torch.empty((H * Cc, Cc), dtype=torch.float32, device=wq.device)
+    check(_lib.load().ofq_wqk_compose(wq.data_ptr(), wk.data_ptr(), H, hd, Cc, out.data_ptr(), _st()))
+    return out
+
+
+def wqk_compose_bwd(dwqk: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, H: int):
+    Cc = wq.shape[1]
+    hd = wq.shape[0] // H
+    dwq = torch.empty_like(wq)
+    dwk = torch.empty_like(wk)
+    check(_lib.load().ofq_wqk_compose_bwd(dwqk.data_ptr(), wq.data_ptr(), wk.data_ptr(), H, hd, Cc, dwq.data_ptr(),
+                                          dwk.data_ptr(), _st()))
+    return dwq, dwk
+
+
+# ------------------------------------------------------------------------------------------------ CGA / AdamW
+def cga_mask(w: torch.Tensor, bits: int, boundary_range: float) -> torch.Tensor:
+    """uint8 [rows, cols]: 1 = frozen, 0 = trainable (cga.py:450-469)."""
+    _cuda(w)
+    assert w.dim() == 2 and w.is_contiguous() and w.dtype == torch.float32
+    R, Cc = w.shape
+    mask = torch.empty((R, Cc), dtype=torch.uint8, device=w.device)
+    rowstat = torch.empty(R, dtype=torch.float32, device=w.device)
+    mm = torch.empty(2, dtype=torch.int32, device=w.device)
+    check(_lib.load().ofq_cga_mask(w.data_ptr(), R, Cc, bits, float(boundary_range), mask.data_ptr(),
+                                   rowstat.data_ptr(), mm.data_ptr(), _st()))
+    return mask
+
+
+def cga_adamw_(p: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
+               lr: float, beta1: float, beta2: float, eps: float, weight_decay: float, bits: int = 0,
+               boundary_range: float = 0.005, scratch=None, mask_out: Optional[torch.Tensor] = None) -> None:
+    """In-place (masked) AdamW step on one parameter. bits == 0: plain AdamW."""
+    _cuda(p, grad, exp_avg, exp_avg_sq)
+    assert p.is_contiguous() and grad.is_contiguous() and p.dtype == torch.float32
+    rows = cols = 0
+    rowstat = mm = None
+    if bits > 0:
+        rows, cols = p.shape
+        if scratch is None:
+            scratch = (torch.empty(rows, dtype=torch.float32, device=p.device),
+                       torch.empty(2, dtype=torch.int32, device=p.device))
+        rowstat, mm = scratch
+    check(_lib.load().ofq_cga_adamw(p.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                    p.numel(), rows, cols, step, lr, beta1, beta2, eps, weight_decay, bits,
+                                    float(boundary_range), _ptr(rowstat), _ptr(mm), _ptr(mask_out), _st()))

@@ -1,0 +1,354 @@
+"""Autograd functions of the OFQ hot path: each forward/backward is a fixed sequence of sm_100a kernels
+reached through the C-ABI (ofq_b200/ops.py).  No arithmetic of the path is done by PyTorch here; torch only
+allocates buffers and re-lays-out a few per-token scale vectors (hundreds of floats).
+
+Data layout (HBM): activations are fp32 [B*N, C] row-major; every quantized operand is stored ONCE as int8
+codes (+ an fp32 scale vector and the `move_aft` shift), so the forward GEMMs are exact integer GEMMs and the
+backward rebuilds bf16 operands from the saved codes.  Reference: src/quantization/modules/{qlinear,attention}.py.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Optional
+
+import torch
+
+from .. import ops
+from ..ops import GEMM_BF16, GEMM_I8, PER_COL, PER_ROW, round_up, vec
+
+NUM_SMS = 148
+# bf16 planes of every real-valued backward GEMM operand: 2 = hi + lo split (~16 mantissa bits, meets the 1e-3
+# parity bound on every gradient), 1 = plain bf16 (~1-2e-3 gradient error, half the operand traffic).
+PLANES = int(os.environ.get("OFQ_BWD_PLANES", "2"))
+
+
+def levels(bit: int, all_positive: bool):
+    """(thd_neg, thd_pos) of lsq.py:519-534."""
+    if bit == 1:
+        raise NotImplementedError("1-bit (sign) LSQ is not part of the OFQ recipes (2/3/4 bit)")
+    if all_positive:
+        return 0, 2 ** bit - 1
+    return -(2 ** (bit - 1)), 2 ** (bit - 1) - 1
+
+
+def grad_scale_factor(hi: int, count: int) -> float:
+    """s_grad_scale of lsq.py:582-591 / 775-778: 1/sqrt(thd_pos * elements-per-scale)."""
+    return 1.0 / ((hi * count) ** 0.5)
+
+
+def _splits_for(tiles: int, kblocks: int) -> int:
+    s = max(1, min((2 * NUM_SMS + tiles - 1) // tiles, max(1, kblocks // 4)))
+    return min(s, 64)
+
+
+def _linear_backward(dY2d, qx, wc, colscale, se_x, period, x_aft, dxhat, accumulate_dx: bool, qxT_all=None):
+    """Backward of out = x_hat @ W_hat^T (+bias):  dX_hat (+)= dY W_hat,  dW = dY^T x_hat,  dbias = colsum(dY).
+    x_hat = qx * se_x[row % period] + x_aft,  W_hat = wc * colscale[row].  Returns (dW, dbias, qxT_all)."""
+    M, Nout = dY2d.shape
+    K = qx.shape[1]
+    prep = ops.grad_prep(dY2d, 1, M, Nout, dY2d.stride(0), 0, cs=colscale, rs=se_x, rs_period=period,
+                         want_rm=True, want_t=True, want_colsum=True, planes=PLANES)
+    m_pad = prep["r_pad"]
+    # dX_hat[M,K] = (dY * colscale)[M,Nout] @ codes[Nout,K]
+    wcT = ops.codes_to_bf16(wc, 1, Nout, K, K, 0, True)            # [1, K, nout_pad]
+    nout_pad = wcT.shape[-1]
+    ops.gemm(GEMM_BF16, prep["rm"], (Nout, M * Nout, 0, 0), wcT, (nout_pad, 0, 0, 0), dxhat, (K, 0, 0), M, K, Nout,
+             k2=PLANES, accumulate=accumulate_dx)
+    # dW[Nout,K] = (dY * se_x)^T[Nout,M] @ qx[M,K]  + colsum(dY)[Nout] x aft[K]
+    if qxT_all is None:
+        qxT_all = ops.codes_to_bf16(qx, 1, M, K, K, 0, True)       # [1, K, m_pad]
+    dW = torch.zeros((Nout, K), dtype=torch.float32, device=dY2d.device)
+    tiles = ((Nout + 127) // 128) * ((K + 127) // 128)
+    splits = _splits_for(tiles, PLANES * ((M + 63) // 64))
+    ops.gemm(GEMM_BF16, prep["t"], (m_pad, Nout * m_pad, 0, 0), qxT_all, (m_pad, 0, 0, 0), dW, (K, 0, 0), Nout, K, M,
+             k2=PLANES, splits=splits, accumulate=True, rt=vec(prep["colsum"]), ct=vec(x_aft))
+    return dW, prep["colsum"], qxT_all
+
+
+# ====================================================================================== QLinear
+class QLinearFn(torch.autograd.Function):
+    """QLinear.forward (qlinear.py:58-73): StatsQ weight codes, (move_b4 -> LSQ -> move_aft) input codes,
+    int8 tcgen05 GEMM with the scales / shift / bias in the epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, b4, aft, s, wbits: int, abits: int, unsigned: bool):
+        K = x.shape[-1]
+        P = x.shape[-2]
+        xc = x.contiguous()
+        x2d = xc.view(-1, K)
+        M = x2d.shape[0]
+        Nout = weight.shape[0]
+        lo, hi = levels(abits, unsigned)
+        g = grad_scale_factor(hi, x.numel() // P)
+        se = ops.lsq_effective_scale(s, g)
+        qx = ops.lsq_quant(x2d, b4, se, PER_ROW, P, 1, lo, hi)
+        wc, colscale, _, colterm, _ = ops.statsq_codes(weight, wbits, aft=aft, bias=bias)
+        out = torch.empty((M, Nout), dtype=torch.float32, device=x.device)
+        ops.gemm(GEMM_I8, qx, (K, 0, 0, 0), wc, (K, 0, 0, 0), out, (Nout, 0, 0), M, Nout, K,
+                 rs=vec(se, P), cs=vec(colscale), ct=vec(colterm))
+        ctx.save_for_backward(xc, qx, wc, colscale, se, b4, aft)
+        ctx.cfg = (P, lo, hi, g, bias is not None)
+        return out.view(*x.shape[:-1], Nout)
+
+    @staticmethod
+    def backward(ctx, dY):
+        xc, qx, wc, colscale, se, b4, aft = ctx.saved_tensors
+        P, lo, hi, g, has_bias = ctx.cfg
+        K = xc.shape[-1]
+        x2d = xc.view(-1, K)
+        M = x2d.shape[0]
+        dY2d = dY.contiguous().view(M, -1)
+        dxhat = torch.empty((M, K), dtype=torch.float32, device=dY.device)
+        dW, dbias, _ = _linear_backward(dY2d, qx, wc, colscale, se, P, aft, dxhat, False)
+        dx, ds, db4, daft = ops.lsq_bwd(dxhat, x2d, b4, se, PER_ROW, P, 1, lo, hi, g)
+        return dx.view_as(xc), dW, (dbias if has_bias else None), db4, daft, ds, None, None, None
+
+
+# ====================================================================================== standalone LSQ
+class LsqFn(torch.autograd.Function):
+    """LsqQuantizer / LsqQuantizer4v forward as a module of its own (lsq.py:571-602, 757-790)."""
+
+    @staticmethod
+    def forward(ctx, x, s, bit: int, all_positive: bool, per_col: bool):
+        K = x.shape[-1]
+        xc = x.contiguous()
+        x2d = xc.view(-1, K)
+        lo, hi = levels(bit, all_positive)
+        if per_col:
+            g = grad_scale_factor(hi, x.numel() // K)
+            mode, period = PER_COL, 1
+        else:
+            period = x.shape[-2]
+            g = grad_scale_factor(hi, x.numel() // period)
+            mode = PER_ROW
+        se = ops.lsq_effective_scale(s, g)
+        zero = torch.zeros(K, dtype=torch.float32, device=x.device)
+        codes = ops.lsq_quant(x2d, zero, se, mode, period, 1, lo, hi)
+        # dequantise: q * s_eff  (exact product of a small integer and the scale, as the reference computes it)
+        scale = se.view(1, -1) if per_col else se.repeat(x2d.shape[0] // period).view(-1, 1)
+        out = (codes.to(torch.float32) * scale).view_as(xc)
+        ctx.save_for_backward(xc, se, zero)
+        ctx.cfg = (mode, period, lo, hi, g)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, se, zero = ctx.saved_tensors
+        mode, period, lo, hi, g = ctx.cfg
+        K = xc.shape[-1]
+        dx, ds, _, _ = ops.lsq_bwd(dy.contiguous().view(-1, K), xc.view(-1, K), zero, se, mode, period, 1, lo, hi, g)
+        return dx.view_as(xc), ds, None, None, None
+
+
+# ====================================================================================== attention core
+def _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C):
+    """out[b,n,h*hd+j] = se_p[n] * (se_v[hj] * sum_d qp[z,n,d] qv[b,d,hj] + v_aft[hj] * sum_d qp[z,n,d])."""
+    hd = C // H
+    qvT = ops.codes_transpose(qv, B, N, C, C, N * C)                 # [B, C, NP16]
+    npad = qvT.shape[-1]
+    out = torch.empty((B, N, C), dtype=torch.float32, device=qv.device)
+    ops.gemm(GEMM_I8, qp, (ldq, 0, N * ldq, H * N * ldq), qvT, (npad, 0, hd * npad, C * npad), out,
+             (C, hd, N * C), N, hd, N, nb1=H, nb2=B,
+             rs=vec(se_p, N), cs=vec(se_v, 0, hd), rt=vec(rowsum, 0, N, H * N), ct=vec(v_aft, 0, hd))
+    return out
+
+
+def _pv_backward(dO, qp, ldq, qv, se_p, se_v, v_aft, B, N, H, C, ldS):
+    """Returns (dPq [B*H,N,ldS] fp32, dvhat [B,N,C] fp32)."""
+    hd = C // H
+    prep = ops.grad_prep(dO, B, N, C, C, N * C, cs=se_v, rs=se_p, rs_period=N, want_rm=True, want_t=True,
+                         u=v_aft, group=hd, planes=PLANES)
+    npad8 = prep["r_pad"]
+    # dP_hat[z,n,d] = sum_j (dO[n,hj] se_v[hj]) qv[d,hj] + sum_j dO[n,hj] v_aft[hj]
+    qv16 = ops.codes_to_bf16(qv, B, N, C, C, N * C, False)           # [B, N, C] bf16
+    dPq = torch.empty((B * H, N, ldS), dtype=torch.float32, device=dO.device)
+    ops.gemm(GEMM_BF16, prep["rm"], (C, B * N * C, hd, N * C), qv16, (C, 0, hd, N * C), dPq, (ldS, N * ldS, H * N * ldS),
+             N, N, hd, k2=PLANES, nb1=H, nb2=B, rt=vec(prep["rowdot"], 0, N, H * N))
+    # dv_hat[b,d,hj] = sum_n qp[z,n,d] (se_p[n] dO[b,n,hj])
+    qpT = ops.codes_to_bf16(qp, B * H, N, ldq, ldq, N * ldq, True)   # [B*H, ldq, npad8]; rows d >= N are zero
+    dvhat = torch.empty((B, N, C), dtype=torch.float32, device=dO.device)
+    ops.gemm(GEMM_BF16, qpT, (npad8, 0, ldq * npad8, H * ldq * npad8), prep["t"],
+             (npad8, B * C * npad8, hd * npad8, C * npad8), dvhat, (C, hd, N * C), N, hd, N, k2=PLANES, nb1=H, nb2=B)
+    return dPq, dvhat
+
+
+class QKRAttnCoreFn(torch.autograd.Function):
+    """QAttention_qkreparam.forward up to (not including) proj (attention.py:174-219), and the Swin variant
+    (swin_attention_and_mlp.py:168-229) through `attn_bias` / `attn_mask`.  x is [B, N, C]."""
+
+    @staticmethod
+    def forward(ctx, x, wq, wk, wv, bv, x_b4, x_aft, s_x, v_b4, v_aft, s_v, k_b4, k_aft, s_k, s_p,
+                attn_bias, attn_mask, H: int, wbits: int, abits: int, nW: int):
+        B, N, C = x.shape
+        M = B * N
+        hd = C // H
+        dev = x.device
+        lo, hi = levels(abits, False)
+        _, hiu = levels(abits, True)
+        scale = hd ** -0.5
+        xc = x.contiguous()
+        x2d = xc.view(M, C)
+        # --- shared quantized input (LSQ_input, qlinear.py:21-26)
+        g_x = grad_scale_factor(hi, B * C)
+        se_x = ops.lsq_effective_scale(s_x, g_x)
+        qx = ops.lsq_quant(x2d, x_b4, se_x, PER_ROW, N, 1, lo, hi)
+        # --- V branch (attention.py:179-186)
+        wvc, cs_v, _, ct_v, _ = ops.statsq_codes(wv, wbits, aft=x_aft, bias=bv)
+        v_out = torch.empty((M, C), dtype=torch.float32, device=dev)
+        ops.gemm(GEMM_I8, qx, (C, 0, 0, 0), wvc, (C, 0, 0, 0), v_out, (C, 0, 0), M, C, C,
+                 rs=vec(se_x, N), cs=vec(cs_v), ct=vec(ct_v))
+        g_v = grad_scale_factor(hi, B * N)
+        se_v = ops.lsq_effective_scale(s_v, g_v)
+        qv = ops.lsq_quant(v_out, v_b4, se_v, PER_COL, 1, 1, lo, hi)
+        # --- QK branch: one StatsQ on the per-head product W_q^T W_k (attention.py:190-196)
+        wqk = ops.wqk_compose(wq, wk, H)
+        wqkc, cs_qk, _, ct_qk, _ = ops.statsq_codes(wqk, wbits, aft=x_aft)
+        qkx = torch.empty((M, H * C), dtype=torch.float32, device=dev)
+        ops.gemm(GEMM_I8, qx, (C, 0, 0, 0), wqkc, (C, 0, 0, 0), qkx, (H * C, 0, 0), M, H * C, C,
+                 rs=vec(se_x, N), cs=vec(cs_qk), ct=vec(ct_qk))
+        g_k = grad_scale_factor(hi, B * C)
+        se_k = ops.lsq_effective_scale(s_k, g_k)                     # [N*H], index n*H + h
+        qk = ops.lsq_quant(qkx, k_b4, se_k, PER_ROW, N, H, lo, hi)   # [M, H*C]
+        # --- scores (attention.py:210-213): S = x_hat . k_hat^T * scale; terms constant along the softmax
+        #     axis are dropped (they cancel exactly in softmax and in its gradient)
+        ctS = ops.codes_rowdot(qk, H, x_aft.repeat(H))               # [M, H]: sum_c x_aft[c] qk[b,d,h,c]
+        se_k_hn = se_k.view(N, H).t().contiguous()                   # [H, N]
+        cs_S = se_k_hn * scale
+        ct_S = (ctS.view(B, N, H).permute(0, 2, 1) * cs_S.unsqueeze(0)).contiguous()   # [B, H, N]
+        ldS = round_up(N, 4)
+        S = torch.empty((B * H, N, ldS), dtype=torch.float32, device=dev)
+        ops.gemm(GEMM_I8, qx, (C, 0, 0, N * C), qk, (H * C, 0, C, N * H * C), S, (ldS, N * ldS, H * N * ldS),
+                 N, N, C, nb1=H, nb2=B, rs=vec(se_x, N), cs=vec(cs_S, 0, N), ct=vec(ct_S, 0, N, H * N))
+        # --- softmax + probability quantizer (attention.py:213-215)
+        g_p = grad_scale_factor(hiu, B * H * N)
+        se_p = ops.lsq_effective_scale(s_p, g_p)
+        need_grad = any(ctx.needs_input_grad)
+        P, qp, rowsum = ops.softmax_quant(S, N, H, se_p, hiu, bias=attn_bias, mask=attn_mask, nW=nW, save_p=need_grad)
+        ldq = qp.shape[-1]
+        del S
+        out = _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C)
+        ctx.save_for_backward(xc, wq, wk, x_b4, x_aft, v_b4, v_aft, k_b4, k_aft, qx, se_x, wvc, cs_v, v_out, qv, se_v,
+                              wqkc, cs_qk, qkx, qk, se_k, se_k_hn, P, qp, se_p)
+        ctx.cfg = (B, N, C, H, lo, hi, hiu, scale, g_x, g_v, g_k, g_p, ldS, ldq, bv is not None,
+                   attn_bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dO):
+        (xc, wq, wk, x_b4, x_aft, v_b4, v_aft, k_b4, k_aft, qx, se_x, wvc, cs_v, v_out, qv, se_v, wqkc, cs_qk, qkx, qk,
+         se_k, se_k_hn, P, qp, se_p) = ctx.saved_tensors
+        B, N, C, H, lo, hi, hiu, scale, g_x, g_v, g_k, g_p, ldS, ldq, has_bv, has_bias = ctx.cfg
+        M = B * N
+        dev = dO.device
+        dO = dO.contiguous()
+        dPq, dvhat = _pv_backward(dO, qp, ldq, qv, se_p, se_v, v_aft, B, N, H, C, ldS)
+        # --- V quantizer and V linear
+        dv_out, ds_v, dvb4, dvaft = ops.lsq_bwd(dvhat.view(M, C), v_out, v_b4, se_v, PER_COL, 1, 1, lo, hi, g_v)
+        dxhat = torch.empty((M, C), dtype=torch.float32, device=dev)
+        dWv, dbv, qxT_all = _linear_backward(dv_out, qx, wvc, cs_v, se_x, N, x_aft, dxhat, False)
+        # --- softmax + probability quantizer
+        dSa, dSbT, ldo, colsum_dS, ds_p, dS32 = ops.softmax_quant_bwd(dPq, P, N, H, se_p, hiu, scale, g_p, se_k_hn, True,
+                                                                    se_x, want_ds32=has_bias, planes=PLANES)
+        slab = N * ldo                      # one (b, plane, h) slab of dSa / dSbT, laid out [B, PLANES, H, N, ldo]
+        del dPq
+        # --- scores: d x_hat += sum_h dS (k_hat)   (outer-K loop over heads)
+        qkT = ops.codes_to_bf16(qk, B, N, H * C, H * C, N * H * C, True)      # [B, H*C, npad8]
+        npad8 = qkT.shape[-1]
+        ops.gemm(GEMM_BF16, dSa, (ldo, slab, PLANES * H * slab, 0), qkT, (npad8, C * npad8, H * C * npad8, 0),
+                 dxhat, (C, N * C, 0), N, C, N, k2=PLANES * H, nb1=B, accumulate=True, b_k2mod=H)
+        # --- scores: d k_hat[b,d,h,c] = sum_n dS[n,d] x_hat[n,c]
+        qxT_b = ops.codes_to_bf16(qx, B, N, C, C, N * C, True)                # [B, C, npad8]
+        dkhat = torch.empty((M, H * C), dtype=torch.float32, device=dev)
+        ops.gemm(GEMM_BF16, dSbT, (ldo, H * slab, slab, PLANES * H * slab), qxT_b, (npad8, 0, 0, C * npad8), dkhat,
+                 (H * C, C, N * H * C), N, C, N, k2=PLANES, nb1=H, nb2=B, rt=vec(colsum_dS, 0, N, H * N), ct=vec(x_aft))
+        del dSa, dSbT
+        # --- qkx quantizer and the qkx "linear" layer (weight = StatsQ(W_q^T W_k), no bias)
+        dqkx, ds_k, dkb4, dkaft = ops.lsq_bwd(dkhat, qkx, k_b4, se_k, PER_ROW, N, H, lo, hi, g_k)
+        del dkhat
+        dWqk, _, _ = _linear_backward(dqkx, qx, wqkc, cs_qk, se_x, N, x_aft, dxhat, True, qxT_all)
+        dwq, dwk = ops.wqk_compose_bwd(dWqk, wq, wk, H)
+        # --- shared input quantizer
+        dx, ds_x, dxb4, dxaft = ops.lsq_bwd(dxhat, xc.view(M, C), x_b4, se_x, PER_ROW, N, 1, lo, hi, g_x)
+        dbias = None
+        if has_bias:
+            dbias = dS32[..., :N].reshape(B, H, N, N).sum(0)
+        return (dx.view(B, N, C), dwq, dwk, dWv, (dbv if has_bv else None), dxb4, dxaft, ds_x, dvb4, dvaft, ds_v,
+                dkb4, dkaft, ds_k, ds_p, dbias, None, None, None, None, None)
+
+
+class QAttnCoreFn(torch.autograd.Function):
+    """QAttention.forward between the qkv QLinear and proj (attention.py:70-102) / QAttention_swin
+    (swin_attention_and_mlp.py:172-229).  qkv is [B, N, 3C] laid out (3, H, hd) along the last dim."""
+
+    @staticmethod
+    def forward(ctx, qkv, b4, s_q, s_k, s_v, q_aft, k_aft, v_aft, s_p, attn_bias, attn_mask, H: int, abits: int, nW: int):
+        B, N, C3 = qkv.shape
+        C = C3 // 3
+        M = B * N
+        hd = C // H
+        dev = qkv.device
+        lo, hi = levels(abits, False)
+        _, hiu = levels(abits, True)
+        scale = hd ** -0.5
+        qkvc = qkv.contiguous()
+        q2d = qkvc.view(M, C3)
+        g_qk = grad_scale_factor(hi, B * C)           # 4-D (B,H,N,hd): B*H*hd elements per token scale
+        se_q = ops.lsq_effective_scale(s_q, g_qk)
+        se_k = ops.lsq_effective_scale(s_k, g_qk)
+        g_v = grad_scale_factor(hi, B * N)
+        se_v = ops.lsq_effective_scale(s_v, g_v)
+        qq = ops.lsq_quant(q2d[:, 0:C], b4[0:C], se_q, PER_ROW, N, 1, lo, hi)
+        qk = ops.lsq_quant(q2d[:, C:2 * C], b4[C:2 * C], se_k, PER_ROW, N, 1, lo, hi)
+        qv = ops.lsq_quant(q2d[:, 2 * C:], b4[2 * C:], se_v, PER_COL, 1, 1, lo, hi)
+        # S = q_hat k_hat^T * scale with q_hat = qq se_q[n] + q_aft, k_hat = qk se_k[d] + k_aft (row-only terms dropped)
+        ctS = ops.codes_rowdot(qk, H, q_aft)                          # [M, H]: sum_j q_aft[hj] qk[b,d,hj]
+        cs_S = se_k * scale                                           # [N]
+        ct_S = (ctS.view(B, N, H).permute(0, 2, 1) * cs_S.view(1, 1, N)).contiguous()   # [B, H, N]
+        ldS = round_up(N, 4)
+        S = torch.empty((B * H, N, ldS), dtype=torch.float32, device=dev)
+        ops.gemm(GEMM_I8, qq, (C, 0, hd, N * C), qk, (C, 0, hd, N * C), S, (ldS, N * ldS, H * N * ldS),
+                 N, N, hd, nb1=H, nb2=B, rs=vec(se_q, N), cs=vec(cs_S), ct=vec(ct_S, 0, N, H * N))
+        g_p = grad_scale_factor(hiu, B * H * N)
+        se_p = ops.lsq_effective_scale(s_p, g_p)
+        need_grad = any(ctx.needs_input_grad)
+        P, qp, rowsum = ops.softmax_quant(S, N, H, se_p, hiu, bias=attn_bias, mask=attn_mask, nW=nW, save_p=need_grad)
+        ldq = qp.shape[-1]
+        del S
+        out = _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C)
+        ctx.save_for_backward(qkvc, b4, q_aft, k_aft, v_aft, qq, qk, qv, se_q, se_k, se_v, P, qp, se_p)
+        ctx.cfg = (B, N, C, H, lo, hi, hiu, scale, g_qk, g_v, g_p, ldS, ldq, attn_bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dO):
+        qkvc, b4, q_aft, k_aft, v_aft, qq, qk, qv, se_q, se_k, se_v, P, qp, se_p = ctx.saved_tensors
+        B, N, C, H, lo, hi, hiu, scale, g_qk, g_v, g_p, ldS, ldq, has_bias = ctx.cfg
+        M = B * N
+        hd = C // H
+        dev = dO.device
+        dO = dO.contiguous()
+        q2d = qkvc.view(M, 3 * C)
+        dPq, dvhat = _pv_backward(dO, qp, ldq, qv, se_p, se_v, v_aft, B, N, H, C, ldS)
+        dSa, dSbT, ldo, colsum_dS, ds_p, dS32 = ops.softmax_quant_bwd(dPq, P, N, H, se_p, hiu, scale, g_p, se_k, False,
+                                                                    se_q, want_ds32=has_bias, planes=PLANES)
+        slab = N * ldo
+        del dPq
+        # dq_hat[b,n,hj] = sum_d (dS se_k[d]) qk[b,d,hj]
+        qkT = ops.codes_to_bf16(qk, B, N, C, C, N * C, True)          # [B, C, npad8]
+        npad8 = qkT.shape[-1]
+        dqhat = torch.empty((M, C), dtype=torch.float32, device=dev)
+        ops.gemm(GEMM_BF16, dSa, (ldo, H * slab, slab, PLANES * H * slab), qkT, (npad8, 0, hd * npad8, C * npad8), dqhat,
+                 (C, hd, N * C), N, hd, N, k2=PLANES, nb1=H, nb2=B)
+        # dk_hat[b,d,hj] = sum_n (dS se_q[n]) qq[b,n,hj] + colsum_dS[z,d] q_aft[hj]
+        qqT = ops.codes_to_bf16(qq, B, N, C, C, N * C, True)
+        dkhat = torch.empty((M, C), dtype=torch.float32, device=dev)
+        ops.gemm(GEMM_BF16, dSbT, (ldo, H * slab, slab, PLANES * H * slab), qqT, (npad8, 0, hd * npad8, C * npad8), dkhat,
+                 (C, hd, N * C), N, hd, N, k2=PLANES, nb1=H, nb2=B, rt=vec(colsum_dS, 0, N, H * N), ct=vec(q_aft, 0, hd))
+        dq, ds_q, db4_q, daft_q = ops.lsq_bwd(dqhat, q2d[:, 0:C], b4[0:C], se_q, PER_ROW, N, 1, lo, hi, g_qk)
+        dk, ds_k, db4_k, daft_k = ops.lsq_bwd(dkhat, q2d[:, C:2 * C], b4[C:2 * C], se_k, PER_ROW, N, 1, lo, hi, g_qk)
+        dv, ds_v, db4_v, daft_v = ops.lsq_bwd(dvhat.view(M, C), q2d[:, 2 * C:], b4[2 * C:], se_v, PER_COL, 1, 1, lo, hi, g_v)
+        dqkv = torch.cat((dq, dk, dv), dim=1).view(B, N, 3 * C)
+        db4 = torch.cat((db4_q, db4_k, db4_v))
+        dbias = dS32[..., :N].reshape(B, H, N, N).sum(0) if has_bias else None
+        return dqkv, db4, ds_q, ds_k, ds_v, daft_q, daft_k, daft_v, ds_p, dbias, None, None, None, None

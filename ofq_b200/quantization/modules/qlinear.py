@@ -1,0 +1,155 @@
+"""Quantized linear layers (reference: src/quantization/modules/qlinear.py). Same class names, constructor
+keywords, forward signatures, sub-module and parameter names; the arithmetic runs in the sm_100a kernels."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ...host.deit import Mlp
+from ..functional import QLinearFn
+from ..quantizer.lsq import (LsqQuantizer, LsqQuantizer4Conv2d, LsqQuantizer4head_input, LsqQuantizer4img,
+                             LsqQuantizerWeight)
+from ..quantizer.statsq import StatsQuantizer
+from .qbias import LearnableBias, LearnableBias4img
+
+
+class LSQ_input(nn.Module):
+    """qlinear.py:12-26: move_b4 -> LsqQuantizer -> move_aft as a stand-alone module. Inside
+    QAttention_qkreparam only its parameters are used (the codes never leave the fused kernels)."""
+
+    def __init__(self, bit=2, all_positive=False, learnable=True, learanbaleBiasdim=192):
+        super().__init__()
+        self.input_bits = bit
+        self.all_positive = all_positive
+        self.learnable = learnable
+        self.input_quant_fn = LsqQuantizer(bit=bit, all_positive=all_positive, learnable=learnable)
+        self.move_b4 = LearnableBias(learanbaleBiasdim)
+        self.move_aft = LearnableBias(learanbaleBiasdim)
+
+    def forward(self, input):
+        return self.move_aft(self.input_quant_fn(self.move_b4(input)))
+
+
+class QLinear(nn.Linear):
+    """qlinear.py:28-87."""
+
+    def __init__(self, *kargs, m: nn.Linear, weight_bits=8, input_bits=8, aq_learnable=True, wq_learnable=True,
+                 symmetric=True, weight_channelwise=True, input_channelwise=True, weight_quant_method="statsq",
+                 input_quant_method="lsq", pretrained_initialized=False, **kwargs):
+        super().__init__(m.in_features, m.out_features, bias=True)
+        self.weight_bits = weight_bits
+        self.input_bits = input_bits
+        self.aq_learnable = aq_learnable
+        self.wq_learnable = wq_learnable
+        self.symmetric = symmetric
+        self.weight_channelwise = weight_channelwise
+        self.input_channelwise = input_channelwise
+        self.weight_quant_method = weight_quant_method
+        self.input_quant_method = input_quant_method
+        self.input_quant_fn = LsqQuantizer(bit=input_bits, all_positive=(symmetric == False), learnable=aq_learnable)  # noqa: E712
+        self.pretrained_initialized = pretrained_initialized
+        if pretrained_initialized != False:  # noqa: E712
+            self.weight = nn.Parameter(m.weight.detach())
+            if m.bias is not None:
+                self.bias = nn.Parameter(m.bias.detach())
+        if weight_quant_method == "statsq":
+            self.statsq_fn = StatsQuantizer(num_bits=self.weight_bits, clip_learnable=wq_learnable).to(m.weight.device)
+        else:
+            raise ValueError("Unknown quant_method")
+        self.move_b4 = LearnableBias(self.weight.shape[1])
+        self.move_aft = LearnableBias(self.weight.shape[1])
+
+    def forward(self, input):
+        if self.weight_quant_method != "statsq":
+            raise ValueError("Unknown quant_method")
+        q = self.input_quant_fn
+        if not q.initialized_alpha:
+            q.init_from(input.detach() + self.move_b4.bias)
+        return QLinearFn.apply(input, self.weight, self.bias, self.move_b4.bias, self.move_aft.bias, q.s,
+                               self.weight_bits, self.input_bits, not self.symmetric)
+
+    def extra_repr(self):
+        return (f"act_bit={self.input_bits}, weight_bit={self.weight_bits}, act_all_positive={not self.symmetric}, "
+                f"wq_learnable={self.wq_learnable}, aq_learnable={self.aq_learnable}, "
+                f"weight_quant_method={self.weight_quant_method}, activation_quant_method={self.input_quant_method}, "
+                f"pretrained_initialized = {self.pretrained_initialized}")
+
+
+class QMLP(Mlp):
+    """qlinear.py:89-136: fc1 (signed input) -> GELU -> fc2 (unsigned input)."""
+
+    def __init__(self, *kargs, m: Mlp, weight_bits=8, input_bits=8, aq_learnable=True, wq_learnable=True,
+                 weight_channelwise=True, input_channelwise=True, weight_quant_method="statsq", input_quant_method="lsq",
+                 act_layer=nn.GELU, pretrained_initialized=False, **kwargs):
+        super().__init__(in_features=m.in_features, hidden_features=m.hidden_features, out_features=m.out_features, drop=m.drop)
+        common = dict(weight_bits=weight_bits, input_bits=input_bits, aq_learnable=aq_learnable, wq_learnable=wq_learnable,
+                      weight_channelwise=weight_channelwise, input_channelwise=input_channelwise,
+                      weight_quant_method=weight_quant_method, input_quant_method=input_quant_method,
+                      pretrained_initialized=pretrained_initialized)
+        self.fc1 = QLinear(m=m.fc1, symmetric=True, **common)
+        self.act_layer = act_layer
+        if act_layer == "rprelu":
+            raise NotImplementedError("rprelu activations are not used by any OFQ recipe")
+        self.act = act_layer() if act_layer != "None" else nn.Identity()
+        self.fc2 = QLinear(m=m.fc2, symmetric=False, **common)
+
+    def forward(self, x):
+        x = self.drop1(self.act(self.fc1(x)))
+        return self.drop2(self.fc2(x))
+
+
+class LSQ_QConv2d(nn.Conv2d):
+    """qlinear.py:138-191: the 8-bit patch-embedding convolution (torch-composed)."""
+
+    def __init__(self, *kargs, m: nn.Conv2d, weight_bits=8, input_bits=8, aq_learnable=True, wq_learnable=True,
+                 symmetric=True, weight_channelwise=True, input_channelwise=True, weight_quant_method="lsq",
+                 input_quant_method="lsq", pretrained_initialized=False, **kwargs):
+        super().__init__(in_channels=m.in_channels, out_channels=m.out_channels, kernel_size=m.kernel_size,
+                         stride=m.stride, padding=m.padding, dilation=m.dilation, groups=m.groups, bias=True)
+        self.weight_bits, self.input_bits = weight_bits, input_bits
+        self.aq_learnable, self.wq_learnable, self.symmetric = aq_learnable, wq_learnable, symmetric
+        self.input_quant_fn = LsqQuantizer4img(bit=input_bits, all_positive=(symmetric == False), learnable=aq_learnable)  # noqa: E712
+        self.pretrained_initialized = pretrained_initialized
+        if pretrained_initialized != False:  # noqa: E712
+            self.weight = nn.Parameter(m.weight.detach())
+            if m.bias is not None:
+                self.bias = nn.Parameter(m.bias.detach())
+        self.lsqw_fn = LsqQuantizer4Conv2d(bit=self.weight_bits, learnable=aq_learnable).to(m.weight.device)
+        self.move_b4 = LearnableBias4img(224 * 224)
+        self.move_aft = LearnableBias4img(224 * 224)
+
+    def forward(self, input):
+        weight = self.lsqw_fn(self.weight)
+        input = self.move_aft(self.input_quant_fn(self.move_b4(input)))
+        return F.conv2d(input, weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+
+
+class LSQ_QLinear4head(nn.Linear):
+    """qlinear.py:193-252: the 8-bit classifier heads (torch-composed)."""
+
+    def __init__(self, *kargs, m: nn.Linear, weight_bits=8, input_bits=8, aq_learnable=True, wq_learnable=True,
+                 symmetric=True, weight_channelwise=True, input_channelwise=True, weight_quant_method="statsq",
+                 input_quant_method="lsq", pretrained_initialized=False, **kwargs):
+        super().__init__(m.in_features, m.out_features, bias=True)
+        self.weight_bits, self.input_bits = weight_bits, input_bits
+        self.aq_learnable, self.wq_learnable, self.symmetric = aq_learnable, wq_learnable, symmetric
+        self.weight_quant_method = weight_quant_method
+        self.input_quant_fn = LsqQuantizer4head_input(bit=input_bits, all_positive=(symmetric == False), learnable=aq_learnable)  # noqa: E712
+        self.pretrained_initialized = pretrained_initialized
+        if pretrained_initialized != False:  # noqa: E712
+            self.weight = nn.Parameter(m.weight.detach())
+            if m.bias is not None:
+                self.bias = nn.Parameter(m.bias.detach())
+        if weight_quant_method == "lsq":
+            self.lsqw_fn = LsqQuantizerWeight(bit=self.weight_bits, per_channel=weight_channelwise, learnable=wq_learnable).to(m.weight.device)
+        else:
+            raise ValueError("Unknown quant_method")
+        self.move_b4 = LearnableBias(self.weight.shape[1])
+        self.move_aft = LearnableBias(self.weight.shape[1])
+
+    def forward(self, input):
+        weight = self.lsqw_fn(self.weight)
+        input = self.move_aft(self.input_quant_fn(self.move_b4(input)))
+        out = F.linear(input, weight)
+        return out + self.bias.view(1, -1).expand_as(out)

@@ -1,0 +1,421 @@
+"""GPU parity tests of the individual sm_100a kernels against the CPU oracle (same seeded inputs).
+Integer codes and freeze masks: bit-exact. Floating-point outputs: tolerance written next to each check."""
+import math
+
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import ofq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from ofq_b200 import _lib, ops
+    assert _lib.load().ofq_device_ok() == 1, "B200 (sm_100) required: " + _lib.load().ofq_last_error().decode()
+    return ops
+
+
+def dev(t):
+    return t.cuda().contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ StatsQ
+@pytest.mark.parametrize("bits", [2, 3, 4])
+def test_statsq_codes_dyadic_exact(ops, bits):
+    """Weights on a dyadic grid: row sums are exact in any order => zero code mismatches allowed."""
+    torch.manual_seed(0)
+    w = torch.round(torch.randn(300, 384) / 8 * 1024) / 1024
+    codes, colscale, sf, _, mm = ops.statsq_codes(dev(w), bits, want_minmax=True)
+    rc, rsf = O.statsq_codes(w, bits)
+    assert torch.equal(sf.cpu(), rsf.squeeze(1))
+    assert torch.equal(codes.cpu().int(), rc)
+    n = 2 ** (bits - 1)
+    assert torch.equal(colscale.cpu(), rsf.squeeze(1) / (2 * n))
+    k = (rc - 1) // 2
+    assert mm.cpu().tolist() == [int(k.min()), int(k.max())]
+
+
+@pytest.mark.parametrize("bits", [2, 4])
+def test_statsq_codes_random_only_ties(ops, bits):
+    """Random fp32 weights: the scale may differ by an ulp (summation order), so a code may flip only when
+    the pre-round value sits within 1e-5 of a rounding boundary (SURVEY.md §7 hard part 3)."""
+    torch.manual_seed(1)
+    w = torch.nn.init.trunc_normal_(torch.empty(1536, 384), std=0.02)
+    codes, colscale, sf, _, _ = ops.statsq_codes(dev(w), bits)
+    rc, rsf = O.statsq_codes(w, bits)
+    assert rel_err(sf.cpu(), rsf.squeeze(1)) < 1e-6
+    assert (sf.cpu() - rsf.squeeze(1)).abs().max() <= 2 * torch.finfo(torch.float32).eps * rsf.abs().max()
+    bad = codes.cpu().int() != rc
+    if bad.any():
+        b4, _ = O.statsq_pre_round(w, bits)
+        frac = (b4[bad] - torch.floor(b4[bad]) - 0.5).abs()
+        assert frac.max() < 1e-5, "a non-tie code mismatch"
+    assert bad.float().mean() < 1e-5
+
+
+def test_statsq_golden_and_colterm(ops):
+    g = load_golden("statsq")
+    for bits, exp in ((2, [1, -1, 1, -3, 1, 1, 3, -3]), (3, [1, -3, 3, -5, 1, 1, 7, -7]), (4, [3, -5, 7, -9, 1, 1, 15, -15])):
+        codes, colscale, sf, _, _ = ops.statsq_codes(dev(g["kat.w"]), bits)
+        assert codes.cpu().tolist() == [exp]
+        assert sf.item() == pytest.approx(0.7625, rel=1e-6)
+    w = g["rand.w"]
+    aft = torch.randn(w.shape[1]) * 0.1
+    bias = torch.randn(w.shape[0])
+    codes, colscale, sf, colterm, _ = ops.statsq_codes(dev(w), 2, aft=dev(aft), bias=dev(bias))
+    ref = colscale.cpu() * (codes.cpu().float() @ aft) + bias
+    assert rel_err(colterm.cpu(), ref) < 1e-6      # fp32 dot of <=40 terms
+
+
+# ------------------------------------------------------------------------------------------------ LSQ
+def _g(hi, count):
+    return 1.0 / ((hi * count) ** 0.5)
+
+
+def test_lsq_effective_scale_bit_exact(ops):
+    torch.manual_seed(2)
+    a = torch.rand(1188) * 0.2
+    a[:5] = torch.tensor([1e-7, 1e-5, 0.0, -1.0, 1.0000001e-5])
+    for g in (_g(1, 128 * 384), _g(3, 25344), 0.123):
+        out = ops.lsq_effective_scale(dev(a), g)
+        ref = O.grad_scaled(O.floor_clip(a), g)
+        assert torch.equal(out.cpu(), ref)
+
+
+@pytest.mark.parametrize("bit,pos", [(2, False), (2, True), (3, False), (4, False), (4, True)])
+def test_lsq_codes_rows_bit_exact(ops, bit, pos):
+    torch.manual_seed(3)
+    B, N, Cc = 4, 198, 384
+    x = torch.randn(B, N, Cc)
+    if pos:
+        x = torch.nn.functional.gelu(x)
+    b4 = torch.randn(Cc) * 0.05
+    lo, hi = O.lsq_levels(bit, pos)
+    s = O.lsq_init_rows(x + b4, hi, pos) * torch.linspace(0.4, 1.6, N)
+    g = _g(hi, B * Cc)
+    se = ops.lsq_effective_scale(dev(s), g)
+    codes = ops.lsq_quant(dev(x).view(B * N, Cc), dev(b4), se, ops.PER_ROW, N, 1, lo, hi)
+    ref = O.lsq_codes_rows(x + b4, s, bit, pos)
+    assert torch.equal(codes.cpu().int().view(B, N, Cc), ref)
+    assert ref.min() == lo and ref.max() == hi
+
+
+def test_lsq_codes_qkx_segments_and_cols(ops):
+    """(B, N*H, C) view of qkx: scale per (token, head), shift of length H*C (attention.py:201-206);
+    LsqQuantizer4v: scale per channel."""
+    torch.manual_seed(4)
+    B, N, H, Cc = 3, 50, 3, 64
+    lo, hi = O.lsq_levels(2, False)
+    x = torch.randn(B, N, H * Cc)
+    b4 = torch.randn(H * Cc) * 0.1
+    xs = (x + b4).reshape(B, N * H, Cc)
+    s = O.lsq_init_rows(xs, hi, False) * torch.linspace(0.5, 1.5, N * H)
+    g = _g(hi, B * Cc)
+    codes = ops.lsq_quant(dev(x).view(B * N, H * Cc), dev(b4), ops.lsq_effective_scale(dev(s), g), ops.PER_ROW, N, H, lo, hi)
+    ref = O.lsq_codes_rows(xs, s, 2, False).reshape(B, N, H * Cc)
+    assert torch.equal(codes.cpu().int().view(B, N, H * Cc), ref)
+    # per-channel
+    xv = torch.randn(B, N, Cc)
+    b4v = torch.randn(Cc) * 0.1
+    sv = O.lsq_init_cols(xv + b4v, hi, False) * torch.linspace(0.5, 1.5, Cc)
+    gv = _g(hi, B * N)
+    codes = ops.lsq_quant(dev(xv).view(B * N, Cc), dev(b4v), ops.lsq_effective_scale(dev(sv), gv), ops.PER_COL, 1, 1, lo, hi)
+    se = O.grad_scaled(O.floor_clip(sv), gv)
+    ref = torch.round(torch.clamp((xv + b4v) / se, lo, hi)).int()
+    assert torch.equal(codes.cpu().int().view(B, N, Cc), ref)
+
+
+@pytest.mark.parametrize("cols,nseg,mode", [(384, 1, 0), (1536, 1, 0), (3 * 192, 3, 0), (384, 1, 1), (96, 1, 0)])
+def test_lsq_backward(ops, cols, nseg, mode):
+    torch.manual_seed(5)
+    B, N = 3, 70
+    bit, pos = 2, False
+    lo, hi = O.lsq_levels(bit, pos)
+    seg = cols // nseg
+    x = torch.randn(B, N, cols)
+    b4 = (torch.randn(cols) * 0.05).requires_grad_(True)
+    aft = torch.zeros(cols, requires_grad=True)
+    dy = torch.randn(B, N, cols)
+    xin = x.clone().requires_grad_(True)
+    if mode == 0:
+        xs = (xin + b4).reshape(B, N * nseg, seg)
+        s = (O.lsq_init_rows(xs.detach(), hi, pos) * torch.linspace(0.4, 1.6, N * nseg)).requires_grad_(True)
+        y = O.lsq_rows(xs, s, bit, pos).reshape(B, N, cols) + aft
+        g = _g(hi, B * seg)
+        period = N
+    else:
+        xs = xin + b4
+        s = (O.lsq_init_cols(xs.detach(), hi, pos) * torch.linspace(0.4, 1.6, cols)).requires_grad_(True)
+        y = O.lsq_cols(xs, s, bit, pos) + aft
+        g = _g(hi, B * N)
+        period = 1
+    y.backward(dy)
+    se = ops.lsq_effective_scale(dev(s.detach()), g)
+    dx, ds, db4, daft = ops.lsq_bwd(dev(dy).view(B * N, cols), dev(x).view(B * N, cols), dev(b4.detach()), se, mode,
+                                    period, nseg, lo, hi, g)
+    mine = dx.cpu().view(B, N, cols)
+    assert torch.equal(mine == 0, xin.grad == 0)                      # the STE clamp mask is exact
+    assert rel_err(mine, xin.grad) < 1e-6                             # autograd computes (dy*s)/s, we pass dy
+    assert rel_err(ds.cpu(), s.grad) < 1e-5                           # fp32 sums in a different order
+    assert rel_err(db4.cpu(), b4.grad) < 1e-5
+    assert rel_err(daft.cpu(), aft.grad) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ GEMM engine
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (1584, 192, 192), (25344, 384, 384), (777, 200, 1536), (198, 198, 64)])
+def test_gemm_i8_exact(ops, M, N, K):
+    torch.manual_seed(6)
+    A = torch.randint(-8, 8, (M, K), dtype=torch.int8, device="cuda")
+    Bm = torch.randint(-15, 16, (N, K), dtype=torch.int8, device="cuda")
+    ld = ops.round_up(N, 4)
+    out = torch.full((M, ld), float("nan"), device="cuda")
+    ops.gemm(ops.GEMM_I8, A, (K, 0, 0, 0), Bm, (K, 0, 0, 0), out, (ld, 0, 0), M, N, K)
+    ref = A.double() @ Bm.double().T
+    assert torch.equal(out[:, :N].double(), ref)                      # int32 accumulation is exact
+    rs = torch.rand(198, device="cuda") + 0.5
+    cs = torch.rand(N, device="cuda") + 0.5
+    rt = torch.randn(198, device="cuda")
+    ct = torch.randn(N, device="cuda")
+    ops.gemm(ops.GEMM_I8, A, (K, 0, 0, 0), Bm, (K, 0, 0, 0), out, (ld, 0, 0), M, N, K,
+             rs=ops.vec(rs, 198), cs=ops.vec(cs), rt=ops.vec(rt, 198), ct=ops.vec(ct))
+    idx = torch.arange(M, device="cuda") % 198
+    ref2 = ref * rs[idx].double()[:, None] * cs.double()[None] + rt[idx].double()[:, None] * ct.double()[None]
+    assert rel_err(out[:, :N], ref2) < 1e-6                           # two fp32 roundings in the epilogue
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(384, 1536, 25344, 8), (25344, 384, 1536, 1), (500, 72, 200, 1), (64, 384, 198 * 4, 3)])
+def test_gemm_bf16(ops, M, N, K, splits):
+    torch.manual_seed(7)
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    Bm = torch.randint(-3, 4, (N, K), device="cuda").bfloat16()
+    out = torch.zeros((M, N), device="cuda")
+    ops.gemm(ops.GEMM_BF16, A, (K, 0, 0, 0), Bm, (K, 0, 0, 0), out, (N, 0, 0), M, N, K, splits=splits, accumulate=splits > 1)
+    ref = A.double() @ Bm.double().T
+    assert rel_err(out, ref) < 1e-5                                   # fp32 accumulation of exact bf16 products
+
+
+def test_gemm_batched_attention_layout(ops):
+    """scores GEMM of QKR attention: A = x codes [b][n][c] shared over heads, B = qkx codes [b][d][h][c]."""
+    torch.manual_seed(8)
+    Bt, H, Nt, Cc = 3, 6, 198, 384
+    qx = torch.randint(-2, 2, (Bt, Nt, Cc), dtype=torch.int8, device="cuda")
+    qk = torch.randint(-2, 2, (Bt, Nt, H, Cc), dtype=torch.int8, device="cuda")
+    S = torch.empty(Bt, H, Nt, 208, device="cuda")
+    ops.gemm(ops.GEMM_I8, qx, (Cc, 0, 0, Nt * Cc), qk, (H * Cc, 0, Cc, Nt * H * Cc), S, (208, Nt * 208, H * Nt * 208),
+             Nt, Nt, Cc, nb1=H, nb2=Bt)
+    ref = torch.einsum("bnc,bdhc->bhnd", qx.double(), qk.double())
+    assert torch.equal(S[..., :Nt].double(), ref)
+
+
+def test_gemm_outer_k_accumulate(ops):
+    """k2 outer-K loop (sum over heads) with bf16 operands."""
+    torch.manual_seed(9)
+    Bt, H, Nt, Cc, NP = 2, 3, 50, 64, 56
+    dS = torch.zeros(Bt, H, Nt, NP, device="cuda")
+    dS[..., :Nt] = torch.randn(Bt, H, Nt, Nt, device="cuda")
+    kT = torch.zeros(Bt, H, Cc, NP, device="cuda")
+    kT[..., :Nt] = torch.randint(-2, 2, (Bt, H, Cc, Nt), device="cuda").float()
+    out = torch.empty(Bt, Nt, Cc, device="cuda")
+    ops.gemm(ops.GEMM_BF16, dS.bfloat16(), (NP, Nt * NP, H * Nt * NP, 0), kT.bfloat16(), (NP, Cc * NP, H * Cc * NP, 0),
+             out, (Cc, Nt * Cc, 0), Nt, Cc, Nt, k2=H, nb1=Bt)
+    ref = torch.einsum("bhnd,bhcd->bnc", dS.bfloat16().double(), kT.double())
+    assert rel_err(out, ref) < 1e-5
+    # hi/lo planes: A laid out [b][plane][h], B indexed with k2 % H; and an operand shared by all slices
+    hi = dS.bfloat16()
+    lo = (dS - hi.float()).bfloat16()
+    A2 = torch.stack((hi, lo), dim=1).contiguous()                       # [B, 2, H, N, NP]
+    ops.gemm(ops.GEMM_BF16, A2, (NP, Nt * NP, 2 * H * Nt * NP, 0), kT.bfloat16(), (NP, Cc * NP, H * Cc * NP, 0),
+             out, (Cc, Nt * Cc, 0), Nt, Cc, Nt, k2=2 * H, nb1=Bt, b_k2mod=H)
+    ref2 = torch.einsum("bhnd,bhcd->bnc", dS.double(), kT.double())
+    assert rel_err(out, ref2) < 2e-5
+    A3 = torch.stack((hi[:, 0], lo[:, 0]), dim=0).contiguous()           # [2, B, N, NP], head 0 only
+    ops.gemm(ops.GEMM_BF16, A3, (NP, Bt * Nt * NP, Nt * NP, 0), kT.bfloat16()[:, 0].contiguous(), (NP, 0, Cc * NP, 0),
+             out, (Cc, Nt * Cc, 0), Nt, Cc, Nt, k2=2, nb1=Bt)
+    assert rel_err(out, torch.einsum("bnd,bcd->bnc", dS[:, 0].double(), kT[:, 0].double())) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ prep kernels
+def test_grad_prep_and_code_conversions(ops):
+    torch.manual_seed(10)
+    nb, R, Cc = 3, 198, 384
+    x = torch.randn(nb, R, Cc, device="cuda")
+    cs = torch.rand(Cc, device="cuda") + 0.5
+    rs = torch.rand(R, device="cuda") + 0.5
+    u = torch.randn(Cc, device="cuda")
+    o = ops.grad_prep(x, nb, R, Cc, Cc, R * Cc, cs=cs, rs=rs, rs_period=R, want_rm=True, want_t=True, want_colsum=True,
+                      u=u, group=64)
+    assert torch.equal(o["rm"][0], (x * cs).bfloat16())
+    t_ref = torch.zeros(nb, Cc, o["r_pad"], device="cuda", dtype=torch.bfloat16)
+    t_ref[..., :R] = (x * rs[None, :, None]).bfloat16().transpose(1, 2)
+    assert torch.equal(o["t"][0], t_ref)
+    o2 = ops.grad_prep(x, nb, R, Cc, Cc, R * Cc, cs=cs, rs=rs, rs_period=R, want_rm=True, want_t=True, planes=2)
+    assert torch.equal(o2["rm"][0], o["rm"][0]) and torch.equal(o2["t"][0], o["t"][0])
+    assert rel_err(o2["rm"][0].float() + o2["rm"][1].float(), x * cs) < 2e-5      # hi + lo: ~16 mantissa bits
+    assert rel_err((o2["t"][0].float() + o2["t"][1].float())[..., :R], (x * rs[None, :, None]).transpose(1, 2)) < 2e-5
+    assert rel_err(o["colsum"], x.sum((0, 1))) < 1e-5
+    assert rel_err(o["rowdot"], (x * u).view(nb, R, Cc // 64, 64).sum(-1).transpose(1, 2)) < 1e-5
+    o32 = ops.grad_prep(x, nb, R, Cc, Cc, R * Cc, u=u, group=32)
+    assert rel_err(o32["rowdot"], (x * u).view(nb, R, Cc // 32, 32).sum(-1).transpose(1, 2)) < 1e-5
+    rd = ops.codes_rowdot(torch.randint(-2, 2, (500, 6 * 64), dtype=torch.int8, device="cuda"), 6, u)
+    assert rd.shape == (500, 6)
+    codes = torch.randint(-8, 8, (nb, R, Cc), dtype=torch.int8, device="cuda")
+    rd = ops.codes_rowdot(codes.view(nb * R, Cc), 6, u)
+    assert rel_err(rd, (codes.float() * u).view(nb * R, 6, 64).sum(-1)) < 1e-5
+    assert torch.equal(ops.codes_to_bf16(codes, nb, R, Cc, Cc, R * Cc, False), codes.bfloat16())
+    tb = ops.codes_to_bf16(codes, nb, R, Cc, Cc, R * Cc, True)
+    assert torch.equal(tb[..., :R], codes.bfloat16().transpose(1, 2)) and bool((tb[..., R:] == 0).all())
+    ti = ops.codes_transpose(codes, nb, R, Cc, Cc, R * Cc)
+    assert torch.equal(ti[..., :R], codes.transpose(1, 2)) and bool((ti[..., R:] == 0).all())
+
+
+# ------------------------------------------------------------------------------------------------ softmax
+@pytest.mark.parametrize("N,H,bit", [(198, 6, 2), (49, 3, 3), (197, 3, 4)])
+def test_softmax_quant_forward(ops, N, H, bit):
+    torch.manual_seed(11)
+    B = 4
+    lo, hi = O.lsq_levels(bit, True)
+    ld = ops.round_up(N, 4)
+    S = torch.randn(B * H, N, ld) * 2
+    prob_ref = torch.softmax(S[..., :N], dim=-1).view(B, H, N, N)
+    s = O.lsq_init_rows(prob_ref, hi, True) * torch.linspace(0.5, 1.5, N)
+    g = _g(hi, B * H * N)
+    se = ops.lsq_effective_scale(dev(s), g)
+    P, codes, rowsum = ops.softmax_quant(dev(S), N, H, se, hi)
+    Pc = P.cpu()[..., :N].view(B, H, N, N)
+    assert rel_err(Pc, prob_ref) < 1e-6                                 # expf / sum order differ by ulps
+    # codes are exact for the probabilities the kernel itself produced ...
+    ref_codes = O.lsq_codes_rows(Pc, s, bit, True)
+    mine = codes.cpu()[..., :N].int().view(B, H, N, N)
+    assert torch.equal(mine, ref_codes)
+    assert bool((codes.cpu()[..., N:] == 0).all())
+    # ... and differ from the codes of torch's own softmax only at rounding ties (SURVEY.md §7 hard part 4)
+    ref2 = O.lsq_codes_rows(prob_ref, s, bit, True)
+    bad = mine != ref2
+    if bad.any():
+        se_c = se.cpu().view(1, 1, N, 1)
+        v = (prob_ref / se_c)[bad]
+        assert ((v - torch.floor(v) - 0.5).abs() < 1e-4).all()
+    assert bad.float().mean() < 1e-4
+    assert rel_err(rowsum.cpu().view(B, H, N), ref_codes.float().sum(-1) * se.cpu().view(1, 1, N)) < 1e-6
+
+
+def test_softmax_quant_bias_mask(ops):
+    torch.manual_seed(12)
+    B, nW, H, N = 8, 4, 3, 49
+    S = torch.randn(B * H, N, 52)
+    bias = torch.randn(H, N, N)
+    mask = (torch.rand(nW, N, N) > 0.7).float() * -100.0
+    se = torch.full((N,), 0.02)
+    P, codes, _ = ops.softmax_quant(dev(S), N, H, dev(se), 3, bias=dev(bias), mask=dev(mask), nW=nW)
+    logits = S[..., :N].view(B, H, N, N) + bias[None] + mask[torch.arange(B) % nW][:, None]
+    assert rel_err(P.cpu()[..., :N].view(B, H, N, N), torch.softmax(logits, -1)) < 1e-6
+
+
+def test_softmax_quant_backward(ops):
+    torch.manual_seed(13)
+    B, H, N, bit = 3, 2, 70, 2
+    lo, hi = O.lsq_levels(bit, True)
+    ld = 72
+    S = (torch.randn(B, H, N, N) * 2).requires_grad_(True)
+    alpha = 0.125
+    prob = torch.softmax(S * alpha, dim=-1)
+    s = (O.lsq_init_rows(prob.detach(), hi, True) * torch.linspace(0.5, 1.5, N)).requires_grad_(True)
+    pq = O.lsq_rows(prob, s, bit, True)
+    dPq = torch.randn(B, H, N, N)
+    pq.backward(dPq)
+    g = _g(hi, B * H * N)
+    se = ops.lsq_effective_scale(dev(s.detach()), g)
+    Sp = torch.zeros(B * H, N, ld)
+    Sp[..., :N] = (S.detach() * alpha).view(B * H, N, N)
+    P, codes, _ = ops.softmax_quant(dev(Sp), N, H, se, hi)
+    dP = torch.zeros(B * H, N, ld)
+    dP[..., :N] = dPq.view(B * H, N, N)
+    ca = torch.rand(H, N) + 0.5
+    rb = torch.rand(N) + 0.5
+    out_a, out_bt, ldo, colsum, d_s, ds32 = ops.softmax_quant_bwd(dev(dP), P, N, H, se, hi, alpha, g, dev(ca), True, dev(rb),
+                                                                  want_ds32=True)
+    dS = ds32.cpu()[..., :N].view(B, H, N, N) * alpha
+    assert rel_err(dS, S.grad) < 1e-5
+    assert rel_err(d_s.cpu(), s.grad) < 1e-4
+    assert rel_err(colsum.cpu().view(B, H, N), dS.sum(2)) < 1e-4
+    ra = (dS * ca.view(1, H, 1, N)).bfloat16().float()
+    assert rel_err(out_a.cpu()[..., :N].float().view(B, H, N, N), ra) < 1e-3      # bf16 output rounding
+    rbt = (dS * rb.view(1, 1, N, 1)).bfloat16().float().transpose(2, 3)
+    assert rel_err(out_bt.cpu()[..., :N].float().view(B, H, N, N), rbt) < 1e-3
+    a2, bt2, _, _, _, _ = ops.softmax_quant_bwd(dev(dP), P, N, H, se, hi, alpha, g, dev(ca), True, dev(rb), planes=2)
+    assert a2.shape == (B, 2, H, N, ldo)
+    assert rel_err((a2[:, 0].float() + a2[:, 1].float()).cpu()[..., :N], dS * ca.view(1, H, 1, N)) < 2e-5
+    assert rel_err((bt2[:, 0].float() + bt2[:, 1].float()).cpu()[..., :N], (dS * rb.view(1, 1, N, 1)).transpose(2, 3)) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ W_qk
+def test_wqk_compose(ops):
+    torch.manual_seed(14)
+    H, hd, Cc = 6, 64, 384
+    wq = torch.randn(H * hd, Cc) * 0.02
+    wk = torch.randn(H * hd, Cc) * 0.02
+    out = ops.wqk_compose(dev(wq), dev(wk), H)
+    ref = O.wqk_compose(wq.double(), wk.double(), H)
+    assert rel_err(out.cpu(), ref) < 1e-6                               # fp32 FMA chain over 64 terms
+    d = torch.randn(H * Cc, Cc)
+    wq_, wk_ = wq.clone().double().requires_grad_(True), wk.clone().double().requires_grad_(True)
+    O.wqk_compose(wq_, wk_, H).backward(d.double())
+    dwq, dwk = ops.wqk_compose_bwd(dev(d), dev(wq), dev(wk), H)
+    assert rel_err(dwq.cpu(), wq_.grad) < 1e-6 and rel_err(dwk.cpu(), wk_.grad) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ CGA
+@pytest.mark.parametrize("bits,br", [(2, 0.005), (3, 0.005), (4, 0.05)])
+def test_cga_mask_bit_exact(ops, bits, br):
+    g = load_golden("cga")
+    m = ops.cga_mask(dev(g["w"]), bits, br)
+    key = f"mask.b{bits}.br{br}"
+    if key in g:
+        assert torch.equal(m.cpu().float(), g[key])                    # reference's own mask
+    torch.manual_seed(15)
+    w = torch.round(torch.nn.init.trunc_normal_(torch.empty(384, 1536), std=0.02) * 2 ** 16) / 2 ** 16  # dyadic
+    m = ops.cga_mask(dev(w), bits, br)
+    assert torch.equal(m.cpu().float(), O.cga_freeze_mask(w, bits, br))
+
+
+def test_cga_masked_adamw(ops):
+    g = load_golden("cga")
+    for step in range(3):
+        # every step starts from the reference's own previous state so that one-ulp AdamW differences do not
+        # accumulate into a different mask
+        if step == 0:
+            w = dev(g["w"].clone())
+            m = torch.zeros_like(w)
+            v = torch.zeros_like(w)
+        else:
+            w = dev(g[f"step{step - 1}.w"].clone())
+            m = dev(g[f"step{step - 1}.exp_avg"].clone())
+            v = dev(g[f"step{step - 1}.exp_avg_sq"].clone())
+        mask = torch.empty(w.shape, dtype=torch.uint8, device="cuda")
+        before = w.clone()
+        ops.cga_adamw_(w, dev(g[f"step{step}.grad"]), m, v, step + 1, 1e-3, 0.9, 0.999, 1e-8, 0.05, bits=2,
+                       boundary_range=0.05, mask_out=mask)
+        assert torch.equal(mask.cpu().float(), g[f"step{step}.mask"])
+        frozen = mask.bool()
+        assert torch.equal(w[frozen], before[frozen])                   # frozen weights untouched bit-for-bit
+        assert torch.equal(w.cpu()[frozen.cpu()], g[f"step{step}.w"][frozen.cpu()])
+        assert rel_err(w.cpu(), g[f"step{step}.w"]) < 1e-6
+        assert rel_err(m.cpu(), g[f"step{step}.exp_avg"]) < 1e-6
+        assert rel_err(v.cpu(), g[f"step{step}.exp_avg_sq"]) < 1e-6
+    # unmasked path == torch.optim.AdamW
+    p = torch.randn(1000, device="cuda")
+    ref = torch.nn.Parameter(p.clone().cpu())
+    opt = torch.optim.AdamW([ref], lr=3e-3, weight_decay=0.01)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    for step in range(4):
+        gr = torch.randn(1000)
+        ref.grad = gr.clone()
+        opt.step()
+        ops.cga_adamw_(p, dev(gr), m, v, step + 1, 3e-3, 0.9, 0.999, 1e-8, 0.01)
+    assert rel_err(p.cpu(), ref.detach()) < 1e-6
