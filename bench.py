@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Headline benchmark: QAT images/sec of the DeiT-S W2A2 attn_q (QKR) step on B200, synthetic 224x224 data.
+
+    python bench.py --gpus N --steps K --warmup W             # this framework (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU fp32 fake-quant path (oracle port)
+
+One "step" = forward + loss + backward (+ NCCL gradient all-reduce for N > 1) + fused AdamW update of one batch of
+128 images per GPU (weak scaling: global batch 128*N; BASELINE.json config 3 is 1024 on 8 GPUs).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how every field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "QAT images/sec, DeiT-S W2A2 attn_q (QKR) step, synthetic 224x224"
+UNIT = "images/s"
+MODELS = {"deit_small": dict(embed_dim=384, depth=12, num_heads=6), "deit_tiny": dict(embed_dim=192, depth=12, num_heads=3)}
+# forward GFLOP per image in the quantized GEMMs of the hot path; a QAT step is 3x
+GFLOP_FWD_PER_IMG = {"deit_small": 13.74, "deit_tiny": 3.00}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ofq_b200", choices=["ofq_b200", "reference"])
+    ap.add_argument("--model", default="deit_small", choices=list(MODELS))
+    ap.add_argument("--batch", type=int, default=128, help="images per GPU")
+    ap.add_argument("--bits", type=int, default=2)
+    ap.add_argument("--no-qkr", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="images per CPU-baseline step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", default="on", choices=["on", "off"],
+                    help="capture the whole QAT step (fwd+bwd+all-reduce+AdamW) in one CUDA graph and replay it")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"{a.model.replace('_', '-')} distilled W{a.bits}A{a.bits} attn_q {'plain' if a.no_qkr else 'QKR'} QAT step "
+            f"(fwd+bwd+AdamW), batch {a.batch}/GPU, synthetic 224x224, random init")
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_step_rate(a, steps, warmup, threads):
+    """The reference's CPU path for this workload, restated in oracle/ofq_oracle.py (the reference itself is
+    Python that needs /root/reference and timm, neither of which exists on the GPU box): fp32 fake-quant forward,
+    autograd backward and AdamW on a bounded sample of `--cpu-batch` images."""
+    import torch
+    import torch.nn.functional as F
+
+    import ofq_b200.quantization as Q
+    from ofq_b200.host.deit import DistilledVisionTransformer
+    from oracle import ofq_oracle as O
+
+    torch.set_num_threads(threads)
+    cfg = MODELS[a.model]
+    torch.manual_seed(0)
+    # parameter dictionary with the reference's key names, taken from a (CPU-constructed) host model
+    model = DistilledVisionTransformer(num_classes=1000, **cfg)
+    names = Q.deit_qmodule_names(cfg["depth"])
+    model = Q.replace_module_by_qmodule_deit(model, Q.make_qconfigs(names, a.bits, a.bits), pretrained_initialized=True,
+                                             qk_reparam=not a.no_qkr)
+    P = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    del model
+    img = torch.randn(a.cpu_batch, 3, 224, 224)
+    labels = torch.randint(0, 1000, (a.cpu_batch,))
+    state = {}
+    with torch.no_grad():
+        O.deit_forward(img, P, cfg["depth"], cfg["num_heads"], a.bits, a.bits, not a.no_qkr, state)   # creates the LSQ scales
+    params = [p for p in P.values() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=5.47e-4, weight_decay=0.05)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        cls, dist = O.deit_forward(img, P, cfg["depth"], cfg["num_heads"], a.bits, a.bits, not a.no_qkr, state)
+        loss = F.cross_entropy(cls, labels) + F.cross_entropy(dist, labels)
+        loss.backward()
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return a.cpu_batch * len(times) / total, total / len(times)
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps = max(1, min(a.steps, 6))
+    warm = max(1, min(a.warmup, 2))
+    ips, sec = cpu_step_rate(a, steps, warm, threads)
+    sample = f"{a.cpu_batch} images/step x {steps} steps (oracle port of the reference CPU fp32 path, torch {threads} threads)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": workload_name(a), "sample": sample},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.index = index
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference_arm(a)
+
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+
+    import ofq_b200.quantization as Q
+    from ofq_b200 import _lib, ops
+    from ofq_b200.cga import CGAAdamW, param_groups_weight_decay
+    from ofq_b200.host.deit import DistilledVisionTransformer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert _lib.load().ofq_device_ok() == 1, _lib.load().ofq_last_error().decode()
+
+    cfg = MODELS[a.model]
+    torch.manual_seed(0)                      # identical initial weights on every rank
+    model = DistilledVisionTransformer(num_classes=1000, **cfg)
+    names = Q.deit_qmodule_names(cfg["depth"])
+    model = Q.replace_module_by_qmodule_deit(model, Q.make_qconfigs(names, a.bits, a.bits), pretrained_initialized=True,
+                                             qk_reparam=not a.no_qkr, qk_reparam_type=0).to(dev)
+    gen = torch.Generator().manual_seed(1234 + rank)
+    B = a.batch
+    h_img = torch.randn(B, 3, 224, 224, generator=gen).pin_memory()
+    h_lbl = torch.randint(0, 1000, (B,), generator=gen).pin_memory()
+    d_img, d_lbl = h_img.to(dev), h_lbl.to(dev)
+
+    model.eval()
+    with torch.no_grad():
+        model(d_img)                           # setup_alpha (train.py:997-1010): creates the LSQ step sizes
+    if world > 1:                              # the step sizes are data dependent: make them identical on all ranks
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    model.train()
+    opt = CGAAdamW(param_groups_weight_decay(model, 0.05, model.no_weight_decay()), lr=5.47e-4)
+    params = [p for p in model.parameters() if p.requires_grad]
+    flat = None
+    if world > 1:
+        # data-parallel gradient exchange: ONE NCCL all-reduce (mean) of a flat fp32 gradient buffer per step
+        # (train.py:727 uses torch DDP; same collective, same bytes). Every .grad is a view into the buffer.
+        flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+        off = 0
+        for p in params:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def step(img, lbl):
+        if flat is None:
+            opt.zero_grad(set_to_none=True)
+        else:
+            flat.zero_()
+        (cls, dst), _ = model(img)
+        loss = F.cross_entropy(cls, lbl) + F.cross_entropy(dst, lbl)
+        (loss / world if world > 1 else loss).backward()
+        if flat is not None:
+            dist.all_reduce(flat)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step(d_img, d_lbl)
+    run = step
+    launches_per_step = None
+    if a.graph == "on":
+        static_img, static_lbl = d_img.clone(), d_lbl.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                step(static_img, static_lbl)
+        torch.cuda.current_stream().wait_stream(side)
+        barrier()
+        if flat is None:
+            opt.zero_grad(set_to_none=True)
+        graph = torch.cuda.CUDAGraph()
+        l0 = ops.LAUNCHES
+        with torch.cuda.graph(graph):
+            static_loss = step(static_img, static_lbl)
+        launches_per_step = ops.LAUNCHES - l0
+        barrier()
+
+        def run(img, lbl):
+            if img is not static_img:
+                static_img.copy_(img, non_blocking=True)
+                static_lbl.copy_(lbl, non_blocking=True)
+            graph.replay()
+            return static_loss
+
+        d_img, d_lbl = static_img, static_lbl
+        for _ in range(2):
+            run(d_img, d_lbl)
+    # ---- timed region 1: inputs resident in HBM
+    barrier()
+    launches0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        t_host0 = time.perf_counter()
+        for _ in range(a.steps):
+            run(d_img, d_lbl)
+        host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / a.steps
+        e1.record()
+        barrier()
+    launches = ops.LAUNCHES - launches0 if launches_per_step is None else launches_per_step * a.steps
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = ms.item()
+    # ---- timed region 2: end to end (pinned host -> device every step, loss read back every step)
+    barrier()
+    e0.record()
+    last = 0.0
+    for _ in range(a.steps):
+        if a.graph == "on":
+            last = run(h_img, h_lbl).item()
+        else:
+            last = run(h_img.to(dev, non_blocking=True), h_lbl.to(dev, non_blocking=True)).item()
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    # ---- instrumented steps: per-kernel CUDA-event timing on the launching stream (share of the step per family)
+    roof = None
+    nprof = 3
+    if rank == 0:
+        ops.PROFILE = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(nprof):              # eager (un-graphed) steps on every rank; only rank 0 records events
+        step(d_img, d_lbl)
+    ev1.record()
+    barrier()
+    if rank == 0:
+        fam = {}
+        for name, s0, s1, nbytes, nflops in ops.PROFILE:
+            f = fam.setdefault(name, [0.0, 0, 0.0, 0.0])
+            f[0] += s0.elapsed_time(s1)
+            f[1] += 1
+            f[2] += nbytes
+            f[3] += nflops
+        ops.PROFILE = None
+        step_ms = ev0.elapsed_time(ev1) / nprof
+        peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            j = json.loads(pk.read_text())
+            peaks = {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j.get("bf16_tflops_sustained", j["bf16_tflops"]),
+                     "source": "MEASURED_PEAKS.json (copy GB/s; sustained cuBLAS bf16)"}
+        top = max(fam.items(), key=lambda kv: kv[1][0])
+        name, (tms, cnt, nbytes, nflops) = top
+        t_hbm = nbytes / (peaks["hbm_gbs"] * 1e9)
+        tensor_peak = peaks["bf16_tflops"] * (2.0 if name == "gemm_i8" else 1.0) * 1e12     # int8 = 2x the bf16 rate
+        t_tensor = nflops / tensor_peak
+        traffic = None
+        tf = ROOT / "profiles" / "traffic.json"
+        if tf.exists():
+            traffic = json.loads(tf.read_text()).get(name)
+        if t_hbm >= t_tensor:
+            ach = nbytes / (tms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]}
+        else:
+            ach = nflops / (tms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": ach, "peak": tensor_peak / 1e12, "unit": "TFLOP/s", "frac": ach / (tensor_peak / 1e12)}
+        roof.update({"traffic": traffic, "kernel": name, "launches_per_step": cnt / nprof, "avg_launch_us": tms / cnt * 1e3,
+                     "share_of_step": tms / nprof / step_ms, "peak_source": peaks["source"],
+                     "families_ms_per_step": {k: round(v[0] / nprof, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])},
+                     "families_gbps": {k: round(v[2] / (v[0] * 1e-3) / 1e9, 1) for k, v in fam.items() if v[0] > 0},
+                     "instrumented_step_ms": step_ms})
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        ips, sec = cpu_step_rate(a, 4, 1, threads)
+        cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{a.cpu_batch} images/step x 4 steps of the same model (oracle port, torch {threads} threads, {sec:.2f} s/step)"}
+    imgs = B * world * a.steps
+    value = imgs / (ms_total * 1e-3)
+    e2e = imgs / (ms2.item() * 1e-3)
+    flops_step = 3 * GFLOP_FWD_PER_IMG[a.model] * 1e9 * B
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int8 codes fwd (s32 accumulate) / bf16 hi+lo bwd (f32 accumulate), f32 activations",
+        "data": "synthetic",
+        "config": {"workload": workload_name(a), "global_batch": B * world, "parallelism": f"dp{world}",
+                   "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush",
+                   "optimizer": "fused AdamW lr 5.47e-4 wd 0.05", "cuda_graph": a.graph == "on", "host_enqueue_ms_per_step": host_enqueue_ms, "bwd_planes": int(os.environ.get("OFQ_BWD_PLANES", "2")),
+                   "quantized_gemm_tflops_per_gpu": flops_step / (ms_total / a.steps * 1e-3) / 1e12},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": (h_img.numel() * 4 + h_lbl.numel() * 8) * world,
+                "d2h_bytes_per_step": 4 * world, "last_loss": last},
+        "gpu_launches": launches,
+        "clocks": clk.summary(),
+        "roofline": roof,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

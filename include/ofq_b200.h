@@ -184,13 +184,16 @@ OFQ_API int ofq_wqk_compose_bwd(const float* dwqk, const float* wq, const float*
  * ofq_cga_adamw updates p, exp_avg, exp_avg_sq in place in ONE pass: frozen elements see a zero gradient
  * (moments decay, weight untouched bit-for-bit); bits == 0 disables masking (plain AdamW for the other params).
  * rowstat: float[rows] scratch for the per-row StatsQ scale; kminmax: int32[2] scratch.
+ * step_dev: optional device int32 holding the optimizer step t (used instead of `step` so that a captured CUDA
+ * graph can be replayed; advance it with ofq_counter_increment once per optimizer step).
  */
 OFQ_API int ofq_cga_mask(const float* w, int rows, int cols, int bits, double boundary_range, uint8_t* mask,
                          float* rowstat, int* kminmax, void* stream);
 OFQ_API int ofq_cga_adamw(float* p, const float* grad, float* exp_avg, float* exp_avg_sq, long long numel,
                           int rows, int cols, int step, double lr, double beta1, double beta2, double eps,
                           double weight_decay, int bits, double boundary_range, float* rowstat, int* kminmax,
-                          uint8_t* mask_out, void* stream);
+                          uint8_t* mask_out, const int* step_dev, void* stream);
+OFQ_API int ofq_counter_increment(int* counter, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,96 @@
+"""AdamW with the confidence-guided-annealing (CGA) weight freeze fused into the update.
+
+Reference semantics (cga.py:953-1013 around torch.optim.AdamW, driven by timm's create_optimizer_v2):
+after backward, for every masked weight a freeze mask is built from the StatsQ pre-round value
+(freeze_outside_boundary_weight_idx, cga.py:450-469), the gradients of frozen weights are zeroed, the frozen
+weights are stashed, AdamW steps, and the frozen weights are restored.  Here all of that is ONE kernel pass per
+parameter (ofq_cga_adamw): frozen elements see a zero gradient (their moments decay exactly as AdamW-with-zero-grad)
+and keep their value bit-for-bit.  With no masked parameters this is a plain fused AdamW (train.py:662, 933).
+"""
+from __future__ import annotations
+
+from typing import Iterable, Optional
+
+import torch
+
+from . import ops
+
+
+def cga_masked_parameter_names(model: torch.nn.Module, qk_reparam: bool = True, model_type: str = "deit"):
+    """Weights the reference masks, by module-name suffix (cga.py:956-980)."""
+    names = []
+    for k, m in model.named_modules():
+        if not hasattr(m, "weight") or getattr(m, "weight", None) is None or m.weight.dim() != 2:
+            continue
+        if qk_reparam and model_type == "swin":
+            hit = k.endswith(("fc1", "fc2", ".v", "proj", "reduction"))
+        elif qk_reparam:
+            hit = "blocks" in k and k.endswith(("fc1", "fc2", ".v", "proj"))
+        else:
+            hit = "blocks" in k and k.endswith(("fc1", "fc2", "qkv", "proj"))
+        if hit:
+            names.append(k + ".weight")
+    return names
+
+
+def param_groups_weight_decay(model: torch.nn.Module, weight_decay: float, no_weight_decay=()):
+    """timm 0.5.4 `add_weight_decay` (used by create_optimizer_v2, train.py:662): 1-D parameters, `.bias` and the
+    names in `no_weight_decay()` get no decay."""
+    decay, no_decay = [], []
+    for name, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        (no_decay if (p.ndim <= 1 or name.endswith(".bias") or name in no_weight_decay) else decay).append(p)
+    return [{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": weight_decay}]
+
+
+class CGAAdamW(torch.optim.Optimizer):
+    """torch.optim.AdamW-compatible optimizer whose step is the fused sm_100a kernel.
+
+    masked: iterable of parameters (2-D weights quantized by StatsQ) that take part in CGA; wq_bitw and
+    boundary_range as in `cga.py --wq-bitw --boundaryRange`. Leave `masked` empty for ordinary QAT training."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, masked: Optional[Iterable] = None,
+                 wq_bitw: int = 2, boundary_range: float = 0.005):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._masked = {id(p) for p in (masked or ())}
+        self.wq_bitw = wq_bitw
+        self.boundary_range = boundary_range
+        self.last_masks = {}
+        self.keep_masks = False
+        self.launches = 0
+        self._step_dev = None      # device-resident step counter: the whole step can be captured in a CUDA graph
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        if self._step_dev is None:
+            dev = next(p for g in self.param_groups for p in g["params"]).device
+            self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        ops.counter_increment_(self._step_dev)
+        for group in self.param_groups:
+            b1, b2 = group["betas"]
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st["step"] += 1
+                masked = id(p) in self._masked
+                if masked and "scratch" not in st:
+                    st["scratch"] = (torch.empty(p.shape[0], dtype=torch.float32, device=p.device),
+                                     torch.empty(2, dtype=torch.int32, device=p.device))
+                mask_out = None
+                if masked and self.keep_masks:
+                    mask_out = torch.empty(p.shape, dtype=torch.uint8, device=p.device)
+                    self.last_masks[id(p)] = mask_out
+                grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                ops.cga_adamw_(p.data, grad, st["exp_avg"], st["exp_avg_sq"], st["step"], group["lr"], b1, b2,
+                               group["eps"], group["weight_decay"], bits=self.wq_bitw if masked else 0,
+                               boundary_range=self.boundary_range, scratch=st.get("scratch"), mask_out=mask_out,
+                               step_dev=self._step_dev)
+                self.launches += 3 if masked else 1
+        return loss

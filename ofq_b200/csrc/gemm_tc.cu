@@ -47,21 +47,45 @@ struct SmemLayout {
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr uint32_t OUT_OFF = STAGES * STAGE_BYTES;          // 4 warps x 2 x (32 x 128 B), swizzled
     static constexpr uint32_t OUT_BYTES = 4 * 2 * 4096;
-    static constexpr uint32_t VEC_OFF = OUT_OFF + OUT_BYTES;            // cs[BN], ct[BN]
-    static constexpr uint32_t BAR_OFF = VEC_OFF + 2 * BN * 4;
-    static constexpr uint32_t TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16;
+    static constexpr uint32_t VEC_OFF = OUT_OFF + OUT_BYTES;            // 2 x {cs[BN], ct[BN]} (double buffered)
+    static constexpr uint32_t BAR_OFF = VEC_OFF + 2 * 2 * BN * 4;
+    static constexpr uint32_t TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
     static constexpr size_t DYN_BYTES = TOTAL + 1024;                   // slack for 1024 B alignment
 };
 
+struct TileCoord {
+    int m0, n0, b1, b2, split, it_begin, nit;
+};
+
+// tile index -> coordinates; consecutive indices share the A (row) block so that it is re-read from L2
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t, int BN_, int mtiles, int ntiles) {
+    TileCoord c;
+    const int nb = t % ntiles; t /= ntiles;
+    const int mb = t % mtiles; t /= mtiles;
+    const int nbatch = p.nb1 * p.nb2;
+    const int z = t % nbatch;
+    c.split = t / nbatch;
+    c.b1 = z % p.nb1; c.b2 = z / p.nb1;
+    c.m0 = mb * BM; c.n0 = nb * BN_;
+    const int total_it = p.k2 * p.kblocks;
+    c.it_begin = (int)((long long)total_it * c.split / p.splits);
+    c.nit = (int)((long long)total_it * (c.split + 1) / p.splits) - c.it_begin;
+    return c;
+}
+
+// Persistent, warp-specialised: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The smem ring runs
+// across tile boundaries and the TMEM accumulator is double buffered, so the epilogue of tile i overlaps the TMA
+// loads and MMAs of tile i+1.
 template <int KIND, int BN, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmC, const GemmParams p, const int num_tiles,
+               const int mtiles, const int ntiles) {
     using L = SmemLayout<BN, STAGES>;
     constexpr uint32_t A_BYTES = L::A_BYTES;
     constexpr uint32_t STAGE_BYTES = L::STAGE_BYTES;
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two");
+    constexpr uint32_t ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));   // per accumulator stage
+    constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
     constexpr uint32_t UMMA_K_BYTES = 32;  // 32 int8 or 16 bf16 per MMA
     constexpr uint32_t IDESC = KIND == 0 ? umma_idesc(2u, 1u, BM, BN)   // S32 acc, signed int8
                                          : umma_idesc(1u, 1u, BM, BN);  // F32 acc, bf16
@@ -71,24 +95,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                ~static_cast<uintptr_t>(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* acc_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
-    float* cs_s = reinterpret_cast<float*>(smem + L::VEC_OFF);
-    float* ct_s = cs_s + BN;
+    uint64_t* acc_full = empty_bar + STAGES;     // [2] MMA -> epilogue
+    uint64_t* acc_empty = acc_full + 2;          // [2] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* vec_s = reinterpret_cast<float*>(smem + L::VEC_OFF);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
-    // batch / split decode
-    const int nbatch = p.nb1 * p.nb2;
-    const int z = blockIdx.z % nbatch;
-    const int split = blockIdx.z / nbatch;
-    const int b1 = z % p.nb1, b2 = z / p.nb1;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-    const int total_it = p.k2 * p.kblocks;
-    const int it_begin = (int)((long long)total_it * split / p.splits);
-    const int it_end = (int)((long long)total_it * (split + 1) / p.splits);
-    const int nit = it_end - it_begin;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -98,7 +111,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(acc_bar, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], 4);         // one arrival per epilogue warp
+        }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -113,111 +129,134 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         if (elect_one()) {
             const int kelem = KIND == 0 ? KBYTES : KBYTES / 2;
-            for (int i = 0; i < nit; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (i / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                const int it = it_begin + i;
-                const int k2i = it / p.kblocks, kb = it % p.kblocks;
-                uint8_t* sa = smem + s * STAGE_BYTES;
-                uint8_t* sb = sa + A_BYTES;
-                mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-                tma_load_5d(sa, &tmA, &full_bar[s], kb * kelem, m0, (k2i % p.a_k2mod) * p.a_k2, b1 * p.a_b1, b2 * p.a_b2);
-                tma_load_5d(sb, &tmB, &full_bar[s], kb * kelem, n0, (k2i % p.b_k2mod) * p.b_k2, b1 * p.b_b1, b2 * p.b_b2);
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);
+                for (int i = 0; i < c.nit; ++i, ++it) {
+                    const uint32_t s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    const int g = c.it_begin + i;
+                    const int k2i = g / p.kblocks, kb = g % p.kblocks;
+                    uint8_t* sa = smem + s * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                    tma_load_5d(sa, &tmA, &full_bar[s], kb * kelem, c.m0, (k2i % p.a_k2mod) * p.a_k2, c.b1 * p.a_b1, c.b2 * p.a_b2);
+                    tma_load_5d(sb, &tmB, &full_bar[s], kb * kelem, c.n0, (k2i % p.b_k2mod) * p.b_k2, c.b1 * p.b_b1, c.b2 * p.b_b2);
+                }
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            for (int i = 0; i < nit; ++i) {
-                const int s = i % STAGES;
-                const uint32_t ph = (i / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+            uint32_t it = 0, tc = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tc) {
+                const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);
+                const uint32_t as = tc & 1, aph = (tc >> 1) & 1;
+                mbar_wait(&acc_empty[as], aph ^ 1);       // epilogue has drained this accumulator stage
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-                const uint64_t adesc = umma_desc_kmajor_sw128(sa);
-                const uint64_t bdesc = umma_desc_kmajor_sw128(sa + A_BYTES);
+                const uint32_t tmem_d = tmem_base + as * ACC_COLS;
+                for (int i = 0; i < c.nit; ++i, ++it) {
+                    const uint32_t s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t adesc = umma_desc_kmajor_sw128(sa);
+                    const uint64_t bdesc = umma_desc_kmajor_sw128(sa + A_BYTES);
 #pragma unroll
-                for (uint32_t kk = 0; kk < KBYTES / UMMA_K_BYTES; ++kk) {
-                    const uint64_t adv = (kk * UMMA_K_BYTES) >> 4;
-                    if (KIND == 0)
-                        umma_i8(tmem_base, adesc + adv, bdesc + adv, IDESC, (i | kk) != 0);
-                    else
-                        umma_f16(tmem_base, adesc + adv, bdesc + adv, IDESC, (i | kk) != 0);
+                    for (uint32_t kk = 0; kk < KBYTES / UMMA_K_BYTES; ++kk) {
+                        const uint64_t adv = (kk * UMMA_K_BYTES) >> 4;
+                        if (KIND == 0)
+                            umma_i8(tmem_d, adesc + adv, bdesc + adv, IDESC, (i | kk) != 0);
+                        else
+                            umma_f16(tmem_d, adesc + adv, bdesc + adv, IDESC, (i | kk) != 0);
+                    }
+                    tc_commit(&empty_bar[s]);      // frees the smem stage when these MMAs retire
                 }
-                tc_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+                tc_commit(&acc_full[as]);          // accumulator of this tile complete
             }
-            tc_commit(acc_bar);            // accumulator complete
         }
     } else {
         // ---- epilogue: warps 2..5 own TMEM lane quarters (warp % 4)
         const int q = warp & 3;
-        const int m = m0 + q * 32 + lane;
-        const bool rank1 = p.has_rank1 && split == 0;
-        {   // stage the column vectors of this tile once
-            const long long cs_off = (long long)b1 * p.cs.bs1 + (long long)b2 * p.cs.bs2;
-            const long long ct_off = (long long)b1 * p.ct.bs1 + (long long)b2 * p.ct.bs2;
-            for (int j = threadIdx.x - 64; j < BN; j += 128) {
-                const int n = n0 + j;
-                const bool ok = n < p.N;
-                cs_s[j] = ok ? (p.cs.p ? __ldg(p.cs.p + cs_off + n) : 1.0f) : 0.f;
-                ct_s[j] = (ok && rank1) ? (p.ct.p ? __ldg(p.ct.p + ct_off + n) : 1.0f) : 0.f;
-            }
-            named_bar_sync(1, 128);
-        }
-        const long long rs_off = (long long)b1 * p.rs.bs1 + (long long)b2 * p.rs.bs2;
-        const long long rt_off = (long long)b1 * p.rt.bs1 + (long long)b2 * p.rt.bs2;
-        const bool row_ok = m < p.M;
-        const float rsv = row_ok ? (p.rs.p ? __ldg(p.rs.p + rs_off + (m % p.rs.period)) : 1.0f) : 0.f;
-        const float rtv = (row_ok && rank1) ? (p.rt.p ? __ldg(p.rt.p + rt_off + (m % p.rt.period)) : 1.0f) : 0.f;
         uint8_t* stage_base = smem + L::OUT_OFF + q * 2 * 4096;
-
-        if (nit > 0) {
-            mbar_wait(acc_bar, 0);
-            tc_fence_after();
-        }
-        int chunk = 0;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32, ++chunk) {
-            if (n0 + c0 >= p.N) break;  // warp-uniform
-            uint32_t r[32];
-            if (nit > 0) {
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
-                tmem_ld_wait();
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0;
-            }
-            uint8_t* buf = stage_base + (chunk & 1) * 4096;
-            if (chunk >= 2) {  // the staging buffer used two chunks ago must have been read by TMA
-                if (lane == 0) tma_store_wait_read<1>();
-                __syncwarp();
-            }
-            // row `lane` of the 32x32 fp32 box, 128B-swizzled: 16-byte chunk j lands at j ^ (lane % 8)
-            float4* rowp = reinterpret_cast<float4*>(buf + lane * 128);
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-                float o[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int j = 4 * j4 + e;
-                    const float acc = KIND == 0 ? static_cast<float>(static_cast<int32_t>(r[j]))
-                                                : __uint_as_float(r[j]);
-                    o[e] = acc * rsv * cs_s[c0 + j] + rtv * ct_s[c0 + j];
+        uint32_t tc = 0, chunk = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tc) {
+            const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);
+            const uint32_t as = tc & 1, aph = (tc >> 1) & 1;
+            const bool rank1 = p.has_rank1 && c.split == 0;
+            float* cs_s = vec_s + as * 2 * BN;
+            float* ct_s = cs_s + BN;
+            {   // stage the column vectors of this tile (double buffered by accumulator stage)
+                const long long cs_off = (long long)c.b1 * p.cs.bs1 + (long long)c.b2 * p.cs.bs2;
+                const long long ct_off = (long long)c.b1 * p.ct.bs1 + (long long)c.b2 * p.ct.bs2;
+                for (int j = threadIdx.x - 64; j < BN; j += 128) {
+                    const int n = c.n0 + j;
+                    const bool ok = n < p.N;
+                    cs_s[j] = ok ? (p.cs.p ? __ldg(p.cs.p + cs_off + n) : 1.0f) : 0.f;
+                    ct_s[j] = (ok && rank1) ? (p.ct.p ? __ldg(p.ct.p + ct_off + n) : 1.0f) : 0.f;
                 }
-                rowp[j4 ^ (lane & 7)] = make_float4(o[0], o[1], o[2], o[3]);
+                named_bar_sync(1, 128);
             }
-            fence_proxy_async_smem();
+            const int m = c.m0 + q * 32 + lane;
+            const bool row_ok = m < p.M;
+            const long long rs_off = (long long)c.b1 * p.rs.bs1 + (long long)c.b2 * p.rs.bs2;
+            const long long rt_off = (long long)c.b1 * p.rt.bs1 + (long long)c.b2 * p.rt.bs2;
+            const float rsv = row_ok ? (p.rs.p ? __ldg(p.rs.p + rs_off + (m % p.rs.period)) : 1.0f) : 0.f;
+            const float rtv = (row_ok && rank1) ? (p.rt.p ? __ldg(p.rt.p + rt_off + (m % p.rt.period)) : 1.0f) : 0.f;
+
+            if (c.nit > 0) {
+                mbar_wait(&acc_full[as], aph);
+                tc_fence_after();
+            }
+            const uint32_t tmem_acc = tmem_base + as * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (c.n0 + c0 >= p.N) break;  // warp-uniform
+                uint32_t r[32];
+                if (c.nit > 0) {
+                    tmem_ld_32x32(tmem_acc + c0, r);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0;
+                }
+                uint8_t* buf = stage_base + (chunk & 1) * 4096;
+                if (chunk >= 2) {  // the staging buffer used two chunks ago must have been read by TMA
+                    if (lane == 0) tma_store_wait_read<1>();
+                    __syncwarp();
+                }
+                ++chunk;
+                // row `lane` of the 32x32 fp32 box, 128B-swizzled: 16-byte chunk j lands at j ^ (lane % 8)
+                float4* rowp = reinterpret_cast<float4*>(buf + lane * 128);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    float o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int j = 4 * j4 + e;
+                        const float acc = KIND == 0 ? static_cast<float>(static_cast<int32_t>(r[j]))
+                                                    : __uint_as_float(r[j]);
+                        o[e] = acc * rsv * cs_s[c0 + j] + rtv * ct_s[c0 + j];
+                    }
+                    rowp[j4 ^ (lane & 7)] = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (p.atomic)
+                        tma_reduce_add_5d(&tmC, buf, c.n0 + c0, c.m0 + q * 32, 0, c.b1 * p.c_b1, c.b2 * p.c_b2);
+                    else
+                        tma_store_5d(&tmC, buf, c.n0 + c0, c.m0 + q * 32, 0, c.b1 * p.c_b1, c.b2 * p.c_b2);
+                    tma_store_commit();
+                }
+            }
+            // all TMEM reads of this tile are complete: hand the accumulator stage back to the MMA warp
+            tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                if (p.atomic)
-                    tma_reduce_add_5d(&tmC, buf, n0 + c0, m0 + q * 32, 0, b1 * p.c_b1, b2 * p.c_b2);
-                else
-                    tma_store_5d(&tmC, buf, n0 + c0, m0 + q * 32, 0, b1 * p.c_b1, b2 * p.c_b2);
-                tma_store_commit();
-            }
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
         }
         if (lane == 0) tma_store_wait_all<0>();
-        tc_fence_before();
     }
     __syncthreads();
     if (warp == 1) {
@@ -231,14 +270,21 @@ template <int KIND, int BN, int STAGES>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                        const GemmParams& p, cudaStream_t stream) {
     constexpr size_t smem = SmemLayout<BN, STAGES>::DYN_BYTES;
+    static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
     auto kern = gemm_tc_kernel<KIND, BN, STAGES>;
     static bool configured = false;  // per instantiation; attribute is per function, idempotent
     if (!configured) {
         OFQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, p.nb1 * p.nb2 * p.splits);
-    kern<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, tmC, p);
+    const int mtiles = (p.M + BM - 1) / BM, ntiles = (p.N + BN - 1) / BN;
+    const long long tiles = (long long)mtiles * ntiles * p.nb1 * p.nb2 * p.splits;
+    if (tiles > 0x7fffffff) {
+        ofq_set_error("ofq_gemm: too many tiles");
+        return OFQ_ERR_ARG;
+    }
+    const int grid = (int)(tiles < ofq_num_sms() ? tiles : ofq_num_sms());   // one persistent CTA per SM
+    kern<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, tmC, p, (int)tiles, mtiles, ntiles);
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }
@@ -332,10 +378,18 @@ extern "C" int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B
         ofq_set_error("ofq_gemm: split-K requires an accumulating (pre-zeroed) output");
         return OFQ_ERR_ARG;
     }
-    // tile width: widest tile that does not waste more than a quarter of its columns
-    int bn = N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
-    if (bn == 256 && (N % 256) != 0 && (N % 256) <= 128 && N < 512) bn = 128;
-    if (bn == 256 && (long long)((M + BM - 1) / BM) * ((N + 255) / 256) * nb1 * nb2 * splits < 148) bn = 128;
+    // tile width: fewest wasted columns first, then the widest tile (fewer re-reads of the row operand from L2)
+    static const int widths[] = {256, 192, 128, 64, 32};
+    int bn = 32;
+    long long best_cost = -1;
+    for (int w : widths) {
+        const long long nt = (N + w - 1) / w;
+        const long long padded = nt * w;
+        // cost ~ MMA columns issued; tie-break on wider tiles. Very small problems prefer more CTAs.
+        const long long ctas = (long long)((M + BM - 1) / BM) * nt * nb1 * nb2 * splits;
+        long long cost = padded * 16 + (ctas < 148 && w > 64 ? (148 - ctas) : 0) - w / 64;
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; bn = w; }
+    }
     CUtensorMap tmA, tmB, tmC;
     int rc = make_operand_map(&tmA, A, eb, M, K, k2, nb1, nb2, BM);
     if (rc) return rc;
@@ -347,9 +401,10 @@ extern "C" int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B
 #define OFQ_DISPATCH(KIND)                                                   \
     switch (bn) {                                                            \
         case 256: return launch_gemm<KIND, 256, 3>(tmA, tmB, tmC, p, st);    \
-        case 128: return launch_gemm<KIND, 128, 2>(tmA, tmB, tmC, p, st);    \
-        case 64:  return launch_gemm<KIND, 64, 4>(tmA, tmB, tmC, p, st);     \
-        default:  return launch_gemm<KIND, 32, 4>(tmA, tmB, tmC, p, st);     \
+        case 192: return launch_gemm<KIND, 192, 4>(tmA, tmB, tmC, p, st);    \
+        case 128: return launch_gemm<KIND, 128, 5>(tmA, tmB, tmC, p, st);    \
+        case 64:  return launch_gemm<KIND, 64, 6>(tmA, tmB, tmC, p, st);     \
+        default:  return launch_gemm<KIND, 32, 6>(tmA, tmB, tmC, p, st);     \
     }
     if (kind == OFQ_GEMM_I8) { OFQ_DISPATCH(0) } else { OFQ_DISPATCH(1) }
 #undef OFQ_DISPATCH

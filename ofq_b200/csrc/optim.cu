@@ -89,7 +89,10 @@ struct AdamScalars {
     float step_size;    // lr / (1 - beta1^t)
     float bc2_sqrt;     // sqrt(1 - beta2^t)
     float eps;
+    double lr, beta1_d, beta2_d;   // for the device-side step counter (CUDA-graph replay)
 };
+
+__global__ void counter_increment_kernel(int* c) { *c += 1; }
 
 // torch/optim/adamw.py::_single_tensor_adamw element-wise math.
 __device__ __forceinline__ void adamw_elem(float& p, float g, float& m, float& v, const AdamScalars& a, bool frozen) {
@@ -107,7 +110,18 @@ __global__ void __launch_bounds__(256)
 cga_adamw_kernel(float* __restrict__ p, const float* __restrict__ grad, float* __restrict__ m,
                  float* __restrict__ v, long long numel, int cols, float n_levels,
                  const float* __restrict__ rowstat, const int* __restrict__ kminmax, float lo_thr, float hi_thr,
-                 AdamScalars a, uint8_t* __restrict__ mask_out) {
+                 AdamScalars a, const int* __restrict__ step_dev, uint8_t* __restrict__ mask_out) {
+    if (step_dev) {   // bias corrections from a device-resident step count: the launch can be replayed by a CUDA graph
+        __shared__ float bc[2];
+        if (threadIdx.x == 0) {
+            const double t = (double)(*step_dev);
+            bc[0] = (float)(a.lr / (1.0 - pow(a.beta1_d, t)));
+            bc[1] = (float)sqrt(1.0 - pow(a.beta2_d, t));
+        }
+        __syncthreads();
+        a.step_size = bc[0];
+        a.bc2_sqrt = bc[1];
+    }
     const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i4 >= numel) return;
     int kmin = 0, kmax = 0;
@@ -169,8 +183,9 @@ extern "C" int ofq_cga_mask(const float* w, int rows, int cols, int bits, double
 extern "C" int ofq_cga_adamw(float* p, const float* grad, float* exp_avg, float* exp_avg_sq, long long numel,
                              int rows, int cols, int step, double lr, double beta1, double beta2, double eps,
                              double weight_decay, int bits, double boundary_range, float* rowstat, int* kminmax,
-                             uint8_t* mask_out, void* stream) {
-    OFQ_REQUIRE(p && grad && exp_avg && exp_avg_sq && numel > 0 && step >= 1, "ofq_cga_adamw: bad argument");
+                             uint8_t* mask_out, const int* step_dev, void* stream) {
+    OFQ_REQUIRE(p && grad && exp_avg && exp_avg_sq && numel > 0 && (step >= 1 || step_dev), "ofq_cga_adamw: bad argument");
+    if (step < 1) step = 1;
     OFQ_REQUIRE((uintptr_t)p % 16 == 0 && (uintptr_t)grad % 16 == 0 && (uintptr_t)exp_avg % 16 == 0 &&
                 (uintptr_t)exp_avg_sq % 16 == 0, "ofq_cga_adamw: tensors must be 16-byte aligned");
     OFQ_CHECK_ARCH();
@@ -183,6 +198,7 @@ extern "C" int ofq_cga_adamw(float* p, const float* grad, float* exp_avg, float*
     a.step_size = (float)(lr / (1.0 - std::pow(beta1, (double)step)));
     a.bc2_sqrt = (float)std::sqrt(1.0 - std::pow(beta2, (double)step));
     a.eps = (float)eps;
+    a.lr = lr; a.beta1_d = beta1; a.beta2_d = beta2;
     const unsigned grid = (unsigned)((numel + 1023) / 1024);
     if (bits > 0) {
         OFQ_REQUIRE(rows > 0 && cols > 0 && (long long)rows * cols == numel && rowstat && kminmax && bits >= 2 && bits <= 7,
@@ -192,11 +208,19 @@ extern "C" int ofq_cga_adamw(float* p, const float* grad, float* exp_avg, float*
         if (rc) return rc;
         cga_adamw_kernel<true><<<grid, 256, 0, st>>>(p, grad, exp_avg, exp_avg_sq, numel, cols, (float)(1 << (bits - 1)),
                                                      rowstat, kminmax, (float)(0.5 - boundary_range),
-                                                     (float)(0.5 + boundary_range), a, mask_out);
+                                                     (float)(0.5 + boundary_range), a, step_dev, mask_out);
     } else {
         cga_adamw_kernel<false><<<grid, 256, 0, st>>>(p, grad, exp_avg, exp_avg_sq, numel, 1, 1.f, nullptr, nullptr, 0.f,
-                                                      0.f, a, nullptr);
+                                                      0.f, a, step_dev, nullptr);
     }
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ofq_counter_increment(int* counter, void* stream) {
+    OFQ_REQUIRE(counter, "ofq_counter_increment: null pointer");
+    OFQ_CHECK_ARCH();
+    counter_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter);
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }

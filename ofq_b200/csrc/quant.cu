@@ -142,9 +142,9 @@ lsq_quant_kernel(const float* __restrict__ x, long long rows, int cols, long lon
 // ------------------------------------------------------------------------------------------- LSQ backward
 // Block = 8 warps, a contiguous range of rows; a warp walks its rows, lanes own fixed float4 columns of the
 // current 512-column chunk so that column partial sums stay in registers; per-(row,segment) partial sums
-// are reduced with shuffles. workspace = rowpart[rows*nseg] | colpart[nblk][3][cols].
+// are reduced with shuffles once per row and chunk. workspace = rowpart[rows*nseg] | colpart[nblk][3][cols].
 constexpr int kBwdChunk = 512;   // columns per register-resident chunk (4 float4 per lane)
-constexpr int kBwdRowsPerBlock = 64;
+constexpr int kBwdRowsPerBlock = 32;
 
 __host__ __device__ inline long long lsq_bwd_nblk(long long rows) {
     return (rows + kBwdRowsPerBlock - 1) / kBwdRowsPerBlock;
@@ -166,64 +166,72 @@ lsq_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __rest
         for (int i = threadIdx.x; i < 3 * kBwdChunk; i += blockDim.x) (&col_s[0][0])[i] = 0.f;
         __syncthreads();
         float a_aft[4][4], a_b4[4][4], a_s[4][4];
+        float4 b4v[4], s4v[4];
+        int segv[4];
+        bool okv[4];
 #pragma unroll
-        for (int p = 0; p < 4; ++p)
+        for (int p = 0; p < 4; ++p) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) a_aft[p][e] = a_b4[p][e] = a_s[p][e] = 0.f;
+            const int col = cbase + p * 128 + lane * 4;
+            okv[p] = col < cols;
+            segv[p] = okv[p] ? col / seg_len : -1;
+            b4v[p] = okv[p] ? __ldg(reinterpret_cast<const float4*>(b4 + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            s4v[p] = (okv[p] && scale_mode == OFQ_SCALE_PER_COL) ? __ldg(reinterpret_cast<const float4*>(s_eff + col))
+                                                                   : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+        const int chunk_end = min(cbase + kBwdChunk, cols) - 1;
+        const int seg_first = cbase / seg_len, seg_last = chunk_end / seg_len;     // block-uniform
 
         for (long long row = r0 + warp; row < r1; row += kWarpsPerBlock) {
-            const float* dyr = dy + row * lddy;
-            const float* xr = x + row * ldx;
-            float* dxr = dx + row * lddx;
+            const float* dyr = dy + row * lddy + cbase + lane * 4;
+            const float* xr = x + row * ldx + cbase + lane * 4;
+            float* dxr = dx + row * lddx + cbase + lane * 4;
             const long long srow = (row % period) * nseg;
+            float4 g4[4], x4[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {          // all loads of the row first: 8 x 16 B in flight per lane
+                if (okv[p]) {
+                    g4[p] = __ldg(reinterpret_cast<const float4*>(dyr + p * 128));
+                    x4[p] = __ldg(reinterpret_cast<const float4*>(xr + p * 128));
+                }
+            }
+            float part[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
-                const int pass0 = cbase + p * 128;            // warp-uniform
-                if (pass0 >= cols) break;
-                const int col = pass0 + lane * 4;
-                const bool ok = col < cols;
-                float part = 0.f;
-                int myseg = ok ? col / seg_len : -1;
-                if (ok) {
-                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(dyr + col));
-                    const float4 x4 = __ldg(reinterpret_cast<const float4*>(xr + col));
-                    const float4 b4v = __ldg(reinterpret_cast<const float4*>(b4 + col));
-                    float sv[4];
-                    if (scale_mode == OFQ_SCALE_PER_ROW) {
-                        const float s = __ldg(s_eff + srow + myseg);
-                        sv[0] = sv[1] = sv[2] = sv[3] = s;
-                    } else {
-                        const float4 s4 = __ldg(reinterpret_cast<const float4*>(s_eff + col));
-                        sv[0] = s4.x; sv[1] = s4.y; sv[2] = s4.z; sv[3] = s4.w;
-                    }
-                    const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
-                    const float xx[4] = {x4.x, x4.y, x4.z, x4.w};
-                    const float bb[4] = {b4v.x, b4v.y, b4v.z, b4v.w};
-                    float o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float v = __fdiv_rn(__fadd_rn(xx[e], bb[e]), sv[e]);
-                        const bool inside = (v >= qlo) && (v <= qhi);
-                        const float q = rintf(fminf(fmaxf(v, qlo), qhi));
-                        const float t = gg[e] * (inside ? (q - v) : q);
-                        o[e] = inside ? gg[e] : 0.f;
-                        a_aft[p][e] += gg[e];
-                        a_b4[p][e] += o[e];
-                        if (scale_mode == OFQ_SCALE_PER_ROW) part += t; else a_s[p][e] += t;
-                    }
-                    *reinterpret_cast<float4*>(dxr + col) = make_float4(o[0], o[1], o[2], o[3]);
-                }
+                if (!okv[p]) continue;
+                float sv[4] = {s4v[p].x, s4v[p].y, s4v[p].z, s4v[p].w};
                 if (scale_mode == OFQ_SCALE_PER_ROW) {
-                    const int pass_end = min(pass0 + 128, cols) - 1;
-                    const int seg_first = pass0 / seg_len, seg_last = pass_end / seg_len;   // warp-uniform
-                    for (int sg = seg_first; sg <= seg_last; ++sg) {
-                        const float v = warp_sum(myseg == sg ? part : 0.f);
-                        if (lane == 0) {
-                            float* dst = rowpart + row * nseg + sg;
-                            // the first pass that touches (row, sg) initialises it, later ones accumulate
-                            const bool first = (pass0 <= sg * seg_len);
-                            *dst = first ? v : (*dst + v);
-                        }
+                    const float s = __ldg(s_eff + srow + segv[p]);
+                    sv[0] = sv[1] = sv[2] = sv[3] = s;
+                }
+                const float gg[4] = {g4[p].x, g4[p].y, g4[p].z, g4[p].w};
+                const float xx[4] = {x4[p].x, x4[p].y, x4[p].z, x4[p].w};
+                const float bb[4] = {b4v[p].x, b4v[p].y, b4v[p].z, b4v[p].w};
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float v = __fdiv_rn(__fadd_rn(xx[e], bb[e]), sv[e]);
+                    const bool inside = (v >= qlo) && (v <= qhi);
+                    const float q = rintf(fminf(fmaxf(v, qlo), qhi));
+                    const float t = gg[e] * (inside ? (q - v) : q);
+                    o[e] = inside ? gg[e] : 0.f;
+                    a_aft[p][e] += gg[e];
+                    a_b4[p][e] += o[e];
+                    if (scale_mode == OFQ_SCALE_PER_ROW) part[p] += t; else a_s[p][e] += t;
+                }
+                *reinterpret_cast<float4*>(dxr + p * 128) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+            if (scale_mode == OFQ_SCALE_PER_ROW) {
+                for (int sg = seg_first; sg <= seg_last; ++sg) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) v += (segv[p] == sg) ? part[p] : 0.f;
+                    v = warp_sum(v);
+                    if (lane == 0) {
+                        float* dst = rowpart + row * nseg + sg;
+                        // the chunk that holds the first column of segment sg initialises it, later chunks accumulate
+                        *dst = (cbase <= sg * seg_len) ? v : (*dst + v);
                     }
                 }
             }
@@ -232,7 +240,7 @@ lsq_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __rest
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             const int lc = p * 128 + lane * 4;
-            if (cbase + lc < cols) {
+            if (okv[p]) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     atomicAdd(&col_s[0][lc + e], a_aft[p][e]);
@@ -253,31 +261,45 @@ lsq_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __rest
     }
 }
 
-__global__ void lsq_bwd_finalize_kernel(const float* __restrict__ rowpart, const float* __restrict__ colpart,
-                                        long long rows, int cols, int scale_mode, int period, int nseg, float g,
-                                        long long nblk, float* __restrict__ d_s, float* __restrict__ d_b4,
-                                        float* __restrict__ d_aft) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < cols) {
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        for (long long b = 0; b < nblk; ++b) {
-            const float* cp = colpart + b * 3 * cols;
-            s0 += cp[i];
-            s1 += cp[cols + i];
-            s2 += cp[2 * cols + i];
-        }
-        if (d_aft) d_aft[i] = s0;
-        if (d_b4) d_b4[i] = s1;
-        if (d_s && scale_mode == OFQ_SCALE_PER_COL) d_s[i] = g * s2;
+// Deterministic tree reductions of the partials: block = 32 outputs x 8 slices of the reduction axis.
+__global__ void __launch_bounds__(256)
+lsq_bwd_finalize_cols_kernel(const float* __restrict__ colpart, int cols, long long nblk, int scale_mode, float g,
+                             float* __restrict__ d_s, float* __restrict__ d_b4, float* __restrict__ d_aft) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + tx;
+    const int vecid = blockIdx.y;                     // 0: aft, 1: b4, 2: per-column scale
+    float acc = 0.f;
+    if (col < cols)
+        for (long long b = ty; b < nblk; b += 8) acc += colpart[(b * 3 + vecid) * cols + col];
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && col < cols) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][tx];
+        if (vecid == 0) { if (d_aft) d_aft[col] = s; }
+        else if (vecid == 1) { if (d_b4) d_b4[col] = s; }
+        else if (d_s && scale_mode == OFQ_SCALE_PER_COL) d_s[col] = g * s;
     }
-    if (d_s && scale_mode == OFQ_SCALE_PER_ROW) {
-        const long long nscale = (long long)min((long long)period, rows) * nseg;
-        if (i < nscale) {
-            float s = 0.f;
-            const long long stride = (long long)period * nseg;
-            for (long long j = i; j < rows * nseg; j += stride) s += rowpart[j];
-            d_s[i] = g * s;
-        }
+}
+
+__global__ void __launch_bounds__(256)
+lsq_bwd_finalize_rows_kernel(const float* __restrict__ rowpart, long long total, long long nscale, float g,
+                             float* __restrict__ d_s) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long i = (long long)blockIdx.x * 32 + tx;
+    float acc = 0.f;
+    if (i < nscale)
+        for (long long j = i + (long long)ty * nscale; j < total; j += 8 * nscale) acc += rowpart[j];
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && i < nscale) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][tx];
+        d_s[i] = g * s;
     }
 }
 
@@ -584,10 +606,13 @@ extern "C" int ofq_lsq_bwd_finalize(const float* workspace, long long rows, int 
     OFQ_CHECK_ARCH();
     const float* rowpart = workspace;
     const float* colpart = workspace + rows * nseg;
-    long long n = cols;
-    if (scale_mode == OFQ_SCALE_PER_ROW) n = n > (long long)period * nseg ? n : (long long)period * nseg;
-    lsq_bwd_finalize_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        rowpart, colpart, rows, cols, scale_mode, period, nseg, g, lsq_bwd_nblk(rows), d_s, d_b4, d_aft);
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 gridc((cols + 31) / 32, 3);
+    lsq_bwd_finalize_cols_kernel<<<gridc, 256, 0, st>>>(colpart, cols, lsq_bwd_nblk(rows), scale_mode, g, d_s, d_b4, d_aft);
+    if (d_s && scale_mode == OFQ_SCALE_PER_ROW) {
+        const long long nscale = (long long)(period < rows ? period : rows) * nseg;
+        lsq_bwd_finalize_rows_kernel<<<(unsigned)((nscale + 31) / 32), 256, 0, st>>>(rowpart, rows * nseg, nscale, g, d_s);
+    }
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }

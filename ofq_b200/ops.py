@@ -16,6 +16,27 @@ from ._lib import GemmOut, Operand, Vec, check
 GEMM_I8, GEMM_BF16 = 0, 1
 PER_ROW, PER_COL = 0, 1
 
+# Launch accounting (bench.py): LAUNCHES counts kernels launched through this module; when PROFILE is a list every
+# call is bracketed by CUDA events on the launching stream and recorded as
+# (family, start_event, end_event, algorithmic_bytes, algorithmic_flops).
+LAUNCHES = 0
+PROFILE = None
+
+
+def _call(family: str, nkernels: int, alg_bytes: float, alg_flops: float, fn, *args):
+    global LAUNCHES
+    LAUNCHES += nkernels
+    if PROFILE is None:
+        check(fn(*args))
+        return
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn(*args)
+    e1.record()
+    check(rc)
+    PROFILE.append((family, e0, e1, alg_bytes, alg_flops))
+
 
 def _cuda(*ts):
     for t in ts:
@@ -47,8 +68,16 @@ def gemm(kind: int, a: torch.Tensor, a_strides, b: torch.Tensor, b_strides, out:
     A = Operand(a.data_ptr(), a_strides[0], a_strides[1], a_k2mod, a_strides[2], a_strides[3])
     B = Operand(b.data_ptr(), b_strides[0], b_strides[1], b_k2mod, b_strides[2], b_strides[3])
     O = GemmOut(out.data_ptr(), *out_strides, 1 if accumulate else 0)
-    check(_lib.load().ofq_gemm(kind, C.byref(A), C.byref(B), C.byref(O), M, N, K, k2, nb1, nb2, splits,
-                               rs, cs, rt, ct, _st()))
+    eb = 1 if kind == GEMM_I8 else 2
+
+    def _n(strides, mod):
+        k2n = (min(mod, k2) if mod else k2) if strides[1] else 1
+        return k2n * (nb1 if strides[2] else 1) * (nb2 if strides[3] else 1)
+    nout = (nb1 if out_strides[1] else 1) * (nb2 if out_strides[2] else 1)
+    alg_bytes = eb * K * (M * _n(a_strides, a_k2mod) + N * _n(b_strides, b_k2mod)) + 4 * M * N * nout * (2 if accumulate else 1)
+    alg_flops = 2.0 * M * N * K * k2 * nb1 * nb2
+    _call("gemm_i8" if kind == GEMM_I8 else "gemm_bf16", 1, alg_bytes, alg_flops, _lib.load().ofq_gemm, kind,
+          C.byref(A), C.byref(B), C.byref(O), M, N, K, k2, nb1, nb2, splits, rs, cs, rt, ct, _st())
 
 
 # ------------------------------------------------------------------------------------------------ quantizers
@@ -68,9 +97,8 @@ def statsq_codes(w: torch.Tensor, bits: int, aft: Optional[torch.Tensor] = None,
         mm = torch.tensor([2 ** 31 - 1, -2 ** 31], dtype=torch.int32, device=w.device)
     if colterm is not None and aft is None:
         aft = torch.zeros(Cc, dtype=torch.float32, device=w.device)
-    check(_lib.load().ofq_statsq_codes(w.data_ptr(), R, Cc, w.stride(0), bits, codes.data_ptr(), Cc,
-                                       colscale.data_ptr(), sf.data_ptr(), _ptr(aft), _ptr(bias), _ptr(colterm),
-                                       _ptr(mm), _st()))
+    _call("statsq", 1, 5.0 * R * Cc, 0, _lib.load().ofq_statsq_codes, w.data_ptr(), R, Cc, w.stride(0), bits,
+          codes.data_ptr(), Cc, colscale.data_ptr(), sf.data_ptr(), _ptr(aft), _ptr(bias), _ptr(colterm), _ptr(mm), _st())
     return codes, colscale, sf, colterm, mm
 
 
@@ -78,7 +106,8 @@ def lsq_effective_scale(alpha: torch.Tensor, g: float) -> torch.Tensor:
     _cuda(alpha)
     a = alpha.detach().contiguous()
     out = torch.empty_like(a)
-    check(_lib.load().ofq_lsq_effective_scale(a.data_ptr(), a.numel(), float(g), out.data_ptr(), _st()))
+    _call("lsq_scale", 1, 8.0 * a.numel(), 0, _lib.load().ofq_lsq_effective_scale, a.data_ptr(), a.numel(), float(g),
+          out.data_ptr(), _st())
     return out
 
 
@@ -90,8 +119,8 @@ def lsq_quant(x2d: torch.Tensor, b4: torch.Tensor, s_eff: torch.Tensor, mode: in
     rows, cols = x2d.shape
     if out is None:
         out = torch.empty((rows, cols), dtype=torch.int8, device=x2d.device)
-    check(_lib.load().ofq_lsq_quant(x2d.data_ptr(), rows, cols, x2d.stride(0), b4.data_ptr(), s_eff.data_ptr(),
-                                    mode, period, nseg, qlo, qhi, out.data_ptr(), out.stride(0), _st()))
+    _call("lsq_quant", 1, 5.0 * rows * cols, 0, _lib.load().ofq_lsq_quant, x2d.data_ptr(), rows, cols, x2d.stride(0),
+          b4.data_ptr(), s_eff.data_ptr(), mode, period, nseg, qlo, qhi, out.data_ptr(), out.stride(0), _st())
     return out
 
 
@@ -104,15 +133,15 @@ def lsq_bwd(dy2d: torch.Tensor, x2d: torch.Tensor, b4: torch.Tensor, s_eff: torc
     lib = _lib.load()
     ws = torch.empty(lib.ofq_lsq_bwd_workspace(rows, cols, nseg), dtype=torch.float32, device=dy2d.device)
     dx = torch.empty((rows, cols), dtype=torch.float32, device=dy2d.device)
-    check(lib.ofq_lsq_bwd(dy2d.data_ptr(), dy2d.stride(0), x2d.data_ptr(), x2d.stride(0), rows, cols, b4.data_ptr(),
-                          s_eff.data_ptr(), mode, period, nseg, qlo, qhi, dx.data_ptr(), dx.stride(0),
-                          ws.data_ptr(), _st()))
+    _call("lsq_bwd", 1, 12.0 * rows * cols, 0, lib.ofq_lsq_bwd, dy2d.data_ptr(), dy2d.stride(0), x2d.data_ptr(),
+          x2d.stride(0), rows, cols, b4.data_ptr(), s_eff.data_ptr(), mode, period, nseg, qlo, qhi, dx.data_ptr(),
+          dx.stride(0), ws.data_ptr(), _st())
     ns = cols if mode == PER_COL else min(period, rows) * nseg
     d_s = torch.empty(ns, dtype=torch.float32, device=dy2d.device) if want_ds else None
     d_b4 = torch.empty(cols, dtype=torch.float32, device=dy2d.device)
     d_aft = torch.empty(cols, dtype=torch.float32, device=dy2d.device)
-    check(lib.ofq_lsq_bwd_finalize(ws.data_ptr(), rows, cols, mode, period, nseg, float(g), _ptr(d_s),
-                                   d_b4.data_ptr(), d_aft.data_ptr(), _st()))
+    _call("lsq_bwd_finalize", 1, 4.0 * ws.numel(), 0, lib.ofq_lsq_bwd_finalize, ws.data_ptr(), rows, cols, mode, period,
+          nseg, float(g), _ptr(d_s), d_b4.data_ptr(), d_aft.data_ptr(), _st())
     return dx, d_s, d_b4, d_aft
 
 
@@ -133,8 +162,9 @@ def grad_prep(x: torch.Tensor, nb: int, R: int, Cc: int, ldx: int, bstride: int,
     t = torch.empty((planes, nb, Cc, r_pad), dtype=torch.bfloat16, device=dev) if want_t else None
     colsum = torch.zeros(Cc, dtype=torch.float32, device=dev) if want_colsum else None
     rowdot = torch.empty((nb, Cc // group, R), dtype=torch.float32, device=dev) if u is not None else None
-    check(_lib.load().ofq_grad_prep(x.data_ptr(), nb, R, Cc, ldx, bstride, _ptr(cs), _ptr(rs), rs_period, planes,
-                                    _ptr(rm), Cc, _ptr(t), r_pad, _ptr(colsum), _ptr(u), group, _ptr(rowdot), _st()))
+    nbytes = nb * R * Cc * (4.0 + 2 * planes * (int(want_rm) + int(want_t)))
+    _call("grad_prep", 1, nbytes, 0, _lib.load().ofq_grad_prep, x.data_ptr(), nb, R, Cc, ldx, bstride, _ptr(cs), _ptr(rs),
+          rs_period, planes, _ptr(rm), Cc, _ptr(t), r_pad, _ptr(colsum), _ptr(u), group, _ptr(rowdot), _st())
     out.update(rm=rm, t=t, colsum=colsum, rowdot=rowdot)
     return out
 
@@ -145,12 +175,12 @@ def codes_to_bf16(codes: torch.Tensor, nb: int, R: int, Cc: int, ld: int, bstrid
     if transpose:
         r_pad = round_up(R, 8)
         out = torch.empty((nb, Cc, r_pad), dtype=torch.bfloat16, device=codes.device)
-        check(_lib.load().ofq_codes_to_bf16(codes.data_ptr(), nb, R, Cc, ld, bstride, out.data_ptr(), r_pad,
-                                            Cc * r_pad, 1, _st()))
+        _call("codes_to_bf16", 1, 3.0 * nb * R * Cc, 0, _lib.load().ofq_codes_to_bf16, codes.data_ptr(), nb, R, Cc, ld,
+              bstride, out.data_ptr(), r_pad, Cc * r_pad, 1, _st())
     else:
         out = torch.empty((nb, R, Cc), dtype=torch.bfloat16, device=codes.device)
-        check(_lib.load().ofq_codes_to_bf16(codes.data_ptr(), nb, R, Cc, ld, bstride, out.data_ptr(), Cc, R * Cc, 0,
-                                            _st()))
+        _call("codes_to_bf16", 1, 3.0 * nb * R * Cc, 0, _lib.load().ofq_codes_to_bf16, codes.data_ptr(), nb, R, Cc, ld,
+              bstride, out.data_ptr(), Cc, R * Cc, 0, _st())
     return out
 
 
@@ -159,8 +189,8 @@ def codes_transpose(codes: torch.Tensor, nb: int, R: int, Cc: int, ld: int, bstr
     _cuda(codes)
     r_pad = round_up(R, 16)
     out = torch.empty((nb, Cc, r_pad), dtype=torch.int8, device=codes.device)
-    check(_lib.load().ofq_codes_transpose(codes.data_ptr(), nb, R, Cc, ld, bstride, out.data_ptr(), r_pad, Cc * r_pad,
-                                          _st()))
+    _call("codes_transpose", 1, 2.0 * nb * R * Cc, 0, _lib.load().ofq_codes_transpose, codes.data_ptr(), nb, R, Cc, ld,
+          bstride, out.data_ptr(), r_pad, Cc * r_pad, _st())
     return out
 
 
@@ -169,8 +199,8 @@ def codes_rowdot(codes2d: torch.Tensor, nseg: int, u: torch.Tensor) -> torch.Ten
     _cuda(codes2d, u)
     rows, cols = codes2d.shape
     out = torch.empty((rows, nseg), dtype=torch.float32, device=codes2d.device)
-    check(_lib.load().ofq_codes_rowdot(codes2d.data_ptr(), rows, cols, codes2d.stride(0), nseg, u.data_ptr(),
-                                       out.data_ptr(), _st()))
+    _call("codes_rowdot", 1, 1.0 * rows * cols, 0, _lib.load().ofq_codes_rowdot, codes2d.data_ptr(), rows, cols,
+          codes2d.stride(0), nseg, u.data_ptr(), out.data_ptr(), _st())
     return out
 
 
@@ -184,8 +214,8 @@ def softmax_quant(S: torch.Tensor, N: int, H: int, s_eff: torch.Tensor, qhi: int
     P = torch.empty_like(S) if save_p else None
     codes = torch.empty((nz, N, ldq), dtype=torch.int8, device=S.device)
     rowsum = torch.empty((nz, N), dtype=torch.float32, device=S.device)
-    check(_lib.load().ofq_softmax_quant(S.data_ptr(), nz, N, ld, H, _ptr(bias), _ptr(mask), nW, s_eff.data_ptr(), qhi,
-                                        _ptr(P), codes.data_ptr(), ldq, rowsum.data_ptr(), _st()))
+    _call("softmax_quant", 1, nz * N * N * (5.0 + (4 if save_p else 0)), 0, _lib.load().ofq_softmax_quant, S.data_ptr(), nz,
+          N, ld, H, _ptr(bias), _ptr(mask), nW, s_eff.data_ptr(), qhi, _ptr(P), codes.data_ptr(), ldq, rowsum.data_ptr(), _st())
     return P, codes, rowsum
 
 
@@ -202,10 +232,10 @@ def softmax_quant_bwd(dPq: torch.Tensor, P: torch.Tensor, N: int, H: int, s_eff:
     colsum = torch.zeros((nz, N), dtype=torch.float32, device=dev)
     d_s = torch.zeros(N, dtype=torch.float32, device=dev)
     ds32 = torch.empty_like(P) if want_ds32 else None
-    check(_lib.load().ofq_softmax_quant_bwd(dPq.data_ptr(), P.data_ptr(), nz, N, ld, H, s_eff.data_ptr(), qhi,
-                                            float(alpha), float(g_s), _ptr(ca), 1 if ca_per_head else 0, _ptr(rb), planes,
-                                            out_a.data_ptr(), out_bt.data_ptr(), ldo, colsum.data_ptr(),
-                                            d_s.data_ptr(), _ptr(ds32), _st()))
+    _call("softmax_quant_bwd", 1, nz * N * N * (8.0 + 4 * planes + (4 if want_ds32 else 0)), 0,
+          _lib.load().ofq_softmax_quant_bwd, dPq.data_ptr(), P.data_ptr(), nz, N, ld, H, s_eff.data_ptr(), qhi,
+          float(alpha), float(g_s), _ptr(ca), 1 if ca_per_head else 0, _ptr(rb), planes, out_a.data_ptr(),
+          out_bt.data_ptr(), ldo, colsum.data_ptr(), d_s.data_ptr(), _ptr(ds32), _st())
     return out_a, out_bt, ldo, colsum, d_s, ds32
 
 
@@ -215,7 +245,8 @@ def wqk_compose(wq: torch.Tensor, wk: torch.Tensor, H: int) -> torch.Tensor:
     Cc = wq.shape[1]
     hd = wq.shape[0] // H
     out = torch.empty((H * Cc, Cc), dtype=torch.float32, device=wq.device)
-    check(_lib.load().ofq_wqk_compose(wq.data_ptr(), wk.data_ptr(), H, hd, Cc, out.data_ptr(), _st()))
+    _call("wqk_compose", 1, 4.0 * (2 * H * hd * Cc + H * Cc * Cc), 2.0 * H * hd * Cc * Cc, _lib.load().ofq_wqk_compose,
+          wq.data_ptr(), wk.data_ptr(), H, hd, Cc, out.data_ptr(), _st())
     return out
 
 
@@ -224,8 +255,9 @@ def wqk_compose_bwd(dwqk: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, H: i
     hd = wq.shape[0] // H
     dwq = torch.empty_like(wq)
     dwk = torch.empty_like(wk)
-    check(_lib.load().ofq_wqk_compose_bwd(dwqk.data_ptr(), wq.data_ptr(), wk.data_ptr(), H, hd, Cc, dwq.data_ptr(),
-                                          dwk.data_ptr(), _st()))
+    _call("wqk_compose_bwd", 2, 4.0 * (4 * H * hd * Cc + 2 * H * Cc * Cc), 4.0 * H * hd * Cc * Cc,
+          _lib.load().ofq_wqk_compose_bwd, dwqk.data_ptr(), wq.data_ptr(), wk.data_ptr(), H, hd, Cc, dwq.data_ptr(),
+          dwk.data_ptr(), _st())
     return dwq, dwk
 
 
@@ -238,15 +270,17 @@ def cga_mask(w: torch.Tensor, bits: int, boundary_range: float) -> torch.Tensor:
     mask = torch.empty((R, Cc), dtype=torch.uint8, device=w.device)
     rowstat = torch.empty(R, dtype=torch.float32, device=w.device)
     mm = torch.empty(2, dtype=torch.int32, device=w.device)
-    check(_lib.load().ofq_cga_mask(w.data_ptr(), R, Cc, bits, float(boundary_range), mask.data_ptr(),
-                                   rowstat.data_ptr(), mm.data_ptr(), _st()))
+    _call("cga_mask", 3, 9.0 * R * Cc, 0, _lib.load().ofq_cga_mask, w.data_ptr(), R, Cc, bits, float(boundary_range),
+          mask.data_ptr(), rowstat.data_ptr(), mm.data_ptr(), _st())
     return mask
 
 
 def cga_adamw_(p: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
                lr: float, beta1: float, beta2: float, eps: float, weight_decay: float, bits: int = 0,
-               boundary_range: float = 0.005, scratch=None, mask_out: Optional[torch.Tensor] = None) -> None:
-    """In-place (masked) AdamW step on one parameter. bits == 0: plain AdamW."""
+               boundary_range: float = 0.005, scratch=None, mask_out: Optional[torch.Tensor] = None,
+               step_dev: Optional[torch.Tensor] = None) -> None:
+    """In-place (masked) AdamW step on one parameter. bits == 0: plain AdamW. step_dev: device int32 step counter
+    (CUDA-graph friendly) used instead of `step`."""
     _cuda(p, grad, exp_avg, exp_avg_sq)
     assert p.is_contiguous() and grad.is_contiguous() and p.dtype == torch.float32
     rows = cols = 0
@@ -257,6 +291,13 @@ def cga_adamw_(p: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_a
             scratch = (torch.empty(rows, dtype=torch.float32, device=p.device),
                        torch.empty(2, dtype=torch.int32, device=p.device))
         rowstat, mm = scratch
-    check(_lib.load().ofq_cga_adamw(p.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
-                                    p.numel(), rows, cols, step, lr, beta1, beta2, eps, weight_decay, bits,
-                                    float(boundary_range), _ptr(rowstat), _ptr(mm), _ptr(mask_out), _st()))
+    _call("cga_adamw", 3 if bits > 0 else 1, (32.0 if bits > 0 else 28.0) * p.numel(), 0, _lib.load().ofq_cga_adamw,
+          p.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), p.numel(), rows, cols, step, lr,
+          beta1, beta2, eps, weight_decay, bits, float(boundary_range), _ptr(rowstat), _ptr(mm), _ptr(mask_out),
+          _ptr(step_dev), _st())
+
+
+def counter_increment_(counter: torch.Tensor) -> None:
+    _cuda(counter)
+    assert counter.dtype == torch.int32
+    _call("counter", 1, 8.0, 0, _lib.load().ofq_counter_increment, counter.data_ptr(), _st())

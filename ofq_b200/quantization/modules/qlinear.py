@@ -122,7 +122,17 @@ class LSQ_QConv2d(nn.Conv2d):
     def forward(self, input):
         weight = self.lsqw_fn(self.weight)
         input = self.move_aft(self.input_quant_fn(self.move_b4(input)))
-        return F.conv2d(input, weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+        kh, kw = self.kernel_size
+        if (tuple(self.stride) == (kh, kw) and tuple(self.padding) == (0, 0) and tuple(self.dilation) == (1, 1)
+                and self.groups == 1 and input.shape[-2] % kh == 0 and input.shape[-1] % kw == 0):
+            # patchify convolution == one GEMM over unfolded patches; done as a true-fp32 matmul because cuDNN
+            # would pick TF32 kernels (forward and backward) and the 8-bit operands would no longer be exact
+            B, Cin, Hh, Ww = input.shape
+            cols = input.view(B, Cin, Hh // kh, kh, Ww // kw, kw).permute(0, 2, 4, 1, 3, 5).reshape(-1, Cin * kh * kw)
+            out = torch.addmm(self.bias, cols, weight.view(weight.shape[0], -1).t())
+            return out.view(B, Hh // kh, Ww // kw, -1).permute(0, 3, 1, 2)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            return F.conv2d(input, weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
 
 
 class LSQ_QLinear4head(nn.Linear):

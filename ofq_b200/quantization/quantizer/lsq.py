@@ -16,8 +16,7 @@ from ..functional import LsqFn, levels
 
 def _eff_scale(alpha, g):
     """grad_scale(clip(alpha, 1e-5), g) of lsq.py:6-18, 593 with the reference's exact value and gradient."""
-    eps = torch.tensor(1e-5, dtype=torch.float32, device=alpha.device)
-    ac = torch.where(alpha > eps, alpha, eps)
+    ac = torch.where(alpha > 1e-5, alpha, 1e-5)      # scalar operands: no host->device copy (CUDA-graph safe)
     ac = alpha - alpha.detach() + ac.detach()
     ag = ac * g
     return (ac - ag).detach() + ag
