@@ -333,7 +333,7 @@ def main():
             ach = nflops / (tms * 1e-3) / 1e12
             roof = {"bound": "tensor", "achieved": ach, "peak": tensor_peak / 1e12, "unit": "TFLOP/s", "frac": ach / (tensor_peak / 1e12)}
         roof.update({"traffic": traffic, "kernel": name, "launches_per_step": cnt / nprof, "avg_launch_us": tms / cnt * 1e3,
-                     "share_of_step": tms / nprof / step_ms, "peak_source": peaks["source"],
+                     "share_of_step": (tms / nprof) / (ms_total / a.steps), "peak_source": peaks["source"],
                      "families_ms_per_step": {k: round(v[0] / nprof, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])},
                      "families_gbps": {k: round(v[2] / (v[0] * 1e-3) / 1e9, 1) for k, v in fam.items() if v[0] > 0},
                      "instrumented_step_ms": step_ms})

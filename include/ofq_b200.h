@@ -194,6 +194,12 @@ OFQ_API int ofq_cga_adamw(float* p, const float* grad, float* exp_avg, float* ex
                           double weight_decay, int bits, double boundary_range, float* rowstat, int* kminmax,
                           uint8_t* mask_out, const int* step_dev, void* stream);
 OFQ_API int ofq_counter_increment(int* counter, void* stream);
+/* Multi-tensor plain AdamW (all un-masked parameters of one learning-rate group in ONE launch).
+ * table: device array of n_entries 48-byte records
+ *   { float* p; const float* g; float* m; float* v; int64 numel; float decay (= 1 - lr*wd); int32 first_block; }
+ * where first_block is the running sum of ceil(numel / 1024) and total_blocks the final sum. */
+OFQ_API int ofq_adamw_multi(const void* table, int n_entries, int total_blocks, int step, double lr, double beta1,
+                            double beta2, double eps, const int* step_dev, void* stream);
 
 #ifdef __cplusplus
 }

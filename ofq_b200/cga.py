@@ -60,6 +60,7 @@ class CGAAdamW(torch.optim.Optimizer):
         self.keep_masks = False
         self.launches = 0
         self._step_dev = None      # device-resident step counter: the whole step can be captured in a CUDA graph
+        self._tables = {}          # per param-group pointer tables of the multi-tensor kernel
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -68,8 +69,10 @@ class CGAAdamW(torch.optim.Optimizer):
             dev = next(p for g in self.param_groups for p in g["params"]).device
             self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         ops.counter_increment_(self._step_dev)
-        for group in self.param_groups:
+        self._host_step = getattr(self, "_host_step", 0) + 1
+        for gi, group in enumerate(self.param_groups):
             b1, b2 = group["betas"]
+            plain = []
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -80,6 +83,9 @@ class CGAAdamW(torch.optim.Optimizer):
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 st["step"] += 1
                 masked = id(p) in self._masked
+                if not masked and p.is_contiguous() and p.grad.is_contiguous():
+                    plain.append(p)
+                    continue
                 if masked and "scratch" not in st:
                     st["scratch"] = (torch.empty(p.shape[0], dtype=torch.float32, device=p.device),
                                      torch.empty(2, dtype=torch.int32, device=p.device))
@@ -93,4 +99,18 @@ class CGAAdamW(torch.optim.Optimizer):
                                boundary_range=self.boundary_range, scratch=st.get("scratch"), mask_out=mask_out,
                                step_dev=self._step_dev)
                 self.launches += 3 if masked else 1
+            if plain:
+                # every un-masked parameter of the group in ONE launch; the pointer table is rebuilt only when a
+                # gradient buffer moved (it never does under CUDA-graph replay or with persistent .grad buffers)
+                key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in plain) + (group["lr"], group["weight_decay"])
+                cache = self._tables.get(gi)
+                if cache is None or cache[0] != key:
+                    decay = 1.0 - group["lr"] * group["weight_decay"]
+                    entries = [(p.data, p.grad, self.state[p]["exp_avg"], self.state[p]["exp_avg_sq"], decay) for p in plain]
+                    cache = (key,) + ops.build_adamw_table(entries, plain[0].device)
+                    self._tables[gi] = cache
+                _, table, n, blocks, numel = cache
+                ops.adamw_multi_(table, n, blocks, numel, self._host_step, group["lr"], b1, b2, group["eps"],
+                                 step_dev=self._step_dev)
+                self.launches += 1
         return loss

@@ -20,7 +20,8 @@ namespace ofq {
 
 constexpr int BM = 128;          // UMMA M
 constexpr int KBYTES = 128;      // one 128B swizzle atom of K per stage
-constexpr int NUM_THREADS = 192; // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int EPI_WARPS = 8;      // two warps per TMEM lane quarter, interleaved over the 32-column chunks
+constexpr int NUM_THREADS = 64 + EPI_WARPS * 32; // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 
 struct VecRef {
     const float* p;   // nullptr -> 1.0
@@ -40,13 +41,15 @@ struct GemmParams {
     int atomic;
 };
 
+constexpr int OUT_BUFS = 2;      // TMA-store staging buffers per epilogue warp (stores in flight)
+
 template <int BN, int STAGES>
 struct SmemLayout {
     static constexpr uint32_t A_BYTES = BM * KBYTES;
     static constexpr uint32_t B_BYTES = BN * KBYTES;
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr uint32_t OUT_OFF = STAGES * STAGE_BYTES;          // 4 warps x 2 x (32 x 128 B), swizzled
-    static constexpr uint32_t OUT_BYTES = 4 * 2 * 4096;
+    static constexpr uint32_t OUT_OFF = STAGES * STAGE_BYTES;          // 4 warps x OUT_BUFS x (32 x 128 B), swizzled
+    static constexpr uint32_t OUT_BYTES = EPI_WARPS * OUT_BUFS * 4096;
     static constexpr uint32_t VEC_OFF = OUT_OFF + OUT_BYTES;            // 2 x {cs[BN], ct[BN]} (double buffered)
     static constexpr uint32_t BAR_OFF = VEC_OFF + 2 * 2 * BN * 4;
     static constexpr uint32_t TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
@@ -90,9 +93,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint32_t IDESC = KIND == 0 ? umma_idesc(2u, 1u, BM, BN)   // S32 acc, signed int8
                                          : umma_idesc(1u, 1u, BM, BN);  // F32 acc, bf16
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                               ~static_cast<uintptr_t>(1023));
+    // 1024-byte alignment is required by the 128B swizzle; the attribute keeps the pointer in the shared address
+    // space (an integer round-up would degrade every access to generic LD/ST)
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* acc_full = empty_bar + STAGES;     // [2] MMA -> epilogue
@@ -113,7 +117,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], 4);         // one arrival per epilogue warp
+            mbar_init(&acc_empty[s], EPI_WARPS); // one arrival per epilogue warp
         }
         fence_mbar_init();
     }
@@ -177,9 +181,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ---- epilogue: warps 2..5 own TMEM lane quarters (warp % 4)
+        // ---- epilogue: warps 2..9. TMEM lane quarter = warp % 4 (hardware restriction); the two warps of a quarter
+        //      take the even / odd 32-column chunks. TMEM loads are software-pipelined one chunk ahead.
         const int q = warp & 3;
-        uint8_t* stage_base = smem + L::OUT_OFF + q * 2 * 4096;
+        const int half = (warp - 2) >> 2;
+        uint8_t* stage_base = smem + L::OUT_OFF + (warp - 2) * OUT_BUFS * 4096;
         uint32_t tc = 0, chunk = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tc) {
             const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);
@@ -190,13 +196,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             {   // stage the column vectors of this tile (double buffered by accumulator stage)
                 const long long cs_off = (long long)c.b1 * p.cs.bs1 + (long long)c.b2 * p.cs.bs2;
                 const long long ct_off = (long long)c.b1 * p.ct.bs1 + (long long)c.b2 * p.ct.bs2;
-                for (int j = threadIdx.x - 64; j < BN; j += 128) {
+                for (int j = threadIdx.x - 64; j < BN; j += EPI_WARPS * 32) {
                     const int n = c.n0 + j;
                     const bool ok = n < p.N;
                     cs_s[j] = ok ? (p.cs.p ? __ldg(p.cs.p + cs_off + n) : 1.0f) : 0.f;
                     ct_s[j] = (ok && rank1) ? (p.ct.p ? __ldg(p.ct.p + ct_off + n) : 1.0f) : 0.f;
                 }
-                named_bar_sync(1, 128);
+                named_bar_sync(1, EPI_WARPS * 32);
             }
             const int m = c.m0 + q * 32 + lane;
             const bool row_ok = m < p.M;
@@ -210,20 +216,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
             }
             const uint32_t tmem_acc = tmem_base + as * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+            // number of chunks this warp owns inside the valid column range (warp-uniform)
+            int nvalid = (min(BN, p.N - c.n0) + 31) / 32;
+            uint32_t r[2][32];
+            int ci = half;
+            if (ci < nvalid && c.nit > 0) tmem_ld_32x32(tmem_acc + ci * 32, r[0]);
+            int buf_sel = 0;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                if (c.n0 + c0 >= p.N) break;  // warp-uniform
-                uint32_t r[32];
+            for (; ci < nvalid; ci += 2, buf_sel ^= 1) {
+                const int c0 = ci * 32;
                 if (c.nit > 0) {
-                    tmem_ld_32x32(tmem_acc + c0, r);
-                    tmem_ld_wait();
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = 0;
+                    tmem_ld_wait();                                          // chunk ci is in r[buf_sel]
+                    if (buf_sel == 0) tmem_ld_pin(r[0]); else tmem_ld_pin(r[1]);
+                    if (ci + 2 < nvalid) {                                   // prefetch the next owned chunk
+                        if (buf_sel == 0) tmem_ld_32x32(tmem_acc + (ci + 2) * 32, r[1]);
+                        else              tmem_ld_32x32(tmem_acc + (ci + 2) * 32, r[0]);
+                    }
                 }
-                uint8_t* buf = stage_base + (chunk & 1) * 4096;
-                if (chunk >= 2) {  // the staging buffer used two chunks ago must have been read by TMA
-                    if (lane == 0) tma_store_wait_read<1>();
+                uint8_t* buf = stage_base + (chunk % OUT_BUFS) * 4096;
+                if (chunk >= OUT_BUFS) {  // the staging buffer used OUT_BUFS chunks ago must have been read by TMA
+                    if (lane == 0) tma_store_wait_read<OUT_BUFS - 1>();
                     __syncwarp();
                 }
                 ++chunk;
@@ -231,13 +243,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 float4* rowp = reinterpret_cast<float4*>(buf + lane * 128);
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 cs4 = *reinterpret_cast<const float4*>(cs_s + c0 + 4 * j4);
+                    const float4 ct4 = *reinterpret_cast<const float4*>(ct_s + c0 + 4 * j4);
+                    const float csv[4] = {cs4.x, cs4.y, cs4.z, cs4.w};
+                    const float ctv[4] = {ct4.x, ct4.y, ct4.z, ct4.w};
                     float o[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int j = 4 * j4 + e;
-                        const float acc = KIND == 0 ? static_cast<float>(static_cast<int32_t>(r[j]))
-                                                    : __uint_as_float(r[j]);
-                        o[e] = acc * rsv * cs_s[c0 + j] + rtv * ct_s[c0 + j];
+                        const uint32_t raw = c.nit > 0 ? (buf_sel == 0 ? r[0][j] : r[1][j]) : 0u;
+                        const float acc = KIND == 0 ? static_cast<float>(static_cast<int32_t>(raw)) : __uint_as_float(raw);
+                        o[e] = acc * rsv * csv[e] + rtv * ctv[e];
                     }
                     rowp[j4 ^ (lane & 7)] = make_float4(o[0], o[1], o[2], o[3]);
                 }
@@ -401,8 +417,8 @@ extern "C" int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B
 #define OFQ_DISPATCH(KIND)                                                   \
     switch (bn) {                                                            \
         case 256: return launch_gemm<KIND, 256, 3>(tmA, tmB, tmC, p, st);    \
-        case 192: return launch_gemm<KIND, 192, 4>(tmA, tmB, tmC, p, st);    \
-        case 128: return launch_gemm<KIND, 128, 5>(tmA, tmB, tmC, p, st);    \
+        case 192: return launch_gemm<KIND, 192, 3>(tmA, tmB, tmC, p, st);    \
+        case 128: return launch_gemm<KIND, 128, 4>(tmA, tmB, tmC, p, st);    \
         case 64:  return launch_gemm<KIND, 64, 6>(tmA, tmB, tmC, p, st);     \
         default:  return launch_gemm<KIND, 32, 6>(tmA, tmB, tmC, p, st);     \
     }

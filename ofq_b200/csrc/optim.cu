@@ -156,6 +156,64 @@ cga_adamw_kernel(float* __restrict__ p, const float* __restrict__ grad, float* _
     }
 }
 
+// Multi-tensor plain AdamW: one launch walks a table of (pointer, length, weight-decay) entries.
+struct AdamWEntry {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    long long numel;
+    float decay;       // 1 - lr * wd of this parameter's group
+    int first_block;   // first CTA that works on this entry
+};
+
+__global__ void __launch_bounds__(256)
+adamw_multi_kernel(const AdamWEntry* __restrict__ table, int n_entries, AdamScalars a, const int* __restrict__ step_dev) {
+    __shared__ float bc[2];
+    __shared__ int entry_s;
+    if (threadIdx.x == 0) {
+        if (step_dev) {
+            const double t = (double)(*step_dev);
+            bc[0] = (float)(a.lr / (1.0 - pow(a.beta1_d, t)));
+            bc[1] = (float)sqrt(1.0 - pow(a.beta2_d, t));
+        } else {
+            bc[0] = a.step_size;
+            bc[1] = a.bc2_sqrt;
+        }
+        int lo = 0, hi = n_entries - 1;             // last entry whose first_block <= blockIdx.x
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (table[mid].first_block <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+        }
+        entry_s = lo;
+    }
+    __syncthreads();
+    a.step_size = bc[0];
+    a.bc2_sqrt = bc[1];
+    const AdamWEntry e = table[entry_s];
+    a.decay = e.decay;
+    const long long base = ((long long)(blockIdx.x - e.first_block) * blockDim.x + threadIdx.x) * 4;
+    if (base >= e.numel) return;
+    if (base + 4 <= e.numel && (((uintptr_t)e.p | (uintptr_t)e.g | (uintptr_t)e.m | (uintptr_t)e.v) & 15) == 0) {
+        float4 pp = *reinterpret_cast<float4*>(e.p + base);
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(e.g + base));
+        float4 mm = *reinterpret_cast<float4*>(e.m + base);
+        float4 vv = *reinterpret_cast<float4*>(e.v + base);
+        float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) adamw_elem(pa[k], ga[k], ma[k], va[k], a, false);
+        *reinterpret_cast<float4*>(e.p + base) = pp;
+        *reinterpret_cast<float4*>(e.m + base) = mm;
+        *reinterpret_cast<float4*>(e.v + base) = vv;
+    } else {
+        for (long long i = base; i < e.numel && i < base + 4; ++i) {
+            float pv = e.p[i], mv = e.m[i], vv = e.v[i];
+            adamw_elem(pv, e.g[i], mv, vv, a, false);
+            e.p[i] = pv; e.m[i] = mv; e.v[i] = vv;
+        }
+    }
+}
+
 }  // namespace
 
 static int cga_prepass(const float* w, int rows, int cols, int bits, float* rowstat, int* kminmax, cudaStream_t st) {
@@ -221,6 +279,28 @@ extern "C" int ofq_counter_increment(int* counter, void* stream) {
     OFQ_REQUIRE(counter, "ofq_counter_increment: null pointer");
     OFQ_CHECK_ARCH();
     counter_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// table: device array of n_entries records {p, g, m, v (pointers), numel (int64), decay (float), first_block (int)}
+// laid out as the AdamWEntry struct above (48 bytes); total_blocks = sum of ceil(numel / 1024).
+extern "C" int ofq_adamw_multi(const void* table, int n_entries, int total_blocks, int step, double lr, double beta1,
+                               double beta2, double eps, const int* step_dev, void* stream) {
+    OFQ_REQUIRE(table && n_entries > 0 && total_blocks > 0 && (step >= 1 || step_dev), "ofq_adamw_multi: bad argument");
+    static_assert(sizeof(AdamWEntry) == 48, "AdamWEntry layout is part of the C-ABI");
+    OFQ_CHECK_ARCH();
+    if (step < 1) step = 1;
+    AdamScalars a;
+    a.decay = 1.f;
+    a.one_m_b1 = (float)(1.0 - beta1);
+    a.beta2 = (float)beta2;
+    a.one_m_b2 = (float)(1.0 - beta2);
+    a.step_size = (float)(lr / (1.0 - std::pow(beta1, (double)step)));
+    a.bc2_sqrt = (float)std::sqrt(1.0 - std::pow(beta2, (double)step));
+    a.eps = (float)eps;
+    a.lr = lr; a.beta1_d = beta1; a.beta2_d = beta2;
+    adamw_multi_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>((const AdamWEntry*)table, n_entries, a, step_dev);
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }

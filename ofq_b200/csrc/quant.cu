@@ -100,42 +100,58 @@ lsq_quant_kernel(const float* __restrict__ x, long long rows, int cols, long lon
                  const float* __restrict__ b4, const float* __restrict__ s_eff, int scale_mode, int period,
                  int nseg, int seg_len, float qlo, float qhi, int8_t* __restrict__ codes, long long ldq) {
     constexpr int W = VEC ? 4 : 1;
-    const int cw = cols / W;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= rows * cw) return;
-    const long long row = idx / cw;
-    const int col = (int)(idx - row * cw) * W;
-    float xv[W], bv[W], sv[W];
-    if (VEC) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(x + row * ldx + col));
-        xv[0] = t.x; xv[1 % W] = t.y; xv[2 % W] = t.z; xv[3 % W] = t.w;
-        const float4 b = __ldg(reinterpret_cast<const float4*>(b4 + col));
-        bv[0] = b.x; bv[1 % W] = b.y; bv[2 % W] = b.z; bv[3 % W] = b.w;
-    } else {
-        xv[0] = __ldg(x + row * ldx + col);
-        bv[0] = __ldg(b4 + col);
-    }
-    if (scale_mode == OFQ_SCALE_PER_ROW) {
-        const float s = __ldg(s_eff + (row % period) * nseg + col / seg_len);
+    constexpr int ITEMS = 2;                                  // independent loads per thread
+    const uint32_t cw = (uint32_t)(cols / W);
+    const uint32_t total = (uint32_t)rows * cw;               // host guarantees < 2^32
+    const uint32_t base = (blockIdx.x * blockDim.x * ITEMS) + threadIdx.x;
+    uint32_t rowv[ITEMS], colv[ITEMS];
+    bool ok[ITEMS];
+    float xv[ITEMS][W];
 #pragma unroll
-        for (int e = 0; e < W; ++e) sv[e] = s;
-    } else {
+    for (int it = 0; it < ITEMS; ++it) {
+        const uint32_t idx = base + it * blockDim.x;
+        ok[it] = idx < total;
+        rowv[it] = ok[it] ? idx / cw : 0;
+        colv[it] = ok[it] ? (idx - rowv[it] * cw) * W : 0;
         if (VEC) {
+            const float4 t = ok[it] ? __ldg(reinterpret_cast<const float4*>(x + (long long)rowv[it] * ldx + colv[it]))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            xv[it][0] = t.x; xv[it][1 % W] = t.y; xv[it][2 % W] = t.z; xv[it][3 % W] = t.w;
+        } else {
+            xv[it][0] = ok[it] ? __ldg(x + (long long)rowv[it] * ldx + colv[it]) : 0.f;
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        if (!ok[it]) continue;
+        const uint32_t row = rowv[it], col = colv[it];
+        float bv[W], sv[W];
+        if (VEC) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(b4 + col));
+            bv[0] = b.x; bv[1 % W] = b.y; bv[2 % W] = b.z; bv[3 % W] = b.w;
+        } else {
+            bv[0] = __ldg(b4 + col);
+        }
+        if (scale_mode == OFQ_SCALE_PER_ROW) {
+            const float s = __ldg(s_eff + (row % (uint32_t)period) * nseg + col / (uint32_t)seg_len);
+#pragma unroll
+            for (int e = 0; e < W; ++e) sv[e] = s;
+        } else if (VEC) {
             const float4 s = __ldg(reinterpret_cast<const float4*>(s_eff + col));
             sv[0] = s.x; sv[1 % W] = s.y; sv[2 % W] = s.z; sv[3 % W] = s.w;
         } else {
             sv[0] = __ldg(s_eff + col);
         }
-    }
-    int q[W];
+        int q[W];
 #pragma unroll
-    for (int e = 0; e < W; ++e) q[e] = lsq_code(xv[e], bv[e], sv[e], qlo, qhi);
-    if (VEC) {
-        const uint32_t packed = (uint32_t)(q[0] & 0xff) | ((uint32_t)(q[1 % W] & 0xff) << 8) |
-                                ((uint32_t)(q[2 % W] & 0xff) << 16) | ((uint32_t)(q[3 % W] & 0xff) << 24);
-        *reinterpret_cast<uint32_t*>(codes + row * ldq + col) = packed;
-    } else {
-        codes[row * ldq + col] = (int8_t)q[0];
+        for (int e = 0; e < W; ++e) q[e] = lsq_code(xv[it][e], bv[e], sv[e], qlo, qhi);
+        if (VEC) {
+            const uint32_t packed = (uint32_t)(q[0] & 0xff) | ((uint32_t)(q[1 % W] & 0xff) << 8) |
+                                    ((uint32_t)(q[2 % W] & 0xff) << 16) | ((uint32_t)(q[3 % W] & 0xff) << 24);
+            *reinterpret_cast<uint32_t*>(codes + (long long)row * ldq + col) = packed;
+        } else {
+            codes[(long long)row * ldq + col] = (int8_t)q[0];
+        }
     }
 }
 
@@ -144,41 +160,50 @@ lsq_quant_kernel(const float* __restrict__ x, long long rows, int cols, long lon
 // current 512-column chunk so that column partial sums stay in registers; per-(row,segment) partial sums
 // are reduced with shuffles once per row and chunk. workspace = rowpart[rows*nseg] | colpart[nblk][3][cols].
 constexpr int kBwdChunk = 512;   // columns per register-resident chunk (4 float4 per lane)
-constexpr int kBwdRowsPerBlock = 32;
+constexpr int kBwdMinRowsPerBlock = 32;
+constexpr int kBwdMaxBlocks = 4 * 148;   // two resident CTAs per SM, two waves; rows per CTA amortise the column fold
 
 __host__ __device__ inline long long lsq_bwd_nblk(long long rows) {
-    return (rows + kBwdRowsPerBlock - 1) / kBwdRowsPerBlock;
+    const long long n = (rows + kBwdMinRowsPerBlock - 1) / kBwdMinRowsPerBlock;
+    return n < kBwdMaxBlocks ? n : kBwdMaxBlocks;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+template <int scale_mode>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)
 lsq_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
                long long rows, int cols, const float* __restrict__ b4, const float* __restrict__ s_eff,
-               int scale_mode, int period, int nseg, int seg_len, float qlo, float qhi,
+               int period, int nseg, int seg_len, float qlo, float qhi,
                float* __restrict__ dx, long long lddx, float* __restrict__ rowpart,
                float* __restrict__ colpart) {
-    __shared__ float col_s[3][kBwdChunk];
+    __shared__ float col_s[3][kBwdChunk];     // index [v][(p * 4 + e) * 32 + lane]: conflict-free for the fold
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long r0 = (long long)blockIdx.x * kBwdRowsPerBlock;
-    const long long r1 = min(rows, r0 + kBwdRowsPerBlock);
+    const long long rpb = (rows + gridDim.x - 1) / gridDim.x;
+    const long long r0 = (long long)blockIdx.x * rpb;
+    const long long r1 = min(rows, r0 + rpb);
     float* cp = colpart + (long long)blockIdx.x * 3 * cols;
 
     for (int cbase = 0; cbase < cols; cbase += kBwdChunk) {
         for (int i = threadIdx.x; i < 3 * kBwdChunk; i += blockDim.x) (&col_s[0][0])[i] = 0.f;
         __syncthreads();
-        float a_aft[4][4], a_b4[4][4], a_s[4][4];
-        float4 b4v[4], s4v[4];
+        constexpr int NS = scale_mode == OFQ_SCALE_PER_COL ? 4 : 1;    // per-column scale gradient accumulators
+        float a_aft[4][4], a_b4[4][4], a_s[NS][4];
+        float4 b4v[4], is4v[NS];       // is4v: reciprocal per-column scales (the backward needs no bit-exact division)
         int segv[4];
         bool okv[4];
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) a_aft[p][e] = a_b4[p][e] = a_s[p][e] = 0.f;
+            for (int e = 0; e < 4; ++e) a_aft[p][e] = a_b4[p][e] = 0.f;
             const int col = cbase + p * 128 + lane * 4;
             okv[p] = col < cols;
             segv[p] = okv[p] ? col / seg_len : -1;
             b4v[p] = okv[p] ? __ldg(reinterpret_cast<const float4*>(b4 + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            s4v[p] = (okv[p] && scale_mode == OFQ_SCALE_PER_COL) ? __ldg(reinterpret_cast<const float4*>(s_eff + col))
-                                                                   : make_float4(1.f, 1.f, 1.f, 1.f);
+            if (scale_mode == OFQ_SCALE_PER_COL) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) a_s[p % NS][e] = 0.f;
+                const float4 s4 = okv[p] ? __ldg(reinterpret_cast<const float4*>(s_eff + col)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                is4v[p % NS] = make_float4(1.0f / s4.x, 1.0f / s4.y, 1.0f / s4.z, 1.0f / s4.w);
+            }
         }
         const int chunk_end = min(cbase + kBwdChunk, cols) - 1;
         const int seg_first = cbase / seg_len, seg_last = chunk_end / seg_len;     // block-uniform
@@ -200,10 +225,12 @@ lsq_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __rest
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 if (!okv[p]) continue;
-                float sv[4] = {s4v[p].x, s4v[p].y, s4v[p].z, s4v[p].w};
+                float sv[4];
                 if (scale_mode == OFQ_SCALE_PER_ROW) {
-                    const float s = __ldg(s_eff + srow + segv[p]);
-                    sv[0] = sv[1] = sv[2] = sv[3] = s;
+                    const float is = 1.0f / __ldg(s_eff + srow + segv[p]);
+                    sv[0] = sv[1] = sv[2] = sv[3] = is;
+                } else {
+                    sv[0] = is4v[p % NS].x; sv[1] = is4v[p % NS].y; sv[2] = is4v[p % NS].z; sv[3] = is4v[p % NS].w;
                 }
                 const float gg[4] = {g4[p].x, g4[p].y, g4[p].z, g4[p].w};
                 const float xx[4] = {x4[p].x, x4[p].y, x4[p].z, x4[p].w};
@@ -211,14 +238,14 @@ lsq_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __rest
                 float o[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float v = __fdiv_rn(__fadd_rn(xx[e], bb[e]), sv[e]);
+                    const float v = (xx[e] + bb[e]) * sv[e];
                     const bool inside = (v >= qlo) && (v <= qhi);
                     const float q = rintf(fminf(fmaxf(v, qlo), qhi));
                     const float t = gg[e] * (inside ? (q - v) : q);
                     o[e] = inside ? gg[e] : 0.f;
                     a_aft[p][e] += gg[e];
                     a_b4[p][e] += o[e];
-                    if (scale_mode == OFQ_SCALE_PER_ROW) part[p] += t; else a_s[p][e] += t;
+                    if (scale_mode == OFQ_SCALE_PER_ROW) part[p] += t; else a_s[p % NS][e] += t;
                 }
                 *reinterpret_cast<float4*>(dxr + p * 128) = make_float4(o[0], o[1], o[2], o[3]);
             }
@@ -236,25 +263,27 @@ lsq_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __rest
                 }
             }
         }
-        // fold the 8 warps' column partials
+        // fold the 8 warps' column partials (lane-major layout: one bank per lane)
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            const int lc = p * 128 + lane * 4;
             if (okv[p]) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    atomicAdd(&col_s[0][lc + e], a_aft[p][e]);
-                    atomicAdd(&col_s[1][lc + e], a_b4[p][e]);
-                    if (scale_mode == OFQ_SCALE_PER_COL) atomicAdd(&col_s[2][lc + e], a_s[p][e]);
+                    const int si = (p * 4 + e) * 32 + lane;
+                    atomicAdd(&col_s[0][si], a_aft[p][e]);
+                    atomicAdd(&col_s[1][si], a_b4[p][e]);
+                    if (scale_mode == OFQ_SCALE_PER_COL) atomicAdd(&col_s[2][si], a_s[p % NS][e]);
                 }
             }
         }
         __syncthreads();
         for (int i = threadIdx.x; i < kBwdChunk; i += blockDim.x) {
             if (cbase + i < cols) {
-                cp[0 * cols + cbase + i] = col_s[0][i];
-                cp[1 * cols + cbase + i] = col_s[1][i];
-                cp[2 * cols + cbase + i] = col_s[2][i];
+                // column i of the chunk = pass p, lane l, element e with i = p*128 + l*4 + e
+                const int si = ((i >> 7) * 4 + (i & 3)) * 32 + ((i >> 2) & 31);
+                cp[0 * cols + cbase + i] = col_s[0][si];
+                cp[1 * cols + cbase + i] = col_s[1][si];
+                cp[2 * cols + cbase + i] = col_s[2][si];
             }
         }
         __syncthreads();
@@ -565,7 +594,8 @@ extern "C" int ofq_lsq_quant(const float* x, long long rows, int cols, long long
                      ((uintptr_t)x % 16 == 0) && ((uintptr_t)b4 % 16 == 0) && ((uintptr_t)s_eff % 16 == 0) &&
                      ((uintptr_t)codes % 4 == 0);
     const long long n = rows * (cols / (vec ? 4 : 1));
-    const unsigned grid = (unsigned)((n + 255) / 256);
+    OFQ_REQUIRE(n < 0xffffffffLL, "ofq_lsq_quant: tensor too large for 32-bit indexing");
+    const unsigned grid = (unsigned)((n + 511) / 512);
     if (vec)
         lsq_quant_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, b4, s_eff, scale_mode,
                                                                       period, nseg, seg_len, (float)qlo, (float)qhi, codes, ldq);
@@ -593,9 +623,12 @@ extern "C" int ofq_lsq_bwd(const float* dy, long long lddy, const float* x, long
     OFQ_CHECK_ARCH();
     float* rowpart = workspace;
     float* colpart = workspace + rows * nseg;
-    lsq_bwd_kernel<<<(unsigned)lsq_bwd_nblk(rows), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-        dy, lddy, x, ldx, rows, cols, b4, s_eff, scale_mode, period, nseg, seg_len, (float)qlo, (float)qhi, dx,
-        lddx, rowpart, colpart);
+    if (scale_mode == OFQ_SCALE_PER_ROW)
+        lsq_bwd_kernel<OFQ_SCALE_PER_ROW><<<(unsigned)lsq_bwd_nblk(rows), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+            dy, lddy, x, ldx, rows, cols, b4, s_eff, period, nseg, seg_len, (float)qlo, (float)qhi, dx, lddx, rowpart, colpart);
+    else
+        lsq_bwd_kernel<OFQ_SCALE_PER_COL><<<(unsigned)lsq_bwd_nblk(rows), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+            dy, lddy, x, ldx, rows, cols, b4, s_eff, period, nseg, seg_len, (float)qlo, (float)qhi, dx, lddx, rowpart, colpart);
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }

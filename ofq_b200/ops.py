@@ -301,3 +301,28 @@ def counter_increment_(counter: torch.Tensor) -> None:
     _cuda(counter)
     assert counter.dtype == torch.int32
     _call("counter", 1, 8.0, 0, _lib.load().ofq_counter_increment, counter.data_ptr(), _st())
+
+
+def build_adamw_table(entries, device) -> tuple:
+    """entries: list of (p, grad, exp_avg, exp_avg_sq, decay). Returns (device uint8 table, n_entries, total_blocks,
+    total_numel). The table holds raw pointers: it is valid as long as those tensors keep their storage."""
+    import struct
+    blob = bytearray()
+    first = 0
+    total = 0
+    for p, g, m, v, decay in entries:
+        n = p.numel()
+        blob += struct.pack("<QQQQqfi", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, float(decay), first)
+        first += (n + 1023) // 1024
+        total += n
+    # pinned staging + async copy: legal inside CUDA-graph capture (the caller keeps `host` alive with the table)
+    host = torch.frombuffer(bytes(blob), dtype=torch.uint8).clone().pin_memory()
+    t = host.to(device, non_blocking=True)
+    t._ofq_host = host
+    return t, len(entries), first, total
+
+
+def adamw_multi_(table, n_entries: int, total_blocks: int, total_numel: int, step: int, lr: float, beta1: float,
+                 beta2: float, eps: float, step_dev: Optional[torch.Tensor] = None) -> None:
+    _call("adamw_multi", 1, 28.0 * total_numel, 0, _lib.load().ofq_adamw_multi, table.data_ptr(), n_entries,
+          total_blocks, step, lr, beta1, beta2, eps, _ptr(step_dev), _st())

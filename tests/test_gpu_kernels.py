@@ -419,3 +419,25 @@ def test_cga_masked_adamw(ops):
         opt.step()
         ops.cga_adamw_(p, dev(gr), m, v, step + 1, 3e-3, 0.9, 0.999, 1e-8, 0.01)
     assert rel_err(p.cpu(), ref.detach()) < 1e-6
+
+
+def test_adamw_multi_tensor(ops):
+    """One launch over a pointer table == torch.optim.AdamW on every tensor (two weight-decay groups)."""
+    from ofq_b200.cga import CGAAdamW
+    torch.manual_seed(16)
+    shapes = [(384, 384), (1536,), (7,), (1000, 384), (1,), (198,), (3, 5, 7)]
+    mine = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().cpu().clone()) for p in mine]
+    groups = lambda ps: [{"params": [p for p in ps if p.ndim <= 1], "weight_decay": 0.0},
+                         {"params": [p for p in ps if p.ndim > 1], "weight_decay": 0.05}]
+    opt = CGAAdamW(groups(mine), lr=2e-3)
+    ropt = torch.optim.AdamW(groups(ref), lr=2e-3)
+    for step in range(5):
+        for p, r in zip(mine, ref):
+            g = torch.randn(r.shape)
+            r.grad = g.clone()
+            p.grad = g.cuda()
+        opt.step()
+        ropt.step()
+    for p, r in zip(mine, ref):
+        assert rel_err(p.detach().cpu(), r.detach()) < 1e-6
