@@ -46,6 +46,14 @@ def parse():
     return ap.parse_args()
 
 
+def note(msg):
+    if os.environ.get("OFQ_BENCH_VERBOSE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')} +{time.perf_counter() - T0:.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+T0 = time.perf_counter()
+
+
 def workload_name(a):
     return (f"{a.model.replace('_', '-')} distilled W{a.bits}A{a.bits} attn_q {'plain' if a.no_qkr else 'QKR'} QAT step "
             f"(fwd+bwd+AdamW), batch {a.batch}/GPU, synthetic 224x224, random init")
@@ -167,6 +175,7 @@ def main():
     import ofq_b200.quantization as Q
     from ofq_b200 import _lib, ops
     from ofq_b200.cga import CGAAdamW, param_groups_weight_decay
+    from ofq_b200.ddp import FlatGradAllReduce, broadcast_parameters
     from ofq_b200.host.deit import DistilledVisionTransformer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -177,6 +186,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert _lib.load().ofq_device_ok() == 1, _lib.load().ofq_last_error().decode()
+    note("process group up")
 
     cfg = MODELS[a.model]
     torch.manual_seed(0)                      # identical initial weights on every rank
@@ -194,31 +204,23 @@ def main():
     with torch.no_grad():
         model(d_img)                           # setup_alpha (train.py:997-1010): creates the LSQ step sizes
     if world > 1:                              # the step sizes are data dependent: make them identical on all ranks
-        for p in model.parameters():
-            dist.broadcast(p.data, 0)
+        broadcast_parameters(model, 0)
     model.train()
     opt = CGAAdamW(param_groups_weight_decay(model, 0.05, model.no_weight_decay()), lr=5.47e-4)
-    params = [p for p in model.parameters() if p.requires_grad]
-    flat = None
-    if world > 1:
-        # data-parallel gradient exchange: ONE NCCL all-reduce (mean) of a flat fp32 gradient buffer per step
-        # (train.py:727 uses torch DDP; same collective, same bytes). Every .grad is a view into the buffer.
-        flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
-        off = 0
-        for p in params:
-            p.grad = flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+    # data-parallel gradient exchange (ofq_b200/ddp.py): ONE NCCL all-reduce (mean) of a flat fp32 gradient buffer
+    ddp = FlatGradAllReduce(model.parameters(), world) if world > 1 else None
+    flat = ddp.flat if ddp is not None else None
 
     def step(img, lbl):
-        if flat is None:
+        if ddp is None:
             opt.zero_grad(set_to_none=True)
         else:
-            flat.zero_()
+            ddp.zero()
         (cls, dst), _ = model(img)
         loss = F.cross_entropy(cls, lbl) + F.cross_entropy(dst, lbl)
-        (loss / world if world > 1 else loss).backward()
-        if flat is not None:
-            dist.all_reduce(flat)
+        (ddp.scale_loss(loss) if ddp is not None else loss).backward()
+        if ddp is not None:
+            ddp.reduce()
         opt.step()
         return loss
 
@@ -227,8 +229,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    note("model built, scales initialised")
     for _ in range(a.warmup):
         step(d_img, d_lbl)
+    barrier()
+    note("eager warm-up done")
     run = step
     launches_per_step = None
     if a.graph == "on":
@@ -247,6 +252,7 @@ def main():
         with torch.cuda.graph(graph):
             static_loss = step(static_img, static_lbl)
         launches_per_step = ops.LAUNCHES - l0
+        note("graph captured")
         barrier()
 
         def run(img, lbl):
@@ -259,6 +265,7 @@ def main():
         d_img, d_lbl = static_img, static_lbl
         for _ in range(2):
             run(d_img, d_lbl)
+    note("timed region starts")
     # ---- timed region 1: inputs resident in HBM
     barrier()
     launches0 = ops.LAUNCHES
@@ -337,10 +344,17 @@ def main():
                      "families_ms_per_step": {k: round(v[0] / nprof, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0])},
                      "families_gbps": {k: round(v[2] / (v[0] * 1e-3) / 1e9, 1) for k, v in fam.items() if v[0] > 0},
                      "instrumented_step_ms": step_ms})
-    if rank != 0:
+    def finish():
+        # NCCL communicators that were captured into a CUDA graph do not tear down reliably: synchronise, agree that
+        # every rank is done, then leave without running destructors (the JSON line is already flushed)
         if world > 1:
-            dist.destroy_process_group()
-        return
+            barrier()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        return finish()
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -368,8 +382,7 @@ def main():
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":

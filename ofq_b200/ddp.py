@@ -1,0 +1,49 @@
+"""Data-parallel gradient exchange of the QAT step (reference: train.py:727 `NativeDDP(model, device_ids=[rank])`).
+
+The path shards by images only: every rank holds the full model, StatsQ statistics and CGA masks are
+weight-only and therefore identical everywhere, and the one exchange per step is the mean of all gradients.  Instead of
+DDP's bucketed hooks the gradients live in ONE flat fp32 buffer (every `.grad` is a view into it) that is all-reduced
+with a single NCCL call after backward; at 90.8 MB (DeiT-S) over NVLink 5 this is ~0.3 ms of a ~50 ms step, and a single
+collective on static memory can be captured inside the whole-step CUDA graph.  The loss is pre-divided by the world size,
+so the SUM all-reduce yields the mean gradient the reference's DDP produces.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List
+
+import torch
+import torch.distributed as dist
+
+
+class FlatGradAllReduce:
+    def __init__(self, params: Iterable[torch.nn.Parameter], world_size: int):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        self.world_size = world_size
+        dev = self.params[0].device
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    @property
+    def nbytes(self) -> int:
+        return self.flat.numel() * 4
+
+    def zero(self) -> None:
+        """Gradients accumulate into the views (autograd adds into an existing .grad), so clear once per step."""
+        self.flat.zero_()
+
+    def scale_loss(self, loss: torch.Tensor) -> torch.Tensor:
+        return loss / self.world_size if self.world_size > 1 else loss
+
+    def reduce(self) -> None:
+        if self.world_size > 1:
+            dist.all_reduce(self.flat)
+
+
+def broadcast_parameters(model: torch.nn.Module, src: int = 0) -> None:
+    """DDP construction broadcast (train.py:727): also makes the lazily created, data-dependent LSQ step sizes
+    identical on every rank."""
+    for t in list(model.parameters()) + list(model.buffers()):
+        dist.broadcast(t.data, src)
