@@ -1,0 +1,53 @@
+"""Summarise an `ncu --metrics gpu__time_duration.sum,dram__bytes_* --csv` launch list per kernel family.
+usage: python tools/summarize_launches.py gpurun_out/r01_launches.csv profiles/r01_launches_summary.md [profiles/traffic.json]"""
+import collections, csv, json, re, sys
+
+src, dst = sys.argv[1], sys.argv[2]
+lines = [l for l in open(src) if not l.startswith("==")]
+cur = {}
+for r in csv.DictReader(lines):
+    scale = {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9, "byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r["Metric Unit"], 1)
+    cur.setdefault((r["ID"], r["Kernel Name"]), {})[r["Metric Name"]] = float(r["Metric Value"].replace(",", "")) * scale
+
+def family(k):
+    m = re.search(r"gemm_tc_kernel<(\d), (\d+), (\d+)>", k)
+    if m:
+        return f"ofq gemm_tc_kernel<{'i8' if m.group(1) == '0' else 'bf16'}, BN={m.group(2)}>"
+    m = re.search(r"<unnamed>::(\w+)", k)
+    if m and "at::" not in k:
+        return "ofq " + m.group(1)
+    m = re.search(r"at::(?:native::)?(?:<unnamed>::)?(\w+)<[^>]*?(\w+Functor|\w+KernelImpl|\w+_kernel|FillFunctor)", k)
+    if m:
+        return f"torch {m.group(1)}[{m.group(2)}]"
+    m = re.search(r"(?:void )?([\w:]+)", k)
+    return "torch " + (m.group(1) if m else k)[:50]
+
+per = collections.defaultdict(lambda: dict(n=0, ns=0.0, rd=0.0, wr=0.0))
+for (_, k), d in cur.items():
+    p = per[family(k)]
+    p["n"] += 1
+    p["ns"] += d.get("gpu__time_duration.sum", 0)
+    p["rd"] += d.get("dram__bytes_read.sum", 0)
+    p["wr"] += d.get("dram__bytes_write.sum", 0)
+tot = sum(p["ns"] for p in per.values())
+ofq = sum(p["ns"] for k, p in per.items() if k.startswith("ofq"))
+rows = sorted(per.items(), key=lambda kv: -kv[1]["ns"])
+with open(dst, "w") as f:
+    f.write(f"# ncu launch list summary ({src})\n\n")
+    f.write(f"{len(cur)} launches, {tot / 1e6:.2f} ms of kernel time (cold-cache, serialised under ncu: compare SHARES, not absolutes).\n")
+    f.write(f"ofq_b200 kernels: {100 * ofq / tot:.1f} % of the captured kernel time; the rest is torch glue (LayerNorm, GELU, residual adds, fills, heads, patch embed).\n\n")
+    f.write("| kernel family | launches | total ms | share % | avg us | DRAM MB / launch (read+write) |\n|---|---:|---:|---:|---:|---:|\n")
+    for k, p in rows[:40]:
+        f.write(f"| {k} | {p['n']} | {p['ns'] / 1e6:.3f} | {100 * p['ns'] / tot:.2f} | {p['ns'] / p['n'] / 1e3:.1f} | {(p['rd'] + p['wr']) / p['n'] / 1e6:.2f} |\n")
+print(open(dst).read()[:3500])
+if len(sys.argv) > 3:
+    fam_map = {"gemm_bf16": "gemm_tc_kernel<bf16", "gemm_i8": "gemm_tc_kernel<i8", "lsq_bwd": "ofq lsq_bwd_kernel", "lsq_quant": "ofq lsq_quant_kernel",
+               "grad_prep": "ofq grad_prep_kernel", "softmax_quant": "ofq softmax_quant_kernel", "softmax_quant_bwd": "ofq softmax_quant_bwd_kernel",
+               "codes_to_bf16": "ofq codes_convert_kernel"}
+    out = {}
+    for name, pat in fam_map.items():
+        sel = [p for k, p in per.items() if pat in k]
+        n = sum(p["n"] for p in sel)
+        if n:
+            out[name] = {"dram_bytes_per_launch": sum(p["rd"] + p["wr"] for p in sel) / n, "launches": n, "source": src}
+    json.dump(out, open(sys.argv[3], "w"), indent=1)
