@@ -11,14 +11,26 @@ import torch
 
 from ...host.deit import Attention as deit_attention
 from ...host.deit import Mlp
+from ...host.swin import MLP as swin_MLP
+from ...host.swin import ShiftedWindowAttention
 from .attention import QAttention, QAttention_qkreparam, QAttention_qkreparam_4_cga
 from .qlinear import LSQ_QConv2d, LSQ_QLinear4head, QLinear, QMLP
+from .swin_attention_and_mlp import (QAttention_swin, QAttention_swin_qkreparam, QAttention_swin_qkreparam_4_cga,
+                                     QMLP_swin)
 
 QMODULE_MAPPINGS = {torch.nn.Linear: QLinear, deit_attention: QAttention, Mlp: QMLP}
 # 0: QAttention_qkreparam, 1: QAttention_qkreparam_4_cga  (utils.py:27-39)
 QMODULE_MAPPINGS_QK_REPARAM = [
     {torch.nn.Linear: QLinear, deit_attention: QAttention_qkreparam, Mlp: QMLP},
     {torch.nn.Linear: QLinear, deit_attention: QAttention_qkreparam_4_cga, Mlp: QMLP},
+]
+
+
+# utils.py:286-303
+QMODULE_MAPPINGS_SWIN = {torch.nn.Linear: QLinear, ShiftedWindowAttention: QAttention_swin, swin_MLP: QMLP_swin}
+QMODULE_MAPPINGS_QK_REPARAM_SWIN = [
+    {torch.nn.Linear: QLinear, ShiftedWindowAttention: QAttention_swin_qkreparam, swin_MLP: QMLP_swin},
+    {torch.nn.Linear: QLinear, ShiftedWindowAttention: QAttention_swin_qkreparam_4_cga, swin_MLP: QMLP_swin},
 ]
 
 
@@ -64,6 +76,39 @@ def replace_module_by_qmodule_deit(model, qconfigs, pretrained_initialized=False
                 act_layer=cfg["act_layer"], pretrained_initialized=pretrained_initialized, **extra)
         set_module_by_name(model, name, qmodule)
     return model
+
+
+def replace_module_by_qmodule_swin(model, qconfigs, pretrained_initialized=False, qk_reparam=False, qk_reparam_type=0,
+                                   boundaryRange=0.005):
+    """utils.py:305-413. `features.0.0` (patch-embed conv) and `head` are always 8/8-bit LSQ; `features.N.reduction`
+    (nn.Linear, 4-D input) becomes a QLinear whose step sizes are per W' index."""
+    mapping = QMODULE_MAPPINGS_QK_REPARAM_SWIN[qk_reparam_type] if qk_reparam else QMODULE_MAPPINGS_SWIN
+    for name, cfg in qconfigs.items():
+        module = get_module_by_name(model, name)
+        if name == "features.0.0":
+            qmodule = LSQ_QConv2d(m=module, **_eight_bit_kwargs(cfg, pretrained_initialized))
+        elif name == "head":
+            qmodule = LSQ_QLinear4head(m=module, symmetric=True, **_eight_bit_kwargs(cfg, pretrained_initialized))
+        else:
+            qmodule = mapping[type(module)](
+                m=module, weight_bits=cfg["weight"]["bit"], input_bits=cfg["act"]["bit"],
+                weight_channelwise=cfg["weight"]["per_channel"], input_channelwise=cfg["act"]["per_channel"],
+                weight_quant_method=cfg["weight"]["mode"], input_quant_method=cfg["act"]["mode"],
+                aq_learnable=cfg["act"]["learnable"], wq_learnable=cfg["weight"]["learnable"],
+                act_layer=cfg["act_layer"], pretrained_initialized=pretrained_initialized)
+        set_module_by_name(model, name, qmodule)
+    return model
+
+
+def swin_qmodule_names(depths=(2, 2, 6, 2)):
+    """configs/swin_t_imagenet.attn_q.yml:44-73."""
+    names = ["features.0.0"]
+    for i, d in enumerate(depths):
+        for j in range(d):
+            names += [f"features.{2 * i + 1}.{j}.attn", f"features.{2 * i + 1}.{j}.mlp"]
+        if i < len(depths) - 1:
+            names.append(f"features.{2 * i + 2}.reduction")
+    return names + ["head"]
 
 
 def make_qconfigs(names, wq_bitw, aq_bitw, act_layer=torch.nn.GELU):

@@ -346,6 +346,88 @@ def deit_forward(img: Tensor, P: Params, depth: int, heads: int, wbits: int, abi
     return (cls + dist) / 2
 
 
+# ------------------------------------------------------------------------------------------ Swin
+def _rel_pos_index(ws):
+    """src/swin.py:203-213."""
+    coords = torch.stack(torch.meshgrid(torch.arange(ws[0]), torch.arange(ws[1]), indexing="ij"))
+    flat = torch.flatten(coords, 1)
+    rel = (flat[:, :, None] - flat[:, None, :]).permute(1, 2, 0).contiguous()
+    rel[:, :, 0] += ws[0] - 1
+    rel[:, :, 1] += ws[1] - 1
+    rel[:, :, 0] *= 2 * ws[1] - 1
+    return rel.sum(-1).view(-1)
+
+
+def swin_window_attention(x: Tensor, P: Params, pre: str, heads: int, wbits: int, abits: int, qkr: bool,
+                          window=(7, 7), shift=(0, 0)) -> Tensor:
+    """QAttention_swin.forward / QAttention_swin_qkreparam.forward, swin_attention_and_mlp.py:143-251 / 344-461:
+    pad, cyclic shift, window partition, quantized attention with relative-position bias and the 0/-100 shift mask,
+    proj, reverse."""
+    B, H, W, C = x.shape
+    N = window[0] * window[1]
+    bias = P[pre + "relative_position_bias_table"][_rel_pos_index(window)].view(N, N, -1).permute(2, 0, 1).contiguous().unsqueeze(0)
+    pad_r = (window[1] - W % window[1]) % window[1]
+    pad_b = (window[0] - H % window[0]) % window[0]
+    x = F.pad(x, (0, 0, 0, pad_r, 0, pad_b))
+    _, pH, pW, _ = x.shape
+    shift = list(shift)
+    if window[0] >= pH:
+        shift[0] = 0
+    if window[1] >= pW:
+        shift[1] = 0
+    if sum(shift) > 0:
+        x = torch.roll(x, shifts=(-shift[0], -shift[1]), dims=(1, 2))
+    nW = (pH // window[0]) * (pW // window[1])
+    x = x.view(B, pH // window[0], window[0], pW // window[1], window[1], C).permute(0, 1, 3, 2, 4, 5).reshape(B * nW, N, C)
+    full_bias = bias
+    if sum(shift) > 0:
+        m = x.new_zeros((pH, pW))
+        hs = ((0, -window[0]), (-window[0], -shift[0]), (-shift[0], None))
+        ws_ = ((0, -window[1]), (-window[1], -shift[1]), (-shift[1], None))
+        cnt = 0
+        for h in hs:
+            for w in ws_:
+                m[h[0]:h[1], w[0]:w[1]] = cnt
+                cnt += 1
+        m = m.view(pH // window[0], window[0], pW // window[1], window[1]).permute(0, 2, 1, 3).reshape(nW, N)
+        m = m.unsqueeze(1) - m.unsqueeze(2)
+        m = m.masked_fill(m != 0, float(-100.0)).masked_fill(m == 0, float(0.0))
+        full_bias = bias + m.repeat(B, 1, 1).unsqueeze(1)                      # [B*nW, 1|H, N, N]
+    out = (qattention_qkr if qkr else qattention)(x, P, pre, heads, wbits, abits, bias=full_bias)
+    out = out.view(B, pH // window[0], pW // window[1], window[0], window[1], C).permute(0, 1, 3, 2, 4, 5).reshape(B, pH, pW, C)
+    if sum(shift) > 0:
+        out = torch.roll(out, shifts=(shift[0], shift[1]), dims=(1, 2))
+    return out[:, :H, :W, :].contiguous()
+
+
+def swin_forward(img: Tensor, P: Params, depths, heads, wbits: int, abits: int, qkr: bool, state: Optional[dict] = None,
+                 window=(7, 7)) -> Tensor:
+    """SwinTransformer.forward (src/swin.py:430-448) with the qmodules of configs/swin_t_imagenet.attn_q.yml:44-73."""
+    state = {} if state is None else state
+    x = patch_embed_q(img, P, "features.0.0.", state).permute(0, 2, 3, 1)
+    C = x.shape[-1]
+    x = F.layer_norm(x, (C,), P["features.0.2.weight"], P["features.0.2.bias"], 1e-5)
+    for i, depth in enumerate(depths):
+        for j in range(depth):
+            pre = f"features.{2 * i + 1}.{j}."
+            C = x.shape[-1]
+            h = F.layer_norm(x, (C,), P[pre + "norm1.weight"], P[pre + "norm1.bias"], 1e-5)
+            shift = (0, 0) if j % 2 == 0 else (window[0] // 2, window[1] // 2)
+            x = x + swin_window_attention(h, P, pre + "attn.", heads[i], wbits, abits, qkr, window, shift)
+            h = F.layer_norm(x, (C,), P[pre + "norm2.weight"], P[pre + "norm2.bias"], 1e-5)
+            x = x + qmlp(h, P, pre + "mlp.", wbits, abits)
+        if i < len(depths) - 1:                                                 # PatchMerging, src/swin.py:40-59
+            pre = f"features.{2 * i + 2}."
+            Hh, Ww, _ = x.shape[-3:]
+            x = F.pad(x, (0, 0, 0, Ww % 2, 0, Hh % 2))
+            x = torch.cat([x[..., 0::2, 0::2, :], x[..., 1::2, 0::2, :], x[..., 0::2, 1::2, :], x[..., 1::2, 1::2, :]], -1)
+            x = F.layer_norm(x, (x.shape[-1],), P[pre + "norm.weight"], P[pre + "norm.bias"], 1e-5)
+            x = qlinear(x, P, pre + "reduction.", wbits, abits, symmetric=True)
+    x = F.layer_norm(x, (x.shape[-1],), P["norm.weight"], P["norm.bias"], 1e-5)
+    x = torch.flatten(F.adaptive_avg_pool2d(x.permute(0, 3, 1, 2), 1), 1)
+    return head_q(x, P, "head.")
+
+
 # ------------------------------------------------------------------------------------------ CGA
 def cga_freeze_mask(w: Tensor, bits: int, boundary_range: float = 0.005) -> Tensor:
     """freeze_outside_boundary_weight_idx, cga.py:450-469: 1.0 where the weight is frozen (its pre-round

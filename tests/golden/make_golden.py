@@ -220,6 +220,51 @@ def gen_deit():
         save(f"deit_tiny2_{'qkr' if qkr else 'plain'}_w2a2", d)
 
 
+# --------------------------------------------------------------------------------------- Swin
+def gen_swin():
+    from src.swin import ShiftedWindowAttention, SwinTransformer
+    from src.quantization.modules.swin_attention_and_mlp import QAttention_swin, QAttention_swin_qkreparam
+    from src.quantization.modules.utils import replace_module_by_qmodule_swin
+    torch.manual_seed(9)
+    dim, heads = 32, 2
+    for shift in (0, 3):
+        for cls, tag in ((QAttention_swin, "plain"), (QAttention_swin_qkreparam, "qkr")):
+            m = ShiftedWindowAttention(dim, [7, 7], [shift, shift], heads)
+            q = cls(m, weight_bits=3, input_bits=3, pretrained_initialized=True)
+            randomize_shifts(q)
+            with torch.no_grad():
+                q.relative_position_bias_table.copy_(torch.randn_like(q.relative_position_bias_table) * 0.2)
+            d = run_module(q, torch.randn(2, 14, 14, dim))
+            d = {k: v for k, v in d.items() if not k.endswith("relative_position_index")}
+            save(f"qattention_swin_{tag}_shift{shift}_w3a3", d)
+    for qkr in (False, True):
+        torch.manual_seed(10)
+        model = SwinTransformer(patch_size=[4, 4], embed_dim=32, depths=[2, 2], num_heads=[1, 2], window_size=[7, 7], num_classes=10)
+        names = ["features.0.0", "features.1.0.attn", "features.1.0.mlp", "features.1.1.attn", "features.1.1.mlp",
+                 "features.2.reduction", "features.3.0.attn", "features.3.0.mlp", "features.3.1.attn", "features.3.1.mlp", "head"]
+        model = replace_module_by_qmodule_swin(model, ref_shim.qconfigs(names, 3, 3), pretrained_initialized=True,
+                                               qk_reparam=qkr, qk_reparam_type=0)
+        randomize_shifts(model, std=0.02)
+        img = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(11))
+        labels = torch.tensor([2, 8])
+        model.eval()
+        with torch.no_grad():
+            model(img)
+        model.train()
+        logits, _ = model(img)
+        loss = nn.functional.cross_entropy(logits, labels)
+        loss.backward()
+        d = {"img_seed": 11, "labels": labels, "logits": logits, "loss": loss}
+        d.update({"param." + k: v for k, v in model.state_dict().items() if not k.endswith("relative_position_index")})
+        for n, p in model.named_parameters():
+            if p.grad is None:
+                continue
+            g = p.grad
+            d["gnorm." + n] = g.norm()
+            d["grad." + n] = g if g.numel() <= 4096 else g.flatten()[:: max(1, g.numel() // 2048)][:2048]
+        save(f"swin_tiny2_{'qkr' if qkr else 'plain'}_w3a3", d)
+
+
 # --------------------------------------------------------------------------------------- CGA
 def load_reference_function(path, name):
     """exec a single top-level function of a reference script without importing the script (cga.py needs timm)."""
@@ -269,4 +314,5 @@ if __name__ == "__main__":
     gen_lsq()
     gen_layers()
     gen_deit()
+    gen_swin()
     gen_cga()

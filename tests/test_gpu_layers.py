@@ -33,6 +33,7 @@ def load_params(mod, g):
     sd = {k[len("param."):]: v for k, v in g.items() if k.startswith("param.")}
     missing, unexpected = mod.load_state_dict(sd, strict=False)
     assert not unexpected, unexpected
+    missing = [m for m in missing if not m.endswith("relative_position_index")]   # a constant buffer, not stored in goldens
     assert not missing, missing          # lazily created LSQ scales must load from a checkpoint too
     return mod
 
@@ -142,3 +143,31 @@ def test_deit_step_against_reference(Q, qkr):
     with torch.no_grad():
         ev, _ = model(img)
     assert rel_err(ev.cpu(), g["eval_logits"]) < OUT_TOL
+
+
+@pytest.mark.parametrize("shift", [0, 3])
+@pytest.mark.parametrize("qkr", [False, True])
+def test_swin_window_attention(Q, shift, qkr):
+    """Quantized shifted-window attention (relative-position bias + 0/-100 shift mask), W3A3, vs the reference."""
+    from ofq_b200.host.swin import ShiftedWindowAttention
+    cls = Q.QAttention_swin_qkreparam if qkr else Q.QAttention_swin
+    mod = cls(ShiftedWindowAttention(32, [7, 7], [shift, shift], 2), weight_bits=3, input_bits=3)
+    run_layer(mod, load_golden(f"qattention_swin_{'qkr' if qkr else 'plain'}_shift{shift}_w3a3"))
+
+
+@pytest.mark.parametrize("qkr", [False, True])
+def test_swin_step_against_reference(Q, qkr):
+    """Two-stage Swin (depths 2+2, width 32/64, 7x7 windows, patch merging `reduction` QLinear), W3A3."""
+    from ofq_b200.host.swin import SwinTransformer
+    g = load_golden(f"swin_tiny2_{'qkr' if qkr else 'plain'}_w3a3")
+    model = SwinTransformer(embed_dim=32, depths=(2, 2), num_heads=(1, 2), num_classes=10)
+    names = Q.swin_qmodule_names((2, 2))
+    model = Q.replace_module_by_qmodule_swin(model, Q.make_qconfigs(names, 3, 3), pretrained_initialized=True, qk_reparam=qkr)
+    model = load_params(model, g).cuda().train()
+    img = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(int(g["img_seed"]))).cuda()
+    logits, _ = model(img)
+    assert rel_err(logits.detach().cpu(), g["logits"]) < OUT_TOL
+    loss = F.cross_entropy(logits, g["labels"].cuda())
+    assert abs(loss.item() - g["loss"].item()) <= OUT_TOL * abs(g["loss"].item())
+    loss.backward()
+    assert check_grads(model.named_parameters(), g, sampled=True) > 80

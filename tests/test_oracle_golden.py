@@ -173,3 +173,36 @@ def test_cga_masked_adamw():
         assert rel_err(w, g[f"step{step}.w"]) < 1e-7
         assert rel_err(m, g[f"step{step}.exp_avg"]) < 1e-6
         assert rel_err(v, g[f"step{step}.exp_avg_sq"]) < 1e-6
+
+
+@pytest.mark.parametrize("shift", [0, 3])
+@pytest.mark.parametrize("qkr", [False, True])
+def test_swin_window_attention(shift, qkr):
+    name = f"qattention_swin_{'qkr' if qkr else 'plain'}_shift{shift}_w3a3"
+    _check_layer(name, lambda x, P: O.swin_window_attention(x, P, "", 2, 3, 3, qkr, (7, 7), (shift, shift)))
+
+
+@pytest.mark.parametrize("qkr", [False, True])
+def test_swin_step(qkr):
+    g = load_golden(f"swin_tiny2_{'qkr' if qkr else 'plain'}_w3a3")
+    P = params_from(g)
+    img = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(int(g["img_seed"])))
+    state = {"signed": int(g["param.features.0.0.input_quant_fn.signed"].item())}
+    logits = O.swin_forward(img, P, (2, 2), (1, 2), 3, 3, qkr, state)
+    assert torch.equal(logits, g["logits"])
+    loss = F.cross_entropy(logits, g["labels"])
+    assert torch.equal(loss, g["loss"])
+    loss.backward()
+    n = 0
+    for k, v in g.items():
+        if not k.startswith("gnorm."):
+            continue
+        name = k[len("gnorm."):]
+        gr = P[name].grad
+        assert gr is not None, name
+        ref = g["grad." + name]
+        mine = gr if gr.numel() <= 4096 else gr.flatten()[:: max(1, gr.numel() // 2048)][:2048]
+        scale = max(ref.abs().max().item(), 1e-12)
+        assert (mine - ref).abs().max().item() <= 1e-4 * scale + 1e-10, name
+        n += 1
+    assert n > 80
