@@ -201,6 +201,17 @@ OFQ_API int ofq_counter_increment(int* counter, void* stream);
 OFQ_API int ofq_adamw_multi(const void* table, int n_entries, int total_blocks, int step, double lr, double beta1,
                             double beta2, double eps, const int* step_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Host glue around the quantized layers: fp32 LayerNorm (nn.LayerNorm semantics: biased
+ * variance, eps inside the square root) of the DeiT / Swin blocks (deit_vision_transformer.py:154-164).
+ * mean / rstd [rows] are saved for the backward. workspace: float[ofq_layernorm_bwd_workspace(rows, cols)]. */
+OFQ_API int ofq_layernorm_fwd(const float* x, long long rows, int cols, const float* gamma, const float* beta,
+                              float eps, float* y, float* mean, float* rstd, void* stream);
+OFQ_API long long ofq_layernorm_bwd_workspace(long long rows, int cols);
+OFQ_API int ofq_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
+                              const float* rstd, long long rows, int cols, float* dx, float* dgamma, float* dbeta,
+                              float* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

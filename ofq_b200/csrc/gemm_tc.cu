@@ -394,16 +394,14 @@ extern "C" int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B
         ofq_set_error("ofq_gemm: split-K requires an accumulating (pre-zeroed) output");
         return OFQ_ERR_ARG;
     }
-    // tile width: fewest wasted columns first, then the widest tile (fewer re-reads of the row operand from L2)
-    static const int widths[] = {256, 192, 128, 64, 32};
+    // tile width: minimise (number of N tiles) x (per-tile fixed cost + tile width); the fixed cost (pipeline fill,
+    // barrier round trips, epilogue start-up) is worth about 128 columns of MMA/epilogue work
+    static const int widths[] = {256, 224, 192, 128, 64, 32};
     int bn = 32;
     long long best_cost = -1;
     for (int w : widths) {
         const long long nt = (N + w - 1) / w;
-        const long long padded = nt * w;
-        // cost ~ MMA columns issued; tie-break on wider tiles. Very small problems prefer more CTAs.
-        const long long ctas = (long long)((M + BM - 1) / BM) * nt * nb1 * nb2 * splits;
-        long long cost = padded * 16 + (ctas < 148 && w > 64 ? (148 - ctas) : 0) - w / 64;
+        const long long cost = nt * (128 + w);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; bn = w; }
     }
     CUtensorMap tmA, tmB, tmC;
@@ -417,6 +415,7 @@ extern "C" int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B
 #define OFQ_DISPATCH(KIND)                                                   \
     switch (bn) {                                                            \
         case 256: return launch_gemm<KIND, 256, 3>(tmA, tmB, tmC, p, st);    \
+        case 224: return launch_gemm<KIND, 224, 3>(tmA, tmB, tmC, p, st);    \
         case 192: return launch_gemm<KIND, 192, 3>(tmA, tmB, tmC, p, st);    \
         case 128: return launch_gemm<KIND, 128, 4>(tmA, tmB, tmC, p, st);    \
         case 64:  return launch_gemm<KIND, 64, 6>(tmA, tmB, tmC, p, st);     \

@@ -12,6 +12,8 @@ from functools import partial
 import torch
 import torch.nn as nn
 
+from .layers import LayerNorm
+
 
 class PatchEmbed(nn.Module):
     def __init__(self, img_size=224, patch_size=16, in_chans=3, embed_dim=768):
@@ -73,7 +75,7 @@ class Block(nn.Module):
     """deit_vision_transformer.py:132-164."""
 
     def __init__(self, dim, num_heads, mlp_ratio=4.0, qkv_bias=False, drop=0.0, attn_drop=0.0,
-                 act_layer=nn.GELU, norm_layer=nn.LayerNorm):
+                 act_layer=nn.GELU, norm_layer=LayerNorm):
         super().__init__()
         self.norm1 = norm_layer(dim)
         self.attn = Attention(dim, num_heads=num_heads, qkv_bias=qkv_bias, attn_drop=attn_drop, proj_drop=drop)
@@ -94,7 +96,7 @@ class DistilledVisionTransformer(nn.Module):
     def __init__(self, img_size=224, patch_size=16, in_chans=3, num_classes=1000, embed_dim=768, depth=12, num_heads=12,
                  mlp_ratio=4.0, qkv_bias=True, norm_layer=None, act_layer=None):
         super().__init__()
-        norm_layer = norm_layer or partial(nn.LayerNorm, eps=1e-6)
+        norm_layer = norm_layer or partial(LayerNorm, eps=1e-6)
         act_layer = act_layer or nn.GELU
         self.num_classes = num_classes
         self.num_features = self.embed_dim = embed_dim

