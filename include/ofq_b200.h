@@ -50,6 +50,9 @@ typedef struct {
     long long row_stride; /* elements between consecutive rows (m or n) */
     long long k2_stride;  /* elements between outer-K slices; 0 = the operand is shared by all slices */
     int k2_mod;           /* > 0: slice index used for this operand is (k2 index % k2_mod); 0: the k2 index itself */
+    int dual_delta;       /* A operand only, bf16: > 0 loads slices k2 and k2 + dual_delta in the same pipeline stage and
+                             multiplies both with one copy of B (hi / lo planes of a gradient operand); the operand then
+                             holds k2 + dual_delta slices. 0 = off */
     long long bstride1;   /* elements between batch-axis-1 entries, 0 = broadcast */
     long long bstride2;   /* elements between batch-axis-2 entries, 0 = broadcast */
 } ofq_operand_t;

@@ -19,7 +19,7 @@ class OfqError(RuntimeError):
 
 class Operand(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("row_stride", C.c_longlong), ("k2_stride", C.c_longlong), ("k2_mod", C.c_int),
-                ("bstride1", C.c_longlong), ("bstride2", C.c_longlong)]
+                ("dual_delta", C.c_int), ("bstride1", C.c_longlong), ("bstride2", C.c_longlong)]
 
 
 class Vec(C.Structure):

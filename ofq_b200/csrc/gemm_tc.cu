@@ -36,18 +36,20 @@ struct GemmParams {
     int a_b1, a_b2, b_b1, b_b2, c_b1, c_b2;
     int a_k2, b_k2;          // 0: operand shared by all outer-K slices
     int a_k2mod, b_k2mod;    // slice index = k2 % mod
+    int a_dual_delta;        // dual-A: second A tile of a stage comes from outer-K slice (k2 + delta)
     VecRef rs, cs, rt, ct;
     int has_rank1;
     int atomic;
 };
 
-constexpr int OUT_BUFS = 2;      // TMA-store staging buffers per epilogue warp (stores in flight)
-
-template <int BN, int STAGES>
+// NA: A tiles per pipeline stage. NA = 2 ("dual-A") loads the bf16 hi and lo planes of a gradient operand together with
+// ONE copy of the shared code operand B, instead of streaming B twice: a third less L2 -> SM traffic per MAC.
+// OUT_BUFS: TMA-store staging buffers per epilogue warp (stores in flight).
+template <int BN, int STAGES, int NA, int OUT_BUFS>
 struct SmemLayout {
     static constexpr uint32_t A_BYTES = BM * KBYTES;
     static constexpr uint32_t B_BYTES = BN * KBYTES;
-    static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr uint32_t STAGE_BYTES = NA * A_BYTES + B_BYTES;
     static constexpr uint32_t OUT_OFF = STAGES * STAGE_BYTES;          // 4 warps x OUT_BUFS x (32 x 128 B), swizzled
     static constexpr uint32_t OUT_BYTES = EPI_WARPS * OUT_BUFS * 4096;
     static constexpr uint32_t VEC_OFF = OUT_OFF + OUT_BYTES;            // 2 x {cs[BN], ct[BN]} (double buffered)
@@ -79,12 +81,12 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t, int
 // Persistent, warp-specialised: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The smem ring runs
 // across tile boundaries and the TMEM accumulator is double buffered, so the epilogue of tile i overlaps the TMA
 // loads and MMAs of tile i+1.
-template <int KIND, int BN, int STAGES>
+template <int KIND, int BN, int STAGES, int NA, int OUT_BUFS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmParams p, const int num_tiles,
                const int mtiles, const int ntiles) {
-    using L = SmemLayout<BN, STAGES>;
+    using L = SmemLayout<BN, STAGES, NA, OUT_BUFS>;
     constexpr uint32_t A_BYTES = L::A_BYTES;
     constexpr uint32_t STAGE_BYTES = L::STAGE_BYTES;
     constexpr uint32_t ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));   // per accumulator stage
@@ -143,9 +145,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int g = c.it_begin + i;
                     const int k2i = g / p.kblocks, kb = g % p.kblocks;
                     uint8_t* sa = smem + s * STAGE_BYTES;
-                    uint8_t* sb = sa + A_BYTES;
+                    uint8_t* sb = sa + NA * A_BYTES;
                     mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
                     tma_load_5d(sa, &tmA, &full_bar[s], kb * kelem, c.m0, (k2i % p.a_k2mod) * p.a_k2, c.b1 * p.a_b1, c.b2 * p.a_b2);
+                    if (NA == 2)
+                        tma_load_5d(sa + A_BYTES, &tmA, &full_bar[s], kb * kelem, c.m0, k2i + p.a_dual_delta, c.b1 * p.a_b1, c.b2 * p.a_b2);
                     tma_load_5d(sb, &tmB, &full_bar[s], kb * kelem, c.n0, (k2i % p.b_k2mod) * p.b_k2, c.b1 * p.b_b1, c.b2 * p.b_b2);
                 }
             }
@@ -165,15 +169,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-                    const uint64_t adesc = umma_desc_kmajor_sw128(sa);
-                    const uint64_t bdesc = umma_desc_kmajor_sw128(sa + A_BYTES);
+                    const uint64_t bdesc = umma_desc_kmajor_sw128(sa + NA * A_BYTES);
 #pragma unroll
-                    for (uint32_t kk = 0; kk < KBYTES / UMMA_K_BYTES; ++kk) {
-                        const uint64_t adv = (kk * UMMA_K_BYTES) >> 4;
-                        if (KIND == 0)
-                            umma_i8(tmem_d, adesc + adv, bdesc + adv, IDESC, (i | kk) != 0);
-                        else
-                            umma_f16(tmem_d, adesc + adv, bdesc + adv, IDESC, (i | kk) != 0);
+                    for (uint32_t na = 0; na < (uint32_t)NA; ++na) {
+                        const uint64_t adesc = umma_desc_kmajor_sw128(sa + na * A_BYTES);
+#pragma unroll
+                        for (uint32_t kk = 0; kk < KBYTES / UMMA_K_BYTES; ++kk) {
+                            const uint64_t adv = (kk * UMMA_K_BYTES) >> 4;
+                            if (KIND == 0)
+                                umma_i8(tmem_d, adesc + adv, bdesc + adv, IDESC, (i | kk | na) != 0);
+                            else
+                                umma_f16(tmem_d, adesc + adv, bdesc + adv, IDESC, (i | kk | na) != 0);
+                        }
                     }
                     tc_commit(&empty_bar[s]);      // frees the smem stage when these MMAs retire
                 }
@@ -282,12 +289,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------ host side
-template <int KIND, int BN, int STAGES>
+template <int KIND, int BN, int STAGES, int NA = 1, int OUT_BUFS = 2>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                        const GemmParams& p, cudaStream_t stream) {
-    constexpr size_t smem = SmemLayout<BN, STAGES>::DYN_BYTES;
+    constexpr size_t smem = SmemLayout<BN, STAGES, NA, OUT_BUFS>::DYN_BYTES;
     static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
-    auto kern = gemm_tc_kernel<KIND, BN, STAGES>;
+    auto kern = gemm_tc_kernel<KIND, BN, STAGES, NA, OUT_BUFS>;
     static bool configured = false;  // per instantiation; attribute is per function, idempotent
     if (!configured) {
         OFQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -321,7 +328,8 @@ using namespace ofq;
 // Build a 5-D tensor map {K, rows, k2, b1, b2} with a {128 bytes of K, box_rows, 1, 1, 1} box, 128B swizzle.
 static int make_operand_map(CUtensorMap* tm, const ofq_operand_t* op, int elem_bytes, int rows, int K,
                             int k2, int nb1, int nb2, int box_rows) {
-    const int k2_eff = op->k2_stride ? (op->k2_mod > 0 ? (op->k2_mod < k2 ? op->k2_mod : k2) : k2) : 1;
+    int k2_eff = op->k2_stride ? (op->k2_mod > 0 ? (op->k2_mod < k2 ? op->k2_mod : k2) : k2) : 1;
+    if (op->dual_delta > 0) k2_eff = k2 + op->dual_delta;     // slices [0, k2) and [delta, delta + k2) are both addressed
     cuuint64_t dims[5] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)k2_eff,
                           (cuuint64_t)(op->bstride1 ? nb1 : 1), (cuuint64_t)(op->bstride2 ? nb2 : 1)};
     const cuuint64_t row_b = (cuuint64_t)op->row_stride * elem_bytes;
@@ -384,6 +392,7 @@ extern "C" int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B
     p.a_b1 = A->bstride1 != 0; p.a_b2 = A->bstride2 != 0;
     p.b_b1 = B->bstride1 != 0; p.b_b2 = B->bstride2 != 0;
     p.a_k2 = A->k2_stride != 0; p.b_k2 = B->k2_stride != 0;
+    p.a_dual_delta = A->dual_delta;
     p.a_k2mod = A->k2_mod > 0 ? A->k2_mod : 0x7fffffff;
     p.b_k2mod = B->k2_mod > 0 ? B->k2_mod : 0x7fffffff;
     p.c_b1 = out->bstride1 != 0; p.c_b2 = out->bstride2 != 0;
@@ -420,6 +429,20 @@ extern "C" int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B
         case 128: return launch_gemm<KIND, 128, 4>(tmA, tmB, tmC, p, st);    \
         case 64:  return launch_gemm<KIND, 64, 6>(tmA, tmB, tmC, p, st);     \
         default:  return launch_gemm<KIND, 32, 6>(tmA, tmB, tmC, p, st);     \
+    }
+    if (A->dual_delta > 0) {
+        if (kind != OFQ_GEMM_BF16 || B->dual_delta != 0 || A->k2_stride == 0) {
+            ofq_set_error("ofq_gemm: dual_delta is for a bf16 A operand with an outer-K stride");
+            return OFQ_ERR_ARG;
+        }
+        switch (bn) {
+            case 256: return launch_gemm<1, 256, 2, 2, 2>(tmA, tmB, tmC, p, st);
+            case 224: return launch_gemm<1, 224, 3, 2, 1>(tmA, tmB, tmC, p, st);
+            case 192: return launch_gemm<1, 192, 3, 2, 1>(tmA, tmB, tmC, p, st);
+            case 128: return launch_gemm<1, 128, 3, 2, 2>(tmA, tmB, tmC, p, st);
+            case 64:  return launch_gemm<1, 64, 4, 2, 2>(tmA, tmB, tmC, p, st);
+            default:  return launch_gemm<1, 32, 4, 2, 2>(tmA, tmB, tmC, p, st);
+        }
     }
     if (kind == OFQ_GEMM_I8) { OFQ_DISPATCH(0) } else { OFQ_DISPATCH(1) }
 #undef OFQ_DISPATCH

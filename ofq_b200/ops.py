@@ -61,21 +61,21 @@ def vec(t: Optional[torch.Tensor], period: int = 0, bs1: int = 0, bs2: int = 0):
 
 def gemm(kind: int, a: torch.Tensor, a_strides, b: torch.Tensor, b_strides, out: torch.Tensor, out_strides,
          M: int, N: int, K: int, *, k2: int = 1, nb1: int = 1, nb2: int = 1, splits: int = 1, accumulate: bool = False,
-         rs=None, cs=None, rt=None, ct=None, a_k2mod: int = 0, b_k2mod: int = 0) -> None:
+         rs=None, cs=None, rt=None, ct=None, a_k2mod: int = 0, b_k2mod: int = 0, a_dual_delta: int = 0) -> None:
     """Raw ofq_gemm call. a_strides/b_strides = (row, k2, batch1, batch2) in elements; out_strides = (ld, b1, b2).
     rs/cs/rt/ct are ctypes Vec references from `vec()` or None."""
     _cuda(a, b, out)
-    A = Operand(a.data_ptr(), a_strides[0], a_strides[1], a_k2mod, a_strides[2], a_strides[3])
-    B = Operand(b.data_ptr(), b_strides[0], b_strides[1], b_k2mod, b_strides[2], b_strides[3])
+    A = Operand(a.data_ptr(), a_strides[0], a_strides[1], a_k2mod, a_dual_delta, a_strides[2], a_strides[3])
+    B = Operand(b.data_ptr(), b_strides[0], b_strides[1], b_k2mod, 0, b_strides[2], b_strides[3])
     O = GemmOut(out.data_ptr(), *out_strides, 1 if accumulate else 0)
     eb = 1 if kind == GEMM_I8 else 2
 
     def _n(strides, mod):
-        k2n = (min(mod, k2) if mod else k2) if strides[1] else 1
+        k2n = ((min(mod, k2) if mod else k2) + (a_dual_delta if strides is a_strides and a_dual_delta else 0)) if strides[1] else 1
         return k2n * (nb1 if strides[2] else 1) * (nb2 if strides[3] else 1)
     nout = (nb1 if out_strides[1] else 1) * (nb2 if out_strides[2] else 1)
     alg_bytes = eb * K * (M * _n(a_strides, a_k2mod) + N * _n(b_strides, b_k2mod)) + 4 * M * N * nout * (2 if accumulate else 1)
-    alg_flops = 2.0 * M * N * K * k2 * nb1 * nb2
+    alg_flops = 2.0 * M * N * K * k2 * nb1 * nb2 * (2 if a_dual_delta else 1)
     _call("gemm_i8" if kind == GEMM_I8 else "gemm_bf16", 1, alg_bytes, alg_flops, _lib.load().ofq_gemm, kind,
           C.byref(A), C.byref(B), C.byref(O), M, N, K, k2, nb1, nb2, splits, rs, cs, rt, ct, _st())
 

@@ -21,6 +21,11 @@ NUM_SMS = 148
 # bf16 planes of every real-valued backward GEMM operand: 2 = hi + lo split (~16 mantissa bits, meets the 1e-3
 # parity bound on every gradient), 1 = plain bf16 (~1-2e-3 gradient error, half the operand traffic).
 PLANES = int(os.environ.get("OFQ_BWD_PLANES", "2"))
+# With two planes the GEMM loads hi and lo of the gradient operand in the same pipeline stage and multiplies both by
+# one copy of the code operand ("dual-A", ofq_operand_t.dual_delta) instead of looping over planes as outer-K slices.
+DUAL = PLANES == 2
+K2P = 1 if DUAL else PLANES          # outer-K slices still looped over
+DD = 1 if DUAL else 0                # dual_delta for operands laid out [plane][...]
 
 
 def levels(bit: int, all_positive: bool):
@@ -54,15 +59,15 @@ def _linear_backward(dY2d, qx, wc, colscale, se_x, period, x_aft, dxhat, accumul
     wcT = ops.codes_to_bf16(wc, 1, Nout, K, K, 0, True)            # [1, K, nout_pad]
     nout_pad = wcT.shape[-1]
     ops.gemm(GEMM_BF16, prep["rm"], (Nout, M * Nout, 0, 0), wcT, (nout_pad, 0, 0, 0), dxhat, (K, 0, 0), M, K, Nout,
-             k2=PLANES, accumulate=accumulate_dx)
+             k2=K2P, a_dual_delta=DD, accumulate=accumulate_dx)
     # dW[Nout,K] = (dY * se_x)^T[Nout,M] @ qx[M,K]  + colsum(dY)[Nout] x aft[K]
     if qxT_all is None:
         qxT_all = ops.codes_to_bf16(qx, 1, M, K, K, 0, True)       # [1, K, m_pad]
     dW = torch.zeros((Nout, K), dtype=torch.float32, device=dY2d.device)
     tiles = ((Nout + 127) // 128) * ((K + 127) // 128)
-    splits = _splits_for(tiles, PLANES * ((M + 63) // 64))
+    splits = _splits_for(tiles, K2P * ((M + 63) // 64))
     ops.gemm(GEMM_BF16, prep["t"], (m_pad, Nout * m_pad, 0, 0), qxT_all, (m_pad, 0, 0, 0), dW, (K, 0, 0), Nout, K, M,
-             k2=PLANES, splits=splits, accumulate=True, rt=vec(prep["colsum"]), ct=vec(x_aft))
+             k2=K2P, a_dual_delta=DD, splits=splits, accumulate=True, rt=vec(prep["colsum"]), ct=vec(x_aft))
     return dW, prep["colsum"], qxT_all
 
 
@@ -164,7 +169,7 @@ def _pv_backward(dO, qp, ldq, qv, se_p, se_v, v_aft, B, N, H, C, ldS):
     qv16 = ops.codes_to_bf16(qv, B, N, C, C, N * C, False)           # [B, N, C] bf16
     dPq = torch.empty((B * H, N, ldS), dtype=torch.float32, device=dO.device)
     ops.gemm(GEMM_BF16, prep["rm"], (C, B * N * C, hd, N * C), qv16, (C, 0, hd, N * C), dPq, (ldS, N * ldS, H * N * ldS),
-             N, N, hd, k2=PLANES, nb1=H, nb2=B, rt=vec(prep["rowdot"], 0, N, H * N))
+             N, N, hd, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B, rt=vec(prep["rowdot"], 0, N, H * N))
     # dv_hat[b,d,hj] = sum_n qp[z,n,d] (se_p[n] dO[b,n,hj])
     qpT = ops.codes_to_bf16(qp, B * H, N, ldq, ldq, N * ldq, True)   # [B*H, ldq, npad8]; rows d >= N are zero
     dvhat = torch.empty((B, N, C), dtype=torch.float32, device=dO.device)
@@ -255,13 +260,18 @@ class QKRAttnCoreFn(torch.autograd.Function):
         # --- scores: d x_hat += sum_h dS (k_hat)   (outer-K loop over heads)
         qkT = ops.codes_to_bf16(qk, B, N, H * C, H * C, N * H * C, True)      # [B, H*C, npad8]
         npad8 = qkT.shape[-1]
-        ops.gemm(GEMM_BF16, dSa, (ldo, slab, PLANES * H * slab, 0), qkT, (npad8, C * npad8, H * C * npad8, 0),
-                 dxhat, (C, N * C, 0), N, C, N, k2=PLANES * H, nb1=B, accumulate=True, b_k2mod=H)
+        if DUAL:     # planes of head h are outer-K slices h and h + H of dSa [B, 2, H, N, ldo]
+            ops.gemm(GEMM_BF16, dSa, (ldo, slab, PLANES * H * slab, 0), qkT, (npad8, C * npad8, H * C * npad8, 0),
+                     dxhat, (C, N * C, 0), N, C, N, k2=H, a_dual_delta=H, nb1=B, accumulate=True)
+        else:
+            ops.gemm(GEMM_BF16, dSa, (ldo, slab, PLANES * H * slab, 0), qkT, (npad8, C * npad8, H * C * npad8, 0),
+                     dxhat, (C, N * C, 0), N, C, N, k2=PLANES * H, nb1=B, accumulate=True, b_k2mod=H)
         # --- scores: d k_hat[b,d,h,c] = sum_n dS[n,d] x_hat[n,c]
         qxT_b = ops.codes_to_bf16(qx, B, N, C, C, N * C, True)                # [B, C, npad8]
         dkhat = torch.empty((M, H * C), dtype=torch.float32, device=dev)
         ops.gemm(GEMM_BF16, dSbT, (ldo, H * slab, slab, PLANES * H * slab), qxT_b, (npad8, 0, 0, C * npad8), dkhat,
-                 (H * C, C, N * H * C), N, C, N, k2=PLANES, nb1=H, nb2=B, rt=vec(colsum_dS, 0, N, H * N), ct=vec(x_aft))
+                 (H * C, C, N * H * C), N, C, N, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B, rt=vec(colsum_dS, 0, N, H * N),
+                 ct=vec(x_aft))
         del dSa, dSbT
         # --- qkx quantizer and the qkx "linear" layer (weight = StatsQ(W_q^T W_k), no bias)
         dqkx, ds_k, dkb4, dkaft = ops.lsq_bwd(dkhat, qkx, k_b4, se_k, PER_ROW, N, H, lo, hi, g_k)
@@ -339,12 +349,13 @@ class QAttnCoreFn(torch.autograd.Function):
         npad8 = qkT.shape[-1]
         dqhat = torch.empty((M, C), dtype=torch.float32, device=dev)
         ops.gemm(GEMM_BF16, dSa, (ldo, H * slab, slab, PLANES * H * slab), qkT, (npad8, 0, hd * npad8, C * npad8), dqhat,
-                 (C, hd, N * C), N, hd, N, k2=PLANES, nb1=H, nb2=B)
+                 (C, hd, N * C), N, hd, N, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B)
         # dk_hat[b,d,hj] = sum_n (dS se_q[n]) qq[b,n,hj] + colsum_dS[z,d] q_aft[hj]
         qqT = ops.codes_to_bf16(qq, B, N, C, C, N * C, True)
         dkhat = torch.empty((M, C), dtype=torch.float32, device=dev)
         ops.gemm(GEMM_BF16, dSbT, (ldo, H * slab, slab, PLANES * H * slab), qqT, (npad8, 0, hd * npad8, C * npad8), dkhat,
-                 (C, hd, N * C), N, hd, N, k2=PLANES, nb1=H, nb2=B, rt=vec(colsum_dS, 0, N, H * N), ct=vec(q_aft, 0, hd))
+                 (C, hd, N * C), N, hd, N, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B, rt=vec(colsum_dS, 0, N, H * N),
+                 ct=vec(q_aft, 0, hd))
         dq, ds_q, db4_q, daft_q = ops.lsq_bwd(dqhat, q2d[:, 0:C], b4[0:C], se_q, PER_ROW, N, 1, lo, hi, g_qk)
         dk, ds_k, db4_k, daft_k = ops.lsq_bwd(dkhat, q2d[:, C:2 * C], b4[C:2 * C], se_k, PER_ROW, N, 1, lo, hi, g_qk)
         dv, ds_v, db4_v, daft_v = ops.lsq_bwd(dvhat.view(M, C), q2d[:, 2 * C:], b4[2 * C:], se_v, PER_COL, 1, 1, lo, hi, g_v)

@@ -233,10 +233,36 @@ def test_gemm_outer_k_accumulate(ops):
              out, (Cc, Nt * Cc, 0), Nt, Cc, Nt, k2=2 * H, nb1=Bt, b_k2mod=H)
     ref2 = torch.einsum("bhnd,bhcd->bnc", dS.double(), kT.double())
     assert rel_err(out, ref2) < 2e-5
+    # dual-A: hi and lo of head h are loaded in one stage (slices h and h + H), B is read once per head
+    ops.gemm(ops.GEMM_BF16, A2, (NP, Nt * NP, 2 * H * Nt * NP, 0), kT.bfloat16(), (NP, Cc * NP, H * Cc * NP, 0),
+             out, (Cc, Nt * Cc, 0), Nt, Cc, Nt, k2=H, nb1=Bt, a_dual_delta=H)
+    assert rel_err(out, ref2) < 2e-5
     A3 = torch.stack((hi[:, 0], lo[:, 0]), dim=0).contiguous()           # [2, B, N, NP], head 0 only
     ops.gemm(ops.GEMM_BF16, A3, (NP, Bt * Nt * NP, Nt * NP, 0), kT.bfloat16()[:, 0].contiguous(), (NP, 0, Cc * NP, 0),
              out, (Cc, Nt * Cc, 0), Nt, Cc, Nt, k2=2, nb1=Bt)
     assert rel_err(out, torch.einsum("bnd,bcd->bnc", dS[:, 0].double(), kT[:, 0].double())) < 2e-5
+    ops.gemm(ops.GEMM_BF16, A3, (NP, Bt * Nt * NP, Nt * NP, 0), kT.bfloat16()[:, 0].contiguous(), (NP, 0, Cc * NP, 0),
+             out, (Cc, Nt * Cc, 0), Nt, Cc, Nt, k2=1, nb1=Bt, a_dual_delta=1)
+    assert rel_err(out, torch.einsum("bnd,bcd->bnc", dS[:, 0].double(), kT[:, 0].double())) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(25344, 384, 1536, 1), (1536, 384, 25344, 9), (300, 200, 500, 1), (128, 64, 64, 1)])
+def test_gemm_bf16_dual_planes(ops, M, N, K, splits):
+    """hi + lo planes of a real-valued operand against exact integer codes: ~16 mantissa bits, one B load per stage."""
+    torch.manual_seed(18)
+    Kp = ops.round_up(K, 8)
+    x = torch.randn(M, K, device="cuda")
+    hi = x.bfloat16()
+    lo = (x - hi.float()).bfloat16()
+    A = torch.zeros(2, M, Kp, device="cuda", dtype=torch.bfloat16)
+    A[0, :, :K], A[1, :, :K] = hi, lo
+    Bm = torch.zeros(N, Kp, device="cuda", dtype=torch.bfloat16)
+    Bm[:, :K] = torch.randint(-3, 4, (N, K), device="cuda").bfloat16()
+    out = torch.zeros(M, ops.round_up(N, 4), device="cuda")
+    ops.gemm(ops.GEMM_BF16, A, (Kp, M * Kp, 0, 0), Bm, (Kp, 0, 0, 0), out, (out.shape[1], 0, 0), M, N, K, k2=1,
+             a_dual_delta=1, splits=splits, accumulate=splits > 1)
+    ref = x.double() @ Bm[:, :K].double().T
+    assert rel_err(out[:, :N], ref) < 2e-5
 
 
 # ------------------------------------------------------------------------------------------------ prep kernels
