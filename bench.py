@@ -29,6 +29,9 @@ MODELS = {"deit_small": dict(embed_dim=384, depth=12, num_heads=6), "deit_tiny":
 GFLOP_FWD_PER_IMG = {"deit_small": 13.74, "deit_tiny": 3.00}
 
 
+BWD_DTYPE = {"f16": "range-scaled fp16", "bf16x2": "bf16 hi+lo", "bf16": "bf16"}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -41,6 +44,7 @@ def parse():
     ap.add_argument("--no-qkr", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=8, help="images per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sites", default="", help="write a per-call-site kernel timing table of the instrumented steps here")
     ap.add_argument("--graph", default="on", choices=["on", "off"],
                     help="capture the whole QAT step (fwd+bwd+all-reduce+AdamW) in one CUDA graph and replay it")
     return ap.parse_args()
@@ -188,6 +192,7 @@ def main():
     assert _lib.load().ofq_device_ok() == 1, _lib.load().ofq_last_error().decode()
     note("process group up")
 
+    from ofq_b200.quantization.functional import BWD_MODE as bwd_mode
     cfg = MODELS[a.model]
     torch.manual_seed(0)                      # identical initial weights on every rank
     model = DistilledVisionTransformer(num_classes=1000, **cfg)
@@ -309,14 +314,21 @@ def main():
     ev1.record()
     barrier()
     if rank == 0:
-        fam = {}
-        for name, s0, s1, nbytes, nflops in ops.PROFILE:
-            f = fam.setdefault(name, [0.0, 0, 0.0, 0.0])
-            f[0] += s0.elapsed_time(s1)
-            f[1] += 1
-            f[2] += nbytes
-            f[3] += nflops
+        fam, sites = {}, {}
+        for name, s0, s1, nbytes, nflops, tag in ops.PROFILE:
+            dt = s0.elapsed_time(s1)
+            for d, k in ((fam, name), (sites, f"{name} {tag}".strip())):
+                f = d.setdefault(k, [0.0, 0, 0.0, 0.0])
+                f[0] += dt
+                f[1] += 1
+                f[2] += nbytes
+                f[3] += nflops
         ops.PROFILE = None
+        if a.sites:
+            with open(a.sites, "w") as fh:
+                for k, v in sorted(sites.items(), key=lambda kv: -kv[1][0]):
+                    fh.write(f"{v[0] / nprof:9.4f} ms/step  {v[1] / nprof:6.1f} launches  {v[0] / v[1] * 1e3:8.1f} us  "
+                             f"{v[2] / (v[0] * 1e-3) / 1e9:8.1f} GB/s  {v[3] / (v[0] * 1e-3) / 1e12:8.1f} TFLOP/s  {k}\n")
         step_ms = ev0.elapsed_time(ev1) / nprof
         peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
         pk = ROOT / "MEASURED_PEAKS.json"
@@ -368,11 +380,11 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int8 codes fwd (s32 accumulate) / bf16 hi+lo bwd (f32 accumulate), f32 activations",
+        "dtype": f"int8 codes fwd (s32 accumulate) / {BWD_DTYPE[bwd_mode]} bwd (f32 accumulate), f32 activations",
         "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": B * world, "parallelism": f"dp{world}",
                    "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush",
-                   "optimizer": "fused AdamW lr 5.47e-4 wd 0.05", "cuda_graph": a.graph == "on", "host_enqueue_ms_per_step": host_enqueue_ms, "bwd_planes": int(os.environ.get("OFQ_BWD_PLANES", "2")),
+                   "optimizer": "fused AdamW lr 5.47e-4 wd 0.05", "cuda_graph": a.graph == "on", "host_enqueue_ms_per_step": host_enqueue_ms, "bwd_mode": bwd_mode,
                    "quantized_gemm_tflops_per_gpu": flops_step / (ms_total / a.steps * 1e-3) / 1e12},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": (h_img.numel() * 4 + h_lbl.numel() * 8) * world,
                 "d2h_bytes_per_step": 4 * world, "last_loss": last},

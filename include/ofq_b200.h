@@ -37,13 +37,18 @@ OFQ_API int ofq_device_ok(void);
  *   D[b][m][n] (=|+=) (sum_{k2,k} A[b][k2][m][k] * B[b][k2][n][k]) * rs[m] * cs[n] + rt[m] * ct[n]
  *
  * Both operands are K-major (k contiguous). kind I8: int8 codes, exact int32 accumulation.
- * kind BF16: bf16 operands, fp32 accumulation. Strides are in elements; a batch stride of 0 means the
+ * kind BF16 / F16: bf16 / fp16 operands, fp32 accumulation. Strides are in elements; a batch stride of 0 means the
  * operand is shared across that batch axis. Row/k2/batch strides must be multiples of 16 bytes.
  * NULL vectors read as 1; the rank-1 term is added only when rt or ct is non-NULL.
  * With splits > 1 (split-K) the output must be pre-zeroed and `accumulate` set (fp32 atomics).
  */
 #define OFQ_GEMM_I8   0
 #define OFQ_GEMM_BF16 1
+#define OFQ_GEMM_F16  2   /* fp16 operands, fp32 accumulation (range-scaled single-plane backward operands) */
+
+/* 16-bit operand formats written by the gradient-preparation kernels */
+#define OFQ_FMT_BF16 0
+#define OFQ_FMT_F16  1
 
 typedef struct {
     const void* ptr;
@@ -131,16 +136,32 @@ OFQ_API int ofq_lsq_bwd_finalize(const float* workspace, long long rows, int col
  *     planes to the GEMM as two outer-K slices gives ~16 mantissa bits (the integer-code operand is exact in bf16).
  *   colsum[c]       = sum_{b,r} x                      (optional; pre-zeroed, atomically accumulated)
  *   rowdot[b][g][r] = sum_{c in group g} x * u[c]      (optional; groups of `group` = 16, 32 or 64 consecutive columns)
+ *   out_fmt = OFQ_FMT_F16 (planes must be 1): single fp16 plane (11 significant bits, ~2e-4 gradient error) of
+ *     ( x * cs[c] * scale4[0] ) and ( x * rs[r] * scale4[2] ); scale4 comes from ofq_absmax_scale and keeps the
+ *     operand inside the fp16 range; the consuming GEMM multiplies its result by scale4[1] / scale4[3].
  */
 OFQ_API int ofq_grad_prep(const float* x, int nb, int R, int C, long long ldx, long long bstride_x,
                           const float* cs, const float* rs, int rs_period, int planes, void* out_rm,
                           long long ld_rm, void* out_t, int r_pad, float* colsum, const float* u, int group,
-                          float* rowdot, void* stream);
+                          float* rowdot, int out_fmt, const float* scale4, void* stream);
+
+/* Range scales for fp16 gradient operands, one read-only pass over x[nb][R][C] (fp32):
+ *   bound_c = max |x * cs[c]| * max_i |v1[i]| * mult,   bound_r = max |x * rs[r % rs_period]| * max_i |v2[i]| * mult
+ *   out4 = { sc_c, 1/sc_c, sc_r, 1/sc_r } with sc = 2^k such that bound * sc lies in [2^14, 2^15)
+ * (cs / rs / v1 / v2 may be NULL = 1). workspace: uint32[ofq_absmax_scale_workspace()], zero-initialised ONCE by the
+ * caller and then reusable by every later call on the same stream (the kernel resets its counter). */
+OFQ_API long long ofq_absmax_scale_workspace(void);
+OFQ_API int ofq_absmax_scale(const float* x, int nb, int R, int C, long long ldx, long long bstride,
+                             const float* cs, const float* rs, int rs_period, const float* v1, int n1,
+                             const float* v2, int n2, float mult, float* out4, void* workspace, void* stream);
 
 /* int8 codes [nb][R][C] (row stride ld, batch stride bstride) -> bf16, optionally transposed per batch:
  *   transpose = 0: out[b][r][c] (row stride ld_out);   transpose = 1: out[b][c][r] (row pitch ld_out >= R) */
 OFQ_API int ofq_codes_to_bf16(const int8_t* codes, int nb, int R, int C, long long ld, long long bstride,
                               void* out, long long ld_out, long long bstride_out, int transpose, void* stream);
+/* Same with the 16-bit format chosen by out_fmt (OFQ_FMT_BF16 / OFQ_FMT_F16); codes are exact in both. */
+OFQ_API int ofq_codes_to_16(const int8_t* codes, int nb, int R, int C, long long ld, long long bstride,
+                            void* out, long long ld_out, long long bstride_out, int transpose, int out_fmt, void* stream);
 /* out[row][seg] = sum_{c in segment seg} u[c] * codes[row][c]  (the move_aft shift of one attention operand
  * folded through the other operand's codes; row has nseg segments of cols/nseg columns). */
 OFQ_API int ofq_codes_rowdot(const int8_t* codes, long long rows, int cols, long long ld, int nseg,
@@ -168,13 +189,15 @@ OFQ_API int ofq_softmax_quant(const float* S, int nz, int N, long long ld, int H
  *   out_a [b][p][h][n][d] = bf16 plane p of ( dS * ca[d] )   ca index (h*N + d) if ca_per_head else d  (pitch ldo)
  *   out_bt[b][p][h][d][n] = bf16 plane p of ( dS * rb[n] )   (transposed, pitch ldo);  planes as in ofq_grad_prep
  *   colsum[z][d]   += sum_n dS              (optional, atomic, pre-zeroed)
+ *   out_fmt = OFQ_FMT_F16 (planes = 1): fp16 planes of ( dS * ca[d] * scale4[0] ) and ( dS * rb[n] * scale4[2] )
  *   dS32            = optional fp32 P * (dP - sum_d P*dP) WITHOUT alpha, layout of P: the gradient w.r.t. the
  *                     additive pre-softmax bias (Swin relative-position bias)
  */
 OFQ_API int ofq_softmax_quant_bwd(const float* dPq, const float* P, int nz, int N, long long ld, int H,
                                   const float* s_eff, int qhi, float alpha, float g_s, const float* ca,
                                   int ca_per_head, const float* rb, int planes, void* out_a, void* out_bt,
-                                  long long ldo, float* colsum, float* d_s, float* dS32, void* stream);
+                                  long long ldo, float* colsum, float* d_s, float* dS32, int out_fmt,
+                                  const float* scale4, void* stream);
 
 /* K4  W_qk[h] = W_q[h]^T W_k[h] in fp32 (attention.py:190-194) and its backward. wq, wk: [H*hd][C]. */
 OFQ_API int ofq_wqk_compose(const float* wq, const float* wk, int H, int hd, int C, float* wqk, void* stream);

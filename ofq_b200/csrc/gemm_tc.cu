@@ -40,6 +40,7 @@ struct GemmParams {
     VecRef rs, cs, rt, ct;
     int has_rank1;
     int atomic;
+    int ab_fmt;              // 16-bit kinds: UMMA a/b format field (0 = F16, 1 = BF16)
 };
 
 // NA: A tiles per pipeline stage. NA = 2 ("dual-A") loads the bf16 hi and lo planes of a gradient operand together with
@@ -92,8 +93,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint32_t ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));   // per accumulator stage
     constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
     constexpr uint32_t UMMA_K_BYTES = 32;  // 32 int8 or 16 bf16 per MMA
-    constexpr uint32_t IDESC = KIND == 0 ? umma_idesc(2u, 1u, BM, BN)   // S32 acc, signed int8
-                                         : umma_idesc(1u, 1u, BM, BN);  // F32 acc, bf16
+    // S32 accumulate / signed int8, or F32 accumulate / {fp16, bf16} (format chosen at run time)
+    const uint32_t IDESC = KIND == 0 ? umma_idesc(2u, 1u, BM, BN) : umma_idesc(1u, (uint32_t)p.ab_fmt, BM, BN);
 
     // 1024-byte alignment is required by the 128B swizzle; the attribute keeps the pointer in the shared address
     // space (an integer round-up would degrade every access to generic LD/ST)
@@ -327,7 +328,7 @@ using namespace ofq;
 
 // Build a 5-D tensor map {K, rows, k2, b1, b2} with a {128 bytes of K, box_rows, 1, 1, 1} box, 128B swizzle.
 static int make_operand_map(CUtensorMap* tm, const ofq_operand_t* op, int elem_bytes, int rows, int K,
-                            int k2, int nb1, int nb2, int box_rows) {
+                            int k2, int nb1, int nb2, int box_rows, bool f16 = false) {
     int k2_eff = op->k2_stride ? (op->k2_mod > 0 ? (op->k2_mod < k2 ? op->k2_mod : k2) : k2) : 1;
     if (op->dual_delta > 0) k2_eff = k2 + op->dual_delta;     // slices [0, k2) and [delta, delta + k2) are both addressed
     cuuint64_t dims[5] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)k2_eff,
@@ -350,7 +351,7 @@ static int make_operand_map(CUtensorMap* tm, const ofq_operand_t* op, int elem_b
     cuuint32_t box[5] = {(cuuint32_t)(KBYTES / elem_bytes), (cuuint32_t)box_rows, 1, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     return ofq_encode_tensor_map(tm, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
-                                                     : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                                 : (f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16),
                                  5, const_cast<void*>(op->ptr), dims, strides, box, estr);
 }
 
@@ -373,7 +374,7 @@ static int make_out_map(CUtensorMap* tm, const ofq_gemm_out_t* out, int M, int N
 extern "C" int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B, const ofq_gemm_out_t* out,
                         int M, int N, int K, int k2, int nb1, int nb2, int splits, const ofq_vec_t* rs,
                         const ofq_vec_t* cs, const ofq_vec_t* rt, const ofq_vec_t* ct, void* stream) {
-    if (kind != OFQ_GEMM_I8 && kind != OFQ_GEMM_BF16) {
+    if (kind != OFQ_GEMM_I8 && kind != OFQ_GEMM_BF16 && kind != OFQ_GEMM_F16) {
         ofq_set_error("ofq_gemm: unknown kind %d", kind);
         return OFQ_ERR_ARG;
     }
@@ -399,6 +400,7 @@ extern "C" int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B
     p.rs = make_vec(rs); p.cs = make_vec(cs); p.rt = make_vec(rt); p.ct = make_vec(ct);
     p.has_rank1 = (rt && rt->ptr) || (ct && ct->ptr);
     p.atomic = out->accumulate;
+    p.ab_fmt = kind == OFQ_GEMM_F16 ? 0 : 1;
     if (splits > 1 && !p.atomic) {
         ofq_set_error("ofq_gemm: split-K requires an accumulating (pre-zeroed) output");
         return OFQ_ERR_ARG;
@@ -414,9 +416,9 @@ extern "C" int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; bn = w; }
     }
     CUtensorMap tmA, tmB, tmC;
-    int rc = make_operand_map(&tmA, A, eb, M, K, k2, nb1, nb2, BM);
+    int rc = make_operand_map(&tmA, A, eb, M, K, k2, nb1, nb2, BM, kind == OFQ_GEMM_F16);
     if (rc) return rc;
-    rc = make_operand_map(&tmB, B, eb, N, K, k2, nb1, nb2, bn);
+    rc = make_operand_map(&tmB, B, eb, N, K, k2, nb1, nb2, bn, kind == OFQ_GEMM_F16);
     if (rc) return rc;
     rc = make_out_map(&tmC, out, M, N, nb1, nb2);
     if (rc) return rc;
@@ -431,7 +433,7 @@ extern "C" int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B
         default:  return launch_gemm<KIND, 32, 6>(tmA, tmB, tmC, p, st);     \
     }
     if (A->dual_delta > 0) {
-        if (kind != OFQ_GEMM_BF16 || B->dual_delta != 0 || A->k2_stride == 0) {
+        if (kind == OFQ_GEMM_I8 || B->dual_delta != 0 || A->k2_stride == 0) {
             ofq_set_error("ofq_gemm: dual_delta is for a bf16 A operand with an outer-K stride");
             return OFQ_ERR_ARG;
         }

@@ -340,12 +340,22 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return r;
 }
 
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi) { return F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+
 __device__ __forceinline__ float bf16_lo_to_float(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16_hi_to_float(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
 
+template <bool F16>
 __global__ void __launch_bounds__(256)
 grad_prep_kernel(const float* __restrict__ x, int R, int C, long long ldx, long long bstride_x,
                  const float* __restrict__ cs, const float* __restrict__ rs, int rs_period, int planes,
+                 const float* __restrict__ scale4,
                  long long plane_rm, long long plane_t,
                  uint16_t* __restrict__ out_rm, long long ld_rm, uint16_t* __restrict__ out_t, int r_pad,
                  float* __restrict__ colsum, const float* __restrict__ u, int group,
@@ -356,6 +366,9 @@ grad_prep_kernel(const float* __restrict__ x, int R, int C, long long ldx, long 
     const int t = threadIdx.x;
     const int tc = (t & 15) * 4, tr = t >> 4;   // 16 float4 per tile row, 16 rows per pass
     const float* xb = x + (long long)b * bstride_x;
+    // power-of-two range scales of the fp16 operands (ofq_absmax_scale): [0] row-major output, [2] transposed output
+    const float sc_rm = scale4 ? __ldg(scale4 + 0) : 1.f;
+    const float sc_t = scale4 ? __ldg(scale4 + 2) : 1.f;
     float colacc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -373,13 +386,13 @@ grad_prep_kernel(const float* __restrict__ x, int R, int C, long long ldx, long 
             }
             float sv[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) sv[e] = v[e] * s[e];
+            for (int e = 0; e < 4; ++e) sv[e] = v[e] * s[e] * sc_rm;
             uint2 pk;
-            pk.x = pack_bf16x2(sv[0], sv[1]);
-            pk.y = pack_bf16x2(sv[2], sv[3]);
+            pk.x = pack16x2<F16>(sv[0], sv[1]);
+            pk.y = pack16x2<F16>(sv[2], sv[3]);
             uint16_t* dst = out_rm + ((long long)b * R + r) * ld_rm + c;
             *reinterpret_cast<uint2*>(dst) = pk;
-            if (planes == 2) {
+            if (!F16 && planes == 2) {
                 uint2 lo;
                 lo.x = pack_bf16x2(sv[0] - bf16_lo_to_float(pk.x), sv[1] - bf16_hi_to_float(pk.x));
                 lo.y = pack_bf16x2(sv[2] - bf16_lo_to_float(pk.y), sv[3] - bf16_hi_to_float(pk.y));
@@ -401,7 +414,7 @@ grad_prep_kernel(const float* __restrict__ x, int R, int C, long long ldx, long 
             if (((t & 15) % lanes) == 0 && r < R && c < C)
                 rowdot[((long long)b * (C / group) + c / group) * R + r] = d;
         }
-        const float rsv = (out_t && rs && r < R) ? __ldg(rs + (r % rs_period)) : 1.f;
+        const float rsv = ((out_t && rs && r < R) ? __ldg(rs + (r % rs_period)) : 1.f) * sc_t;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             colacc[e] += v[e];
@@ -436,13 +449,13 @@ grad_prep_kernel(const float* __restrict__ x, int R, int C, long long ldx, long 
             const int c = item >> 3, ro = (item & 7) * 8;
             if (c0 + c < C && r0 + ro < r_pad) {
                 uint4 pk;
-                pk.x = pack_bf16x2(tile[ro + 0][c], tile[ro + 1][c]);
-                pk.y = pack_bf16x2(tile[ro + 2][c], tile[ro + 3][c]);
-                pk.z = pack_bf16x2(tile[ro + 4][c], tile[ro + 5][c]);
-                pk.w = pack_bf16x2(tile[ro + 6][c], tile[ro + 7][c]);
+                pk.x = pack16x2<F16>(tile[ro + 0][c], tile[ro + 1][c]);
+                pk.y = pack16x2<F16>(tile[ro + 2][c], tile[ro + 3][c]);
+                pk.z = pack16x2<F16>(tile[ro + 4][c], tile[ro + 5][c]);
+                pk.w = pack16x2<F16>(tile[ro + 6][c], tile[ro + 7][c]);
                 uint16_t* dst = ob + (long long)(c0 + c) * r_pad + r0 + ro;
                 *reinterpret_cast<uint4*>(dst) = pk;
-                if (planes == 2) {
+                if (!F16 && planes == 2) {
                     uint4 lo;
                     lo.x = pack_bf16x2(tile[ro + 0][c] - bf16_lo_to_float(pk.x), tile[ro + 1][c] - bf16_hi_to_float(pk.x));
                     lo.y = pack_bf16x2(tile[ro + 2][c] - bf16_lo_to_float(pk.y), tile[ro + 3][c] - bf16_hi_to_float(pk.y));
@@ -455,8 +468,98 @@ grad_prep_kernel(const float* __restrict__ x, int R, int C, long long ldx, long 
     }
 }
 
-// int8 codes -> bf16 (exact), optional per-batch transpose, 64x64 tiles.
-template <bool TRANSPOSE, typename OutT>
+// ------------------------------------------------------------------------------------------- fp16 range scale
+// One read-only pass: amax_c = max |x[r][c] * cs[c]|, amax_r = max |x[r][c] * rs[r % period]|, each multiplied by
+// max|v1| / max|v2| and `mult` (analytic bounds of a later product), then turned into power-of-two scales that place
+// the bound in [2^14, 2^15): out4 = {sc_c, 1/sc_c, sc_r, 1/sc_r}.  Last-block-done reduction over a persistent
+// workspace (uint32 counter at ws[0], self-resetting; partials from ws[2]).
+constexpr int kAbsmaxMaxBlocks = 148 * 8;
+
+__device__ __forceinline__ void pow2_scale_pair(float bound, float* sc, float* inv) {
+    const uint32_t e = (__float_as_uint(bound) >> 23) & 0xffu;
+    if (e < 16u || e > 250u) { *sc = 1.f; *inv = 1.f; return; }   // zero / denormal / non-finite bound: no scaling
+    *sc = __uint_as_float((268u - e) << 23);                     // 2^(141 - e): bound * sc in [2^14, 2^15)
+    *inv = __uint_as_float((e - 14u) << 23);                      // 2^(e - 141)
+}
+
+__global__ void __launch_bounds__(256)
+absmax_scale_kernel(const float* __restrict__ x, int nb, int R, int C, long long ldx, long long bstride,
+                    const float* __restrict__ cs, const float* __restrict__ rs, int rs_period,
+                    const float* __restrict__ v1, int n1, const float* __restrict__ v2, int n2, float mult,
+                    float* __restrict__ out4, unsigned int* __restrict__ ws) {
+    __shared__ float red[2][8];
+    __shared__ bool last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long rows = (long long)nb * R;
+    float mc = 0.f, mr = 0.f;
+    for (long long row = (long long)blockIdx.x * 8 + warp; row < rows; row += (long long)gridDim.x * 8) {
+        const int b = (int)(row / R), r = (int)(row - (long long)b * R);
+        const float* xr = x + (long long)b * bstride + (long long)r * ldx;
+        float rowmax = 0.f;
+        for (int c = lane * 4; c < C; c += 128) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(xr + c));   // the row pitch covers the last quad
+            const float a0 = fabsf(f.x), a1 = c + 1 < C ? fabsf(f.y) : 0.f, a2 = c + 2 < C ? fabsf(f.z) : 0.f,
+                        a3 = c + 3 < C ? fabsf(f.w) : 0.f;
+            rowmax = fmaxf(fmaxf(rowmax, fmaxf(a0, a1)), fmaxf(a2, a3));
+            if (cs) {                                                          // host guarantees C % 4 == 0 with cs
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(cs + c));
+                mc = fmaxf(fmaxf(mc, fmaxf(a0 * fabsf(s4.x), a1 * fabsf(s4.y))), fmaxf(a2 * fabsf(s4.z), a3 * fabsf(s4.w)));
+            }
+        }
+        if (!cs) mc = fmaxf(mc, rowmax);
+        mr = fmaxf(mr, rowmax * (rs ? fabsf(__ldg(rs + (r % rs_period))) : 1.f));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mc = fmaxf(mc, __shfl_xor_sync(0xffffffffu, mc, o));
+        mr = fmaxf(mr, __shfl_xor_sync(0xffffffffu, mr, o));
+    }
+    if (lane == 0) { red[0][warp] = mc; red[1][warp] = mr; }
+    __syncthreads();
+    float* part = reinterpret_cast<float*>(ws + 2);
+    if (threadIdx.x == 0) {
+        float a = 0.f, b2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { a = fmaxf(a, red[0][w]); b2 = fmaxf(b2, red[1][w]); }
+        part[2 * blockIdx.x] = a;
+        part[2 * blockIdx.x + 1] = b2;
+        __threadfence();
+        last = atomicAdd(ws, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    float a = 0.f, b2 = 0.f, m1 = v1 ? 0.f : 1.f, m2 = v2 ? 0.f : 1.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+        a = fmaxf(a, __ldcg(part + 2 * i));
+        b2 = fmaxf(b2, __ldcg(part + 2 * i + 1));
+    }
+    if (v1) for (int i = threadIdx.x; i < n1; i += blockDim.x) m1 = fmaxf(m1, fabsf(__ldg(v1 + i)));
+    if (v2) for (int i = threadIdx.x; i < n2; i += blockDim.x) m2 = fmaxf(m2, fabsf(__ldg(v2 + i)));
+    __shared__ float fin[4][8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b2 = fmaxf(b2, __shfl_xor_sync(0xffffffffu, b2, o));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+        m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    }
+    if (lane == 0) { fin[0][warp] = a; fin[1][warp] = b2; fin[2][warp] = m1; fin[3][warp] = m2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = b2 = m1 = m2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            a = fmaxf(a, fin[0][w]); b2 = fmaxf(b2, fin[1][w]); m1 = fmaxf(m1, fin[2][w]); m2 = fmaxf(m2, fin[3][w]);
+        }
+        pow2_scale_pair(a * m1 * mult, out4 + 0, out4 + 1);
+        pow2_scale_pair(b2 * m2 * mult, out4 + 2, out4 + 3);
+        ws[0] = 0u;                                   // ready for the next launch on this stream
+    }
+}
+
+// int8 codes -> bf16 / fp16 (exact), optional per-batch transpose, 64x64 tiles.
+template <bool TRANSPOSE, typename OutT, bool F16 = false>
 __global__ void __launch_bounds__(256)
 codes_convert_kernel(const int8_t* __restrict__ codes, int R, int C, long long ld, long long bstride,
                      OutT* __restrict__ out, long long ld_out, long long bstride_out) {
@@ -486,10 +589,10 @@ codes_convert_kernel(const int8_t* __restrict__ codes, int R, int C, long long l
                 if (r >= ld_out) continue;
                 if (sizeof(OutT) == 2) {
                     uint4 pk;
-                    pk.x = pack_bf16x2((float)tile[ro + j + 0][c], (float)tile[ro + j + 1][c]);
-                    pk.y = pack_bf16x2((float)tile[ro + j + 2][c], (float)tile[ro + j + 3][c]);
-                    pk.z = pack_bf16x2((float)tile[ro + j + 4][c], (float)tile[ro + j + 5][c]);
-                    pk.w = pack_bf16x2((float)tile[ro + j + 6][c], (float)tile[ro + j + 7][c]);
+                    pk.x = pack16x2<F16>((float)tile[ro + j + 0][c], (float)tile[ro + j + 1][c]);
+                    pk.y = pack16x2<F16>((float)tile[ro + j + 2][c], (float)tile[ro + j + 3][c]);
+                    pk.z = pack16x2<F16>((float)tile[ro + j + 4][c], (float)tile[ro + j + 5][c]);
+                    pk.w = pack16x2<F16>((float)tile[ro + j + 6][c], (float)tile[ro + j + 7][c]);
                     *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ob) + (long long)(c0 + c) * ld_out + r) = pk;
                 } else {
                     uint2 pk;
@@ -510,10 +613,10 @@ codes_convert_kernel(const int8_t* __restrict__ codes, int R, int C, long long l
                 const int c = c0 + co + j;
                 if (c >= C) continue;
                 uint4 pk;
-                pk.x = pack_bf16x2((float)tile[r][co + j + 0], (float)tile[r][co + j + 1]);
-                pk.y = pack_bf16x2((float)tile[r][co + j + 2], (float)tile[r][co + j + 3]);
-                pk.z = pack_bf16x2((float)tile[r][co + j + 4], (float)tile[r][co + j + 5]);
-                pk.w = pack_bf16x2((float)tile[r][co + j + 6], (float)tile[r][co + j + 7]);
+                pk.x = pack16x2<F16>((float)tile[r][co + j + 0], (float)tile[r][co + j + 1]);
+                pk.y = pack16x2<F16>((float)tile[r][co + j + 2], (float)tile[r][co + j + 3]);
+                pk.z = pack16x2<F16>((float)tile[r][co + j + 4], (float)tile[r][co + j + 5]);
+                pk.w = pack16x2<F16>((float)tile[r][co + j + 6], (float)tile[r][co + j + 7]);
                 *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(ob) + (long long)(r0 + r) * ld_out + c) = pk;
             }
         }
@@ -650,10 +753,30 @@ extern "C" int ofq_lsq_bwd_finalize(const float* workspace, long long rows, int 
     return 0;
 }
 
+extern "C" long long ofq_absmax_scale_workspace(void) { return 2 + 2 * kAbsmaxMaxBlocks; }
+
+extern "C" int ofq_absmax_scale(const float* x, int nb, int R, int C, long long ldx, long long bstride,
+                                const float* cs, const float* rs, int rs_period, const float* v1, int n1,
+                                const float* v2, int n2, float mult, float* out4, void* workspace, void* stream) {
+    OFQ_REQUIRE(x && out4 && workspace && nb > 0 && R > 0 && C > 0, "ofq_absmax_scale: bad argument");
+    OFQ_REQUIRE(ldx % 4 == 0 && ldx >= (C + 3) / 4 * 4 && bstride % 4 == 0 && (uintptr_t)x % 16 == 0,
+                "ofq_absmax_scale: ldx, bstride must be multiples of 4 (ldx covering the last quad) and x 16-byte aligned");
+    OFQ_REQUIRE(!cs || (C % 4 == 0 && (uintptr_t)cs % 16 == 0), "ofq_absmax_scale: cs needs C % 4 == 0 and 16-byte alignment");
+    OFQ_CHECK_ARCH();
+    if (rs_period <= 0) rs_period = 0x7fffffff;
+    const long long rows = (long long)nb * R;
+    long long grid = (rows + 7) / 8;
+    if (grid > kAbsmaxMaxBlocks) grid = kAbsmaxMaxBlocks;
+    absmax_scale_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, nb, R, C, ldx, bstride, cs, rs, rs_period,
+                                                                         v1, n1, v2, n2, mult, out4, (unsigned int*)workspace);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int ofq_grad_prep(const float* x, int nb, int R, int C, long long ldx, long long bstride_x,
                              const float* cs, const float* rs, int rs_period, int planes, void* out_rm,
                              long long ld_rm, void* out_t, int r_pad, float* colsum, const float* u, int group,
-                             float* rowdot, void* stream) {
+                             float* rowdot, int out_fmt, const float* scale4, void* stream) {
     OFQ_REQUIRE(x && nb > 0 && R > 0 && C > 0, "ofq_grad_prep: bad argument");
     OFQ_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && bstride_x % 4 == 0 && (uintptr_t)x % 16 == 0,
                 "ofq_grad_prep: C, ldx must be multiples of 4 and x 16-byte aligned");
@@ -661,30 +784,51 @@ extern "C" int ofq_grad_prep(const float* x, int nb, int R, int C, long long ldx
     OFQ_REQUIRE(!out_t || (r_pad % 8 == 0 && r_pad >= R && (uintptr_t)out_t % 16 == 0), "ofq_grad_prep: out_t pitch must be a multiple of 8 and >= R");
     OFQ_REQUIRE(!rowdot || (u && (group == 16 || group == 32 || group == 64) && C % group == 0), "ofq_grad_prep: rowdot needs u and group 16, 32 or 64");
     OFQ_REQUIRE(planes == 1 || planes == 2, "ofq_grad_prep: planes must be 1 or 2");
+    OFQ_REQUIRE(out_fmt == OFQ_FMT_BF16 || (out_fmt == OFQ_FMT_F16 && planes == 1), "ofq_grad_prep: fp16 output is single-plane");
     OFQ_REQUIRE(!cs || (uintptr_t)cs % 16 == 0, "ofq_grad_prep: cs alignment");
     OFQ_CHECK_ARCH();
     if (rs_period <= 0) rs_period = 0x7fffffff;
     dim3 grid((C + 63) / 64, (R + 63) / 64, nb);
-    grad_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, R, C, ldx, bstride_x, cs, rs, rs_period, planes,
-                                                             (long long)nb * R * ld_rm, (long long)nb * C * r_pad,
-                                                             (uint16_t*)out_rm, ld_rm, (uint16_t*)out_t, r_pad,
-                                                             colsum, u, group, rowdot);
+    if (out_fmt == OFQ_FMT_F16)
+        grad_prep_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, R, C, ldx, bstride_x, cs, rs, rs_period, planes, scale4,
+                                                                 (long long)nb * R * ld_rm, (long long)nb * C * r_pad,
+                                                                 (uint16_t*)out_rm, ld_rm, (uint16_t*)out_t, r_pad,
+                                                                 colsum, u, group, rowdot);
+    else
+        grad_prep_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, R, C, ldx, bstride_x, cs, rs, rs_period, planes, scale4,
+                                                                 (long long)nb * R * ld_rm, (long long)nb * C * r_pad,
+                                                                 (uint16_t*)out_rm, ld_rm, (uint16_t*)out_t, r_pad,
+                                                                 colsum, u, group, rowdot);
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }
 
+extern "C" int ofq_codes_to_16(const int8_t* codes, int nb, int R, int C, long long ld, long long bstride,
+                               void* out, long long ld_out, long long bstride_out, int transpose, int out_fmt, void* stream);
+
 extern "C" int ofq_codes_to_bf16(const int8_t* codes, int nb, int R, int C, long long ld, long long bstride,
                                  void* out, long long ld_out, long long bstride_out, int transpose, void* stream) {
-    OFQ_REQUIRE(codes && out && nb > 0 && R > 0 && C > 0, "ofq_codes_to_bf16: bad argument");
+    return ofq_codes_to_16(codes, nb, R, C, ld, bstride, out, ld_out, bstride_out, transpose, OFQ_FMT_BF16, stream);
+}
+
+extern "C" int ofq_codes_to_16(const int8_t* codes, int nb, int R, int C, long long ld, long long bstride,
+                               void* out, long long ld_out, long long bstride_out, int transpose, int out_fmt, void* stream) {
+    OFQ_REQUIRE(out_fmt == OFQ_FMT_BF16 || out_fmt == OFQ_FMT_F16, "ofq_codes_to_16: unknown format");
+    OFQ_REQUIRE(codes && out && nb > 0 && R > 0 && C > 0, "ofq_codes_to_16: bad argument");
     OFQ_REQUIRE(C % 4 == 0 && ld % 4 == 0 && bstride % 4 == 0 && (uintptr_t)codes % 4 == 0, "ofq_codes_to_bf16: input alignment");
     OFQ_REQUIRE(ld_out % 8 == 0 && bstride_out % 8 == 0 && (uintptr_t)out % 16 == 0, "ofq_codes_to_bf16: output alignment");
     OFQ_REQUIRE(transpose ? ld_out >= R : (ld_out >= C && C % 8 == 0), "ofq_codes_to_bf16: output pitch too small");
     OFQ_CHECK_ARCH();
     dim3 grid((C + 63) / 64, (R + 63) / 64, nb);
-    if (transpose)
-        codes_convert_kernel<true, uint16_t><<<grid, 256, 0, (cudaStream_t)stream>>>(codes, R, C, ld, bstride, (uint16_t*)out, ld_out, bstride_out);
-    else
-        codes_convert_kernel<false, uint16_t><<<grid, 256, 0, (cudaStream_t)stream>>>(codes, R, C, ld, bstride, (uint16_t*)out, ld_out, bstride_out);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint16_t* o = (uint16_t*)out;
+    if (out_fmt == OFQ_FMT_F16) {
+        if (transpose) codes_convert_kernel<true, uint16_t, true><<<grid, 256, 0, st>>>(codes, R, C, ld, bstride, o, ld_out, bstride_out);
+        else codes_convert_kernel<false, uint16_t, true><<<grid, 256, 0, st>>>(codes, R, C, ld, bstride, o, ld_out, bstride_out);
+    } else {
+        if (transpose) codes_convert_kernel<true, uint16_t, false><<<grid, 256, 0, st>>>(codes, R, C, ld, bstride, o, ld_out, bstride_out);
+        else codes_convert_kernel<false, uint16_t, false><<<grid, 256, 0, st>>>(codes, R, C, ld, bstride, o, ld_out, bstride_out);
+    }
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }

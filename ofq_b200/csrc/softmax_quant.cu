@@ -25,6 +25,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return r;
 }
 __device__ __forceinline__ uint16_t to_bf16(float v) { return (uint16_t)(pack_bf16x2(v, 0.f) & 0xffff); }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi) { return F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+template <bool F16>
+__device__ __forceinline__ uint16_t to16(float v) { return (uint16_t)(pack16x2<F16>(v, 0.f) & 0xffff); }
 
 __global__ void __launch_bounds__(256)
 softmax_quant_kernel(const float* __restrict__ S, int nz, int N, long long ld, int H,
@@ -84,10 +93,12 @@ softmax_quant_kernel(const float* __restrict__ S, int nz, int N, long long ld, i
 }
 
 // Backward: block = 32 query rows of one (b, h); 8 warps x 4 rows.
+template <bool F16>
 __global__ void __launch_bounds__(256)
 softmax_quant_bwd_kernel(const float* __restrict__ dPq, const float* __restrict__ P, int N, long long ld, int H,
                          const float* __restrict__ s_eff, float qhi, float alpha, float g_s,
                          const float* __restrict__ ca, int ca_per_head, const float* __restrict__ rb, int planes,
+                         const float* __restrict__ scale4,
                          uint16_t* __restrict__ out_a, uint16_t* __restrict__ out_bt, long long ldo,
                          float* __restrict__ colsum, float* __restrict__ d_s, float* __restrict__ dS32) {
     extern __shared__ float tile[];           // [32][N + 1] dS * rb[n] for the transposed output
@@ -102,6 +113,9 @@ softmax_quant_bwd_kernel(const float* __restrict__ dPq, const float* __restrict_
     for (int i = threadIdx.x; i < kMaxPer * 32; i += blockDim.x) csum_s[i] = 0.f;
     __syncthreads();
     const float* cav = ca ? (ca_per_head ? ca + (long long)h * N : ca) : nullptr;
+    // power-of-two range scales of the fp16 operands (ofq_absmax_scale): [0] out_a, [2] out_bt
+    const float sc_a = scale4 ? __ldg(scale4 + 0) : 1.f;
+    const float sc_b = scale4 ? __ldg(scale4 + 2) : 1.f;
     float colacc[kMaxPer];
 #pragma unroll
     for (int i = 0; i < kMaxPer; ++i) colacc[i] = 0.f;
@@ -135,7 +149,7 @@ softmax_quant_bwd_kernel(const float* __restrict__ dPq, const float* __restrict_
         dot = wsum(dot);
         dsp = wsum(dsp);
         if (lane == 0 && d_s) atomicAdd(d_s + n, g_s * dsp);
-        const float rbv = rb ? __ldg(rb + n) : 1.f;
+        const float rbv = (rb ? __ldg(rb + n) : 1.f) * sc_b;
 #pragma unroll
         for (int i = 0; i < kMaxPer; ++i) {
             const int d = lane + 32 * i;
@@ -144,17 +158,17 @@ softmax_quant_bwd_kernel(const float* __restrict__ dPq, const float* __restrict_
                 const float ds = alpha * ds_raw;             // gradient w.r.t. the un-scaled q.k product
                 colacc[i] += ds;
                 if (out_a) {
-                    const float va = ds * (cav ? __ldg(cav + d) : 1.f);
-                    const uint16_t hi16 = to_bf16(va);
+                    const float va = ds * (cav ? __ldg(cav + d) : 1.f) * sc_a;
+                    const uint16_t hi16 = to16<F16>(va);
                     uint16_t* dst = out_a + (zo + n) * ldo + d;
                     *dst = hi16;
-                    if (planes == 2) dst[plane] = to_bf16(va - __uint_as_float((uint32_t)hi16 << 16));
+                    if (!F16 && planes == 2) dst[plane] = to_bf16(va - __uint_as_float((uint32_t)hi16 << 16));
                 }
                 if (dS32) dS32[ro + d] = ds_raw;
                 tile[ln * pitch + d] = ds * rbv;
             } else if (out_a && d < ldo) {
                 out_a[(zo + n) * ldo + d] = 0;
-                if (planes == 2) out_a[(zo + n) * ldo + d + plane] = 0;
+                if (!F16 && planes == 2) out_a[(zo + n) * ldo + d + plane] = 0;
             }
         }
     }
@@ -175,13 +189,13 @@ softmax_quant_bwd_kernel(const float* __restrict__ dPq, const float* __restrict_
 #pragma unroll
             for (int e = 0; e < 8; ++e) t8[e] = tile[(no + e) * pitch + d];
             uint4 pk;
-            pk.x = pack_bf16x2(t8[0], t8[1]);
-            pk.y = pack_bf16x2(t8[2], t8[3]);
-            pk.z = pack_bf16x2(t8[4], t8[5]);
-            pk.w = pack_bf16x2(t8[6], t8[7]);
+            pk.x = pack16x2<F16>(t8[0], t8[1]);
+            pk.y = pack16x2<F16>(t8[2], t8[3]);
+            pk.z = pack16x2<F16>(t8[4], t8[5]);
+            pk.w = pack16x2<F16>(t8[6], t8[7]);
             uint16_t* dst = out_bt + (zo + d) * ldo + n0 + no;
             *reinterpret_cast<uint4*>(dst) = pk;
-            if (planes == 2) {
+            if (!F16 && planes == 2) {
                 uint4 lo;
                 lo.x = pack_bf16x2(t8[0] - __uint_as_float(pk.x << 16), t8[1] - __uint_as_float(pk.x & 0xffff0000u));
                 lo.y = pack_bf16x2(t8[2] - __uint_as_float(pk.y << 16), t8[3] - __uint_as_float(pk.y & 0xffff0000u));
@@ -213,18 +227,25 @@ extern "C" int ofq_softmax_quant(const float* S, int nz, int N, long long ld, in
 extern "C" int ofq_softmax_quant_bwd(const float* dPq, const float* P, int nz, int N, long long ld, int H,
                                      const float* s_eff, int qhi, float alpha, float g_s, const float* ca,
                                      int ca_per_head, const float* rb, int planes, void* out_a, void* out_bt,
-                                     long long ldo, float* colsum, float* d_s, float* dS32, void* stream) {
+                                     long long ldo, float* colsum, float* d_s, float* dS32, int out_fmt,
+                                     const float* scale4, void* stream) {
     OFQ_REQUIRE(dPq && P && s_eff && nz > 0 && N > 0 && H > 0, "ofq_softmax_quant_bwd: bad argument");
     OFQ_REQUIRE(N <= kMaxPer * 32, "ofq_softmax_quant_bwd: at most 256 keys per row are supported");
     OFQ_REQUIRE((!out_a && !out_bt) || (ldo % 8 == 0 && ldo >= N), "ofq_softmax_quant_bwd: output pitch must be a multiple of 8 and >= N");
     OFQ_REQUIRE(!out_bt || (uintptr_t)out_bt % 16 == 0, "ofq_softmax_quant_bwd: out_bt alignment");
     OFQ_REQUIRE(planes == 1 || planes == 2, "ofq_softmax_quant_bwd: planes must be 1 or 2");
+    OFQ_REQUIRE(out_fmt == OFQ_FMT_BF16 || (out_fmt == OFQ_FMT_F16 && planes == 1), "ofq_softmax_quant_bwd: fp16 output is single-plane");
     OFQ_CHECK_ARCH();
     dim3 grid((N + 31) / 32, nz);
     const size_t smem = (size_t)32 * (N + 1) * sizeof(float);
-    softmax_quant_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
-        dPq, P, N, ld, H, s_eff, (float)qhi, alpha, g_s, ca, ca_per_head, rb, planes, (uint16_t*)out_a,
-        (uint16_t*)out_bt, ldo, colsum, d_s, dS32);
+    if (out_fmt == OFQ_FMT_F16)
+        softmax_quant_bwd_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(
+            dPq, P, N, ld, H, s_eff, (float)qhi, alpha, g_s, ca, ca_per_head, rb, planes, scale4, (uint16_t*)out_a,
+            (uint16_t*)out_bt, ldo, colsum, d_s, dS32);
+    else
+        softmax_quant_bwd_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(
+            dPq, P, N, ld, H, s_eff, (float)qhi, alpha, g_s, ca, ca_per_head, rb, planes, scale4, (uint16_t*)out_a,
+            (uint16_t*)out_bt, ldo, colsum, d_s, dS32);
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }

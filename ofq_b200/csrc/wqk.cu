@@ -6,25 +6,38 @@
 
 namespace {
 
-// C[b][m][n] = sum_k A[b][k*sAk + m*sAm] * B[b][k*sBk + n*sBn];  64x64 tile, 256 threads, 4x4 per thread.
+// C[b][m][n] = sum_k A[b][k*sAk + m*sAm] * B[b][k*sBk + n*sBn];  TM x 64 tile, 256 threads, (TM/16) x 4 per thread.
+// Up to two independent problems share one launch (blockIdx.z = problem * nb + batch): the two backward products
+// of a layer are 36 + 36 tiles of 64 x 64, far fewer than the 148 SMs, so they run side by side on 16-row tiles (288 CTAs).
+struct SgemmProblem {
+    const float* A; long long sAk, sAm, bsA;
+    const float* B; long long sBk, sBn, bsB;
+    float* C; long long ldc, bsC;
+};
+struct SgemmPair { SgemmProblem p[2]; };
+
+template <int TM>
 __global__ void __launch_bounds__(256)
-sgemm_strided_kernel(const float* __restrict__ A, long long sAk, long long sAm, long long bsA,
-                     const float* __restrict__ B, long long sBk, long long sBn, long long bsB,
-                     float* __restrict__ C, long long ldc, long long bsC, int M, int N, int K) {
-    __shared__ float As[16][64 + 4];
+sgemm_strided_kernel(const SgemmPair pair, int nb, int M, int N, int K) {
+    constexpr int RM = TM / 16;
+    __shared__ float As[16][TM + 4];
     __shared__ float Bs[16][64 + 4];
-    const int b = blockIdx.z;
-    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const SgemmProblem& q = pair.p[blockIdx.z / nb];
+    const int b = blockIdx.z % nb;
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * 64;
     const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
-    const float* Ab = A + b * bsA;
-    const float* Bb = B + b * bsB;
-    float acc[4][4] = {};
+    const float* Ab = q.A + b * q.bsA;
+    const float* Bb = q.B + b * q.bsB;
+    const long long sAk = q.sAk, sAm = q.sAm, sBk = q.sBk, sBn = q.sBn;
+    float acc[RM][4] = {};
     for (int k0 = 0; k0 < K; k0 += 16) {
-        for (int i = t; i < 16 * 64; i += 256) {
+        for (int i = t; i < 16 * TM; i += 256) {
             int kk, mm;
-            if (sAm == 1) { kk = i >> 6; mm = i & 63; } else { kk = i & 15; mm = i >> 4; }
+            if (sAm == 1) { kk = i / TM; mm = i % TM; } else { kk = i & 15; mm = i >> 4; }
             const int k = k0 + kk, m = m0 + mm;
             As[kk][mm] = (k < K && m < M) ? __ldg(Ab + k * sAk + m * sAm) : 0.f;
+        }
+        for (int i = t; i < 16 * 64; i += 256) {
             int kb, nn;
             if (sBn == 1) { kb = i >> 6; nn = i & 63; } else { kb = i & 15; nn = i >> 4; }
             const int k2 = k0 + kb, n = n0 + nn;
@@ -33,33 +46,40 @@ sgemm_strided_kernel(const float* __restrict__ A, long long sAk, long long sAm, 
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk) {
-            float a[4], bb[4];
+            float a[RM], bb[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; bb[i] = Bs[kk][tx * 4 + i]; }
+            for (int i = 0; i < RM; ++i) a[i] = As[kk][ty * RM + i];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) bb[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < RM; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
         }
         __syncthreads();
     }
-    float* Cb = C + b * bsC;
+    float* Cb = q.C + b * q.bsC;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
+    for (int i = 0; i < RM; ++i) {
+        const int m = m0 + ty * RM + i;
         if (m >= M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
-            if (n < N) Cb[m * ldc + n] = acc[i][j];
+            if (n < N) Cb[m * q.ldc + n] = acc[i][j];
         }
     }
 }
 
-int launch(const float* A, long long sAk, long long sAm, long long bsA, const float* B, long long sBk, long long sBn,
-           long long bsB, float* C, long long ldc, long long bsC, int M, int N, int K, int nb, cudaStream_t st) {
-    dim3 grid((N + 63) / 64, (M + 63) / 64, nb);
-    sgemm_strided_kernel<<<grid, 256, 0, st>>>(A, sAk, sAm, bsA, B, sBk, sBn, bsB, C, ldc, bsC, M, N, K);
+int launch(const SgemmPair& pair, int nprob, int M, int N, int K, int nb, cudaStream_t st) {
+    const long long tiles64 = (long long)((N + 63) / 64) * ((M + 63) / 64) * nb * nprob;
+    if (tiles64 >= 148) {
+        dim3 grid((N + 63) / 64, (M + 63) / 64, nb * nprob);
+        sgemm_strided_kernel<64><<<grid, 256, 0, st>>>(pair, nb, M, N, K);
+    } else {
+        dim3 grid((N + 63) / 64, (M + 15) / 16, nb * nprob);
+        sgemm_strided_kernel<16><<<grid, 256, 0, st>>>(pair, nb, M, N, K);
+    }
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }
@@ -70,18 +90,19 @@ extern "C" int ofq_wqk_compose(const float* wq, const float* wk, int H, int hd, 
     OFQ_REQUIRE(wq && wk && wqk && H > 0 && hd > 0 && C > 0, "ofq_wqk_compose: bad argument");
     OFQ_CHECK_ARCH();
     // wqk[h][i][j] = sum_d wq[h*hd+d][i] * wk[h*hd+d][j]
-    return launch(wq, C, 1, (long long)hd * C, wk, C, 1, (long long)hd * C, wqk, C, (long long)C * C, C, C, hd, H,
-                  (cudaStream_t)stream);
+    SgemmPair pair = {};
+    pair.p[0] = {wq, C, 1, (long long)hd * C, wk, C, 1, (long long)hd * C, wqk, C, (long long)C * C};
+    return launch(pair, 1, C, C, hd, H, (cudaStream_t)stream);
 }
 
 extern "C" int ofq_wqk_compose_bwd(const float* dwqk, const float* wq, const float* wk, int H, int hd, int C,
                                    float* dwq, float* dwk, void* stream) {
     OFQ_REQUIRE(dwqk && wq && wk && dwq && dwk && H > 0 && hd > 0 && C > 0, "ofq_wqk_compose_bwd: bad argument");
     OFQ_CHECK_ARCH();
-    cudaStream_t st = (cudaStream_t)stream;
+    SgemmPair pair;
     // dwq[h*hd+d][i] = sum_j wk[h*hd+d][j] * dwqk[h][i][j]
-    int rc = launch(wk, 1, C, (long long)hd * C, dwqk, 1, C, (long long)C * C, dwq, C, (long long)hd * C, hd, C, C, H, st);
-    if (rc) return rc;
+    pair.p[0] = {wk, 1, C, (long long)hd * C, dwqk, 1, C, (long long)C * C, dwq, C, (long long)hd * C};
     // dwk[h*hd+d][j] = sum_i wq[h*hd+d][i] * dwqk[h][i][j]
-    return launch(wq, 1, C, (long long)hd * C, dwqk, C, 1, (long long)C * C, dwk, C, (long long)hd * C, hd, C, C, H, st);
+    pair.p[1] = {wq, 1, C, (long long)hd * C, dwqk, C, 1, (long long)C * C, dwk, C, (long long)hd * C};
+    return launch(pair, 2, hd, C, C, H, (cudaStream_t)stream);
 }

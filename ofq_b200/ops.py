@@ -13,17 +13,20 @@ import torch
 from . import _lib
 from ._lib import GemmOut, Operand, Vec, check
 
-GEMM_I8, GEMM_BF16 = 0, 1
+GEMM_I8, GEMM_BF16, GEMM_F16 = 0, 1, 2
+FMT_BF16, FMT_F16 = 0, 1
 PER_ROW, PER_COL = 0, 1
+_T16 = {FMT_BF16: torch.bfloat16, FMT_F16: torch.float16}
 
 # Launch accounting (bench.py): LAUNCHES counts kernels launched through this module; when PROFILE is a list every
 # call is bracketed by CUDA events on the launching stream and recorded as
 # (family, start_event, end_event, algorithmic_bytes, algorithmic_flops).
 LAUNCHES = 0
 PROFILE = None
+TAG = ""          # set by callers that want the next launches attributed to a site (bench.py per-site table)
 
 
-def _call(family: str, nkernels: int, alg_bytes: float, alg_flops: float, fn, *args):
+def _call(family: str, nkernels: int, alg_bytes: float, alg_flops: float, fn, *args, tag: str = ""):
     global LAUNCHES
     LAUNCHES += nkernels
     if PROFILE is None:
@@ -35,7 +38,7 @@ def _call(family: str, nkernels: int, alg_bytes: float, alg_flops: float, fn, *a
     rc = fn(*args)
     e1.record()
     check(rc)
-    PROFILE.append((family, e0, e1, alg_bytes, alg_flops))
+    PROFILE.append((family, e0, e1, alg_bytes, alg_flops, tag))
 
 
 def _cuda(*ts):
@@ -69,6 +72,7 @@ def gemm(kind: int, a: torch.Tensor, a_strides, b: torch.Tensor, b_strides, out:
     B = Operand(b.data_ptr(), b_strides[0], b_strides[1], b_k2mod, 0, b_strides[2], b_strides[3])
     O = GemmOut(out.data_ptr(), *out_strides, 1 if accumulate else 0)
     eb = 1 if kind == GEMM_I8 else 2
+    tag = f"M{M} N{N} K{K} k2={k2}{'+dual' if a_dual_delta else ''} nb={nb1}x{nb2} sp={splits}"
 
     def _n(strides, mod):
         k2n = ((min(mod, k2) if mod else k2) + (a_dual_delta if strides is a_strides and a_dual_delta else 0)) if strides[1] else 1
@@ -76,8 +80,8 @@ def gemm(kind: int, a: torch.Tensor, a_strides, b: torch.Tensor, b_strides, out:
     nout = (nb1 if out_strides[1] else 1) * (nb2 if out_strides[2] else 1)
     alg_bytes = eb * K * (M * _n(a_strides, a_k2mod) + N * _n(b_strides, b_k2mod)) + 4 * M * N * nout * (2 if accumulate else 1)
     alg_flops = 2.0 * M * N * K * k2 * nb1 * nb2 * (2 if a_dual_delta else 1)
-    _call("gemm_i8" if kind == GEMM_I8 else "gemm_bf16", 1, alg_bytes, alg_flops, _lib.load().ofq_gemm, kind,
-          C.byref(A), C.byref(B), C.byref(O), M, N, K, k2, nb1, nb2, splits, rs, cs, rt, ct, _st())
+    _call(("gemm_i8", "gemm_bf16", "gemm_f16")[kind], 1, alg_bytes, alg_flops, _lib.load().ofq_gemm, kind,
+          C.byref(A), C.byref(B), C.byref(O), M, N, K, k2, nb1, nb2, splits, rs, cs, rt, ct, _st(), tag=tag)
 
 
 # ------------------------------------------------------------------------------------------------ quantizers
@@ -149,38 +153,58 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+_ABSMAX_WS = {}
+
+
+def absmax_scale(x: torch.Tensor, nb: int, R: int, Cc: int, ldx: int, bstride: int, *, cs=None, rs=None, rs_period=0,
+                 v1=None, v2=None, mult: float = 1.0) -> torch.Tensor:
+    """Power-of-two fp16 range scales of x*cs (out[0], inverse out[1]) and x*rs (out[2], inverse out[3]); the bounds are
+    further multiplied by max|v1| / max|v2| and `mult` (see ofq_absmax_scale)."""
+    _cuda(x)
+    lib = _lib.load()
+    ws = _ABSMAX_WS.get(x.device)
+    if ws is None:
+        ws = _ABSMAX_WS[x.device] = torch.zeros(lib.ofq_absmax_scale_workspace(), dtype=torch.int32, device=x.device)
+    out = torch.empty(4, dtype=torch.float32, device=x.device)
+    _call("absmax_scale", 1, 4.0 * nb * R * Cc, 0, lib.ofq_absmax_scale, x.data_ptr(), nb, R, Cc, ldx, bstride, _ptr(cs),
+          _ptr(rs), rs_period, _ptr(v1), 0 if v1 is None else v1.numel(), _ptr(v2), 0 if v2 is None else v2.numel(),
+          float(mult), out.data_ptr(), ws.data_ptr(), _st())
+    return out
+
+
 def grad_prep(x: torch.Tensor, nb: int, R: int, Cc: int, ldx: int, bstride: int, *, cs=None, rs=None, rs_period=0,
               want_rm: bool = False, want_t: bool = False, want_colsum: bool = False, u=None, group: int = 64,
-              planes: int = 1):
-    """One pass over a fp32 gradient: returns dict(rm=bf16 [planes,nb,R,C], t=bf16 [planes,nb,C,r_pad], r_pad,
+              planes: int = 1, fmt: int = FMT_BF16, scale4=None):
+    """One pass over a fp32 gradient: returns dict(rm=16-bit [planes,nb,R,C], t=16-bit [planes,nb,C,r_pad], r_pad,
     colsum [C], rowdot [nb,C/group,R])."""
     _cuda(x)
     dev = x.device
     r_pad = round_up(R, 8)
     out = {"r_pad": r_pad}
-    rm = torch.empty((planes, nb, R, Cc), dtype=torch.bfloat16, device=dev) if want_rm else None
-    t = torch.empty((planes, nb, Cc, r_pad), dtype=torch.bfloat16, device=dev) if want_t else None
+    rm = torch.empty((planes, nb, R, Cc), dtype=_T16[fmt], device=dev) if want_rm else None
+    t = torch.empty((planes, nb, Cc, r_pad), dtype=_T16[fmt], device=dev) if want_t else None
     colsum = torch.zeros(Cc, dtype=torch.float32, device=dev) if want_colsum else None
     rowdot = torch.empty((nb, Cc // group, R), dtype=torch.float32, device=dev) if u is not None else None
     nbytes = nb * R * Cc * (4.0 + 2 * planes * (int(want_rm) + int(want_t)))
     _call("grad_prep", 1, nbytes, 0, _lib.load().ofq_grad_prep, x.data_ptr(), nb, R, Cc, ldx, bstride, _ptr(cs), _ptr(rs),
-          rs_period, planes, _ptr(rm), Cc, _ptr(t), r_pad, _ptr(colsum), _ptr(u), group, _ptr(rowdot), _st())
+          rs_period, planes, _ptr(rm), Cc, _ptr(t), r_pad, _ptr(colsum), _ptr(u), group, _ptr(rowdot), fmt, _ptr(scale4), _st())
     out.update(rm=rm, t=t, colsum=colsum, rowdot=rowdot)
     return out
 
 
-def codes_to_bf16(codes: torch.Tensor, nb: int, R: int, Cc: int, ld: int, bstride: int, transpose: bool):
-    """int8 codes [nb][R][C] -> bf16 [nb,R,C] or transposed [nb,C,r_pad]."""
+def codes_to_bf16(codes: torch.Tensor, nb: int, R: int, Cc: int, ld: int, bstride: int, transpose: bool,
+                  fmt: int = FMT_BF16):
+    """int8 codes [nb][R][C] -> bf16 / fp16 (exact) [nb,R,C] or transposed [nb,C,r_pad]."""
     _cuda(codes)
     if transpose:
         r_pad = round_up(R, 8)
-        out = torch.empty((nb, Cc, r_pad), dtype=torch.bfloat16, device=codes.device)
-        _call("codes_to_bf16", 1, 3.0 * nb * R * Cc, 0, _lib.load().ofq_codes_to_bf16, codes.data_ptr(), nb, R, Cc, ld,
-              bstride, out.data_ptr(), r_pad, Cc * r_pad, 1, _st())
+        out = torch.empty((nb, Cc, r_pad), dtype=_T16[fmt], device=codes.device)
+        _call("codes_to_bf16", 1, 3.0 * nb * R * Cc, 0, _lib.load().ofq_codes_to_16, codes.data_ptr(), nb, R, Cc, ld,
+              bstride, out.data_ptr(), r_pad, Cc * r_pad, 1, fmt, _st())
     else:
-        out = torch.empty((nb, R, Cc), dtype=torch.bfloat16, device=codes.device)
-        _call("codes_to_bf16", 1, 3.0 * nb * R * Cc, 0, _lib.load().ofq_codes_to_bf16, codes.data_ptr(), nb, R, Cc, ld,
-              bstride, out.data_ptr(), Cc, R * Cc, 0, _st())
+        out = torch.empty((nb, R, Cc), dtype=_T16[fmt], device=codes.device)
+        _call("codes_to_bf16", 1, 3.0 * nb * R * Cc, 0, _lib.load().ofq_codes_to_16, codes.data_ptr(), nb, R, Cc, ld,
+              bstride, out.data_ptr(), Cc, R * Cc, 0, fmt, _st())
     return out
 
 
@@ -221,21 +245,21 @@ def softmax_quant(S: torch.Tensor, N: int, H: int, s_eff: torch.Tensor, qhi: int
 
 def softmax_quant_bwd(dPq: torch.Tensor, P: torch.Tensor, N: int, H: int, s_eff: torch.Tensor, qhi: int, alpha: float,
                       g_s: float, ca: torch.Tensor, ca_per_head: bool, rb: torch.Tensor, want_ds32: bool = False,
-                      planes: int = 1):
+                      planes: int = 1, fmt: int = FMT_BF16, scale4=None):
     """Returns (out_a bf16 [B,planes,H,N,ldo], out_bt bf16 [B,planes,H,N,ldo], ldo, colsum [nz,N], d_s [N], dS32 | None)."""
     _cuda(dPq, P)
     nz, _, ld = P.shape
     ldo = round_up(N, 8)
     dev = P.device
-    out_a = torch.empty((nz // H, planes, H, N, ldo), dtype=torch.bfloat16, device=dev)
-    out_bt = torch.empty((nz // H, planes, H, N, ldo), dtype=torch.bfloat16, device=dev)
+    out_a = torch.empty((nz // H, planes, H, N, ldo), dtype=_T16[fmt], device=dev)
+    out_bt = torch.empty((nz // H, planes, H, N, ldo), dtype=_T16[fmt], device=dev)
     colsum = torch.zeros((nz, N), dtype=torch.float32, device=dev)
     d_s = torch.zeros(N, dtype=torch.float32, device=dev)
     ds32 = torch.empty_like(P) if want_ds32 else None
     _call("softmax_quant_bwd", 1, nz * N * N * (8.0 + 4 * planes + (4 if want_ds32 else 0)), 0,
           _lib.load().ofq_softmax_quant_bwd, dPq.data_ptr(), P.data_ptr(), nz, N, ld, H, s_eff.data_ptr(), qhi,
           float(alpha), float(g_s), _ptr(ca), 1 if ca_per_head else 0, _ptr(rb), planes, out_a.data_ptr(),
-          out_bt.data_ptr(), ldo, colsum.data_ptr(), d_s.data_ptr(), _ptr(ds32), _st())
+          out_bt.data_ptr(), ldo, colsum.data_ptr(), d_s.data_ptr(), _ptr(ds32), fmt, _ptr(scale4), _st())
     return out_a, out_bt, ldo, colsum, d_s, ds32
 
 
@@ -255,7 +279,7 @@ def wqk_compose_bwd(dwqk: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, H: i
     hd = wq.shape[0] // H
     dwq = torch.empty_like(wq)
     dwk = torch.empty_like(wk)
-    _call("wqk_compose_bwd", 2, 4.0 * (4 * H * hd * Cc + 2 * H * Cc * Cc), 4.0 * H * hd * Cc * Cc,
+    _call("wqk_compose_bwd", 1, 4.0 * (4 * H * hd * Cc + 2 * H * Cc * Cc), 4.0 * H * hd * Cc * Cc,
           _lib.load().ofq_wqk_compose_bwd, dwqk.data_ptr(), wq.data_ptr(), wk.data_ptr(), H, hd, Cc, dwq.data_ptr(),
           dwk.data_ptr(), _st())
     return dwq, dwk

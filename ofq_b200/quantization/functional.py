@@ -15,12 +15,24 @@ from typing import Optional
 import torch
 
 from .. import ops
-from ..ops import GEMM_BF16, GEMM_I8, PER_COL, PER_ROW, round_up, vec
+from ..ops import FMT_BF16, FMT_F16, GEMM_BF16, GEMM_F16, GEMM_I8, PER_COL, PER_ROW, round_up, vec
 
 NUM_SMS = 148
-# bf16 planes of every real-valued backward GEMM operand: 2 = hi + lo split (~16 mantissa bits, meets the 1e-3
-# parity bound on every gradient), 1 = plain bf16 (~1-2e-3 gradient error, half the operand traffic).
-PLANES = int(os.environ.get("OFQ_BWD_PLANES", "2"))
+# Number format of the real-valued (gradient) operand of every backward GEMM; the integer-code operand is exact in all:
+#   "f16"    one fp16 plane (11 significant bits, ~2e-4 gradient error), range-scaled per tensor by a power of two
+#            from an absmax pass (ops.absmax_scale) and un-scaled in the GEMM epilogue              [default]
+#   "bf16x2" bf16 hi + lo planes (~16 significant bits, ~5e-6 gradient error, twice the tensor work)
+#   "bf16"   one bf16 plane (1-2e-3 gradient error: outside the 1e-3 parity bound, kept for experiments)
+_mode = os.environ.get("OFQ_BWD_MODE")
+if _mode is None:
+    _mode = {"2": "bf16x2", "1": "bf16"}.get(os.environ.get("OFQ_BWD_PLANES", ""), "f16")
+if _mode not in ("f16", "bf16x2", "bf16"):
+    raise ValueError(f"OFQ_BWD_MODE={_mode!r}: expected f16, bf16x2 or bf16")
+BWD_MODE = _mode
+F16 = BWD_MODE == "f16"
+PLANES = 2 if BWD_MODE == "bf16x2" else 1
+GEMM_BWD = GEMM_F16 if F16 else GEMM_BF16
+FMT = FMT_F16 if F16 else FMT_BF16
 # With two planes the GEMM loads hi and lo of the gradient operand in the same pipeline stage and multiplies both by
 # one copy of the code operand ("dual-A", ofq_operand_t.dual_delta) instead of looping over planes as outer-K slices.
 DUAL = PLANES == 2
@@ -42,6 +54,11 @@ def grad_scale_factor(hi: int, count: int) -> float:
     return 1.0 / ((hi * count) ** 0.5)
 
 
+def _inv(sc, which: int):
+    """Epilogue un-scale of a range-scaled fp16 operand: device scalar 1/scale as a period-1 row vector."""
+    return vec(sc[2 * which + 1:2 * which + 2], 1) if sc is not None else None
+
+
 def _splits_for(tiles: int, kblocks: int) -> int:
     s = max(1, min((2 * NUM_SMS + tiles - 1) // tiles, max(1, kblocks // 4)))
     return min(s, 64)
@@ -52,22 +69,23 @@ def _linear_backward(dY2d, qx, wc, colscale, se_x, period, x_aft, dxhat, accumul
     x_hat = qx * se_x[row % period] + x_aft,  W_hat = wc * colscale[row].  Returns (dW, dbias, qxT_all)."""
     M, Nout = dY2d.shape
     K = qx.shape[1]
+    sc = ops.absmax_scale(dY2d, 1, M, Nout, dY2d.stride(0), 0, cs=colscale, rs=se_x, rs_period=period) if F16 else None
     prep = ops.grad_prep(dY2d, 1, M, Nout, dY2d.stride(0), 0, cs=colscale, rs=se_x, rs_period=period,
-                         want_rm=True, want_t=True, want_colsum=True, planes=PLANES)
+                         want_rm=True, want_t=True, want_colsum=True, planes=PLANES, fmt=FMT, scale4=sc)
     m_pad = prep["r_pad"]
     # dX_hat[M,K] = (dY * colscale)[M,Nout] @ codes[Nout,K]
-    wcT = ops.codes_to_bf16(wc, 1, Nout, K, K, 0, True)            # [1, K, nout_pad]
+    wcT = ops.codes_to_bf16(wc, 1, Nout, K, K, 0, True, FMT)       # [1, K, nout_pad]
     nout_pad = wcT.shape[-1]
-    ops.gemm(GEMM_BF16, prep["rm"], (Nout, M * Nout, 0, 0), wcT, (nout_pad, 0, 0, 0), dxhat, (K, 0, 0), M, K, Nout,
-             k2=K2P, a_dual_delta=DD, accumulate=accumulate_dx)
+    ops.gemm(GEMM_BWD, prep["rm"], (Nout, M * Nout, 0, 0), wcT, (nout_pad, 0, 0, 0), dxhat, (K, 0, 0), M, K, Nout,
+             k2=K2P, a_dual_delta=DD, accumulate=accumulate_dx, rs=_inv(sc, 0))
     # dW[Nout,K] = (dY * se_x)^T[Nout,M] @ qx[M,K]  + colsum(dY)[Nout] x aft[K]
     if qxT_all is None:
-        qxT_all = ops.codes_to_bf16(qx, 1, M, K, K, 0, True)       # [1, K, m_pad]
+        qxT_all = ops.codes_to_bf16(qx, 1, M, K, K, 0, True, FMT)  # [1, K, m_pad]
     dW = torch.zeros((Nout, K), dtype=torch.float32, device=dY2d.device)
     tiles = ((Nout + 127) // 128) * ((K + 127) // 128)
     splits = _splits_for(tiles, K2P * ((M + 63) // 64))
-    ops.gemm(GEMM_BF16, prep["t"], (m_pad, Nout * m_pad, 0, 0), qxT_all, (m_pad, 0, 0, 0), dW, (K, 0, 0), Nout, K, M,
-             k2=K2P, a_dual_delta=DD, splits=splits, accumulate=True, rt=vec(prep["colsum"]), ct=vec(x_aft))
+    ops.gemm(GEMM_BWD, prep["t"], (m_pad, Nout * m_pad, 0, 0), qxT_all, (m_pad, 0, 0, 0), dW, (K, 0, 0), Nout, K, M,
+             k2=K2P, a_dual_delta=DD, splits=splits, accumulate=True, rs=_inv(sc, 1), rt=vec(prep["colsum"]), ct=vec(x_aft))
     return dW, prep["colsum"], qxT_all
 
 
@@ -162,19 +180,21 @@ def _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C):
 def _pv_backward(dO, qp, ldq, qv, se_p, se_v, v_aft, B, N, H, C, ldS):
     """Returns (dPq [B*H,N,ldS] fp32, dvhat [B,N,C] fp32)."""
     hd = C // H
+    sc = ops.absmax_scale(dO, B, N, C, C, N * C, cs=se_v, rs=se_p, rs_period=N) if F16 else None
     prep = ops.grad_prep(dO, B, N, C, C, N * C, cs=se_v, rs=se_p, rs_period=N, want_rm=True, want_t=True,
-                         u=v_aft, group=hd, planes=PLANES)
+                         u=v_aft, group=hd, planes=PLANES, fmt=FMT, scale4=sc)
     npad8 = prep["r_pad"]
     # dP_hat[z,n,d] = sum_j (dO[n,hj] se_v[hj]) qv[d,hj] + sum_j dO[n,hj] v_aft[hj]
-    qv16 = ops.codes_to_bf16(qv, B, N, C, C, N * C, False)           # [B, N, C] bf16
+    qv16 = ops.codes_to_bf16(qv, B, N, C, C, N * C, False, FMT)      # [B, N, C] 16-bit
     dPq = torch.empty((B * H, N, ldS), dtype=torch.float32, device=dO.device)
-    ops.gemm(GEMM_BF16, prep["rm"], (C, B * N * C, hd, N * C), qv16, (C, 0, hd, N * C), dPq, (ldS, N * ldS, H * N * ldS),
-             N, N, hd, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B, rt=vec(prep["rowdot"], 0, N, H * N))
+    ops.gemm(GEMM_BWD, prep["rm"], (C, B * N * C, hd, N * C), qv16, (C, 0, hd, N * C), dPq, (ldS, N * ldS, H * N * ldS),
+             N, N, hd, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B, rs=_inv(sc, 0), rt=vec(prep["rowdot"], 0, N, H * N))
     # dv_hat[b,d,hj] = sum_n qp[z,n,d] (se_p[n] dO[b,n,hj])
-    qpT = ops.codes_to_bf16(qp, B * H, N, ldq, ldq, N * ldq, True)   # [B*H, ldq, npad8]; rows d >= N are zero
+    qpT = ops.codes_to_bf16(qp, B * H, N, ldq, ldq, N * ldq, True, FMT)   # [B*H, ldq, npad8]; rows d >= N are zero
     dvhat = torch.empty((B, N, C), dtype=torch.float32, device=dO.device)
-    ops.gemm(GEMM_BF16, qpT, (npad8, 0, ldq * npad8, H * ldq * npad8), prep["t"],
-             (npad8, B * C * npad8, hd * npad8, C * npad8), dvhat, (C, hd, N * C), N, hd, N, k2=PLANES, nb1=H, nb2=B)
+    ops.gemm(GEMM_BWD, qpT, (npad8, 0, ldq * npad8, H * ldq * npad8), prep["t"],
+             (npad8, B * C * npad8, hd * npad8, C * npad8), dvhat, (C, hd, N * C), N, hd, N, k2=PLANES, nb1=H, nb2=B,
+             rs=_inv(sc, 1))
     return dPq, dvhat
 
 
@@ -253,25 +273,28 @@ class QKRAttnCoreFn(torch.autograd.Function):
         dxhat = torch.empty((M, C), dtype=torch.float32, device=dev)
         dWv, dbv, qxT_all = _linear_backward(dv_out, qx, wvc, cs_v, se_x, N, x_aft, dxhat, False)
         # --- softmax + probability quantizer
+        # fp16 range bound of dS * {se_k, se_x}: |dS| = |alpha P (dP - sum P dP)| <= 2 alpha max|dPq|
+        sc = (ops.absmax_scale(dPq, B * H, N, N, ldS, N * ldS, v1=se_k_hn, v2=se_x, mult=2.0 * scale) if F16 else None)
         dSa, dSbT, ldo, colsum_dS, ds_p, dS32 = ops.softmax_quant_bwd(dPq, P, N, H, se_p, hiu, scale, g_p, se_k_hn, True,
-                                                                    se_x, want_ds32=has_bias, planes=PLANES)
+                                                                    se_x, want_ds32=has_bias, planes=PLANES, fmt=FMT,
+                                                                    scale4=sc)
         slab = N * ldo                      # one (b, plane, h) slab of dSa / dSbT, laid out [B, PLANES, H, N, ldo]
         del dPq
         # --- scores: d x_hat += sum_h dS (k_hat)   (outer-K loop over heads)
-        qkT = ops.codes_to_bf16(qk, B, N, H * C, H * C, N * H * C, True)      # [B, H*C, npad8]
+        qkT = ops.codes_to_bf16(qk, B, N, H * C, H * C, N * H * C, True, FMT)      # [B, H*C, npad8]
         npad8 = qkT.shape[-1]
         if DUAL:     # planes of head h are outer-K slices h and h + H of dSa [B, 2, H, N, ldo]
-            ops.gemm(GEMM_BF16, dSa, (ldo, slab, PLANES * H * slab, 0), qkT, (npad8, C * npad8, H * C * npad8, 0),
+            ops.gemm(GEMM_BWD, dSa, (ldo, slab, PLANES * H * slab, 0), qkT, (npad8, C * npad8, H * C * npad8, 0),
                      dxhat, (C, N * C, 0), N, C, N, k2=H, a_dual_delta=H, nb1=B, accumulate=True)
         else:
-            ops.gemm(GEMM_BF16, dSa, (ldo, slab, PLANES * H * slab, 0), qkT, (npad8, C * npad8, H * C * npad8, 0),
-                     dxhat, (C, N * C, 0), N, C, N, k2=PLANES * H, nb1=B, accumulate=True, b_k2mod=H)
+            ops.gemm(GEMM_BWD, dSa, (ldo, slab, PLANES * H * slab, 0), qkT, (npad8, C * npad8, H * C * npad8, 0),
+                     dxhat, (C, N * C, 0), N, C, N, k2=PLANES * H, nb1=B, accumulate=True, b_k2mod=H, rs=_inv(sc, 0))
         # --- scores: d k_hat[b,d,h,c] = sum_n dS[n,d] x_hat[n,c]
-        qxT_b = ops.codes_to_bf16(qx, B, N, C, C, N * C, True)                # [B, C, npad8]
+        qxT_b = ops.codes_to_bf16(qx, B, N, C, C, N * C, True, FMT)           # [B, C, npad8]
         dkhat = torch.empty((M, H * C), dtype=torch.float32, device=dev)
-        ops.gemm(GEMM_BF16, dSbT, (ldo, H * slab, slab, PLANES * H * slab), qxT_b, (npad8, 0, 0, C * npad8), dkhat,
-                 (H * C, C, N * H * C), N, C, N, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B, rt=vec(colsum_dS, 0, N, H * N),
-                 ct=vec(x_aft))
+        ops.gemm(GEMM_BWD, dSbT, (ldo, H * slab, slab, PLANES * H * slab), qxT_b, (npad8, 0, 0, C * npad8), dkhat,
+                 (H * C, C, N * H * C), N, C, N, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B, rs=_inv(sc, 1),
+                 rt=vec(colsum_dS, 0, N, H * N), ct=vec(x_aft))
         del dSa, dSbT
         # --- qkx quantizer and the qkx "linear" layer (weight = StatsQ(W_q^T W_k), no bias)
         dqkx, ds_k, dkb4, dkaft = ops.lsq_bwd(dkhat, qkx, k_b4, se_k, PER_ROW, N, H, lo, hi, g_k)
@@ -340,22 +363,24 @@ class QAttnCoreFn(torch.autograd.Function):
         dO = dO.contiguous()
         q2d = qkvc.view(M, 3 * C)
         dPq, dvhat = _pv_backward(dO, qp, ldq, qv, se_p, se_v, v_aft, B, N, H, C, ldS)
+        sc = (ops.absmax_scale(dPq, B * H, N, N, ldS, N * ldS, v1=se_k, v2=se_q, mult=2.0 * scale) if F16 else None)
         dSa, dSbT, ldo, colsum_dS, ds_p, dS32 = ops.softmax_quant_bwd(dPq, P, N, H, se_p, hiu, scale, g_p, se_k, False,
-                                                                    se_q, want_ds32=has_bias, planes=PLANES)
+                                                                    se_q, want_ds32=has_bias, planes=PLANES, fmt=FMT,
+                                                                    scale4=sc)
         slab = N * ldo
         del dPq
         # dq_hat[b,n,hj] = sum_d (dS se_k[d]) qk[b,d,hj]
-        qkT = ops.codes_to_bf16(qk, B, N, C, C, N * C, True)          # [B, C, npad8]
+        qkT = ops.codes_to_bf16(qk, B, N, C, C, N * C, True, FMT)     # [B, C, npad8]
         npad8 = qkT.shape[-1]
         dqhat = torch.empty((M, C), dtype=torch.float32, device=dev)
-        ops.gemm(GEMM_BF16, dSa, (ldo, H * slab, slab, PLANES * H * slab), qkT, (npad8, 0, hd * npad8, C * npad8), dqhat,
-                 (C, hd, N * C), N, hd, N, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B)
+        ops.gemm(GEMM_BWD, dSa, (ldo, H * slab, slab, PLANES * H * slab), qkT, (npad8, 0, hd * npad8, C * npad8), dqhat,
+                 (C, hd, N * C), N, hd, N, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B, rs=_inv(sc, 0))
         # dk_hat[b,d,hj] = sum_n (dS se_q[n]) qq[b,n,hj] + colsum_dS[z,d] q_aft[hj]
-        qqT = ops.codes_to_bf16(qq, B, N, C, C, N * C, True)
+        qqT = ops.codes_to_bf16(qq, B, N, C, C, N * C, True, FMT)
         dkhat = torch.empty((M, C), dtype=torch.float32, device=dev)
-        ops.gemm(GEMM_BF16, dSbT, (ldo, H * slab, slab, PLANES * H * slab), qqT, (npad8, 0, hd * npad8, C * npad8), dkhat,
-                 (C, hd, N * C), N, hd, N, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B, rt=vec(colsum_dS, 0, N, H * N),
-                 ct=vec(q_aft, 0, hd))
+        ops.gemm(GEMM_BWD, dSbT, (ldo, H * slab, slab, PLANES * H * slab), qqT, (npad8, 0, hd * npad8, C * npad8), dkhat,
+                 (C, hd, N * C), N, hd, N, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B, rs=_inv(sc, 1),
+                 rt=vec(colsum_dS, 0, N, H * N), ct=vec(q_aft, 0, hd))
         dq, ds_q, db4_q, daft_q = ops.lsq_bwd(dqhat, q2d[:, 0:C], b4[0:C], se_q, PER_ROW, N, 1, lo, hi, g_qk)
         dk, ds_k, db4_k, daft_k = ops.lsq_bwd(dkhat, q2d[:, C:2 * C], b4[C:2 * C], se_k, PER_ROW, N, 1, lo, hi, g_qk)
         dv, ds_v, db4_v, daft_v = ops.lsq_bwd(dvhat.view(M, C), q2d[:, 2 * C:], b4[2 * C:], se_v, PER_COL, 1, 1, lo, hi, g_v)

@@ -299,6 +299,61 @@ def test_grad_prep_and_code_conversions(ops):
     assert torch.equal(ti[..., :R], codes.transpose(1, 2)) and bool((ti[..., R:] == 0).all())
 
 
+def test_absmax_scale_and_fp16_prep(ops):
+    """Range-scaled fp16 operands (backward mode "f16"): the power-of-two scale places the operand's absmax in
+    [2^14, 2^15), the fp16 planes are the correctly rounded scaled values and the GEMM un-scales in its epilogue."""
+    torch.manual_seed(11)
+    nb, R, Cc = 2, 198, 384
+    x = torch.randn(nb, R, Cc, device="cuda") * 3e-6           # gradient-like magnitudes: far below the fp16 normal range
+    x[1, 17, 5] = 2.5e-3                                       # one outlier sets the range
+    cs = torch.rand(Cc, device="cuda") * 0.05 + 0.01
+    rs = torch.rand(R, device="cuda") + 0.5
+    sc = ops.absmax_scale(x, nb, R, Cc, Cc, R * Cc, cs=cs, rs=rs, rs_period=R)
+    sc2 = ops.absmax_scale(x, nb, R, Cc, Cc, R * Cc, cs=cs, rs=rs, rs_period=R)     # the workspace counter self-resets
+    assert torch.equal(sc, sc2)
+    for bound, k in (((x * cs).abs().max(), 0), ((x * rs[None, :, None]).abs().max(), 2)):
+        s, inv = sc[k].item(), sc[k + 1].item()
+        assert s * inv == 1.0 and torch.frexp(torch.tensor(s))[0].item() == 0.5            # exact power of two
+        assert 2.0 ** 14 <= bound.item() * s < 2.0 ** 15
+    o = ops.grad_prep(x, nb, R, Cc, Cc, R * Cc, cs=cs, rs=rs, rs_period=R, want_rm=True, want_t=True, want_colsum=True,
+                      fmt=ops.FMT_F16, scale4=sc)
+    assert o["rm"].dtype == torch.float16
+    assert torch.equal(o["rm"][0], (x * cs * sc[0]).half())
+    assert torch.equal(o["t"][0][..., :R], (x * (rs[None, :, None] * sc[2])).half().transpose(1, 2))
+    assert rel_err(o["rm"][0].float() * sc[1], x * cs) < 4e-4                     # 11 significant bits
+    # bound multipliers and a ragged (N = 198, pitch 200) operand such as dL/dP_hat
+    y = torch.randn(6, R, 200, device="cuda")
+    y[..., R:] = float("nan")                                   # pitch padding is never read as data
+    v1 = torch.rand(R, device="cuda") + 1.0
+    v2 = torch.rand(R, device="cuda") + 3.0
+    sc3 = ops.absmax_scale(y, 6, R, R, 200, R * 200, v1=v1, v2=v2, mult=0.25)
+    amax = y[..., :R].abs().max().item()
+    assert 2.0 ** 14 <= amax * v1.max().item() * 0.25 * sc3[0].item() < 2.0 ** 15
+    assert 2.0 ** 14 <= amax * v2.max().item() * 0.25 * sc3[2].item() < 2.0 ** 15
+    z = torch.zeros(1, 8, 64, device="cuda")
+    assert ops.absmax_scale(z, 1, 8, 64, 64, 512).tolist() == [1.0, 1.0, 1.0, 1.0]           # all-zero gradient: no scaling
+    codes = torch.randint(-8, 8, (nb, R, Cc), dtype=torch.int8, device="cuda")
+    assert torch.equal(ops.codes_to_bf16(codes, nb, R, Cc, Cc, R * Cc, False, ops.FMT_F16), codes.half())
+    tb = ops.codes_to_bf16(codes, nb, R, Cc, Cc, R * Cc, True, ops.FMT_F16)
+    assert torch.equal(tb[..., :R], codes.half().transpose(1, 2)) and bool((tb[..., R:] == 0).all())
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(384, 1536, 25344, 8), (25344, 384, 1536, 1), (500, 72, 200, 1)])
+def test_gemm_f16_scaled(ops, M, N, K, splits):
+    """fp16 tensor-core GEMM with the range scale undone by a period-1 row vector in the epilogue."""
+    torch.manual_seed(12)
+    g = torch.randn(M, K, device="cuda") * 1e-5
+    sc = ops.absmax_scale(g, 1, M, K, K, 0)
+    A = (g * sc[0]).half()
+    Bm = torch.randint(-3, 4, (N, K), device="cuda").half()
+    out = torch.zeros((M, N), device="cuda")
+    ops.gemm(ops.GEMM_F16, A, (K, 0, 0, 0), Bm, (K, 0, 0, 0), out, (N, 0, 0), M, N, K, splits=splits, accumulate=splits > 1,
+             rs=ops.vec(sc[1:2], 1))
+    exact = (A.double() * sc[1].double()) @ Bm.double().T
+    assert rel_err(out, exact) < 1e-5                                 # fp32 accumulation of exact fp16 products
+    assert rel_err(out, g.double() @ Bm.double().T) < 4e-4            # operand rounding: 11 significant bits
+
+
 # ------------------------------------------------------------------------------------------------ softmax
 @pytest.mark.parametrize("N,H,bit", [(198, 6, 2), (49, 3, 3), (197, 3, 4)])
 def test_softmax_quant_forward(ops, N, H, bit):

@@ -10,9 +10,12 @@ for r in csv.DictReader(lines):
     cur.setdefault((r["ID"], r["Kernel Name"]), {})[r["Metric Name"]] = float(r["Metric Value"].replace(",", "")) * scale
 
 def family(k):
-    m = re.search(r"gemm_tc_kernel<(\d), (\d+), (\d+)>", k)
+    m = re.search(r"gemm_tc_kernel<(\d), (\d+), (\d+)(?:, (\d+), (\d+))?>", k)
     if m:
-        return f"ofq gemm_tc_kernel<{'i8' if m.group(1) == '0' else 'bf16'}, BN={m.group(2)}>"
+        return f"ofq gemm_tc_kernel<{'i8' if m.group(1) == '0' else '16-bit'}, BN={m.group(2)}{', dual-A' if m.group(4) == '2' else ''}>"
+    m = re.search(r"ofq::(\w+)", k)
+    if m:
+        return "ofq " + m.group(1)
     m = re.search(r"<unnamed>::(\w+)", k)
     if m and "at::" not in k:
         return "ofq " + m.group(1)
@@ -41,7 +44,7 @@ with open(dst, "w") as f:
         f.write(f"| {k} | {p['n']} | {p['ns'] / 1e6:.3f} | {100 * p['ns'] / tot:.2f} | {p['ns'] / p['n'] / 1e3:.1f} | {(p['rd'] + p['wr']) / p['n'] / 1e6:.2f} |\n")
 print(open(dst).read()[:3500])
 if len(sys.argv) > 3:
-    fam_map = {"gemm_bf16": "gemm_tc_kernel<bf16", "gemm_i8": "gemm_tc_kernel<i8", "lsq_bwd": "ofq lsq_bwd_kernel", "lsq_quant": "ofq lsq_quant_kernel",
+    fam_map = {"gemm_bf16": "gemm_tc_kernel<16-bit", "gemm_f16": "gemm_tc_kernel<16-bit", "absmax_scale": "ofq absmax_scale_kernel", "gemm_i8": "gemm_tc_kernel<i8", "lsq_bwd": "ofq lsq_bwd_kernel", "lsq_quant": "ofq lsq_quant_kernel",
                "grad_prep": "ofq grad_prep_kernel", "softmax_quant": "ofq softmax_quant_kernel", "softmax_quant_bwd": "ofq softmax_quant_bwd_kernel",
                "codes_to_bf16": "ofq codes_convert_kernel"}
     out = {}
