@@ -60,6 +60,9 @@ typedef struct {
                              holds k2 + dual_delta slices. 0 = off */
     long long bstride1;   /* elements between batch-axis-1 entries, 0 = broadcast */
     long long bstride2;   /* elements between batch-axis-2 entries, 0 = broadcast */
+    int mn_major;         /* 16-bit kinds only: 1 = the operand is stored [k][row] (rows contiguous) and row_stride is the
+                             distance between consecutive k; lets a row-major [tokens][features] tensor serve as the
+                             transposed operand of dW = dY^T X without a transposed copy. 0 = K-major */
 } ofq_operand_t;
 
 typedef struct {
@@ -128,6 +131,10 @@ OFQ_API int ofq_lsq_bwd(const float* dy, long long lddy, const float* x, long lo
                         int qlo, int qhi, float* dx, long long lddx, float* workspace, void* stream);
 OFQ_API int ofq_lsq_bwd_finalize(const float* workspace, long long rows, int cols, int scale_mode, int period,
                                  int nseg, float g, float* d_s, float* d_b4, float* d_aft, void* stream);
+/* fp16 range scales (layout of ofq_absmax_scale's out4) for the NEXT consumer of dx, from the per-block max |dx| that
+ * ofq_lsq_bwd left in its workspace: bound_1 = max|dx| * max|v1| * mult, bound_2 = max|dx| * max|v2| * mult. */
+OFQ_API int ofq_lsq_bwd_scale(const float* workspace, long long rows, int cols, int nseg, const float* v1, int n1,
+                              const float* v2, int n2, float mult, float* out4, void* stream);
 
 /* Gradient operand preparation for the bf16 backward GEMMs: one pass over a fp32 gradient x[nb][R][C]:
  *   out_rm[p][b][r][c] = bf16 plane p of ( x * cs[c] )              (row-major, ld = ld_rm; NULL to skip)

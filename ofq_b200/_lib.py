@@ -19,7 +19,7 @@ class OfqError(RuntimeError):
 
 class Operand(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("row_stride", C.c_longlong), ("k2_stride", C.c_longlong), ("k2_mod", C.c_int),
-                ("dual_delta", C.c_int), ("bstride1", C.c_longlong), ("bstride2", C.c_longlong)]
+                ("dual_delta", C.c_int), ("bstride1", C.c_longlong), ("bstride2", C.c_longlong), ("mn_major", C.c_int)]
 
 
 class Vec(C.Structure):
@@ -47,6 +47,7 @@ SIGNATURES = {
     "ofq_lsq_bwd_workspace": (_ll, [_ll, _i, _i]),
     "ofq_lsq_bwd": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _i, _i, _i, _i, _i, _p, _ll, _p, _p]),
     "ofq_lsq_bwd_finalize": (_i, [_p, _ll, _i, _i, _i, _i, _f, _p, _p, _p, _p]),
+    "ofq_lsq_bwd_scale": (_i, [_p, _ll, _i, _i, _p, _i, _p, _i, _f, _p, _p]),
     "ofq_grad_prep": (_i, [_p, _i, _i, _i, _ll, _ll, _p, _p, _i, _i, _p, _ll, _p, _i, _p, _p, _i, _p, _i, _p, _p]),
     "ofq_absmax_scale_workspace": (_ll, []),
     "ofq_absmax_scale": (_i, [_p, _i, _i, _i, _ll, _ll, _p, _p, _i, _p, _i, _p, _i, _f, _p, _p, _p]),

@@ -41,6 +41,7 @@ struct GemmParams {
     int has_rank1;
     int atomic;
     int ab_fmt;              // 16-bit kinds: UMMA a/b format field (0 = F16, 1 = BF16)
+    int a_mn, b_mn;          // 16-bit kinds: operand is MN-major (rows contiguous, K strided) instead of K-major
 };
 
 // NA: A tiles per pipeline stage. NA = 2 ("dual-A") loads the bf16 hi and lo planes of a gradient operand together with
@@ -94,7 +95,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
     constexpr uint32_t UMMA_K_BYTES = 32;  // 32 int8 or 16 bf16 per MMA
     // S32 accumulate / signed int8, or F32 accumulate / {fp16, bf16} (format chosen at run time)
-    const uint32_t IDESC = KIND == 0 ? umma_idesc(2u, 1u, BM, BN) : umma_idesc(1u, (uint32_t)p.ab_fmt, BM, BN);
+    const uint32_t IDESC = KIND == 0 ? umma_idesc(2u, 1u, BM, BN)
+                                     : (umma_idesc(1u, (uint32_t)p.ab_fmt, BM, BN) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16));
 
     // 1024-byte alignment is required by the 128B swizzle; the attribute keeps the pointer in the shared address
     // space (an integer round-up would degrade every access to generic LD/ST)
@@ -148,10 +150,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint8_t* sa = smem + s * STAGE_BYTES;
                     uint8_t* sb = sa + NA * A_BYTES;
                     mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-                    tma_load_5d(sa, &tmA, &full_bar[s], kb * kelem, c.m0, (k2i % p.a_k2mod) * p.a_k2, c.b1 * p.a_b1, c.b2 * p.a_b2);
-                    if (NA == 2)
-                        tma_load_5d(sa + A_BYTES, &tmA, &full_bar[s], kb * kelem, c.m0, k2i + p.a_dual_delta, c.b1 * p.a_b1, c.b2 * p.a_b2);
-                    tma_load_5d(sb, &tmB, &full_bar[s], kb * kelem, c.n0, (k2i % p.b_k2mod) * p.b_k2, c.b1 * p.b_b1, c.b2 * p.b_b2);
+                    if (KIND != 0 && p.a_mn) {   // MN-major: 64-row x 64-k boxes, one 8 KB swizzle-atom column each
+                        for (int j = 0; j < BM / 64; ++j)
+                            tma_load_5d(sa + j * 8192, &tmA, &full_bar[s], c.m0 + 64 * j, kb * kelem, (k2i % p.a_k2mod) * p.a_k2, c.b1 * p.a_b1, c.b2 * p.a_b2);
+                    } else {
+                        tma_load_5d(sa, &tmA, &full_bar[s], kb * kelem, c.m0, (k2i % p.a_k2mod) * p.a_k2, c.b1 * p.a_b1, c.b2 * p.a_b2);
+                        if (NA == 2)
+                            tma_load_5d(sa + A_BYTES, &tmA, &full_bar[s], kb * kelem, c.m0, k2i + p.a_dual_delta, c.b1 * p.a_b1, c.b2 * p.a_b2);
+                    }
+                    if (KIND != 0 && p.b_mn) {
+                        for (int j = 0; j < BN / 64; ++j)
+                            tma_load_5d(sb + j * 8192, &tmB, &full_bar[s], c.n0 + 64 * j, kb * kelem, (k2i % p.b_k2mod) * p.b_k2, c.b1 * p.b_b1, c.b2 * p.b_b2);
+                    } else {
+                        tma_load_5d(sb, &tmB, &full_bar[s], kb * kelem, c.n0, (k2i % p.b_k2mod) * p.b_k2, c.b1 * p.b_b1, c.b2 * p.b_b2);
+                    }
                 }
             }
         }
@@ -170,17 +182,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-                    const uint64_t bdesc = umma_desc_kmajor_sw128(sa + NA * A_BYTES);
+                    // K-major: one MMA consumes 32 bytes of the 128-byte K row. MN-major (16-bit): 16 k-rows of 128 bytes.
+                    const bool bmn = KIND != 0 && p.b_mn, amn = KIND != 0 && p.a_mn;
+                    const uint64_t bdesc = bmn ? umma_desc_mnmajor_sw128(sa + NA * A_BYTES) : umma_desc_kmajor_sw128(sa + NA * A_BYTES);
+                    const uint64_t badv = bmn ? (2048u >> 4) : (UMMA_K_BYTES >> 4);
+                    const uint64_t aadv = amn ? (2048u >> 4) : (UMMA_K_BYTES >> 4);
 #pragma unroll
                     for (uint32_t na = 0; na < (uint32_t)NA; ++na) {
-                        const uint64_t adesc = umma_desc_kmajor_sw128(sa + na * A_BYTES);
+                        const uint64_t adesc = amn ? umma_desc_mnmajor_sw128(sa + na * A_BYTES) : umma_desc_kmajor_sw128(sa + na * A_BYTES);
 #pragma unroll
                         for (uint32_t kk = 0; kk < KBYTES / UMMA_K_BYTES; ++kk) {
-                            const uint64_t adv = (kk * UMMA_K_BYTES) >> 4;
                             if (KIND == 0)
-                                umma_i8(tmem_d, adesc + adv, bdesc + adv, IDESC, (i | kk | na) != 0);
+                                umma_i8(tmem_d, adesc + kk * aadv, bdesc + kk * badv, IDESC, (i | kk | na) != 0);
                             else
-                                umma_f16(tmem_d, adesc + adv, bdesc + adv, IDESC, (i | kk | na) != 0);
+                                umma_f16(tmem_d, adesc + kk * aadv, bdesc + kk * badv, IDESC, (i | kk | na) != 0);
                         }
                     }
                     tc_commit(&empty_bar[s]);      // frees the smem stage when these MMAs retire
@@ -350,6 +365,10 @@ static int make_operand_map(CUtensorMap* tm, const ofq_operand_t* op, int elem_b
     }
     cuuint32_t box[5] = {(cuuint32_t)(KBYTES / elem_bytes), (cuuint32_t)box_rows, 1, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (op->mn_major) {   // {rows (contiguous), K, k2, b1, b2}; box = 64 rows (128 B) x 64 k
+        dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K;
+        box[0] = 64; box[1] = (cuuint32_t)(KBYTES / elem_bytes);
+    }
     return ofq_encode_tensor_map(tm, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
                                  : (f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16),
                                  5, const_cast<void*>(op->ptr), dims, strides, box, estr);
@@ -401,6 +420,11 @@ extern "C" int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B
     p.has_rank1 = (rt && rt->ptr) || (ct && ct->ptr);
     p.atomic = out->accumulate;
     p.ab_fmt = kind == OFQ_GEMM_F16 ? 0 : 1;
+    p.a_mn = A->mn_major != 0; p.b_mn = B->mn_major != 0;
+    if ((p.a_mn || p.b_mn) && (kind == OFQ_GEMM_I8 || A->dual_delta > 0)) {
+        ofq_set_error("ofq_gemm: MN-major operands are supported for the 16-bit kinds without dual-A only");
+        return OFQ_ERR_ARG;
+    }
     if (splits > 1 && !p.atomic) {
         ofq_set_error("ofq_gemm: split-K requires an accumulating (pre-zeroed) output");
         return OFQ_ERR_ARG;
@@ -411,6 +435,7 @@ extern "C" int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B
     int bn = 32;
     long long best_cost = -1;
     for (int w : widths) {
+        if (p.b_mn && w % 64) continue;          // MN-major B tiles are whole 64-row swizzle atoms
         const long long nt = (N + w - 1) / w;
         const long long cost = nt * (128 + w);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; bn = w; }

@@ -160,6 +160,20 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// MN-major operand (rows contiguous), 16-bit elements, 128-byte swizzle: the tile is stored as 64-row x 64-k boxes
+// (TMA box {64 rows = 128 B, 64 k}); inside a box k-row j sits at j * 128 B, so 8-k groups are 1024 B apart (SBO) and
+// consecutive 64-row boxes are 64 * 128 = 8192 B apart (LBO). Canonical form ((8,n),(8,k)):((1,LBO),(8,SBO)) in
+// 16-byte units (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>).
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);  // start address   [0,14)
+    d |= static_cast<uint64_t>(8192 >> 4) << 16;              // LBO = 8192 B    [16,30)
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;              // SBO = 1024 B    [32,46)
+    d |= static_cast<uint64_t>(1) << 46;                      // version = 1     [46,48)
+    d |= static_cast<uint64_t>(2) << 61;                      // SWIZZLE_128B    [61,64)
+    return d;
+}
+
 // Instruction descriptor (cute::UMMA::InstrDescriptor): dense, K-major A and B.
 //   c_format [4,6): 1 = F32, 2 = S32;  a/b_format [7,10)/[10,13): kind::i8 1 = signed int8, kind::f16 1 = BF16
 //   n_dim [17,23) = N>>3;  m_dim [24,29) = M>>4

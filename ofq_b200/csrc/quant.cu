@@ -23,6 +23,14 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Power-of-two scale that places `bound` in [2^14, 2^15) (fp16 operands of the backward GEMMs) and its inverse.
+__device__ __forceinline__ void pow2_scale_pair(float bound, float* sc, float* inv) {
+    const uint32_t e = (__float_as_uint(bound) >> 23) & 0xffu;
+    if (e < 16u || e > 250u) { *sc = 1.f; *inv = 1.f; return; }   // zero / denormal / non-finite bound: no scaling
+    *sc = __uint_as_float((268u - e) << 23);                     // 2^(141 - e): bound * sc in [2^14, 2^15)
+    *inv = __uint_as_float((e - 14u) << 23);                      // 2^(e - 141)
+}
+
 // ------------------------------------------------------------------------------------------- K1 StatsQ
 // One warp per weight row. statsq.py:137-147.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -174,8 +182,10 @@ lsq_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __rest
                long long rows, int cols, const float* __restrict__ b4, const float* __restrict__ s_eff,
                int period, int nseg, int seg_len, float qlo, float qhi,
                float* __restrict__ dx, long long lddx, float* __restrict__ rowpart,
-               float* __restrict__ colpart) {
+               float* __restrict__ colpart, float* __restrict__ blockmax) {
     __shared__ float col_s[3][kBwdChunk];     // index [v][(p * 4 + e) * 32 + lane]: conflict-free for the fold
+    __shared__ float bmax_s[kWarpsPerBlock];
+    float tmax = 0.f;                         // max |dx| seen by this thread (fp16 range scale of the next GEMM operand)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long rpb = (rows + gridDim.x - 1) / gridDim.x;
     const long long r0 = (long long)blockIdx.x * rpb;
@@ -243,6 +253,7 @@ lsq_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __rest
                     const float q = rintf(fminf(fmaxf(v, qlo), qhi));
                     const float t = gg[e] * (inside ? (q - v) : q);
                     o[e] = inside ? gg[e] : 0.f;
+                    tmax = fmaxf(tmax, fabsf(o[e]));
                     a_aft[p][e] += gg[e];
                     a_b4[p][e] += o[e];
                     if (scale_mode == OFQ_SCALE_PER_ROW) part[p] += t; else a_s[p % NS][e] += t;
@@ -287,6 +298,43 @@ lsq_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __rest
             }
         }
         __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    if (lane == 0) bmax_s[warp] = tmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < kWarpsPerBlock; ++w) tmax = fmaxf(tmax, bmax_s[w]);
+        blockmax[blockIdx.x] = tmax;
+    }
+}
+
+// out4 = power-of-two fp16 range scales from per-block maxima of a gradient: bound_1 = max(blockmax) * max|v1| * mult,
+// bound_2 = max(blockmax) * max|v2| * mult (looser than ofq_absmax_scale by the spread of v1 / v2, costs no pass).
+__global__ void __launch_bounds__(256)
+scale_from_blockmax_kernel(const float* __restrict__ blockmax, int nblk, const float* __restrict__ v1, int n1,
+                           const float* __restrict__ v2, int n2, float mult, float* __restrict__ out4) {
+    __shared__ float fin[3][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float a = 0.f, m1 = v1 ? 0.f : 1.f, m2 = v2 ? 0.f : 1.f;
+    for (int i = threadIdx.x; i < nblk; i += blockDim.x) a = fmaxf(a, __ldg(blockmax + i));
+    if (v1) for (int i = threadIdx.x; i < n1; i += blockDim.x) m1 = fmaxf(m1, fabsf(__ldg(v1 + i)));
+    if (v2) for (int i = threadIdx.x; i < n2; i += blockDim.x) m2 = fmaxf(m2, fabsf(__ldg(v2 + i)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+        m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    }
+    if (lane == 0) { fin[0][warp] = a; fin[1][warp] = m1; fin[2][warp] = m2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = m1 = m2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { a = fmaxf(a, fin[0][w]); m1 = fmaxf(m1, fin[1][w]); m2 = fmaxf(m2, fin[2][w]); }
+        pow2_scale_pair(a * m1 * mult, out4 + 0, out4 + 1);
+        pow2_scale_pair(a * m2 * mult, out4 + 2, out4 + 3);
     }
 }
 
@@ -475,39 +523,44 @@ grad_prep_kernel(const float* __restrict__ x, int R, int C, long long ldx, long 
 // workspace (uint32 counter at ws[0], self-resetting; partials from ws[2]).
 constexpr int kAbsmaxMaxBlocks = 148 * 8;
 
-__device__ __forceinline__ void pow2_scale_pair(float bound, float* sc, float* inv) {
-    const uint32_t e = (__float_as_uint(bound) >> 23) & 0xffu;
-    if (e < 16u || e > 250u) { *sc = 1.f; *inv = 1.f; return; }   // zero / denormal / non-finite bound: no scaling
-    *sc = __uint_as_float((268u - e) << 23);                     // 2^(141 - e): bound * sc in [2^14, 2^15)
-    *inv = __uint_as_float((e - 14u) << 23);                      // 2^(e - 141)
-}
-
 __global__ void __launch_bounds__(256)
-absmax_scale_kernel(const float* __restrict__ x, int nb, int R, int C, long long ldx, long long bstride,
+absmax_scale_kernel(const float* __restrict__ x, long long nquads, int C, int ldq, int R,
                     const float* __restrict__ cs, const float* __restrict__ rs, int rs_period,
                     const float* __restrict__ v1, int n1, const float* __restrict__ v2, int n2, float mult,
                     float* __restrict__ out4, unsigned int* __restrict__ ws) {
+    // x is walked as a flat array of float4 quads, ldq quads per row (rows are densely packed: batch stride = R * ld)
     __shared__ float red[2][8];
     __shared__ bool last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long rows = (long long)nb * R;
     float mc = 0.f, mr = 0.f;
-    for (long long row = (long long)blockIdx.x * 8 + warp; row < rows; row += (long long)gridDim.x * 8) {
-        const int b = (int)(row / R), r = (int)(row - (long long)b * R);
-        const float* xr = x + (long long)b * bstride + (long long)r * ldx;
-        float rowmax = 0.f;
-        for (int c = lane * 4; c < C; c += 128) {
-            const float4 f = __ldg(reinterpret_cast<const float4*>(xr + c));   // the row pitch covers the last quad
-            const float a0 = fabsf(f.x), a1 = c + 1 < C ? fabsf(f.y) : 0.f, a2 = c + 2 < C ? fabsf(f.z) : 0.f,
-                        a3 = c + 3 < C ? fabsf(f.w) : 0.f;
-            rowmax = fmaxf(fmaxf(rowmax, fmaxf(a0, a1)), fmaxf(a2, a3));
-            if (cs) {                                                          // host guarantees C % 4 == 0 with cs
+    constexpr int ILP = 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < nquads; q0 += stride * ILP) {
+        float4 f[ILP];
+        bool ok[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            const long long q = q0 + u * stride;
+            ok[u] = q < nquads;
+            f[u] = ok[u] ? __ldg(reinterpret_cast<const float4*>(x) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            if (!ok[u]) continue;
+            const long long q = q0 + u * stride;
+            const long long row = q / ldq;
+            const int c = (int)(q - row * ldq) * 4;
+            const float a0 = c < C ? fabsf(f[u].x) : 0.f, a1 = c + 1 < C ? fabsf(f[u].y) : 0.f,
+                        a2 = c + 2 < C ? fabsf(f[u].z) : 0.f, a3 = c + 3 < C ? fabsf(f[u].w) : 0.f;
+            const float m4 = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+            if (cs && c < C) {                                                 // host guarantees C % 4 == 0 with cs
                 const float4 s4 = __ldg(reinterpret_cast<const float4*>(cs + c));
                 mc = fmaxf(fmaxf(mc, fmaxf(a0 * fabsf(s4.x), a1 * fabsf(s4.y))), fmaxf(a2 * fabsf(s4.z), a3 * fabsf(s4.w)));
+            } else {
+                mc = fmaxf(mc, m4);
             }
+            mr = fmaxf(mr, m4 * (rs ? fabsf(__ldg(rs + (int)((row % R) % rs_period))) : 1.f));
         }
-        if (!cs) mc = fmaxf(mc, rowmax);
-        mr = fmaxf(mr, rowmax * (rs ? fabsf(__ldg(rs + (r % rs_period))) : 1.f));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -710,7 +763,18 @@ extern "C" int ofq_lsq_quant(const float* x, long long rows, int cols, long long
 }
 
 extern "C" long long ofq_lsq_bwd_workspace(long long rows, int cols, int nseg) {
-    return rows * nseg + lsq_bwd_nblk(rows) * 3 * cols;
+    return rows * nseg + lsq_bwd_nblk(rows) * 3 * cols + lsq_bwd_nblk(rows);
+}
+
+extern "C" int ofq_lsq_bwd_scale(const float* workspace, long long rows, int cols, int nseg, const float* v1, int n1,
+                                 const float* v2, int n2, float mult, float* out4, void* stream) {
+    OFQ_REQUIRE(workspace && out4 && rows > 0 && cols > 0 && nseg > 0, "ofq_lsq_bwd_scale: bad argument");
+    OFQ_CHECK_ARCH();
+    const long long nblk = lsq_bwd_nblk(rows);
+    scale_from_blockmax_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(workspace + rows * nseg + nblk * 3 * cols, (int)nblk,
+                                                                   v1, n1, v2, n2, mult, out4);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int ofq_lsq_bwd(const float* dy, long long lddy, const float* x, long long ldx, long long rows,
@@ -726,12 +790,13 @@ extern "C" int ofq_lsq_bwd(const float* dy, long long lddy, const float* x, long
     OFQ_CHECK_ARCH();
     float* rowpart = workspace;
     float* colpart = workspace + rows * nseg;
+    float* blockmax = colpart + lsq_bwd_nblk(rows) * 3 * cols;
     if (scale_mode == OFQ_SCALE_PER_ROW)
         lsq_bwd_kernel<OFQ_SCALE_PER_ROW><<<(unsigned)lsq_bwd_nblk(rows), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-            dy, lddy, x, ldx, rows, cols, b4, s_eff, period, nseg, seg_len, (float)qlo, (float)qhi, dx, lddx, rowpart, colpart);
+            dy, lddy, x, ldx, rows, cols, b4, s_eff, period, nseg, seg_len, (float)qlo, (float)qhi, dx, lddx, rowpart, colpart, blockmax);
     else
         lsq_bwd_kernel<OFQ_SCALE_PER_COL><<<(unsigned)lsq_bwd_nblk(rows), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-            dy, lddy, x, ldx, rows, cols, b4, s_eff, period, nseg, seg_len, (float)qlo, (float)qhi, dx, lddx, rowpart, colpart);
+            dy, lddy, x, ldx, rows, cols, b4, s_eff, period, nseg, seg_len, (float)qlo, (float)qhi, dx, lddx, rowpart, colpart, blockmax);
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }
@@ -762,12 +827,13 @@ extern "C" int ofq_absmax_scale(const float* x, int nb, int R, int C, long long 
     OFQ_REQUIRE(ldx % 4 == 0 && ldx >= (C + 3) / 4 * 4 && bstride % 4 == 0 && (uintptr_t)x % 16 == 0,
                 "ofq_absmax_scale: ldx, bstride must be multiples of 4 (ldx covering the last quad) and x 16-byte aligned");
     OFQ_REQUIRE(!cs || (C % 4 == 0 && (uintptr_t)cs % 16 == 0), "ofq_absmax_scale: cs needs C % 4 == 0 and 16-byte alignment");
+    OFQ_REQUIRE(nb == 1 || bstride == (long long)R * ldx, "ofq_absmax_scale: batches must be densely packed (bstride = R * ldx)");
     OFQ_CHECK_ARCH();
     if (rs_period <= 0) rs_period = 0x7fffffff;
-    const long long rows = (long long)nb * R;
-    long long grid = (rows + 7) / 8;
+    const long long nquads = (long long)nb * R * (ldx / 4);
+    long long grid = (nquads + 256 * 4 - 1) / (256 * 4);
     if (grid > kAbsmaxMaxBlocks) grid = kAbsmaxMaxBlocks;
-    absmax_scale_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, nb, R, C, ldx, bstride, cs, rs, rs_period,
+    absmax_scale_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, nquads, C, (int)(ldx / 4), R, cs, rs, rs_period,
                                                                          v1, n1, v2, n2, mult, out4, (unsigned int*)workspace);
     OFQ_CUDA(cudaGetLastError());
     return 0;

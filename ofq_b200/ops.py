@@ -64,15 +64,17 @@ def vec(t: Optional[torch.Tensor], period: int = 0, bs1: int = 0, bs2: int = 0):
 
 def gemm(kind: int, a: torch.Tensor, a_strides, b: torch.Tensor, b_strides, out: torch.Tensor, out_strides,
          M: int, N: int, K: int, *, k2: int = 1, nb1: int = 1, nb2: int = 1, splits: int = 1, accumulate: bool = False,
-         rs=None, cs=None, rt=None, ct=None, a_k2mod: int = 0, b_k2mod: int = 0, a_dual_delta: int = 0) -> None:
+         rs=None, cs=None, rt=None, ct=None, a_k2mod: int = 0, b_k2mod: int = 0, a_dual_delta: int = 0,
+         a_mn: bool = False, b_mn: bool = False) -> None:
     """Raw ofq_gemm call. a_strides/b_strides = (row, k2, batch1, batch2) in elements; out_strides = (ld, b1, b2).
+    a_mn / b_mn: the operand is stored [k][row] (MN-major) and its first stride is the distance between consecutive k.
     rs/cs/rt/ct are ctypes Vec references from `vec()` or None."""
     _cuda(a, b, out)
-    A = Operand(a.data_ptr(), a_strides[0], a_strides[1], a_k2mod, a_dual_delta, a_strides[2], a_strides[3])
-    B = Operand(b.data_ptr(), b_strides[0], b_strides[1], b_k2mod, 0, b_strides[2], b_strides[3])
+    A = Operand(a.data_ptr(), a_strides[0], a_strides[1], a_k2mod, a_dual_delta, a_strides[2], a_strides[3], int(a_mn))
+    B = Operand(b.data_ptr(), b_strides[0], b_strides[1], b_k2mod, 0, b_strides[2], b_strides[3], int(b_mn))
     O = GemmOut(out.data_ptr(), *out_strides, 1 if accumulate else 0)
     eb = 1 if kind == GEMM_I8 else 2
-    tag = f"M{M} N{N} K{K} k2={k2}{'+dual' if a_dual_delta else ''} nb={nb1}x{nb2} sp={splits}"
+    tag = f"M{M} N{N} K{K} k2={k2}{'+dual' if a_dual_delta else ''} nb={nb1}x{nb2} sp={splits}{' aT' if a_mn else ''}{' bT' if b_mn else ''}"
 
     def _n(strides, mod):
         k2n = ((min(mod, k2) if mod else k2) + (a_dual_delta if strides is a_strides and a_dual_delta else 0)) if strides[1] else 1
@@ -129,8 +131,10 @@ def lsq_quant(x2d: torch.Tensor, b4: torch.Tensor, s_eff: torch.Tensor, mode: in
 
 
 def lsq_bwd(dy2d: torch.Tensor, x2d: torch.Tensor, b4: torch.Tensor, s_eff: torch.Tensor, mode: int, period: int,
-            nseg: int, qlo: int, qhi: int, g: float, want_ds: bool = True):
-    """Returns (dx [rows, cols], d_s, d_b4 [cols], d_aft [cols])."""
+            nseg: int, qlo: int, qhi: int, g: float, want_ds: bool = True, want_aft: bool = True, next_scale=None):
+    """Returns (dx [rows, cols], d_s, d_b4 [cols], d_aft [cols] | None).  next_scale = (v1, v2, mult): additionally
+    returns the fp16 range scales (absmax_scale layout) of dx*v1[c] / dx*v2[r] for the GEMM operand made from dx,
+    derived from max|dx| at no extra pass over dx."""
     _cuda(dy2d, x2d)
     assert dy2d.dim() == 2 and dy2d.stride(1) == 1 and x2d.stride(1) == 1
     rows, cols = dy2d.shape
@@ -143,10 +147,16 @@ def lsq_bwd(dy2d: torch.Tensor, x2d: torch.Tensor, b4: torch.Tensor, s_eff: torc
     ns = cols if mode == PER_COL else min(period, rows) * nseg
     d_s = torch.empty(ns, dtype=torch.float32, device=dy2d.device) if want_ds else None
     d_b4 = torch.empty(cols, dtype=torch.float32, device=dy2d.device)
-    d_aft = torch.empty(cols, dtype=torch.float32, device=dy2d.device)
+    d_aft = torch.empty(cols, dtype=torch.float32, device=dy2d.device) if want_aft else None
     _call("lsq_bwd_finalize", 1, 4.0 * ws.numel(), 0, lib.ofq_lsq_bwd_finalize, ws.data_ptr(), rows, cols, mode, period,
-          nseg, float(g), _ptr(d_s), d_b4.data_ptr(), d_aft.data_ptr(), _st())
-    return dx, d_s, d_b4, d_aft
+          nseg, float(g), _ptr(d_s), d_b4.data_ptr(), _ptr(d_aft), _st())
+    if next_scale is None:
+        return dx, d_s, d_b4, d_aft
+    v1, v2, mult = next_scale
+    sc = torch.empty(4, dtype=torch.float32, device=dy2d.device)
+    _call("lsq_bwd_scale", 1, 0.0, 0, lib.ofq_lsq_bwd_scale, ws.data_ptr(), rows, cols, nseg, _ptr(v1),
+          0 if v1 is None else v1.numel(), _ptr(v2), 0 if v2 is None else v2.numel(), float(mult), sc.data_ptr(), _st())
+    return dx, d_s, d_b4, d_aft, sc
 
 
 def round_up(x: int, m: int) -> int:

@@ -64,12 +64,13 @@ def _splits_for(tiles: int, kblocks: int) -> int:
     return min(s, 64)
 
 
-def _linear_backward(dY2d, qx, wc, colscale, se_x, period, x_aft, dxhat, accumulate_dx: bool, qxT_all=None):
+def _linear_backward(dY2d, qx, wc, colscale, se_x, period, x_aft, dxhat, accumulate_dx: bool, qxT_all=None, sc=None):
     """Backward of out = x_hat @ W_hat^T (+bias):  dX_hat (+)= dY W_hat,  dW = dY^T x_hat,  dbias = colsum(dY).
     x_hat = qx * se_x[row % period] + x_aft,  W_hat = wc * colscale[row].  Returns (dW, dbias, qxT_all)."""
     M, Nout = dY2d.shape
     K = qx.shape[1]
-    sc = ops.absmax_scale(dY2d, 1, M, Nout, dY2d.stride(0), 0, cs=colscale, rs=se_x, rs_period=period) if F16 else None
+    if F16 and sc is None:      # fp16 range scales of dY*colscale / dY*se_x (the caller passes them when it already knows)
+        sc = ops.absmax_scale(dY2d, 1, M, Nout, dY2d.stride(0), 0, cs=colscale, rs=se_x, rs_period=period)
     prep = ops.grad_prep(dY2d, 1, M, Nout, dY2d.stride(0), 0, cs=colscale, rs=se_x, rs_period=period,
                          want_rm=True, want_t=True, want_colsum=True, planes=PLANES, fmt=FMT, scale4=sc)
     m_pad = prep["r_pad"]
@@ -269,9 +270,10 @@ class QKRAttnCoreFn(torch.autograd.Function):
         dO = dO.contiguous()
         dPq, dvhat = _pv_backward(dO, qp, ldq, qv, se_p, se_v, v_aft, B, N, H, C, ldS)
         # --- V quantizer and V linear
-        dv_out, ds_v, dvb4, dvaft = ops.lsq_bwd(dvhat.view(M, C), v_out, v_b4, se_v, PER_COL, 1, 1, lo, hi, g_v)
+        dv_out, ds_v, dvb4, dvaft, *sc_v = ops.lsq_bwd(dvhat.view(M, C), v_out, v_b4, se_v, PER_COL, 1, 1, lo, hi, g_v,
+                                                       next_scale=(cs_v, se_x, 1.0) if F16 else None)
         dxhat = torch.empty((M, C), dtype=torch.float32, device=dev)
-        dWv, dbv, qxT_all = _linear_backward(dv_out, qx, wvc, cs_v, se_x, N, x_aft, dxhat, False)
+        dWv, dbv, qxT_all = _linear_backward(dv_out, qx, wvc, cs_v, se_x, N, x_aft, dxhat, False, sc=sc_v[0] if sc_v else None)
         # --- softmax + probability quantizer
         # fp16 range bound of dS * {se_k, se_x}: |dS| = |alpha P (dP - sum P dP)| <= 2 alpha max|dPq|
         sc = (ops.absmax_scale(dPq, B * H, N, N, ldS, N * ldS, v1=se_k_hn, v2=se_x, mult=2.0 * scale) if F16 else None)
@@ -297,9 +299,12 @@ class QKRAttnCoreFn(torch.autograd.Function):
                  rt=vec(colsum_dS, 0, N, H * N), ct=vec(x_aft))
         del dSa, dSbT
         # --- qkx quantizer and the qkx "linear" layer (weight = StatsQ(W_q^T W_k), no bias)
-        dqkx, ds_k, dkb4, dkaft = ops.lsq_bwd(dkhat, qkx, k_b4, se_k, PER_ROW, N, H, lo, hi, g_k)
+        # d(move_qkx_aft) is analytically zero: the shift adds a term to the logits that is constant along the softmax axis
+        dqkx, ds_k, dkb4, _, *sc_k = ops.lsq_bwd(dkhat, qkx, k_b4, se_k, PER_ROW, N, H, lo, hi, g_k, want_aft=False,
+                                                 next_scale=(cs_qk, se_x, 1.0) if F16 else None)
+        dkaft = torch.zeros_like(k_aft)
         del dkhat
-        dWqk, _, _ = _linear_backward(dqkx, qx, wqkc, cs_qk, se_x, N, x_aft, dxhat, True, qxT_all)
+        dWqk, _, _ = _linear_backward(dqkx, qx, wqkc, cs_qk, se_x, N, x_aft, dxhat, True, qxT_all, sc=sc_k[0] if sc_k else None)
         dwq, dwk = ops.wqk_compose_bwd(dWqk, wq, wk, H)
         # --- shared input quantizer
         dx, ds_x, dxb4, dxaft = ops.lsq_bwd(dxhat, xc.view(M, C), x_b4, se_x, PER_ROW, N, 1, lo, hi, g_x)
@@ -382,7 +387,9 @@ class QAttnCoreFn(torch.autograd.Function):
                  (C, hd, N * C), N, hd, N, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B, rs=_inv(sc, 1),
                  rt=vec(colsum_dS, 0, N, H * N), ct=vec(q_aft, 0, hd))
         dq, ds_q, db4_q, daft_q = ops.lsq_bwd(dqhat, q2d[:, 0:C], b4[0:C], se_q, PER_ROW, N, 1, lo, hi, g_qk)
-        dk, ds_k, db4_k, daft_k = ops.lsq_bwd(dkhat, q2d[:, C:2 * C], b4[C:2 * C], se_k, PER_ROW, N, 1, lo, hi, g_qk)
+        # d(move_k_aft) is analytically zero (its logit term q_hat . k_aft is constant along the softmax axis)
+        dk, ds_k, db4_k, _ = ops.lsq_bwd(dkhat, q2d[:, C:2 * C], b4[C:2 * C], se_k, PER_ROW, N, 1, lo, hi, g_qk, want_aft=False)
+        daft_k = torch.zeros_like(k_aft)
         dv, ds_v, db4_v, daft_v = ops.lsq_bwd(dvhat.view(M, C), q2d[:, 2 * C:], b4[2 * C:], se_v, PER_COL, 1, 1, lo, hi, g_v)
         dqkv = torch.cat((dq, dk, dv), dim=1).view(B, N, 3 * C)
         db4 = torch.cat((db4_q, db4_k, db4_v))

@@ -299,6 +299,37 @@ def test_grad_prep_and_code_conversions(ops):
     assert torch.equal(ti[..., :R], codes.transpose(1, 2)) and bool((ti[..., R:] == 0).all())
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("M,N,K,splits,fmt", [(1536, 384, 25344, 8, "f16"), (200, 72, 198, 1, "bf16"), (384, 2304, 1000, 2, "f16")])
+def test_gemm_mn_major_operands(ops, a_mn, b_mn, M, N, K, splits, fmt):
+    """MN-major (rows contiguous, K strided) 16-bit operands: a row-major [tokens][features] tensor is consumed as the
+    transposed operand of dW = dY^T X without a transposed copy."""
+    torch.manual_seed(14)
+    dt = torch.float16 if fmt == "f16" else torch.bfloat16
+    A = torch.randn(M, K, device="cuda").to(dt)
+    Bm = torch.randint(-3, 4, (N, K), device="cuda").to(dt)
+    a_arg, a_str = (A.t().contiguous(), (M, 0, 0, 0)) if a_mn else (A, (K, 0, 0, 0))
+    b_arg, b_str = (Bm.t().contiguous(), (N, 0, 0, 0)) if b_mn else (Bm, (K, 0, 0, 0))
+    out = torch.zeros((M, N), device="cuda")
+    ops.gemm(ops.GEMM_F16 if fmt == "f16" else ops.GEMM_BF16, a_arg, a_str, b_arg, b_str, out, (N, 0, 0), M, N, K,
+             splits=splits, accumulate=splits > 1, a_mn=a_mn, b_mn=b_mn)
+    assert rel_err(out, A.double() @ Bm.double().T) < 1e-5
+
+
+def test_gemm_mn_major_batched(ops):
+    """Batched MN-major operands with batch strides (attention backward layout: dK_hat[d,c] = sum_n dS[n,d] x_hat[n,c])."""
+    torch.manual_seed(15)
+    Bt, H, N, C = 3, 2, 198, 128
+    dS = torch.randn(Bt, H, N, 200, device="cuda").half()          # [b][h][n][d], pitch 200
+    dS[..., N:] = 0
+    xh = torch.randn(Bt, N, C, device="cuda").half()               # [b][n][c]
+    out = torch.empty(Bt, N, H, C, device="cuda")                  # [b][d][h][c]
+    ops.gemm(ops.GEMM_F16, dS, (200, 0, N * 200, H * N * 200), xh, (C, 0, 0, N * C), out, (H * C, C, N * H * C), N, C, N,
+             nb1=H, nb2=Bt, a_mn=True, b_mn=True)
+    ref = torch.einsum("bhnd,bnc->bdhc", dS[..., :N].double(), xh.double())
+    assert rel_err(out, ref) < 1e-5
+
+
 def test_absmax_scale_and_fp16_prep(ops):
     """Range-scaled fp16 operands (backward mode "f16"): the power-of-two scale places the operand's absmax in
     [2^14, 2^15), the fp16 planes are the correctly rounded scaled values and the GEMM un-scales in its epilogue."""
