@@ -67,7 +67,7 @@ typedef struct {
 
 typedef struct {
     const float* ptr;     /* NULL = all ones */
-    int period;           /* value for index i is ptr[i % period]; <= 0 means no wrap */
+    int period;           /* value for index i is ptr[i % period]; <= 0 means no wrap (honoured by rs, rt and cs) */
     long long bstride1;   /* offset per batch-axis-1 index */
     long long bstride2;   /* offset per batch-axis-2 index */
 } ofq_vec_t;
@@ -93,16 +93,17 @@ OFQ_API int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B, c
  *   colscale[r] = sf[r] / (2n)
  *   colterm[r]  = colscale[r] * sum_c aft[c] * codes[r][c] + bias[r]   (optional: the move_aft shift of the
  *                 layer input folded through the weights, qlinear.py:68-71; aft/bias may be NULL)
+ *   inv_colscale= optional 1 / colscale[r] (epilogue un-scale vector of the backward dW GEMM)
  *   kminmax     = optional int32[2] {min k, max k} over the whole tensor, atomically updated (pre-set to
  *                 {INT_MAX, INT_MIN}); cga.py:459-463 needs it.
  */
 OFQ_API int ofq_statsq_codes(const float* w, int rows, int cols, long long ldw, int bits, int8_t* codes,
                              long long ldq, float* colscale, float* sf, const float* aft, const float* bias,
-                             float* colterm, int* kminmax, void* stream);
+                             float* colterm, int* kminmax, float* inv_colscale, void* stream);
 
 /* LSQ effective step size (lsq.py:593): out[i] = (a - a*g) + a*g with a = alpha[i] > 1e-5 ? alpha[i] : 1e-5,
- * evaluated in fp32 exactly as grad_scale(clip(alpha)) does. */
-OFQ_API int ofq_lsq_effective_scale(const float* alpha, int n, float g, float* out, void* stream);
+ * evaluated in fp32 exactly as grad_scale(clip(alpha)) does. out_recip (optional) receives 1 / out[i]. */
+OFQ_API int ofq_lsq_effective_scale(const float* alpha, int n, float g, float* out, float* out_recip, void* stream);
 
 /* K2  LearnableBias + LsqQuantizer / LsqQuantizer4v forward as integer codes
  * (qbias.py:10-13, lsq.py:571-602, 757-790):   codes = rint( clamp( (x + b4[col]) / s_eff, qlo, qhi ) ).
@@ -124,17 +125,20 @@ OFQ_API int ofq_lsq_quant(const float* x, long long rows, int cols, long long ld
  *   dx = dy * inside;  d_aft[c] = sum dy;  d_b4[c] = sum dx;  d_s[idx] = g * sum dy * (q - inside * v)
  * Partial sums go to `workspace` (float[ofq_lsq_bwd_workspace(...)], no atomics, deterministic) and are
  * reduced by ofq_lsq_bwd_finalize. dx may alias dy.
+ * zero_sum != 0 declares that sum_rows dy is analytically zero for every column (the K operand of attention: a shift of
+ * K only adds a term that is constant along the softmax axis); d_b4 is then evaluated as -(sum over clipped elements),
+ * which removes the cancellation noise of the un-clipped ones, and d_aft (exactly zero) need not be requested.
  */
 OFQ_API long long ofq_lsq_bwd_workspace(long long rows, int cols, int nseg);
 OFQ_API int ofq_lsq_bwd(const float* dy, long long lddy, const float* x, long long ldx, long long rows, int cols,
                         const float* b4, const float* s_eff, int scale_mode, int period, int nseg,
                         int qlo, int qhi, float* dx, long long lddx, float* workspace, void* stream);
 OFQ_API int ofq_lsq_bwd_finalize(const float* workspace, long long rows, int cols, int scale_mode, int period,
-                                 int nseg, float g, float* d_s, float* d_b4, float* d_aft, void* stream);
+                                 int nseg, float g, float* d_s, float* d_b4, float* d_aft, int zero_sum, void* stream);
 /* fp16 range scales (layout of ofq_absmax_scale's out4) for the NEXT consumer of dx, from the per-block max |dx| that
  * ofq_lsq_bwd left in its workspace: bound_1 = max|dx| * max|v1| * mult, bound_2 = max|dx| * max|v2| * mult. */
 OFQ_API int ofq_lsq_bwd_scale(const float* workspace, long long rows, int cols, int nseg, const float* v1, int n1,
-                              const float* v2, int n2, float mult, float* out4, void* stream);
+                              const float* v2, int n2, float mult, int product, float* out4, void* stream);
 
 /* Gradient operand preparation for the bf16 backward GEMMs: one pass over a fp32 gradient x[nb][R][C]:
  *   out_rm[p][b][r][c] = bf16 plane p of ( x * cs[c] )              (row-major, ld = ld_rm; NULL to skip)
@@ -146,21 +150,24 @@ OFQ_API int ofq_lsq_bwd_scale(const float* workspace, long long rows, int cols, 
  *   out_fmt = OFQ_FMT_F16 (planes must be 1): single fp16 plane (11 significant bits, ~2e-4 gradient error) of
  *     ( x * cs[c] * scale4[0] ) and ( x * rs[r] * scale4[2] ); scale4 comes from ofq_absmax_scale and keeps the
  *     operand inside the fp16 range; the consuming GEMM multiplies its result by scale4[1] / scale4[3].
+ *   rm_rowscale != 0: out_rm additionally carries rs[r]: ONE row-major copy ( x * cs[c] * rs[r] * scale4[0] ) then serves
+ *     the dX GEMM (K-major, rs undone per output row) and the dW GEMM (MN-major, cs undone per output row).
  */
 OFQ_API int ofq_grad_prep(const float* x, int nb, int R, int C, long long ldx, long long bstride_x,
                           const float* cs, const float* rs, int rs_period, int planes, void* out_rm,
                           long long ld_rm, void* out_t, int r_pad, float* colsum, const float* u, int group,
-                          float* rowdot, int out_fmt, const float* scale4, void* stream);
+                          float* rowdot, int out_fmt, const float* scale4, int rm_rowscale, void* stream);
 
 /* Range scales for fp16 gradient operands, one read-only pass over x[nb][R][C] (fp32):
  *   bound_c = max |x * cs[c]| * max_i |v1[i]| * mult,   bound_r = max |x * rs[r % rs_period]| * max_i |v2[i]| * mult
  *   out4 = { sc_c, 1/sc_c, sc_r, 1/sc_r } with sc = 2^k such that bound * sc lies in [2^14, 2^15)
- * (cs / rs / v1 / v2 may be NULL = 1). workspace: uint32[ofq_absmax_scale_workspace()], zero-initialised ONCE by the
+ * (cs / rs / v1 / v2 may be NULL = 1). product != 0: a single bound max |x * cs[c] * rs[r]| * max|v1| * max|v2| * mult
+ * for an operand that carries both scale vectors (out4[2..3] repeat out4[0..1]). workspace: uint32[ofq_absmax_scale_workspace()], zero-initialised ONCE by the
  * caller and then reusable by every later call on the same stream (the kernel resets its counter). */
 OFQ_API long long ofq_absmax_scale_workspace(void);
 OFQ_API int ofq_absmax_scale(const float* x, int nb, int R, int C, long long ldx, long long bstride,
                              const float* cs, const float* rs, int rs_period, const float* v1, int n1,
-                             const float* v2, int n2, float mult, float* out4, void* workspace, void* stream);
+                             const float* v2, int n2, float mult, int product, float* out4, void* workspace, void* stream);
 
 /* int8 codes [nb][R][C] (row stride ld, batch stride bstride) -> bf16, optionally transposed per batch:
  *   transpose = 0: out[b][r][c] (row stride ld_out);   transpose = 1: out[b][c][r] (row pitch ld_out >= R) */
@@ -197,6 +204,8 @@ OFQ_API int ofq_softmax_quant(const float* S, int nz, int N, long long ld, int H
  *   out_bt[b][p][h][d][n] = bf16 plane p of ( dS * rb[n] )   (transposed, pitch ldo);  planes as in ofq_grad_prep
  *   colsum[z][d]   += sum_n dS              (optional, atomic, pre-zeroed)
  *   out_fmt = OFQ_FMT_F16 (planes = 1): fp16 planes of ( dS * ca[d] * scale4[0] ) and ( dS * rb[n] * scale4[2] )
+ *   a_rowscale != 0: out_a = dS * ca[d] * rb[n] (* scale4[0]) and out_bt may be NULL: one copy that the K-major
+ *                     dQ-side GEMM and the MN-major dK-side GEMM both read (the other vector is undone per output row)
  *   dS32            = optional fp32 P * (dP - sum_d P*dP) WITHOUT alpha, layout of P: the gradient w.r.t. the
  *                     additive pre-softmax bias (Swin relative-position bias)
  */
@@ -204,7 +213,7 @@ OFQ_API int ofq_softmax_quant_bwd(const float* dPq, const float* P, int nz, int 
                                   const float* s_eff, int qhi, float alpha, float g_s, const float* ca,
                                   int ca_per_head, const float* rb, int planes, void* out_a, void* out_bt,
                                   long long ldo, float* colsum, float* d_s, float* dS32, int out_fmt,
-                                  const float* scale4, void* stream);
+                                  const float* scale4, int a_rowscale, void* stream);
 
 /* K4  W_qk[h] = W_q[h]^T W_k[h] in fp32 (attention.py:190-194) and its backward. wq, wk: [H*hd][C]. */
 OFQ_API int ofq_wqk_compose(const float* wq, const float* wk, int H, int hd, int C, float* wqk, void* stream);

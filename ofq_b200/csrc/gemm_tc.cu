@@ -25,7 +25,7 @@ constexpr int NUM_THREADS = 64 + EPI_WARPS * 32; // warp0 TMA, warp1 MMA, warps 
 
 struct VecRef {
     const float* p;   // nullptr -> 1.0
-    int period;       // row vectors only: index = i % period
+    int period;       // rs / rt / cs: index = i % period (ct is never wrapped)
     long long bs1, bs2;
 };
 
@@ -222,7 +222,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int j = threadIdx.x - 64; j < BN; j += EPI_WARPS * 32) {
                     const int n = c.n0 + j;
                     const bool ok = n < p.N;
-                    cs_s[j] = ok ? (p.cs.p ? __ldg(p.cs.p + cs_off + n) : 1.0f) : 0.f;
+                    cs_s[j] = ok ? (p.cs.p ? __ldg(p.cs.p + cs_off + (n % p.cs.period)) : 1.0f) : 0.f;
                     ct_s[j] = (ok && rank1) ? (p.ct.p ? __ldg(p.ct.p + ct_off + n) : 1.0f) : 0.f;
                 }
                 named_bar_sync(1, EPI_WARPS * 32);

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 statsq_codes_kernel(const float* __restrict__ w, int rows, int cols, long long ldw, float n_levels,
                     int8_t* __restrict__ codes, long long ldq, float* __restrict__ colscale,
                     float* __restrict__ sf_out, const float* __restrict__ aft, const float* __restrict__ bias,
-                    float* __restrict__ colterm, int* __restrict__ kminmax) {
+                    float* __restrict__ colterm, int* __restrict__ kminmax, float* __restrict__ inv_colscale) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * kWarpsPerBlock + warp;
     if (row >= rows) return;
@@ -80,19 +80,22 @@ statsq_codes_kernel(const float* __restrict__ w, int rows, int cols, long long l
     }
     if (lane == 0) {
         colscale[row] = cs;
+        if (inv_colscale) inv_colscale[row] = 1.0f / cs;
         if (sf_out) sf_out[row] = sf;
     }
 }
 
 // ------------------------------------------------------------------------------------------- LSQ scale
 __global__ void lsq_effective_scale_kernel(const float* __restrict__ alpha, int n, float g,
-                                           float* __restrict__ out) {
+                                           float* __restrict__ out, float* __restrict__ out_recip) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float a = alpha[i];
     const float ac = a > 1e-5f ? a : 1e-5f;          // clip(): where(x > eps, x, eps)
     const float ag = __fmul_rn(ac, g);               // grad_scale(): (y - y*g) + y*g
-    out[i] = __fadd_rn(__fsub_rn(ac, ag), ag);
+    const float se = __fadd_rn(__fsub_rn(ac, ag), ag);
+    out[i] = se;
+    if (out_recip) out_recip[i] = 1.0f / se;     // epilogue un-scale vector of the backward GEMMs
 }
 
 // ------------------------------------------------------------------------------------------- K2 LSQ codes
@@ -314,7 +317,7 @@ lsq_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __rest
 // bound_2 = max(blockmax) * max|v2| * mult (looser than ofq_absmax_scale by the spread of v1 / v2, costs no pass).
 __global__ void __launch_bounds__(256)
 scale_from_blockmax_kernel(const float* __restrict__ blockmax, int nblk, const float* __restrict__ v1, int n1,
-                           const float* __restrict__ v2, int n2, float mult, float* __restrict__ out4) {
+                           const float* __restrict__ v2, int n2, float mult, int product, float* __restrict__ out4) {
     __shared__ float fin[3][8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float a = 0.f, m1 = v1 ? 0.f : 1.f, m2 = v2 ? 0.f : 1.f;
@@ -333,22 +336,28 @@ scale_from_blockmax_kernel(const float* __restrict__ blockmax, int nblk, const f
         a = m1 = m2 = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) { a = fmaxf(a, fin[0][w]); m1 = fmaxf(m1, fin[1][w]); m2 = fmaxf(m2, fin[2][w]); }
-        pow2_scale_pair(a * m1 * mult, out4 + 0, out4 + 1);
-        pow2_scale_pair(a * m2 * mult, out4 + 2, out4 + 3);
+        pow2_scale_pair(a * m1 * (product ? m2 : 1.f) * mult, out4 + 0, out4 + 1);
+        pow2_scale_pair(a * m2 * (product ? m1 : 1.f) * mult, out4 + 2, out4 + 3);
     }
 }
 
 // Deterministic tree reductions of the partials: block = 32 outputs x 8 slices of the reduction axis.
 __global__ void __launch_bounds__(256)
 lsq_bwd_finalize_cols_kernel(const float* __restrict__ colpart, int cols, long long nblk, int scale_mode, float g,
-                             float* __restrict__ d_s, float* __restrict__ d_b4, float* __restrict__ d_aft) {
+                             float* __restrict__ d_s, float* __restrict__ d_b4, float* __restrict__ d_aft, int zero_sum) {
     __shared__ float red[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int col = blockIdx.x * 32 + tx;
     const int vecid = blockIdx.y;                     // 0: aft, 1: b4, 2: per-column scale
     float acc = 0.f;
-    if (col < cols)
-        for (long long b = ty; b < nblk; b += 8) acc += colpart[(b * 3 + vecid) * cols + col];
+    if (col < cols) {
+        // zero_sum: sum_rows dy is analytically zero, so d_b4 = sum_inside dy = -sum_outside dy; subtracting the two
+        // partial sums block by block cancels the (reduced-precision) noise carried by the un-clipped elements
+        if (zero_sum && vecid == 1)
+            for (long long b = ty; b < nblk; b += 8) acc += colpart[(b * 3 + 1) * cols + col] - colpart[(b * 3 + 0) * cols + col];
+        else
+            for (long long b = ty; b < nblk; b += 8) acc += colpart[(b * 3 + vecid) * cols + col];
+    }
     red[ty][tx] = acc;
     __syncthreads();
     if (ty == 0 && col < cols) {
@@ -403,7 +412,7 @@ template <bool F16>
 __global__ void __launch_bounds__(256)
 grad_prep_kernel(const float* __restrict__ x, int R, int C, long long ldx, long long bstride_x,
                  const float* __restrict__ cs, const float* __restrict__ rs, int rs_period, int planes,
-                 const float* __restrict__ scale4,
+                 const float* __restrict__ scale4, int rm_rowscale,
                  long long plane_rm, long long plane_t,
                  uint16_t* __restrict__ out_rm, long long ld_rm, uint16_t* __restrict__ out_t, int r_pad,
                  float* __restrict__ colsum, const float* __restrict__ u, int group,
@@ -426,7 +435,9 @@ grad_prep_kernel(const float* __restrict__ x, int R, int C, long long ldx, long 
             const float4 f = __ldg(reinterpret_cast<const float4*>(xb + (long long)r * ldx + c));
             v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
         }
+        const float rs_raw = (rs && r < R) ? __ldg(rs + (r % rs_period)) : 1.f;
         if (out_rm && r < R && c < C) {
+            const float sc_row = rm_rowscale ? sc_rm * rs_raw : sc_rm;
             float s[4] = {1.f, 1.f, 1.f, 1.f};
             if (cs) {
                 const float4 f = __ldg(reinterpret_cast<const float4*>(cs + c));
@@ -434,7 +445,7 @@ grad_prep_kernel(const float* __restrict__ x, int R, int C, long long ldx, long 
             }
             float sv[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) sv[e] = v[e] * s[e] * sc_rm;
+            for (int e = 0; e < 4; ++e) sv[e] = v[e] * s[e] * sc_row;
             uint2 pk;
             pk.x = pack16x2<F16>(sv[0], sv[1]);
             pk.y = pack16x2<F16>(sv[2], sv[3]);
@@ -462,7 +473,7 @@ grad_prep_kernel(const float* __restrict__ x, int R, int C, long long ldx, long 
             if (((t & 15) % lanes) == 0 && r < R && c < C)
                 rowdot[((long long)b * (C / group) + c / group) * R + r] = d;
         }
-        const float rsv = ((out_t && rs && r < R) ? __ldg(rs + (r % rs_period)) : 1.f) * sc_t;
+        const float rsv = rs_raw * sc_t;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             colacc[e] += v[e];
@@ -524,42 +535,43 @@ grad_prep_kernel(const float* __restrict__ x, int R, int C, long long ldx, long 
 constexpr int kAbsmaxMaxBlocks = 148 * 8;
 
 __global__ void __launch_bounds__(256)
-absmax_scale_kernel(const float* __restrict__ x, long long nquads, int C, int ldq, int R,
+absmax_scale_kernel(const float* __restrict__ x, uint32_t nquads, int C, uint32_t ldq, uint32_t R,
                     const float* __restrict__ cs, const float* __restrict__ rs, int rs_period,
                     const float* __restrict__ v1, int n1, const float* __restrict__ v2, int n2, float mult,
-                    float* __restrict__ out4, unsigned int* __restrict__ ws) {
+                    int product, float* __restrict__ out4, unsigned int* __restrict__ ws) {
     // x is walked as a flat array of float4 quads, ldq quads per row (rows are densely packed: batch stride = R * ld)
     __shared__ float red[2][8];
     __shared__ bool last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float mc = 0.f, mr = 0.f;
     constexpr int ILP = 4;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < nquads; q0 += stride * ILP) {
+    const uint32_t stride = gridDim.x * blockDim.x;             // host guarantees nquads + ILP * stride < 2^32
+    for (uint32_t q0 = blockIdx.x * blockDim.x + threadIdx.x; q0 < nquads; q0 += stride * ILP) {
         float4 f[ILP];
         bool ok[ILP];
 #pragma unroll
         for (int u = 0; u < ILP; ++u) {
-            const long long q = q0 + u * stride;
+            const uint32_t q = q0 + u * stride;
             ok[u] = q < nquads;
             f[u] = ok[u] ? __ldg(reinterpret_cast<const float4*>(x) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < ILP; ++u) {
             if (!ok[u]) continue;
-            const long long q = q0 + u * stride;
-            const long long row = q / ldq;
+            const uint32_t q = q0 + u * stride;
+            const uint32_t row = q / ldq;
             const int c = (int)(q - row * ldq) * 4;
             const float a0 = c < C ? fabsf(f[u].x) : 0.f, a1 = c + 1 < C ? fabsf(f[u].y) : 0.f,
                         a2 = c + 2 < C ? fabsf(f[u].z) : 0.f, a3 = c + 3 < C ? fabsf(f[u].w) : 0.f;
             const float m4 = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+            float mcs = m4;
             if (cs && c < C) {                                                 // host guarantees C % 4 == 0 with cs
                 const float4 s4 = __ldg(reinterpret_cast<const float4*>(cs + c));
-                mc = fmaxf(fmaxf(mc, fmaxf(a0 * fabsf(s4.x), a1 * fabsf(s4.y))), fmaxf(a2 * fabsf(s4.z), a3 * fabsf(s4.w)));
-            } else {
-                mc = fmaxf(mc, m4);
+                mcs = fmaxf(fmaxf(a0 * fabsf(s4.x), a1 * fabsf(s4.y)), fmaxf(a2 * fabsf(s4.z), a3 * fabsf(s4.w)));
             }
-            mr = fmaxf(mr, m4 * (rs ? fabsf(__ldg(rs + (int)((row % R) % rs_period))) : 1.f));
+            const float rsv = rs ? fabsf(__ldg(rs + (row % R) % (uint32_t)rs_period)) : 1.f;
+            mc = fmaxf(mc, product ? mcs * rsv : mcs);
+            mr = fmaxf(mr, m4 * rsv);
         }
     }
 #pragma unroll
@@ -605,8 +617,9 @@ absmax_scale_kernel(const float* __restrict__ x, long long nquads, int C, int ld
         for (int w = 0; w < 8; ++w) {
             a = fmaxf(a, fin[0][w]); b2 = fmaxf(b2, fin[1][w]); m1 = fmaxf(m1, fin[2][w]); m2 = fmaxf(m2, fin[3][w]);
         }
-        pow2_scale_pair(a * m1 * mult, out4 + 0, out4 + 1);
-        pow2_scale_pair(b2 * m2 * mult, out4 + 2, out4 + 3);
+        if (product) b2 = a;                          // one operand scaled by both vectors: out4[2..3] repeats out4[0..1]
+        pow2_scale_pair(a * m1 * (product ? m2 : 1.f) * mult, out4 + 0, out4 + 1);
+        pow2_scale_pair(b2 * m2 * (product ? m1 : 1.f) * mult, out4 + 2, out4 + 3);
         ws[0] = 0u;                                   // ready for the next launch on this stream
     }
 }
@@ -718,22 +731,22 @@ extern "C" int ofq_codes_rowdot(const int8_t* codes, long long rows, int cols, l
 
 extern "C" int ofq_statsq_codes(const float* w, int rows, int cols, long long ldw, int bits, int8_t* codes,
                                 long long ldq, float* colscale, float* sf, const float* aft, const float* bias,
-                                float* colterm, int* kminmax, void* stream) {
+                                float* colterm, int* kminmax, float* inv_colscale, void* stream) {
     OFQ_REQUIRE(w && codes && colscale, "ofq_statsq_codes: null pointer");
     OFQ_REQUIRE(rows > 0 && cols > 0 && bits >= 2 && bits <= 7, "ofq_statsq_codes: bad shape or bits (2..7)");
     OFQ_CHECK_ARCH();
     const float n = (float)(1 << (bits - 1));
     const int grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
     statsq_codes_kernel<<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-        w, rows, cols, ldw, n, codes, ldq, colscale, sf, aft, bias, colterm, kminmax);
+        w, rows, cols, ldw, n, codes, ldq, colscale, sf, aft, bias, colterm, kminmax, inv_colscale);
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }
 
-extern "C" int ofq_lsq_effective_scale(const float* alpha, int n, float g, float* out, void* stream) {
+extern "C" int ofq_lsq_effective_scale(const float* alpha, int n, float g, float* out, float* out_recip, void* stream) {
     OFQ_REQUIRE(alpha && out && n > 0, "ofq_lsq_effective_scale: bad argument");
     OFQ_CHECK_ARCH();
-    lsq_effective_scale_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(alpha, n, g, out);
+    lsq_effective_scale_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(alpha, n, g, out, out_recip);
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }
@@ -767,12 +780,12 @@ extern "C" long long ofq_lsq_bwd_workspace(long long rows, int cols, int nseg) {
 }
 
 extern "C" int ofq_lsq_bwd_scale(const float* workspace, long long rows, int cols, int nseg, const float* v1, int n1,
-                                 const float* v2, int n2, float mult, float* out4, void* stream) {
+                                 const float* v2, int n2, float mult, int product, float* out4, void* stream) {
     OFQ_REQUIRE(workspace && out4 && rows > 0 && cols > 0 && nseg > 0, "ofq_lsq_bwd_scale: bad argument");
     OFQ_CHECK_ARCH();
     const long long nblk = lsq_bwd_nblk(rows);
     scale_from_blockmax_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(workspace + rows * nseg + nblk * 3 * cols, (int)nblk,
-                                                                   v1, n1, v2, n2, mult, out4);
+                                                                   v1, n1, v2, n2, mult, product, out4);
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }
@@ -802,14 +815,14 @@ extern "C" int ofq_lsq_bwd(const float* dy, long long lddy, const float* x, long
 }
 
 extern "C" int ofq_lsq_bwd_finalize(const float* workspace, long long rows, int cols, int scale_mode, int period,
-                                    int nseg, float g, float* d_s, float* d_b4, float* d_aft, void* stream) {
+                                    int nseg, float g, float* d_s, float* d_b4, float* d_aft, int zero_sum, void* stream) {
     OFQ_REQUIRE(workspace && rows > 0 && cols > 0, "ofq_lsq_bwd_finalize: bad argument");
     OFQ_CHECK_ARCH();
     const float* rowpart = workspace;
     const float* colpart = workspace + rows * nseg;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 gridc((cols + 31) / 32, 3);
-    lsq_bwd_finalize_cols_kernel<<<gridc, 256, 0, st>>>(colpart, cols, lsq_bwd_nblk(rows), scale_mode, g, d_s, d_b4, d_aft);
+    lsq_bwd_finalize_cols_kernel<<<gridc, 256, 0, st>>>(colpart, cols, lsq_bwd_nblk(rows), scale_mode, g, d_s, d_b4, d_aft, zero_sum);
     if (d_s && scale_mode == OFQ_SCALE_PER_ROW) {
         const long long nscale = (long long)(period < rows ? period : rows) * nseg;
         lsq_bwd_finalize_rows_kernel<<<(unsigned)((nscale + 31) / 32), 256, 0, st>>>(rowpart, rows * nseg, nscale, g, d_s);
@@ -822,7 +835,7 @@ extern "C" long long ofq_absmax_scale_workspace(void) { return 2 + 2 * kAbsmaxMa
 
 extern "C" int ofq_absmax_scale(const float* x, int nb, int R, int C, long long ldx, long long bstride,
                                 const float* cs, const float* rs, int rs_period, const float* v1, int n1,
-                                const float* v2, int n2, float mult, float* out4, void* workspace, void* stream) {
+                                const float* v2, int n2, float mult, int product, float* out4, void* workspace, void* stream) {
     OFQ_REQUIRE(x && out4 && workspace && nb > 0 && R > 0 && C > 0, "ofq_absmax_scale: bad argument");
     OFQ_REQUIRE(ldx % 4 == 0 && ldx >= (C + 3) / 4 * 4 && bstride % 4 == 0 && (uintptr_t)x % 16 == 0,
                 "ofq_absmax_scale: ldx, bstride must be multiples of 4 (ldx covering the last quad) and x 16-byte aligned");
@@ -831,10 +844,11 @@ extern "C" int ofq_absmax_scale(const float* x, int nb, int R, int C, long long 
     OFQ_CHECK_ARCH();
     if (rs_period <= 0) rs_period = 0x7fffffff;
     const long long nquads = (long long)nb * R * (ldx / 4);
+    OFQ_REQUIRE(nquads < 0x7fffffffLL, "ofq_absmax_scale: tensor too large for 32-bit indexing");
     long long grid = (nquads + 256 * 4 - 1) / (256 * 4);
     if (grid > kAbsmaxMaxBlocks) grid = kAbsmaxMaxBlocks;
-    absmax_scale_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, nquads, C, (int)(ldx / 4), R, cs, rs, rs_period,
-                                                                         v1, n1, v2, n2, mult, out4, (unsigned int*)workspace);
+    absmax_scale_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, (uint32_t)nquads, C, (uint32_t)(ldx / 4), (uint32_t)R, cs, rs, rs_period,
+                                                                         v1, n1, v2, n2, mult, product, out4, (unsigned int*)workspace);
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }
@@ -842,7 +856,7 @@ extern "C" int ofq_absmax_scale(const float* x, int nb, int R, int C, long long 
 extern "C" int ofq_grad_prep(const float* x, int nb, int R, int C, long long ldx, long long bstride_x,
                              const float* cs, const float* rs, int rs_period, int planes, void* out_rm,
                              long long ld_rm, void* out_t, int r_pad, float* colsum, const float* u, int group,
-                             float* rowdot, int out_fmt, const float* scale4, void* stream) {
+                             float* rowdot, int out_fmt, const float* scale4, int rm_rowscale, void* stream) {
     OFQ_REQUIRE(x && nb > 0 && R > 0 && C > 0, "ofq_grad_prep: bad argument");
     OFQ_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && bstride_x % 4 == 0 && (uintptr_t)x % 16 == 0,
                 "ofq_grad_prep: C, ldx must be multiples of 4 and x 16-byte aligned");
@@ -856,12 +870,12 @@ extern "C" int ofq_grad_prep(const float* x, int nb, int R, int C, long long ldx
     if (rs_period <= 0) rs_period = 0x7fffffff;
     dim3 grid((C + 63) / 64, (R + 63) / 64, nb);
     if (out_fmt == OFQ_FMT_F16)
-        grad_prep_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, R, C, ldx, bstride_x, cs, rs, rs_period, planes, scale4,
+        grad_prep_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, R, C, ldx, bstride_x, cs, rs, rs_period, planes, scale4, rm_rowscale,
                                                                  (long long)nb * R * ld_rm, (long long)nb * C * r_pad,
                                                                  (uint16_t*)out_rm, ld_rm, (uint16_t*)out_t, r_pad,
                                                                  colsum, u, group, rowdot);
     else
-        grad_prep_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, R, C, ldx, bstride_x, cs, rs, rs_period, planes, scale4,
+        grad_prep_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, R, C, ldx, bstride_x, cs, rs, rs_period, planes, scale4, rm_rowscale,
                                                                  (long long)nb * R * ld_rm, (long long)nb * C * r_pad,
                                                                  (uint16_t*)out_rm, ld_rm, (uint16_t*)out_t, r_pad,
                                                                  colsum, u, group, rowdot);

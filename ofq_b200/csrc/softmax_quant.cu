@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256)
 softmax_quant_bwd_kernel(const float* __restrict__ dPq, const float* __restrict__ P, int N, long long ld, int H,
                          const float* __restrict__ s_eff, float qhi, float alpha, float g_s,
                          const float* __restrict__ ca, int ca_per_head, const float* __restrict__ rb, int planes,
-                         const float* __restrict__ scale4,
+                         const float* __restrict__ scale4, int a_rowscale,
                          uint16_t* __restrict__ out_a, uint16_t* __restrict__ out_bt, long long ldo,
                          float* __restrict__ colsum, float* __restrict__ d_s, float* __restrict__ dS32) {
     extern __shared__ float tile[];           // [32][N + 1] dS * rb[n] for the transposed output
@@ -149,7 +149,9 @@ softmax_quant_bwd_kernel(const float* __restrict__ dPq, const float* __restrict_
         dot = wsum(dot);
         dsp = wsum(dsp);
         if (lane == 0 && d_s) atomicAdd(d_s + n, g_s * dsp);
-        const float rbv = (rb ? __ldg(rb + n) : 1.f) * sc_b;
+        const float rb_raw = rb ? __ldg(rb + n) : 1.f;
+        const float rbv = rb_raw * sc_b;
+        const float sca_row = a_rowscale ? sc_a * rb_raw : sc_a;
 #pragma unroll
         for (int i = 0; i < kMaxPer; ++i) {
             const int d = lane + 32 * i;
@@ -158,7 +160,7 @@ softmax_quant_bwd_kernel(const float* __restrict__ dPq, const float* __restrict_
                 const float ds = alpha * ds_raw;             // gradient w.r.t. the un-scaled q.k product
                 colacc[i] += ds;
                 if (out_a) {
-                    const float va = ds * (cav ? __ldg(cav + d) : 1.f) * sc_a;
+                    const float va = ds * (cav ? __ldg(cav + d) : 1.f) * sca_row;
                     const uint16_t hi16 = to16<F16>(va);
                     uint16_t* dst = out_a + (zo + n) * ldo + d;
                     *dst = hi16;
@@ -228,7 +230,7 @@ extern "C" int ofq_softmax_quant_bwd(const float* dPq, const float* P, int nz, i
                                      const float* s_eff, int qhi, float alpha, float g_s, const float* ca,
                                      int ca_per_head, const float* rb, int planes, void* out_a, void* out_bt,
                                      long long ldo, float* colsum, float* d_s, float* dS32, int out_fmt,
-                                     const float* scale4, void* stream) {
+                                     const float* scale4, int a_rowscale, void* stream) {
     OFQ_REQUIRE(dPq && P && s_eff && nz > 0 && N > 0 && H > 0, "ofq_softmax_quant_bwd: bad argument");
     OFQ_REQUIRE(N <= kMaxPer * 32, "ofq_softmax_quant_bwd: at most 256 keys per row are supported");
     OFQ_REQUIRE((!out_a && !out_bt) || (ldo % 8 == 0 && ldo >= N), "ofq_softmax_quant_bwd: output pitch must be a multiple of 8 and >= N");
@@ -240,11 +242,11 @@ extern "C" int ofq_softmax_quant_bwd(const float* dPq, const float* P, int nz, i
     const size_t smem = (size_t)32 * (N + 1) * sizeof(float);
     if (out_fmt == OFQ_FMT_F16)
         softmax_quant_bwd_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(
-            dPq, P, N, ld, H, s_eff, (float)qhi, alpha, g_s, ca, ca_per_head, rb, planes, scale4, (uint16_t*)out_a,
+            dPq, P, N, ld, H, s_eff, (float)qhi, alpha, g_s, ca, ca_per_head, rb, planes, scale4, a_rowscale, (uint16_t*)out_a,
             (uint16_t*)out_bt, ldo, colsum, d_s, dS32);
     else
         softmax_quant_bwd_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(
-            dPq, P, N, ld, H, s_eff, (float)qhi, alpha, g_s, ca, ca_per_head, rb, planes, scale4, (uint16_t*)out_a,
+            dPq, P, N, ld, H, s_eff, (float)qhi, alpha, g_s, ca, ca_per_head, rb, planes, scale4, a_rowscale, (uint16_t*)out_a,
             (uint16_t*)out_bt, ldo, colsum, d_s, dS32);
     OFQ_CUDA(cudaGetLastError());
     return 0;

@@ -88,14 +88,15 @@ def gemm(kind: int, a: torch.Tensor, a_strides, b: torch.Tensor, b_strides, out:
 
 # ------------------------------------------------------------------------------------------------ quantizers
 def statsq_codes(w: torch.Tensor, bits: int, aft: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
-                 want_minmax: bool = False):
+                 want_minmax: bool = False, want_inv: bool = False):
     """StatsQ codes of a 2-D fp32 weight. Returns (codes int8 [R,C], colscale [R], sf [R], colterm [R] | None,
-    kminmax int32[2] | None)."""
+    kminmax int32[2] | None [, 1/colscale [R] if want_inv])."""
     _cuda(w)
     assert w.dim() == 2 and w.dtype == torch.float32 and w.stride(1) == 1
     R, Cc = w.shape
     codes = torch.empty((R, Cc), dtype=torch.int8, device=w.device)
-    colscale = torch.empty(R, dtype=torch.float32, device=w.device)
+    cs2 = torch.empty((2, R), dtype=torch.float32, device=w.device)
+    colscale = cs2[0]
     sf = torch.empty(R, dtype=torch.float32, device=w.device)
     colterm = torch.empty(R, dtype=torch.float32, device=w.device) if (aft is not None or bias is not None) else None
     mm = None
@@ -104,16 +105,25 @@ def statsq_codes(w: torch.Tensor, bits: int, aft: Optional[torch.Tensor] = None,
     if colterm is not None and aft is None:
         aft = torch.zeros(Cc, dtype=torch.float32, device=w.device)
     _call("statsq", 1, 5.0 * R * Cc, 0, _lib.load().ofq_statsq_codes, w.data_ptr(), R, Cc, w.stride(0), bits,
-          codes.data_ptr(), Cc, colscale.data_ptr(), sf.data_ptr(), _ptr(aft), _ptr(bias), _ptr(colterm), _ptr(mm), _st())
+          codes.data_ptr(), Cc, colscale.data_ptr(), sf.data_ptr(), _ptr(aft), _ptr(bias), _ptr(colterm), _ptr(mm),
+          cs2[1].data_ptr(), _st())
+    if want_inv:
+        return codes, colscale, sf, colterm, mm, cs2[1]
     return codes, colscale, sf, colterm, mm
 
 
-def lsq_effective_scale(alpha: torch.Tensor, g: float) -> torch.Tensor:
+def lsq_effective_scale(alpha: torch.Tensor, g: float, recip: bool = False):
+    """Effective LSQ step sizes; recip=True returns [2, n]: row 0 = scales, row 1 = their reciprocals."""
     _cuda(alpha)
     a = alpha.detach().contiguous()
+    if recip:
+        out = torch.empty((2,) + tuple(a.shape), dtype=a.dtype, device=a.device)
+        _call("lsq_scale", 1, 12.0 * a.numel(), 0, _lib.load().ofq_lsq_effective_scale, a.data_ptr(), a.numel(), float(g),
+              out[0].data_ptr(), out[1].data_ptr(), _st())
+        return out
     out = torch.empty_like(a)
     _call("lsq_scale", 1, 8.0 * a.numel(), 0, _lib.load().ofq_lsq_effective_scale, a.data_ptr(), a.numel(), float(g),
-          out.data_ptr(), _st())
+          out.data_ptr(), None, _st())
     return out
 
 
@@ -131,8 +141,9 @@ def lsq_quant(x2d: torch.Tensor, b4: torch.Tensor, s_eff: torch.Tensor, mode: in
 
 
 def lsq_bwd(dy2d: torch.Tensor, x2d: torch.Tensor, b4: torch.Tensor, s_eff: torch.Tensor, mode: int, period: int,
-            nseg: int, qlo: int, qhi: int, g: float, want_ds: bool = True, want_aft: bool = True, next_scale=None):
-    """Returns (dx [rows, cols], d_s, d_b4 [cols], d_aft [cols] | None).  next_scale = (v1, v2, mult): additionally
+            nseg: int, qlo: int, qhi: int, g: float, want_ds: bool = True, want_aft: bool = True, next_scale=None,
+            zero_sum: bool = False):
+    """Returns (dx [rows, cols], d_s, d_b4 [cols], d_aft [cols] | None).  next_scale = (v1, v2, mult, product): additionally
     returns the fp16 range scales (absmax_scale layout) of dx*v1[c] / dx*v2[r] for the GEMM operand made from dx,
     derived from max|dx| at no extra pass over dx."""
     _cuda(dy2d, x2d)
@@ -149,13 +160,14 @@ def lsq_bwd(dy2d: torch.Tensor, x2d: torch.Tensor, b4: torch.Tensor, s_eff: torc
     d_b4 = torch.empty(cols, dtype=torch.float32, device=dy2d.device)
     d_aft = torch.empty(cols, dtype=torch.float32, device=dy2d.device) if want_aft else None
     _call("lsq_bwd_finalize", 1, 4.0 * ws.numel(), 0, lib.ofq_lsq_bwd_finalize, ws.data_ptr(), rows, cols, mode, period,
-          nseg, float(g), _ptr(d_s), d_b4.data_ptr(), _ptr(d_aft), _st())
+          nseg, float(g), _ptr(d_s), d_b4.data_ptr(), _ptr(d_aft), int(zero_sum), _st())
     if next_scale is None:
         return dx, d_s, d_b4, d_aft
-    v1, v2, mult = next_scale
+    v1, v2, mult, product = next_scale
     sc = torch.empty(4, dtype=torch.float32, device=dy2d.device)
     _call("lsq_bwd_scale", 1, 0.0, 0, lib.ofq_lsq_bwd_scale, ws.data_ptr(), rows, cols, nseg, _ptr(v1),
-          0 if v1 is None else v1.numel(), _ptr(v2), 0 if v2 is None else v2.numel(), float(mult), sc.data_ptr(), _st())
+          0 if v1 is None else v1.numel(), _ptr(v2), 0 if v2 is None else v2.numel(), float(mult), int(product),
+          sc.data_ptr(), _st())
     return dx, d_s, d_b4, d_aft, sc
 
 
@@ -167,7 +179,7 @@ _ABSMAX_WS = {}
 
 
 def absmax_scale(x: torch.Tensor, nb: int, R: int, Cc: int, ldx: int, bstride: int, *, cs=None, rs=None, rs_period=0,
-                 v1=None, v2=None, mult: float = 1.0) -> torch.Tensor:
+                 v1=None, v2=None, mult: float = 1.0, product: bool = False) -> torch.Tensor:
     """Power-of-two fp16 range scales of x*cs (out[0], inverse out[1]) and x*rs (out[2], inverse out[3]); the bounds are
     further multiplied by max|v1| / max|v2| and `mult` (see ofq_absmax_scale)."""
     _cuda(x)
@@ -178,13 +190,13 @@ def absmax_scale(x: torch.Tensor, nb: int, R: int, Cc: int, ldx: int, bstride: i
     out = torch.empty(4, dtype=torch.float32, device=x.device)
     _call("absmax_scale", 1, 4.0 * nb * R * Cc, 0, lib.ofq_absmax_scale, x.data_ptr(), nb, R, Cc, ldx, bstride, _ptr(cs),
           _ptr(rs), rs_period, _ptr(v1), 0 if v1 is None else v1.numel(), _ptr(v2), 0 if v2 is None else v2.numel(),
-          float(mult), out.data_ptr(), ws.data_ptr(), _st())
+          float(mult), int(product), out.data_ptr(), ws.data_ptr(), _st())
     return out
 
 
 def grad_prep(x: torch.Tensor, nb: int, R: int, Cc: int, ldx: int, bstride: int, *, cs=None, rs=None, rs_period=0,
               want_rm: bool = False, want_t: bool = False, want_colsum: bool = False, u=None, group: int = 64,
-              planes: int = 1, fmt: int = FMT_BF16, scale4=None):
+              planes: int = 1, fmt: int = FMT_BF16, scale4=None, rm_rowscale: bool = False):
     """One pass over a fp32 gradient: returns dict(rm=16-bit [planes,nb,R,C], t=16-bit [planes,nb,C,r_pad], r_pad,
     colsum [C], rowdot [nb,C/group,R])."""
     _cuda(x)
@@ -197,7 +209,7 @@ def grad_prep(x: torch.Tensor, nb: int, R: int, Cc: int, ldx: int, bstride: int,
     rowdot = torch.empty((nb, Cc // group, R), dtype=torch.float32, device=dev) if u is not None else None
     nbytes = nb * R * Cc * (4.0 + 2 * planes * (int(want_rm) + int(want_t)))
     _call("grad_prep", 1, nbytes, 0, _lib.load().ofq_grad_prep, x.data_ptr(), nb, R, Cc, ldx, bstride, _ptr(cs), _ptr(rs),
-          rs_period, planes, _ptr(rm), Cc, _ptr(t), r_pad, _ptr(colsum), _ptr(u), group, _ptr(rowdot), fmt, _ptr(scale4), _st())
+          rs_period, planes, _ptr(rm), Cc, _ptr(t), r_pad, _ptr(colsum), _ptr(u), group, _ptr(rowdot), fmt, _ptr(scale4), int(rm_rowscale), _st())
     out.update(rm=rm, t=t, colsum=colsum, rowdot=rowdot)
     return out
 
@@ -255,21 +267,21 @@ def softmax_quant(S: torch.Tensor, N: int, H: int, s_eff: torch.Tensor, qhi: int
 
 def softmax_quant_bwd(dPq: torch.Tensor, P: torch.Tensor, N: int, H: int, s_eff: torch.Tensor, qhi: int, alpha: float,
                       g_s: float, ca: torch.Tensor, ca_per_head: bool, rb: torch.Tensor, want_ds32: bool = False,
-                      planes: int = 1, fmt: int = FMT_BF16, scale4=None):
+                      planes: int = 1, fmt: int = FMT_BF16, scale4=None, rm_rowscale: bool = False):
     """Returns (out_a bf16 [B,planes,H,N,ldo], out_bt bf16 [B,planes,H,N,ldo], ldo, colsum [nz,N], d_s [N], dS32 | None)."""
     _cuda(dPq, P)
     nz, _, ld = P.shape
     ldo = round_up(N, 8)
     dev = P.device
     out_a = torch.empty((nz // H, planes, H, N, ldo), dtype=_T16[fmt], device=dev)
-    out_bt = torch.empty((nz // H, planes, H, N, ldo), dtype=_T16[fmt], device=dev)
+    out_bt = None if single else torch.empty((nz // H, planes, H, N, ldo), dtype=_T16[fmt], device=dev)
     colsum = torch.zeros((nz, N), dtype=torch.float32, device=dev)
     d_s = torch.zeros(N, dtype=torch.float32, device=dev)
     ds32 = torch.empty_like(P) if want_ds32 else None
-    _call("softmax_quant_bwd", 1, nz * N * N * (8.0 + 4 * planes + (4 if want_ds32 else 0)), 0,
+    _call("softmax_quant_bwd", 1, nz * N * N * (8.0 + (2 if single else 4) * planes + (4 if want_ds32 else 0)), 0,
           _lib.load().ofq_softmax_quant_bwd, dPq.data_ptr(), P.data_ptr(), nz, N, ld, H, s_eff.data_ptr(), qhi,
           float(alpha), float(g_s), _ptr(ca), 1 if ca_per_head else 0, _ptr(rb), planes, out_a.data_ptr(),
-          out_bt.data_ptr(), ldo, colsum.data_ptr(), d_s.data_ptr(), _ptr(ds32), fmt, _ptr(scale4), _st())
+          _ptr(out_bt), ldo, colsum.data_ptr(), d_s.data_ptr(), _ptr(ds32), fmt, _ptr(scale4), int(single), _st())
     return out_a, out_bt, ldo, colsum, d_s, ds32
 
 

@@ -54,31 +54,59 @@ def grad_scale_factor(hi: int, count: int) -> float:
     return 1.0 / ((hi * count) ** 0.5)
 
 
-def _inv(sc, which: int):
-    """Epilogue un-scale of a range-scaled fp16 operand: device scalar 1/scale as a period-1 row vector."""
-    return vec(sc[2 * which + 1:2 * which + 2], 1) if sc is not None else None
-
-
 def _splits_for(tiles: int, kblocks: int) -> int:
     s = max(1, min((2 * NUM_SMS + tiles - 1) // tiles, max(1, kblocks // 4)))
     return min(s, 64)
 
 
-def _linear_backward(dY2d, qx, wc, colscale, se_x, period, x_aft, dxhat, accumulate_dx: bool, qxT_all=None, sc=None):
-    """Backward of out = x_hat @ W_hat^T (+bias):  dX_hat (+)= dY W_hat,  dW = dY^T x_hat,  dbias = colsum(dY).
-    x_hat = qx * se_x[row % period] + x_aft,  W_hat = wc * colscale[row].  Returns (dW, dbias, qxT_all)."""
+def _scalar(sc):
+    """The un-scale 1/sc of a range-scaled fp16 operand as a period-1 epilogue vector."""
+    return vec(sc[1:2], 1)
+
+
+def _linear_backward_f16(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulate_dx: bool, qx16=None, sc=None):
+    """fp16 backward of out = x_hat @ W_hat^T (+bias) with ONE range-scaled copy of the gradient,
+    A16[t,n] = fp16(dY[t,n] * colscale[n] * se_x[t] * sc), read K-major by the dX GEMM and MN-major by the dW GEMM; the
+    code operands stay exact and un-transposed (MN-major B), the folded scale vectors are undone per output row:
+        dX_hat[t,k] (+)= 1/(se_x[t] sc) * sum_n A16[t,n] wc[n,k]
+        dW[n,k]        = 1/(colscale[n] sc) * sum_t A16[t,n] qx[t,k] + colsum(dY)[n] * aft[k]
+    cs2 = [colscale, 1/colscale], se2 = [se_x, 1/se_x]. Returns (dW, dbias, qx16)."""
     M, Nout = dY2d.shape
     K = qx.shape[1]
-    if F16 and sc is None:      # fp16 range scales of dY*colscale / dY*se_x (the caller passes them when it already knows)
-        sc = ops.absmax_scale(dY2d, 1, M, Nout, dY2d.stride(0), 0, cs=colscale, rs=se_x, rs_period=period)
+    if sc is None:
+        sc = ops.absmax_scale(dY2d, 1, M, Nout, dY2d.stride(0), 0, cs=cs2[0], rs=se2[0], rs_period=period, product=True)
+    prep = ops.grad_prep(dY2d, 1, M, Nout, dY2d.stride(0), 0, cs=cs2[0], rs=se2[0], rs_period=period, want_rm=True,
+                         want_colsum=True, fmt=FMT, scale4=sc, rm_rowscale=True)
+    a16 = prep["rm"]
+    wc16 = ops.codes_to_bf16(wc, 1, Nout, K, K, 0, False, FMT)           # [1, Nout, K]
+    ops.gemm(GEMM_BWD, a16, (Nout, 0, 0, 0), wc16, (K, 0, 0, 0), dxhat, (K, 0, 0), M, K, Nout, b_mn=True,
+             accumulate=accumulate_dx, rs=vec(se2[1], period), cs=_scalar(sc))
+    if qx16 is None:
+        qx16 = ops.codes_to_bf16(qx, 1, M, K, K, 0, False, FMT)          # [1, M, K]
+    dW = torch.zeros((Nout, K), dtype=torch.float32, device=dY2d.device)
+    tiles = ((Nout + 127) // 128) * ((K + 127) // 128)
+    splits = _splits_for(tiles, (M + 63) // 64)
+    ops.gemm(GEMM_BWD, a16, (Nout, 0, 0, 0), qx16, (K, 0, 0, 0), dW, (K, 0, 0), Nout, K, M, a_mn=True, b_mn=True,
+             splits=splits, accumulate=True, rs=vec(cs2[1]), cs=_scalar(sc), rt=vec(prep["colsum"]), ct=vec(x_aft))
+    return dW, prep["colsum"], qx16
+
+
+def _linear_backward(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulate_dx: bool, qxT_all=None, sc=None):
+    """Backward of out = x_hat @ W_hat^T (+bias):  dX_hat (+)= dY W_hat,  dW = dY^T x_hat,  dbias = colsum(dY).
+    x_hat = qx * se_x[row % period] + x_aft,  W_hat = wc * colscale[row].  Returns (dW, dbias, shared code operand)."""
+    if F16:
+        return _linear_backward_f16(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulate_dx, qxT_all, sc)
+    colscale, se_x = cs2[0], se2[0]
+    M, Nout = dY2d.shape
+    K = qx.shape[1]
     prep = ops.grad_prep(dY2d, 1, M, Nout, dY2d.stride(0), 0, cs=colscale, rs=se_x, rs_period=period,
-                         want_rm=True, want_t=True, want_colsum=True, planes=PLANES, fmt=FMT, scale4=sc)
+                         want_rm=True, want_t=True, want_colsum=True, planes=PLANES)
     m_pad = prep["r_pad"]
     # dX_hat[M,K] = (dY * colscale)[M,Nout] @ codes[Nout,K]
     wcT = ops.codes_to_bf16(wc, 1, Nout, K, K, 0, True, FMT)       # [1, K, nout_pad]
     nout_pad = wcT.shape[-1]
     ops.gemm(GEMM_BWD, prep["rm"], (Nout, M * Nout, 0, 0), wcT, (nout_pad, 0, 0, 0), dxhat, (K, 0, 0), M, K, Nout,
-             k2=K2P, a_dual_delta=DD, accumulate=accumulate_dx, rs=_inv(sc, 0))
+             k2=K2P, a_dual_delta=DD, accumulate=accumulate_dx)
     # dW[Nout,K] = (dY * se_x)^T[Nout,M] @ qx[M,K]  + colsum(dY)[Nout] x aft[K]
     if qxT_all is None:
         qxT_all = ops.codes_to_bf16(qx, 1, M, K, K, 0, True, FMT)  # [1, K, m_pad]
@@ -86,7 +114,7 @@ def _linear_backward(dY2d, qx, wc, colscale, se_x, period, x_aft, dxhat, accumul
     tiles = ((Nout + 127) // 128) * ((K + 127) // 128)
     splits = _splits_for(tiles, K2P * ((M + 63) // 64))
     ops.gemm(GEMM_BWD, prep["t"], (m_pad, Nout * m_pad, 0, 0), qxT_all, (m_pad, 0, 0, 0), dW, (K, 0, 0), Nout, K, M,
-             k2=K2P, a_dual_delta=DD, splits=splits, accumulate=True, rs=_inv(sc, 1), rt=vec(prep["colsum"]), ct=vec(x_aft))
+             k2=K2P, a_dual_delta=DD, splits=splits, accumulate=True, rt=vec(prep["colsum"]), ct=vec(x_aft))
     return dW, prep["colsum"], qxT_all
 
 
@@ -105,27 +133,28 @@ class QLinearFn(torch.autograd.Function):
         Nout = weight.shape[0]
         lo, hi = levels(abits, unsigned)
         g = grad_scale_factor(hi, x.numel() // P)
-        se = ops.lsq_effective_scale(s, g)
+        se2 = ops.lsq_effective_scale(s, g, recip=True)
+        se = se2[0]
         qx = ops.lsq_quant(x2d, b4, se, PER_ROW, P, 1, lo, hi)
-        wc, colscale, _, colterm, _ = ops.statsq_codes(weight, wbits, aft=aft, bias=bias)
+        wc, colscale, _, colterm, _, inv_cs = ops.statsq_codes(weight, wbits, aft=aft, bias=bias, want_inv=True)
         out = torch.empty((M, Nout), dtype=torch.float32, device=x.device)
         ops.gemm(GEMM_I8, qx, (K, 0, 0, 0), wc, (K, 0, 0, 0), out, (Nout, 0, 0), M, Nout, K,
                  rs=vec(se, P), cs=vec(colscale), ct=vec(colterm))
-        ctx.save_for_backward(xc, qx, wc, colscale, se, b4, aft)
+        ctx.save_for_backward(xc, qx, wc, colscale, inv_cs, se2, b4, aft)
         ctx.cfg = (P, lo, hi, g, bias is not None)
         return out.view(*x.shape[:-1], Nout)
 
     @staticmethod
     def backward(ctx, dY):
-        xc, qx, wc, colscale, se, b4, aft = ctx.saved_tensors
+        xc, qx, wc, colscale, inv_cs, se2, b4, aft = ctx.saved_tensors
         P, lo, hi, g, has_bias = ctx.cfg
         K = xc.shape[-1]
         x2d = xc.view(-1, K)
         M = x2d.shape[0]
         dY2d = dY.contiguous().view(M, -1)
         dxhat = torch.empty((M, K), dtype=torch.float32, device=dY.device)
-        dW, dbias, _ = _linear_backward(dY2d, qx, wc, colscale, se, P, aft, dxhat, False)
-        dx, ds, db4, daft = ops.lsq_bwd(dxhat, x2d, b4, se, PER_ROW, P, 1, lo, hi, g)
+        dW, dbias, _ = _linear_backward(dY2d, qx, wc, (colscale, inv_cs), se2, P, aft, dxhat, False)
+        dx, ds, db4, daft = ops.lsq_bwd(dxhat, x2d, b4, se2[0], PER_ROW, P, 1, lo, hi, g)
         return dx.view_as(xc), dW, (dbias if has_bias else None), db4, daft, ds, None, None, None
 
 
@@ -178,24 +207,45 @@ def _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C):
     return out
 
 
-def _pv_backward(dO, qp, ldq, qv, se_p, se_v, v_aft, B, N, H, C, ldS):
-    """Returns (dPq [B*H,N,ldS] fp32, dvhat [B,N,C] fp32)."""
+def _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS):
+    """fp16 backward of P_hat V_hat with ONE copy A16[b,n,c] = fp16(dO * se_v[c] * se_p[n] * sc):
+        dP_hat[z,n,d]  = 1/(se_p[n] sc) * sum_j A16[b,n,hj] qv[b,d,hj] + sum_j dO[b,n,hj] v_aft[hj]
+        dv_hat[b,d,hj] = 1/(se_v[hj] sc) * sum_n qp[z,n,d] A16[b,n,hj]                    (both operands MN-major)"""
     hd = C // H
-    sc = ops.absmax_scale(dO, B, N, C, C, N * C, cs=se_v, rs=se_p, rs_period=N) if F16 else None
+    sc = ops.absmax_scale(dO, B, N, C, C, N * C, cs=sv2[0], rs=sp2[0], rs_period=N, product=True)
+    prep = ops.grad_prep(dO, B, N, C, C, N * C, cs=sv2[0], rs=sp2[0], rs_period=N, want_rm=True, u=v_aft, group=hd,
+                         fmt=FMT, scale4=sc, rm_rowscale=True)
+    a16 = prep["rm"]                                                     # [1, B, N, C]
+    qv16 = ops.codes_to_bf16(qv, B, N, C, C, N * C, False, FMT)          # [B, N, C]
+    dPq = torch.empty((B * H, N, ldS), dtype=torch.float32, device=dO.device)
+    ops.gemm(GEMM_BWD, a16, (C, 0, hd, N * C), qv16, (C, 0, hd, N * C), dPq, (ldS, N * ldS, H * N * ldS), N, N, hd,
+             nb1=H, nb2=B, rs=vec(sp2[1], N), cs=_scalar(sc), rt=vec(prep["rowdot"], 0, N, H * N))
+    qp16 = ops.codes_to_bf16(qp, B * H, N, ldq, ldq, N * ldq, False, FMT)    # [B*H, N, ldq]
+    dvhat = torch.empty((B, N, C), dtype=torch.float32, device=dO.device)
+    ops.gemm(GEMM_BWD, qp16, (ldq, 0, N * ldq, H * N * ldq), a16, (C, 0, hd, N * C), dvhat, (C, hd, N * C), N, hd, N,
+             nb1=H, nb2=B, a_mn=True, b_mn=True, rs=_scalar(sc), cs=vec(sv2[1], 0, hd))
+    return dPq, dvhat
+
+
+def _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS):
+    """Returns (dPq [B*H,N,ldS] fp32, dvhat [B,N,C] fp32). sp2 / sv2 = [scale, 1/scale] of the probability / V quantizer."""
+    if F16:
+        return _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS)
+    se_p, se_v = sp2[0], sv2[0]
+    hd = C // H
     prep = ops.grad_prep(dO, B, N, C, C, N * C, cs=se_v, rs=se_p, rs_period=N, want_rm=True, want_t=True,
-                         u=v_aft, group=hd, planes=PLANES, fmt=FMT, scale4=sc)
+                         u=v_aft, group=hd, planes=PLANES)
     npad8 = prep["r_pad"]
     # dP_hat[z,n,d] = sum_j (dO[n,hj] se_v[hj]) qv[d,hj] + sum_j dO[n,hj] v_aft[hj]
-    qv16 = ops.codes_to_bf16(qv, B, N, C, C, N * C, False, FMT)      # [B, N, C] 16-bit
+    qv16 = ops.codes_to_bf16(qv, B, N, C, C, N * C, False)           # [B, N, C] bf16
     dPq = torch.empty((B * H, N, ldS), dtype=torch.float32, device=dO.device)
-    ops.gemm(GEMM_BWD, prep["rm"], (C, B * N * C, hd, N * C), qv16, (C, 0, hd, N * C), dPq, (ldS, N * ldS, H * N * ldS),
-             N, N, hd, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B, rs=_inv(sc, 0), rt=vec(prep["rowdot"], 0, N, H * N))
+    ops.gemm(GEMM_BF16, prep["rm"], (C, B * N * C, hd, N * C), qv16, (C, 0, hd, N * C), dPq, (ldS, N * ldS, H * N * ldS),
+             N, N, hd, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B, rt=vec(prep["rowdot"], 0, N, H * N))
     # dv_hat[b,d,hj] = sum_n qp[z,n,d] (se_p[n] dO[b,n,hj])
-    qpT = ops.codes_to_bf16(qp, B * H, N, ldq, ldq, N * ldq, True, FMT)   # [B*H, ldq, npad8]; rows d >= N are zero
+    qpT = ops.codes_to_bf16(qp, B * H, N, ldq, ldq, N * ldq, True)   # [B*H, ldq, npad8]; rows d >= N are zero
     dvhat = torch.empty((B, N, C), dtype=torch.float32, device=dO.device)
-    ops.gemm(GEMM_BWD, qpT, (npad8, 0, ldq * npad8, H * ldq * npad8), prep["t"],
-             (npad8, B * C * npad8, hd * npad8, C * npad8), dvhat, (C, hd, N * C), N, hd, N, k2=PLANES, nb1=H, nb2=B,
-             rs=_inv(sc, 1))
+    ops.gemm(GEMM_BF16, qpT, (npad8, 0, ldq * npad8, H * ldq * npad8), prep["t"],
+             (npad8, B * C * npad8, hd * npad8, C * npad8), dvhat, (C, hd, N * C), N, hd, N, k2=PLANES, nb1=H, nb2=B)
     return dPq, dvhat
 
 
@@ -217,29 +267,33 @@ class QKRAttnCoreFn(torch.autograd.Function):
         x2d = xc.view(M, C)
         # --- shared quantized input (LSQ_input, qlinear.py:21-26)
         g_x = grad_scale_factor(hi, B * C)
-        se_x = ops.lsq_effective_scale(s_x, g_x)
+        sx2 = ops.lsq_effective_scale(s_x, g_x, recip=True)
+        se_x = sx2[0]
         qx = ops.lsq_quant(x2d, x_b4, se_x, PER_ROW, N, 1, lo, hi)
         # --- V branch (attention.py:179-186)
-        wvc, cs_v, _, ct_v, _ = ops.statsq_codes(wv, wbits, aft=x_aft, bias=bv)
+        wvc, cs_v, _, ct_v, _, ics_v = ops.statsq_codes(wv, wbits, aft=x_aft, bias=bv, want_inv=True)
         v_out = torch.empty((M, C), dtype=torch.float32, device=dev)
         ops.gemm(GEMM_I8, qx, (C, 0, 0, 0), wvc, (C, 0, 0, 0), v_out, (C, 0, 0), M, C, C,
                  rs=vec(se_x, N), cs=vec(cs_v), ct=vec(ct_v))
         g_v = grad_scale_factor(hi, B * N)
-        se_v = ops.lsq_effective_scale(s_v, g_v)
+        sv2 = ops.lsq_effective_scale(s_v, g_v, recip=True)
+        se_v = sv2[0]
         qv = ops.lsq_quant(v_out, v_b4, se_v, PER_COL, 1, 1, lo, hi)
         # --- QK branch: one StatsQ on the per-head product W_q^T W_k (attention.py:190-196)
         wqk = ops.wqk_compose(wq, wk, H)
-        wqkc, cs_qk, _, ct_qk, _ = ops.statsq_codes(wqk, wbits, aft=x_aft)
+        wqkc, cs_qk, _, ct_qk, _, ics_qk = ops.statsq_codes(wqk, wbits, aft=x_aft, want_inv=True)
         qkx = torch.empty((M, H * C), dtype=torch.float32, device=dev)
         ops.gemm(GEMM_I8, qx, (C, 0, 0, 0), wqkc, (C, 0, 0, 0), qkx, (H * C, 0, 0), M, H * C, C,
                  rs=vec(se_x, N), cs=vec(cs_qk), ct=vec(ct_qk))
         g_k = grad_scale_factor(hi, B * C)
-        se_k = ops.lsq_effective_scale(s_k, g_k)                     # [N*H], index n*H + h
+        sk2 = ops.lsq_effective_scale(s_k, g_k, recip=True)          # [2, N*H], index n*H + h
+        se_k = sk2[0]
         qk = ops.lsq_quant(qkx, k_b4, se_k, PER_ROW, N, H, lo, hi)   # [M, H*C]
         # --- scores (attention.py:210-213): S = x_hat . k_hat^T * scale; terms constant along the softmax
         #     axis are dropped (they cancel exactly in softmax and in its gradient)
         ctS = ops.codes_rowdot(qk, H, x_aft.repeat(H))               # [M, H]: sum_c x_aft[c] qk[b,d,h,c]
-        se_k_hn = se_k.view(N, H).t().contiguous()                   # [H, N]
+        sk2_hn = sk2.view(2, N, H).transpose(1, 2).contiguous()      # [2, H, N]
+        se_k_hn = sk2_hn[0]
         cs_S = se_k_hn * scale
         ct_S = (ctS.view(B, N, H).permute(0, 2, 1) * cs_S.unsqueeze(0)).contiguous()   # [B, H, N]
         ldS = round_up(N, 4)
@@ -248,63 +302,83 @@ class QKRAttnCoreFn(torch.autograd.Function):
                  N, N, C, nb1=H, nb2=B, rs=vec(se_x, N), cs=vec(cs_S, 0, N), ct=vec(ct_S, 0, N, H * N))
         # --- softmax + probability quantizer (attention.py:213-215)
         g_p = grad_scale_factor(hiu, B * H * N)
-        se_p = ops.lsq_effective_scale(s_p, g_p)
+        sp2 = ops.lsq_effective_scale(s_p, g_p, recip=True)
+        se_p = sp2[0]
         need_grad = any(ctx.needs_input_grad)
         P, qp, rowsum = ops.softmax_quant(S, N, H, se_p, hiu, bias=attn_bias, mask=attn_mask, nW=nW, save_p=need_grad)
         ldq = qp.shape[-1]
         del S
         out = _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C)
-        ctx.save_for_backward(xc, wq, wk, x_b4, x_aft, v_b4, v_aft, k_b4, k_aft, qx, se_x, wvc, cs_v, v_out, qv, se_v,
-                              wqkc, cs_qk, qkx, qk, se_k, se_k_hn, P, qp, se_p)
+        ctx.save_for_backward(xc, wq, wk, x_b4, x_aft, v_b4, v_aft, k_b4, k_aft, qx, sx2, wvc, cs_v, ics_v, v_out, qv, sv2,
+                              wqkc, cs_qk, ics_qk, qkx, qk, sk2, sk2_hn, P, qp, sp2)
         ctx.cfg = (B, N, C, H, lo, hi, hiu, scale, g_x, g_v, g_k, g_p, ldS, ldq, bv is not None,
                    attn_bias is not None)
         return out
 
     @staticmethod
     def backward(ctx, dO):
-        (xc, wq, wk, x_b4, x_aft, v_b4, v_aft, k_b4, k_aft, qx, se_x, wvc, cs_v, v_out, qv, se_v, wqkc, cs_qk, qkx, qk,
-         se_k, se_k_hn, P, qp, se_p) = ctx.saved_tensors
+        (xc, wq, wk, x_b4, x_aft, v_b4, v_aft, k_b4, k_aft, qx, sx2, wvc, cs_v, ics_v, v_out, qv, sv2, wqkc, cs_qk, ics_qk,
+         qkx, qk, sk2, sk2_hn, P, qp, sp2) = ctx.saved_tensors
         B, N, C, H, lo, hi, hiu, scale, g_x, g_v, g_k, g_p, ldS, ldq, has_bv, has_bias = ctx.cfg
+        se_x, se_v, se_k, se_p, se_k_hn = sx2[0], sv2[0], sk2[0], sp2[0], sk2_hn[0]
         M = B * N
         dev = dO.device
         dO = dO.contiguous()
-        dPq, dvhat = _pv_backward(dO, qp, ldq, qv, se_p, se_v, v_aft, B, N, H, C, ldS)
+        dPq, dvhat = _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS)
         # --- V quantizer and V linear
         dv_out, ds_v, dvb4, dvaft, *sc_v = ops.lsq_bwd(dvhat.view(M, C), v_out, v_b4, se_v, PER_COL, 1, 1, lo, hi, g_v,
-                                                       next_scale=(cs_v, se_x, 1.0) if F16 else None)
+                                                       next_scale=(cs_v, se_x, 1.0, True) if F16 else None)
         dxhat = torch.empty((M, C), dtype=torch.float32, device=dev)
-        dWv, dbv, qxT_all = _linear_backward(dv_out, qx, wvc, cs_v, se_x, N, x_aft, dxhat, False, sc=sc_v[0] if sc_v else None)
-        # --- softmax + probability quantizer
-        # fp16 range bound of dS * {se_k, se_x}: |dS| = |alpha P (dP - sum P dP)| <= 2 alpha max|dPq|
-        sc = (ops.absmax_scale(dPq, B * H, N, N, ldS, N * ldS, v1=se_k_hn, v2=se_x, mult=2.0 * scale) if F16 else None)
-        dSa, dSbT, ldo, colsum_dS, ds_p, dS32 = ops.softmax_quant_bwd(dPq, P, N, H, se_p, hiu, scale, g_p, se_k_hn, True,
-                                                                    se_x, want_ds32=has_bias, planes=PLANES, fmt=FMT,
-                                                                    scale4=sc)
-        slab = N * ldo                      # one (b, plane, h) slab of dSa / dSbT, laid out [B, PLANES, H, N, ldo]
-        del dPq
-        # --- scores: d x_hat += sum_h dS (k_hat)   (outer-K loop over heads)
-        qkT = ops.codes_to_bf16(qk, B, N, H * C, H * C, N * H * C, True, FMT)      # [B, H*C, npad8]
-        npad8 = qkT.shape[-1]
-        if DUAL:     # planes of head h are outer-K slices h and h + H of dSa [B, 2, H, N, ldo]
-            ops.gemm(GEMM_BWD, dSa, (ldo, slab, PLANES * H * slab, 0), qkT, (npad8, C * npad8, H * C * npad8, 0),
-                     dxhat, (C, N * C, 0), N, C, N, k2=H, a_dual_delta=H, nb1=B, accumulate=True)
+        dWv, dbv, qx_op = _linear_backward(dv_out, qx, wvc, (cs_v, ics_v), sx2, N, x_aft, dxhat, False,
+                                           sc=sc_v[0] if sc_v else None)
+        # --- softmax + probability quantizer, then the two score GEMMs
+        if F16:
+            # |dS| = |alpha P (dP - sum P dP)| <= 2 alpha max|dPq|; ONE copy dS16[b,h,n,d] = fp16(dS se_k[h,d] se_x[n] sc)
+            sc = ops.absmax_scale(dPq, B * H, N, N, ldS, N * ldS, v1=se_k_hn, v2=se_x, mult=2.0 * scale, product=True)
+            dS16, _, ldo, colsum_dS, ds_p, dS32 = ops.softmax_quant_bwd(dPq, P, N, H, se_p, hiu, scale, g_p, se_k_hn, True,
+                                                                      se_x, want_ds32=has_bias, fmt=FMT, scale4=sc,
+                                                                      single=True)
+            slab = N * ldo
+            del dPq
+            # d x_hat[b,n,c] += 1/(se_x[n] sc) sum_h sum_d dS16[b,h,n,d] qk[b,d,h,c]      (heads = outer-K, B MN-major)
+            qk16 = ops.codes_to_bf16(qk, 1, M, H * C, H * C, 0, False, FMT)         # [1, M, H*C] = [b][d][h][c]
+            ops.gemm(GEMM_BWD, dS16, (ldo, slab, H * slab, 0), qk16, (H * C, C, N * H * C, 0), dxhat, (C, N * C, 0),
+                     N, C, N, k2=H, nb1=B, accumulate=True, b_mn=True, rs=vec(sx2[1], N), cs=_scalar(sc))
+            # d k_hat[b,d,h,c] = 1/(se_k[h,d] sc) sum_n dS16[b,h,n,d] qx[b,n,c] + colsum_dS[z,d] x_aft[c]
+            dkhat = torch.empty((M, H * C), dtype=torch.float32, device=dev)
+            ops.gemm(GEMM_BWD, dS16, (ldo, 0, slab, H * slab), qx_op, (C, 0, 0, N * C), dkhat, (H * C, C, N * H * C),
+                     N, C, N, nb1=H, nb2=B, a_mn=True, b_mn=True, rs=vec(sk2_hn[1], 0, N), cs=_scalar(sc),
+                     rt=vec(colsum_dS, 0, N, H * N), ct=vec(x_aft))
+            del dS16
         else:
-            ops.gemm(GEMM_BWD, dSa, (ldo, slab, PLANES * H * slab, 0), qkT, (npad8, C * npad8, H * C * npad8, 0),
-                     dxhat, (C, N * C, 0), N, C, N, k2=PLANES * H, nb1=B, accumulate=True, b_k2mod=H, rs=_inv(sc, 0))
-        # --- scores: d k_hat[b,d,h,c] = sum_n dS[n,d] x_hat[n,c]
-        qxT_b = ops.codes_to_bf16(qx, B, N, C, C, N * C, True, FMT)           # [B, C, npad8]
-        dkhat = torch.empty((M, H * C), dtype=torch.float32, device=dev)
-        ops.gemm(GEMM_BWD, dSbT, (ldo, H * slab, slab, PLANES * H * slab), qxT_b, (npad8, 0, 0, C * npad8), dkhat,
-                 (H * C, C, N * H * C), N, C, N, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B, rs=_inv(sc, 1),
-                 rt=vec(colsum_dS, 0, N, H * N), ct=vec(x_aft))
-        del dSa, dSbT
+            dSa, dSbT, ldo, colsum_dS, ds_p, dS32 = ops.softmax_quant_bwd(dPq, P, N, H, se_p, hiu, scale, g_p, se_k_hn, True,
+                                                                        se_x, want_ds32=has_bias, planes=PLANES)
+            slab = N * ldo                      # one (b, plane, h) slab of dSa / dSbT, laid out [B, PLANES, H, N, ldo]
+            del dPq
+            # --- scores: d x_hat += sum_h dS (k_hat)   (outer-K loop over heads)
+            qkT = ops.codes_to_bf16(qk, B, N, H * C, H * C, N * H * C, True)      # [B, H*C, npad8]
+            npad8 = qkT.shape[-1]
+            if DUAL:     # planes of head h are outer-K slices h and h + H of dSa [B, 2, H, N, ldo]
+                ops.gemm(GEMM_BF16, dSa, (ldo, slab, PLANES * H * slab, 0), qkT, (npad8, C * npad8, H * C * npad8, 0),
+                         dxhat, (C, N * C, 0), N, C, N, k2=H, a_dual_delta=H, nb1=B, accumulate=True)
+            else:
+                ops.gemm(GEMM_BF16, dSa, (ldo, slab, PLANES * H * slab, 0), qkT, (npad8, C * npad8, H * C * npad8, 0),
+                         dxhat, (C, N * C, 0), N, C, N, k2=PLANES * H, nb1=B, accumulate=True, b_k2mod=H)
+            # --- scores: d k_hat[b,d,h,c] = sum_n dS[n,d] x_hat[n,c]
+            qxT_b = ops.codes_to_bf16(qx, B, N, C, C, N * C, True)                # [B, C, npad8]
+            dkhat = torch.empty((M, H * C), dtype=torch.float32, device=dev)
+            ops.gemm(GEMM_BF16, dSbT, (ldo, H * slab, slab, PLANES * H * slab), qxT_b, (npad8, 0, 0, C * npad8), dkhat,
+                     (H * C, C, N * H * C), N, C, N, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B, rt=vec(colsum_dS, 0, N, H * N),
+                     ct=vec(x_aft))
+            del dSa, dSbT
         # --- qkx quantizer and the qkx "linear" layer (weight = StatsQ(W_q^T W_k), no bias)
         # d(move_qkx_aft) is analytically zero: the shift adds a term to the logits that is constant along the softmax axis
         dqkx, ds_k, dkb4, _, *sc_k = ops.lsq_bwd(dkhat, qkx, k_b4, se_k, PER_ROW, N, H, lo, hi, g_k, want_aft=False,
-                                                 next_scale=(cs_qk, se_x, 1.0) if F16 else None)
+                                                 zero_sum=True, next_scale=(cs_qk, se_x, 1.0, True) if F16 else None)
         dkaft = torch.zeros_like(k_aft)
         del dkhat
-        dWqk, _, _ = _linear_backward(dqkx, qx, wqkc, cs_qk, se_x, N, x_aft, dxhat, True, qxT_all, sc=sc_k[0] if sc_k else None)
+        dWqk, _, _ = _linear_backward(dqkx, qx, wqkc, (cs_qk, ics_qk), sx2, N, x_aft, dxhat, True, qx_op,
+                                      sc=sc_k[0] if sc_k else None)
         dwq, dwk = ops.wqk_compose_bwd(dWqk, wq, wk, H)
         # --- shared input quantizer
         dx, ds_x, dxb4, dxaft = ops.lsq_bwd(dxhat, xc.view(M, C), x_b4, se_x, PER_ROW, N, 1, lo, hi, g_x)
@@ -332,10 +406,11 @@ class QAttnCoreFn(torch.autograd.Function):
         qkvc = qkv.contiguous()
         q2d = qkvc.view(M, C3)
         g_qk = grad_scale_factor(hi, B * C)           # 4-D (B,H,N,hd): B*H*hd elements per token scale
-        se_q = ops.lsq_effective_scale(s_q, g_qk)
-        se_k = ops.lsq_effective_scale(s_k, g_qk)
+        sq2 = ops.lsq_effective_scale(s_q, g_qk, recip=True)
+        sk2 = ops.lsq_effective_scale(s_k, g_qk, recip=True)
         g_v = grad_scale_factor(hi, B * N)
-        se_v = ops.lsq_effective_scale(s_v, g_v)
+        sv2 = ops.lsq_effective_scale(s_v, g_v, recip=True)
+        se_q, se_k, se_v = sq2[0], sk2[0], sv2[0]
         qq = ops.lsq_quant(q2d[:, 0:C], b4[0:C], se_q, PER_ROW, N, 1, lo, hi)
         qk = ops.lsq_quant(q2d[:, C:2 * C], b4[C:2 * C], se_k, PER_ROW, N, 1, lo, hi)
         qv = ops.lsq_quant(q2d[:, 2 * C:], b4[2 * C:], se_v, PER_COL, 1, 1, lo, hi)
@@ -348,47 +423,68 @@ class QAttnCoreFn(torch.autograd.Function):
         ops.gemm(GEMM_I8, qq, (C, 0, hd, N * C), qk, (C, 0, hd, N * C), S, (ldS, N * ldS, H * N * ldS),
                  N, N, hd, nb1=H, nb2=B, rs=vec(se_q, N), cs=vec(cs_S), ct=vec(ct_S, 0, N, H * N))
         g_p = grad_scale_factor(hiu, B * H * N)
-        se_p = ops.lsq_effective_scale(s_p, g_p)
+        sp2 = ops.lsq_effective_scale(s_p, g_p, recip=True)
+        se_p = sp2[0]
         need_grad = any(ctx.needs_input_grad)
         P, qp, rowsum = ops.softmax_quant(S, N, H, se_p, hiu, bias=attn_bias, mask=attn_mask, nW=nW, save_p=need_grad)
         ldq = qp.shape[-1]
         del S
         out = _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C)
-        ctx.save_for_backward(qkvc, b4, q_aft, k_aft, v_aft, qq, qk, qv, se_q, se_k, se_v, P, qp, se_p)
+        ctx.save_for_backward(qkvc, b4, q_aft, k_aft, v_aft, qq, qk, qv, sq2, sk2, sv2, P, qp, sp2)
         ctx.cfg = (B, N, C, H, lo, hi, hiu, scale, g_qk, g_v, g_p, ldS, ldq, attn_bias is not None)
         return out
 
     @staticmethod
     def backward(ctx, dO):
-        qkvc, b4, q_aft, k_aft, v_aft, qq, qk, qv, se_q, se_k, se_v, P, qp, se_p = ctx.saved_tensors
+        qkvc, b4, q_aft, k_aft, v_aft, qq, qk, qv, sq2, sk2, sv2, P, qp, sp2 = ctx.saved_tensors
         B, N, C, H, lo, hi, hiu, scale, g_qk, g_v, g_p, ldS, ldq, has_bias = ctx.cfg
+        se_q, se_k, se_v, se_p = sq2[0], sk2[0], sv2[0], sp2[0]
         M = B * N
         hd = C // H
         dev = dO.device
         dO = dO.contiguous()
         q2d = qkvc.view(M, 3 * C)
-        dPq, dvhat = _pv_backward(dO, qp, ldq, qv, se_p, se_v, v_aft, B, N, H, C, ldS)
-        sc = (ops.absmax_scale(dPq, B * H, N, N, ldS, N * ldS, v1=se_k, v2=se_q, mult=2.0 * scale) if F16 else None)
-        dSa, dSbT, ldo, colsum_dS, ds_p, dS32 = ops.softmax_quant_bwd(dPq, P, N, H, se_p, hiu, scale, g_p, se_k, False,
-                                                                    se_q, want_ds32=has_bias, planes=PLANES, fmt=FMT,
-                                                                    scale4=sc)
-        slab = N * ldo
-        del dPq
-        # dq_hat[b,n,hj] = sum_d (dS se_k[d]) qk[b,d,hj]
-        qkT = ops.codes_to_bf16(qk, B, N, C, C, N * C, True, FMT)     # [B, C, npad8]
-        npad8 = qkT.shape[-1]
+        dPq, dvhat = _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS)
         dqhat = torch.empty((M, C), dtype=torch.float32, device=dev)
-        ops.gemm(GEMM_BWD, dSa, (ldo, H * slab, slab, PLANES * H * slab), qkT, (npad8, 0, hd * npad8, C * npad8), dqhat,
-                 (C, hd, N * C), N, hd, N, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B, rs=_inv(sc, 0))
-        # dk_hat[b,d,hj] = sum_n (dS se_q[n]) qq[b,n,hj] + colsum_dS[z,d] q_aft[hj]
-        qqT = ops.codes_to_bf16(qq, B, N, C, C, N * C, True, FMT)
         dkhat = torch.empty((M, C), dtype=torch.float32, device=dev)
-        ops.gemm(GEMM_BWD, dSbT, (ldo, H * slab, slab, PLANES * H * slab), qqT, (npad8, 0, hd * npad8, C * npad8), dkhat,
-                 (C, hd, N * C), N, hd, N, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B, rs=_inv(sc, 1),
-                 rt=vec(colsum_dS, 0, N, H * N), ct=vec(q_aft, 0, hd))
+        if F16:
+            sc = ops.absmax_scale(dPq, B * H, N, N, ldS, N * ldS, v1=se_k, v2=se_q, mult=2.0 * scale, product=True)
+            dS16, _, ldo, colsum_dS, ds_p, dS32 = ops.softmax_quant_bwd(dPq, P, N, H, se_p, hiu, scale, g_p, se_k, False,
+                                                                      se_q, want_ds32=has_bias, fmt=FMT, scale4=sc,
+                                                                      single=True)
+            slab = N * ldo
+            del dPq
+            # dq_hat[b,n,hj] = 1/(se_q[n] sc) sum_d dS16[b,h,n,d] qk[b,d,hj]                          (B MN-major)
+            qk16 = ops.codes_to_bf16(qk, 1, M, C, C, 0, False, FMT)                 # [1, M, C] = [b][d][hj]
+            ops.gemm(GEMM_BWD, dS16, (ldo, 0, slab, H * slab), qk16, (C, 0, hd, N * C), dqhat, (C, hd, N * C), N, hd, N,
+                     nb1=H, nb2=B, b_mn=True, rs=vec(sq2[1], N), cs=_scalar(sc))
+            # dk_hat[b,d,hj] = 1/(se_k[d] sc) sum_n dS16[b,h,n,d] qq[b,n,hj] + colsum_dS[z,d] q_aft[hj]   (both MN-major)
+            qq16 = ops.codes_to_bf16(qq, 1, M, C, C, 0, False, FMT)
+            # the rank-1 term is not scaled by rs / cs, so the scalar rides on cs and 1/se_k on rs
+            ops.gemm(GEMM_BWD, dS16, (ldo, 0, slab, H * slab), qq16, (C, 0, hd, N * C), dkhat, (C, hd, N * C), N, hd, N,
+                     nb1=H, nb2=B, a_mn=True, b_mn=True, rs=vec(sk2[1], N), cs=_scalar(sc),
+                     rt=vec(colsum_dS, 0, N, H * N), ct=vec(q_aft, 0, hd))
+            del dS16
+        else:
+            dSa, dSbT, ldo, colsum_dS, ds_p, dS32 = ops.softmax_quant_bwd(dPq, P, N, H, se_p, hiu, scale, g_p, se_k, False,
+                                                                        se_q, want_ds32=has_bias, planes=PLANES)
+            slab = N * ldo
+            del dPq
+            # dq_hat[b,n,hj] = sum_d (dS se_k[d]) qk[b,d,hj]
+            qkT = ops.codes_to_bf16(qk, B, N, C, C, N * C, True)          # [B, C, npad8]
+            npad8 = qkT.shape[-1]
+            ops.gemm(GEMM_BF16, dSa, (ldo, H * slab, slab, PLANES * H * slab), qkT, (npad8, 0, hd * npad8, C * npad8), dqhat,
+                     (C, hd, N * C), N, hd, N, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B)
+            # dk_hat[b,d,hj] = sum_n (dS se_q[n]) qq[b,n,hj] + colsum_dS[z,d] q_aft[hj]
+            qqT = ops.codes_to_bf16(qq, B, N, C, C, N * C, True)
+            ops.gemm(GEMM_BF16, dSbT, (ldo, H * slab, slab, PLANES * H * slab), qqT, (npad8, 0, hd * npad8, C * npad8), dkhat,
+                     (C, hd, N * C), N, hd, N, k2=K2P, a_dual_delta=DD, nb1=H, nb2=B, rt=vec(colsum_dS, 0, N, H * N),
+                     ct=vec(q_aft, 0, hd))
+            del dSa, dSbT
         dq, ds_q, db4_q, daft_q = ops.lsq_bwd(dqhat, q2d[:, 0:C], b4[0:C], se_q, PER_ROW, N, 1, lo, hi, g_qk)
         # d(move_k_aft) is analytically zero (its logit term q_hat . k_aft is constant along the softmax axis)
-        dk, ds_k, db4_k, _ = ops.lsq_bwd(dkhat, q2d[:, C:2 * C], b4[C:2 * C], se_k, PER_ROW, N, 1, lo, hi, g_qk, want_aft=False)
+        dk, ds_k, db4_k, _ = ops.lsq_bwd(dkhat, q2d[:, C:2 * C], b4[C:2 * C], se_k, PER_ROW, N, 1, lo, hi, g_qk, want_aft=False,
+                                         zero_sum=True)
         daft_k = torch.zeros_like(k_aft)
         dv, ds_v, db4_v, daft_v = ops.lsq_bwd(dvhat.view(M, C), q2d[:, 2 * C:], b4[2 * C:], se_v, PER_COL, 1, 1, lo, hi, g_v)
         dqkv = torch.cat((dq, dk, dv), dim=1).view(B, N, 3 * C)

@@ -5,6 +5,7 @@ Tolerance: BASELINE.json asks for <= 1e-3 relative on outputs, logits, loss and 
 tighter 1e-4 on outputs and 1e-3 on gradients (norm-wise relative error ||a-b||/||b||). Gradients that are
 analytically zero in the reference (shift added to an operand whose contribution cancels in softmax:
 move_k_aft / move_qkx_aft) are checked against an absolute bound instead."""
+import os
 from functools import partial
 
 import pytest
@@ -38,10 +39,21 @@ def load_params(mod, g):
     return mod
 
 
+REPORT = os.environ.get("OFQ_GRAD_REPORT")      # diagnostic: append "<rel err> <abs/gmax> <name>" lines instead of asserting
+
+
 def check_grads(named_params, g, sampled=False):
     params = dict(named_params)
     gmax = max(v.abs().max().item() for k, v in g.items() if k.startswith("grad."))
     n = 0
+    if REPORT:
+        with open(REPORT, "a") as fh:
+            fh.write(f"# {os.environ.get('PYTEST_CURRENT_TEST', '')}\n")
+            for k, ref in g.items():
+                if k.startswith("grad."):
+                    mine = params[k[5:]].grad.detach().cpu()
+                    fh.write(f"{rel_err(mine, ref):.2e} {(mine - ref).abs().max().item() / gmax:.2e} {k[5:]}\n")
+        return 1
     for k, ref in g.items():
         if not k.startswith("grad."):
             continue
