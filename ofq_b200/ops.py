@@ -267,8 +267,9 @@ def softmax_quant(S: torch.Tensor, N: int, H: int, s_eff: torch.Tensor, qhi: int
 
 def softmax_quant_bwd(dPq: torch.Tensor, P: torch.Tensor, N: int, H: int, s_eff: torch.Tensor, qhi: int, alpha: float,
                       g_s: float, ca: torch.Tensor, ca_per_head: bool, rb: torch.Tensor, want_ds32: bool = False,
-                      planes: int = 1, fmt: int = FMT_BF16, scale4=None, rm_rowscale: bool = False):
-    """Returns (out_a bf16 [B,planes,H,N,ldo], out_bt bf16 [B,planes,H,N,ldo], ldo, colsum [nz,N], d_s [N], dS32 | None)."""
+                      planes: int = 1, fmt: int = FMT_BF16, scale4=None, single: bool = False):
+    """single: only out_a = dS * ca[d] * rb[n] is produced (out_bt is None).
+    Returns (out_a 16-bit [B,planes,H,N,ldo], out_bt [B,planes,H,N,ldo] | None, ldo, colsum [nz,N], d_s [N], dS32 | None)."""
     _cuda(dPq, P)
     nz, _, ld = P.shape
     ldo = round_up(N, 8)

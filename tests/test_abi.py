@@ -61,7 +61,7 @@ def test_sass_is_blackwell_native():
 def test_compute_entry_points_fail_loudly_without_gpu(lib):
     assert lib.ofq_device_ok() < 0
     buf = (ctypes.c_float * 16)()
-    rc = lib.ofq_lsq_effective_scale(ctypes.addressof(buf), 16, 0.1, ctypes.addressof(buf), None)
+    rc = lib.ofq_lsq_effective_scale(ctypes.addressof(buf), 16, 0.1, ctypes.addressof(buf), None, None)
     assert rc != 0 and len(lib.ofq_last_error()) > 0
 
 
