@@ -105,87 +105,133 @@ __device__ __forceinline__ int lsq_code(float x, float b4, float s, float qlo, f
     return (int)rintf(v);
 }
 
-template <bool VEC>
+// Exact code with a cheap quotient: v~ = a * rcp(s) is within ~3 ulp of the IEEE quotient a / s, so rint(clamp(.)) can
+// differ from the reference only when a rounding boundary k + 1/2 lies inside those ulps. |v| <= 128 wherever the clamp
+// does not decide (codes are int8), so 3 ulp <= 4.6e-5 < 2e-4: only when v~ is within 2e-4 of a half-integer (about one
+// element in 2500) the IEEE division is evaluated. The elementwise kernels are instruction-bound, not HBM-bound, with a
+// full division per element.
+__device__ __forceinline__ float rcp_approx(float s) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(r) : "f"(s));
+    return r;
+}
+__device__ __forceinline__ int lsq_code_fast(float x, float b4, float s, float inv_s, float qlo, float qhi) {
+    const float a = __fadd_rn(x, b4);
+    const float v = __fmul_rn(a, inv_s);
+    float r = rintf(v);
+    if (fabsf(v - r) > 0.4998f) r = rintf(fminf(fmaxf(__fdiv_rn(a, s), qlo), qhi));
+    return __float2int_rn(fminf(fmaxf(r, qlo), qhi));      // rint(clamp(v)) == clamp(rint(v)) for integer bounds
+}
+// {a, b, c, d} -> four saturated int8 bytes, a in the lowest byte
+__device__ __forceinline__ uint32_t pack4_i8(int a, int b, int c, int d) {
+    uint32_t hi, r;
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;\n" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;\n" : "=r"(r) : "r"(b), "r"(a), "r"(hi));
+    return r;
+}
+
+// Plan shared by the streaming kernels below: 592 CTAs x 8 warps (32 warps per SM keep ~64 KB of loads in flight); a warp owns ONE 128-column group (one float4 per lane,
+// so per-column vectors are loaded once) and strides over the rows; warps beyond the last whole set of column groups idle.
+constexpr int kStreamCtas = 4 * 148;
+constexpr int kStreamWarps = kStreamCtas * 8;
+struct StreamPlan { uint32_t cg, lanes_rows; };     // column groups per row, row-lanes (= warps per column group)
+__host__ __device__ inline StreamPlan stream_plan(int cols) {
+    StreamPlan p;
+    p.cg = (uint32_t)(cols + 127) / 128;
+    p.lanes_rows = (uint32_t)kStreamWarps / p.cg;
+    return p;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+lsq_quant_vec_kernel(const float* __restrict__ x, uint32_t rows, int cols, long long ldx,
+                     const float* __restrict__ b4, const float* __restrict__ s_eff, uint32_t period,
+                     int nseg, int seg_len, float qlo, float qhi, int8_t* __restrict__ codes, long long ldq) {
+    constexpr int ILP = 4;
+    const uint32_t lane = threadIdx.x & 31;
+    const StreamPlan pl = stream_plan(cols);
+    const uint32_t w = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= pl.cg * pl.lanes_rows) return;
+    const uint32_t g = w % pl.cg, dr = pl.lanes_rows;
+    const int col = (int)(g * 128 + lane * 4);
+    if (col >= cols) return;
+    const float4 b = __ldg(reinterpret_cast<const float4*>(b4 + col));
+    float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), i4 = s4;
+    if (MODE == OFQ_SCALE_PER_COL) {
+        s4 = __ldg(reinterpret_cast<const float4*>(s_eff + col));
+        i4 = make_float4(rcp_approx(s4.x), rcp_approx(s4.y), rcp_approx(s4.z), rcp_approx(s4.w));
+    }
+    const float* sp = s_eff + (nseg == 1 ? 0 : col / seg_len);
+    const uint32_t dn = dr % period;
+    uint32_t n = (w / pl.cg) % period;
+    const float* xp = x + col;
+    int8_t* cp = codes + col;
+    for (uint32_t row = w / pl.cg; row < rows; row += dr * ILP) {
+        float4 xv[ILP];
+        float sv[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            const uint32_t r = row + u * dr;
+            if (r < rows) {
+                xv[u] = __ldg(reinterpret_cast<const float4*>(xp + (long long)r * ldx));
+                if (MODE == OFQ_SCALE_PER_ROW) sv[u] = __ldg(sp + n * nseg);
+            }
+            n += dn;
+            if (n >= period) n -= period;
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            const uint32_t r = row + u * dr;
+            if (r >= rows) break;
+            if (MODE == OFQ_SCALE_PER_ROW) {
+                const float iv = rcp_approx(sv[u]);
+                s4 = make_float4(sv[u], sv[u], sv[u], sv[u]);
+                i4 = make_float4(iv, iv, iv, iv);
+            }
+            const int q0 = lsq_code_fast(xv[u].x, b.x, s4.x, i4.x, qlo, qhi);
+            const int q1 = lsq_code_fast(xv[u].y, b.y, s4.y, i4.y, qlo, qhi);
+            const int q2 = lsq_code_fast(xv[u].z, b.z, s4.z, i4.z, qlo, qhi);
+            const int q3 = lsq_code_fast(xv[u].w, b.w, s4.w, i4.w, qlo, qhi);
+            *reinterpret_cast<uint32_t*>(cp + (long long)r * ldq) = pack4_i8(q0, q1, q2, q3);
+        }
+    }
+}
+
+// Generic (unaligned / odd-sized) path: one element per thread, IEEE division.
 __global__ void __launch_bounds__(256)
 lsq_quant_kernel(const float* __restrict__ x, long long rows, int cols, long long ldx,
                  const float* __restrict__ b4, const float* __restrict__ s_eff, int scale_mode, int period,
                  int nseg, int seg_len, float qlo, float qhi, int8_t* __restrict__ codes, long long ldq) {
-    constexpr int W = VEC ? 4 : 1;
-    constexpr int ITEMS = 2;                                  // independent loads per thread
-    const uint32_t cw = (uint32_t)(cols / W);
-    const uint32_t total = (uint32_t)rows * cw;               // host guarantees < 2^32
-    const uint32_t base = (blockIdx.x * blockDim.x * ITEMS) + threadIdx.x;
-    uint32_t rowv[ITEMS], colv[ITEMS];
-    bool ok[ITEMS];
-    float xv[ITEMS][W];
-#pragma unroll
-    for (int it = 0; it < ITEMS; ++it) {
-        const uint32_t idx = base + it * blockDim.x;
-        ok[it] = idx < total;
-        rowv[it] = ok[it] ? idx / cw : 0;
-        colv[it] = ok[it] ? (idx - rowv[it] * cw) * W : 0;
-        if (VEC) {
-            const float4 t = ok[it] ? __ldg(reinterpret_cast<const float4*>(x + (long long)rowv[it] * ldx + colv[it]))
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-            xv[it][0] = t.x; xv[it][1 % W] = t.y; xv[it][2 % W] = t.z; xv[it][3 % W] = t.w;
-        } else {
-            xv[it][0] = ok[it] ? __ldg(x + (long long)rowv[it] * ldx + colv[it]) : 0.f;
-        }
-    }
-#pragma unroll
-    for (int it = 0; it < ITEMS; ++it) {
-        if (!ok[it]) continue;
-        const uint32_t row = rowv[it], col = colv[it];
-        float bv[W], sv[W];
-        if (VEC) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(b4 + col));
-            bv[0] = b.x; bv[1 % W] = b.y; bv[2 % W] = b.z; bv[3 % W] = b.w;
-        } else {
-            bv[0] = __ldg(b4 + col);
-        }
-        if (scale_mode == OFQ_SCALE_PER_ROW) {
-            const float s = __ldg(s_eff + (row % (uint32_t)period) * nseg + col / (uint32_t)seg_len);
-#pragma unroll
-            for (int e = 0; e < W; ++e) sv[e] = s;
-        } else if (VEC) {
-            const float4 s = __ldg(reinterpret_cast<const float4*>(s_eff + col));
-            sv[0] = s.x; sv[1 % W] = s.y; sv[2 % W] = s.z; sv[3 % W] = s.w;
-        } else {
-            sv[0] = __ldg(s_eff + col);
-        }
-        int q[W];
-#pragma unroll
-        for (int e = 0; e < W; ++e) q[e] = lsq_code(xv[it][e], bv[e], sv[e], qlo, qhi);
-        if (VEC) {
-            const uint32_t packed = (uint32_t)(q[0] & 0xff) | ((uint32_t)(q[1 % W] & 0xff) << 8) |
-                                    ((uint32_t)(q[2 % W] & 0xff) << 16) | ((uint32_t)(q[3 % W] & 0xff) << 24);
-            *reinterpret_cast<uint32_t*>(codes + (long long)row * ldq + col) = packed;
-        } else {
-            codes[(long long)row * ldq + col] = (int8_t)q[0];
-        }
-    }
+    const uint32_t total = (uint32_t)rows * (uint32_t)cols;   // host guarantees < 2^32
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const uint32_t row = idx / (uint32_t)cols, col = idx - row * (uint32_t)cols;
+    const float s = scale_mode == OFQ_SCALE_PER_ROW ? __ldg(s_eff + (row % (uint32_t)period) * nseg + col / (uint32_t)seg_len)
+                                                    : __ldg(s_eff + col);
+    codes[(long long)row * ldq + col] = (int8_t)lsq_code(__ldg(x + (long long)row * ldx + col), __ldg(b4 + col), s, qlo, qhi);
 }
 
 // ------------------------------------------------------------------------------------------- LSQ backward
 // Block = 8 warps, a contiguous range of rows; a warp walks its rows, lanes own fixed float4 columns of the
 // current 512-column chunk so that column partial sums stay in registers; per-(row,segment) partial sums
 // are reduced with shuffles once per row and chunk. workspace = rowpart[rows*nseg] | colpart[nblk][3][cols].
-constexpr int kBwdChunk = 512;   // columns per register-resident chunk (4 float4 per lane)
+constexpr int kBwdChunkMax = 512;   // columns per register-resident chunk: NP float4 per lane, NP = 3 (384) or 4 (512)
 constexpr int kBwdMinRowsPerBlock = 32;
-constexpr int kBwdMaxBlocks = 4 * 148;   // two resident CTAs per SM, two waves; rows per CTA amortise the column fold
+constexpr int kBwdMaxBlocks = 2 * 148;   // two resident CTAs per SM, one wave: many rows per CTA amortise the column fold
 
 __host__ __device__ inline long long lsq_bwd_nblk(long long rows) {
     const long long n = (rows + kBwdMinRowsPerBlock - 1) / kBwdMinRowsPerBlock;
     return n < kBwdMaxBlocks ? n : kBwdMaxBlocks;
 }
 
-template <int scale_mode>
+template <int scale_mode, int NP>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)
 lsq_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
                long long rows, int cols, const float* __restrict__ b4, const float* __restrict__ s_eff,
                int period, int nseg, int seg_len, float qlo, float qhi,
                float* __restrict__ dx, long long lddx, float* __restrict__ rowpart,
                float* __restrict__ colpart, float* __restrict__ blockmax) {
+    constexpr int kBwdChunk = NP * 128;
     __shared__ float col_s[3][kBwdChunk];     // index [v][(p * 4 + e) * 32 + lane]: conflict-free for the fold
     __shared__ float bmax_s[kWarpsPerBlock];
     float tmax = 0.f;                         // max |dx| seen by this thread (fp16 range scale of the next GEMM operand)
@@ -198,13 +244,13 @@ lsq_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __rest
     for (int cbase = 0; cbase < cols; cbase += kBwdChunk) {
         for (int i = threadIdx.x; i < 3 * kBwdChunk; i += blockDim.x) (&col_s[0][0])[i] = 0.f;
         __syncthreads();
-        constexpr int NS = scale_mode == OFQ_SCALE_PER_COL ? 4 : 1;    // per-column scale gradient accumulators
-        float a_aft[4][4], a_b4[4][4], a_s[NS][4];
-        float4 b4v[4], is4v[NS];       // is4v: reciprocal per-column scales (the backward needs no bit-exact division)
-        int segv[4];
-        bool okv[4];
+        constexpr int NS = scale_mode == OFQ_SCALE_PER_COL ? NP : 1;    // per-column scale gradient accumulators
+        float a_aft[NP][4], a_b4[NP][4], a_s[NS][4];
+        float4 b4v[NP], is4v[NS];       // is4v: reciprocal per-column scales (the backward needs no bit-exact division)
+        int segv[NP];
+        bool okv[NP];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
+        for (int p = 0; p < NP; ++p) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) a_aft[p][e] = a_b4[p][e] = 0.f;
             const int col = cbase + p * 128 + lane * 4;
@@ -226,17 +272,19 @@ lsq_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __rest
             const float* xr = x + row * ldx + cbase + lane * 4;
             float* dxr = dx + row * lddx + cbase + lane * 4;
             const long long srow = (row % period) * nseg;
-            float4 g4[4], x4[4];
+            float4 g4[NP], x4[NP];
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {          // all loads of the row first: 8 x 16 B in flight per lane
+            for (int p = 0; p < NP; ++p) {          // all loads of the row first: 8 x 16 B in flight per lane
                 if (okv[p]) {
                     g4[p] = __ldg(reinterpret_cast<const float4*>(dyr + p * 128));
                     x4[p] = __ldg(reinterpret_cast<const float4*>(xr + p * 128));
                 }
             }
-            float part[4] = {0.f, 0.f, 0.f, 0.f};
+            float part[NP];
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
+            for (int p = 0; p < NP; ++p) part[p] = 0.f;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
                 if (!okv[p]) continue;
                 float sv[4];
                 if (scale_mode == OFQ_SCALE_PER_ROW) {
@@ -267,7 +315,7 @@ lsq_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __rest
                 for (int sg = seg_first; sg <= seg_last; ++sg) {
                     float v = 0.f;
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) v += (segv[p] == sg) ? part[p] : 0.f;
+                    for (int p = 0; p < NP; ++p) v += (segv[p] == sg) ? part[p] : 0.f;
                     v = warp_sum(v);
                     if (lane == 0) {
                         float* dst = rowpart + row * nseg + sg;
@@ -279,7 +327,7 @@ lsq_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __rest
         }
         // fold the 8 warps' column partials (lane-major layout: one bank per lane)
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
+        for (int p = 0; p < NP; ++p) {
             if (okv[p]) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -339,6 +387,105 @@ scale_from_blockmax_kernel(const float* __restrict__ blockmax, int nblk, const f
         pow2_scale_pair(a * m1 * (product ? m2 : 1.f) * mult, out4 + 0, out4 + 1);
         pow2_scale_pair(a * m2 * (product ? m1 : 1.f) * mult, out4 + 2, out4 + 3);
     }
+}
+
+// Streaming variant (stream_plan): a warp owns one 128-column group and strides over the rows, so the column sums stay in
+// 12 registers and are written once per warp (no shared-memory fold, no barrier), four rows (8 x 16 B per lane) are in
+// flight, and the per-(row, segment) scale-gradient partial of a row is one value per column group.
+// workspace = rowpart[gps][rows*nseg] | colpart[lanes_rows][3][cols] | warpmax[cg * lanes_rows], gps = groups per segment.
+__host__ __device__ inline bool lsq_bwd_streaming(int cols, int nseg) {
+    const int seg_len = cols / nseg;
+    return cols % 4 == 0 && (nseg == 1 || seg_len % 128 == 0) && (cols + 127) / 128 <= kStreamWarps / 8;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 4)
+lsq_bwd_stream_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
+                      uint32_t rows, int cols, const float* __restrict__ b4, const float* __restrict__ s_eff,
+                      uint32_t period, int nseg, int seg_len, float qlo, float qhi,
+                      float* __restrict__ dx, long long lddx, float* __restrict__ rowpart,
+                      float* __restrict__ colpart, float* __restrict__ warpmax) {
+    constexpr int ILP = 2;
+    const uint32_t lane = threadIdx.x & 31;
+    const StreamPlan pl = stream_plan(cols);
+    const uint32_t w = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= pl.cg * pl.lanes_rows) return;
+    const uint32_t g = w % pl.cg, rl = w / pl.cg, dr = pl.lanes_rows;
+    const int col = (int)(g * 128 + lane * 4);
+    const bool act = col < cols;
+    const float4 b = act ? __ldg(reinterpret_cast<const float4*>(b4 + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 i4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (MODE == OFQ_SCALE_PER_COL && act) {
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(s_eff + col));
+        i4 = make_float4(1.0f / s4.x, 1.0f / s4.y, 1.0f / s4.z, 1.0f / s4.w);
+    }
+    // a 128-column group lies inside one segment (seg_len % 128 == 0, or a single segment)
+    const int seg = nseg == 1 ? 0 : (int)(g * 128) / seg_len;
+    const uint32_t gi = nseg == 1 ? g : g - (uint32_t)seg * (uint32_t)(seg_len / 128);      // group index inside the segment
+    float* rp = rowpart + (long long)gi * rows * nseg + seg;
+    const uint32_t dn = dr % period;
+    uint32_t n = rl % period;
+    float aft[4] = {0.f, 0.f, 0.f, 0.f}, ab4[4] = {0.f, 0.f, 0.f, 0.f}, as[4] = {0.f, 0.f, 0.f, 0.f};
+    float tmax = 0.f;
+    for (uint32_t row = rl; row < rows; row += dr * ILP) {
+        float4 g4[ILP], x4[ILP];
+        float isv[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            const uint32_t r = row + u * dr;
+            g4[u] = x4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            isv[u] = 1.f;
+            if (r < rows) {
+                if (act) {
+                    g4[u] = __ldg(reinterpret_cast<const float4*>(dy + (long long)r * lddy + col));
+                    x4[u] = __ldg(reinterpret_cast<const float4*>(x + (long long)r * ldx + col));
+                }
+                if (MODE == OFQ_SCALE_PER_ROW) isv[u] = __ldg(s_eff + n * nseg + seg);
+            }
+            n += dn;
+            if (n >= period) n -= period;
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u) {
+            const uint32_t r = row + u * dr;
+            if (r >= rows) break;
+            if (MODE == OFQ_SCALE_PER_ROW) {
+                const float is = 1.0f / isv[u];
+                i4 = make_float4(is, is, is, is);
+            }
+            const float gg[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
+            const float xx[4] = {x4[u].x, x4[u].y, x4[u].z, x4[u].w};
+            const float bb[4] = {b.x, b.y, b.z, b.w};
+            const float ii[4] = {i4.x, i4.y, i4.z, i4.w};
+            float o[4], part = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float v = (xx[e] + bb[e]) * ii[e];
+                const bool inside = (v >= qlo) && (v <= qhi);
+                const float q = rintf(fminf(fmaxf(v, qlo), qhi));
+                const float t = gg[e] * (inside ? (q - v) : q);
+                o[e] = inside ? gg[e] : 0.f;
+                tmax = fmaxf(tmax, fabsf(o[e]));
+                aft[e] += gg[e];
+                ab4[e] += o[e];
+                if (MODE == OFQ_SCALE_PER_ROW) part += t; else as[e] += t;
+            }
+            if (act) *reinterpret_cast<float4*>(dx + (long long)r * lddx + col) = make_float4(o[0], o[1], o[2], o[3]);
+            if (MODE == OFQ_SCALE_PER_ROW) {
+                part = warp_sum(part);
+                if (lane == 0) rp[(long long)r * nseg] = part;
+            }
+        }
+    }
+    if (act) {
+        float* cp = colpart + (long long)rl * 3 * cols + col;
+        *reinterpret_cast<float4*>(cp) = make_float4(aft[0], aft[1], aft[2], aft[3]);
+        *reinterpret_cast<float4*>(cp + cols) = make_float4(ab4[0], ab4[1], ab4[2], ab4[3]);
+        *reinterpret_cast<float4*>(cp + 2 * cols) = make_float4(as[0], as[1], as[2], as[3]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    if (lane == 0) warpmax[w] = tmax;
 }
 
 // Deterministic tree reductions of the partials: block = 32 outputs x 8 slices of the reduction axis.
@@ -532,46 +679,56 @@ grad_prep_kernel(const float* __restrict__ x, int R, int C, long long ldx, long 
 // max|v1| / max|v2| and `mult` (analytic bounds of a later product), then turned into power-of-two scales that place
 // the bound in [2^14, 2^15): out4 = {sc_c, 1/sc_c, sc_r, 1/sc_r}.  Last-block-done reduction over a persistent
 // workspace (uint32 counter at ws[0], self-resetting; partials from ws[2]).
-constexpr int kAbsmaxMaxBlocks = 148 * 8;
+constexpr int kAbsmaxMaxBlocks = kStreamCtas;
 
 __global__ void __launch_bounds__(256)
-absmax_scale_kernel(const float* __restrict__ x, uint32_t nquads, int C, uint32_t ldq, uint32_t R,
-                    const float* __restrict__ cs, const float* __restrict__ rs, int rs_period,
+absmax_scale_kernel(const float* __restrict__ x, uint32_t rows, int C, long long ldx,
+                    const float* __restrict__ cs, const float* __restrict__ rs, uint32_t period,
                     const float* __restrict__ v1, int n1, const float* __restrict__ v2, int n2, float mult,
                     int product, float* __restrict__ out4, unsigned int* __restrict__ ws) {
-    // x is walked as a flat array of float4 quads, ldq quads per row (rows are densely packed: batch stride = R * ld)
+    // rows are densely packed (batch stride = R * ld); stream_plan: a warp owns one 128-column group and strides over rows
     __shared__ float red[2][8];
     __shared__ bool last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float mc = 0.f, mr = 0.f;
     constexpr int ILP = 4;
-    const uint32_t stride = gridDim.x * blockDim.x;             // host guarantees nquads + ILP * stride < 2^32
-    for (uint32_t q0 = blockIdx.x * blockDim.x + threadIdx.x; q0 < nquads; q0 += stride * ILP) {
-        float4 f[ILP];
-        bool ok[ILP];
-#pragma unroll
-        for (int u = 0; u < ILP; ++u) {
-            const uint32_t q = q0 + u * stride;
-            ok[u] = q < nquads;
-            f[u] = ok[u] ? __ldg(reinterpret_cast<const float4*>(x) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const StreamPlan pl = stream_plan(C);
+    const uint32_t w = blockIdx.x * 8 + warp;
+    const int c = (int)((w % pl.cg) * 128 + lane * 4);
+    if (w < pl.cg * pl.lanes_rows && c < C) {
+        const uint32_t dr = pl.lanes_rows, dn = dr % period;
+        uint32_t n = (w / pl.cg) % period;
+        float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (cs) {                                                              // host guarantees C % 4 == 0 with cs
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(cs + c));
+            s4 = make_float4(fabsf(t4.x), fabsf(t4.y), fabsf(t4.z), fabsf(t4.w));
         }
+        // pitch padding is not data: columns >= C of the last quad are masked
+        const float k1 = c + 1 < C ? 1.f : 0.f, k2 = c + 2 < C ? 1.f : 0.f, k3 = c + 3 < C ? 1.f : 0.f;
+        const float* xp = x + c;
+        for (uint32_t row = w / pl.cg; row < rows; row += dr * ILP) {
+            float4 f[ILP];
+            float rsv[ILP];
 #pragma unroll
-        for (int u = 0; u < ILP; ++u) {
-            if (!ok[u]) continue;
-            const uint32_t q = q0 + u * stride;
-            const uint32_t row = q / ldq;
-            const int c = (int)(q - row * ldq) * 4;
-            const float a0 = c < C ? fabsf(f[u].x) : 0.f, a1 = c + 1 < C ? fabsf(f[u].y) : 0.f,
-                        a2 = c + 2 < C ? fabsf(f[u].z) : 0.f, a3 = c + 3 < C ? fabsf(f[u].w) : 0.f;
-            const float m4 = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
-            float mcs = m4;
-            if (cs && c < C) {                                                 // host guarantees C % 4 == 0 with cs
-                const float4 s4 = __ldg(reinterpret_cast<const float4*>(cs + c));
-                mcs = fmaxf(fmaxf(a0 * fabsf(s4.x), a1 * fabsf(s4.y)), fmaxf(a2 * fabsf(s4.z), a3 * fabsf(s4.w)));
+            for (int u = 0; u < ILP; ++u) {
+                const uint32_t r = row + u * dr;
+                f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                rsv[u] = 1.f;
+                if (r < rows) {
+                    f[u] = __ldg(reinterpret_cast<const float4*>(xp + (long long)r * ldx));
+                    if (rs) rsv[u] = fabsf(__ldg(rs + n));
+                }
+                n += dn;
+                if (n >= period) n -= period;
             }
-            const float rsv = rs ? fabsf(__ldg(rs + (row % R) % (uint32_t)rs_period)) : 1.f;
-            mc = fmaxf(mc, product ? mcs * rsv : mcs);
-            mr = fmaxf(mr, m4 * rsv);
+#pragma unroll
+            for (int u = 0; u < ILP; ++u) {
+                const float a0 = fabsf(f[u].x), a1 = fabsf(f[u].y) * k1, a2 = fabsf(f[u].z) * k2, a3 = fabsf(f[u].w) * k3;
+                const float m4 = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+                const float mcs = fmaxf(fmaxf(a0 * s4.x, a1 * s4.y), fmaxf(a2 * s4.z, a3 * s4.w));
+                mc = fmaxf(mc, product ? mcs * rsv[u] : mcs);
+                mr = fmaxf(mr, m4 * rsv[u]);
+            }
         }
     }
 #pragma unroll
@@ -689,6 +846,37 @@ codes_convert_kernel(const int8_t* __restrict__ codes, int R, int C, long long l
     }
 }
 
+// int8 codes -> fp16, same layout (no transpose): 16 codes per thread, no shared memory. The conversion is two byte
+// permutes and one half2 subtraction per pair: fp16 bits 0x6400 | u encode 1024 + u for u in [0, 1023], so with
+// u = code + 128 the value is (1024 + u) - 1152.
+__device__ __forceinline__ uint32_t i8pair_to_f16x2(uint32_t biased, uint32_t sel) {
+    uint32_t h, r;
+    asm("prmt.b32 %0, %1, %2, %3;\n" : "=r"(h) : "r"(biased), "r"(0x64646464u), "r"(sel));
+    asm("sub.rn.f16x2 %0, %1, %2;\n" : "=r"(r) : "r"(h), "r"(0x64806480u));    // 0x6480 = 1152.0
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+codes_to_f16_rowmajor_kernel(const int8_t* __restrict__ codes, uint32_t rows, uint32_t c16, long long ld,
+                             uint16_t* __restrict__ out, long long ld_out, int C) {
+    // c16 = 16-code groups per row; a group past C (pitch padding) is still converted, the caller sizes ld_out for it
+    const uint32_t total = rows * c16;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t row = i / c16, g = i - row * c16;
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(codes + (long long)row * ld + g * 16));
+        const uint32_t in[4] = {w.x ^ 0x80808080u, w.y ^ 0x80808080u, w.z ^ 0x80808080u, w.w ^ 0x80808080u};
+        uint32_t o[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            o[2 * k] = i8pair_to_f16x2(in[k], 0x4140u);       // bytes {b0, 0x64, b1, 0x64}
+            o[2 * k + 1] = i8pair_to_f16x2(in[k], 0x4342u);   // bytes {b2, 0x64, b3, 0x64}
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + (long long)row * ld_out + g * 16);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+}
+
 // out[row][seg] = sum_{c in seg} u[c] * codes[row][c]; one warp per (row, segment).
 __global__ void __launch_bounds__(256)
 codes_rowdot_kernel(const int8_t* __restrict__ codes, long long rows, int cols, long long ld, int nseg,
@@ -762,29 +950,55 @@ extern "C" int ofq_lsq_quant(const float* x, long long rows, int cols, long long
     const bool vec = (cols % 4 == 0) && (seg_len % 4 == 0) && (ldx % 4 == 0) && (ldq % 4 == 0) &&
                      ((uintptr_t)x % 16 == 0) && ((uintptr_t)b4 % 16 == 0) && ((uintptr_t)s_eff % 16 == 0) &&
                      ((uintptr_t)codes % 4 == 0);
-    const long long n = rows * (cols / (vec ? 4 : 1));
-    OFQ_REQUIRE(n < 0xffffffffLL, "ofq_lsq_quant: tensor too large for 32-bit indexing");
-    const unsigned grid = (unsigned)((n + 511) / 512);
-    if (vec)
-        lsq_quant_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, b4, s_eff, scale_mode,
-                                                                      period, nseg, seg_len, (float)qlo, (float)qhi, codes, ldq);
-    else
-        lsq_quant_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, b4, s_eff, scale_mode,
-                                                                       period, nseg, seg_len, (float)qlo, (float)qhi, codes, ldq);
+    OFQ_REQUIRE(rows * (long long)cols < 0x7fffffffLL, "ofq_lsq_quant: tensor too large for 32-bit indexing");
+    if (vec && (cols + 127) / 128 <= kStreamWarps) {
+        if (scale_mode == OFQ_SCALE_PER_ROW)
+            lsq_quant_vec_kernel<OFQ_SCALE_PER_ROW><<<kStreamCtas, 256, 0, (cudaStream_t)stream>>>(
+                x, (uint32_t)rows, cols, ldx, b4, s_eff, (uint32_t)period, nseg, seg_len, (float)qlo, (float)qhi, codes, ldq);
+        else
+            lsq_quant_vec_kernel<OFQ_SCALE_PER_COL><<<kStreamCtas, 256, 0, (cudaStream_t)stream>>>(
+                x, (uint32_t)rows, cols, ldx, b4, s_eff, 1u, nseg, seg_len, (float)qlo, (float)qhi, codes, ldq);
+    } else {
+        const unsigned grid = (unsigned)((rows * cols + 255) / 256);
+        lsq_quant_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, b4, s_eff, scale_mode,
+                                                                period, nseg, seg_len, (float)qlo, (float)qhi, codes, ldq);
+    }
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }
 
+// layout of the partial-sum workspace for either variant
+struct LsqBwdWs { long long rowpart_used, rowpart_n, colslots, nmax; };
+static LsqBwdWs lsq_bwd_ws(long long rows, int cols, int nseg) {
+    LsqBwdWs w;
+    if (lsq_bwd_streaming(cols, nseg)) {
+        const StreamPlan pl = stream_plan(cols);
+        const long long gps = nseg == 1 ? pl.cg : (cols / nseg) / 128;
+        w.rowpart_used = gps * rows * nseg;
+        w.rowpart_n = (w.rowpart_used + 3) / 4 * 4;          // colpart is written with float4 stores
+        w.colslots = pl.lanes_rows;
+        w.nmax = (long long)pl.cg * pl.lanes_rows;
+    } else {
+        w.rowpart_used = w.rowpart_n = rows * nseg;
+        w.colslots = lsq_bwd_nblk(rows);
+        w.nmax = lsq_bwd_nblk(rows);
+    }
+    return w;
+}
+
 extern "C" long long ofq_lsq_bwd_workspace(long long rows, int cols, int nseg) {
-    return rows * nseg + lsq_bwd_nblk(rows) * 3 * cols + lsq_bwd_nblk(rows);
+    if (rows <= 0 || cols <= 0 || nseg <= 0 || cols % nseg) return 0;
+    const LsqBwdWs w = lsq_bwd_ws(rows, cols, nseg);
+    return w.rowpart_n + w.colslots * 3 * cols + w.nmax;
 }
 
 extern "C" int ofq_lsq_bwd_scale(const float* workspace, long long rows, int cols, int nseg, const float* v1, int n1,
                                  const float* v2, int n2, float mult, int product, float* out4, void* stream) {
     OFQ_REQUIRE(workspace && out4 && rows > 0 && cols > 0 && nseg > 0, "ofq_lsq_bwd_scale: bad argument");
     OFQ_CHECK_ARCH();
-    const long long nblk = lsq_bwd_nblk(rows);
-    scale_from_blockmax_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(workspace + rows * nseg + nblk * 3 * cols, (int)nblk,
+    const LsqBwdWs wsl = lsq_bwd_ws(rows, cols, nseg);
+    const long long nblk = wsl.nmax;
+    scale_from_blockmax_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(workspace + wsl.rowpart_n + wsl.colslots * 3 * cols, (int)nblk,
                                                                    v1, n1, v2, n2, mult, product, out4);
     OFQ_CUDA(cudaGetLastError());
     return 0;
@@ -801,15 +1015,34 @@ extern "C" int ofq_lsq_bwd(const float* dy, long long lddy, const float* x, long
     OFQ_REQUIRE((uintptr_t)dy % 16 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)dx % 16 == 0 &&
                 (uintptr_t)b4 % 16 == 0 && (uintptr_t)s_eff % 16 == 0, "ofq_lsq_bwd: pointers must be 16-byte aligned");
     OFQ_CHECK_ARCH();
+    const LsqBwdWs wsl = lsq_bwd_ws(rows, cols, nseg);
     float* rowpart = workspace;
-    float* colpart = workspace + rows * nseg;
-    float* blockmax = colpart + lsq_bwd_nblk(rows) * 3 * cols;
-    if (scale_mode == OFQ_SCALE_PER_ROW)
-        lsq_bwd_kernel<OFQ_SCALE_PER_ROW><<<(unsigned)lsq_bwd_nblk(rows), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-            dy, lddy, x, ldx, rows, cols, b4, s_eff, period, nseg, seg_len, (float)qlo, (float)qhi, dx, lddx, rowpart, colpart, blockmax);
-    else
-        lsq_bwd_kernel<OFQ_SCALE_PER_COL><<<(unsigned)lsq_bwd_nblk(rows), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-            dy, lddy, x, ldx, rows, cols, b4, s_eff, period, nseg, seg_len, (float)qlo, (float)qhi, dx, lddx, rowpart, colpart, blockmax);
+    float* colpart = workspace + wsl.rowpart_n;
+    float* blockmax = colpart + wsl.colslots * 3 * cols;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (lsq_bwd_streaming(cols, nseg)) {
+        OFQ_REQUIRE(rows < 0x7fffffffLL, "ofq_lsq_bwd: too many rows");
+        OFQ_REQUIRE(scale_mode != OFQ_SCALE_PER_ROW || period >= rows || rows % period == 0,
+                    "ofq_lsq_bwd: rows must be a multiple of the scale period");
+        if (scale_mode == OFQ_SCALE_PER_ROW)
+            lsq_bwd_stream_kernel<OFQ_SCALE_PER_ROW><<<kStreamCtas, 256, 0, st>>>(
+                dy, lddy, x, ldx, (uint32_t)rows, cols, b4, s_eff, (uint32_t)period, nseg, seg_len, (float)qlo, (float)qhi, dx, lddx,
+                rowpart, colpart, blockmax);
+        else
+            lsq_bwd_stream_kernel<OFQ_SCALE_PER_COL><<<kStreamCtas, 256, 0, st>>>(
+                dy, lddy, x, ldx, (uint32_t)rows, cols, b4, s_eff, 1u, nseg, seg_len, (float)qlo, (float)qhi, dx, lddx,
+                rowpart, colpart, blockmax);
+        OFQ_CUDA(cudaGetLastError());
+        return 0;
+    }
+    const unsigned grid = (unsigned)lsq_bwd_nblk(rows);
+#define OFQ_LSQ_BWD(MODE, NP)                                                                                          \
+    lsq_bwd_kernel<MODE, NP><<<grid, kWarpsPerBlock * 32, 0, st>>>(dy, lddy, x, ldx, rows, cols, b4, s_eff, period, nseg, \
+                                                                  seg_len, (float)qlo, (float)qhi, dx, lddx, rowpart, colpart, blockmax)
+    const bool np3 = cols % 384 == 0;      // 384-column chunks leave no idle lanes for C = 384 / 1536 / 2304
+    if (scale_mode == OFQ_SCALE_PER_ROW) { if (np3) OFQ_LSQ_BWD(OFQ_SCALE_PER_ROW, 3); else OFQ_LSQ_BWD(OFQ_SCALE_PER_ROW, 4); }
+    else { if (np3) OFQ_LSQ_BWD(OFQ_SCALE_PER_COL, 3); else OFQ_LSQ_BWD(OFQ_SCALE_PER_COL, 4); }
+#undef OFQ_LSQ_BWD
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }
@@ -818,14 +1051,17 @@ extern "C" int ofq_lsq_bwd_finalize(const float* workspace, long long rows, int 
                                     int nseg, float g, float* d_s, float* d_b4, float* d_aft, int zero_sum, void* stream) {
     OFQ_REQUIRE(workspace && rows > 0 && cols > 0, "ofq_lsq_bwd_finalize: bad argument");
     OFQ_CHECK_ARCH();
+    OFQ_REQUIRE(nseg > 0 && cols % nseg == 0, "ofq_lsq_bwd_finalize: bad segment count");
+    const LsqBwdWs wsl = lsq_bwd_ws(rows, cols, nseg);
     const float* rowpart = workspace;
-    const float* colpart = workspace + rows * nseg;
+    const float* colpart = workspace + wsl.rowpart_n;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 gridc((cols + 31) / 32, 3);
-    lsq_bwd_finalize_cols_kernel<<<gridc, 256, 0, st>>>(colpart, cols, lsq_bwd_nblk(rows), scale_mode, g, d_s, d_b4, d_aft, zero_sum);
+    lsq_bwd_finalize_cols_kernel<<<gridc, 256, 0, st>>>(colpart, cols, wsl.colslots, scale_mode, g, d_s, d_b4, d_aft, zero_sum);
     if (d_s && scale_mode == OFQ_SCALE_PER_ROW) {
+        // every partial whose index is congruent to i modulo nscale belongs to scale i (rows is a multiple of period)
         const long long nscale = (long long)(period < rows ? period : rows) * nseg;
-        lsq_bwd_finalize_rows_kernel<<<(unsigned)((nscale + 31) / 32), 256, 0, st>>>(rowpart, rows * nseg, nscale, g, d_s);
+        lsq_bwd_finalize_rows_kernel<<<(unsigned)((nscale + 31) / 32), 256, 0, st>>>(rowpart, wsl.rowpart_used, nscale, g, d_s);
     }
     OFQ_CUDA(cudaGetLastError());
     return 0;
@@ -842,12 +1078,11 @@ extern "C" int ofq_absmax_scale(const float* x, int nb, int R, int C, long long 
     OFQ_REQUIRE(!cs || (C % 4 == 0 && (uintptr_t)cs % 16 == 0), "ofq_absmax_scale: cs needs C % 4 == 0 and 16-byte alignment");
     OFQ_REQUIRE(nb == 1 || bstride == (long long)R * ldx, "ofq_absmax_scale: batches must be densely packed (bstride = R * ldx)");
     OFQ_CHECK_ARCH();
-    if (rs_period <= 0) rs_period = 0x7fffffff;
-    const long long nquads = (long long)nb * R * (ldx / 4);
-    OFQ_REQUIRE(nquads < 0x7fffffffLL, "ofq_absmax_scale: tensor too large for 32-bit indexing");
-    long long grid = (nquads + 256 * 4 - 1) / (256 * 4);
-    if (grid > kAbsmaxMaxBlocks) grid = kAbsmaxMaxBlocks;
-    absmax_scale_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, (uint32_t)nquads, C, (uint32_t)(ldx / 4), (uint32_t)R, cs, rs, rs_period,
+    if (rs_period <= 0 || !rs) rs_period = 0x7fffffff;
+    OFQ_REQUIRE(nb == 1 || rs_period == 0x7fffffff || R % rs_period == 0, "ofq_absmax_scale: R must be a multiple of rs_period when batched");
+    OFQ_REQUIRE((long long)nb * R < 0x7fffffffLL && (C + 127) / 128 <= kStreamWarps, "ofq_absmax_scale: tensor too large");
+    const long long grid = kStreamCtas;
+    absmax_scale_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, (uint32_t)((long long)nb * R), C, ldx, cs, rs, (uint32_t)rs_period,
                                                                          v1, n1, v2, n2, mult, product, out4, (unsigned int*)workspace);
     OFQ_CUDA(cudaGetLastError());
     return 0;
@@ -902,6 +1137,18 @@ extern "C" int ofq_codes_to_16(const int8_t* codes, int nb, int R, int C, long l
     dim3 grid((C + 63) / 64, (R + 63) / 64, nb);
     cudaStream_t st = (cudaStream_t)stream;
     uint16_t* o = (uint16_t*)out;
+    // fast path: fp16, no transpose, batches densely packed on both sides, rows made of whole 16-code groups
+    if (out_fmt == OFQ_FMT_F16 && !transpose && C % 16 == 0 && ld % 16 == 0 && (uintptr_t)codes % 16 == 0 &&
+        (nb == 1 || (bstride == (long long)R * ld && bstride_out == (long long)R * ld_out)) &&
+        (long long)nb * R * (C / 16) < 0x7fffffffLL) {
+        const long long total = (long long)nb * R * (C / 16);
+        long long g1 = (total + 255) / 256;
+        const long long cap = (long long)ofq_num_sms() * 32;
+        if (g1 > cap) g1 = cap;
+        codes_to_f16_rowmajor_kernel<<<(unsigned)g1, 256, 0, st>>>(codes, (uint32_t)((long long)nb * R), (uint32_t)(C / 16), ld, o, ld_out, C);
+        OFQ_CUDA(cudaGetLastError());
+        return 0;
+    }
     if (out_fmt == OFQ_FMT_F16) {
         if (transpose) codes_convert_kernel<true, uint16_t, true><<<grid, 256, 0, st>>>(codes, R, C, ld, bstride, o, ld_out, bstride_out);
         else codes_convert_kernel<false, uint16_t, true><<<grid, 256, 0, st>>>(codes, R, C, ld, bstride, o, ld_out, bstride_out);

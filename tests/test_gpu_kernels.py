@@ -130,7 +130,8 @@ def test_lsq_codes_qkx_segments_and_cols(ops):
     assert torch.equal(codes.cpu().int().view(B, N, Cc), ref)
 
 
-@pytest.mark.parametrize("cols,nseg,mode", [(384, 1, 0), (1536, 1, 0), (3 * 192, 3, 0), (384, 1, 1), (96, 1, 0)])
+@pytest.mark.parametrize("cols,nseg,mode", [(384, 1, 0), (1536, 1, 0), (3 * 192, 3, 0), (384, 1, 1), (96, 1, 0), (6 * 384, 6, 0),
+                                            (2 * 128, 2, 0), (200, 1, 1)])
 def test_lsq_backward(ops, cols, nseg, mode):
     torch.manual_seed(5)
     B, N = 3, 70
