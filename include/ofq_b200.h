@@ -116,9 +116,18 @@ OFQ_API int ofq_lsq_effective_scale(const float* alpha, int n, float g, float* o
  */
 #define OFQ_SCALE_PER_ROW 0
 #define OFQ_SCALE_PER_COL 1
+#define OFQ_ACT_NONE 0
+#define OFQ_ACT_GELU 1   /* nn.GELU() (erf form) applied to x before the shift: the fc2 input of QMLP (qlinear.py:123-136) */
 OFQ_API int ofq_lsq_quant(const float* x, long long rows, int cols, long long ldx, const float* b4,
                           const float* s_eff, int scale_mode, int period, int nseg, int qlo, int qhi,
                           int8_t* codes, long long ldq, void* stream);
+
+/* Same with (a) an activation fused in front of the quantizer, codes = Q(act(x) + b4), so that the GELU output of QMLP
+ * never travels through HBM, and (b) an optional exact 16-bit copy codes16 [rows][ld16] (fmt16 = OFQ_FMT_BF16 / _F16)
+ * of the codes, written in the same pass: the operand the backward GEMMs read. */
+OFQ_API int ofq_lsq_quant_ex(const float* x, long long rows, int cols, long long ldx, const float* b4,
+                             const float* s_eff, int scale_mode, int period, int nseg, int qlo, int qhi, int act,
+                             int8_t* codes, long long ldq, void* codes16, long long ld16, int fmt16, void* stream);
 
 /* Backward of (LearnableBias -> LSQ -> LearnableBias) given dy = dL/d(x_hat) (autograd of lsq.py:571-602):
  *   v = (x + b4)/s_eff;  inside = qlo <= v <= qhi;  q = rint(clamp(v))
@@ -133,8 +142,19 @@ OFQ_API long long ofq_lsq_bwd_workspace(long long rows, int cols, int nseg);
 OFQ_API int ofq_lsq_bwd(const float* dy, long long lddy, const float* x, long long ldx, long long rows, int cols,
                         const float* b4, const float* s_eff, int scale_mode, int period, int nseg,
                         int qlo, int qhi, float* dx, long long lddx, float* workspace, void* stream);
+/* Same for codes = Q(act(x) + b4) (ofq_lsq_quant_ex): x is the saved PRE-activation, the quantizer terms use act(x) and
+ * dx = dy * inside * act'(x) is the gradient w.r.t. x; d_aft / d_b4 / d_s are unchanged (they live after the activation). */
+OFQ_API int ofq_lsq_bwd_act(const float* dy, long long lddy, const float* x, long long ldx, long long rows, int cols,
+                            const float* b4, const float* s_eff, int scale_mode, int period, int nseg,
+                            int qlo, int qhi, int act, float* dx, long long lddx, float* workspace, void* stream);
 OFQ_API int ofq_lsq_bwd_finalize(const float* workspace, long long rows, int cols, int scale_mode, int period,
                                  int nseg, float g, float* d_s, float* d_b4, float* d_aft, int zero_sum, void* stream);
+/* ofq_lsq_bwd_finalize and ofq_lsq_bwd_scale (below) in ONE launch: the reductions of the partial sums and the fp16
+ * range scales out4 of the next consumer of dx (autograd of lsq.py:571-602 feeding the dX / dW GEMMs of qlinear.py:69). */
+OFQ_API int ofq_lsq_bwd_finalize_scale(const float* workspace, long long rows, int cols, int scale_mode, int period,
+                                       int nseg, float g, float* d_s, float* d_b4, float* d_aft, int zero_sum,
+                                       const float* v1, int n1, const float* v2, int n2, float mult, int product,
+                                       float* out4, void* stream);
 /* fp16 range scales (layout of ofq_absmax_scale's out4) for the NEXT consumer of dx, from the per-block max |dx| that
  * ofq_lsq_bwd left in its workspace: bound_1 = max|dx| * max|v1| * mult, bound_2 = max|dx| * max|v2| * mult. */
 OFQ_API int ofq_lsq_bwd_scale(const float* workspace, long long rows, int cols, int nseg, const float* v1, int n1,
@@ -195,6 +215,12 @@ OFQ_API int ofq_codes_transpose(const int8_t* codes, int nb, int R, int C, long 
 OFQ_API int ofq_softmax_quant(const float* S, int nz, int N, long long ld, int H, const float* bias,
                               const float* mask, int nW, const float* s_eff, int qhi, float* P, int8_t* codes,
                               long long ldq, float* rowsum, void* stream);
+
+/* Same, plus an optional exact 16-bit copy codes16 [nz][N][ldq] (OFQ_FMT_BF16 / _F16) of the codes written in the same
+ * pass (the A operand of the dV GEMM of the backward). Only without bias / mask and with 16-byte aligned rows. */
+OFQ_API int ofq_softmax_quant_ex(const float* S, int nz, int N, long long ld, int H, const float* bias,
+                                 const float* mask, int nW, const float* s_eff, int qhi, float* P, int8_t* codes,
+                                 long long ldq, float* rowsum, void* codes16, int fmt16, void* stream);
 
 /* Backward of softmax + LSQ given dPq = dL/dP_hat [nz][N][ld] and the saved P:
  *   v = P/s;  inside = v <= qhi (v >= 0 always);  dP = dPq * inside

@@ -45,8 +45,11 @@ SIGNATURES = {
     "ofq_lsq_effective_scale": (_i, [_p, _i, _f, _p, _p, _p]),
     "ofq_lsq_quant": (_i, [_p, _ll, _i, _ll, _p, _p, _i, _i, _i, _i, _i, _p, _ll, _p]),
     "ofq_lsq_bwd_workspace": (_ll, [_ll, _i, _i]),
+    "ofq_lsq_quant_ex": (_i, [_p, _ll, _i, _ll, _p, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p, _ll, _i, _p]),
+    "ofq_lsq_bwd_act": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p, _p]),
     "ofq_lsq_bwd": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _i, _i, _i, _i, _i, _p, _ll, _p, _p]),
     "ofq_lsq_bwd_finalize": (_i, [_p, _ll, _i, _i, _i, _i, _f, _p, _p, _p, _i, _p]),
+    "ofq_lsq_bwd_finalize_scale": (_i, [_p, _ll, _i, _i, _i, _i, _f, _p, _p, _p, _i, _p, _i, _p, _i, _f, _i, _p, _p]),
     "ofq_lsq_bwd_scale": (_i, [_p, _ll, _i, _i, _p, _i, _p, _i, _f, _i, _p, _p]),
     "ofq_grad_prep": (_i, [_p, _i, _i, _i, _ll, _ll, _p, _p, _i, _i, _p, _ll, _p, _i, _p, _p, _i, _p, _i, _p, _i, _p]),
     "ofq_absmax_scale_workspace": (_ll, []),
@@ -56,6 +59,7 @@ SIGNATURES = {
     "ofq_codes_transpose": (_i, [_p, _i, _i, _i, _ll, _ll, _p, _ll, _ll, _p]),
     "ofq_codes_rowdot": (_i, [_p, _ll, _i, _ll, _i, _p, _p, _p]),
     "ofq_softmax_quant": (_i, [_p, _i, _i, _ll, _i, _p, _p, _i, _p, _i, _p, _p, _ll, _p, _p]),
+    "ofq_softmax_quant_ex": (_i, [_p, _i, _i, _ll, _i, _p, _p, _i, _p, _i, _p, _p, _ll, _p, _p, _i, _p]),
     "ofq_softmax_quant_bwd": (_i, [_p, _p, _i, _i, _ll, _i, _p, _i, _f, _f, _p, _i, _p, _i, _p, _p, _ll, _p, _p, _p, _i, _p, _i, _p]),
     "ofq_wqk_compose": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "ofq_wqk_compose_bwd": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),

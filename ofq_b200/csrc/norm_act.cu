@@ -128,21 +128,22 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
         }
 }
 
-__global__ void __launch_bounds__(256)
+// block = 32 columns x 32 slices of the partial rows (a few hundred partial rows: ~20 dependent loads per thread)
+__global__ void __launch_bounds__(1024)
 colpart_reduce2_kernel(const float* __restrict__ part, int cols, long long nblk, float* __restrict__ out0,
                        float* __restrict__ out1) {
-    __shared__ float red[8][33];
+    __shared__ float red[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int col = blockIdx.x * 32 + tx, vecid = blockIdx.y;
     float acc = 0.f;
     if (col < cols)
-        for (long long b = ty; b < nblk; b += 8) acc += part[(b * 2 + vecid) * cols + col];
+        for (long long b = ty; b < nblk; b += 32) acc += part[(b * 2 + vecid) * cols + col];
     red[ty][tx] = acc;
     __syncthreads();
     if (ty == 0 && col < cols) {
         float s = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s += red[k][tx];
+        for (int k = 0; k < 32; ++k) s += red[k][tx];
         (vecid == 0 ? out0 : out1)[col] = s;
     }
 }
@@ -180,7 +181,7 @@ extern "C" int ofq_layernorm_bwd(const float* dy, const float* x, const float* g
     dim3 grid((unsigned)nblk, (cols + kChunk - 1) / kChunk);
     layernorm_bwd_kernel<<<grid, 256, 0, st>>>(dy, x, gamma, mean, rstd, rows, cols, dx, workspace);
     dim3 g2((cols + 31) / 32, 2);
-    colpart_reduce2_kernel<<<g2, 256, 0, st>>>(workspace, cols, nblk, dgamma, dbeta);
+    colpart_reduce2_kernel<<<g2, 1024, 0, st>>>(workspace, cols, nblk, dgamma, dbeta);
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }

@@ -130,6 +130,26 @@ __device__ __forceinline__ uint32_t pack4_i8(int a, int b, int c, int d) {
     return r;
 }
 
+
+// nn.GELU() (erf form) exactly as ATen's CUDA kernel evaluates it in fp32: (x * 0.5) * (1 + erf(x * sqrt(1/2))), and its
+// derivative cdf + x * pdf (ActivationGeluKernel.cu). Fused into the fc2 input quantizer (qlinear.py:123-136): the GELU
+// output is never written to HBM, the backward recomputes it from the saved fc1 output.
+__device__ __forceinline__ float gelu_fwd(float x) {
+    return __fmul_rn(__fmul_rn(x, 0.5f), __fadd_rn(1.0f, erff(__fmul_rn(x, 0.70710678118654752440f))));
+}
+__device__ __forceinline__ float gelu_grad(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = expf(-0.5f * x * x) * 0.39894228040143267794f;      // 2/sqrt(pi) * sqrt(1/2) * 0.5
+    return cdf + x * pdf;
+}
+// two small integers -> packed fp16 / bf16 pair (exact), first in the low half
+__device__ __forceinline__ uint32_t pack_codes16(int a, int b, bool f16) {
+    uint32_t r;
+    if (f16) asm("cvt.rn.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"((float)b), "f"((float)a));
+    else     asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"((float)b), "f"((float)a));
+    return r;
+}
+
 // Plan shared by the streaming kernels below: 592 CTAs x 8 warps (32 warps per SM keep ~64 KB of loads in flight); a warp owns ONE 128-column group (one float4 per lane,
 // so per-column vectors are loaded once) and strides over the rows; warps beyond the last whole set of column groups idle.
 constexpr int kStreamCtas = 4 * 148;
@@ -142,11 +162,12 @@ __host__ __device__ inline StreamPlan stream_plan(int cols) {
     return p;
 }
 
-template <int MODE>
+template <int MODE, int ACT>
 __global__ void __launch_bounds__(256)
 lsq_quant_vec_kernel(const float* __restrict__ x, uint32_t rows, int cols, long long ldx,
                      const float* __restrict__ b4, const float* __restrict__ s_eff, uint32_t period,
-                     int nseg, int seg_len, float qlo, float qhi, int8_t* __restrict__ codes, long long ldq) {
+                     int nseg, int seg_len, float qlo, float qhi, int8_t* __restrict__ codes, long long ldq,
+                     uint16_t* __restrict__ codes16, long long ld16, int f16) {
     constexpr int ILP = 4;
     const uint32_t lane = threadIdx.x & 31;
     const StreamPlan pl = stream_plan(cols);
@@ -188,11 +209,16 @@ lsq_quant_vec_kernel(const float* __restrict__ x, uint32_t rows, int cols, long 
                 s4 = make_float4(sv[u], sv[u], sv[u], sv[u]);
                 i4 = make_float4(iv, iv, iv, iv);
             }
+            if (ACT == OFQ_ACT_GELU)
+                xv[u] = make_float4(gelu_fwd(xv[u].x), gelu_fwd(xv[u].y), gelu_fwd(xv[u].z), gelu_fwd(xv[u].w));
             const int q0 = lsq_code_fast(xv[u].x, b.x, s4.x, i4.x, qlo, qhi);
             const int q1 = lsq_code_fast(xv[u].y, b.y, s4.y, i4.y, qlo, qhi);
             const int q2 = lsq_code_fast(xv[u].z, b.z, s4.z, i4.z, qlo, qhi);
             const int q3 = lsq_code_fast(xv[u].w, b.w, s4.w, i4.w, qlo, qhi);
             *reinterpret_cast<uint32_t*>(cp + (long long)r * ldq) = pack4_i8(q0, q1, q2, q3);
+            if (codes16)       // exact 16-bit copy: the operand of the backward GEMMs, written while the codes are in registers
+                *reinterpret_cast<uint2*>(codes16 + (long long)r * ld16 + col) =
+                    make_uint2(pack_codes16(q0, q1, f16 != 0), pack_codes16(q2, q3, f16 != 0));
         }
     }
 }
@@ -201,14 +227,19 @@ lsq_quant_vec_kernel(const float* __restrict__ x, uint32_t rows, int cols, long 
 __global__ void __launch_bounds__(256)
 lsq_quant_kernel(const float* __restrict__ x, long long rows, int cols, long long ldx,
                  const float* __restrict__ b4, const float* __restrict__ s_eff, int scale_mode, int period,
-                 int nseg, int seg_len, float qlo, float qhi, int8_t* __restrict__ codes, long long ldq) {
+                 int nseg, int seg_len, float qlo, float qhi, int8_t* __restrict__ codes, long long ldq, int act,
+                 uint16_t* __restrict__ codes16, long long ld16, int f16) {
     const uint32_t total = (uint32_t)rows * (uint32_t)cols;   // host guarantees < 2^32
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const uint32_t row = idx / (uint32_t)cols, col = idx - row * (uint32_t)cols;
     const float s = scale_mode == OFQ_SCALE_PER_ROW ? __ldg(s_eff + (row % (uint32_t)period) * nseg + col / (uint32_t)seg_len)
                                                     : __ldg(s_eff + col);
-    codes[(long long)row * ldq + col] = (int8_t)lsq_code(__ldg(x + (long long)row * ldx + col), __ldg(b4 + col), s, qlo, qhi);
+    float xv = __ldg(x + (long long)row * ldx + col);
+    if (act == OFQ_ACT_GELU) xv = gelu_fwd(xv);
+    const int q = lsq_code(xv, __ldg(b4 + col), s, qlo, qhi);
+    codes[(long long)row * ldq + col] = (int8_t)q;
+    if (codes16) codes16[(long long)row * ld16 + col] = (uint16_t)(pack_codes16(q, 0, f16 != 0) & 0xffffu);
 }
 
 // ------------------------------------------------------------------------------------------- LSQ backward
@@ -230,7 +261,7 @@ lsq_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __rest
                long long rows, int cols, const float* __restrict__ b4, const float* __restrict__ s_eff,
                int period, int nseg, int seg_len, float qlo, float qhi,
                float* __restrict__ dx, long long lddx, float* __restrict__ rowpart,
-               float* __restrict__ colpart, float* __restrict__ blockmax) {
+               float* __restrict__ colpart, float* __restrict__ blockmax, int act) {
     constexpr int kBwdChunk = NP * 128;
     __shared__ float col_s[3][kBwdChunk];     // index [v][(p * 4 + e) * 32 + lane]: conflict-free for the fold
     __shared__ float bmax_s[kWarpsPerBlock];
@@ -299,14 +330,16 @@ lsq_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __rest
                 float o[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float v = (xx[e] + bb[e]) * sv[e];
+                    const float xa = act == OFQ_ACT_GELU ? gelu_fwd(xx[e]) : xx[e];
+                    const float v = (xa + bb[e]) * sv[e];
                     const bool inside = (v >= qlo) && (v <= qhi);
                     const float q = rintf(fminf(fmaxf(v, qlo), qhi));
                     const float t = gg[e] * (inside ? (q - v) : q);
                     o[e] = inside ? gg[e] : 0.f;
-                    tmax = fmaxf(tmax, fabsf(o[e]));
                     a_aft[p][e] += gg[e];
                     a_b4[p][e] += o[e];
+                    if (act == OFQ_ACT_GELU) o[e] *= gelu_grad(xx[e]);
+                    tmax = fmaxf(tmax, fabsf(o[e]));
                     if (scale_mode == OFQ_SCALE_PER_ROW) part[p] += t; else a_s[p % NS][e] += t;
                 }
                 *reinterpret_cast<float4*>(dxr + p * 128) = make_float4(o[0], o[1], o[2], o[3]);
@@ -363,9 +396,9 @@ lsq_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __rest
 
 // out4 = power-of-two fp16 range scales from per-block maxima of a gradient: bound_1 = max(blockmax) * max|v1| * mult,
 // bound_2 = max(blockmax) * max|v2| * mult (looser than ofq_absmax_scale by the spread of v1 / v2, costs no pass).
-__global__ void __launch_bounds__(256)
-scale_from_blockmax_kernel(const float* __restrict__ blockmax, int nblk, const float* __restrict__ v1, int n1,
-                           const float* __restrict__ v2, int n2, float mult, int product, float* __restrict__ out4) {
+__device__ __forceinline__ void
+scale_from_blockmax(const float* __restrict__ blockmax, int nblk, const float* __restrict__ v1, int n1,
+                    const float* __restrict__ v2, int n2, float mult, int product, float* __restrict__ out4) {
     __shared__ float fin[3][8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float a = 0.f, m1 = v1 ? 0.f : 1.f, m2 = v2 ? 0.f : 1.f;
@@ -388,29 +421,44 @@ scale_from_blockmax_kernel(const float* __restrict__ blockmax, int nblk, const f
         pow2_scale_pair(a * m2 * (product ? m1 : 1.f) * mult, out4 + 2, out4 + 3);
     }
 }
-
-// Streaming variant (stream_plan): a warp owns one 128-column group and strides over the rows, so the column sums stay in
-// 12 registers and are written once per warp (no shared-memory fold, no barrier), four rows (8 x 16 B per lane) are in
-// flight, and the per-(row, segment) scale-gradient partial of a row is one value per column group.
-// workspace = rowpart[gps][rows*nseg] | colpart[lanes_rows][3][cols] | warpmax[cg * lanes_rows], gps = groups per segment.
-__host__ __device__ inline bool lsq_bwd_streaming(int cols, int nseg) {
-    const int seg_len = cols / nseg;
-    return cols % 4 == 0 && (nseg == 1 || seg_len % 128 == 0) && (cols + 127) / 128 <= kStreamWarps / 8;
+__global__ void __launch_bounds__(256)
+scale_from_blockmax_kernel(const float* __restrict__ blockmax, int nblk, const float* __restrict__ v1, int n1,
+                           const float* __restrict__ v2, int n2, float mult, int product, float* __restrict__ out4) {
+    scale_from_blockmax(blockmax, nblk, v1, n1, v2, n2, mult, product, out4);
 }
 
-template <int MODE>
+// Streaming variant: the 8 warps of a CTA own the SAME 128-column group (CTA b -> group b % cg, row slot b / cg) and
+// stride over the rows, so the column sums stay in 12 registers per lane, are folded across the CTA once in shared memory
+// and leave as ONE partial per CTA (a few hundred partial rows for the finalize pass instead of one per warp); four rows
+// (8 x 16 B per lane) are in flight, and the per-(row, segment) scale-gradient partial of a row is one value per column group.
+// workspace = rowpart[gps][rows*nseg] | colpart[bpg][3][cols] | blockmax[cg * bpg], gps = groups per segment.
+__host__ __device__ inline bool lsq_bwd_streaming(int cols, int nseg) {
+    const int seg_len = cols / nseg;
+    return cols % 4 == 0 && (nseg == 1 || seg_len % 128 == 0) && (cols + 127) / 128 <= kStreamCtas;
+}
+struct BwdPlan { uint32_t cg, bpg; };               // column groups per row, CTAs (row slots) per column group
+__host__ __device__ inline BwdPlan bwd_plan(int cols) {
+    BwdPlan p;
+    p.cg = (uint32_t)(cols + 127) / 128;
+    p.bpg = (uint32_t)kStreamCtas / p.cg;
+    return p;
+}
+
+template <int MODE, int ACT>
 __global__ void __launch_bounds__(256, 4)
 lsq_bwd_stream_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
                       uint32_t rows, int cols, const float* __restrict__ b4, const float* __restrict__ s_eff,
                       uint32_t period, int nseg, int seg_len, float qlo, float qhi,
                       float* __restrict__ dx, long long lddx, float* __restrict__ rowpart,
-                      float* __restrict__ colpart, float* __restrict__ warpmax) {
+                      float* __restrict__ colpart, float* __restrict__ blockmax) {
     constexpr int ILP = 2;
-    const uint32_t lane = threadIdx.x & 31;
-    const StreamPlan pl = stream_plan(cols);
-    const uint32_t w = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (w >= pl.cg * pl.lanes_rows) return;
-    const uint32_t g = w % pl.cg, rl = w / pl.cg, dr = pl.lanes_rows;
+    __shared__ float fold_s[8][3][128];
+    __shared__ float bmax_s[8];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const BwdPlan pl = bwd_plan(cols);
+    const uint32_t g = blockIdx.x % pl.cg, bslot = blockIdx.x / pl.cg;
+    if (bslot >= pl.bpg) return;                    // block-uniform: the CTAs beyond the last whole set of groups idle
+    const uint32_t rl = bslot * 8 + warp, dr = pl.bpg * 8;
     const int col = (int)(g * 128 + lane * 4);
     const bool act = col < cols;
     const float4 b = act ? __ldg(reinterpret_cast<const float4*>(b4 + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -460,14 +508,16 @@ lsq_bwd_stream_kernel(const float* __restrict__ dy, long long lddy, const float*
             float o[4], part = 0.f;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float v = (xx[e] + bb[e]) * ii[e];
+                const float xa = ACT == OFQ_ACT_GELU ? gelu_fwd(xx[e]) : xx[e];     // the quantizer saw act(x)
+                const float v = (xa + bb[e]) * ii[e];
                 const bool inside = (v >= qlo) && (v <= qhi);
                 const float q = rintf(fminf(fmaxf(v, qlo), qhi));
                 const float t = gg[e] * (inside ? (q - v) : q);
                 o[e] = inside ? gg[e] : 0.f;
-                tmax = fmaxf(tmax, fabsf(o[e]));
                 aft[e] += gg[e];
                 ab4[e] += o[e];
+                if (ACT == OFQ_ACT_GELU) o[e] *= gelu_grad(xx[e]);                  // dx is the gradient w.r.t. the pre-activation
+                tmax = fmaxf(tmax, fabsf(o[e]));
                 if (MODE == OFQ_SCALE_PER_ROW) part += t; else as[e] += t;
             }
             if (act) *reinterpret_cast<float4*>(dx + (long long)r * lddx + col) = make_float4(o[0], o[1], o[2], o[3]);
@@ -477,25 +527,39 @@ lsq_bwd_stream_kernel(const float* __restrict__ dy, long long lddy, const float*
             }
         }
     }
-    if (act) {
-        float* cp = colpart + (long long)rl * 3 * cols + col;
-        *reinterpret_cast<float4*>(cp) = make_float4(aft[0], aft[1], aft[2], aft[3]);
-        *reinterpret_cast<float4*>(cp + cols) = make_float4(ab4[0], ab4[1], ab4[2], ab4[3]);
-        *reinterpret_cast<float4*>(cp + 2 * cols) = make_float4(as[0], as[1], as[2], as[3]);
-    }
+    // fold the 8 warps of the CTA (fixed order: deterministic), one partial row per CTA
+    *reinterpret_cast<float4*>(&fold_s[warp][0][lane * 4]) = make_float4(aft[0], aft[1], aft[2], aft[3]);
+    *reinterpret_cast<float4*>(&fold_s[warp][1][lane * 4]) = make_float4(ab4[0], ab4[1], ab4[2], ab4[3]);
+    *reinterpret_cast<float4*>(&fold_s[warp][2][lane * 4]) = make_float4(as[0], as[1], as[2], as[3]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-    if (lane == 0) warpmax[w] = tmax;
+    if (lane == 0) bmax_s[warp] = tmax;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * 128; i += blockDim.x) {
+        const int v = i >> 7, c = i & 127;
+        if ((int)(g * 128) + c < cols) {
+            float a = 0.f;
+#pragma unroll
+            for (int w2 = 0; w2 < 8; ++w2) a += fold_s[w2][v][c];
+            colpart[((long long)bslot * 3 + v) * cols + g * 128 + c] = a;
+        }
+    }
+    if (threadIdx.x == 0) {
+        float m = bmax_s[0];
+#pragma unroll
+        for (int w2 = 1; w2 < 8; ++w2) m = fmaxf(m, bmax_s[w2]);
+        blockmax[blockIdx.x] = m;
+    }
 }
 
 // Deterministic tree reductions of the partials: block = 32 outputs x 8 slices of the reduction axis.
-__global__ void __launch_bounds__(256)
-lsq_bwd_finalize_cols_kernel(const float* __restrict__ colpart, int cols, long long nblk, int scale_mode, float g,
-                             float* __restrict__ d_s, float* __restrict__ d_b4, float* __restrict__ d_aft, int zero_sum) {
+__device__ __forceinline__ void
+lsq_bwd_finalize_cols(const float* __restrict__ colpart, int cols, long long nblk, int scale_mode, float g,
+                      float* __restrict__ d_s, float* __restrict__ d_b4, float* __restrict__ d_aft, int zero_sum,
+                      int bx, int vecid) {                // vecid 0: aft, 1: b4, 2: per-column scale
     __shared__ float red[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int col = blockIdx.x * 32 + tx;
-    const int vecid = blockIdx.y;                     // 0: aft, 1: b4, 2: per-column scale
+    const int col = bx * 32 + tx;
     float acc = 0.f;
     if (col < cols) {
         // zero_sum: sum_rows dy is analytically zero, so d_b4 = sum_inside dy = -sum_outside dy; subtracting the two
@@ -517,12 +581,12 @@ lsq_bwd_finalize_cols_kernel(const float* __restrict__ colpart, int cols, long l
     }
 }
 
-__global__ void __launch_bounds__(256)
-lsq_bwd_finalize_rows_kernel(const float* __restrict__ rowpart, long long total, long long nscale, float g,
-                             float* __restrict__ d_s) {
+__device__ __forceinline__ void
+lsq_bwd_finalize_rows(const float* __restrict__ rowpart, long long total, long long nscale, float g,
+                      float* __restrict__ d_s, int bx) {
     __shared__ float red[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const long long i = (long long)blockIdx.x * 32 + tx;
+    const long long i = (long long)bx * 32 + tx;
     float acc = 0.f;
     if (i < nscale)
         for (long long j = i + (long long)ty * nscale; j < total; j += 8 * nscale) acc += rowpart[j];
@@ -534,6 +598,27 @@ lsq_bwd_finalize_rows_kernel(const float* __restrict__ rowpart, long long total,
         for (int k = 0; k < 8; ++k) s += red[k][tx];
         d_s[i] = g * s;
     }
+}
+
+// ONE launch for everything that follows the streaming pass: CTAs [0, ncb) reduce the column partials (d_aft, d_b4 and
+// the per-column d_s), CTAs [ncb, ncb + nrb) the per-row scale-gradient partials, and the last CTA (when out4 is
+// requested) turns the block maxima into the fp16 range scales of the next GEMM operand.
+struct FinalizeArgs {
+    const float* colpart; int cols; long long nslots; int scale_mode; float g;
+    float* d_s; float* d_b4; float* d_aft; int zero_sum;
+    const float* rowpart; long long total; long long nscale;
+    const float* blockmax; int nblk; const float* v1; int n1; const float* v2; int n2; float mult; int product; float* out4;
+    int ncx, ncb, nrb;
+};
+__global__ void __launch_bounds__(256)
+lsq_bwd_finalize_kernel(const FinalizeArgs a) {
+    const int b = blockIdx.x;
+    if (b < a.ncb)
+        lsq_bwd_finalize_cols(a.colpart, a.cols, a.nslots, a.scale_mode, a.g, a.d_s, a.d_b4, a.d_aft, a.zero_sum, b % a.ncx, b / a.ncx);
+    else if (b < a.ncb + a.nrb)
+        lsq_bwd_finalize_rows(a.rowpart, a.total, a.nscale, a.g, a.d_s, b - a.ncb);
+    else
+        scale_from_blockmax(a.blockmax, a.nblk, a.v1, a.n1, a.v2, a.n2, a.mult, a.product, a.out4);
 }
 
 // ------------------------------------------------------------------------------------------- gradient prep
@@ -670,6 +755,86 @@ grad_prep_kernel(const float* __restrict__ x, int R, int C, long long ldx, long 
                     *reinterpret_cast<uint4*>(dst + plane_t) = lo;
                 }
             }
+        }
+    }
+}
+
+
+// Streaming variant for the single row-major 16-bit copy the fp16 backward uses (no transposed output, one plane): CTA b
+// owns the 128-column group b % cg (BwdPlan), its warps stride over the rows with four 16-byte loads in flight per lane,
+// the column sums stay in registers and leave as one atomicAdd per column and CTA; no shared-memory tile.
+template <bool F16>
+__global__ void __launch_bounds__(256, 4)
+grad_prep_stream_kernel(const float* __restrict__ x, uint32_t rows, uint32_t R, int C, long long ldx,
+                        const float* __restrict__ cs, const float* __restrict__ rs, uint32_t period,
+                        const float* __restrict__ scale4, int rm_rowscale, uint16_t* __restrict__ out_rm, long long ld_rm,
+                        float* __restrict__ colsum, const float* __restrict__ u, int group, float* __restrict__ rowdot) {
+    constexpr int ILP = 4;
+    __shared__ float fold_s[8][128];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const BwdPlan pl = bwd_plan(C);
+    const uint32_t g = blockIdx.x % pl.cg, bslot = blockIdx.x / pl.cg;
+    if (bslot >= pl.bpg) return;                    // block-uniform
+    const uint32_t rl = bslot * 8 + warp, dr = pl.bpg * 8;
+    const int col = (int)(g * 128 + lane * 4);
+    const bool act = col < C;
+    const float sc = scale4 ? __ldg(scale4) : 1.f;
+    float4 c4 = make_float4(1.f, 1.f, 1.f, 1.f), u4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act && cs) c4 = __ldg(reinterpret_cast<const float4*>(cs + col));
+    if (act && u) u4 = __ldg(reinterpret_cast<const float4*>(u + col));
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const uint32_t dn = dr % period;
+    uint32_t n = rl % period;
+    const int ngrp = rowdot ? C / group : 0;
+    for (uint32_t row = rl; row < rows; row += dr * ILP) {
+        float4 f[ILP];
+        float rsv[ILP];
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) {
+            const uint32_t r = row + k * dr;
+            f[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            rsv[k] = 1.f;
+            if (r < rows) {
+                if (act) f[k] = __ldg(reinterpret_cast<const float4*>(x + (long long)r * ldx + col));
+                if (rs) rsv[k] = __ldg(rs + n);
+            }
+            n += dn;
+            if (n >= period) n -= period;
+        }
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) {
+            const uint32_t r = row + k * dr;
+            if (r >= rows) break;                   // warp-uniform
+            if (out_rm && act) {
+                const float sc_row = rm_rowscale ? sc * rsv[k] : sc;
+                const uint2 pk = make_uint2(pack16x2<F16>(f[k].x * c4.x * sc_row, f[k].y * c4.y * sc_row),
+                                            pack16x2<F16>(f[k].z * c4.z * sc_row, f[k].w * c4.w * sc_row));
+                *reinterpret_cast<uint2*>(out_rm + (long long)r * ld_rm + col) = pk;
+            }
+            acc[0] += f[k].x; acc[1] += f[k].y; acc[2] += f[k].z; acc[3] += f[k].w;
+            if (rowdot) {
+                float d = f[k].x * u4.x + f[k].y * u4.y + f[k].z * u4.z + f[k].w * u4.w;
+                // a group of `group` columns is group / 4 consecutive lanes
+                d += __shfl_xor_sync(0xffffffffu, d, 1);
+                d += __shfl_xor_sync(0xffffffffu, d, 2);
+                if (group >= 32) d += __shfl_xor_sync(0xffffffffu, d, 4);
+                if (group >= 64) d += __shfl_xor_sync(0xffffffffu, d, 8);
+                if (group >= 128) d += __shfl_xor_sync(0xffffffffu, d, 16);
+                if (act && (lane % (uint32_t)(group >> 2)) == 0) {
+                    const uint32_t b = r / R, rr = r - b * R;
+                    rowdot[((long long)b * ngrp + col / group) * R + rr] = d;
+                }
+            }
+        }
+    }
+    if (colsum) {
+        *reinterpret_cast<float4*>(&fold_s[warp][lane * 4]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        __syncthreads();
+        if (threadIdx.x < 128 && (int)(g * 128 + threadIdx.x) < C) {
+            float a = 0.f;
+#pragma unroll
+            for (int w2 = 0; w2 < 8; ++w2) a += fold_s[w2][threadIdx.x];
+            atomicAdd(colsum + g * 128 + threadIdx.x, a);
         }
     }
 }
@@ -939,32 +1104,51 @@ extern "C" int ofq_lsq_effective_scale(const float* alpha, int n, float g, float
     return 0;
 }
 
-extern "C" int ofq_lsq_quant(const float* x, long long rows, int cols, long long ldx, const float* b4,
-                             const float* s_eff, int scale_mode, int period, int nseg, int qlo, int qhi,
-                             int8_t* codes, long long ldq, void* stream) {
+extern "C" int ofq_lsq_quant_ex(const float* x, long long rows, int cols, long long ldx, const float* b4,
+                                const float* s_eff, int scale_mode, int period, int nseg, int qlo, int qhi, int act,
+                                int8_t* codes, long long ldq, void* codes16, long long ld16, int fmt16, void* stream) {
     OFQ_REQUIRE(x && b4 && s_eff && codes, "ofq_lsq_quant: null pointer");
     OFQ_REQUIRE(rows > 0 && cols > 0 && nseg > 0 && cols % nseg == 0 && period > 0, "ofq_lsq_quant: bad shape");
     OFQ_REQUIRE(qlo >= -128 && qhi <= 127 && qlo < qhi, "ofq_lsq_quant: codes must fit int8");
+    OFQ_REQUIRE(act == OFQ_ACT_NONE || act == OFQ_ACT_GELU, "ofq_lsq_quant: unknown activation");
+    OFQ_REQUIRE(!codes16 || ((uintptr_t)codes16 % 8 == 0 && ld16 % 4 == 0 && ld16 >= cols &&
+                             (fmt16 == OFQ_FMT_BF16 || fmt16 == OFQ_FMT_F16)),
+                "ofq_lsq_quant: the 16-bit copy needs 8-byte alignment, a pitch that is a multiple of 4 and a valid format");
     OFQ_CHECK_ARCH();
     const int seg_len = cols / nseg;
     const bool vec = (cols % 4 == 0) && (seg_len % 4 == 0) && (ldx % 4 == 0) && (ldq % 4 == 0) &&
                      ((uintptr_t)x % 16 == 0) && ((uintptr_t)b4 % 16 == 0) && ((uintptr_t)s_eff % 16 == 0) &&
                      ((uintptr_t)codes % 4 == 0);
     OFQ_REQUIRE(rows * (long long)cols < 0x7fffffffLL, "ofq_lsq_quant: tensor too large for 32-bit indexing");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint16_t* c16 = (uint16_t*)codes16;
+    const int f16 = fmt16 == OFQ_FMT_F16;
     if (vec && (cols + 127) / 128 <= kStreamWarps) {
-        if (scale_mode == OFQ_SCALE_PER_ROW)
-            lsq_quant_vec_kernel<OFQ_SCALE_PER_ROW><<<kStreamCtas, 256, 0, (cudaStream_t)stream>>>(
-                x, (uint32_t)rows, cols, ldx, b4, s_eff, (uint32_t)period, nseg, seg_len, (float)qlo, (float)qhi, codes, ldq);
-        else
-            lsq_quant_vec_kernel<OFQ_SCALE_PER_COL><<<kStreamCtas, 256, 0, (cudaStream_t)stream>>>(
-                x, (uint32_t)rows, cols, ldx, b4, s_eff, 1u, nseg, seg_len, (float)qlo, (float)qhi, codes, ldq);
+#define OFQ_LSQ_QUANT(MODE, ACT, PERIOD)                                                                                     \
+    lsq_quant_vec_kernel<MODE, ACT><<<kStreamCtas, 256, 0, st>>>(x, (uint32_t)rows, cols, ldx, b4, s_eff, PERIOD, nseg, seg_len, \
+                                                                 (float)qlo, (float)qhi, codes, ldq, c16, ld16, f16)
+        if (scale_mode == OFQ_SCALE_PER_ROW) {
+            if (act == OFQ_ACT_GELU) OFQ_LSQ_QUANT(OFQ_SCALE_PER_ROW, OFQ_ACT_GELU, (uint32_t)period);
+            else OFQ_LSQ_QUANT(OFQ_SCALE_PER_ROW, OFQ_ACT_NONE, (uint32_t)period);
+        } else {
+            if (act == OFQ_ACT_GELU) OFQ_LSQ_QUANT(OFQ_SCALE_PER_COL, OFQ_ACT_GELU, 1u);
+            else OFQ_LSQ_QUANT(OFQ_SCALE_PER_COL, OFQ_ACT_NONE, 1u);
+        }
+#undef OFQ_LSQ_QUANT
     } else {
         const unsigned grid = (unsigned)((rows * cols + 255) / 256);
-        lsq_quant_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, b4, s_eff, scale_mode,
-                                                                period, nseg, seg_len, (float)qlo, (float)qhi, codes, ldq);
+        lsq_quant_kernel<<<grid, 256, 0, st>>>(x, rows, cols, ldx, b4, s_eff, scale_mode, period, nseg, seg_len, (float)qlo,
+                                               (float)qhi, codes, ldq, act, c16, ld16, f16);
     }
     OFQ_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int ofq_lsq_quant(const float* x, long long rows, int cols, long long ldx, const float* b4,
+                             const float* s_eff, int scale_mode, int period, int nseg, int qlo, int qhi,
+                             int8_t* codes, long long ldq, void* stream) {
+    return ofq_lsq_quant_ex(x, rows, cols, ldx, b4, s_eff, scale_mode, period, nseg, qlo, qhi, OFQ_ACT_NONE, codes, ldq,
+                            nullptr, 0, OFQ_FMT_F16, stream);
 }
 
 // layout of the partial-sum workspace for either variant
@@ -972,12 +1156,12 @@ struct LsqBwdWs { long long rowpart_used, rowpart_n, colslots, nmax; };
 static LsqBwdWs lsq_bwd_ws(long long rows, int cols, int nseg) {
     LsqBwdWs w;
     if (lsq_bwd_streaming(cols, nseg)) {
-        const StreamPlan pl = stream_plan(cols);
+        const BwdPlan pl = bwd_plan(cols);
         const long long gps = nseg == 1 ? pl.cg : (cols / nseg) / 128;
         w.rowpart_used = gps * rows * nseg;
-        w.rowpart_n = (w.rowpart_used + 3) / 4 * 4;          // colpart is written with float4 stores
-        w.colslots = pl.lanes_rows;
-        w.nmax = (long long)pl.cg * pl.lanes_rows;
+        w.rowpart_n = (w.rowpart_used + 3) / 4 * 4;
+        w.colslots = pl.bpg;
+        w.nmax = (long long)pl.cg * pl.bpg;
     } else {
         w.rowpart_used = w.rowpart_n = rows * nseg;
         w.colslots = lsq_bwd_nblk(rows);
@@ -1007,7 +1191,15 @@ extern "C" int ofq_lsq_bwd_scale(const float* workspace, long long rows, int col
 extern "C" int ofq_lsq_bwd(const float* dy, long long lddy, const float* x, long long ldx, long long rows,
                            int cols, const float* b4, const float* s_eff, int scale_mode, int period, int nseg,
                            int qlo, int qhi, float* dx, long long lddx, float* workspace, void* stream) {
+    return ofq_lsq_bwd_act(dy, lddy, x, ldx, rows, cols, b4, s_eff, scale_mode, period, nseg, qlo, qhi, OFQ_ACT_NONE, dx, lddx,
+                           workspace, stream);
+}
+
+extern "C" int ofq_lsq_bwd_act(const float* dy, long long lddy, const float* x, long long ldx, long long rows,
+                               int cols, const float* b4, const float* s_eff, int scale_mode, int period, int nseg,
+                               int qlo, int qhi, int act, float* dx, long long lddx, float* workspace, void* stream) {
     OFQ_REQUIRE(dy && x && b4 && s_eff && dx && workspace, "ofq_lsq_bwd: null pointer");
+    OFQ_REQUIRE(act == OFQ_ACT_NONE || act == OFQ_ACT_GELU, "ofq_lsq_bwd: unknown activation");
     OFQ_REQUIRE(rows > 0 && cols > 0 && nseg > 0 && cols % nseg == 0 && period > 0, "ofq_lsq_bwd: bad shape");
     const int seg_len = cols / nseg;
     OFQ_REQUIRE(cols % 4 == 0 && seg_len % 4 == 0 && lddy % 4 == 0 && ldx % 4 == 0 && lddx % 4 == 0,
@@ -1024,21 +1216,24 @@ extern "C" int ofq_lsq_bwd(const float* dy, long long lddy, const float* x, long
         OFQ_REQUIRE(rows < 0x7fffffffLL, "ofq_lsq_bwd: too many rows");
         OFQ_REQUIRE(scale_mode != OFQ_SCALE_PER_ROW || period >= rows || rows % period == 0,
                     "ofq_lsq_bwd: rows must be a multiple of the scale period");
-        if (scale_mode == OFQ_SCALE_PER_ROW)
-            lsq_bwd_stream_kernel<OFQ_SCALE_PER_ROW><<<kStreamCtas, 256, 0, st>>>(
-                dy, lddy, x, ldx, (uint32_t)rows, cols, b4, s_eff, (uint32_t)period, nseg, seg_len, (float)qlo, (float)qhi, dx, lddx,
-                rowpart, colpart, blockmax);
-        else
-            lsq_bwd_stream_kernel<OFQ_SCALE_PER_COL><<<kStreamCtas, 256, 0, st>>>(
-                dy, lddy, x, ldx, (uint32_t)rows, cols, b4, s_eff, 1u, nseg, seg_len, (float)qlo, (float)qhi, dx, lddx,
-                rowpart, colpart, blockmax);
+#define OFQ_LSQ_BWD_STREAM(MODE, ACT, PERIOD)                                                                              \
+    lsq_bwd_stream_kernel<MODE, ACT><<<kStreamCtas, 256, 0, st>>>(dy, lddy, x, ldx, (uint32_t)rows, cols, b4, s_eff, PERIOD, nseg, \
+                                                                  seg_len, (float)qlo, (float)qhi, dx, lddx, rowpart, colpart, blockmax)
+        if (scale_mode == OFQ_SCALE_PER_ROW) {
+            if (act == OFQ_ACT_GELU) OFQ_LSQ_BWD_STREAM(OFQ_SCALE_PER_ROW, OFQ_ACT_GELU, (uint32_t)period);
+            else OFQ_LSQ_BWD_STREAM(OFQ_SCALE_PER_ROW, OFQ_ACT_NONE, (uint32_t)period);
+        } else {
+            if (act == OFQ_ACT_GELU) OFQ_LSQ_BWD_STREAM(OFQ_SCALE_PER_COL, OFQ_ACT_GELU, 1u);
+            else OFQ_LSQ_BWD_STREAM(OFQ_SCALE_PER_COL, OFQ_ACT_NONE, 1u);
+        }
+#undef OFQ_LSQ_BWD_STREAM
         OFQ_CUDA(cudaGetLastError());
         return 0;
     }
     const unsigned grid = (unsigned)lsq_bwd_nblk(rows);
 #define OFQ_LSQ_BWD(MODE, NP)                                                                                          \
     lsq_bwd_kernel<MODE, NP><<<grid, kWarpsPerBlock * 32, 0, st>>>(dy, lddy, x, ldx, rows, cols, b4, s_eff, period, nseg, \
-                                                                  seg_len, (float)qlo, (float)qhi, dx, lddx, rowpart, colpart, blockmax)
+                                                                  seg_len, (float)qlo, (float)qhi, dx, lddx, rowpart, colpart, blockmax, act)
     const bool np3 = cols % 384 == 0;      // 384-column chunks leave no idle lanes for C = 384 / 1536 / 2304
     if (scale_mode == OFQ_SCALE_PER_ROW) { if (np3) OFQ_LSQ_BWD(OFQ_SCALE_PER_ROW, 3); else OFQ_LSQ_BWD(OFQ_SCALE_PER_ROW, 4); }
     else { if (np3) OFQ_LSQ_BWD(OFQ_SCALE_PER_COL, 3); else OFQ_LSQ_BWD(OFQ_SCALE_PER_COL, 4); }
@@ -1047,24 +1242,42 @@ extern "C" int ofq_lsq_bwd(const float* dy, long long lddy, const float* x, long
     return 0;
 }
 
-extern "C" int ofq_lsq_bwd_finalize(const float* workspace, long long rows, int cols, int scale_mode, int period,
-                                    int nseg, float g, float* d_s, float* d_b4, float* d_aft, int zero_sum, void* stream) {
+static int lsq_bwd_finalize_impl(const float* workspace, long long rows, int cols, int scale_mode, int period, int nseg,
+                                 float g, float* d_s, float* d_b4, float* d_aft, int zero_sum, const float* v1, int n1,
+                                 const float* v2, int n2, float mult, int product, float* out4, void* stream) {
     OFQ_REQUIRE(workspace && rows > 0 && cols > 0, "ofq_lsq_bwd_finalize: bad argument");
     OFQ_CHECK_ARCH();
     OFQ_REQUIRE(nseg > 0 && cols % nseg == 0, "ofq_lsq_bwd_finalize: bad segment count");
     const LsqBwdWs wsl = lsq_bwd_ws(rows, cols, nseg);
-    const float* rowpart = workspace;
-    const float* colpart = workspace + wsl.rowpart_n;
-    cudaStream_t st = (cudaStream_t)stream;
-    dim3 gridc((cols + 31) / 32, 3);
-    lsq_bwd_finalize_cols_kernel<<<gridc, 256, 0, st>>>(colpart, cols, wsl.colslots, scale_mode, g, d_s, d_b4, d_aft, zero_sum);
-    if (d_s && scale_mode == OFQ_SCALE_PER_ROW) {
-        // every partial whose index is congruent to i modulo nscale belongs to scale i (rows is a multiple of period)
-        const long long nscale = (long long)(period < rows ? period : rows) * nseg;
-        lsq_bwd_finalize_rows_kernel<<<(unsigned)((nscale + 31) / 32), 256, 0, st>>>(rowpart, wsl.rowpart_used, nscale, g, d_s);
-    }
+    FinalizeArgs a;
+    a.colpart = workspace + wsl.rowpart_n; a.cols = cols; a.nslots = wsl.colslots; a.scale_mode = scale_mode; a.g = g;
+    a.d_s = d_s; a.d_b4 = d_b4; a.d_aft = d_aft; a.zero_sum = zero_sum;
+    a.rowpart = workspace; a.total = wsl.rowpart_used;
+    // every partial whose index is congruent to i modulo nscale belongs to scale i (rows is a multiple of period)
+    a.nscale = (long long)(period < rows ? period : rows) * nseg;
+    a.blockmax = workspace + wsl.rowpart_n + wsl.colslots * 3 * cols; a.nblk = (int)wsl.nmax;
+    a.v1 = v1; a.n1 = n1; a.v2 = v2; a.n2 = n2; a.mult = mult; a.product = product; a.out4 = out4;
+    a.ncx = (cols + 31) / 32;
+    a.ncb = 3 * a.ncx;
+    a.nrb = (d_s && scale_mode == OFQ_SCALE_PER_ROW) ? (int)((a.nscale + 31) / 32) : 0;
+    lsq_bwd_finalize_kernel<<<(unsigned)(a.ncb + a.nrb + (out4 ? 1 : 0)), 256, 0, (cudaStream_t)stream>>>(a);
     OFQ_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int ofq_lsq_bwd_finalize(const float* workspace, long long rows, int cols, int scale_mode, int period,
+                                    int nseg, float g, float* d_s, float* d_b4, float* d_aft, int zero_sum, void* stream) {
+    return lsq_bwd_finalize_impl(workspace, rows, cols, scale_mode, period, nseg, g, d_s, d_b4, d_aft, zero_sum, nullptr, 0,
+                                 nullptr, 0, 1.f, 0, nullptr, stream);
+}
+
+extern "C" int ofq_lsq_bwd_finalize_scale(const float* workspace, long long rows, int cols, int scale_mode, int period,
+                                          int nseg, float g, float* d_s, float* d_b4, float* d_aft, int zero_sum,
+                                          const float* v1, int n1, const float* v2, int n2, float mult, int product,
+                                          float* out4, void* stream) {
+    OFQ_REQUIRE(out4, "ofq_lsq_bwd_finalize_scale: out4 is required");
+    return lsq_bwd_finalize_impl(workspace, rows, cols, scale_mode, period, nseg, g, d_s, d_b4, d_aft, zero_sum, v1, n1, v2, n2,
+                                 mult, product, out4, stream);
 }
 
 extern "C" long long ofq_absmax_scale_workspace(void) { return 2 + 2 * kAbsmaxMaxBlocks; }
@@ -1103,6 +1316,21 @@ extern "C" int ofq_grad_prep(const float* x, int nb, int R, int C, long long ldx
     OFQ_REQUIRE(!cs || (uintptr_t)cs % 16 == 0, "ofq_grad_prep: cs alignment");
     OFQ_CHECK_ARCH();
     if (rs_period <= 0) rs_period = 0x7fffffff;
+    const bool dense = nb == 1 || (bstride_x == (long long)R * ldx && (!rs || rs_period >= R || R % rs_period == 0));
+    if (!out_t && planes == 1 && dense && (long long)nb * R < 0x7fffffffLL && (C + 127) / 128 <= kStreamCtas &&
+        (!u || (uintptr_t)u % 16 == 0) && (!rowdot || 128 % group == 0)) {
+        const uint32_t rows = (uint32_t)((long long)nb * R);
+        if (out_fmt == OFQ_FMT_F16)
+            grad_prep_stream_kernel<true><<<kStreamCtas, 256, 0, (cudaStream_t)stream>>>(
+                x, rows, (uint32_t)R, C, ldx, cs, rs, (uint32_t)rs_period, scale4, rm_rowscale, (uint16_t*)out_rm, ld_rm, colsum, u,
+                group, rowdot);
+        else
+            grad_prep_stream_kernel<false><<<kStreamCtas, 256, 0, (cudaStream_t)stream>>>(
+                x, rows, (uint32_t)R, C, ldx, cs, rs, (uint32_t)rs_period, scale4, rm_rowscale, (uint16_t*)out_rm, ld_rm, colsum, u,
+                group, rowdot);
+        OFQ_CUDA(cudaGetLastError());
+        return 0;
+    }
     dim3 grid((C + 63) / 64, (R + 63) / 64, nb);
     if (out_fmt == OFQ_FMT_F16)
         grad_prep_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, R, C, ldx, bstride_x, cs, rs, rs_period, planes, scale4, rm_rowscale,

@@ -209,21 +209,248 @@ softmax_quant_bwd_kernel(const float* __restrict__ dPq, const float* __restrict_
     }
 }
 
+
+// ------------------------------------------------------------------------------------------- vectorised paths
+// DeiT-sized rows (N = 197/198, pitch 200) are 16-byte aligned: a lane owns the float4 columns {lane, lane + 32} of a
+// row (8 keys), so a row is two 16-byte loads per lane, probabilities leave as float4, codes as packed 32-bit words and
+// the 16-bit gradient operand as 8-byte stores. The two divisions per element of the scalar path (p = e / sum and
+// v = p / s) are replaced by per-row reciprocals:
+//   p  : Markstein's sequence on a Newton-refined reciprocal of the row sum (q = e r; q += fma(-sum, q, e) r), which is the
+//        correctly rounded quotient for these operands (e in [0, 1], sum in [1, 256]) up to the ulp-level tie class the
+//        DESIGN documents for expf / summation order;
+//   code: rint(p * rcp(s)) unless the product is within 2e-4 of a rounding boundary, where the IEEE quotient decides
+//        (same argument as lsq_code_fast in quant.cu): codes stay bit-exact for the stored probabilities.
+__device__ __forceinline__ float rcp_fast(float s) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(r) : "f"(s));
+    return r;
+}
+// exact rint(clamp(p / s, 0, qhi)) with a cheap quotient; *vq receives the quotient used for the decision
+__device__ __forceinline__ float prob_code(float p, float s, float inv_s, float qhi, float* vq) {
+    float v = __fmul_rn(p, inv_s);
+    float r = rintf(v);
+    const float dv = fabsf(v - r);
+    if (dv > 0.4998f || (dv < 2e-4f && r == qhi)) {     // rounding boundary, or the clamp bound itself (STE mask)
+        v = __fdiv_rn(p, s);
+        r = rintf(v);
+    }
+    *vq = v;
+    return fminf(r, qhi);
+}
+__device__ __forceinline__ uint32_t pack4_u8(float a, float b, float c, float d) {
+    return (uint32_t)(int)a | ((uint32_t)(int)b << 8) | ((uint32_t)(int)c << 16) | ((uint32_t)(int)d << 24);
+}
+
+constexpr int kVecRows = 2;   // rows per warp in flight (4 x 16 B loads per lane)
+
+__global__ void __launch_bounds__(256)
+softmax_quant_vec_kernel(const float* __restrict__ S, long long rows, int N, long long ld,
+                         const float* __restrict__ s_eff, float qhi, float* __restrict__ P,
+                         int8_t* __restrict__ codes, long long ldq, float* __restrict__ rowsum,
+                         uint16_t* __restrict__ codes16, int f16) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const long long r0 = gw * kVecRows;
+    if (r0 >= rows) return;
+    const int nv = (int)(ld >> 2), nq = (int)(ldq >> 2);
+    const int j0 = lane, j1 = lane + 32;
+    const float NEG = -INFINITY;
+    float4 a[kVecRows][2];
+#pragma unroll
+    for (int u = 0; u < kVecRows; ++u) {
+        const long long r = r0 + u;
+        a[u][0] = a[u][1] = make_float4(NEG, NEG, NEG, NEG);
+        if (r < rows) {
+            const float4* sp = reinterpret_cast<const float4*>(S + r * ld);
+            if (j0 < nv) a[u][0] = __ldg(sp + j0);
+            if (j1 < nv) a[u][1] = __ldg(sp + j1);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kVecRows; ++u) {
+        const long long r = r0 + u;
+        if (r >= rows) break;                      // warp-uniform
+        const int n = (int)(r % N);
+        float x[8] = {a[u][0].x, a[u][0].y, a[u][0].z, a[u][0].w, a[u][1].x, a[u][1].y, a[u][1].z, a[u][1].w};
+        float m = NEG;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int col = 4 * (e < 4 ? j0 : j1) + (e & 3);
+            if (col >= N) x[e] = NEG;
+            m = fmaxf(m, x[e]);
+        }
+        m = wmax(m);
+        float sum = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int col = 4 * (e < 4 ? j0 : j1) + (e & 3);
+            x[e] = col < N ? expf(x[e] - m) : 0.f;
+            sum += x[e];
+        }
+        sum = wsum(sum);
+        float rinv = rcp_fast(sum);
+        rinv = fmaf(rinv, fmaf(-sum, rinv, 1.0f), rinv);         // Newton step: rinv = RN(1 / sum) for almost every sum
+        const float s = __ldg(s_eff + n);
+        const float inv_s = rcp_fast(s);
+        float q[8], csum = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float p = __fmul_rn(x[e], rinv);
+            p = fmaf(fmaf(-sum, p, x[e]), rinv, p);              // Markstein correction of the quotient
+            x[e] = p;
+            float vq;
+            q[e] = prob_code(p, s, inv_s, qhi, &vq);
+            csum += q[e];
+        }
+        if (P) {
+            float4* pp = reinterpret_cast<float4*>(P + r * ld);
+            if (j0 < nv) pp[j0] = make_float4(x[0], x[1], x[2], x[3]);
+            if (j1 < nv) pp[j1] = make_float4(x[4], x[5], x[6], x[7]);
+        }
+        uint32_t* cp = reinterpret_cast<uint32_t*>(codes + r * ldq);
+        if (j0 < nq) cp[j0] = pack4_u8(q[0], q[1], q[2], q[3]);     // columns >= N hold p = 0 -> code 0
+        if (j1 < nq) cp[j1] = pack4_u8(q[4], q[5], q[6], q[7]);
+        if (codes16) {     // exact 16-bit copy (same pitch, zero padding): the operand of the dV GEMM of the backward
+            uint2* hp = reinterpret_cast<uint2*>(codes16 + r * ldq);
+            if (j0 < nq) hp[j0] = f16 ? make_uint2(pack_f16x2(q[0], q[1]), pack_f16x2(q[2], q[3]))
+                                      : make_uint2(pack_bf16x2(q[0], q[1]), pack_bf16x2(q[2], q[3]));
+            if (j1 < nq) hp[j1] = f16 ? make_uint2(pack_f16x2(q[4], q[5]), pack_f16x2(q[6], q[7]))
+                                      : make_uint2(pack_bf16x2(q[4], q[5]), pack_bf16x2(q[6], q[7]));
+        }
+        csum = wsum(csum);
+        if (lane == 0 && rowsum) rowsum[r] = s * csum;
+    }
+}
+
+// Backward, single 16-bit output (out_a only, one plane): block = 4 warps, one (b, h) slab per block, a warp walks rows
+// warp, warp + 4, ... two at a time; per-key column sums stay in 8 registers per lane and are folded across the 4 warps
+// once, so colsum is written without atomics.
+template <bool F16>
+__global__ void __launch_bounds__(128)
+softmax_quant_bwd_vec_kernel(const float* __restrict__ dPq, const float* __restrict__ P, int N, long long ld, int H,
+                             const float* __restrict__ s_eff, float qhi, float alpha, float g_s,
+                             const float* __restrict__ ca, int ca_per_head, const float* __restrict__ rb,
+                             const float* __restrict__ scale4, int a_rowscale, uint16_t* __restrict__ out_a,
+                             long long ldo, float* __restrict__ colsum, float* __restrict__ d_s,
+                             float* __restrict__ dS32) {
+    __shared__ float fold[4][kMaxPer * 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int z = blockIdx.x, h = z % H;
+    const int nv = (int)(ld >> 2), no = (int)(ldo >> 2);
+    const int j0 = lane, j1 = lane + 32;
+    const float sc_a = scale4 ? __ldg(scale4 + 0) : 1.f;
+    const float* cav = ca ? (ca_per_head ? ca + (long long)h * N : ca) : nullptr;
+    float cv[8], colacc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int col = 4 * (e < 4 ? j0 : j1) + (e & 3);
+        cv[e] = (cav && col < N) ? __ldg(cav + col) : 1.f;
+        colacc[e] = 0.f;
+    }
+    for (int nb = warp * kVecRows; nb < N; nb += 4 * kVecRows) {
+        float4 pv[kVecRows][2], gv[kVecRows][2];
+#pragma unroll
+        for (int u = 0; u < kVecRows; ++u) {
+            const int n = nb + u;
+            pv[u][0] = pv[u][1] = gv[u][0] = gv[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < N) {
+                const long long ro = ((long long)z * N + n) * ld;
+                const float4* pp = reinterpret_cast<const float4*>(P + ro);
+                const float4* gp = reinterpret_cast<const float4*>(dPq + ro);
+                if (j0 < nv) { pv[u][0] = __ldg(pp + j0); gv[u][0] = __ldg(gp + j0); }
+                if (j1 < nv) { pv[u][1] = __ldg(pp + j1); gv[u][1] = __ldg(gp + j1); }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kVecRows; ++u) {
+            const int n = nb + u;
+            if (n >= N) break;                     // warp-uniform
+            const long long ro = ((long long)z * N + n) * ld;
+            const float s = __ldg(s_eff + n);
+            const float inv_s = rcp_fast(s);
+            float p[8] = {pv[u][0].x, pv[u][0].y, pv[u][0].z, pv[u][0].w, pv[u][1].x, pv[u][1].y, pv[u][1].z, pv[u][1].w};
+            float g[8] = {gv[u][0].x, gv[u][0].y, gv[u][0].z, gv[u][0].w, gv[u][1].x, gv[u][1].y, gv[u][1].z, gv[u][1].w};
+            float dot = 0.f, dsp = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int col = 4 * (e < 4 ? j0 : j1) + (e & 3);
+                if (col >= N) { p[e] = 0.f; g[e] = 0.f; }       // the pitch padding of P / dPq is not defined
+                float v;
+                const float q = prob_code(p[e], s, inv_s, qhi, &v);
+                const bool inside = v <= qhi;                    // v >= 0 always holds for probabilities
+                dsp += g[e] * (inside ? (q - v) : q);
+                g[e] = inside ? g[e] : 0.f;
+                dot += p[e] * g[e];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                dsp += __shfl_xor_sync(0xffffffffu, dsp, o);
+            }
+            if (lane == 0 && d_s) atomicAdd(d_s + n, g_s * dsp);
+            const float rb_raw = rb ? __ldg(rb + n) : 1.f;
+            const float sca_row = a_rowscale ? sc_a * rb_raw : sc_a;
+            float raw[8], va[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                raw[e] = p[e] * (g[e] - dot);                    // gradient w.r.t. the (scaled) logits / additive bias
+                const float ds = alpha * raw[e];                 // gradient w.r.t. the un-scaled q.k product
+                colacc[e] += ds;
+                va[e] = ds * cv[e] * sca_row;                    // columns >= N: p = 0 -> exact zeros in the padding
+            }
+            if (out_a) {
+                uint2* op = reinterpret_cast<uint2*>(out_a + ((long long)z * N + n) * ldo);
+                if (j0 < no) op[j0] = make_uint2(pack16x2<F16>(va[0], va[1]), pack16x2<F16>(va[2], va[3]));
+                if (j1 < no) op[j1] = make_uint2(pack16x2<F16>(va[4], va[5]), pack16x2<F16>(va[6], va[7]));
+            }
+            if (dS32) {
+                float4* dp = reinterpret_cast<float4*>(dS32 + ro);
+                if (j0 < nv) dp[j0] = make_float4(raw[0], raw[1], raw[2], raw[3]);
+                if (j1 < nv) dp[j1] = make_float4(raw[4], raw[5], raw[6], raw[7]);
+            }
+        }
+    }
+    if (colsum) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) fold[warp][(e < 4 ? j0 : j1) * 4 + (e & 3)] = colacc[e];
+        __syncthreads();
+        for (int d = threadIdx.x; d < N; d += blockDim.x)
+            colsum[(long long)z * N + d] = (fold[0][d] + fold[1][d]) + (fold[2][d] + fold[3][d]);
+    }
+}
+
 }  // namespace
 
-extern "C" int ofq_softmax_quant(const float* S, int nz, int N, long long ld, int H, const float* bias,
-                                 const float* mask, int nW, const float* s_eff, int qhi, float* P, int8_t* codes,
-                                 long long ldq, float* rowsum, void* stream) {
+extern "C" int ofq_softmax_quant_ex(const float* S, int nz, int N, long long ld, int H, const float* bias,
+                                    const float* mask, int nW, const float* s_eff, int qhi, float* P, int8_t* codes,
+                                    long long ldq, float* rowsum, void* codes16, int fmt16, void* stream) {
     OFQ_REQUIRE(S && s_eff && codes && nz > 0 && N > 0 && H > 0, "ofq_softmax_quant: bad argument");
     OFQ_REQUIRE(N <= kMaxPer * 32, "ofq_softmax_quant: at most 256 keys per row are supported");
     OFQ_REQUIRE(ld >= N && ldq >= N && qhi > 0 && qhi <= 127, "ofq_softmax_quant: bad pitch or level count");
     OFQ_REQUIRE(!mask || nW > 0, "ofq_softmax_quant: mask needs nW");
     OFQ_CHECK_ARCH();
     const long long rows = (long long)nz * N;
+    const bool vec = !bias && !mask && ld % 4 == 0 && ldq % 4 == 0 && (uintptr_t)S % 16 == 0 && (!P || (uintptr_t)P % 16 == 0) &&
+                     (uintptr_t)codes % 4 == 0 && (!codes16 || (uintptr_t)codes16 % 8 == 0);
+    OFQ_REQUIRE(!codes16 || vec, "ofq_softmax_quant: the 16-bit copy is produced by the vectorised path only "
+                                 "(no bias / mask, pitches that are multiples of 4, aligned pointers)");
+    OFQ_REQUIRE(!codes16 || fmt16 == OFQ_FMT_BF16 || fmt16 == OFQ_FMT_F16, "ofq_softmax_quant: bad 16-bit format");
+    if (vec) {
+        softmax_quant_vec_kernel<<<(unsigned)((rows + 8 * kVecRows - 1) / (8 * kVecRows)), 256, 0, (cudaStream_t)stream>>>(
+            S, rows, N, ld, s_eff, (float)qhi, P, codes, ldq, rowsum, (uint16_t*)codes16, fmt16 == OFQ_FMT_F16);
+        OFQ_CUDA(cudaGetLastError());
+        return 0;
+    }
     softmax_quant_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
         S, nz, N, ld, H, bias, mask, nW > 0 ? nW : 1, s_eff, (float)qhi, P, codes, ldq, rowsum);
     OFQ_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int ofq_softmax_quant(const float* S, int nz, int N, long long ld, int H, const float* bias,
+                                 const float* mask, int nW, const float* s_eff, int qhi, float* P, int8_t* codes,
+                                 long long ldq, float* rowsum, void* stream) {
+    return ofq_softmax_quant_ex(S, nz, N, ld, H, bias, mask, nW, s_eff, qhi, P, codes, ldq, rowsum, nullptr, OFQ_FMT_F16, stream);
 }
 
 extern "C" int ofq_softmax_quant_bwd(const float* dPq, const float* P, int nz, int N, long long ld, int H,
@@ -238,6 +465,22 @@ extern "C" int ofq_softmax_quant_bwd(const float* dPq, const float* P, int nz, i
     OFQ_REQUIRE(planes == 1 || planes == 2, "ofq_softmax_quant_bwd: planes must be 1 or 2");
     OFQ_REQUIRE(out_fmt == OFQ_FMT_BF16 || (out_fmt == OFQ_FMT_F16 && planes == 1), "ofq_softmax_quant_bwd: fp16 output is single-plane");
     OFQ_CHECK_ARCH();
+    // single-output, one-plane requests on 16-byte aligned rows take the vectorised kernel (colsum is then written,
+    // not accumulated: pre-zeroing it is harmless)
+    const bool vec = !out_bt && planes == 1 && ld % 4 == 0 && ldo % 4 == 0 && (uintptr_t)dPq % 16 == 0 && (uintptr_t)P % 16 == 0 &&
+                     (!out_a || (uintptr_t)out_a % 8 == 0) && (!dS32 || (uintptr_t)dS32 % 16 == 0);
+    if (vec) {
+        if (out_fmt == OFQ_FMT_F16)
+            softmax_quant_bwd_vec_kernel<true><<<nz, 128, 0, (cudaStream_t)stream>>>(
+                dPq, P, N, ld, H, s_eff, (float)qhi, alpha, g_s, ca, ca_per_head, rb, scale4, a_rowscale, (uint16_t*)out_a, ldo,
+                colsum, d_s, dS32);
+        else
+            softmax_quant_bwd_vec_kernel<false><<<nz, 128, 0, (cudaStream_t)stream>>>(
+                dPq, P, N, ld, H, s_eff, (float)qhi, alpha, g_s, ca, ca_per_head, rb, scale4, a_rowscale, (uint16_t*)out_a, ldo,
+                colsum, d_s, dS32);
+        OFQ_CUDA(cudaGetLastError());
+        return 0;
+    }
     dim3 grid((N + 31) / 32, nz);
     const size_t smem = (size_t)32 * (N + 1) * sizeof(float);
     if (out_fmt == OFQ_FMT_F16)

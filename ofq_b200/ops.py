@@ -127,47 +127,58 @@ def lsq_effective_scale(alpha: torch.Tensor, g: float, recip: bool = False):
     return out
 
 
+ACT_NONE, ACT_GELU = 0, 1
+
+
 def lsq_quant(x2d: torch.Tensor, b4: torch.Tensor, s_eff: torch.Tensor, mode: int, period: int, nseg: int,
-              qlo: int, qhi: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x2d: [rows, cols] fp32 view (last dim contiguous). Returns int8 codes [rows, cols]."""
+              qlo: int, qhi: int, out: Optional[torch.Tensor] = None, act: int = ACT_NONE, fmt16: Optional[int] = None):
+    """x2d: [rows, cols] fp32 view (last dim contiguous). Returns int8 codes [rows, cols] of Q(act(x) + b4); with fmt16
+    (FMT_BF16 / FMT_F16) returns (codes, exact 16-bit copy [rows, cols]) written in the same pass."""
     _cuda(x2d, b4, s_eff)
     assert x2d.dim() == 2 and x2d.stride(1) == 1 and x2d.dtype == torch.float32
     rows, cols = x2d.shape
     if out is None:
         out = torch.empty((rows, cols), dtype=torch.int8, device=x2d.device)
-    _call("lsq_quant", 1, 5.0 * rows * cols, 0, _lib.load().ofq_lsq_quant, x2d.data_ptr(), rows, cols, x2d.stride(0),
-          b4.data_ptr(), s_eff.data_ptr(), mode, period, nseg, qlo, qhi, out.data_ptr(), out.stride(0), _st())
-    return out
+    if act == ACT_NONE and fmt16 is None:
+        _call("lsq_quant", 1, 5.0 * rows * cols, 0, _lib.load().ofq_lsq_quant, x2d.data_ptr(), rows, cols, x2d.stride(0),
+              b4.data_ptr(), s_eff.data_ptr(), mode, period, nseg, qlo, qhi, out.data_ptr(), out.stride(0), _st())
+        return out
+    out16 = torch.empty((rows, cols), dtype=_T16[fmt16], device=x2d.device) if fmt16 is not None else None
+    _call("lsq_quant", 1, (5.0 + (2 if fmt16 is not None else 0)) * rows * cols, 0, _lib.load().ofq_lsq_quant_ex, x2d.data_ptr(),
+          rows, cols, x2d.stride(0), b4.data_ptr(), s_eff.data_ptr(), mode, period, nseg, qlo, qhi, act, out.data_ptr(),
+          out.stride(0), _ptr(out16), cols, fmt16 if fmt16 is not None else FMT_F16, _st())
+    return out if fmt16 is None else (out, out16)
 
 
 def lsq_bwd(dy2d: torch.Tensor, x2d: torch.Tensor, b4: torch.Tensor, s_eff: torch.Tensor, mode: int, period: int,
             nseg: int, qlo: int, qhi: int, g: float, want_ds: bool = True, want_aft: bool = True, next_scale=None,
-            zero_sum: bool = False):
+            zero_sum: bool = False, act: int = ACT_NONE):
     """Returns (dx [rows, cols], d_s, d_b4 [cols], d_aft [cols] | None).  next_scale = (v1, v2, mult, product): additionally
     returns the fp16 range scales (absmax_scale layout) of dx*v1[c] / dx*v2[r] for the GEMM operand made from dx,
-    derived from max|dx| at no extra pass over dx."""
+    derived from max|dx| at no extra pass over dx.  act: the quantizer saw act(x2d) (lsq_quant(act=...)); dx is then the
+    gradient w.r.t. the pre-activation x2d."""
     _cuda(dy2d, x2d)
     assert dy2d.dim() == 2 and dy2d.stride(1) == 1 and x2d.stride(1) == 1
     rows, cols = dy2d.shape
     lib = _lib.load()
     ws = torch.empty(lib.ofq_lsq_bwd_workspace(rows, cols, nseg), dtype=torch.float32, device=dy2d.device)
     dx = torch.empty((rows, cols), dtype=torch.float32, device=dy2d.device)
-    _call("lsq_bwd", 1, 12.0 * rows * cols, 0, lib.ofq_lsq_bwd, dy2d.data_ptr(), dy2d.stride(0), x2d.data_ptr(),
-          x2d.stride(0), rows, cols, b4.data_ptr(), s_eff.data_ptr(), mode, period, nseg, qlo, qhi, dx.data_ptr(),
+    _call("lsq_bwd", 1, 12.0 * rows * cols, 0, lib.ofq_lsq_bwd_act, dy2d.data_ptr(), dy2d.stride(0), x2d.data_ptr(),
+          x2d.stride(0), rows, cols, b4.data_ptr(), s_eff.data_ptr(), mode, period, nseg, qlo, qhi, act, dx.data_ptr(),
           dx.stride(0), ws.data_ptr(), _st())
     ns = cols if mode == PER_COL else min(period, rows) * nseg
     d_s = torch.empty(ns, dtype=torch.float32, device=dy2d.device) if want_ds else None
     d_b4 = torch.empty(cols, dtype=torch.float32, device=dy2d.device)
     d_aft = torch.empty(cols, dtype=torch.float32, device=dy2d.device) if want_aft else None
-    _call("lsq_bwd_finalize", 1, 4.0 * ws.numel(), 0, lib.ofq_lsq_bwd_finalize, ws.data_ptr(), rows, cols, mode, period,
-          nseg, float(g), _ptr(d_s), d_b4.data_ptr(), _ptr(d_aft), int(zero_sum), _st())
     if next_scale is None:
+        _call("lsq_bwd_finalize", 1, 4.0 * ws.numel(), 0, lib.ofq_lsq_bwd_finalize, ws.data_ptr(), rows, cols, mode, period,
+              nseg, float(g), _ptr(d_s), d_b4.data_ptr(), _ptr(d_aft), int(zero_sum), _st())
         return dx, d_s, d_b4, d_aft
     v1, v2, mult, product = next_scale
     sc = torch.empty(4, dtype=torch.float32, device=dy2d.device)
-    _call("lsq_bwd_scale", 1, 0.0, 0, lib.ofq_lsq_bwd_scale, ws.data_ptr(), rows, cols, nseg, _ptr(v1),
-          0 if v1 is None else v1.numel(), _ptr(v2), 0 if v2 is None else v2.numel(), float(mult), int(product),
-          sc.data_ptr(), _st())
+    _call("lsq_bwd_finalize", 1, 4.0 * ws.numel(), 0, lib.ofq_lsq_bwd_finalize_scale, ws.data_ptr(), rows, cols, mode, period,
+          nseg, float(g), _ptr(d_s), d_b4.data_ptr(), _ptr(d_aft), int(zero_sum), _ptr(v1), 0 if v1 is None else v1.numel(),
+          _ptr(v2), 0 if v2 is None else v2.numel(), float(mult), int(product), sc.data_ptr(), _st())
     return dx, d_s, d_b4, d_aft, sc
 
 
@@ -252,16 +263,21 @@ def codes_rowdot(codes2d: torch.Tensor, nseg: int, u: torch.Tensor) -> torch.Ten
 
 # ------------------------------------------------------------------------------------------------ softmax
 def softmax_quant(S: torch.Tensor, N: int, H: int, s_eff: torch.Tensor, qhi: int, *, bias=None, mask=None, nW: int = 0,
-                  save_p: bool = True):
-    """S: [nz, N, ld] fp32 scaled logits. Returns (P fp32 [nz,N,ld] | None, codes int8 [nz,N,ldq], rowsum [nz,N])."""
+                  save_p: bool = True, fmt16: Optional[int] = None):
+    """S: [nz, N, ld] fp32 scaled logits. Returns (P fp32 [nz,N,ld] | None, codes int8 [nz,N,ldq], rowsum [nz,N]) and, with
+    fmt16 (no bias / mask), a fourth element: the exact 16-bit copy of the codes [nz,N,ldq]."""
     _cuda(S, s_eff)
     nz, _, ld = S.shape
     ldq = round_up(N, 16)
     P = torch.empty_like(S) if save_p else None
     codes = torch.empty((nz, N, ldq), dtype=torch.int8, device=S.device)
     rowsum = torch.empty((nz, N), dtype=torch.float32, device=S.device)
-    _call("softmax_quant", 1, nz * N * N * (5.0 + (4 if save_p else 0)), 0, _lib.load().ofq_softmax_quant, S.data_ptr(), nz,
-          N, ld, H, _ptr(bias), _ptr(mask), nW, s_eff.data_ptr(), qhi, _ptr(P), codes.data_ptr(), ldq, rowsum.data_ptr(), _st())
+    c16 = torch.empty((nz, N, ldq), dtype=_T16[fmt16], device=S.device) if fmt16 is not None else None
+    _call("softmax_quant", 1, nz * N * N * (5.0 + (4 if save_p else 0) + (2 if fmt16 is not None else 0)), 0,
+          _lib.load().ofq_softmax_quant_ex, S.data_ptr(), nz, N, ld, H, _ptr(bias), _ptr(mask), nW, s_eff.data_ptr(), qhi,
+          _ptr(P), codes.data_ptr(), ldq, rowsum.data_ptr(), _ptr(c16), fmt16 if fmt16 is not None else FMT_F16, _st())
+    if fmt16 is not None:
+        return P, codes, rowsum, c16
     return P, codes, rowsum
 
 

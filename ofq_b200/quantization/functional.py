@@ -15,7 +15,7 @@ from typing import Optional
 import torch
 
 from .. import ops
-from ..ops import FMT_BF16, FMT_F16, GEMM_BF16, GEMM_F16, GEMM_I8, PER_COL, PER_ROW, round_up, vec
+from ..ops import ACT_GELU, ACT_NONE, FMT_BF16, FMT_F16, GEMM_BF16, GEMM_F16, GEMM_I8, PER_COL, PER_ROW, round_up, vec
 
 NUM_SMS = 148
 # Number format of the real-valued (gradient) operand of every backward GEMM; the integer-code operand is exact in all:
@@ -119,12 +119,26 @@ def _linear_backward(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulate_dx
 
 
 # ====================================================================================== QLinear
+class MlpLink:
+    """Side channel between the two QLinearFn nodes of a QMLP: fc1's forward leaves its folded scale vectors here, the
+    backward of fc2 (which runs first) turns the max |d fc1_out| its LSQ pass sees anyway into the fp16 range scale of
+    fc1's gradient operand (`sc`), and fc1's backward then skips its absmax pass."""
+    __slots__ = ("cs", "se", "sc")
+
+    def __init__(self):
+        self.cs = self.se = self.sc = None
+
+
 class QLinearFn(torch.autograd.Function):
     """QLinear.forward (qlinear.py:58-73): StatsQ weight codes, (move_b4 -> LSQ -> move_aft) input codes,
-    int8 tcgen05 GEMM with the scales / shift / bias in the epilogue."""
+    int8 tcgen05 GEMM with the scales / shift / bias in the epilogue.
+    act = ACT_GELU: the layer computes QLinear(GELU(x)) (fc2 of QMLP, qlinear.py:123-136) with the activation fused into
+    the quantizer pass; x is then the saved fc1 output and the returned gradient is w.r.t. that pre-activation.
+    link / role: optional MlpLink shared by fc1 (role 1) and fc2 (role 2) of one QMLP."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, b4, aft, s, wbits: int, abits: int, unsigned: bool):
+    def forward(ctx, x, weight, bias, b4, aft, s, wbits: int, abits: int, unsigned: bool, act: int = ACT_NONE,
+                link: Optional[MlpLink] = None, role: int = 0):
         K = x.shape[-1]
         P = x.shape[-2]
         xc = x.contiguous()
@@ -135,27 +149,39 @@ class QLinearFn(torch.autograd.Function):
         g = grad_scale_factor(hi, x.numel() // P)
         se2 = ops.lsq_effective_scale(s, g, recip=True)
         se = se2[0]
-        qx = ops.lsq_quant(x2d, b4, se, PER_ROW, P, 1, lo, hi)
+        qx16 = None
+        if F16 and any(ctx.needs_input_grad):
+            qx, qx16 = ops.lsq_quant(x2d, b4, se, PER_ROW, P, 1, lo, hi, act=act, fmt16=FMT)
+        else:
+            qx = ops.lsq_quant(x2d, b4, se, PER_ROW, P, 1, lo, hi, act=act)
         wc, colscale, _, colterm, _, inv_cs = ops.statsq_codes(weight, wbits, aft=aft, bias=bias, want_inv=True)
         out = torch.empty((M, Nout), dtype=torch.float32, device=x.device)
         ops.gemm(GEMM_I8, qx, (K, 0, 0, 0), wc, (K, 0, 0, 0), out, (Nout, 0, 0), M, Nout, K,
                  rs=vec(se, P), cs=vec(colscale), ct=vec(colterm))
-        ctx.save_for_backward(xc, qx, wc, colscale, inv_cs, se2, b4, aft)
-        ctx.cfg = (P, lo, hi, g, bias is not None)
+        if link is not None and role == 1:
+            link.cs, link.se, link.sc = colscale, se, None
+        ctx.save_for_backward(xc, qx, wc, colscale, inv_cs, se2, b4, aft, qx16)
+        ctx.cfg = (P, lo, hi, g, bias is not None, act, link, role)
         return out.view(*x.shape[:-1], Nout)
 
     @staticmethod
     def backward(ctx, dY):
-        xc, qx, wc, colscale, inv_cs, se2, b4, aft = ctx.saved_tensors
-        P, lo, hi, g, has_bias = ctx.cfg
+        xc, qx, wc, colscale, inv_cs, se2, b4, aft, qx16 = ctx.saved_tensors
+        P, lo, hi, g, has_bias, act, link, role = ctx.cfg
         K = xc.shape[-1]
         x2d = xc.view(-1, K)
         M = x2d.shape[0]
         dY2d = dY.contiguous().view(M, -1)
         dxhat = torch.empty((M, K), dtype=torch.float32, device=dY.device)
-        dW, dbias, _ = _linear_backward(dY2d, qx, wc, (colscale, inv_cs), se2, P, aft, dxhat, False)
-        dx, ds, db4, daft = ops.lsq_bwd(dxhat, x2d, b4, se2[0], PER_ROW, P, 1, lo, hi, g)
-        return dx.view_as(xc), dW, (dbias if has_bias else None), db4, daft, ds, None, None, None
+        sc = link.sc if (link is not None and role == 1) else None
+        dW, dbias, _ = _linear_backward(dY2d, qx, wc, (colscale, inv_cs), se2, P, aft, dxhat, False, qx16, sc=sc)
+        nxt = None
+        if F16 and link is not None and role == 2 and link.cs is not None and link.cs.shape[0] == K:
+            nxt = (link.cs, link.se, 1.0, True)
+        dx, ds, db4, daft, *scn = ops.lsq_bwd(dxhat, x2d, b4, se2[0], PER_ROW, P, 1, lo, hi, g, act=act, next_scale=nxt)
+        if nxt is not None:
+            link.sc = scn[0]
+        return dx.view_as(xc), dW, (dbias if has_bias else None), db4, daft, ds, None, None, None, None, None, None
 
 
 # ====================================================================================== standalone LSQ
@@ -207,7 +233,7 @@ def _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C):
     return out
 
 
-def _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS):
+def _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=None, qp16=None):
     """fp16 backward of P_hat V_hat with ONE copy A16[b,n,c] = fp16(dO * se_v[c] * se_p[n] * sc):
         dP_hat[z,n,d]  = 1/(se_p[n] sc) * sum_j A16[b,n,hj] qv[b,d,hj] + sum_j dO[b,n,hj] v_aft[hj]
         dv_hat[b,d,hj] = 1/(se_v[hj] sc) * sum_n qp[z,n,d] A16[b,n,hj]                    (both operands MN-major)"""
@@ -216,21 +242,24 @@ def _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS):
     prep = ops.grad_prep(dO, B, N, C, C, N * C, cs=sv2[0], rs=sp2[0], rs_period=N, want_rm=True, u=v_aft, group=hd,
                          fmt=FMT, scale4=sc, rm_rowscale=True)
     a16 = prep["rm"]                                                     # [1, B, N, C]
-    qv16 = ops.codes_to_bf16(qv, B, N, C, C, N * C, False, FMT)          # [B, N, C]
+    if qv16 is None:
+        qv16 = ops.codes_to_bf16(qv, B, N, C, C, N * C, False, FMT)      # [B, N, C]
     dPq = torch.empty((B * H, N, ldS), dtype=torch.float32, device=dO.device)
     ops.gemm(GEMM_BWD, a16, (C, 0, hd, N * C), qv16, (C, 0, hd, N * C), dPq, (ldS, N * ldS, H * N * ldS), N, N, hd,
              nb1=H, nb2=B, rs=vec(sp2[1], N), cs=_scalar(sc), rt=vec(prep["rowdot"], 0, N, H * N))
-    qp16 = ops.codes_to_bf16(qp, B * H, N, ldq, ldq, N * ldq, False, FMT)    # [B*H, N, ldq]
+    if qp16 is None:
+        qp16 = ops.codes_to_bf16(qp, B * H, N, ldq, ldq, N * ldq, False, FMT)    # [B*H, N, ldq]
     dvhat = torch.empty((B, N, C), dtype=torch.float32, device=dO.device)
     ops.gemm(GEMM_BWD, qp16, (ldq, 0, N * ldq, H * N * ldq), a16, (C, 0, hd, N * C), dvhat, (C, hd, N * C), N, hd, N,
              nb1=H, nb2=B, a_mn=True, b_mn=True, rs=_scalar(sc), cs=vec(sv2[1], 0, hd))
     return dPq, dvhat
 
 
-def _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS):
-    """Returns (dPq [B*H,N,ldS] fp32, dvhat [B,N,C] fp32). sp2 / sv2 = [scale, 1/scale] of the probability / V quantizer."""
+def _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=None, qp16=None):
+    """Returns (dPq [B*H,N,ldS] fp32, dvhat [B,N,C] fp32). sp2 / sv2 = [scale, 1/scale] of the probability / V quantizer.
+    qv16 / qp16: exact 16-bit copies of the codes left by the forward quantizer passes (fp16 mode)."""
     if F16:
-        return _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS)
+        return _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16, qp16)
     se_p, se_v = sp2[0], sv2[0]
     hd = C // H
     prep = ops.grad_prep(dO, B, N, C, C, N * C, cs=se_v, rs=se_p, rs_period=N, want_rm=True, want_t=True,
@@ -269,7 +298,12 @@ class QKRAttnCoreFn(torch.autograd.Function):
         g_x = grad_scale_factor(hi, B * C)
         sx2 = ops.lsq_effective_scale(s_x, g_x, recip=True)
         se_x = sx2[0]
-        qx = ops.lsq_quant(x2d, x_b4, se_x, PER_ROW, N, 1, lo, hi)
+        need_grad = any(ctx.needs_input_grad)
+        f16 = FMT if (F16 and need_grad) else None     # every quantizer pass also leaves the exact fp16 copy the backward GEMMs read
+        qx16 = qv16 = qk16 = qp16 = None
+        qx = ops.lsq_quant(x2d, x_b4, se_x, PER_ROW, N, 1, lo, hi, fmt16=f16)
+        if f16 is not None:
+            qx, qx16 = qx
         # --- V branch (attention.py:179-186)
         wvc, cs_v, _, ct_v, _, ics_v = ops.statsq_codes(wv, wbits, aft=x_aft, bias=bv, want_inv=True)
         v_out = torch.empty((M, C), dtype=torch.float32, device=dev)
@@ -278,7 +312,9 @@ class QKRAttnCoreFn(torch.autograd.Function):
         g_v = grad_scale_factor(hi, B * N)
         sv2 = ops.lsq_effective_scale(s_v, g_v, recip=True)
         se_v = sv2[0]
-        qv = ops.lsq_quant(v_out, v_b4, se_v, PER_COL, 1, 1, lo, hi)
+        qv = ops.lsq_quant(v_out, v_b4, se_v, PER_COL, 1, 1, lo, hi, fmt16=f16)
+        if f16 is not None:
+            qv, qv16 = qv
         # --- QK branch: one StatsQ on the per-head product W_q^T W_k (attention.py:190-196)
         wqk = ops.wqk_compose(wq, wk, H)
         wqkc, cs_qk, _, ct_qk, _, ics_qk = ops.statsq_codes(wqk, wbits, aft=x_aft, want_inv=True)
@@ -288,7 +324,9 @@ class QKRAttnCoreFn(torch.autograd.Function):
         g_k = grad_scale_factor(hi, B * C)
         sk2 = ops.lsq_effective_scale(s_k, g_k, recip=True)          # [2, N*H], index n*H + h
         se_k = sk2[0]
-        qk = ops.lsq_quant(qkx, k_b4, se_k, PER_ROW, N, H, lo, hi)   # [M, H*C]
+        qk = ops.lsq_quant(qkx, k_b4, se_k, PER_ROW, N, H, lo, hi, fmt16=f16)   # [M, H*C]
+        if f16 is not None:
+            qk, qk16 = qk
         # --- scores (attention.py:210-213): S = x_hat . k_hat^T * scale; terms constant along the softmax
         #     axis are dropped (they cancel exactly in softmax and in its gradient)
         ctS = ops.codes_rowdot(qk, H, x_aft.repeat(H))               # [M, H]: sum_c x_aft[c] qk[b,d,h,c]
@@ -304,13 +342,15 @@ class QKRAttnCoreFn(torch.autograd.Function):
         g_p = grad_scale_factor(hiu, B * H * N)
         sp2 = ops.lsq_effective_scale(s_p, g_p, recip=True)
         se_p = sp2[0]
-        need_grad = any(ctx.needs_input_grad)
-        P, qp, rowsum = ops.softmax_quant(S, N, H, se_p, hiu, bias=attn_bias, mask=attn_mask, nW=nW, save_p=need_grad)
+        if f16 is not None and attn_bias is None and attn_mask is None:
+            P, qp, rowsum, qp16 = ops.softmax_quant(S, N, H, se_p, hiu, save_p=need_grad, fmt16=f16)
+        else:
+            P, qp, rowsum = ops.softmax_quant(S, N, H, se_p, hiu, bias=attn_bias, mask=attn_mask, nW=nW, save_p=need_grad)
         ldq = qp.shape[-1]
         del S
         out = _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C)
         ctx.save_for_backward(xc, wq, wk, x_b4, x_aft, v_b4, v_aft, k_b4, k_aft, qx, sx2, wvc, cs_v, ics_v, v_out, qv, sv2,
-                              wqkc, cs_qk, ics_qk, qkx, qk, sk2, sk2_hn, P, qp, sp2)
+                              wqkc, cs_qk, ics_qk, qkx, qk, sk2, sk2_hn, P, qp, sp2, qx16, qv16, qk16, qp16)
         ctx.cfg = (B, N, C, H, lo, hi, hiu, scale, g_x, g_v, g_k, g_p, ldS, ldq, bv is not None,
                    attn_bias is not None)
         return out
@@ -318,18 +358,18 @@ class QKRAttnCoreFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dO):
         (xc, wq, wk, x_b4, x_aft, v_b4, v_aft, k_b4, k_aft, qx, sx2, wvc, cs_v, ics_v, v_out, qv, sv2, wqkc, cs_qk, ics_qk,
-         qkx, qk, sk2, sk2_hn, P, qp, sp2) = ctx.saved_tensors
+         qkx, qk, sk2, sk2_hn, P, qp, sp2, qx16, qv16, qk16, qp16) = ctx.saved_tensors
         B, N, C, H, lo, hi, hiu, scale, g_x, g_v, g_k, g_p, ldS, ldq, has_bv, has_bias = ctx.cfg
         se_x, se_v, se_k, se_p, se_k_hn = sx2[0], sv2[0], sk2[0], sp2[0], sk2_hn[0]
         M = B * N
         dev = dO.device
         dO = dO.contiguous()
-        dPq, dvhat = _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS)
+        dPq, dvhat = _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16, qp16)
         # --- V quantizer and V linear
         dv_out, ds_v, dvb4, dvaft, *sc_v = ops.lsq_bwd(dvhat.view(M, C), v_out, v_b4, se_v, PER_COL, 1, 1, lo, hi, g_v,
                                                        next_scale=(cs_v, se_x, 1.0, True) if F16 else None)
         dxhat = torch.empty((M, C), dtype=torch.float32, device=dev)
-        dWv, dbv, qx_op = _linear_backward(dv_out, qx, wvc, (cs_v, ics_v), sx2, N, x_aft, dxhat, False,
+        dWv, dbv, qx_op = _linear_backward(dv_out, qx, wvc, (cs_v, ics_v), sx2, N, x_aft, dxhat, False, qx16,
                                            sc=sc_v[0] if sc_v else None)
         # --- softmax + probability quantizer, then the two score GEMMs
         if F16:
@@ -341,7 +381,8 @@ class QKRAttnCoreFn(torch.autograd.Function):
             slab = N * ldo
             del dPq
             # d x_hat[b,n,c] += 1/(se_x[n] sc) sum_h sum_d dS16[b,h,n,d] qk[b,d,h,c]      (heads = outer-K, B MN-major)
-            qk16 = ops.codes_to_bf16(qk, 1, M, H * C, H * C, 0, False, FMT)         # [1, M, H*C] = [b][d][h][c]
+            if qk16 is None:
+                qk16 = ops.codes_to_bf16(qk, 1, M, H * C, H * C, 0, False, FMT)     # [1, M, H*C] = [b][d][h][c]
             ops.gemm(GEMM_BWD, dS16, (ldo, slab, H * slab, 0), qk16, (H * C, C, N * H * C, 0), dxhat, (C, N * C, 0),
                      N, C, N, k2=H, nb1=B, accumulate=True, b_mn=True, rs=vec(sx2[1], N), cs=_scalar(sc))
             # d k_hat[b,d,h,c] = 1/(se_k[h,d] sc) sum_n dS16[b,h,n,d] qx[b,n,c] + colsum_dS[z,d] x_aft[c]

@@ -7,7 +7,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ...host.deit import Mlp
-from ..functional import QLinearFn
+from ...ops import ACT_GELU, ACT_NONE
+from ..functional import MlpLink, QLinearFn
 from ..quantizer.lsq import (LsqQuantizer, LsqQuantizer4Conv2d, LsqQuantizer4head_input, LsqQuantizer4img,
                              LsqQuantizerWeight)
 from ..quantizer.statsq import StatsQuantizer
@@ -60,14 +61,17 @@ class QLinear(nn.Linear):
         self.move_b4 = LearnableBias(self.weight.shape[1])
         self.move_aft = LearnableBias(self.weight.shape[1])
 
-    def forward(self, input):
+    def forward(self, input, act: int = ACT_NONE, link=None, role: int = 0):
+        """act / link / role are used by QMLP only (GELU fused into this layer's input quantizer, see QLinearFn);
+        the reference signature forward(input) is unchanged."""
         if self.weight_quant_method != "statsq":
             raise ValueError("Unknown quant_method")
         q = self.input_quant_fn
         if not q.initialized_alpha:
-            q.init_from(input.detach() + self.move_b4.bias)
+            seen = F.gelu(input.detach()) if act == ACT_GELU else input.detach()
+            q.init_from(seen + self.move_b4.bias)
         return QLinearFn.apply(input, self.weight, self.bias, self.move_b4.bias, self.move_aft.bias, q.s,
-                               self.weight_bits, self.input_bits, not self.symmetric)
+                               self.weight_bits, self.input_bits, not self.symmetric, act, link, role)
 
     def extra_repr(self):
         return (f"act_bit={self.input_bits}, weight_bit={self.weight_bits}, act_all_positive={not self.symmetric}, "
@@ -95,8 +99,21 @@ class QMLP(Mlp):
         self.fc2 = QLinear(m=m.fc2, symmetric=False, **common)
 
     def forward(self, x):
-        x = self.drop1(self.act(self.fc1(x)))
-        return self.drop2(self.fc2(x))
+        return qmlp_forward(self, x)
+
+
+def qmlp_forward(mlp, x):
+    """fc2(drop(GELU(fc1(x)))) (qlinear.py:123-136). With nn.GELU() and no active dropout in between, the activation is
+    evaluated inside fc2's input-quantizer kernel (forward) and inside its LSQ backward kernel (GELU'), so the GELU output
+    and its gradient never travel through HBM."""
+    fused = (type(mlp.act) is nn.GELU and getattr(mlp.act, "approximate", "none") == "none" and x.is_cuda
+             and (not mlp.training or getattr(mlp.drop1, "p", 0.0) == 0.0) and type(mlp.fc2) is QLinear)
+    if not fused:
+        x = mlp.drop1(mlp.act(mlp.fc1(x)))
+        return mlp.drop2(mlp.fc2(x))
+    link = MlpLink()
+    h = mlp.fc1(x, ACT_NONE, link, 1)
+    return mlp.drop2(mlp.fc2(h, ACT_GELU, link, 2))
 
 
 class LSQ_QConv2d(nn.Conv2d):

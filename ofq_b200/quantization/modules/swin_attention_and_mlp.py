@@ -13,7 +13,7 @@ from ..quantizer.lsq import LsqQuantizer, LsqQuantizer4v
 from ..quantizer.statsq import StatsQuantizer, StatsQuantizer_specific_4_qkreparam_cga
 from .attention import QAttention, QAttention_qkreparam, _qlinear_kwargs
 from .qbias import LearnableBias
-from .qlinear import LSQ_input, QLinear
+from .qlinear import LSQ_input, QLinear, qmlp_forward
 
 
 class QMLP_swin(nn.Module):
@@ -37,7 +37,7 @@ class QMLP_swin(nn.Module):
         self.drop2 = m[4]
 
     def forward(self, x):
-        return self.drop2(self.fc2(self.drop1(self.act(self.fc1(x)))))
+        return qmlp_forward(self, x)
 
 
 class _SwinWindows:

@@ -167,6 +167,49 @@ def test_lsq_backward(ops, cols, nseg, mode):
     assert rel_err(daft.cpu(), aft.grad) < 1e-5
 
 
+@pytest.mark.parametrize("cols", [1536, 200])
+def test_lsq_gelu_fused_and_fp16_copy(ops, cols):
+    """fc2 of QMLP: codes = Q(GELU(h) + b4) with the activation evaluated inside the quantizer pass (cols = 1536: streaming
+    kernels, cols = 200: generic kernels), the exact fp16 copy of the codes written in the same pass, and the backward that
+    recomputes GELU(h) and returns the gradient w.r.t. h together with the fp16 range scale of the next GEMM operand."""
+    torch.manual_seed(6)
+    B, N, bit = 3, 66, 2
+    lo, hi = O.lsq_levels(bit, True)
+    h = (torch.randn(B, N, cols) * 1.5).requires_grad_(True)
+    b4 = (torch.randn(cols) * 0.05).requires_grad_(True)
+    aft = torch.zeros(cols, requires_grad=True)
+    a = torch.nn.functional.gelu(h)
+    xs = a + b4
+    s = (O.lsq_init_rows(xs.detach(), hi, True) * torch.linspace(0.4, 1.6, N)).requires_grad_(True)
+    y = O.lsq_rows(xs, s, bit, True) + aft
+    dy = torch.randn(B, N, cols)
+    y.backward(dy)
+    g = _g(hi, B * cols)
+    se = ops.lsq_effective_scale(dev(s.detach()), g)
+    hd = dev(h.detach()).view(B * N, cols)
+    codes, c16 = ops.lsq_quant(hd, dev(b4.detach()), se, ops.PER_ROW, N, 1, lo, hi, act=ops.ACT_GELU, fmt16=ops.FMT_F16)
+    assert c16.dtype == torch.float16 and torch.equal(c16.float(), codes.float())
+    # exact w.r.t. the GELU the GPU evaluates (ATen's formula); against the CPU's erf only rounding ties may differ
+    a_gpu = torch.nn.functional.gelu(dev(h.detach())).cpu()
+    ref_gpu = O.lsq_codes_rows(a_gpu + b4.detach(), s.detach(), bit, True)
+    mine = codes.cpu().int().view(B, N, cols)
+    assert (mine != ref_gpu).float().mean() < 1e-5
+    ref_cpu = O.lsq_codes_rows(xs.detach(), s.detach(), bit, True)
+    assert (mine != ref_cpu).float().mean() < 1e-4
+    cs = torch.rand(cols) + 0.5
+    dx, ds, db4, daft, sc = ops.lsq_bwd(dev(dy).view(B * N, cols), hd, dev(b4.detach()), se, ops.PER_ROW, N, 1, lo, hi, g,
+                                        act=ops.ACT_GELU, next_scale=(dev(cs), se, 1.0, True))
+    assert rel_err(dx.cpu().view(B, N, cols), h.grad) < 1e-5
+    assert rel_err(ds.cpu(), s.grad) < 1e-4
+    assert rel_err(db4.cpu(), b4.grad) < 1e-5
+    assert rel_err(daft.cpu(), aft.grad) < 1e-5
+    # range scale: a power of two that places max|dx| * max|cs| * max|se| inside fp16's range with head-room
+    bound = dx.abs().max().item() * cs.max().item() * se.max().item()
+    sc = sc.cpu()
+    assert sc[0] * sc[1] == 1.0 and math.log2(sc[0].item()) == int(math.log2(sc[0].item()))
+    assert 2.0 ** 14 <= bound * sc[0].item() < 2.0 ** 15
+
+
 # ------------------------------------------------------------------------------------------------ GEMM engine
 @pytest.mark.parametrize("M,N,K", [(128, 128, 128), (1584, 192, 192), (25344, 384, 384), (777, 200, 1536), (198, 198, 64)])
 def test_gemm_i8_exact(ops, M, N, K):
@@ -331,6 +374,27 @@ def test_gemm_mn_major_batched(ops):
     assert rel_err(out, ref) < 1e-5
 
 
+@pytest.mark.parametrize("nb,R,Cc,group", [(1, 1000, 384, 64), (3, 198, 384, 64), (4, 49, 96, 32), (1, 777, 1536, 64), (2, 50, 200, 0)])
+def test_grad_prep_streaming_single_copy(ops, nb, R, Cc, group):
+    """The single row-major fp16 copy of the fp16 backward (x * cs[c] * rs[r] * scale), with column sums and per-head row
+    dots, produced by the streaming kernel (no transposed output requested)."""
+    torch.manual_seed(21)
+    x = torch.randn(nb, R, Cc, device="cuda") * 1e-4
+    cs = torch.rand(Cc, device="cuda") * 0.05 + 0.01
+    rs = torch.rand(R, device="cuda") + 0.5
+    u = torch.randn(Cc, device="cuda") if group else None
+    sc = ops.absmax_scale(x, nb, R, Cc, Cc, R * Cc, cs=cs, rs=rs, rs_period=R, product=True)
+    o = ops.grad_prep(x, nb, R, Cc, Cc, R * Cc, cs=cs, rs=rs, rs_period=R, want_rm=True, want_colsum=True, u=u,
+                      group=group or 64, fmt=ops.FMT_F16, scale4=sc, rm_rowscale=True)
+    ref = x * cs * (sc[0] * rs)[None, :, None]
+    assert rel_err(o["rm"][0].float(), ref) < 4e-4                                # fp16 rounding: 11 significant bits
+    assert float((o["rm"][0].float() - ref).abs().max()) <= float(ref.abs().max()) * 2.0 ** -11
+    assert rel_err(o["colsum"], x.sum((0, 1))) < 1e-5
+    if group:
+        rd = (x * u).view(nb, R, Cc // group, group).sum(-1).permute(0, 2, 1)
+        assert rel_err(o["rowdot"], rd) < 1e-5
+
+
 def test_absmax_scale_and_fp16_prep(ops):
     """Range-scaled fp16 operands (backward mode "f16"): the power-of-two scale places the operand's absmax in
     [2^14, 2^15), the fp16 planes are the correctly rounded scaled values and the GEMM un-scales in its epilogue."""
@@ -464,6 +528,50 @@ def test_softmax_quant_backward(ops):
     assert a2.shape == (B, 2, H, N, ldo)
     assert rel_err((a2[:, 0].float() + a2[:, 1].float()).cpu()[..., :N], dS * ca.view(1, H, 1, N)) < 2e-5
     assert rel_err((bt2[:, 0].float() + bt2[:, 1].float()).cpu()[..., :N], (dS * rb.view(1, 1, N, 1)).transpose(2, 3)) < 2e-5
+
+
+@pytest.mark.parametrize("N,H,B", [(198, 6, 3), (197, 3, 2), (49, 3, 5)])
+def test_softmax_quant_vectorised_single_f16(ops, N, H, B):
+    """The 16-byte-aligned fast paths (forward, and the single-copy fp16 backward the DeiT step uses): pitch padding of the
+    inputs is undefined (NaN here) and must never be read into a result; padding of the outputs is zero."""
+    torch.manual_seed(14)
+    bit = 2
+    lo, hi = O.lsq_levels(bit, True)
+    ld = ops.round_up(N, 4)
+    S = (torch.randn(B, H, N, N) * 2).requires_grad_(True)
+    alpha = 0.125
+    prob = torch.softmax(S * alpha, dim=-1)
+    s = (O.lsq_init_rows(prob.detach(), hi, True) * torch.linspace(0.5, 1.5, N)).requires_grad_(True)
+    pq = O.lsq_rows(prob, s, bit, True)
+    dPq = torch.randn(B, H, N, N)
+    pq.backward(dPq)
+    g = _g(hi, B * H * N)
+    se = ops.lsq_effective_scale(dev(s.detach()), g)
+    Sp = torch.full((B * H, N, ld), float("nan"))
+    Sp[..., :N] = (S.detach() * alpha).view(B * H, N, N)
+    P, codes, rowsum = ops.softmax_quant(dev(Sp), N, H, se, hi)
+    Pc = P.cpu()[..., :N].view(B, H, N, N)
+    assert rel_err(Pc, prob.detach()) < 1e-6
+    ref_codes = O.lsq_codes_rows(Pc, s.detach(), bit, True)
+    assert torch.equal(codes.cpu()[..., :N].int().view(B, H, N, N), ref_codes)      # exact for the stored probabilities
+    assert bool((codes.cpu()[..., N:] == 0).all())
+    assert rel_err(rowsum.cpu().view(B, H, N), ref_codes.float().sum(-1) * se.cpu().view(1, 1, N)) < 1e-6
+    dP = torch.full((B * H, N, ld), float("nan"))
+    dP[..., :N] = dPq.view(B * H, N, N)
+    ca = torch.rand(H, N) + 0.5
+    rb = torch.rand(N) + 0.5
+    sc = torch.tensor([64.0, 1.0 / 64.0, 1.0, 1.0])
+    out_a, out_bt, ldo, colsum, d_s, ds32 = ops.softmax_quant_bwd(dev(dP), P, N, H, se, hi, alpha, g, dev(ca), True, dev(rb),
+                                                                  want_ds32=True, fmt=ops.FMT_F16, scale4=dev(sc), single=True)
+    assert out_bt is None and out_a.dtype == torch.float16
+    dS = ds32.cpu()[..., :N].view(B, H, N, N) * alpha
+    assert rel_err(dS, S.grad) < 1e-5
+    assert rel_err(d_s.cpu(), s.grad) < 1e-4
+    assert rel_err(colsum.cpu().view(B, H, N), dS.sum(2)) < 1e-4
+    ref = (dS * ca.view(1, H, 1, N) * rb.view(1, 1, N, 1) * 64.0).half().float()
+    oa = out_a.cpu().view(B, H, N, ldo)
+    assert rel_err(oa[..., :N].float(), ref) < 1e-3                                  # fp16 output rounding
+    assert bool((oa[..., N:] == 0).all())
 
 
 # ------------------------------------------------------------------------------------------------ W_qk
