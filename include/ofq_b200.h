@@ -279,6 +279,11 @@ OFQ_API long long ofq_layernorm_bwd_workspace(long long rows, int cols);
 OFQ_API int ofq_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
                               const float* rstd, long long rows, int cols, float* dx, float* dgamma, float* dbeta,
                               float* workspace, void* stream);
+/* Same with the gradient `res` [rows][cols] that arrives over the residual connection around the LayerNorm
+ * (x + f(LN(x)), deit_vision_transformer.py:154-164) added in the same pass: dx = res + LayerNorm'(dy). res may be NULL. */
+OFQ_API int ofq_layernorm_bwd_res(const float* dy, const float* x, const float* gamma, const float* mean,
+                                  const float* rstd, long long rows, int cols, const float* res, float* dx,
+                                  float* dgamma, float* dbeta, float* workspace, void* stream);
 
 #ifdef __cplusplus
 }

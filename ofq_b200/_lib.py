@@ -69,6 +69,7 @@ SIGNATURES = {
     "ofq_layernorm_fwd": (_i, [_p, _ll, _i, _p, _p, _f, _p, _p, _p, _p]),
     "ofq_layernorm_bwd_workspace": (_ll, [_ll, _i]),
     "ofq_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _ll, _i, _p, _p, _p, _p, _p]),
+    "ofq_layernorm_bwd_res": (_i, [_p, _p, _p, _p, _p, _ll, _i, _p, _p, _p, _p, _p, _p]),
     "ofq_adamw_multi": (_i, [_p, _i, _i, _i, _d, _d, _d, _d, _p, _p]),
 }
 EXPORTS = list(SIGNATURES)

@@ -57,7 +57,7 @@ constexpr int kMaxBlocks = 4 * 148;
 __global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, long long rows, int cols,
-                     float* __restrict__ dx, float* __restrict__ part) {
+                     const float* __restrict__ res, float* __restrict__ dx, float* __restrict__ part) {
     __shared__ float col_s[2][kChunk];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long rpb = (rows + gridDim.x - 1) / gridDim.x;
@@ -105,6 +105,10 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
                 o[e] = rs * (dd[e] * gg[e] - c1 - xh * c2);
                 a_g[p][e] += dd[e] * xh;
                 a_b[p][e] += dd[e];
+            }
+            if (res) {      // gradient arriving over the residual connection around this LayerNorm: summed here, not by a separate add
+                const float4 r4 = __ldg(reinterpret_cast<const float4*>(res + row * cols) + i);
+                o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
             }
             reinterpret_cast<float4*>(dx + row * cols)[i] = make_float4(o[0], o[1], o[2], o[3]);
         }
@@ -168,20 +172,27 @@ extern "C" int ofq_layernorm_fwd(const float* x, long long rows, int cols, const
 
 extern "C" long long ofq_layernorm_bwd_workspace(long long rows, int cols) { return ln_nblk(rows) * 2 * cols; }
 
-extern "C" int ofq_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
-                                 const float* rstd, long long rows, int cols, float* dx, float* dgamma, float* dbeta,
-                                 float* workspace, void* stream) {
+extern "C" int ofq_layernorm_bwd_res(const float* dy, const float* x, const float* gamma, const float* mean,
+                                     const float* rstd, long long rows, int cols, const float* res, float* dx,
+                                     float* dgamma, float* dbeta, float* workspace, void* stream) {
     OFQ_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && workspace && rows > 0 && cols > 0,
                 "ofq_layernorm_bwd: bad argument");
     OFQ_REQUIRE(cols % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)dy % 16 == 0 && (uintptr_t)dx % 16 == 0 &&
-                (uintptr_t)gamma % 16 == 0, "ofq_layernorm_bwd: cols must be a multiple of 4 and pointers 16-byte aligned");
+                (uintptr_t)gamma % 16 == 0 && (uintptr_t)res % 16 == 0,
+                "ofq_layernorm_bwd: cols must be a multiple of 4 and pointers 16-byte aligned");
     OFQ_CHECK_ARCH();
     cudaStream_t st = (cudaStream_t)stream;
     const long long nblk = ln_nblk(rows);
     dim3 grid((unsigned)nblk, (cols + kChunk - 1) / kChunk);
-    layernorm_bwd_kernel<<<grid, 256, 0, st>>>(dy, x, gamma, mean, rstd, rows, cols, dx, workspace);
+    layernorm_bwd_kernel<<<grid, 256, 0, st>>>(dy, x, gamma, mean, rstd, rows, cols, res, dx, workspace);
     dim3 g2((cols + 31) / 32, 2);
     colpart_reduce2_kernel<<<g2, 1024, 0, st>>>(workspace, cols, nblk, dgamma, dbeta);
     OFQ_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int ofq_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
+                                 const float* rstd, long long rows, int cols, float* dx, float* dgamma, float* dbeta,
+                                 float* workspace, void* stream) {
+    return ofq_layernorm_bwd_res(dy, x, gamma, mean, rstd, rows, cols, nullptr, dx, dgamma, dbeta, workspace, stream);
 }

@@ -84,9 +84,13 @@ class Block(nn.Module):
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
 
     def forward(self, x):
-        a, _ = self.attn(self.norm1(x))
+        res = getattr(self.norm1, "forward_res", None)       # ofq_b200 LayerNorm: residual gradient summed in its backward kernel
+        x, y = res(x) if res is not None else (x, self.norm1(x))
+        a, _ = self.attn(y)
         x = x + self.drop_path(a)
-        x = x + self.drop_path(self.mlp(self.norm2(x)))
+        res = getattr(self.norm2, "forward_res", None)
+        x, y = res(x) if res is not None else (x, self.norm2(x))
+        x = x + self.drop_path(self.mlp(y))
         return x, None
 
 

@@ -23,13 +23,46 @@ class _LayerNormFn(torch.autograd.Function):
         return dx.view_as(dy), dg, db, None
 
 
+class _LayerNormResFn(torch.autograd.Function):
+    """(x, LayerNorm(x)) for a pre-norm residual branch x + f(LayerNorm(x)) (deit_vision_transformer.py:154-164): the first
+    output is x itself, to be used by the residual add, so that the backward receives both gradient streams and sums them
+    inside the LayerNorm backward kernel instead of a separate elementwise add."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        xc = x.contiguous()
+        x2d = xc.view(-1, xc.shape[-1])
+        y, mean, rstd = ops.layernorm_fwd(x2d, weight, bias, eps)
+        ctx.save_for_backward(x2d, weight, mean, rstd)
+        ctx.set_materialize_grads(False)
+        return xc.view_as(xc), y.view_as(xc)
+
+    @staticmethod
+    def backward(ctx, dres, dy):
+        x2d, weight, mean, rstd = ctx.saved_tensors
+        if dy is None:
+            return dres, None, None, None
+        res2d = dres.contiguous().view_as(x2d) if dres is not None else None
+        dx, dg, db = ops.layernorm_bwd(dy.contiguous().view_as(x2d), x2d, weight, mean, rstd, res2d)
+        return dx.view_as(dy), dg, db, None
+
+
 class LayerNorm(nn.LayerNorm):
     """nn.LayerNorm over the last dimension with the same parameters / state-dict keys; fp32 CUDA inputs take the
     ofq_b200 kernels (forward ~HBM roofline, backward 4-5x faster than ATen's for 384-wide rows), anything else falls
     through to torch (this layer is host glue, not part of the quantized hot path's parity contract)."""
 
+    def _native(self, x):
+        return (x.is_cuda and x.dtype == torch.float32 and self.elementwise_affine and len(self.normalized_shape) == 1
+                and x.shape[-1] % 4 == 0 and self.bias is not None)
+
     def forward(self, x):
-        if (x.is_cuda and x.dtype == torch.float32 and self.elementwise_affine and len(self.normalized_shape) == 1
-                and x.shape[-1] % 4 == 0 and self.bias is not None):
+        if self._native(x):
             return _LayerNormFn.apply(x, self.weight, self.bias, self.eps)
         return super().forward(x)
+
+    def forward_res(self, x):
+        """(x, LayerNorm(x)): use the returned x in the residual add around the normalised branch."""
+        if self._native(x) and torch.is_grad_enabled() and x.requires_grad:
+            return _LayerNormResFn.apply(x, self.weight, self.bias, self.eps)
+        return x, self.forward(x)

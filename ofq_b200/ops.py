@@ -403,13 +403,15 @@ def layernorm_fwd(x2d: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, ep
     return y, mean, rstd
 
 
-def layernorm_bwd(dy2d, x2d, gamma, mean, rstd):
+def layernorm_bwd(dy2d, x2d, gamma, mean, rstd, res2d=None):
+    """dx = LayerNorm'(dy) (+ res2d: the gradient arriving over the residual connection, added in the same pass)."""
     rows, cols = x2d.shape
     lib = _lib.load()
     ws = torch.empty(lib.ofq_layernorm_bwd_workspace(rows, cols), dtype=torch.float32, device=x2d.device)
     dx = torch.empty_like(x2d)
     dgamma = torch.empty(cols, dtype=torch.float32, device=x2d.device)
     dbeta = torch.empty(cols, dtype=torch.float32, device=x2d.device)
-    _call("layernorm_bwd", 2, 12.0 * rows * cols, 0, lib.ofq_layernorm_bwd, dy2d.data_ptr(), x2d.data_ptr(), gamma.data_ptr(),
-          mean.data_ptr(), rstd.data_ptr(), rows, cols, dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), _st())
+    _call("layernorm_bwd", 2, (12.0 + (4 if res2d is not None else 0)) * rows * cols, 0, lib.ofq_layernorm_bwd_res, dy2d.data_ptr(),
+          x2d.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, cols, _ptr(res2d), dx.data_ptr(),
+          dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), _st())
     return dx, dgamma, dbeta

@@ -120,9 +120,10 @@ def _linear_backward(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulate_dx
 
 # ====================================================================================== QLinear
 class MlpLink:
-    """Side channel between the two QLinearFn nodes of a QMLP: fc1's forward leaves its folded scale vectors here, the
-    backward of fc2 (which runs first) turns the max |d fc1_out| its LSQ pass sees anyway into the fp16 range scale of
-    fc1's gradient operand (`sc`), and fc1's backward then skips its absmax pass."""
+    """Side channel between a producer node and the QLinearFn that consumes its output (fc1 -> fc2 of a QMLP, attention
+    core -> proj): the producer's forward leaves the two scale vectors folded into its gradient operand here (cs per
+    column, se per row), the backward of the consumer (which runs first) turns the max |d producer_out| its LSQ pass sees
+    anyway into the fp16 range scale of that operand (`sc`), and the producer's backward then skips its absmax pass."""
     __slots__ = ("cs", "se", "sc")
 
     def __init__(self):
@@ -233,12 +234,13 @@ def _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C):
     return out
 
 
-def _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=None, qp16=None):
+def _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=None, qp16=None, sc=None):
     """fp16 backward of P_hat V_hat with ONE copy A16[b,n,c] = fp16(dO * se_v[c] * se_p[n] * sc):
         dP_hat[z,n,d]  = 1/(se_p[n] sc) * sum_j A16[b,n,hj] qv[b,d,hj] + sum_j dO[b,n,hj] v_aft[hj]
         dv_hat[b,d,hj] = 1/(se_v[hj] sc) * sum_n qp[z,n,d] A16[b,n,hj]                    (both operands MN-major)"""
     hd = C // H
-    sc = ops.absmax_scale(dO, B, N, C, C, N * C, cs=sv2[0], rs=sp2[0], rs_period=N, product=True)
+    if sc is None:
+        sc = ops.absmax_scale(dO, B, N, C, C, N * C, cs=sv2[0], rs=sp2[0], rs_period=N, product=True)
     prep = ops.grad_prep(dO, B, N, C, C, N * C, cs=sv2[0], rs=sp2[0], rs_period=N, want_rm=True, u=v_aft, group=hd,
                          fmt=FMT, scale4=sc, rm_rowscale=True)
     a16 = prep["rm"]                                                     # [1, B, N, C]
@@ -255,11 +257,11 @@ def _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=Non
     return dPq, dvhat
 
 
-def _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=None, qp16=None):
+def _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=None, qp16=None, sc=None):
     """Returns (dPq [B*H,N,ldS] fp32, dvhat [B,N,C] fp32). sp2 / sv2 = [scale, 1/scale] of the probability / V quantizer.
     qv16 / qp16: exact 16-bit copies of the codes left by the forward quantizer passes (fp16 mode)."""
     if F16:
-        return _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16, qp16)
+        return _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16, qp16, sc)
     se_p, se_v = sp2[0], sv2[0]
     hd = C // H
     prep = ops.grad_prep(dO, B, N, C, C, N * C, cs=se_v, rs=se_p, rs_period=N, want_rm=True, want_t=True,
@@ -284,7 +286,7 @@ class QKRAttnCoreFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, wq, wk, wv, bv, x_b4, x_aft, s_x, v_b4, v_aft, s_v, k_b4, k_aft, s_k, s_p,
-                attn_bias, attn_mask, H: int, wbits: int, abits: int, nW: int):
+                attn_bias, attn_mask, H: int, wbits: int, abits: int, nW: int, link: Optional[MlpLink] = None):
         B, N, C = x.shape
         M = B * N
         hd = C // H
@@ -352,19 +354,22 @@ class QKRAttnCoreFn(torch.autograd.Function):
         ctx.save_for_backward(xc, wq, wk, x_b4, x_aft, v_b4, v_aft, k_b4, k_aft, qx, sx2, wvc, cs_v, ics_v, v_out, qv, sv2,
                               wqkc, cs_qk, ics_qk, qkx, qk, sk2, sk2_hn, P, qp, sp2, qx16, qv16, qk16, qp16)
         ctx.cfg = (B, N, C, H, lo, hi, hiu, scale, g_x, g_v, g_k, g_p, ldS, ldq, bv is not None,
-                   attn_bias is not None)
+                   attn_bias is not None, link)
+        if link is not None:
+            link.cs, link.se, link.sc = se_v, se_p, None
         return out
 
     @staticmethod
     def backward(ctx, dO):
         (xc, wq, wk, x_b4, x_aft, v_b4, v_aft, k_b4, k_aft, qx, sx2, wvc, cs_v, ics_v, v_out, qv, sv2, wqkc, cs_qk, ics_qk,
          qkx, qk, sk2, sk2_hn, P, qp, sp2, qx16, qv16, qk16, qp16) = ctx.saved_tensors
-        B, N, C, H, lo, hi, hiu, scale, g_x, g_v, g_k, g_p, ldS, ldq, has_bv, has_bias = ctx.cfg
+        B, N, C, H, lo, hi, hiu, scale, g_x, g_v, g_k, g_p, ldS, ldq, has_bv, has_bias, link = ctx.cfg
         se_x, se_v, se_k, se_p, se_k_hn = sx2[0], sv2[0], sk2[0], sp2[0], sk2_hn[0]
         M = B * N
         dev = dO.device
         dO = dO.contiguous()
-        dPq, dvhat = _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16, qp16)
+        dPq, dvhat = _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16, qp16,
+                                  link.sc if link is not None else None)
         # --- V quantizer and V linear
         dv_out, ds_v, dvb4, dvaft, *sc_v = ops.lsq_bwd(dvhat.view(M, C), v_out, v_b4, se_v, PER_COL, 1, 1, lo, hi, g_v,
                                                        next_scale=(cs_v, se_x, 1.0, True) if F16 else None)
@@ -427,7 +432,7 @@ class QKRAttnCoreFn(torch.autograd.Function):
         if has_bias:
             dbias = dS32[..., :N].reshape(B, H, N, N).sum(0)
         return (dx.view(B, N, C), dwq, dwk, dWv, (dbv if has_bv else None), dxb4, dxaft, ds_x, dvb4, dvaft, ds_v,
-                dkb4, dkaft, ds_k, ds_p, dbias, None, None, None, None, None)
+                dkb4, dkaft, ds_k, ds_p, dbias, None, None, None, None, None, None)
 
 
 class QAttnCoreFn(torch.autograd.Function):
@@ -435,7 +440,8 @@ class QAttnCoreFn(torch.autograd.Function):
     (swin_attention_and_mlp.py:172-229).  qkv is [B, N, 3C] laid out (3, H, hd) along the last dim."""
 
     @staticmethod
-    def forward(ctx, qkv, b4, s_q, s_k, s_v, q_aft, k_aft, v_aft, s_p, attn_bias, attn_mask, H: int, abits: int, nW: int):
+    def forward(ctx, qkv, b4, s_q, s_k, s_v, q_aft, k_aft, v_aft, s_p, attn_bias, attn_mask, H: int, abits: int, nW: int,
+                link: Optional[MlpLink] = None):
         B, N, C3 = qkv.shape
         C = C3 // 3
         M = B * N
@@ -472,20 +478,22 @@ class QAttnCoreFn(torch.autograd.Function):
         del S
         out = _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C)
         ctx.save_for_backward(qkvc, b4, q_aft, k_aft, v_aft, qq, qk, qv, sq2, sk2, sv2, P, qp, sp2)
-        ctx.cfg = (B, N, C, H, lo, hi, hiu, scale, g_qk, g_v, g_p, ldS, ldq, attn_bias is not None)
+        ctx.cfg = (B, N, C, H, lo, hi, hiu, scale, g_qk, g_v, g_p, ldS, ldq, attn_bias is not None, link)
+        if link is not None:
+            link.cs, link.se, link.sc = se_v, se_p, None
         return out
 
     @staticmethod
     def backward(ctx, dO):
         qkvc, b4, q_aft, k_aft, v_aft, qq, qk, qv, sq2, sk2, sv2, P, qp, sp2 = ctx.saved_tensors
-        B, N, C, H, lo, hi, hiu, scale, g_qk, g_v, g_p, ldS, ldq, has_bias = ctx.cfg
+        B, N, C, H, lo, hi, hiu, scale, g_qk, g_v, g_p, ldS, ldq, has_bias, link = ctx.cfg
         se_q, se_k, se_v, se_p = sq2[0], sk2[0], sv2[0], sp2[0]
         M = B * N
         hd = C // H
         dev = dO.device
         dO = dO.contiguous()
         q2d = qkvc.view(M, 3 * C)
-        dPq, dvhat = _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS)
+        dPq, dvhat = _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, sc=link.sc if link is not None else None)
         dqhat = torch.empty((M, C), dtype=torch.float32, device=dev)
         dkhat = torch.empty((M, C), dtype=torch.float32, device=dev)
         if F16:
@@ -531,4 +539,4 @@ class QAttnCoreFn(torch.autograd.Function):
         dqkv = torch.cat((dq, dk, dv), dim=1).view(B, N, 3 * C)
         db4 = torch.cat((db4_q, db4_k, db4_v))
         dbias = dS32[..., :N].reshape(B, H, N, N).sum(0) if has_bias else None
-        return dqkv, db4, ds_q, ds_k, ds_v, daft_q, daft_k, daft_v, ds_p, dbias, None, None, None, None
+        return dqkv, db4, ds_q, ds_k, ds_v, daft_q, daft_k, daft_v, ds_p, dbias, None, None, None, None, None

@@ -8,7 +8,8 @@ import torch.nn.functional as F
 
 from ... import ops
 from ...host.deit import Attention as deit_attention
-from ..functional import QAttnCoreFn, QKRAttnCoreFn
+from ...ops import ACT_NONE
+from ..functional import MlpLink, QAttnCoreFn, QKRAttnCoreFn
 from ..quantizer.lsq import LsqQuantizer, LsqQuantizer4v
 from ..quantizer.statsq import StatsQuantizer, StatsQuantizer_specific_4_qkreparam_cga
 from .qbias import LearnableBias
@@ -74,7 +75,7 @@ class QAttention(deit_attention):
             attn = attn + attn_bias
         self.quan_a_softmax_fn(F.softmax(attn, dim=-1))
 
-    def _core(self, qkv, attn_bias=None, attn_mask=None, nW=0):
+    def _core(self, qkv, attn_bias=None, attn_mask=None, nW=0, link=None):
         if not self._scales_ready():
             full_bias = attn_bias
             if attn_mask is not None:
@@ -84,12 +85,13 @@ class QAttention(deit_attention):
             self._init_scales(qkv.detach(), full_bias)
         return QAttnCoreFn.apply(qkv, self.move_qkv_b4.bias, self.quan_a_q_fn.s, self.quan_a_k_fn.s, self.quan_a_v_fn.s,
                                  self.move_q_aft.bias, self.move_k_aft.bias, self.move_v_aft.bias,
-                                 self.quan_a_softmax_fn.s, attn_bias, attn_mask, self.num_heads, self.input_bits, nW)
+                                 self.quan_a_softmax_fn.s, attn_bias, attn_mask, self.num_heads, self.input_bits, nW, link)
 
     def forward(self, x):
         qkv = self.qkv(x)
-        x = self._core(qkv)
-        x = self.proj(x)
+        link = MlpLink()        # proj's backward hands the fp16 range scale of d(core output) to the core's backward
+        x = self._core(qkv, link=link)
+        x = self.proj(x, ACT_NONE, link, 2)
         x = self.proj_drop(x)
         return x, None
 
@@ -161,7 +163,7 @@ class QAttention_qkreparam(deit_attention):
             attn = attn + attn_bias
         self.quan_a_softmax_fn(F.softmax(attn, dim=-1))
 
-    def _core(self, x, attn_bias=None, attn_mask=None, nW=0):
+    def _core(self, x, attn_bias=None, attn_mask=None, nW=0, link=None):
         if not self._scales_ready():
             full_bias = attn_bias
             if attn_mask is not None:
@@ -175,11 +177,12 @@ class QAttention_qkreparam(deit_attention):
                                    self.move_v_b4.bias, self.move_v_aft.bias, self.quan_a_v_fn.s,
                                    self.move_qkx_b4.bias, self.move_qkx_aft.bias, self.quan_a_qkx_fn.s,
                                    self.quan_a_softmax_fn.s, attn_bias, attn_mask, self.num_heads, self.weight_bits,
-                                   self.input_bits, nW)
+                                   self.input_bits, nW, link)
 
     def forward(self, x):
-        x = self._core(x)
-        x = self.proj(x)
+        link = MlpLink()        # proj's backward hands the fp16 range scale of d(core output) to the core's backward
+        x = self._core(x, link=link)
+        x = self.proj(x, ACT_NONE, link, 2)
         x = self.proj_drop(x)
         return x, None
 

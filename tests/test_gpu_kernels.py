@@ -679,3 +679,33 @@ def test_layernorm_fwd_bwd(ops, rows, cols):
     assert rel_err(y, yr.detach()) < 1e-6
     dx, dg, db = ops.layernorm_bwd(dy, x, g, mean, rstd)
     assert rel_err(dx, xd.grad) < 1e-5 and rel_err(dg, gd.grad) < 1e-5 and rel_err(db, bd.grad) < 1e-5
+    # gradient of the residual connection around the LayerNorm added in the same pass (host/layers.py forward_res)
+    res = torch.randn(rows, cols, device="cuda")
+    dx2, dg2, db2 = ops.layernorm_bwd(dy, x, g, mean, rstd, res)
+    assert rel_err(dx2, xd.grad + res.double()) < 1e-5 and torch.equal(dg2, dg) and torch.equal(db2, db)
+
+
+def test_layernorm_residual_module(ops):
+    """x + f(LayerNorm(x)) through LayerNorm.forward_res equals the plain composition (value and gradients)."""
+    from ofq_b200.host.layers import LayerNorm
+    torch.manual_seed(18)
+    ln = LayerNorm(384, eps=1e-6).cuda()
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.normal_()
+    x0 = torch.randn(4, 50, 384, device="cuda")
+    w = torch.randn(384, 384, device="cuda") * 0.05
+    outs = []
+    for fused in (True, False):
+        x = x0.clone().requires_grad_(True)
+        h = x * 1.5
+        ln.zero_grad()
+        if fused:
+            r, y = ln.forward_res(h)
+        else:
+            r, y = h, ln(h)
+        out = r + torch.tanh(y @ w)
+        out.square().sum().backward()
+        outs.append((out.detach(), x.grad.clone(), ln.weight.grad.clone(), ln.bias.grad.clone()))
+    for a, b in zip(*outs):
+        assert rel_err(a, b) < 1e-6
