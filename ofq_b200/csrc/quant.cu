@@ -142,6 +142,13 @@ __device__ __forceinline__ float gelu_grad(float x) {
     const float pdf = expf(-0.5f * x * x) * 0.39894228040143267794f;      // 2/sqrt(pi) * sqrt(1/2) * 0.5
     return cdf + x * pdf;
 }
+// GELU(x) (bit-identical to gelu_fwd) and GELU'(x) from ONE erf evaluation; the Gaussian of the derivative uses the fast
+// exponential (2 ulp: it only scales a gradient).
+__device__ __forceinline__ void gelu_both(float x, float* a, float* d) {
+    const float e1 = __fadd_rn(1.0f, erff(__fmul_rn(x, 0.70710678118654752440f)));
+    *a = __fmul_rn(__fmul_rn(x, 0.5f), e1);
+    *d = fmaf(x, __expf(-0.5f * x * x) * 0.39894228040143267794f, 0.5f * e1);
+}
 // two small integers -> packed fp16 / bf16 pair (exact), first in the low half
 __device__ __forceinline__ uint32_t pack_codes16(int a, int b, bool f16) {
     uint32_t r;
@@ -508,7 +515,8 @@ lsq_bwd_stream_kernel(const float* __restrict__ dy, long long lddy, const float*
             float o[4], part = 0.f;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float xa = ACT == OFQ_ACT_GELU ? gelu_fwd(xx[e]) : xx[e];     // the quantizer saw act(x)
+                float xa = xx[e], dact = 1.f;
+                if (ACT == OFQ_ACT_GELU) gelu_both(xx[e], &xa, &dact);               // the quantizer saw act(x)
                 const float v = (xa + bb[e]) * ii[e];
                 const bool inside = (v >= qlo) && (v <= qhi);
                 const float q = rintf(fminf(fmaxf(v, qlo), qhi));
@@ -516,7 +524,7 @@ lsq_bwd_stream_kernel(const float* __restrict__ dy, long long lddy, const float*
                 o[e] = inside ? gg[e] : 0.f;
                 aft[e] += gg[e];
                 ab4[e] += o[e];
-                if (ACT == OFQ_ACT_GELU) o[e] *= gelu_grad(xx[e]);                  // dx is the gradient w.r.t. the pre-activation
+                if (ACT == OFQ_ACT_GELU) o[e] *= dact;                              // dx is the gradient w.r.t. the pre-activation
                 tmax = fmaxf(tmax, fabsf(o[e]));
                 if (MODE == OFQ_SCALE_PER_ROW) part += t; else as[e] += t;
             }
@@ -585,6 +593,23 @@ __device__ __forceinline__ void
 lsq_bwd_finalize_rows(const float* __restrict__ rowpart, long long total, long long nscale, float g,
                       float* __restrict__ d_s, int bx) {
     __shared__ float red[8][33];
+    if (nscale < 32) {
+        // few scales, many partials each (the per-channel step sizes of the image quantizer: 3 scales, 10^5 partials):
+        // all threads stride over the partials with a stride that is a multiple of nscale, so a thread stays on one scale
+        __shared__ float wide[256];
+        const int ns = (int)nscale, T = (256 / ns) * ns, t = threadIdx.x;
+        float acc = 0.f;
+        if (t < T)
+            for (long long j = t; j < total; j += T) acc += rowpart[j];
+        wide[t] = acc;
+        __syncthreads();
+        if (t < ns) {
+            float s2 = 0.f;
+            for (int k = t; k < T; k += ns) s2 += wide[k];
+            d_s[t] = g * s2;
+        }
+        return;
+    }
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const long long i = (long long)bx * 32 + tx;
     float acc = 0.f;

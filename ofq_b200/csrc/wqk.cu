@@ -73,9 +73,13 @@ sgemm_strided_kernel(const SgemmPair pair, int nb, int M, int N, int K) {
 
 int launch(const SgemmPair& pair, int nprob, int M, int N, int K, int nb, cudaStream_t st) {
     const long long tiles64 = (long long)((N + 63) / 64) * ((M + 63) / 64) * nb * nprob;
+    const long long tiles32 = (long long)((N + 63) / 64) * ((M + 31) / 32) * nb * nprob;
     if (tiles64 >= 148) {
         dim3 grid((N + 63) / 64, (M + 63) / 64, nb * nprob);
         sgemm_strided_kernel<64><<<grid, 256, 0, st>>>(pair, nb, M, N, K);
+    } else if (tiles32 >= 128) {   // the backward pair of a DeiT-S layer: 144 CTAs of 32 x 64 (2 x 4 outputs per thread)
+        dim3 grid((N + 63) / 64, (M + 31) / 32, nb * nprob);
+        sgemm_strided_kernel<32><<<grid, 256, 0, st>>>(pair, nb, M, N, K);
     } else {
         dim3 grid((N + 63) / 64, (M + 15) / 16, nb * nprob);
         sgemm_strided_kernel<16><<<grid, 256, 0, st>>>(pair, nb, M, N, K);

@@ -221,6 +221,36 @@ class LsqFn(torch.autograd.Function):
         return dx.view_as(xc), ds, None, None, None
 
 
+class ImgLsqFn(torch.autograd.Function):
+    """move_aft(LsqQuantizer4img(move_b4(img))) of the 8-bit patch-embedding input (qlinear.py:138-177, lsq.py:306-382,
+    qbias.py:15-23) on the [B*Cin, H*W] view of the image: the per-input-channel step size is a per-row scale with period
+    Cin, the per-pixel shifts are per-column vectors, so the hot-path kernels apply unchanged: one codes pass forward,
+    one STE / reduction pass backward (the torch composition is ~20 elementwise passes over the batch of images)."""
+
+    @staticmethod
+    def forward(ctx, x, b4, aft, s, lo: int, hi: int):
+        B, Cin, H, W = x.shape
+        xc = x.contiguous()
+        x2d = xc.view(B * Cin, H * W)
+        g = grad_scale_factor(hi, B * H * W)
+        se = ops.lsq_effective_scale(s, g)
+        codes = ops.lsq_quant(x2d, b4, se, PER_ROW, Cin, 1, lo, hi)
+        # dequantise exactly as the reference: round(.) * s, then the shift
+        out = torch.mul(codes.view(B, Cin, H * W), se.view(1, Cin, 1)) + aft.view(1, 1, H * W)
+        ctx.save_for_backward(xc, b4, se)
+        ctx.cfg = (lo, hi, g)
+        return out.view(B, Cin, H, W)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, b4, se = ctx.saved_tensors
+        lo, hi, g = ctx.cfg
+        B, Cin, H, W = xc.shape
+        dx, ds, db4, daft = ops.lsq_bwd(dy.contiguous().view(B * Cin, H * W), xc.view(B * Cin, H * W), b4, se, PER_ROW, Cin, 1,
+                                        lo, hi, g)
+        return (dx.view_as(xc) if ctx.needs_input_grad[0] else None), db4, daft, ds, None, None
+
+
 # ====================================================================================== attention core
 def _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C):
     """out[b,n,h*hd+j] = se_p[n] * (se_v[hj] * sum_d qp[z,n,d] qv[b,d,hj] + v_aft[hj] * sum_d qp[z,n,d])."""

@@ -138,7 +138,7 @@ class LSQ_QConv2d(nn.Conv2d):
 
     def forward(self, input):
         weight = self.lsqw_fn(self.weight)
-        input = self.move_aft(self.input_quant_fn(self.move_b4(input)))
+        input = self.input_quant_fn.forward_with_shifts(input, self.move_b4, self.move_aft)
         kh, kw = self.kernel_size
         if (tuple(self.stride) == (kh, kw) and tuple(self.padding) == (0, 0) and tuple(self.dilation) == (1, 1)
                 and self.groups == 1 and input.shape[-2] % kh == 0 and input.shape[-1] % kw == 0):

@@ -11,7 +11,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from ..functional import LsqFn, levels
+from ..functional import ImgLsqFn, LsqFn, levels
 
 
 def _eff_scale(alpha, g):
@@ -158,3 +158,13 @@ class LsqQuantizer4img(_Lsq8):
             f = 4 if self.all_positive else 2
             self._set_s(f * x.detach().abs().mean(dim=-1).mean(dim=-1).mean(dim=0) / (self.thd_pos ** 0.5))
         return self._quant(x, self.s.view(1, -1, 1, 1), x.shape[0] * x.shape[2] * x.shape[3])
+
+    def forward_with_shifts(self, x, move_b4, move_aft):
+        """move_aft(self(move_b4(x))) (qlinear.py:171). Once the step size exists and the data is known to be signed (8-bit
+        codes in [-128, 127]), fp32 CUDA images take ONE fused kernel per direction (functional.ImgLsqFn)."""
+        H, W = x.shape[-2], x.shape[-1]
+        if (self.initialized_alpha and self._signed_host == 1 and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+                and H == W and move_b4.bias.numel() == H * W and move_aft.bias.numel() == H * W and (H * W) % 4 == 0
+                and self.bit <= 8 and x.shape[1] == self.s.numel()):
+            return ImgLsqFn.apply(x, move_b4.bias, move_aft.bias, self.s, -(2 ** (self.bit - 1)), 2 ** (self.bit - 1) - 1)
+        return move_aft(self(move_b4(x)))

@@ -50,6 +50,10 @@ for cols, nseg in ((384, 1), (1536, 1), (2304, 6)):
     se = torch.rand(N * nseg, device=dev) * 0.5 + 0.2
     timeit(f"lsq_quant rows C={cols} nseg={nseg}", 5.0 * M * cols, lambda i: ops.lsq_quant(x[i], b4, se, PER_ROW, N, nseg, -2, 1))
     timeit(f"lsq_bwd rows C={cols} nseg={nseg}", 12.0 * M * cols, lambda i: ops.lsq_bwd(dy[i], x[i], b4, se, PER_ROW, N, nseg, -2, 1, 0.01))
+    timeit(f"lsq_quant rows +fp16 copy C={cols} nseg={nseg}", 7.0 * M * cols, lambda i: ops.lsq_quant(x[i], b4, se, PER_ROW, N, nseg, -2, 1, fmt16=FMT_F16))
+    if cols == 1536:
+        timeit(f"lsq_quant rows GELU +fp16 copy C={cols}", 7.0 * M * cols, lambda i: ops.lsq_quant(x[i], b4, se, PER_ROW, N, nseg, 0, 3, act=ops.ACT_GELU, fmt16=FMT_F16))
+        timeit(f"lsq_bwd rows GELU C={cols}", 12.0 * M * cols, lambda i: ops.lsq_bwd(dy[i], x[i], b4, se, PER_ROW, N, nseg, 0, 3, 0.01, act=ops.ACT_GELU))
     cs = torch.rand(cols, device=dev) + 0.5
     sx = torch.rand(N, device=dev) + 0.5
     sc = ops.absmax_scale(dy[0], 1, M, cols, cols, 0, cs=cs, rs=sx, rs_period=N, product=True)
