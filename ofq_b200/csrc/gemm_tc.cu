@@ -12,6 +12,7 @@
 // read the accumulator back with tcgen05.ld and apply the rank-1 scale/offset epilogue straight to HBM.
 // Quantizer scales never touch the operands: per-row (token) scales, per-column (StatsQ channel) scales
 // and the affine "move_aft" shift all live in the epilogue vectors, so the MMA itself is exact.
+#include <cstdlib>
 #include "ofq_b200.h"
 #include "ptx.cuh"
 #include "host_util.h"
@@ -304,6 +305,246 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------ CTA-pair variant
+// Same pipeline on a 2-CTA cluster: one tcgen05.mma.cta_group::2 of M = 256 per instruction. CTA r of the pair owns rows
+// [m0 + 128 r, m0 + 128 r + 128) of the 256 x BN tile (its accumulator lives in its own TMEM) and stages its own A rows
+// plus HALF of the B tile (rows n0 + r BN/2 ...): (128 + BN/2) operand rows per k-block and CTA instead of (128 + BN), a
+// third less L2 -> shared-memory traffic, which is what bounds these GEMMs (profiles/: ~9.5 of the ~12 TB/s the L2 slices
+// can deliver at 33 % tensor-pipe activity). Protocol (cutlass sm100 2-SM kernels): both CTAs issue TMA, all transaction
+// bytes are credited to the LEADER's stage barrier; the leader's elected thread issues the MMAs and multicasts its
+// commits to both CTAs' empty / acc_full barriers; the epilogue warps of both CTAs arrive on the leader's acc_empty.
+template <int BN, int STAGES, int OUT_BUFS>
+struct SmemLayout2 {
+    static constexpr uint32_t A_BYTES = BM * KBYTES;
+    static constexpr uint32_t B_BYTES = (BN / 2) * KBYTES;
+    static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr uint32_t OUT_OFF = STAGES * STAGE_BYTES;
+    static constexpr uint32_t OUT_BYTES = EPI_WARPS * OUT_BUFS * 4096;
+    static constexpr uint32_t VEC_OFF = OUT_OFF + OUT_BYTES;
+    static constexpr uint32_t BAR_OFF = VEC_OFF + 2 * 2 * BN * 4;
+    static constexpr uint32_t TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
+    static constexpr size_t DYN_BYTES = TOTAL + 1024;
+};
+
+template <int KIND, int BN, int STAGES, int OUT_BUFS>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const GemmParams p, const int num_tiles,
+                    const int mtiles, const int ntiles) {
+    using L = SmemLayout2<BN, STAGES, OUT_BUFS>;
+    constexpr uint32_t A_BYTES = L::A_BYTES;
+    constexpr uint32_t STAGE_BYTES = L::STAGE_BYTES;
+    constexpr uint32_t ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+    constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
+    constexpr uint32_t UMMA_K_BYTES = 32;
+    constexpr int BNH = BN / 2;                       // B rows staged by each CTA
+    const uint32_t IDESC = KIND == 0 ? umma_idesc(2u, 1u, 2 * BM, BN)
+                                     : (umma_idesc(1u, (uint32_t)p.ab_fmt, 2 * BM, BN) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16));
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_full = empty_bar + STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* vec_s = reinterpret_cast<float*>(smem + L::VEC_OFF);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs), 1 = peer
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);               // leader's: one arrive.expect_tx + the bytes of both CTAs
+            mbar_init(&empty_bar[s], 1);              // one multicast commit per use
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], 2 * EPI_WARPS);  // leader's: the epilogue warps of both CTAs
+        }
+        fence_mbar_init();
+    }
+    cluster_sync_all();                               // barrier inits visible to the peer before any remote arrive / TMA
+    if (warp == 1) {
+        tmem_alloc_pair(tmem_slot, TMEM_COLS);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            const int kelem = KIND == 0 ? KBYTES : KBYTES / 2;
+            uint32_t it = 0;
+            for (int t = pair; t < num_tiles; t += npairs) {
+                const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);     // c.m0 = base of the 256-row pair tile
+                const int m0 = 2 * c.m0 + (int)rank * BM;
+                const int n0 = c.n0 + (int)rank * BNH;
+                for (int i = 0; i < c.nit; ++i, ++it) {
+                    const uint32_t s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    const int g = c.it_begin + i;
+                    const int k2i = g / p.kblocks, kb = g % p.kblocks;
+                    uint8_t* sa = smem + s * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+                    if (KIND != 0 && p.a_mn) {
+                        for (int j = 0; j < BM / 64; ++j)
+                            tma_load_5d_pair(sa + j * 8192, &tmA, bar, m0 + 64 * j, kb * kelem, (k2i % p.a_k2mod) * p.a_k2, c.b1 * p.a_b1, c.b2 * p.a_b2);
+                    } else {
+                        tma_load_5d_pair(sa, &tmA, bar, kb * kelem, m0, (k2i % p.a_k2mod) * p.a_k2, c.b1 * p.a_b1, c.b2 * p.a_b2);
+                    }
+                    if (KIND != 0 && p.b_mn) {
+                        for (int j = 0; j < BNH / 64; ++j)
+                            tma_load_5d_pair(sb + j * 8192, &tmB, bar, n0 + 64 * j, kb * kelem, (k2i % p.b_k2mod) * p.b_k2, c.b1 * p.b_b1, c.b2 * p.b_b2);
+                    } else {
+                        tma_load_5d_pair(sb, &tmB, bar, kb * kelem, n0, (k2i % p.b_k2mod) * p.b_k2, c.b1 * p.b_b1, c.b2 * p.b_b2);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && elect_one()) {
+            uint32_t it = 0, tc = 0;
+            for (int t = pair; t < num_tiles; t += npairs, ++tc) {
+                const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);
+                const uint32_t as = tc & 1, aph = (tc >> 1) & 1;
+                mbar_wait(&acc_empty[as], aph ^ 1);       // both CTAs' epilogues have drained this accumulator stage
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * ACC_COLS;
+                for (int i = 0; i < c.nit; ++i, ++it) {
+                    const uint32_t s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                    const bool bmn = KIND != 0 && p.b_mn, amn = KIND != 0 && p.a_mn;
+                    const uint64_t bdesc = bmn ? umma_desc_mnmajor_sw128(sa + A_BYTES) : umma_desc_kmajor_sw128(sa + A_BYTES);
+                    const uint64_t adesc = amn ? umma_desc_mnmajor_sw128(sa) : umma_desc_kmajor_sw128(sa);
+                    const uint64_t badv = bmn ? (2048u >> 4) : (UMMA_K_BYTES >> 4);
+                    const uint64_t aadv = amn ? (2048u >> 4) : (UMMA_K_BYTES >> 4);
+#pragma unroll
+                    for (uint32_t kk = 0; kk < KBYTES / UMMA_K_BYTES; ++kk) {
+                        if (KIND == 0)
+                            umma_i8_pair(tmem_d, adesc + kk * aadv, bdesc + kk * badv, IDESC, (i | kk) != 0);
+                        else
+                            umma_f16_pair(tmem_d, adesc + kk * aadv, bdesc + kk * badv, IDESC, (i | kk) != 0);
+                    }
+                    tc_commit_pair(&empty_bar[s]);      // frees the stage in both CTAs when these MMAs retire
+                }
+                tc_commit_pair(&acc_full[as]);          // accumulators of both CTAs complete
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        uint8_t* stage_base = smem + L::OUT_OFF + (warp - 2) * OUT_BUFS * 4096;
+        uint32_t tc = 0, chunk = 0;
+        for (int t = pair; t < num_tiles; t += npairs, ++tc) {
+            const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);
+            const int m0 = 2 * c.m0 + (int)rank * BM;
+            const uint32_t as = tc & 1, aph = (tc >> 1) & 1;
+            const bool rank1 = p.has_rank1 && c.split == 0;
+            float* cs_s = vec_s + as * 2 * BN;
+            float* ct_s = cs_s + BN;
+            {
+                const long long cs_off = (long long)c.b1 * p.cs.bs1 + (long long)c.b2 * p.cs.bs2;
+                const long long ct_off = (long long)c.b1 * p.ct.bs1 + (long long)c.b2 * p.ct.bs2;
+                for (int j = threadIdx.x - 64; j < BN; j += EPI_WARPS * 32) {
+                    const int n = c.n0 + j;
+                    const bool ok = n < p.N;
+                    cs_s[j] = ok ? (p.cs.p ? __ldg(p.cs.p + cs_off + (n % p.cs.period)) : 1.0f) : 0.f;
+                    ct_s[j] = (ok && rank1) ? (p.ct.p ? __ldg(p.ct.p + ct_off + n) : 1.0f) : 0.f;
+                }
+                named_bar_sync(1, EPI_WARPS * 32);
+            }
+            const int m = m0 + q * 32 + lane;
+            const bool row_ok = m < p.M;
+            const long long rs_off = (long long)c.b1 * p.rs.bs1 + (long long)c.b2 * p.rs.bs2;
+            const long long rt_off = (long long)c.b1 * p.rt.bs1 + (long long)c.b2 * p.rt.bs2;
+            const float rsv = row_ok ? (p.rs.p ? __ldg(p.rs.p + rs_off + (m % p.rs.period)) : 1.0f) : 0.f;
+            const float rtv = (row_ok && rank1) ? (p.rt.p ? __ldg(p.rt.p + rt_off + (m % p.rt.period)) : 1.0f) : 0.f;
+
+            if (c.nit > 0) {
+                mbar_wait(&acc_full[as], aph);
+                tc_fence_after();
+            }
+            const uint32_t tmem_acc = tmem_base + as * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+            int nvalid = (min(BN, p.N - c.n0) + 31) / 32;
+            if (m0 >= p.M) nvalid = 0;                 // this CTA's half of the pair tile lies entirely below the matrix
+            uint32_t r[2][32];
+            int ci = half;
+            if (ci < nvalid && c.nit > 0) tmem_ld_32x32(tmem_acc + ci * 32, r[0]);
+            int buf_sel = 0;
+#pragma unroll 1
+            for (; ci < nvalid; ci += 2, buf_sel ^= 1) {
+                const int c0 = ci * 32;
+                if (c.nit > 0) {
+                    tmem_ld_wait();
+                    if (buf_sel == 0) tmem_ld_pin(r[0]); else tmem_ld_pin(r[1]);
+                    if (ci + 2 < nvalid) {
+                        if (buf_sel == 0) tmem_ld_32x32(tmem_acc + (ci + 2) * 32, r[1]);
+                        else              tmem_ld_32x32(tmem_acc + (ci + 2) * 32, r[0]);
+                    }
+                }
+                uint8_t* buf = stage_base + (chunk % OUT_BUFS) * 4096;
+                if (chunk >= OUT_BUFS) {
+                    if (lane == 0) tma_store_wait_read<OUT_BUFS - 1>();
+                    __syncwarp();
+                }
+                ++chunk;
+                float4* rowp = reinterpret_cast<float4*>(buf + lane * 128);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 cs4 = *reinterpret_cast<const float4*>(cs_s + c0 + 4 * j4);
+                    const float4 ct4 = *reinterpret_cast<const float4*>(ct_s + c0 + 4 * j4);
+                    const float csv[4] = {cs4.x, cs4.y, cs4.z, cs4.w};
+                    const float ctv[4] = {ct4.x, ct4.y, ct4.z, ct4.w};
+                    float o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int j = 4 * j4 + e;
+                        const uint32_t raw = c.nit > 0 ? (buf_sel == 0 ? r[0][j] : r[1][j]) : 0u;
+                        const float acc = KIND == 0 ? static_cast<float>(static_cast<int32_t>(raw)) : __uint_as_float(raw);
+                        o[e] = acc * rsv * csv[e] + rtv * ctv[e];
+                    }
+                    rowp[j4 ^ (lane & 7)] = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (p.atomic)
+                        tma_reduce_add_5d(&tmC, buf, c.n0 + c0, m0 + q * 32, 0, c.b1 * p.c_b1, c.b2 * p.c_b2);
+                    else
+                        tma_store_5d(&tmC, buf, c.n0 + c0, m0 + q * 32, 0, c.b1 * p.c_b1, c.b2 * p.c_b2);
+                    tma_store_commit();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[as]), 0));
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+    // no CTA of the pair may leave (or free its TMEM) while the other can still issue / receive MMAs, commits or arrives
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 template <int KIND, int BN, int STAGES, int NA = 1, int OUT_BUFS = 2>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
@@ -325,6 +566,50 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     const int grid = (int)(tiles < ofq_num_sms() ? tiles : ofq_num_sms());   // one persistent CTA per SM
     kern<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, tmC, p, (int)tiles, mtiles, ntiles);
     OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+
+// Largest number of co-resident CTA pairs for an instantiation (clusters need two free SMs of one TPC).
+template <int KIND, int BN, int STAGES, int OUT_BUFS = 2>
+static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                            const GemmParams& p, cudaStream_t stream) {
+    constexpr size_t smem = SmemLayout2<BN, STAGES, OUT_BUFS>::DYN_BYTES;
+    static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
+    auto kern = gemm_tc_pair_kernel<KIND, BN, STAGES, OUT_BUFS>;
+    static int max_pairs = 0;         // per instantiation
+    if (max_pairs == 0) {
+        OFQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3(ofq_num_sms() & ~1);
+        q.blockDim = dim3(NUM_THREADS);
+        q.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        q.attrs = at; q.numAttrs = 1;
+        int n = 0;
+        OFQ_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &q));
+        if (n <= 0) { ofq_set_error("ofq_gemm: no CTA pair fits on this device"); return OFQ_ERR_CUDA; }
+        max_pairs = n < ofq_num_sms() / 2 ? n : ofq_num_sms() / 2;
+    }
+    const int mtiles = (p.M + 2 * BM - 1) / (2 * BM), ntiles = (p.N + BN - 1) / BN;
+    const long long tiles = (long long)mtiles * ntiles * p.nb1 * p.nb2 * p.splits;
+    if (tiles > 0x7fffffff) {
+        ofq_set_error("ofq_gemm: too many tiles");
+        return OFQ_ERR_ARG;
+    }
+    const int pairs = (int)(tiles < max_pairs ? tiles : max_pairs);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    OFQ_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p, (int)tiles, mtiles, ntiles));
     return 0;
 }
 
@@ -429,13 +714,18 @@ extern "C" int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B
         ofq_set_error("ofq_gemm: split-K requires an accumulating (pre-zeroed) output");
         return OFQ_ERR_ARG;
     }
+    // CTA pairs (cta_group::2, 256-row tiles) whenever the problem has more than one 128-row block and no dual-A stage;
+    // OFQ_GEMM_PAIR=0 keeps the single-CTA kernel (A/B measurements, debugging)
+    static const bool pair_enabled = [] { const char* e = getenv("OFQ_GEMM_PAIR"); return !(e && e[0] == '0'); }();
+    const bool pair = pair_enabled && A->dual_delta == 0 && M > BM;
     // tile width: minimise (number of N tiles) x (per-tile fixed cost + tile width); the fixed cost (pipeline fill,
     // barrier round trips, epilogue start-up) is worth about 128 columns of MMA/epilogue work
     static const int widths[] = {256, 224, 192, 128, 64, 32};
     int bn = 32;
     long long best_cost = -1;
     for (int w : widths) {
-        if (p.b_mn && w % 64) continue;          // MN-major B tiles are whole 64-row swizzle atoms
+        // MN-major B tiles are whole 64-row swizzle atoms (per CTA: half the tile in pair mode)
+        if (p.b_mn && w % (pair ? 128 : 64)) continue;
         const long long nt = (N + w - 1) / w;
         const long long cost = nt * (128 + w);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; bn = w; }
@@ -443,11 +733,24 @@ extern "C" int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B
     CUtensorMap tmA, tmB, tmC;
     int rc = make_operand_map(&tmA, A, eb, M, K, k2, nb1, nb2, BM, kind == OFQ_GEMM_F16);
     if (rc) return rc;
-    rc = make_operand_map(&tmB, B, eb, N, K, k2, nb1, nb2, bn, kind == OFQ_GEMM_F16);
+    rc = make_operand_map(&tmB, B, eb, N, K, k2, nb1, nb2, pair ? bn / 2 : bn, kind == OFQ_GEMM_F16);
     if (rc) return rc;
     rc = make_out_map(&tmC, out, M, N, nb1, nb2);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (pair) {
+#define OFQ_DISPATCH_PAIR(KIND)                                                    \
+    switch (bn) {                                                                  \
+        case 256: return launch_gemm_pair<KIND, 256, 4>(tmA, tmB, tmC, p, st);     \
+        case 224: return launch_gemm_pair<KIND, 224, 5>(tmA, tmB, tmC, p, st);     \
+        case 192: return launch_gemm_pair<KIND, 192, 5>(tmA, tmB, tmC, p, st);     \
+        case 128: return launch_gemm_pair<KIND, 128, 6>(tmA, tmB, tmC, p, st);     \
+        case 64:  return launch_gemm_pair<KIND, 64, 6>(tmA, tmB, tmC, p, st);      \
+        default:  return launch_gemm_pair<KIND, 32, 6>(tmA, tmB, tmC, p, st);      \
+    }
+        if (kind == OFQ_GEMM_I8) { OFQ_DISPATCH_PAIR(0) } else { OFQ_DISPATCH_PAIR(1) }
+#undef OFQ_DISPATCH_PAIR
+    }
 #define OFQ_DISPATCH(KIND)                                                   \
     switch (bn) {                                                            \
         case 256: return launch_gemm<KIND, 256, 3>(tmA, tmB, tmC, p, st);    \

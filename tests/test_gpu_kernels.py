@@ -682,7 +682,7 @@ def test_layernorm_fwd_bwd(ops, rows, cols):
     # gradient of the residual connection around the LayerNorm added in the same pass (host/layers.py forward_res)
     res = torch.randn(rows, cols, device="cuda")
     dx2, dg2, db2 = ops.layernorm_bwd(dy, x, g, mean, rstd, res)
-    assert rel_err(dx2, xd.grad + res.double()) < 1e-5 and torch.equal(dg2, dg) and torch.equal(db2, db)
+    assert rel_err(dx2, xd.grad + res.double()) < 1e-5 and rel_err(dg2, dg) < 1e-5 and rel_err(db2, db) < 1e-5
 
 
 def test_layernorm_residual_module(ops):
