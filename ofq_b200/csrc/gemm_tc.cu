@@ -714,10 +714,13 @@ extern "C" int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B
         ofq_set_error("ofq_gemm: split-K requires an accumulating (pre-zeroed) output");
         return OFQ_ERR_ARG;
     }
-    // CTA pairs (cta_group::2, 256-row tiles) whenever the problem has more than one 128-row block and no dual-A stage;
-    // OFQ_GEMM_PAIR=0 keeps the single-CTA kernel (A/B measurements, debugging)
-    static const bool pair_enabled = [] { const char* e = getenv("OFQ_GEMM_PAIR"); return !(e && e[0] == '0'); }();
-    const bool pair = pair_enabled && A->dual_delta == 0 && M > BM;
+    // CTA pairs (cta_group::2, 256-row tiles) for the long-K / wide-N problems with many row blocks, where the third less
+    // operand traffic per CTA pays (measured on B200, tools/gemm_sweep.py and the per-site bench table: +4..14 % there,
+    // -3..15 % on the 198-row attention batches and the K = 384 layers, which stay on the single-CTA kernel).
+    // OFQ_GEMM_PAIR=0 / 2 forces the single-CTA / the pair kernel wherever it is legal (A/B measurements, tests).
+    static const int pair_mode = [] { const char* e = getenv("OFQ_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+    const bool pair_legal = A->dual_delta == 0 && M > BM;
+    const bool pair = pair_legal && (pair_mode == 2 || (pair_mode == 1 && M >= 4 * BM && ((long long)K * k2 >= 1024 || N >= 1024)));
     // tile width: minimise (number of N tiles) x (per-tile fixed cost + tile width); the fixed cost (pipeline fill,
     // barrier round trips, epilogue start-up) is worth about 128 columns of MMA/epilogue work
     static const int widths[] = {256, 224, 192, 128, 64, 32};

@@ -54,6 +54,7 @@ constexpr int kChunk = 512;
 constexpr int kMaxBlocks = 4 * 148;
 
 // grid (row blocks, column chunks of 512). dx for the chunk, per-block partial sums of dgamma / dbeta.
+template <bool ONE_CHUNK>
 __global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, long long rows, int cols,
@@ -78,6 +79,55 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     }
     const int c4 = cols >> 2;
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    if (ONE_CHUNK) {
+        // the whole row fits the 512-column chunk (C = 384): ONE pass, the row stays in registers (8 x 16 B in flight per lane)
+        for (long long r = r0 + warp; r < r1; r += 8) {
+            float4 d[4], v[4];
+            const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                d[p] = v[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok[p]) {
+                    d[p] = __ldg(reinterpret_cast<const float4*>(dy + r * cols) + p * 32 + lane);
+                    v[p] = __ldg(reinterpret_cast<const float4*>(x + r * cols) + p * 32 + lane);
+                }
+            }
+            float c1 = 0.f, c2 = 0.f;               // sum(dy*g), sum(dy*g*(x-mu)) over the whole row
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const float t0 = d[p].x * gv[p].x, t1 = d[p].y * gv[p].y, t2 = d[p].z * gv[p].z, t3 = d[p].w * gv[p].w;
+                c1 += (t0 + t1) + (t2 + t3);
+                c2 += ok[p] ? (t0 * (v[p].x - mu) + t1 * (v[p].y - mu)) + (t2 * (v[p].z - mu) + t3 * (v[p].w - mu)) : 0.f;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+                c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+            }
+            c1 = c1 / (float)cols;
+            c2 = c2 * rs / (float)cols;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                if (!ok[p]) continue;
+                const float dd[4] = {d[p].x, d[p].y, d[p].z, d[p].w};
+                const float vv[4] = {v[p].x, v[p].y, v[p].z, v[p].w};
+                const float gg[4] = {gv[p].x, gv[p].y, gv[p].z, gv[p].w};
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float xh = (vv[e] - mu) * rs;
+                    o[e] = rs * (dd[e] * gg[e] - c1 - xh * c2);
+                    a_g[p][e] += dd[e] * xh;
+                    a_b[p][e] += dd[e];
+                }
+                if (res) {
+                    const float4 r4 = __ldg(reinterpret_cast<const float4*>(res + r * cols) + p * 32 + lane);
+                    o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+                }
+                reinterpret_cast<float4*>(dx + r * cols)[p * 32 + lane] = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    } else
     for (long long row = r0 + warp; row < r1; row += 8) {
         const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
         const float4* dyr = reinterpret_cast<const float4*>(dy + row * cols);
@@ -184,7 +234,8 @@ extern "C" int ofq_layernorm_bwd_res(const float* dy, const float* x, const floa
     cudaStream_t st = (cudaStream_t)stream;
     const long long nblk = ln_nblk(rows);
     dim3 grid((unsigned)nblk, (cols + kChunk - 1) / kChunk);
-    layernorm_bwd_kernel<<<grid, 256, 0, st>>>(dy, x, gamma, mean, rstd, rows, cols, res, dx, workspace);
+    if (grid.y == 1) layernorm_bwd_kernel<true><<<grid, 256, 0, st>>>(dy, x, gamma, mean, rstd, rows, cols, res, dx, workspace);
+    else layernorm_bwd_kernel<false><<<grid, 256, 0, st>>>(dy, x, gamma, mean, rstd, rows, cols, res, dx, workspace);
     dim3 g2((cols + 31) / 32, 2);
     colpart_reduce2_kernel<<<g2, 1024, 0, st>>>(workspace, cols, nblk, dgamma, dbeta);
     OFQ_CUDA(cudaGetLastError());

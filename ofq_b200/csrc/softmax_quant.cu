@@ -325,8 +325,10 @@ softmax_quant_vec_kernel(const float* __restrict__ S, long long rows, int N, lon
 // Backward, single 16-bit output (out_a only, one plane): block = 4 warps, one (b, h) slab per block, a warp walks rows
 // warp, warp + 4, ... two at a time; per-key column sums stay in 8 registers per lane and are folded across the 4 warps
 // once, so colsum is written without atomics.
+// 6 CTAs per SM (<= 85 registers): the 768 slabs of a DeiT-S batch then fit in ONE wave of 888 slots (5 per SM would be
+// 740 slots: a second wave with 28 CTAs that costs as much as the first).
 template <bool F16>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 softmax_quant_bwd_vec_kernel(const float* __restrict__ dPq, const float* __restrict__ P, int N, long long ld, int H,
                              const float* __restrict__ s_eff, float qhi, float alpha, float g_s,
                              const float* __restrict__ ca, int ca_per_head, const float* __restrict__ rb,

@@ -709,3 +709,17 @@ def test_layernorm_residual_module(ops):
         outs.append((out.detach(), x.grad.clone(), ln.weight.grad.clone(), ln.bias.grad.clone()))
     for a, b in zip(*outs):
         assert rel_err(a, b) < 1e-6
+
+
+def test_gemm_pair_kernel_forced(ops):
+    """The CTA-pair (cta_group::2) kernel is chosen by a shape heuristic; OFQ_GEMM_PAIR=2 forces it wherever it is legal
+    (M > 128, no dual-A), so the whole GEMM test matrix (int8 exact, fp16 / bf16, MN-major, batched, split-K, outer-K) runs
+    on it in a child process (the switch is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, OFQ_GEMM_PAIR="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                        "gemm and not pair_kernel_forced", "-p", "no:cacheprovider"], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
