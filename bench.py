@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=8, help="images per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sites", default="", help="write a per-call-site kernel timing table of the instrumented steps here")
+    ap.add_argument("--mode", default="qat", choices=["qat", "cga", "eval"],
+                    help="qat: the headline QAT step. cga: BASELINE.json config 5, the CGA fine-tune step (qk_reparam_type=1, "
+                         "freeze mask fused into AdamW for every StatsQ weight, boundaryRange 0.005, lr 1e-5). eval: no-grad "
+                         "inference forward (eval_scripts/deit_s/w2a2.sh uses batch 200)")
     ap.add_argument("--graph", default="on", choices=["on", "off"],
                     help="capture the whole QAT step (fwd+bwd+all-reduce+AdamW) in one CUDA graph and replay it")
     return ap.parse_args()
@@ -59,8 +63,10 @@ T0 = time.perf_counter()
 
 
 def workload_name(a):
-    return (f"{a.model.replace('_', '-')} distilled W{a.bits}A{a.bits} attn_q {'plain' if a.no_qkr else 'QKR'} QAT step "
-            f"(fwd+bwd+AdamW), batch {a.batch}/GPU, synthetic 224x224, random init")
+    what = {"qat": "QAT step (fwd+bwd+AdamW)", "cga": "CGA fine-tune step (fwd+bwd+freeze-masked AdamW)",
+            "eval": "eval forward (no grad)"}[getattr(a, "mode", "qat")]
+    return (f"{a.model.replace('_', '-')} distilled W{a.bits}A{a.bits} attn_q {'plain' if a.no_qkr else 'QKR'} {what}, "
+            f"batch {a.batch}/GPU, synthetic 224x224, random init")
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -178,7 +184,7 @@ def main():
 
     import ofq_b200.quantization as Q
     from ofq_b200 import _lib, ops
-    from ofq_b200.cga import CGAAdamW, param_groups_weight_decay
+    from ofq_b200.cga import CGAAdamW, cga_masked_parameter_names, param_groups_weight_decay
     from ofq_b200.ddp import FlatGradAllReduce, broadcast_parameters
     from ofq_b200.host.deit import DistilledVisionTransformer
 
@@ -198,7 +204,7 @@ def main():
     model = DistilledVisionTransformer(num_classes=1000, **cfg)
     names = Q.deit_qmodule_names(cfg["depth"])
     model = Q.replace_module_by_qmodule_deit(model, Q.make_qconfigs(names, a.bits, a.bits), pretrained_initialized=True,
-                                             qk_reparam=not a.no_qkr, qk_reparam_type=0).to(dev)
+                                             qk_reparam=not a.no_qkr, qk_reparam_type=1 if a.mode == "cga" else 0).to(dev)
     gen = torch.Generator().manual_seed(1234 + rank)
     B = a.batch
     h_img = torch.randn(B, 3, 224, 224, generator=gen).pin_memory()
@@ -210,13 +216,23 @@ def main():
         model(d_img)                           # setup_alpha (train.py:997-1010): creates the LSQ step sizes
     if world > 1:                              # the step sizes are data dependent: make them identical on all ranks
         broadcast_parameters(model, 0)
-    model.train()
-    opt = CGAAdamW(param_groups_weight_decay(model, 0.05, model.no_weight_decay()), lr=5.47e-4)
+    model.train(a.mode != "eval")
+    if a.mode == "cga":       # cga.py:953-1013: every StatsQ-quantized block weight is freeze-masked inside the AdamW kernel
+        pd = dict(model.named_parameters())
+        masked = [pd[n] for n in cga_masked_parameter_names(model, qk_reparam=not a.no_qkr)]
+        opt = CGAAdamW(param_groups_weight_decay(model, 0.05, model.no_weight_decay()), lr=1e-5, masked=masked,
+                       wq_bitw=a.bits, boundary_range=0.005)
+    else:
+        opt = CGAAdamW(param_groups_weight_decay(model, 0.05, model.no_weight_decay()), lr=5.47e-4)
     # data-parallel gradient exchange (ofq_b200/ddp.py): ONE NCCL all-reduce (mean) of a flat fp32 gradient buffer
     ddp = FlatGradAllReduce(model.parameters(), world) if world > 1 else None
     flat = ddp.flat if ddp is not None else None
 
     def step(img, lbl):
+        if a.mode == "eval":
+            with torch.no_grad():
+                (cls, dst), _ = model(img)
+            return cls.float().mean()
         if ddp is None:
             opt.zero_grad(set_to_none=True)
         else:
@@ -376,15 +392,16 @@ def main():
     imgs = B * world * a.steps
     value = imgs / (ms_total * 1e-3)
     e2e = imgs / (ms2.item() * 1e-3)
-    flops_step = 3 * GFLOP_FWD_PER_IMG[a.model] * 1e9 * B
+    flops_step = (1 if a.mode == "eval" else 3) * GFLOP_FWD_PER_IMG[a.model] * 1e9 * B
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "metric": METRIC if a.mode == "qat" else METRIC.replace("QAT images/sec", f"{a.mode} images/sec").replace(" step,", f" {a.mode},"),
+        "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": f"int8 codes fwd (s32 accumulate) / {BWD_DTYPE[bwd_mode]} bwd (f32 accumulate), f32 activations",
         "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": B * world, "parallelism": f"dp{world}",
                    "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush",
-                   "optimizer": "fused AdamW lr 5.47e-4 wd 0.05", "cuda_graph": a.graph == "on", "host_enqueue_ms_per_step": host_enqueue_ms, "bwd_mode": bwd_mode,
+                   "optimizer": {"qat": "fused AdamW lr 5.47e-4 wd 0.05", "cga": "fused CGA-masked AdamW lr 1e-5 wd 0.05 BR 0.005", "eval": "none"}[a.mode], "cuda_graph": a.graph == "on", "host_enqueue_ms_per_step": host_enqueue_ms, "bwd_mode": bwd_mode,
                    "quantized_gemm_tflops_per_gpu": flops_step / (ms_total / a.steps * 1e-3) / 1e12},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": (h_img.numel() * 4 + h_lbl.numel() * 8) * world,
                 "d2h_bytes_per_step": 4 * world, "last_loss": last},

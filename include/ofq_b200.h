@@ -240,6 +240,14 @@ OFQ_API int ofq_softmax_quant_bwd(const float* dPq, const float* P, int nz, int 
                                   int ca_per_head, const float* rb, int planes, void* out_a, void* out_bt,
                                   long long ldo, float* colsum, float* d_s, float* dS32, int out_fmt,
                                   const float* scale4, int a_rowscale, void* stream);
+/* Same with a partial buffer ds_partial [nz][N] (or NULL): on the vectorised path (single 16-bit output, aligned rows) the
+ * per-row scale-gradient terms are stored there and reduced over the slabs by a second tiny launch (d_s is then written,
+ * deterministically, instead of accumulated with same-address atomics). */
+OFQ_API int ofq_softmax_quant_bwd_ex(const float* dPq, const float* P, int nz, int N, long long ld, int H,
+                                     const float* s_eff, int qhi, float alpha, float g_s, const float* ca,
+                                     int ca_per_head, const float* rb, int planes, void* out_a, void* out_bt,
+                                     long long ldo, float* colsum, float* d_s, float* dS32, int out_fmt,
+                                     const float* scale4, int a_rowscale, float* ds_partial, void* stream);
 
 /* K4  W_qk[h] = W_q[h]^T W_k[h] in fp32 (attention.py:190-194) and its backward. wq, wk: [H*hd][C]. */
 OFQ_API int ofq_wqk_compose(const float* wq, const float* wk, int H, int hd, int C, float* wqk, void* stream);

@@ -334,7 +334,7 @@ softmax_quant_bwd_vec_kernel(const float* __restrict__ dPq, const float* __restr
                              const float* __restrict__ ca, int ca_per_head, const float* __restrict__ rb,
                              const float* __restrict__ scale4, int a_rowscale, uint16_t* __restrict__ out_a,
                              long long ldo, float* __restrict__ colsum, float* __restrict__ d_s,
-                             float* __restrict__ dS32) {
+                             float* __restrict__ dS32, float* __restrict__ ds_part) {
     __shared__ float fold[4][kMaxPer * 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int z = blockIdx.x, h = z % H;
@@ -389,7 +389,12 @@ softmax_quant_bwd_vec_kernel(const float* __restrict__ dPq, const float* __restr
                 dot += __shfl_xor_sync(0xffffffffu, dot, o);
                 dsp += __shfl_xor_sync(0xffffffffu, dsp, o);
             }
-            if (lane == 0 && d_s) atomicAdd(d_s + n, g_s * dsp);
+            if (lane == 0) {
+                // 768 slabs x 198 rows all target the same 198 scale gradients: with a partial buffer the per-row term is a
+                // plain store, reduced over the slabs by ds_reduce_kernel (deterministic, no same-address atomics)
+                if (ds_part) ds_part[(long long)z * N + n] = dsp;
+                else if (d_s) atomicAdd(d_s + n, g_s * dsp);
+            }
             const float rb_raw = rb ? __ldg(rb + n) : 1.f;
             const float sca_row = a_rowscale ? sc_a * rb_raw : sc_a;
             float raw[8], va[8];
@@ -418,6 +423,25 @@ softmax_quant_bwd_vec_kernel(const float* __restrict__ dPq, const float* __restr
         __syncthreads();
         for (int d = threadIdx.x; d < N; d += blockDim.x)
             colsum[(long long)z * N + d] = (fold[0][d] + fold[1][d]) + (fold[2][d] + fold[3][d]);
+    }
+}
+
+// d_s[n] = g_s * sum_z part[z][n]: block = 32 rows n x 8 slices of z (fixed order)
+__global__ void __launch_bounds__(256)
+ds_reduce_kernel(const float* __restrict__ part, int nz, int N, float g_s, float* __restrict__ d_s) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + tx;
+    float acc = 0.f;
+    if (n < N)
+        for (int z = ty; z < nz; z += 8) acc += part[(long long)z * N + n];
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && n < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][tx];
+        d_s[n] = g_s * s;
     }
 }
 
@@ -455,11 +479,11 @@ extern "C" int ofq_softmax_quant(const float* S, int nz, int N, long long ld, in
     return ofq_softmax_quant_ex(S, nz, N, ld, H, bias, mask, nW, s_eff, qhi, P, codes, ldq, rowsum, nullptr, OFQ_FMT_F16, stream);
 }
 
-extern "C" int ofq_softmax_quant_bwd(const float* dPq, const float* P, int nz, int N, long long ld, int H,
+extern "C" int ofq_softmax_quant_bwd_ex(const float* dPq, const float* P, int nz, int N, long long ld, int H,
                                      const float* s_eff, int qhi, float alpha, float g_s, const float* ca,
                                      int ca_per_head, const float* rb, int planes, void* out_a, void* out_bt,
                                      long long ldo, float* colsum, float* d_s, float* dS32, int out_fmt,
-                                     const float* scale4, int a_rowscale, void* stream) {
+                                     const float* scale4, int a_rowscale, float* ds_partial, void* stream) {
     OFQ_REQUIRE(dPq && P && s_eff && nz > 0 && N > 0 && H > 0, "ofq_softmax_quant_bwd: bad argument");
     OFQ_REQUIRE(N <= kMaxPer * 32, "ofq_softmax_quant_bwd: at most 256 keys per row are supported");
     OFQ_REQUIRE((!out_a && !out_bt) || (ldo % 8 == 0 && ldo >= N), "ofq_softmax_quant_bwd: output pitch must be a multiple of 8 and >= N");
@@ -475,11 +499,13 @@ extern "C" int ofq_softmax_quant_bwd(const float* dPq, const float* P, int nz, i
         if (out_fmt == OFQ_FMT_F16)
             softmax_quant_bwd_vec_kernel<true><<<nz, 128, 0, (cudaStream_t)stream>>>(
                 dPq, P, N, ld, H, s_eff, (float)qhi, alpha, g_s, ca, ca_per_head, rb, scale4, a_rowscale, (uint16_t*)out_a, ldo,
-                colsum, d_s, dS32);
+                colsum, d_s, dS32, d_s ? ds_partial : nullptr);
         else
             softmax_quant_bwd_vec_kernel<false><<<nz, 128, 0, (cudaStream_t)stream>>>(
                 dPq, P, N, ld, H, s_eff, (float)qhi, alpha, g_s, ca, ca_per_head, rb, scale4, a_rowscale, (uint16_t*)out_a, ldo,
-                colsum, d_s, dS32);
+                colsum, d_s, dS32, d_s ? ds_partial : nullptr);
+        if (d_s && ds_partial)
+            ds_reduce_kernel<<<(N + 31) / 32, 256, 0, (cudaStream_t)stream>>>(ds_partial, nz, N, g_s, d_s);
         OFQ_CUDA(cudaGetLastError());
         return 0;
     }
@@ -495,4 +521,13 @@ extern "C" int ofq_softmax_quant_bwd(const float* dPq, const float* P, int nz, i
             (uint16_t*)out_bt, ldo, colsum, d_s, dS32);
     OFQ_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int ofq_softmax_quant_bwd(const float* dPq, const float* P, int nz, int N, long long ld, int H,
+                                     const float* s_eff, int qhi, float alpha, float g_s, const float* ca,
+                                     int ca_per_head, const float* rb, int planes, void* out_a, void* out_bt,
+                                     long long ldo, float* colsum, float* d_s, float* dS32, int out_fmt,
+                                     const float* scale4, int a_rowscale, void* stream) {
+    return ofq_softmax_quant_bwd_ex(dPq, P, nz, N, ld, H, s_eff, qhi, alpha, g_s, ca, ca_per_head, rb, planes, out_a, out_bt, ldo,
+                                    colsum, d_s, dS32, out_fmt, scale4, a_rowscale, nullptr, stream);
 }

@@ -292,13 +292,16 @@ def softmax_quant_bwd(dPq: torch.Tensor, P: torch.Tensor, N: int, H: int, s_eff:
     dev = P.device
     out_a = torch.empty((nz // H, planes, H, N, ldo), dtype=_T16[fmt], device=dev)
     out_bt = None if single else torch.empty((nz // H, planes, H, N, ldo), dtype=_T16[fmt], device=dev)
+    # the vectorised path (single output, one plane, aligned rows) writes colsum and d_s; the generic one accumulates into them
+    vec_path = single and planes == 1 and ld % 4 == 0
     colsum = torch.zeros((nz, N), dtype=torch.float32, device=dev)
     d_s = torch.zeros(N, dtype=torch.float32, device=dev)
+    ds_part = torch.empty((nz, N), dtype=torch.float32, device=dev) if vec_path else None
     ds32 = torch.empty_like(P) if want_ds32 else None
-    _call("softmax_quant_bwd", 1, nz * N * N * (8.0 + (2 if single else 4) * planes + (4 if want_ds32 else 0)), 0,
-          _lib.load().ofq_softmax_quant_bwd, dPq.data_ptr(), P.data_ptr(), nz, N, ld, H, s_eff.data_ptr(), qhi,
+    _call("softmax_quant_bwd", 2 if vec_path else 1, nz * N * N * (8.0 + (2 if single else 4) * planes + (4 if want_ds32 else 0)), 0,
+          _lib.load().ofq_softmax_quant_bwd_ex, dPq.data_ptr(), P.data_ptr(), nz, N, ld, H, s_eff.data_ptr(), qhi,
           float(alpha), float(g_s), _ptr(ca), 1 if ca_per_head else 0, _ptr(rb), planes, out_a.data_ptr(),
-          _ptr(out_bt), ldo, colsum.data_ptr(), d_s.data_ptr(), _ptr(ds32), fmt, _ptr(scale4), int(single), _st())
+          _ptr(out_bt), ldo, colsum.data_ptr(), d_s.data_ptr(), _ptr(ds32), fmt, _ptr(scale4), int(single), _ptr(ds_part), _st())
     return out_a, out_bt, ldo, colsum, d_s, ds32
 
 
