@@ -85,6 +85,14 @@ OFQ_API int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B, c
              const ofq_vec_t* rs, const ofq_vec_t* cs, const ofq_vec_t* rt, const ofq_vec_t* ct,
              void* stream);
 
+/* Same; out_absmax (optional, one float PRE-SET to 0) receives max |D| over the whole problem, tracked by the epilogue
+ * (atomicMax on the float's bits): the bound from which the fp16 range scale of the next gradient operand is derived
+ * without a pass over D (ofq_scale_from_max). Plain stores only (no accumulate, no split-K). */
+OFQ_API int ofq_gemm_ex(int kind, const ofq_operand_t* A, const ofq_operand_t* B, const ofq_gemm_out_t* out,
+             int M, int N, int K, int k2, int nb1, int nb2, int splits,
+             const ofq_vec_t* rs, const ofq_vec_t* cs, const ofq_vec_t* rt, const ofq_vec_t* ct,
+             float* out_absmax, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K1  StatsQuantizer.forward as integer codes (reference statsq.py:133-150).
  *   sf[r]       = 2 * mean_c |w[r][c]|                       (row sum accumulated in fp64, then fp32 ops)
@@ -147,6 +155,20 @@ OFQ_API int ofq_lsq_bwd(const float* dy, long long lddy, const float* x, long lo
 OFQ_API int ofq_lsq_bwd_act(const float* dy, long long lddy, const float* x, long long ldx, long long rows, int cols,
                             const float* b4, const float* s_eff, int scale_mode, int period, int nseg,
                             int qlo, int qhi, int act, float* dx, long long lddx, float* workspace, void* stream);
+/* Same, and the 16-bit operand of the NEXT backward GEMMs written by the same pass (what ofq_grad_prep would make from dx):
+ *   out16[r][c] = rn16( dx[r][c] * cs16[c] * rs16[r % rs16_period] * scale4[0] )      (pitch ld16, OFQ_FMT_BF16 / _F16)
+ * dx may then be NULL: the gradient of a quantizer input that only feeds a linear layer's backward (the qkx and V
+ * quantizers of attention.py:179-206) never exists in fp32 in HBM. scale4 (ofq_scale_from_max / ofq_absmax_scale layout)
+ * must bound |dx| <= |dy| up front. Streaming layout only (cols % 4 == 0, segments that are multiples of 128 columns). */
+OFQ_API int ofq_lsq_bwd_ex(const float* dy, long long lddy, const float* x, long long ldx, long long rows, int cols,
+                           const float* b4, const float* s_eff, int scale_mode, int period, int nseg,
+                           int qlo, int qhi, int act, float* dx, long long lddx, void* out16, long long ld16, int fmt16,
+                           const float* cs16, const float* rs16, int rs16_period, const float* scale4,
+                           float* workspace, void* stream);
+/* fp16 range scales (ofq_absmax_scale's out4 layout) from n maxima (e.g. the |output| maximum a GEMM epilogue tracked,
+ * ofq_gemm_ex): bound = max(amax) * max|v1| * max|v2| * mult (product != 0), see ofq_absmax_scale. */
+OFQ_API int ofq_scale_from_max(const float* amax, int n, const float* v1, int n1, const float* v2, int n2, float mult,
+                               int product, float* out4, void* stream);
 OFQ_API int ofq_lsq_bwd_finalize(const float* workspace, long long rows, int cols, int scale_mode, int period,
                                  int nseg, float g, float* d_s, float* d_b4, float* d_aft, int zero_sum, void* stream);
 /* ofq_lsq_bwd_finalize and ofq_lsq_bwd_scale (below) in ONE launch: the reductions of the partial sums and the fp16

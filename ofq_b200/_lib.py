@@ -41,11 +41,15 @@ SIGNATURES = {
     "ofq_device_ok": (_i, []),
     "ofq_gemm": (_i, [_i, C.POINTER(Operand), C.POINTER(Operand), C.POINTER(GemmOut), _i, _i, _i, _i, _i, _i, _i,
                       C.POINTER(Vec), C.POINTER(Vec), C.POINTER(Vec), C.POINTER(Vec), _p]),
+    "ofq_gemm_ex": (_i, [_i, C.POINTER(Operand), C.POINTER(Operand), C.POINTER(GemmOut), _i, _i, _i, _i, _i, _i, _i,
+                         C.POINTER(Vec), C.POINTER(Vec), C.POINTER(Vec), C.POINTER(Vec), _p, _p]),
     "ofq_statsq_codes": (_i, [_p, _i, _i, _ll, _i, _p, _ll, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ofq_lsq_effective_scale": (_i, [_p, _i, _f, _p, _p, _p]),
     "ofq_lsq_quant": (_i, [_p, _ll, _i, _ll, _p, _p, _i, _i, _i, _i, _i, _p, _ll, _p]),
     "ofq_lsq_bwd_workspace": (_ll, [_ll, _i, _i]),
     "ofq_lsq_quant_ex": (_i, [_p, _ll, _i, _ll, _p, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p, _ll, _i, _p]),
+    "ofq_lsq_bwd_ex": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p, _ll, _i, _p, _p, _i, _p, _p, _p]),
+    "ofq_scale_from_max": (_i, [_p, _i, _p, _i, _p, _i, _f, _i, _p, _p]),
     "ofq_lsq_bwd_act": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p, _p]),
     "ofq_lsq_bwd": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _i, _i, _i, _i, _i, _p, _ll, _p, _p]),
     "ofq_lsq_bwd_finalize": (_i, [_p, _ll, _i, _i, _i, _i, _f, _p, _p, _p, _i, _p]),

@@ -43,6 +43,7 @@ struct GemmParams {
     int atomic;
     int ab_fmt;              // 16-bit kinds: UMMA a/b format field (0 = F16, 1 = BF16)
     int a_mn, b_mn;          // 16-bit kinds: operand is MN-major (rows contiguous, K strided) instead of K-major
+    unsigned int* amax;      // optional: max |output| over the whole problem (bits of a non-negative float, atomicMax)
 };
 
 // NA: A tiles per pipeline stage. NA = 2 ("dual-A") loads the bf16 hi and lo planes of a gradient operand together with
@@ -211,6 +212,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int half = (warp - 2) >> 2;
         uint8_t* stage_base = smem + L::OUT_OFF + (warp - 2) * OUT_BUFS * 4096;
         uint32_t tc = 0, chunk = 0;
+        float omax = 0.f;                          // max |output| seen by this thread (p.amax)
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tc) {
             const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);
             const uint32_t as = tc & 1, aph = (tc >> 1) & 1;
@@ -278,6 +280,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint32_t raw = c.nit > 0 ? (buf_sel == 0 ? r[0][j] : r[1][j]) : 0u;
                         const float acc = KIND == 0 ? static_cast<float>(static_cast<int32_t>(raw)) : __uint_as_float(raw);
                         o[e] = acc * rsv * csv[e] + rtv * ctv[e];
+                        omax = fmaxf(omax, fabsf(o[e]));    // rows / columns outside the matrix carry exact zeros
                     }
                     rowp[j4 ^ (lane & 7)] = make_float4(o[0], o[1], o[2], o[3]);
                 }
@@ -295,6 +298,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+        if (p.amax) {
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) omax = fmaxf(omax, __shfl_xor_sync(0xffffffffu, omax, o2));
+            if (lane == 0) atomicMax(p.amax, __float_as_uint(omax));
         }
         if (lane == 0) tma_store_wait_all<0>();
     }
@@ -450,6 +458,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int half = (warp - 2) >> 2;
         uint8_t* stage_base = smem + L::OUT_OFF + (warp - 2) * OUT_BUFS * 4096;
         uint32_t tc = 0, chunk = 0;
+        float omax = 0.f;                          // max |output| seen by this thread (p.amax)
         for (int t = pair; t < num_tiles; t += npairs, ++tc) {
             const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);
             const int m0 = 2 * c.m0 + (int)rank * BM;
@@ -517,6 +526,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const uint32_t raw = c.nit > 0 ? (buf_sel == 0 ? r[0][j] : r[1][j]) : 0u;
                         const float acc = KIND == 0 ? static_cast<float>(static_cast<int32_t>(raw)) : __uint_as_float(raw);
                         o[e] = acc * rsv * csv[e] + rtv * ctv[e];
+                        omax = fmaxf(omax, fabsf(o[e]));    // rows / columns outside the matrix carry exact zeros
                     }
                     rowp[j4 ^ (lane & 7)] = make_float4(o[0], o[1], o[2], o[3]);
                 }
@@ -533,6 +543,11 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[as]), 0));
+        }
+        if (p.amax) {
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) omax = fmaxf(omax, __shfl_xor_sync(0xffffffffu, omax, o2));
+            if (lane == 0) atomicMax(p.amax, __float_as_uint(omax));
         }
         if (lane == 0) tma_store_wait_all<0>();
     }
@@ -678,6 +693,12 @@ static int make_out_map(CUtensorMap* tm, const ofq_gemm_out_t* out, int M, int N
 extern "C" int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B, const ofq_gemm_out_t* out,
                         int M, int N, int K, int k2, int nb1, int nb2, int splits, const ofq_vec_t* rs,
                         const ofq_vec_t* cs, const ofq_vec_t* rt, const ofq_vec_t* ct, void* stream) {
+    return ofq_gemm_ex(kind, A, B, out, M, N, K, k2, nb1, nb2, splits, rs, cs, rt, ct, nullptr, stream);
+}
+
+extern "C" int ofq_gemm_ex(int kind, const ofq_operand_t* A, const ofq_operand_t* B, const ofq_gemm_out_t* out,
+                           int M, int N, int K, int k2, int nb1, int nb2, int splits, const ofq_vec_t* rs,
+                           const ofq_vec_t* cs, const ofq_vec_t* rt, const ofq_vec_t* ct, float* out_absmax, void* stream) {
     if (kind != OFQ_GEMM_I8 && kind != OFQ_GEMM_BF16 && kind != OFQ_GEMM_F16) {
         ofq_set_error("ofq_gemm: unknown kind %d", kind);
         return OFQ_ERR_ARG;
@@ -708,6 +729,11 @@ extern "C" int ofq_gemm(int kind, const ofq_operand_t* A, const ofq_operand_t* B
     p.a_mn = A->mn_major != 0; p.b_mn = B->mn_major != 0;
     if ((p.a_mn || p.b_mn) && (kind == OFQ_GEMM_I8 || A->dual_delta > 0)) {
         ofq_set_error("ofq_gemm: MN-major operands are supported for the 16-bit kinds without dual-A only");
+        return OFQ_ERR_ARG;
+    }
+    p.amax = reinterpret_cast<unsigned int*>(out_absmax);
+    if (out_absmax && (p.atomic || splits > 1)) {
+        ofq_set_error("ofq_gemm: the output maximum is tracked for plain (non-accumulating, unsplit) stores only");
         return OFQ_ERR_ARG;
     }
     if (splits > 1 && !p.atomic) {

@@ -149,6 +149,13 @@ __device__ __forceinline__ void gelu_both(float x, float* a, float* d) {
     *a = __fmul_rn(__fmul_rn(x, 0.5f), e1);
     *d = fmaf(x, __expf(-0.5f * x * x) * 0.39894228040143267794f, 0.5f * e1);
 }
+// two floats -> packed fp16 / bf16 pair (round to nearest), first in the low half
+__device__ __forceinline__ uint32_t pack_rn16(float a, float b, bool f16) {
+    uint32_t r;
+    if (f16) asm("cvt.rn.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(b), "f"(a));
+    else     asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
 // two small integers -> packed fp16 / bf16 pair (exact), first in the low half
 __device__ __forceinline__ uint32_t pack_codes16(int a, int b, bool f16) {
     uint32_t r;
@@ -451,13 +458,21 @@ __host__ __device__ inline BwdPlan bwd_plan(int cols) {
     return p;
 }
 
-template <int MODE, int ACT>
-__global__ void __launch_bounds__(256, 4)
+// OUT16: additionally (or instead of the fp32 dx, which may be NULL) emit the 16-bit operand of the NEXT backward GEMMs,
+// out16[r][c] = rn16(dx * cs16[c] * rs16[r % period16] * scale4[0]) (what ofq_grad_prep would make from dx in a second
+// pass): the gradient then never exists in fp32 in HBM. scale4 must be known up front (from a bound on |dy|).
+struct Out16 {
+    uint16_t* ptr; long long ld; int f16;
+    const float* cs; const float* rs; uint32_t period; const float* scale4;
+};
+
+template <int MODE, int ACT, bool OUT16>
+__global__ void __launch_bounds__(256, OUT16 ? 3 : 4)
 lsq_bwd_stream_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
                       uint32_t rows, int cols, const float* __restrict__ b4, const float* __restrict__ s_eff,
                       uint32_t period, int nseg, int seg_len, float qlo, float qhi,
                       float* __restrict__ dx, long long lddx, float* __restrict__ rowpart,
-                      float* __restrict__ colpart, float* __restrict__ blockmax) {
+                      float* __restrict__ colpart, float* __restrict__ blockmax, const Out16 o16) {
     constexpr int ILP = 2;
     __shared__ float fold_s[8][3][128];
     __shared__ float bmax_s[8];
@@ -482,9 +497,18 @@ lsq_bwd_stream_kernel(const float* __restrict__ dy, long long lddy, const float*
     uint32_t n = rl % period;
     float aft[4] = {0.f, 0.f, 0.f, 0.f}, ab4[4] = {0.f, 0.f, 0.f, 0.f}, as[4] = {0.f, 0.f, 0.f, 0.f};
     float tmax = 0.f;
+    float4 c16 = make_float4(1.f, 1.f, 1.f, 1.f);
+    float sc16 = 1.f;
+    uint32_t n16 = 0, dn16 = 0;
+    if (OUT16) {
+        if (act && o16.cs) c16 = __ldg(reinterpret_cast<const float4*>(o16.cs + col));
+        sc16 = o16.scale4 ? __ldg(o16.scale4) : 1.f;
+        n16 = rl % o16.period;
+        dn16 = dr % o16.period;
+    }
     for (uint32_t row = rl; row < rows; row += dr * ILP) {
         float4 g4[ILP], x4[ILP];
-        float isv[ILP];
+        float isv[ILP], r16[ILP];
 #pragma unroll
         for (int u = 0; u < ILP; ++u) {
             const uint32_t r = row + u * dr;
@@ -496,9 +520,14 @@ lsq_bwd_stream_kernel(const float* __restrict__ dy, long long lddy, const float*
                     x4[u] = __ldg(reinterpret_cast<const float4*>(x + (long long)r * ldx + col));
                 }
                 if (MODE == OFQ_SCALE_PER_ROW) isv[u] = __ldg(s_eff + n * nseg + seg);
+                if (OUT16) r16[u] = o16.rs ? __ldg(o16.rs + n16) : 1.f;
             }
             n += dn;
             if (n >= period) n -= period;
+            if (OUT16) {
+                n16 += dn16;
+                if (n16 >= o16.period) n16 -= o16.period;
+            }
         }
 #pragma unroll
         for (int u = 0; u < ILP; ++u) {
@@ -528,7 +557,13 @@ lsq_bwd_stream_kernel(const float* __restrict__ dy, long long lddy, const float*
                 tmax = fmaxf(tmax, fabsf(o[e]));
                 if (MODE == OFQ_SCALE_PER_ROW) part += t; else as[e] += t;
             }
-            if (act) *reinterpret_cast<float4*>(dx + (long long)r * lddx + col) = make_float4(o[0], o[1], o[2], o[3]);
+            if (act && dx) *reinterpret_cast<float4*>(dx + (long long)r * lddx + col) = make_float4(o[0], o[1], o[2], o[3]);
+            if (OUT16 && act) {
+                const float sr = sc16 * r16[u];
+                *reinterpret_cast<uint2*>(o16.ptr + (long long)r * o16.ld + col) =
+                    make_uint2(pack_rn16(o[0] * c16.x * sr, o[1] * c16.y * sr, o16.f16 != 0),
+                               pack_rn16(o[2] * c16.z * sr, o[3] * c16.w * sr, o16.f16 != 0));
+            }
             if (MODE == OFQ_SCALE_PER_ROW) {
                 part = warp_sum(part);
                 if (lane == 0) rp[(long long)r * nseg] = part;
@@ -1213,6 +1248,15 @@ extern "C" int ofq_lsq_bwd_scale(const float* workspace, long long rows, int col
     return 0;
 }
 
+extern "C" int ofq_scale_from_max(const float* amax, int n, const float* v1, int n1, const float* v2, int n2, float mult,
+                                  int product, float* out4, void* stream) {
+    OFQ_REQUIRE(amax && out4 && n > 0, "ofq_scale_from_max: bad argument");
+    OFQ_CHECK_ARCH();
+    scale_from_blockmax_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(amax, n, v1, n1, v2, n2, mult, product, out4);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int ofq_lsq_bwd(const float* dy, long long lddy, const float* x, long long ldx, long long rows,
                            int cols, const float* b4, const float* s_eff, int scale_mode, int period, int nseg,
                            int qlo, int qhi, float* dx, long long lddx, float* workspace, void* stream) {
@@ -1223,7 +1267,22 @@ extern "C" int ofq_lsq_bwd(const float* dy, long long lddy, const float* x, long
 extern "C" int ofq_lsq_bwd_act(const float* dy, long long lddy, const float* x, long long ldx, long long rows,
                                int cols, const float* b4, const float* s_eff, int scale_mode, int period, int nseg,
                                int qlo, int qhi, int act, float* dx, long long lddx, float* workspace, void* stream) {
-    OFQ_REQUIRE(dy && x && b4 && s_eff && dx && workspace, "ofq_lsq_bwd: null pointer");
+    OFQ_REQUIRE(dx, "ofq_lsq_bwd: null pointer");
+    return ofq_lsq_bwd_ex(dy, lddy, x, ldx, rows, cols, b4, s_eff, scale_mode, period, nseg, qlo, qhi, act, dx, lddx, nullptr, 0,
+                          OFQ_FMT_F16, nullptr, nullptr, 0, nullptr, workspace, stream);
+}
+
+extern "C" int ofq_lsq_bwd_ex(const float* dy, long long lddy, const float* x, long long ldx, long long rows,
+                              int cols, const float* b4, const float* s_eff, int scale_mode, int period, int nseg,
+                              int qlo, int qhi, int act, float* dx, long long lddx, void* out16, long long ld16, int fmt16,
+                              const float* cs16, const float* rs16, int rs16_period, const float* scale4,
+                              float* workspace, void* stream) {
+    OFQ_REQUIRE(dy && x && b4 && s_eff && (dx || out16) && workspace, "ofq_lsq_bwd: null pointer");
+    OFQ_REQUIRE(!out16 || (lsq_bwd_streaming(cols, nseg) && (uintptr_t)out16 % 8 == 0 && ld16 % 4 == 0 && ld16 >= cols &&
+                           (fmt16 == OFQ_FMT_BF16 || fmt16 == OFQ_FMT_F16) && (!cs16 || (uintptr_t)cs16 % 16 == 0)),
+                "ofq_lsq_bwd: the fused 16-bit operand needs the streaming layout (columns % 4 == 0, 128-column segment multiples), "
+                "an 8-byte aligned output with a pitch that is a multiple of 4 and a 16-byte aligned cs16");
+    OFQ_REQUIRE(!out16 || !rs16 || rs16_period >= rows || rows % rs16_period == 0, "ofq_lsq_bwd: rows must be a multiple of rs16_period");
     OFQ_REQUIRE(act == OFQ_ACT_NONE || act == OFQ_ACT_GELU, "ofq_lsq_bwd: unknown activation");
     OFQ_REQUIRE(rows > 0 && cols > 0 && nseg > 0 && cols % nseg == 0 && period > 0, "ofq_lsq_bwd: bad shape");
     const int seg_len = cols / nseg;
@@ -1231,6 +1290,9 @@ extern "C" int ofq_lsq_bwd_act(const float* dy, long long lddy, const float* x, 
                 "ofq_lsq_bwd: columns, segment length and row strides must be multiples of 4");
     OFQ_REQUIRE((uintptr_t)dy % 16 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)dx % 16 == 0 &&
                 (uintptr_t)b4 % 16 == 0 && (uintptr_t)s_eff % 16 == 0, "ofq_lsq_bwd: pointers must be 16-byte aligned");
+    Out16 o16;
+    o16.ptr = (uint16_t*)out16; o16.ld = ld16; o16.f16 = fmt16 == OFQ_FMT_F16; o16.cs = cs16; o16.rs = rs16;
+    o16.period = (rs16 && rs16_period > 0) ? (uint32_t)rs16_period : 0x7fffffffu; o16.scale4 = scale4;
     OFQ_CHECK_ARCH();
     const LsqBwdWs wsl = lsq_bwd_ws(rows, cols, nseg);
     float* rowpart = workspace;
@@ -1242,8 +1304,14 @@ extern "C" int ofq_lsq_bwd_act(const float* dy, long long lddy, const float* x, 
         OFQ_REQUIRE(scale_mode != OFQ_SCALE_PER_ROW || period >= rows || rows % period == 0,
                     "ofq_lsq_bwd: rows must be a multiple of the scale period");
 #define OFQ_LSQ_BWD_STREAM(MODE, ACT, PERIOD)                                                                              \
-    lsq_bwd_stream_kernel<MODE, ACT><<<kStreamCtas, 256, 0, st>>>(dy, lddy, x, ldx, (uint32_t)rows, cols, b4, s_eff, PERIOD, nseg, \
-                                                                  seg_len, (float)qlo, (float)qhi, dx, lddx, rowpart, colpart, blockmax)
+    do {                                                                                                                   \
+        if (out16)                                                                                                         \
+            lsq_bwd_stream_kernel<MODE, ACT, true><<<kStreamCtas, 256, 0, st>>>(dy, lddy, x, ldx, (uint32_t)rows, cols, b4, s_eff, PERIOD, nseg, \
+                                                                                seg_len, (float)qlo, (float)qhi, dx, lddx, rowpart, colpart, blockmax, o16); \
+        else                                                                                                               \
+            lsq_bwd_stream_kernel<MODE, ACT, false><<<kStreamCtas, 256, 0, st>>>(dy, lddy, x, ldx, (uint32_t)rows, cols, b4, s_eff, PERIOD, nseg, \
+                                                                                 seg_len, (float)qlo, (float)qhi, dx, lddx, rowpart, colpart, blockmax, o16); \
+    } while (0)
         if (scale_mode == OFQ_SCALE_PER_ROW) {
             if (act == OFQ_ACT_GELU) OFQ_LSQ_BWD_STREAM(OFQ_SCALE_PER_ROW, OFQ_ACT_GELU, (uint32_t)period);
             else OFQ_LSQ_BWD_STREAM(OFQ_SCALE_PER_ROW, OFQ_ACT_NONE, (uint32_t)period);
@@ -1255,6 +1323,7 @@ extern "C" int ofq_lsq_bwd_act(const float* dy, long long lddy, const float* x, 
         OFQ_CUDA(cudaGetLastError());
         return 0;
     }
+    OFQ_REQUIRE(dx && !out16, "ofq_lsq_bwd: the generic (non-streaming) layout produces the fp32 dx only");
     const unsigned grid = (unsigned)lsq_bwd_nblk(rows);
 #define OFQ_LSQ_BWD(MODE, NP)                                                                                          \
     lsq_bwd_kernel<MODE, NP><<<grid, kWarpsPerBlock * 32, 0, st>>>(dy, lddy, x, ldx, rows, cols, b4, s_eff, period, nseg, \

@@ -65,10 +65,10 @@ def vec(t: Optional[torch.Tensor], period: int = 0, bs1: int = 0, bs2: int = 0):
 def gemm(kind: int, a: torch.Tensor, a_strides, b: torch.Tensor, b_strides, out: torch.Tensor, out_strides,
          M: int, N: int, K: int, *, k2: int = 1, nb1: int = 1, nb2: int = 1, splits: int = 1, accumulate: bool = False,
          rs=None, cs=None, rt=None, ct=None, a_k2mod: int = 0, b_k2mod: int = 0, a_dual_delta: int = 0,
-         a_mn: bool = False, b_mn: bool = False) -> None:
+         a_mn: bool = False, b_mn: bool = False, amax: Optional[torch.Tensor] = None) -> None:
     """Raw ofq_gemm call. a_strides/b_strides = (row, k2, batch1, batch2) in elements; out_strides = (ld, b1, b2).
     a_mn / b_mn: the operand is stored [k][row] (MN-major) and its first stride is the distance between consecutive k.
-    rs/cs/rt/ct are ctypes Vec references from `vec()` or None."""
+    rs/cs/rt/ct are ctypes Vec references from `vec()` or None. amax: one fp32 element pre-set to 0 that receives max |out|."""
     _cuda(a, b, out)
     A = Operand(a.data_ptr(), a_strides[0], a_strides[1], a_k2mod, a_dual_delta, a_strides[2], a_strides[3], int(a_mn))
     B = Operand(b.data_ptr(), b_strides[0], b_strides[1], b_k2mod, 0, b_strides[2], b_strides[3], int(b_mn))
@@ -82,8 +82,8 @@ def gemm(kind: int, a: torch.Tensor, a_strides, b: torch.Tensor, b_strides, out:
     nout = (nb1 if out_strides[1] else 1) * (nb2 if out_strides[2] else 1)
     alg_bytes = eb * K * (M * _n(a_strides, a_k2mod) + N * _n(b_strides, b_k2mod)) + 4 * M * N * nout * (2 if accumulate else 1)
     alg_flops = 2.0 * M * N * K * k2 * nb1 * nb2 * (2 if a_dual_delta else 1)
-    _call(("gemm_i8", "gemm_bf16", "gemm_f16")[kind], 1, alg_bytes, alg_flops, _lib.load().ofq_gemm, kind,
-          C.byref(A), C.byref(B), C.byref(O), M, N, K, k2, nb1, nb2, splits, rs, cs, rt, ct, _st(), tag=tag)
+    _call(("gemm_i8", "gemm_bf16", "gemm_f16")[kind], 1, alg_bytes, alg_flops, _lib.load().ofq_gemm_ex, kind,
+          C.byref(A), C.byref(B), C.byref(O), M, N, K, k2, nb1, nb2, splits, rs, cs, rt, ct, _ptr(amax), _st(), tag=tag)
 
 
 # ------------------------------------------------------------------------------------------------ quantizers
@@ -152,20 +152,31 @@ def lsq_quant(x2d: torch.Tensor, b4: torch.Tensor, s_eff: torch.Tensor, mode: in
 
 def lsq_bwd(dy2d: torch.Tensor, x2d: torch.Tensor, b4: torch.Tensor, s_eff: torch.Tensor, mode: int, period: int,
             nseg: int, qlo: int, qhi: int, g: float, want_ds: bool = True, want_aft: bool = True, next_scale=None,
-            zero_sum: bool = False, act: int = ACT_NONE):
+            zero_sum: bool = False, act: int = ACT_NONE, out16=None, want_dx: bool = True):
     """Returns (dx [rows, cols], d_s, d_b4 [cols], d_aft [cols] | None).  next_scale = (v1, v2, mult, product): additionally
     returns the fp16 range scales (absmax_scale layout) of dx*v1[c] / dx*v2[r] for the GEMM operand made from dx,
     derived from max|dx| at no extra pass over dx.  act: the quantizer saw act(x2d) (lsq_quant(act=...)); dx is then the
-    gradient w.r.t. the pre-activation x2d."""
+    gradient w.r.t. the pre-activation x2d.  out16 = (fmt, cs [cols], rs, rs_period, scale4): the same pass also writes the
+    16-bit GEMM operand rn16(dx * cs[c] * rs[r % rs_period] * scale4[0]) (appended to the result); with want_dx=False the
+    fp32 dx is not written at all (returned as None)."""
     _cuda(dy2d, x2d)
     assert dy2d.dim() == 2 and dy2d.stride(1) == 1 and x2d.stride(1) == 1
     rows, cols = dy2d.shape
     lib = _lib.load()
     ws = torch.empty(lib.ofq_lsq_bwd_workspace(rows, cols, nseg), dtype=torch.float32, device=dy2d.device)
-    dx = torch.empty((rows, cols), dtype=torch.float32, device=dy2d.device)
-    _call("lsq_bwd", 1, 12.0 * rows * cols, 0, lib.ofq_lsq_bwd_act, dy2d.data_ptr(), dy2d.stride(0), x2d.data_ptr(),
-          x2d.stride(0), rows, cols, b4.data_ptr(), s_eff.data_ptr(), mode, period, nseg, qlo, qhi, act, dx.data_ptr(),
-          dx.stride(0), ws.data_ptr(), _st())
+    dx = torch.empty((rows, cols), dtype=torch.float32, device=dy2d.device) if (want_dx or out16 is None) else None
+    o16 = None
+    if out16 is None:
+        _call("lsq_bwd", 1, 12.0 * rows * cols, 0, lib.ofq_lsq_bwd_act, dy2d.data_ptr(), dy2d.stride(0), x2d.data_ptr(),
+              x2d.stride(0), rows, cols, b4.data_ptr(), s_eff.data_ptr(), mode, period, nseg, qlo, qhi, act, dx.data_ptr(),
+              dx.stride(0), ws.data_ptr(), _st())
+    else:
+        fmt16, cs16, rs16, rs16_period, scale4 = out16
+        o16 = torch.empty((rows, cols), dtype=_T16[fmt16], device=dy2d.device)
+        _call("lsq_bwd", 1, (10.0 + (4 if dx is not None else 0)) * rows * cols, 0, lib.ofq_lsq_bwd_ex, dy2d.data_ptr(),
+              dy2d.stride(0), x2d.data_ptr(), x2d.stride(0), rows, cols, b4.data_ptr(), s_eff.data_ptr(), mode, period, nseg, qlo,
+              qhi, act, _ptr(dx), cols, o16.data_ptr(), cols, fmt16, _ptr(cs16), _ptr(rs16), rs16_period, _ptr(scale4),
+              ws.data_ptr(), _st())
     ns = cols if mode == PER_COL else min(period, rows) * nseg
     d_s = torch.empty(ns, dtype=torch.float32, device=dy2d.device) if want_ds else None
     d_b4 = torch.empty(cols, dtype=torch.float32, device=dy2d.device)
@@ -173,6 +184,8 @@ def lsq_bwd(dy2d: torch.Tensor, x2d: torch.Tensor, b4: torch.Tensor, s_eff: torc
     if next_scale is None:
         _call("lsq_bwd_finalize", 1, 4.0 * ws.numel(), 0, lib.ofq_lsq_bwd_finalize, ws.data_ptr(), rows, cols, mode, period,
               nseg, float(g), _ptr(d_s), d_b4.data_ptr(), _ptr(d_aft), int(zero_sum), _st())
+        if out16 is not None:
+            return dx, d_s, d_b4, d_aft, o16
         return dx, d_s, d_b4, d_aft
     v1, v2, mult, product = next_scale
     sc = torch.empty(4, dtype=torch.float32, device=dy2d.device)
@@ -184,6 +197,15 @@ def lsq_bwd(dy2d: torch.Tensor, x2d: torch.Tensor, b4: torch.Tensor, s_eff: torc
 
 def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
+
+
+def scale_from_max(amax: torch.Tensor, *, v1=None, v2=None, mult: float = 1.0, product: bool = False) -> torch.Tensor:
+    """fp16 range scales (absmax_scale layout) from maxima tracked elsewhere (e.g. gemm(amax=...))."""
+    out = torch.empty(4, dtype=torch.float32, device=amax.device)
+    _call("absmax_scale", 1, 0.0, 0, _lib.load().ofq_scale_from_max, amax.data_ptr(), amax.numel(), _ptr(v1),
+          0 if v1 is None else v1.numel(), _ptr(v2), 0 if v2 is None else v2.numel(), float(mult), int(product), out.data_ptr(),
+          _st())
+    return out
 
 
 _ABSMAX_WS = {}

@@ -38,6 +38,8 @@ FMT = FMT_F16 if F16 else FMT_BF16
 DUAL = PLANES == 2
 K2P = 1 if DUAL else PLANES          # outer-K slices still looped over
 DD = 1 if DUAL else 0                # dual_delta for operands laid out [plane][...]
+# fp16 mode: let the LSQ backward of the V / qkx quantizers write the fp16 GEMM operand directly (tests toggle this)
+FUSED16 = os.environ.get("OFQ_FUSED16", "1") != "0"
 
 
 def levels(bit: int, all_positive: bool):
@@ -64,31 +66,35 @@ def _scalar(sc):
     return vec(sc[1:2], 1)
 
 
-def _linear_backward_f16(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulate_dx: bool, qx16=None, sc=None):
+def _linear_backward_f16(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulate_dx: bool, qx16=None, sc=None, a16=None,
+                         colsum=None):
     """fp16 backward of out = x_hat @ W_hat^T (+bias) with ONE range-scaled copy of the gradient,
     A16[t,n] = fp16(dY[t,n] * colscale[n] * se_x[t] * sc), read K-major by the dX GEMM and MN-major by the dW GEMM; the
     code operands stay exact and un-transposed (MN-major B), the folded scale vectors are undone per output row:
         dX_hat[t,k] (+)= 1/(se_x[t] sc) * sum_n A16[t,n] wc[n,k]
         dW[n,k]        = 1/(colscale[n] sc) * sum_t A16[t,n] qx[t,k] + colsum(dY)[n] * aft[k]
-    cs2 = [colscale, 1/colscale], se2 = [se_x, 1/se_x]. Returns (dW, dbias, qx16)."""
-    M, Nout = dY2d.shape
-    K = qx.shape[1]
-    if sc is None:
-        sc = ops.absmax_scale(dY2d, 1, M, Nout, dY2d.stride(0), 0, cs=cs2[0], rs=se2[0], rs_period=period, product=True)
-    prep = ops.grad_prep(dY2d, 1, M, Nout, dY2d.stride(0), 0, cs=cs2[0], rs=se2[0], rs_period=period, want_rm=True,
-                         want_colsum=True, fmt=FMT, scale4=sc, rm_rowscale=True)
-    a16 = prep["rm"]
+    cs2 = [colscale, 1/colscale], se2 = [se_x, 1/se_x]. Returns (dW, dbias, qx16).
+    a16 / colsum: the operand and colsum(dY) already produced by the pass that made dY (ops.lsq_bwd(out16=...)); dY2d is
+    then not read (and may be None)."""
+    M, K = qx.shape
+    Nout = wc.shape[0]
+    if a16 is None:
+        if sc is None:
+            sc = ops.absmax_scale(dY2d, 1, M, Nout, dY2d.stride(0), 0, cs=cs2[0], rs=se2[0], rs_period=period, product=True)
+        prep = ops.grad_prep(dY2d, 1, M, Nout, dY2d.stride(0), 0, cs=cs2[0], rs=se2[0], rs_period=period, want_rm=True,
+                             want_colsum=True, fmt=FMT, scale4=sc, rm_rowscale=True)
+        a16, colsum = prep["rm"], prep["colsum"]
     wc16 = ops.codes_to_bf16(wc, 1, Nout, K, K, 0, False, FMT)           # [1, Nout, K]
     ops.gemm(GEMM_BWD, a16, (Nout, 0, 0, 0), wc16, (K, 0, 0, 0), dxhat, (K, 0, 0), M, K, Nout, b_mn=True,
              accumulate=accumulate_dx, rs=vec(se2[1], period), cs=_scalar(sc))
     if qx16 is None:
         qx16 = ops.codes_to_bf16(qx, 1, M, K, K, 0, False, FMT)          # [1, M, K]
-    dW = torch.zeros((Nout, K), dtype=torch.float32, device=dY2d.device)
+    dW = torch.zeros((Nout, K), dtype=torch.float32, device=a16.device)
     tiles = ((Nout + 127) // 128) * ((K + 127) // 128)
     splits = _splits_for(tiles, (M + 63) // 64)
     ops.gemm(GEMM_BWD, a16, (Nout, 0, 0, 0), qx16, (K, 0, 0, 0), dW, (K, 0, 0), Nout, K, M, a_mn=True, b_mn=True,
-             splits=splits, accumulate=True, rs=vec(cs2[1]), cs=_scalar(sc), rt=vec(prep["colsum"]), ct=vec(x_aft))
-    return dW, prep["colsum"], qx16
+             splits=splits, accumulate=True, rs=vec(cs2[1]), cs=_scalar(sc), rt=vec(colsum), ct=vec(x_aft))
+    return dW, colsum, qx16
 
 
 def _linear_backward(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulate_dx: bool, qxT_all=None, sc=None):
@@ -264,7 +270,7 @@ def _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C):
     return out
 
 
-def _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=None, qp16=None, sc=None):
+def _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=None, qp16=None, sc=None, amax_dv=None):
     """fp16 backward of P_hat V_hat with ONE copy A16[b,n,c] = fp16(dO * se_v[c] * se_p[n] * sc):
         dP_hat[z,n,d]  = 1/(se_p[n] sc) * sum_j A16[b,n,hj] qv[b,d,hj] + sum_j dO[b,n,hj] v_aft[hj]
         dv_hat[b,d,hj] = 1/(se_v[hj] sc) * sum_n qp[z,n,d] A16[b,n,hj]                    (both operands MN-major)"""
@@ -283,15 +289,15 @@ def _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=Non
         qp16 = ops.codes_to_bf16(qp, B * H, N, ldq, ldq, N * ldq, False, FMT)    # [B*H, N, ldq]
     dvhat = torch.empty((B, N, C), dtype=torch.float32, device=dO.device)
     ops.gemm(GEMM_BWD, qp16, (ldq, 0, N * ldq, H * N * ldq), a16, (C, 0, hd, N * C), dvhat, (C, hd, N * C), N, hd, N,
-             nb1=H, nb2=B, a_mn=True, b_mn=True, rs=_scalar(sc), cs=vec(sv2[1], 0, hd))
+             nb1=H, nb2=B, a_mn=True, b_mn=True, rs=_scalar(sc), cs=vec(sv2[1], 0, hd), amax=amax_dv)
     return dPq, dvhat
 
 
-def _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=None, qp16=None, sc=None):
+def _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=None, qp16=None, sc=None, amax_dv=None):
     """Returns (dPq [B*H,N,ldS] fp32, dvhat [B,N,C] fp32). sp2 / sv2 = [scale, 1/scale] of the probability / V quantizer.
     qv16 / qp16: exact 16-bit copies of the codes left by the forward quantizer passes (fp16 mode)."""
     if F16:
-        return _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16, qp16, sc)
+        return _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16, qp16, sc, amax_dv)
     se_p, se_v = sp2[0], sv2[0]
     hd = C // H
     prep = ops.grad_prep(dO, B, N, C, C, N * C, cs=se_v, rs=se_p, rs_period=N, want_rm=True, want_t=True,
@@ -398,14 +404,26 @@ class QKRAttnCoreFn(torch.autograd.Function):
         M = B * N
         dev = dO.device
         dO = dO.contiguous()
+        # fp16 mode: the GEMMs that produce d v_hat / d k_hat track max |output| in their epilogue; the LSQ backward passes
+        # of the V and qkx quantizers then write the fp16 operand of the next linear layer's backward GEMMs directly
+        # (range scale from that bound), so d v_out / d qkx never exist in fp32 and ofq_grad_prep is not needed there
+        fused16 = F16 and FUSED16 and C % 128 == 0      # streaming layout of the (token, head)-segmented qkx pass
+        amax = torch.zeros(2, dtype=torch.float32, device=dev) if fused16 else None
         dPq, dvhat = _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16, qp16,
-                                  link.sc if link is not None else None)
+                                  link.sc if link is not None else None, amax_dv=amax[0:1] if fused16 else None)
         # --- V quantizer and V linear
-        dv_out, ds_v, dvb4, dvaft, *sc_v = ops.lsq_bwd(dvhat.view(M, C), v_out, v_b4, se_v, PER_COL, 1, 1, lo, hi, g_v,
-                                                       next_scale=(cs_v, se_x, 1.0, True) if F16 else None)
         dxhat = torch.empty((M, C), dtype=torch.float32, device=dev)
-        dWv, dbv, qx_op = _linear_backward(dv_out, qx, wvc, (cs_v, ics_v), sx2, N, x_aft, dxhat, False, qx16,
-                                           sc=sc_v[0] if sc_v else None)
+        if fused16:
+            sc_v = ops.scale_from_max(amax[0:1], v1=cs_v, v2=se_x, product=True)
+            _, ds_v, dvb4, dvaft, a16_v = ops.lsq_bwd(dvhat.view(M, C), v_out, v_b4, se_v, PER_COL, 1, 1, lo, hi, g_v,
+                                                      out16=(FMT, cs_v, se_x, N, sc_v), want_dx=False)
+            dWv, dbv, qx_op = _linear_backward_f16(None, qx, wvc, (cs_v, ics_v), sx2, N, x_aft, dxhat, False, qx16, sc=sc_v,
+                                                   a16=a16_v, colsum=dvb4)
+        else:
+            dv_out, ds_v, dvb4, dvaft, *sc_v = ops.lsq_bwd(dvhat.view(M, C), v_out, v_b4, se_v, PER_COL, 1, 1, lo, hi, g_v,
+                                                           next_scale=(cs_v, se_x, 1.0, True) if F16 else None)
+            dWv, dbv, qx_op = _linear_backward(dv_out, qx, wvc, (cs_v, ics_v), sx2, N, x_aft, dxhat, False, qx16,
+                                               sc=sc_v[0] if sc_v else None)
         # --- softmax + probability quantizer, then the two score GEMMs
         if F16:
             # |dS| = |alpha P (dP - sum P dP)| <= 2 alpha max|dPq|; ONE copy dS16[b,h,n,d] = fp16(dS se_k[h,d] se_x[n] sc)
@@ -424,7 +442,7 @@ class QKRAttnCoreFn(torch.autograd.Function):
             dkhat = torch.empty((M, H * C), dtype=torch.float32, device=dev)
             ops.gemm(GEMM_BWD, dS16, (ldo, 0, slab, H * slab), qx_op, (C, 0, 0, N * C), dkhat, (H * C, C, N * H * C),
                      N, C, N, nb1=H, nb2=B, a_mn=True, b_mn=True, rs=vec(sk2_hn[1], 0, N), cs=_scalar(sc),
-                     rt=vec(colsum_dS, 0, N, H * N), ct=vec(x_aft))
+                     rt=vec(colsum_dS, 0, N, H * N), ct=vec(x_aft), amax=amax[1:2] if fused16 else None)
             del dS16
         else:
             dSa, dSbT, ldo, colsum_dS, ds_p, dS32 = ops.softmax_quant_bwd(dPq, P, N, H, se_p, hiu, scale, g_p, se_k_hn, True,
@@ -449,12 +467,22 @@ class QKRAttnCoreFn(torch.autograd.Function):
             del dSa, dSbT
         # --- qkx quantizer and the qkx "linear" layer (weight = StatsQ(W_q^T W_k), no bias)
         # d(move_qkx_aft) is analytically zero: the shift adds a term to the logits that is constant along the softmax axis
-        dqkx, ds_k, dkb4, _, *sc_k = ops.lsq_bwd(dkhat, qkx, k_b4, se_k, PER_ROW, N, H, lo, hi, g_k, want_aft=False,
-                                                 zero_sum=True, next_scale=(cs_qk, se_x, 1.0, True) if F16 else None)
         dkaft = torch.zeros_like(k_aft)
-        del dkhat
-        dWqk, _, _ = _linear_backward(dqkx, qx, wqkc, (cs_qk, ics_qk), sx2, N, x_aft, dxhat, True, qx_op,
-                                      sc=sc_k[0] if sc_k else None)
+        if fused16:
+            sc_k = ops.scale_from_max(amax[1:2], v1=cs_qk, v2=se_x, product=True)
+            _, ds_k, dkb4, _, a16_k = ops.lsq_bwd(dkhat, qkx, k_b4, se_k, PER_ROW, N, H, lo, hi, g_k, want_aft=False, zero_sum=True,
+                                                  out16=(FMT, cs_qk, se_x, N, sc_k), want_dx=False)
+            del dkhat
+            # colsum(d qkx) = sum over rows of the masked gradient = d(move_qkx_b4) (its zero-sum form differs from the plain
+            # sum by sum_rows d k_hat, which is analytically zero)
+            dWqk, _, _ = _linear_backward_f16(None, qx, wqkc, (cs_qk, ics_qk), sx2, N, x_aft, dxhat, True, qx_op, sc=sc_k,
+                                              a16=a16_k, colsum=dkb4)
+        else:
+            dqkx, ds_k, dkb4, _, *sc_k = ops.lsq_bwd(dkhat, qkx, k_b4, se_k, PER_ROW, N, H, lo, hi, g_k, want_aft=False,
+                                                     zero_sum=True, next_scale=(cs_qk, se_x, 1.0, True) if F16 else None)
+            del dkhat
+            dWqk, _, _ = _linear_backward(dqkx, qx, wqkc, (cs_qk, ics_qk), sx2, N, x_aft, dxhat, True, qx_op,
+                                          sc=sc_k[0] if sc_k else None)
         dwq, dwk = ops.wqk_compose_bwd(dWqk, wq, wk, H)
         # --- shared input quantizer
         dx, ds_x, dxb4, dxaft = ops.lsq_bwd(dxhat, xc.view(M, C), x_b4, se_x, PER_ROW, N, 1, lo, hi, g_x)

@@ -113,6 +113,57 @@ def test_qattention_qkreparam(Q, bits, cga):
               load_golden(f"qattention_qkr_w{bits}a{bits}"))
 
 
+def test_qattention_qkreparam_fused_fp16_operands(Q):
+    """C = 128 (a multiple of the 128-column streaming group): the backward takes the fused route of the fp16 mode: GEMM
+    epilogues track max |d v_hat| / |d k_hat|, the LSQ backward passes write the fp16 GEMM operands directly (no fp32
+    d v_out / d qkx, no ofq_grad_prep). Checked against the CPU oracle (autograd of the reference op sequence) on the same
+    parameters, and against the unfused route."""
+    from oracle import ofq_oracle as O
+    from ofq_b200.host.deit import Attention
+    from ofq_b200.quantization import functional as Fn
+    torch.manual_seed(31)
+    B, N, C, H, bits = 3, 40, 128, 2, 2
+    mod = Q.QAttention_qkreparam(Attention(C, H, qkv_bias=True), weight_bits=bits, input_bits=bits, pretrained_initialized=True)
+    with torch.no_grad():
+        for n, p in mod.named_parameters():
+            if n.endswith(".bias") and p.dim() == 1:
+                p.copy_(torch.randn(p.shape) * 0.02)
+    mod = mod.cuda().train()
+    x0 = torch.randn(B, N, C)
+    go = torch.randn(B, N, C)
+    with torch.no_grad():
+        mod(x0.cuda())                                   # creates the LSQ step sizes
+    grads = {}
+    for fused in (True, False):
+        Fn.FUSED16 = fused
+        try:
+            mod.zero_grad()
+            x = x0.cuda().requires_grad_(True)
+            y, _ = mod(x)
+            y.backward(go.cuda())
+        finally:
+            Fn.FUSED16 = True
+        grads[fused] = {n: p.grad.detach().cpu().clone() for n, p in mod.named_parameters() if p.grad is not None}
+        grads[fused]["x"] = x.grad.detach().cpu().clone()
+        grads[fused]["y"] = y.detach().cpu()
+    # oracle on the same parameters
+    P = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point()) for k, v in mod.state_dict().items()}
+    xo = x0.clone().requires_grad_(True)
+    yo = O.qattention_qkr(xo, P, "", H, bits, bits)
+    yo.backward(go)
+    assert rel_err(grads[True]["y"], yo.detach()) < OUT_TOL
+    gmax = max(P[n].grad.abs().max().item() for n in grads[True] if n in P and P[n].grad is not None)
+    for n, g in grads[True].items():
+        if n == "y":
+            continue
+        ref = xo.grad if n == "x" else P[n].grad
+        if n.endswith(ANALYTIC_ZERO):
+            assert g.abs().max().item() <= 1e-5 * gmax, n
+            continue
+        assert rel_err(g, ref) < GRAD_TOL or (g - ref).abs().max().item() <= 1e-5 * gmax, f"{n}: {rel_err(g, ref):.2e}"
+        assert rel_err(g, grads[False][n]) < GRAD_TOL or (g - grads[False][n]).abs().max().item() <= 1e-5 * gmax, n
+
+
 def test_unknown_quant_method_raises(Q):
     with pytest.raises(ValueError, match="Unknown quant_method"):
         Q.QLinear(m=nn.Linear(8, 8), weight_quant_method="lsq")
