@@ -171,6 +171,12 @@ OFQ_API int ofq_scale_from_max(const float* amax, int n, const float* v1, int n1
                                int product, float* out4, void* stream);
 OFQ_API int ofq_lsq_bwd_finalize(const float* workspace, long long rows, int cols, int scale_mode, int period,
                                  int nseg, float g, float* d_s, float* d_b4, float* d_aft, int zero_sum, void* stream);
+/* Same, plus dx_colsum[c] = sum over rows of the dx that ofq_lsq_bwd_ex produced with a fused 16-bit operand (per-row scale
+ * mode only; with a fused activation this differs from d_b4 by the activation derivative): colsum(dY) of the next linear
+ * layer's backward (its bias gradient and the rank-1 shift term of its dW). */
+OFQ_API int ofq_lsq_bwd_finalize_colsum(const float* workspace, long long rows, int cols, int scale_mode, int period,
+                                        int nseg, float g, float* d_s, float* d_b4, float* d_aft, int zero_sum,
+                                        float* dx_colsum, void* stream);
 /* ofq_lsq_bwd_finalize and ofq_lsq_bwd_scale (below) in ONE launch: the reductions of the partial sums and the fp16
  * range scales out4 of the next consumer of dx (autograd of lsq.py:571-602 feeding the dX / dW GEMMs of qlinear.py:69). */
 OFQ_API int ofq_lsq_bwd_finalize_scale(const float* workspace, long long rows, int cols, int scale_mode, int period,

@@ -53,6 +53,7 @@ SIGNATURES = {
     "ofq_lsq_bwd_act": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p, _p]),
     "ofq_lsq_bwd": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _i, _i, _i, _i, _i, _p, _ll, _p, _p]),
     "ofq_lsq_bwd_finalize": (_i, [_p, _ll, _i, _i, _i, _i, _f, _p, _p, _p, _i, _p]),
+    "ofq_lsq_bwd_finalize_colsum": (_i, [_p, _ll, _i, _i, _i, _i, _f, _p, _p, _p, _i, _p, _p]),
     "ofq_lsq_bwd_finalize_scale": (_i, [_p, _ll, _i, _i, _i, _i, _f, _p, _p, _p, _i, _p, _i, _p, _i, _f, _i, _p, _p]),
     "ofq_lsq_bwd_scale": (_i, [_p, _ll, _i, _i, _p, _i, _p, _i, _f, _i, _p, _p]),
     "ofq_grad_prep": (_i, [_p, _i, _i, _i, _ll, _ll, _p, _p, _i, _i, _p, _ll, _p, _i, _p, _p, _i, _p, _i, _p, _i, _p]),

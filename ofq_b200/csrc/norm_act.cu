@@ -84,6 +84,11 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
         for (long long r = r0 + warp; r < r1; r += 8) {
             float4 d[4], v[4];
             const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+            if (res && (lane & 7) == 0) {       // the residual gradient is consumed after the row reductions: start it now
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                    if (ok[p]) asm volatile("prefetch.global.L2 [%0];" ::"l"(res + r * cols + (p * 32 + lane) * 4));
+            }
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 d[p] = v[p] = make_float4(0.f, 0.f, 0.f, 0.f);

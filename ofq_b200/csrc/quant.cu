@@ -467,7 +467,7 @@ struct Out16 {
 };
 
 template <int MODE, int ACT, bool OUT16>
-__global__ void __launch_bounds__(256, OUT16 ? 3 : 4)
+__global__ void __launch_bounds__(256, 4)
 lsq_bwd_stream_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
                       uint32_t rows, int cols, const float* __restrict__ b4, const float* __restrict__ s_eff,
                       uint32_t period, int nseg, int seg_len, float qlo, float qhi,
@@ -503,6 +503,7 @@ lsq_bwd_stream_kernel(const float* __restrict__ dy, long long lddy, const float*
     if (OUT16) {
         if (act && o16.cs) c16 = __ldg(reinterpret_cast<const float4*>(o16.cs + col));
         sc16 = o16.scale4 ? __ldg(o16.scale4) : 1.f;
+        c16.x *= sc16; c16.y *= sc16; c16.z *= sc16; c16.w *= sc16;      // power-of-two scale: exact
         n16 = rl % o16.period;
         dn16 = dr % o16.period;
     }
@@ -555,11 +556,16 @@ lsq_bwd_stream_kernel(const float* __restrict__ dy, long long lddy, const float*
                 ab4[e] += o[e];
                 if (ACT == OFQ_ACT_GELU) o[e] *= dact;                              // dx is the gradient w.r.t. the pre-activation
                 tmax = fmaxf(tmax, fabsf(o[e]));
-                if (MODE == OFQ_SCALE_PER_ROW) part += t; else as[e] += t;
+                if (MODE == OFQ_SCALE_PER_ROW) {
+                    part += t;
+                    if (OUT16) as[e] += o[e];      // third column vector (unused by per-row scales): colsum of the final dx
+                } else {
+                    as[e] += t;
+                }
             }
             if (act && dx) *reinterpret_cast<float4*>(dx + (long long)r * lddx + col) = make_float4(o[0], o[1], o[2], o[3]);
             if (OUT16 && act) {
-                const float sr = sc16 * r16[u];
+                const float sr = r16[u];
                 *reinterpret_cast<uint2*>(o16.ptr + (long long)r * o16.ld + col) =
                     make_uint2(pack_rn16(o[0] * c16.x * sr, o[1] * c16.y * sr, o16.f16 != 0),
                                pack_rn16(o[2] * c16.z * sr, o[3] * c16.w * sr, o16.f16 != 0));
@@ -599,7 +605,7 @@ lsq_bwd_stream_kernel(const float* __restrict__ dy, long long lddy, const float*
 __device__ __forceinline__ void
 lsq_bwd_finalize_cols(const float* __restrict__ colpart, int cols, long long nblk, int scale_mode, float g,
                       float* __restrict__ d_s, float* __restrict__ d_b4, float* __restrict__ d_aft, int zero_sum,
-                      int bx, int vecid) {                // vecid 0: aft, 1: b4, 2: per-column scale
+                      float* __restrict__ dx_colsum, int bx, int vecid) {   // vecid 0: aft, 1: b4, 2: per-column scale / colsum(dx)
     __shared__ float red[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int col = bx * 32 + tx;
@@ -620,7 +626,8 @@ lsq_bwd_finalize_cols(const float* __restrict__ colpart, int cols, long long nbl
         for (int k = 0; k < 8; ++k) s += red[k][tx];
         if (vecid == 0) { if (d_aft) d_aft[col] = s; }
         else if (vecid == 1) { if (d_b4) d_b4[col] = s; }
-        else if (d_s && scale_mode == OFQ_SCALE_PER_COL) d_s[col] = g * s;
+        else if (scale_mode == OFQ_SCALE_PER_COL) { if (d_s) d_s[col] = g * s; }
+        else if (dx_colsum) dx_colsum[col] = s;
     }
 }
 
@@ -665,7 +672,7 @@ lsq_bwd_finalize_rows(const float* __restrict__ rowpart, long long total, long l
 // requested) turns the block maxima into the fp16 range scales of the next GEMM operand.
 struct FinalizeArgs {
     const float* colpart; int cols; long long nslots; int scale_mode; float g;
-    float* d_s; float* d_b4; float* d_aft; int zero_sum;
+    float* d_s; float* d_b4; float* d_aft; int zero_sum; float* dx_colsum;
     const float* rowpart; long long total; long long nscale;
     const float* blockmax; int nblk; const float* v1; int n1; const float* v2; int n2; float mult; int product; float* out4;
     int ncx, ncb, nrb;
@@ -674,7 +681,7 @@ __global__ void __launch_bounds__(256)
 lsq_bwd_finalize_kernel(const FinalizeArgs a) {
     const int b = blockIdx.x;
     if (b < a.ncb)
-        lsq_bwd_finalize_cols(a.colpart, a.cols, a.nslots, a.scale_mode, a.g, a.d_s, a.d_b4, a.d_aft, a.zero_sum, b % a.ncx, b / a.ncx);
+        lsq_bwd_finalize_cols(a.colpart, a.cols, a.nslots, a.scale_mode, a.g, a.d_s, a.d_b4, a.d_aft, a.zero_sum, a.dx_colsum, b % a.ncx, b / a.ncx);
     else if (b < a.ncb + a.nrb)
         lsq_bwd_finalize_rows(a.rowpart, a.total, a.nscale, a.g, a.d_s, b - a.ncb);
     else
@@ -1337,7 +1344,7 @@ extern "C" int ofq_lsq_bwd_ex(const float* dy, long long lddy, const float* x, l
 }
 
 static int lsq_bwd_finalize_impl(const float* workspace, long long rows, int cols, int scale_mode, int period, int nseg,
-                                 float g, float* d_s, float* d_b4, float* d_aft, int zero_sum, const float* v1, int n1,
+                                 float g, float* d_s, float* d_b4, float* d_aft, int zero_sum, float* dx_colsum, const float* v1, int n1,
                                  const float* v2, int n2, float mult, int product, float* out4, void* stream) {
     OFQ_REQUIRE(workspace && rows > 0 && cols > 0, "ofq_lsq_bwd_finalize: bad argument");
     OFQ_CHECK_ARCH();
@@ -1345,7 +1352,7 @@ static int lsq_bwd_finalize_impl(const float* workspace, long long rows, int col
     const LsqBwdWs wsl = lsq_bwd_ws(rows, cols, nseg);
     FinalizeArgs a;
     a.colpart = workspace + wsl.rowpart_n; a.cols = cols; a.nslots = wsl.colslots; a.scale_mode = scale_mode; a.g = g;
-    a.d_s = d_s; a.d_b4 = d_b4; a.d_aft = d_aft; a.zero_sum = zero_sum;
+    a.d_s = d_s; a.d_b4 = d_b4; a.d_aft = d_aft; a.zero_sum = zero_sum; a.dx_colsum = dx_colsum;
     a.rowpart = workspace; a.total = wsl.rowpart_used;
     // every partial whose index is congruent to i modulo nscale belongs to scale i (rows is a multiple of period)
     a.nscale = (long long)(period < rows ? period : rows) * nseg;
@@ -1361,7 +1368,15 @@ static int lsq_bwd_finalize_impl(const float* workspace, long long rows, int col
 
 extern "C" int ofq_lsq_bwd_finalize(const float* workspace, long long rows, int cols, int scale_mode, int period,
                                     int nseg, float g, float* d_s, float* d_b4, float* d_aft, int zero_sum, void* stream) {
-    return lsq_bwd_finalize_impl(workspace, rows, cols, scale_mode, period, nseg, g, d_s, d_b4, d_aft, zero_sum, nullptr, 0,
+    return lsq_bwd_finalize_impl(workspace, rows, cols, scale_mode, period, nseg, g, d_s, d_b4, d_aft, zero_sum, nullptr, nullptr, 0,
+                                 nullptr, 0, 1.f, 0, nullptr, stream);
+}
+
+extern "C" int ofq_lsq_bwd_finalize_colsum(const float* workspace, long long rows, int cols, int scale_mode, int period,
+                                           int nseg, float g, float* d_s, float* d_b4, float* d_aft, int zero_sum,
+                                           float* dx_colsum, void* stream) {
+    OFQ_REQUIRE(!dx_colsum || scale_mode == OFQ_SCALE_PER_ROW, "ofq_lsq_bwd_finalize_colsum: per-row scale mode only");
+    return lsq_bwd_finalize_impl(workspace, rows, cols, scale_mode, period, nseg, g, d_s, d_b4, d_aft, zero_sum, dx_colsum, nullptr, 0,
                                  nullptr, 0, 1.f, 0, nullptr, stream);
 }
 
@@ -1370,7 +1385,7 @@ extern "C" int ofq_lsq_bwd_finalize_scale(const float* workspace, long long rows
                                           const float* v1, int n1, const float* v2, int n2, float mult, int product,
                                           float* out4, void* stream) {
     OFQ_REQUIRE(out4, "ofq_lsq_bwd_finalize_scale: out4 is required");
-    return lsq_bwd_finalize_impl(workspace, rows, cols, scale_mode, period, nseg, g, d_s, d_b4, d_aft, zero_sum, v1, n1, v2, n2,
+    return lsq_bwd_finalize_impl(workspace, rows, cols, scale_mode, period, nseg, g, d_s, d_b4, d_aft, zero_sum, nullptr, v1, n1, v2, n2,
                                  mult, product, out4, stream);
 }
 

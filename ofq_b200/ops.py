@@ -152,13 +152,13 @@ def lsq_quant(x2d: torch.Tensor, b4: torch.Tensor, s_eff: torch.Tensor, mode: in
 
 def lsq_bwd(dy2d: torch.Tensor, x2d: torch.Tensor, b4: torch.Tensor, s_eff: torch.Tensor, mode: int, period: int,
             nseg: int, qlo: int, qhi: int, g: float, want_ds: bool = True, want_aft: bool = True, next_scale=None,
-            zero_sum: bool = False, act: int = ACT_NONE, out16=None, want_dx: bool = True):
+            zero_sum: bool = False, act: int = ACT_NONE, out16=None, want_dx: bool = True, want_colsum: bool = False):
     """Returns (dx [rows, cols], d_s, d_b4 [cols], d_aft [cols] | None).  next_scale = (v1, v2, mult, product): additionally
     returns the fp16 range scales (absmax_scale layout) of dx*v1[c] / dx*v2[r] for the GEMM operand made from dx,
     derived from max|dx| at no extra pass over dx.  act: the quantizer saw act(x2d) (lsq_quant(act=...)); dx is then the
     gradient w.r.t. the pre-activation x2d.  out16 = (fmt, cs [cols], rs, rs_period, scale4): the same pass also writes the
     16-bit GEMM operand rn16(dx * cs[c] * rs[r % rs_period] * scale4[0]) (appended to the result); with want_dx=False the
-    fp32 dx is not written at all (returned as None)."""
+    fp32 dx is not written at all (returned as None); want_colsum (per-row scale mode, with out16) appends colsum(dx)."""
     _cuda(dy2d, x2d)
     assert dy2d.dim() == 2 and dy2d.stride(1) == 1 and x2d.stride(1) == 1
     rows, cols = dy2d.shape
@@ -182,10 +182,11 @@ def lsq_bwd(dy2d: torch.Tensor, x2d: torch.Tensor, b4: torch.Tensor, s_eff: torc
     d_b4 = torch.empty(cols, dtype=torch.float32, device=dy2d.device)
     d_aft = torch.empty(cols, dtype=torch.float32, device=dy2d.device) if want_aft else None
     if next_scale is None:
-        _call("lsq_bwd_finalize", 1, 4.0 * ws.numel(), 0, lib.ofq_lsq_bwd_finalize, ws.data_ptr(), rows, cols, mode, period,
-              nseg, float(g), _ptr(d_s), d_b4.data_ptr(), _ptr(d_aft), int(zero_sum), _st())
+        csum = torch.empty(cols, dtype=torch.float32, device=dy2d.device) if (want_colsum and out16 is not None) else None
+        _call("lsq_bwd_finalize", 1, 4.0 * ws.numel(), 0, lib.ofq_lsq_bwd_finalize_colsum, ws.data_ptr(), rows, cols, mode, period,
+              nseg, float(g), _ptr(d_s), d_b4.data_ptr(), _ptr(d_aft), int(zero_sum), _ptr(csum), _st())
         if out16 is not None:
-            return dx, d_s, d_b4, d_aft, o16
+            return (dx, d_s, d_b4, d_aft, o16, csum) if csum is not None else (dx, d_s, d_b4, d_aft, o16)
         return dx, d_s, d_b4, d_aft
     v1, v2, mult, product = next_scale
     sc = torch.empty(4, dtype=torch.float32, device=dy2d.device)

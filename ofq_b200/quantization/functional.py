@@ -67,7 +67,7 @@ def _scalar(sc):
 
 
 def _linear_backward_f16(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulate_dx: bool, qx16=None, sc=None, a16=None,
-                         colsum=None):
+                         colsum=None, amax_dx=None):
     """fp16 backward of out = x_hat @ W_hat^T (+bias) with ONE range-scaled copy of the gradient,
     A16[t,n] = fp16(dY[t,n] * colscale[n] * se_x[t] * sc), read K-major by the dX GEMM and MN-major by the dW GEMM; the
     code operands stay exact and un-transposed (MN-major B), the folded scale vectors are undone per output row:
@@ -86,7 +86,7 @@ def _linear_backward_f16(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulat
         a16, colsum = prep["rm"], prep["colsum"]
     wc16 = ops.codes_to_bf16(wc, 1, Nout, K, K, 0, False, FMT)           # [1, Nout, K]
     ops.gemm(GEMM_BWD, a16, (Nout, 0, 0, 0), wc16, (K, 0, 0, 0), dxhat, (K, 0, 0), M, K, Nout, b_mn=True,
-             accumulate=accumulate_dx, rs=vec(se2[1], period), cs=_scalar(sc))
+             accumulate=accumulate_dx, rs=vec(se2[1], period), cs=_scalar(sc), amax=amax_dx)
     if qx16 is None:
         qx16 = ops.codes_to_bf16(qx, 1, M, K, K, 0, False, FMT)          # [1, M, K]
     dW = torch.zeros((Nout, K), dtype=torch.float32, device=a16.device)
@@ -97,11 +97,11 @@ def _linear_backward_f16(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulat
     return dW, colsum, qx16
 
 
-def _linear_backward(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulate_dx: bool, qxT_all=None, sc=None):
+def _linear_backward(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulate_dx: bool, qxT_all=None, sc=None, **f16kw):
     """Backward of out = x_hat @ W_hat^T (+bias):  dX_hat (+)= dY W_hat,  dW = dY^T x_hat,  dbias = colsum(dY).
     x_hat = qx * se_x[row % period] + x_aft,  W_hat = wc * colscale[row].  Returns (dW, dbias, shared code operand)."""
     if F16:
-        return _linear_backward_f16(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulate_dx, qxT_all, sc)
+        return _linear_backward_f16(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulate_dx, qxT_all, sc, **f16kw)
     colscale, se_x = cs2[0], se2[0]
     M, Nout = dY2d.shape
     K = qx.shape[1]
@@ -130,10 +130,13 @@ class MlpLink:
     core -> proj): the producer's forward leaves the two scale vectors folded into its gradient operand here (cs per
     column, se per row), the backward of the consumer (which runs first) turns the max |d producer_out| its LSQ pass sees
     anyway into the fp16 range scale of that operand (`sc`), and the producer's backward then skips its absmax pass."""
-    __slots__ = ("cs", "se", "sc")
+    __slots__ = ("cs", "se", "sc", "fuse", "a16", "colsum")
 
-    def __init__(self):
-        self.cs = self.se = self.sc = None
+    def __init__(self, fuse: bool = False):
+        # fuse: the consumer's LSQ backward writes the producer's fp16 gradient operand (a16) and colsum(dY) itself; the
+        # fp32 gradient tensor handed back through autograd is then an uninitialised placeholder that the producer ignores
+        self.cs = self.se = self.sc = self.a16 = self.colsum = None
+        self.fuse = fuse
 
 
 class QLinearFn(torch.autograd.Function):
@@ -180,8 +183,29 @@ class QLinearFn(torch.autograd.Function):
         M = x2d.shape[0]
         dY2d = dY.contiguous().view(M, -1)
         dxhat = torch.empty((M, K), dtype=torch.float32, device=dY.device)
-        sc = link.sc if (link is not None and role == 1) else None
-        dW, dbias, _ = _linear_backward(dY2d, qx, wc, (colscale, inv_cs), se2, P, aft, dxhat, False, qx16, sc=sc)
+        if link is not None and role == 1 and link.a16 is not None:
+            # fc1 of a fused QMLP: fc2's backward already wrote this layer's fp16 gradient operand and colsum(dY); the dY
+            # tensor that arrived through autograd is a placeholder
+            dW, dbias, _ = _linear_backward_f16(None, qx, wc, (colscale, inv_cs), se2, P, aft, dxhat, False, qx16, sc=link.sc,
+                                                a16=link.a16, colsum=link.colsum)
+            link.a16 = link.colsum = None
+        else:
+            sc = link.sc if (link is not None and role == 1) else None
+            fuse_next = (F16 and FUSED16 and link is not None and role == 2 and link.fuse and link.cs is not None
+                         and link.cs.shape[0] == K and K % 4 == 0 and M % link.se.numel() == 0)
+            amax = torch.zeros(1, dtype=torch.float32, device=dY.device) if fuse_next else None
+            dW, dbias, _ = _linear_backward(dY2d, qx, wc, (colscale, inv_cs), se2, P, aft, dxhat, False, qx16, sc=sc,
+                                            **({"amax_dx": amax} if fuse_next else {}))
+            if fuse_next:
+                # the producer (fc1) only needs fp16(dx * colscale1[c] * se1[r] * sc) and colsum(dx): written by this pass
+                # |dx| <= |dxhat| * max GELU' (1.13)
+                sc1 = ops.scale_from_max(amax, v1=link.cs, v2=link.se, mult=1.13 if act == ACT_GELU else 1.0, product=True)
+                _, ds, db4, daft, a16, csum = ops.lsq_bwd(dxhat, x2d, b4, se2[0], PER_ROW, P, 1, lo, hi, g, act=act,
+                                                          out16=(FMT, link.cs, link.se, link.se.numel(), sc1), want_dx=False,
+                                                          want_colsum=True)
+                link.sc, link.a16, link.colsum = sc1, a16, csum
+                dx = torch.empty_like(xc)         # placeholder: never read (see MlpLink.fuse)
+                return dx, dW, (dbias if has_bias else None), db4, daft, ds, None, None, None, None, None, None
         nxt = None
         if F16 and link is not None and role == 2 and link.cs is not None and link.cs.shape[0] == K:
             nxt = (link.cs, link.se, 1.0, True)
@@ -189,42 +213,6 @@ class QLinearFn(torch.autograd.Function):
         if nxt is not None:
             link.sc = scn[0]
         return dx.view_as(xc), dW, (dbias if has_bias else None), db4, daft, ds, None, None, None, None, None, None
-
-
-# ====================================================================================== standalone LSQ
-class LsqFn(torch.autograd.Function):
-    """LsqQuantizer / LsqQuantizer4v forward as a module of its own (lsq.py:571-602, 757-790)."""
-
-    @staticmethod
-    def forward(ctx, x, s, bit: int, all_positive: bool, per_col: bool):
-        K = x.shape[-1]
-        xc = x.contiguous()
-        x2d = xc.view(-1, K)
-        lo, hi = levels(bit, all_positive)
-        if per_col:
-            g = grad_scale_factor(hi, x.numel() // K)
-            mode, period = PER_COL, 1
-        else:
-            period = x.shape[-2]
-            g = grad_scale_factor(hi, x.numel() // period)
-            mode = PER_ROW
-        se = ops.lsq_effective_scale(s, g)
-        zero = torch.zeros(K, dtype=torch.float32, device=x.device)
-        codes = ops.lsq_quant(x2d, zero, se, mode, period, 1, lo, hi)
-        # dequantise: q * s_eff  (exact product of a small integer and the scale, as the reference computes it)
-        scale = se.view(1, -1) if per_col else se.repeat(x2d.shape[0] // period).view(-1, 1)
-        out = (codes.to(torch.float32) * scale).view_as(xc)
-        ctx.save_for_backward(xc, se, zero)
-        ctx.cfg = (mode, period, lo, hi, g)
-        return out
-
-    @staticmethod
-    def backward(ctx, dy):
-        xc, se, zero = ctx.saved_tensors
-        mode, period, lo, hi, g = ctx.cfg
-        K = xc.shape[-1]
-        dx, ds, _, _ = ops.lsq_bwd(dy.contiguous().view(-1, K), xc.view(-1, K), zero, se, mode, period, 1, lo, hi, g)
-        return dx.view_as(xc), ds, None, None, None
 
 
 class ImgLsqFn(torch.autograd.Function):

@@ -111,7 +111,7 @@ def qmlp_forward(mlp, x):
     if not fused:
         x = mlp.drop1(mlp.act(mlp.fc1(x)))
         return mlp.drop2(mlp.fc2(x))
-    link = MlpLink()
+    link = MlpLink(fuse=True)      # h feeds fc2 only: its gradient travels as fc1's fp16 GEMM operand, not as an fp32 tensor
     h = mlp.fc1(x, ACT_NONE, link, 1)
     return mlp.drop2(mlp.fc2(h, ACT_GELU, link, 2))
 
