@@ -215,6 +215,42 @@ class QLinearFn(torch.autograd.Function):
         return dx.view_as(xc), dW, (dbias if has_bias else None), db4, daft, ds, None, None, None, None, None, None
 
 
+# ====================================================================================== standalone LSQ
+class LsqFn(torch.autograd.Function):
+    """LsqQuantizer / LsqQuantizer4v forward as a module of its own (lsq.py:571-602, 757-790)."""
+
+    @staticmethod
+    def forward(ctx, x, s, bit: int, all_positive: bool, per_col: bool):
+        K = x.shape[-1]
+        xc = x.contiguous()
+        x2d = xc.view(-1, K)
+        lo, hi = levels(bit, all_positive)
+        if per_col:
+            g = grad_scale_factor(hi, x.numel() // K)
+            mode, period = PER_COL, 1
+        else:
+            period = x.shape[-2]
+            g = grad_scale_factor(hi, x.numel() // period)
+            mode = PER_ROW
+        se = ops.lsq_effective_scale(s, g)
+        zero = torch.zeros(K, dtype=torch.float32, device=x.device)
+        codes = ops.lsq_quant(x2d, zero, se, mode, period, 1, lo, hi)
+        # dequantise: q * s_eff  (exact product of a small integer and the scale, as the reference computes it)
+        scale = se.view(1, -1) if per_col else se.repeat(x2d.shape[0] // period).view(-1, 1)
+        out = (codes.to(torch.float32) * scale).view_as(xc)
+        ctx.save_for_backward(xc, se, zero)
+        ctx.cfg = (mode, period, lo, hi, g)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, se, zero = ctx.saved_tensors
+        mode, period, lo, hi, g = ctx.cfg
+        K = xc.shape[-1]
+        dx, ds, _, _ = ops.lsq_bwd(dy.contiguous().view(-1, K), xc.view(-1, K), zero, se, mode, period, 1, lo, hi, g)
+        return dx.view_as(xc), ds, None, None, None
+
+
 class ImgLsqFn(torch.autograd.Function):
     """move_aft(LsqQuantizer4img(move_b4(img))) of the 8-bit patch-embedding input (qlinear.py:138-177, lsq.py:306-382,
     qbias.py:15-23) on the [B*Cin, H*W] view of the image: the per-input-channel step size is a per-row scale with period
