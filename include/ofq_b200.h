@@ -283,6 +283,27 @@ OFQ_API int ofq_wqk_compose_bwd(const float* dwqk, const float* wq, const float*
                                 float* dwq, float* dwk, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Step prologue: the weight-side work of a whole model in three launches. The weights, shifts and LSQ step sizes only
+ * change at the optimizer step, so every StatsQ code tensor (statsq.py:133-150), every W_qk product (attention.py:190-194)
+ * and every effective LSQ step size (lsq.py:593) can be produced once per forward by multi-tensor kernels instead of one
+ * small launch per layer (157 launches per DeiT-S step). Job tables are device arrays of these records; a CTA finds its
+ * job by binary search over first_block (cumulative CTA count: ceil(rows / 8) per StatsQ job, ceil(n / 256) per scale job).
+ */
+typedef struct {
+    const float* w; const float* aft; const float* bias;       /* aft / bias may be NULL (see ofq_statsq_codes) */
+    int8_t* codes; float* colscale; float* inv_colscale; float* colterm;   /* inv_colscale / colterm may be NULL */
+    long long ldw; int rows, cols; float n_levels; int first_block;        /* n_levels = 2^(bits-1); codes pitch = cols */
+} ofq_statsq_job_t;
+typedef struct {
+    const float* alpha; float* out; float* out_recip;          /* out_recip may be NULL */
+    int n; float g; int first_block; int pad;
+} ofq_scale_job_t;
+typedef struct { const float* wq; const float* wk; float* wqk; } ofq_wqk_job_t;
+OFQ_API int ofq_statsq_codes_multi(const void* table, int n_jobs, int total_blocks, void* stream);
+OFQ_API int ofq_lsq_effective_scale_multi(const void* table, int n_jobs, int total_blocks, void* stream);
+OFQ_API int ofq_wqk_compose_multi(const void* table, int n_jobs, int H, int hd, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K7  CGA: freeze mask (cga.py:450-469) and the masked AdamW step (cga.py:953-1013 + torch.optim.AdamW).
  * ofq_cga_mask writes 1 for frozen, 0 for trainable (the reference's `freeze_idx`).
  * ofq_cga_adamw updates p, exp_avg, exp_avg_sq in place in ONE pass: frozen elements see a zero gradient

@@ -44,6 +44,9 @@ SIGNATURES = {
     "ofq_gemm_ex": (_i, [_i, C.POINTER(Operand), C.POINTER(Operand), C.POINTER(GemmOut), _i, _i, _i, _i, _i, _i, _i,
                          C.POINTER(Vec), C.POINTER(Vec), C.POINTER(Vec), C.POINTER(Vec), _p, _p]),
     "ofq_statsq_codes": (_i, [_p, _i, _i, _ll, _i, _p, _ll, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ofq_statsq_codes_multi": (_i, [_p, _i, _i, _p]),
+    "ofq_lsq_effective_scale_multi": (_i, [_p, _i, _i, _p]),
+    "ofq_wqk_compose_multi": (_i, [_p, _i, _i, _i, _i, _p]),
     "ofq_lsq_effective_scale": (_i, [_p, _i, _f, _p, _p, _p]),
     "ofq_lsq_quant": (_i, [_p, _ll, _i, _ll, _p, _p, _i, _i, _i, _i, _i, _p, _ll, _p]),
     "ofq_lsq_bwd_workspace": (_ll, [_ll, _i, _i]),

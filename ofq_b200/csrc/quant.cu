@@ -33,14 +33,11 @@ __device__ __forceinline__ void pow2_scale_pair(float bound, float* sc, float* i
 
 // ------------------------------------------------------------------------------------------- K1 StatsQ
 // One warp per weight row. statsq.py:137-147.
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-statsq_codes_kernel(const float* __restrict__ w, int rows, int cols, long long ldw, float n_levels,
-                    int8_t* __restrict__ codes, long long ldq, float* __restrict__ colscale,
-                    float* __restrict__ sf_out, const float* __restrict__ aft, const float* __restrict__ bias,
-                    float* __restrict__ colterm, int* __restrict__ kminmax, float* __restrict__ inv_colscale) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * kWarpsPerBlock + warp;
-    if (row >= rows) return;
+__device__ __forceinline__ void
+statsq_row(const float* __restrict__ w, int row, int cols, long long ldw, float n_levels,
+           int8_t* __restrict__ codes, long long ldq, float* __restrict__ colscale,
+           float* __restrict__ sf_out, const float* __restrict__ aft, const float* __restrict__ bias,
+           float* __restrict__ colterm, int* __restrict__ kminmax, float* __restrict__ inv_colscale, int lane) {
     const float* wr = w + (long long)row * ldw;
     double acc = 0.0;
     for (int c = lane; c < cols; c += 32) acc += (double)fabsf(__ldg(wr + c));
@@ -85,6 +82,47 @@ statsq_codes_kernel(const float* __restrict__ w, int rows, int cols, long long l
     }
 }
 
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+statsq_codes_kernel(const float* __restrict__ w, int rows, int cols, long long ldw, float n_levels,
+                    int8_t* __restrict__ codes, long long ldq, float* __restrict__ colscale,
+                    float* __restrict__ sf_out, const float* __restrict__ aft, const float* __restrict__ bias,
+                    float* __restrict__ colterm, int* __restrict__ kminmax, float* __restrict__ inv_colscale) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kWarpsPerBlock + warp;
+    if (row >= rows) return;
+    statsq_row(w, row, cols, ldw, n_levels, codes, ldq, colscale, sf_out, aft, bias, colterm, kminmax, inv_colscale, lane);
+}
+
+// Multi-tensor variants (one launch for every quantized weight / every LSQ step size of a model): the jobs live in a device
+// table, a CTA finds its job by binary search over first_block. Layouts are part of the C-ABI (include/ofq_b200.h).
+struct StatsqJob {
+    const float* w; const float* aft; const float* bias;
+    int8_t* codes; float* colscale; float* inv_colscale; float* colterm;
+    long long ldw; int rows, cols; float n_levels; int first_block;
+};
+struct ScaleJob {
+    const float* alpha; float* out; float* out_recip;
+    int n; float g; int first_block; int pad;
+};
+template <typename Job>
+__device__ __forceinline__ int find_job(const Job* __restrict__ table, int n_jobs) {
+    int lo = 0, hi = n_jobs - 1;                      // last job whose first_block <= blockIdx.x
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (table[mid].first_block <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+statsq_codes_multi_kernel(const StatsqJob* __restrict__ table, int n_jobs) {
+    const StatsqJob j = table[find_job(table, n_jobs)];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = ((int)blockIdx.x - j.first_block) * kWarpsPerBlock + warp;
+    if (row >= j.rows) return;
+    statsq_row(j.w, row, j.cols, j.ldw, j.n_levels, j.codes, j.cols, j.colscale, nullptr, j.aft, j.bias, j.colterm, nullptr,
+               j.inv_colscale, lane);
+}
+
 // ------------------------------------------------------------------------------------------- LSQ scale
 __global__ void lsq_effective_scale_kernel(const float* __restrict__ alpha, int n, float g,
                                            float* __restrict__ out, float* __restrict__ out_recip) {
@@ -96,6 +134,19 @@ __global__ void lsq_effective_scale_kernel(const float* __restrict__ alpha, int 
     const float se = __fadd_rn(__fsub_rn(ac, ag), ag);
     out[i] = se;
     if (out_recip) out_recip[i] = 1.0f / se;     // epilogue un-scale vector of the backward GEMMs
+}
+
+__global__ void __launch_bounds__(256)
+lsq_effective_scale_multi_kernel(const ScaleJob* __restrict__ table, int n_jobs) {
+    const ScaleJob j = table[find_job(table, n_jobs)];
+    const int i = ((int)blockIdx.x - j.first_block) * 256 + threadIdx.x;
+    if (i >= j.n) return;
+    const float a = j.alpha[i];
+    const float ac = a > 1e-5f ? a : 1e-5f;
+    const float ag = __fmul_rn(ac, j.g);
+    const float se = __fadd_rn(__fsub_rn(ac, ag), ag);
+    j.out[i] = se;
+    if (j.out_recip) j.out_recip[i] = 1.0f / se;
 }
 
 // ------------------------------------------------------------------------------------------- K2 LSQ codes
@@ -1159,6 +1210,24 @@ extern "C" int ofq_statsq_codes(const float* w, int rows, int cols, long long ld
     const int grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
     statsq_codes_kernel<<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
         w, rows, cols, ldw, n, codes, ldq, colscale, sf, aft, bias, colterm, kminmax, inv_colscale);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ofq_statsq_codes_multi(const void* table, int n_jobs, int total_blocks, void* stream) {
+    OFQ_REQUIRE(table && n_jobs > 0 && total_blocks > 0, "ofq_statsq_codes_multi: bad argument");
+    static_assert(sizeof(StatsqJob) == 80, "StatsqJob layout is part of the C-ABI");
+    OFQ_CHECK_ARCH();
+    statsq_codes_multi_kernel<<<total_blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>((const StatsqJob*)table, n_jobs);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ofq_lsq_effective_scale_multi(const void* table, int n_jobs, int total_blocks, void* stream) {
+    OFQ_REQUIRE(table && n_jobs > 0 && total_blocks > 0, "ofq_lsq_effective_scale_multi: bad argument");
+    static_assert(sizeof(ScaleJob) == 40, "ScaleJob layout is part of the C-ABI");
+    OFQ_CHECK_ARCH();
+    lsq_effective_scale_multi_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>((const ScaleJob*)table, n_jobs);
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }

@@ -71,13 +71,73 @@ sgemm_strided_kernel(const SgemmPair pair, int nb, int M, int N, int K) {
     }
 }
 
+// W_qk of every layer in one launch: blockIdx.z = job * H + head, jobs = {wq, wk, wqk} pointer triples in device memory
+struct WqkJob { const float* wq; const float* wk; float* wqk; };
+template <int TM>
+__global__ void __launch_bounds__(256)
+wqk_compose_multi_kernel(const WqkJob* __restrict__ table, int nb, int hd, int C) {
+    constexpr int RM = TM / 16;
+    __shared__ float As[16][TM + 4];
+    __shared__ float Bs[16][64 + 4];
+    const WqkJob job = table[blockIdx.z / nb];
+    // wqk[h][i][j] = sum_d wq[h*hd+d][i] * wk[h*hd+d][j]
+    const SgemmProblem q = {job.wq, C, 1, (long long)hd * C, job.wk, C, 1, (long long)hd * C, job.wqk, C, (long long)C * C};
+    const int M = C, N = C, K = hd;
+    const int b = blockIdx.z % nb;
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * 64;
+    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+    const float* Ab = q.A + b * q.bsA;
+    const float* Bb = q.B + b * q.bsB;
+    const long long sAk = q.sAk, sAm = q.sAm, sBk = q.sBk, sBn = q.sBn;
+    float acc[RM][4] = {};
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        for (int i = t; i < 16 * TM; i += 256) {
+            int kk, mm;
+            if (sAm == 1) { kk = i / TM; mm = i % TM; } else { kk = i & 15; mm = i >> 4; }
+            const int k = k0 + kk, m = m0 + mm;
+            As[kk][mm] = (k < K && m < M) ? __ldg(Ab + k * sAk + m * sAm) : 0.f;
+        }
+        for (int i = t; i < 16 * 64; i += 256) {
+            int kb, nn;
+            if (sBn == 1) { kb = i >> 6; nn = i & 63; } else { kb = i & 15; nn = i >> 4; }
+            const int k2 = k0 + kb, n = n0 + nn;
+            Bs[kb][nn] = (k2 < K && n < N) ? __ldg(Bb + k2 * sBk + n * sBn) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float a[RM], bb[4];
+#pragma unroll
+            for (int i = 0; i < RM; ++i) a[i] = As[kk][ty * RM + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bb[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < RM; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* Cb = q.C + b * q.bsC;
+#pragma unroll
+    for (int i = 0; i < RM; ++i) {
+        const int m = m0 + ty * RM + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < N) Cb[m * q.ldc + n] = acc[i][j];
+        }
+    }
+}
+
 int launch(const SgemmPair& pair, int nprob, int M, int N, int K, int nb, cudaStream_t st) {
     const long long tiles64 = (long long)((N + 63) / 64) * ((M + 63) / 64) * nb * nprob;
     const long long tiles32 = (long long)((N + 63) / 64) * ((M + 31) / 32) * nb * nprob;
     if (tiles64 >= 148) {
         dim3 grid((N + 63) / 64, (M + 63) / 64, nb * nprob);
         sgemm_strided_kernel<64><<<grid, 256, 0, st>>>(pair, nb, M, N, K);
-    } else if (tiles32 >= 128) {   // the backward pair of a DeiT-S layer: 144 CTAs of 32 x 64 (2 x 4 outputs per thread)
+    } else if (false && tiles32 >= 128) {   // measured slower than the 16-row tiles on B200 (67 vs 58 us): kept for reference   // the backward pair of a DeiT-S layer: 144 CTAs of 32 x 64 (2 x 4 outputs per thread)
         dim3 grid((N + 63) / 64, (M + 31) / 32, nb * nprob);
         sgemm_strided_kernel<32><<<grid, 256, 0, st>>>(pair, nb, M, N, K);
     } else {
@@ -109,4 +169,16 @@ extern "C" int ofq_wqk_compose_bwd(const float* dwqk, const float* wq, const flo
     // dwk[h*hd+d][j] = sum_i wq[h*hd+d][i] * dwqk[h][i][j]
     pair.p[1] = {wq, 1, C, (long long)hd * C, dwqk, C, 1, (long long)C * C, dwk, C, (long long)hd * C};
     return launch(pair, 2, hd, C, C, H, (cudaStream_t)stream);
+}
+
+// Every layer's W_qk in one launch. table: device array of n_jobs records {wq, wk, wqk} (three pointers, 24 bytes).
+extern "C" int ofq_wqk_compose_multi(const void* table, int n_jobs, int H, int hd, int C, void* stream) {
+    OFQ_REQUIRE(table && n_jobs > 0 && H > 0 && hd > 0 && C > 0, "ofq_wqk_compose_multi: bad argument");
+    OFQ_REQUIRE((long long)n_jobs * H <= 65535, "ofq_wqk_compose_multi: too many (layer, head) pairs");
+    static_assert(sizeof(WqkJob) == 24, "WqkJob layout is part of the C-ABI");
+    OFQ_CHECK_ARCH();
+    dim3 grid((C + 63) / 64, (C + 63) / 64, n_jobs * H);
+    wqk_compose_multi_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>((const WqkJob*)table, H, hd, C);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
 }

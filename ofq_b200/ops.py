@@ -88,17 +88,27 @@ def gemm(kind: int, a: torch.Tensor, a_strides, b: torch.Tensor, b_strides, out:
 
 # ------------------------------------------------------------------------------------------------ quantizers
 def statsq_codes(w: torch.Tensor, bits: int, aft: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
-                 want_minmax: bool = False, want_inv: bool = False):
-    """StatsQ codes of a 2-D fp32 weight. Returns (codes int8 [R,C], colscale [R], sf [R], colterm [R] | None,
-    kminmax int32[2] | None [, 1/colscale [R] if want_inv])."""
+                 want_minmax: bool = False, want_inv: bool = False, want_sf: bool = False):
+    """StatsQ codes of a 2-D fp32 weight. Returns (codes int8 [R,C], colscale [R], sf [R] | None, colterm [R] | None,
+    kminmax int32[2] | None [, 1/colscale [R] if want_inv]). sf is only guaranteed with want_sf (the step prologue does
+    not produce it)."""
     _cuda(w)
     assert w.dim() == 2 and w.dtype == torch.float32 and w.stride(1) == 1
     R, Cc = w.shape
-    codes = torch.empty((R, Cc), dtype=torch.int8, device=w.device)
-    cs2 = torch.empty((2, R), dtype=torch.float32, device=w.device)
+    from . import prologue
+    pro = prologue.ACTIVE if prologue.ENABLED else None
+    job = None
+    if pro is not None and not want_minmax and not want_sf:
+        job, ready = pro.get_statsq(w, bits, aft, bias)     # persistent outputs; `ready`: already produced by the step prologue
+        codes, cs2, colterm = job.out["codes"], job.out["cs2"], job.out["colterm"]
+        if ready:
+            return (codes, cs2[0], None, colterm, None, cs2[1]) if want_inv else (codes, cs2[0], None, colterm, None)
+    else:
+        codes = torch.empty((R, Cc), dtype=torch.int8, device=w.device)
+        cs2 = torch.empty((2, R), dtype=torch.float32, device=w.device)
+        colterm = torch.empty(R, dtype=torch.float32, device=w.device) if (aft is not None or bias is not None) else None
     colscale = cs2[0]
     sf = torch.empty(R, dtype=torch.float32, device=w.device)
-    colterm = torch.empty(R, dtype=torch.float32, device=w.device) if (aft is not None or bias is not None) else None
     mm = None
     if want_minmax:
         mm = torch.tensor([2 ** 31 - 1, -2 ** 31], dtype=torch.int32, device=w.device)
@@ -116,6 +126,14 @@ def lsq_effective_scale(alpha: torch.Tensor, g: float, recip: bool = False):
     """Effective LSQ step sizes; recip=True returns [2, n]: row 0 = scales, row 1 = their reciprocals."""
     _cuda(alpha)
     a = alpha.detach().contiguous()
+    from . import prologue
+    pro = prologue.ACTIVE if prologue.ENABLED else None
+    if pro is not None and a.dtype == torch.float32:
+        job, ready = pro.get_scale(a, g, recip)
+        if not ready:
+            _call("lsq_scale", 1, (12.0 if recip else 8.0) * a.numel(), 0, _lib.load().ofq_lsq_effective_scale, a.data_ptr(),
+                  a.numel(), float(g), (job.out[0] if recip else job.out).data_ptr(), job.out[1].data_ptr() if recip else None, _st())
+        return job.out
     if recip:
         out = torch.empty((2,) + tuple(a.shape), dtype=a.dtype, device=a.device)
         _call("lsq_scale", 1, 12.0 * a.numel(), 0, _lib.load().ofq_lsq_effective_scale, a.data_ptr(), a.numel(), float(g),
@@ -333,7 +351,15 @@ def wqk_compose(wq: torch.Tensor, wk: torch.Tensor, H: int) -> torch.Tensor:
     _cuda(wq, wk)
     Cc = wq.shape[1]
     hd = wq.shape[0] // H
-    out = torch.empty((H * Cc, Cc), dtype=torch.float32, device=wq.device)
+    from . import prologue
+    pro = prologue.ACTIVE if prologue.ENABLED else None
+    if pro is not None and wq.is_contiguous() and wk.is_contiguous():
+        job, ready = pro.get_wqk(wq, wk, H)
+        if ready:
+            return job.out
+        out = job.out
+    else:
+        out = torch.empty((H * Cc, Cc), dtype=torch.float32, device=wq.device)
     _call("wqk_compose", 1, 4.0 * (2 * H * hd * Cc + H * Cc * Cc), 2.0 * H * hd * Cc * Cc, _lib.load().ofq_wqk_compose,
           wq.data_ptr(), wk.data_ptr(), H, hd, Cc, out.data_ptr(), _st())
     return out

@@ -294,7 +294,8 @@ def _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C):
     return out
 
 
-def _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=None, qp16=None, sc=None, amax_dv=None):
+def _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=None, qp16=None, sc=None, amax_dv=None,
+                     amax_dp=None):
     """fp16 backward of P_hat V_hat with ONE copy A16[b,n,c] = fp16(dO * se_v[c] * se_p[n] * sc):
         dP_hat[z,n,d]  = 1/(se_p[n] sc) * sum_j A16[b,n,hj] qv[b,d,hj] + sum_j dO[b,n,hj] v_aft[hj]
         dv_hat[b,d,hj] = 1/(se_v[hj] sc) * sum_n qp[z,n,d] A16[b,n,hj]                    (both operands MN-major)"""
@@ -308,7 +309,7 @@ def _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=Non
         qv16 = ops.codes_to_bf16(qv, B, N, C, C, N * C, False, FMT)      # [B, N, C]
     dPq = torch.empty((B * H, N, ldS), dtype=torch.float32, device=dO.device)
     ops.gemm(GEMM_BWD, a16, (C, 0, hd, N * C), qv16, (C, 0, hd, N * C), dPq, (ldS, N * ldS, H * N * ldS), N, N, hd,
-             nb1=H, nb2=B, rs=vec(sp2[1], N), cs=_scalar(sc), rt=vec(prep["rowdot"], 0, N, H * N))
+             nb1=H, nb2=B, rs=vec(sp2[1], N), cs=_scalar(sc), rt=vec(prep["rowdot"], 0, N, H * N), amax=amax_dp)
     if qp16 is None:
         qp16 = ops.codes_to_bf16(qp, B * H, N, ldq, ldq, N * ldq, False, FMT)    # [B*H, N, ldq]
     dvhat = torch.empty((B, N, C), dtype=torch.float32, device=dO.device)
@@ -317,11 +318,11 @@ def _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=Non
     return dPq, dvhat
 
 
-def _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=None, qp16=None, sc=None, amax_dv=None):
+def _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=None, qp16=None, sc=None, amax_dv=None, amax_dp=None):
     """Returns (dPq [B*H,N,ldS] fp32, dvhat [B,N,C] fp32). sp2 / sv2 = [scale, 1/scale] of the probability / V quantizer.
     qv16 / qp16: exact 16-bit copies of the codes left by the forward quantizer passes (fp16 mode)."""
     if F16:
-        return _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16, qp16, sc, amax_dv)
+        return _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16, qp16, sc, amax_dv, amax_dp)
     se_p, se_v = sp2[0], sv2[0]
     hd = C // H
     prep = ops.grad_prep(dO, B, N, C, C, N * C, cs=se_v, rs=se_p, rs_period=N, want_rm=True, want_t=True,
@@ -432,9 +433,10 @@ class QKRAttnCoreFn(torch.autograd.Function):
         # of the V and qkx quantizers then write the fp16 operand of the next linear layer's backward GEMMs directly
         # (range scale from that bound), so d v_out / d qkx never exist in fp32 and ofq_grad_prep is not needed there
         fused16 = F16 and FUSED16 and C % 128 == 0      # streaming layout of the (token, head)-segmented qkx pass
-        amax = torch.zeros(2, dtype=torch.float32, device=dev) if fused16 else None
+        amax = torch.zeros(3, dtype=torch.float32, device=dev) if F16 else None      # max |d v_hat|, |d k_hat|, |dP_hat|
         dPq, dvhat = _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16, qp16,
-                                  link.sc if link is not None else None, amax_dv=amax[0:1] if fused16 else None)
+                                  link.sc if link is not None else None, amax_dv=amax[0:1] if fused16 else None,
+                                  amax_dp=amax[2:3] if F16 else None)
         # --- V quantizer and V linear
         dxhat = torch.empty((M, C), dtype=torch.float32, device=dev)
         if fused16:
@@ -451,7 +453,8 @@ class QKRAttnCoreFn(torch.autograd.Function):
         # --- softmax + probability quantizer, then the two score GEMMs
         if F16:
             # |dS| = |alpha P (dP - sum P dP)| <= 2 alpha max|dPq|; ONE copy dS16[b,h,n,d] = fp16(dS se_k[h,d] se_x[n] sc)
-            sc = ops.absmax_scale(dPq, B * H, N, N, ldS, N * ldS, v1=se_k_hn, v2=se_x, mult=2.0 * scale, product=True)
+            # (max |dP_hat| comes from the epilogue of the GEMM that produced it: no pass over dP_hat)
+            sc = ops.scale_from_max(amax[2:3], v1=se_k_hn, v2=se_x, mult=2.0 * scale, product=True)
             dS16, _, ldo, colsum_dS, ds_p, dS32 = ops.softmax_quant_bwd(dPq, P, N, H, se_p, hiu, scale, g_p, se_k_hn, True,
                                                                       se_x, want_ds32=has_bias, fmt=FMT, scale4=sc,
                                                                       single=True)

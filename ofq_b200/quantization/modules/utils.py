@@ -9,6 +9,8 @@ from __future__ import annotations
 
 import torch
 
+from ... import prologue
+
 from ...host.deit import Attention as deit_attention
 from ...host.deit import Mlp
 from ...host.swin import MLP as swin_MLP
@@ -75,6 +77,7 @@ def replace_module_by_qmodule_deit(model, qconfigs, pretrained_initialized=False
                 aq_learnable=cfg["act"]["learnable"], wq_learnable=cfg["weight"]["learnable"],
                 act_layer=cfg["act_layer"], pretrained_initialized=pretrained_initialized, **extra)
         set_module_by_name(model, name, qmodule)
+    prologue.install(model)     # weight codes / W_qk / step sizes of all layers in three launches per forward (ofq_b200/prologue.py)
     return model
 
 
@@ -97,6 +100,7 @@ def replace_module_by_qmodule_swin(model, qconfigs, pretrained_initialized=False
                 aq_learnable=cfg["act"]["learnable"], wq_learnable=cfg["weight"]["learnable"],
                 act_layer=cfg["act_layer"], pretrained_initialized=pretrained_initialized)
         set_module_by_name(model, name, qmodule)
+    prologue.install(model)
     return model
 
 

@@ -10,7 +10,7 @@ from ... import ops
 class _StatsQFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, weight, bits):
-        codes, colscale, sf, _, _ = ops.statsq_codes(weight.contiguous(), bits)
+        codes, colscale, sf, _, _ = ops.statsq_codes(weight.contiguous(), bits, want_sf=True)
         ctx.mark_non_differentiable(sf)
         return codes.to(torch.float32) * colscale.unsqueeze(1), sf
 

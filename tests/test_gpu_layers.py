@@ -234,3 +234,51 @@ def test_swin_step_against_reference(Q, qkr):
     assert abs(loss.item() - g["loss"].item()) <= OUT_TOL * abs(g["loss"].item())
     loss.backward()
     assert check_grads(model.named_parameters(), g, sampled=True) > 80
+
+
+def test_step_prologue_matches_per_layer_path(Q):
+    """The step prologue (all StatsQ codes, W_qk products and LSQ step sizes of the model in three launches per forward,
+    ofq_b200/prologue.py) is a pure re-scheduling: logits, loss and every gradient are bit-identical to the per-layer path,
+    also after the weights changed (an optimizer step) and for a different batch size (new gradient-scale factors)."""
+    from ofq_b200 import ops, prologue
+    from ofq_b200.cga import CGAAdamW, param_groups_weight_decay
+    from ofq_b200.host.deit import DistilledVisionTransformer
+    torch.manual_seed(41)
+    depth = 2
+    model = DistilledVisionTransformer(embed_dim=128, depth=depth, num_heads=2, num_classes=10)
+    model = Q.replace_module_by_qmodule_deit(model, Q.make_qconfigs(Q.deit_qmodule_names(depth), 2, 2),
+                                             pretrained_initialized=True, qk_reparam=True).cuda()
+    img = torch.randn(3, 3, 224, 224, device="cuda")
+    lbl = torch.tensor([1, 5, 7], device="cuda")
+    model.eval()
+    with torch.no_grad():
+        model(img)
+    model.train()
+    opt = CGAAdamW(param_groups_weight_decay(model, 0.05, model.no_weight_decay()), lr=1e-3)
+
+    def run(x, y):
+        model.zero_grad(set_to_none=True)
+        (cls, dst), _ = model(x)
+        loss = F.cross_entropy(cls, y) + F.cross_entropy(dst, y)
+        loss.backward()
+        return cls.detach().clone(), {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    assert prologue.ENABLED and getattr(model, "_ofq_prologue", None) is not None
+    for x, y in ((img, lbl), (img[:2], lbl[:2])):
+        run(x, y)                                   # registers the jobs of this batch shape
+        l0 = ops.LAUNCHES
+        cls_a, g_a = run(x, y)                      # served by the prologue
+        n_pro = ops.LAUNCHES - l0
+        assert model._ofq_prologue.fresh is False and len(model._ofq_prologue.statsq) >= 5 * depth
+        prologue.ENABLED = False
+        try:
+            l0 = ops.LAUNCHES
+            cls_b, g_b = run(x, y)                  # per-layer path
+            n_ref = ops.LAUNCHES - l0
+        finally:
+            prologue.ENABLED = True
+        assert n_pro < n_ref - 10 * depth           # ~13 small launches per block became 3 per model
+        assert torch.equal(cls_a, cls_b)
+        for n in g_b:
+            assert torch.equal(g_a[n], g_b[n]), n
+        opt.step()                                  # weights move: the next forward must see the new codes
