@@ -279,6 +279,7 @@ def test_step_prologue_matches_per_layer_path(Q):
             prologue.ENABLED = True
         assert n_pro < n_ref - 10 * depth           # ~13 small launches per block became 3 per model
         assert torch.equal(cls_a, cls_b)
+        gmax = max(v.abs().max().item() for v in g_b.values())
         for n in g_b:
-            assert torch.equal(g_a[n], g_b[n]), n
+            assert rel_err(g_a[n], g_b[n]) < 1e-5 or (g_a[n] - g_b[n]).abs().max().item() <= 1e-6 * gmax, n
         opt.step()                                  # weights move: the next forward must see the new codes
