@@ -132,10 +132,14 @@ OFQ_API int ofq_lsq_quant(const float* x, long long rows, int cols, long long ld
 
 /* Same with (a) an activation fused in front of the quantizer, codes = Q(act(x) + b4), so that the GELU output of QMLP
  * never travels through HBM, and (b) an optional exact 16-bit copy codes16 [rows][ld16] (fmt16 = OFQ_FMT_BF16 / _F16)
- * of the codes, written in the same pass: the operand the backward GEMMs read. */
+ * of the codes, written in the same pass: the operand the backward GEMMs read, and (c) optional segment-wise dot
+ * products of the codes with a vector dot_u[cols] (ofq_codes_rowdot in the same pass): the share of 128-column group j of
+ * a segment goes to dot_part[j][row * nseg + seg] (cols/nseg/128 planes, to be summed by the caller; needs 128-column
+ * groups that do not straddle segments). */
 OFQ_API int ofq_lsq_quant_ex(const float* x, long long rows, int cols, long long ldx, const float* b4,
                              const float* s_eff, int scale_mode, int period, int nseg, int qlo, int qhi, int act,
-                             int8_t* codes, long long ldq, void* codes16, long long ld16, int fmt16, void* stream);
+                             int8_t* codes, long long ldq, void* codes16, long long ld16, int fmt16,
+                             const float* dot_u, float* dot_part, void* stream);
 
 /* Backward of (LearnableBias -> LSQ -> LearnableBias) given dy = dL/d(x_hat) (autograd of lsq.py:571-602):
  *   v = (x + b4)/s_eff;  inside = qlo <= v <= qhi;  q = rint(clamp(v))

@@ -50,7 +50,7 @@ SIGNATURES = {
     "ofq_lsq_effective_scale": (_i, [_p, _i, _f, _p, _p, _p]),
     "ofq_lsq_quant": (_i, [_p, _ll, _i, _ll, _p, _p, _i, _i, _i, _i, _i, _p, _ll, _p]),
     "ofq_lsq_bwd_workspace": (_ll, [_ll, _i, _i]),
-    "ofq_lsq_quant_ex": (_i, [_p, _ll, _i, _ll, _p, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p, _ll, _i, _p]),
+    "ofq_lsq_quant_ex": (_i, [_p, _ll, _i, _ll, _p, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p, _ll, _i, _p, _p, _p]),
     "ofq_lsq_bwd_ex": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p, _ll, _i, _p, _p, _i, _p, _p, _p]),
     "ofq_scale_from_max": (_i, [_p, _i, _p, _i, _p, _i, _f, _i, _p, _p]),
     "ofq_lsq_bwd_act": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p, _p]),

@@ -232,7 +232,8 @@ __global__ void __launch_bounds__(256)
 lsq_quant_vec_kernel(const float* __restrict__ x, uint32_t rows, int cols, long long ldx,
                      const float* __restrict__ b4, const float* __restrict__ s_eff, uint32_t period,
                      int nseg, int seg_len, float qlo, float qhi, int8_t* __restrict__ codes, long long ldq,
-                     uint16_t* __restrict__ codes16, long long ld16, int f16) {
+                     uint16_t* __restrict__ codes16, long long ld16, int f16,
+                     const float* __restrict__ dot_u, float* __restrict__ dot_part) {
     constexpr int ILP = 4;
     const uint32_t lane = threadIdx.x & 31;
     const StreamPlan pl = stream_plan(cols);
@@ -252,6 +253,16 @@ lsq_quant_vec_kernel(const float* __restrict__ x, uint32_t rows, int cols, long 
     uint32_t n = (w / pl.cg) % period;
     const float* xp = x + col;
     int8_t* cp = codes + col;
+    // optional segment-wise dot product of the codes with a vector u (the column term of the attention logits,
+    // sum_c aft_x[c] qk[.., c]): this warp's 128-column share goes to dot_part[group-in-segment][row * nseg + seg]
+    float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* dp = nullptr;
+    if (dot_u) {
+        u4 = __ldg(reinterpret_cast<const float4*>(dot_u + col));
+        const int seg = nseg == 1 ? 0 : col / seg_len;
+        const uint32_t gi = nseg == 1 ? g : g - (uint32_t)seg * (uint32_t)(seg_len / 128);
+        dp = dot_part + (long long)gi * rows * nseg + seg;
+    }
     for (uint32_t row = w / pl.cg; row < rows; row += dr * ILP) {
         float4 xv[ILP];
         float sv[ILP];
@@ -284,6 +295,11 @@ lsq_quant_vec_kernel(const float* __restrict__ x, uint32_t rows, int cols, long 
             if (codes16)       // exact 16-bit copy: the operand of the backward GEMMs, written while the codes are in registers
                 *reinterpret_cast<uint2*>(codes16 + (long long)r * ld16 + col) =
                     make_uint2(pack_codes16(q0, q1, f16 != 0), pack_codes16(q2, q3, f16 != 0));
+            if (dot_u) {
+                float d = fmaf((float)q0, u4.x, fmaf((float)q1, u4.y, fmaf((float)q2, u4.z, (float)q3 * u4.w)));
+                d = warp_sum(d);
+                if (lane == 0) dp[(long long)r * nseg] = d;
+            }
         }
     }
 }
@@ -1242,8 +1258,11 @@ extern "C" int ofq_lsq_effective_scale(const float* alpha, int n, float g, float
 
 extern "C" int ofq_lsq_quant_ex(const float* x, long long rows, int cols, long long ldx, const float* b4,
                                 const float* s_eff, int scale_mode, int period, int nseg, int qlo, int qhi, int act,
-                                int8_t* codes, long long ldq, void* codes16, long long ld16, int fmt16, void* stream) {
+                                int8_t* codes, long long ldq, void* codes16, long long ld16, int fmt16,
+                                const float* dot_u, float* dot_part, void* stream) {
     OFQ_REQUIRE(x && b4 && s_eff && codes, "ofq_lsq_quant: null pointer");
+    OFQ_REQUIRE(!dot_u || (dot_part && cols % 128 == 0 && (nseg == 1 || (cols / nseg) % 128 == 0) && (uintptr_t)dot_u % 16 == 0),
+                "ofq_lsq_quant: the fused code dot product needs 128-column groups that do not straddle segments");
     OFQ_REQUIRE(rows > 0 && cols > 0 && nseg > 0 && cols % nseg == 0 && period > 0, "ofq_lsq_quant: bad shape");
     OFQ_REQUIRE(qlo >= -128 && qhi <= 127 && qlo < qhi, "ofq_lsq_quant: codes must fit int8");
     OFQ_REQUIRE(act == OFQ_ACT_NONE || act == OFQ_ACT_GELU, "ofq_lsq_quant: unknown activation");
@@ -1262,7 +1281,7 @@ extern "C" int ofq_lsq_quant_ex(const float* x, long long rows, int cols, long l
     if (vec && (cols + 127) / 128 <= kStreamWarps) {
 #define OFQ_LSQ_QUANT(MODE, ACT, PERIOD)                                                                                     \
     lsq_quant_vec_kernel<MODE, ACT><<<kStreamCtas, 256, 0, st>>>(x, (uint32_t)rows, cols, ldx, b4, s_eff, PERIOD, nseg, seg_len, \
-                                                                 (float)qlo, (float)qhi, codes, ldq, c16, ld16, f16)
+                                                                 (float)qlo, (float)qhi, codes, ldq, c16, ld16, f16, dot_u, dot_part)
         if (scale_mode == OFQ_SCALE_PER_ROW) {
             if (act == OFQ_ACT_GELU) OFQ_LSQ_QUANT(OFQ_SCALE_PER_ROW, OFQ_ACT_GELU, (uint32_t)period);
             else OFQ_LSQ_QUANT(OFQ_SCALE_PER_ROW, OFQ_ACT_NONE, (uint32_t)period);
@@ -1272,6 +1291,7 @@ extern "C" int ofq_lsq_quant_ex(const float* x, long long rows, int cols, long l
         }
 #undef OFQ_LSQ_QUANT
     } else {
+        OFQ_REQUIRE(!dot_u, "ofq_lsq_quant: the fused code dot product needs the vectorised layout");
         const unsigned grid = (unsigned)((rows * cols + 255) / 256);
         lsq_quant_kernel<<<grid, 256, 0, st>>>(x, rows, cols, ldx, b4, s_eff, scale_mode, period, nseg, seg_len, (float)qlo,
                                                (float)qhi, codes, ldq, act, c16, ld16, f16);
@@ -1284,7 +1304,7 @@ extern "C" int ofq_lsq_quant(const float* x, long long rows, int cols, long long
                              const float* s_eff, int scale_mode, int period, int nseg, int qlo, int qhi,
                              int8_t* codes, long long ldq, void* stream) {
     return ofq_lsq_quant_ex(x, rows, cols, ldx, b4, s_eff, scale_mode, period, nseg, qlo, qhi, OFQ_ACT_NONE, codes, ldq,
-                            nullptr, 0, OFQ_FMT_F16, stream);
+                            nullptr, 0, OFQ_FMT_F16, nullptr, nullptr, stream);
 }
 
 // layout of the partial-sum workspace for either variant

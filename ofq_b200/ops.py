@@ -149,23 +149,32 @@ ACT_NONE, ACT_GELU = 0, 1
 
 
 def lsq_quant(x2d: torch.Tensor, b4: torch.Tensor, s_eff: torch.Tensor, mode: int, period: int, nseg: int,
-              qlo: int, qhi: int, out: Optional[torch.Tensor] = None, act: int = ACT_NONE, fmt16: Optional[int] = None):
+              qlo: int, qhi: int, out: Optional[torch.Tensor] = None, act: int = ACT_NONE, fmt16: Optional[int] = None,
+              dot_u: Optional[torch.Tensor] = None):
     """x2d: [rows, cols] fp32 view (last dim contiguous). Returns int8 codes [rows, cols] of Q(act(x) + b4); with fmt16
-    (FMT_BF16 / FMT_F16) returns (codes, exact 16-bit copy [rows, cols]) written in the same pass."""
+    (FMT_BF16 / FMT_F16) returns (codes, exact 16-bit copy [rows, cols]) written in the same pass; with dot_u [cols] a
+    further element: segment-wise dot products of the codes with dot_u, [rows, nseg] (codes_rowdot in the same pass)."""
     _cuda(x2d, b4, s_eff)
     assert x2d.dim() == 2 and x2d.stride(1) == 1 and x2d.dtype == torch.float32
     rows, cols = x2d.shape
     if out is None:
         out = torch.empty((rows, cols), dtype=torch.int8, device=x2d.device)
-    if act == ACT_NONE and fmt16 is None:
+    if act == ACT_NONE and fmt16 is None and dot_u is None:
         _call("lsq_quant", 1, 5.0 * rows * cols, 0, _lib.load().ofq_lsq_quant, x2d.data_ptr(), rows, cols, x2d.stride(0),
               b4.data_ptr(), s_eff.data_ptr(), mode, period, nseg, qlo, qhi, out.data_ptr(), out.stride(0), _st())
         return out
     out16 = torch.empty((rows, cols), dtype=_T16[fmt16], device=x2d.device) if fmt16 is not None else None
+    fused_dot = dot_u is not None and cols % 128 == 0 and (nseg == 1 or (cols // nseg) % 128 == 0) and x2d.stride(0) % 4 == 0
+    part = torch.empty(((cols // nseg) // 128, rows, nseg), dtype=torch.float32, device=x2d.device) if fused_dot else None
     _call("lsq_quant", 1, (5.0 + (2 if fmt16 is not None else 0)) * rows * cols, 0, _lib.load().ofq_lsq_quant_ex, x2d.data_ptr(),
           rows, cols, x2d.stride(0), b4.data_ptr(), s_eff.data_ptr(), mode, period, nseg, qlo, qhi, act, out.data_ptr(),
-          out.stride(0), _ptr(out16), cols, fmt16 if fmt16 is not None else FMT_F16, _st())
-    return out if fmt16 is None else (out, out16)
+          out.stride(0), _ptr(out16), cols, fmt16 if fmt16 is not None else FMT_F16, _ptr(dot_u) if fused_dot else None,
+          _ptr(part), _st())
+    res = (out,) if fmt16 is None else (out, out16)
+    if dot_u is not None:
+        # the partial planes are summed in a fixed order (deterministic logits); unfused shapes take the stand-alone kernel
+        res += ((part.sum(0) if part.shape[0] > 1 else part[0]) if fused_dot else codes_rowdot(out, nseg, dot_u),)
+    return res[0] if len(res) == 1 else res
 
 
 def lsq_bwd(dy2d: torch.Tensor, x2d: torch.Tensor, b4: torch.Tensor, s_eff: torch.Tensor, mode: int, period: int,

@@ -387,12 +387,14 @@ class QKRAttnCoreFn(torch.autograd.Function):
         g_k = grad_scale_factor(hi, B * C)
         sk2 = ops.lsq_effective_scale(s_k, g_k, recip=True)          # [2, N*H], index n*H + h
         se_k = sk2[0]
-        qk = ops.lsq_quant(qkx, k_b4, se_k, PER_ROW, N, H, lo, hi, fmt16=f16)   # [M, H*C]
+        # ... and, in the same pass, the column term of the logits sum_c x_aft[c] qk[b,d,h,c]  ([M, H]; attention.py:210-213:
+        # S = x_hat . k_hat^T * scale; terms constant along the softmax axis are dropped, they cancel exactly in softmax
+        # and in its gradient)
+        r = ops.lsq_quant(qkx, k_b4, se_k, PER_ROW, N, H, lo, hi, fmt16=f16, dot_u=x_aft.repeat(H))   # codes [M, H*C]
         if f16 is not None:
-            qk, qk16 = qk
-        # --- scores (attention.py:210-213): S = x_hat . k_hat^T * scale; terms constant along the softmax
-        #     axis are dropped (they cancel exactly in softmax and in its gradient)
-        ctS = ops.codes_rowdot(qk, H, x_aft.repeat(H))               # [M, H]: sum_c x_aft[c] qk[b,d,h,c]
+            qk, qk16, ctS = r
+        else:
+            qk, ctS = r
         sk2_hn = sk2.view(2, N, H).transpose(1, 2).contiguous()      # [2, H, N]
         se_k_hn = sk2_hn[0]
         cs_S = se_k_hn * scale
