@@ -227,7 +227,7 @@ __host__ __device__ inline StreamPlan stream_plan(int cols) {
     return p;
 }
 
-template <int MODE, int ACT>
+template <int MODE, int ACT, bool DOT>
 __global__ void __launch_bounds__(256)
 lsq_quant_vec_kernel(const float* __restrict__ x, uint32_t rows, int cols, long long ldx,
                      const float* __restrict__ b4, const float* __restrict__ s_eff, uint32_t period,
@@ -257,7 +257,7 @@ lsq_quant_vec_kernel(const float* __restrict__ x, uint32_t rows, int cols, long 
     // sum_c aft_x[c] qk[.., c]): this warp's 128-column share goes to dot_part[group-in-segment][row * nseg + seg]
     float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float* dp = nullptr;
-    if (dot_u) {
+    if (DOT) {
         u4 = __ldg(reinterpret_cast<const float4*>(dot_u + col));
         const int seg = nseg == 1 ? 0 : col / seg_len;
         const uint32_t gi = nseg == 1 ? g : g - (uint32_t)seg * (uint32_t)(seg_len / 128);
@@ -266,6 +266,7 @@ lsq_quant_vec_kernel(const float* __restrict__ x, uint32_t rows, int cols, long 
     for (uint32_t row = w / pl.cg; row < rows; row += dr * ILP) {
         float4 xv[ILP];
         float sv[ILP];
+        float dsum[ILP] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int u = 0; u < ILP; ++u) {
             const uint32_t r = row + u * dr;
@@ -295,10 +296,17 @@ lsq_quant_vec_kernel(const float* __restrict__ x, uint32_t rows, int cols, long 
             if (codes16)       // exact 16-bit copy: the operand of the backward GEMMs, written while the codes are in registers
                 *reinterpret_cast<uint2*>(codes16 + (long long)r * ld16 + col) =
                     make_uint2(pack_codes16(q0, q1, f16 != 0), pack_codes16(q2, q3, f16 != 0));
-            if (dot_u) {
-                float d = fmaf((float)q0, u4.x, fmaf((float)q1, u4.y, fmaf((float)q2, u4.z, (float)q3 * u4.w)));
-                d = warp_sum(d);
-                if (lane == 0) dp[(long long)r * nseg] = d;
+            if (DOT) dsum[u] = fmaf((float)q0, u4.x, fmaf((float)q1, u4.y, fmaf((float)q2, u4.z, (float)q3 * u4.w)));
+        }
+        if (DOT) {       // the ILP row reductions run interleaved (independent shuffle chains), lane u stores row u
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int u = 0; u < ILP; ++u) dsum[u] += __shfl_xor_sync(0xffffffffu, dsum[u], o);
+#pragma unroll
+            for (int u = 0; u < ILP; ++u) {
+                const uint32_t r = row + u * dr;
+                if (lane == (uint32_t)u && r < rows) dp[(long long)r * nseg] = dsum[u];
             }
         }
     }
@@ -1280,10 +1288,16 @@ extern "C" int ofq_lsq_quant_ex(const float* x, long long rows, int cols, long l
     const int f16 = fmt16 == OFQ_FMT_F16;
     if (vec && (cols + 127) / 128 <= kStreamWarps) {
 #define OFQ_LSQ_QUANT(MODE, ACT, PERIOD)                                                                                     \
-    lsq_quant_vec_kernel<MODE, ACT><<<kStreamCtas, 256, 0, st>>>(x, (uint32_t)rows, cols, ldx, b4, s_eff, PERIOD, nseg, seg_len, \
-                                                                 (float)qlo, (float)qhi, codes, ldq, c16, ld16, f16, dot_u, dot_part)
+    lsq_quant_vec_kernel<MODE, ACT, false><<<kStreamCtas, 256, 0, st>>>(x, (uint32_t)rows, cols, ldx, b4, s_eff, PERIOD, nseg, seg_len, \
+                                                                 (float)qlo, (float)qhi, codes, ldq, c16, ld16, f16, nullptr, nullptr)
+        OFQ_REQUIRE(!dot_u || (scale_mode == OFQ_SCALE_PER_ROW && act == OFQ_ACT_NONE),
+                    "ofq_lsq_quant: the fused code dot product is built for per-row scales without an activation");
         if (scale_mode == OFQ_SCALE_PER_ROW) {
-            if (act == OFQ_ACT_GELU) OFQ_LSQ_QUANT(OFQ_SCALE_PER_ROW, OFQ_ACT_GELU, (uint32_t)period);
+            if (dot_u)
+                lsq_quant_vec_kernel<OFQ_SCALE_PER_ROW, OFQ_ACT_NONE, true><<<kStreamCtas, 256, 0, st>>>(
+                    x, (uint32_t)rows, cols, ldx, b4, s_eff, (uint32_t)period, nseg, seg_len, (float)qlo, (float)qhi, codes, ldq, c16,
+                    ld16, f16, dot_u, dot_part);
+            else if (act == OFQ_ACT_GELU) OFQ_LSQ_QUANT(OFQ_SCALE_PER_ROW, OFQ_ACT_GELU, (uint32_t)period);
             else OFQ_LSQ_QUANT(OFQ_SCALE_PER_ROW, OFQ_ACT_NONE, (uint32_t)period);
         } else {
             if (act == OFQ_ACT_GELU) OFQ_LSQ_QUANT(OFQ_SCALE_PER_COL, OFQ_ACT_GELU, 1u);

@@ -51,6 +51,9 @@ for cols, nseg in ((384, 1), (1536, 1), (2304, 6)):
     timeit(f"lsq_quant rows C={cols} nseg={nseg}", 5.0 * M * cols, lambda i: ops.lsq_quant(x[i], b4, se, PER_ROW, N, nseg, -2, 1))
     timeit(f"lsq_bwd rows C={cols} nseg={nseg}", 12.0 * M * cols, lambda i: ops.lsq_bwd(dy[i], x[i], b4, se, PER_ROW, N, nseg, -2, 1, 0.01))
     timeit(f"lsq_quant rows +fp16 copy C={cols} nseg={nseg}", 7.0 * M * cols, lambda i: ops.lsq_quant(x[i], b4, se, PER_ROW, N, nseg, -2, 1, fmt16=FMT_F16))
+    if cols == 2304:
+        u = torch.randn(cols, device=dev)
+        timeit(f"lsq_quant rows +fp16 copy +rowdot C={cols} nseg={nseg}", 7.0 * M * cols, lambda i: ops.lsq_quant(x[i], b4, se, PER_ROW, N, nseg, -2, 1, fmt16=FMT_F16, dot_u=u))
     if cols == 1536:
         timeit(f"lsq_quant rows GELU +fp16 copy C={cols}", 7.0 * M * cols, lambda i: ops.lsq_quant(x[i], b4, se, PER_ROW, N, nseg, 0, 3, act=ops.ACT_GELU, fmt16=FMT_F16))
         timeit(f"lsq_bwd rows GELU C={cols}", 12.0 * M * cols, lambda i: ops.lsq_bwd(dy[i], x[i], b4, se, PER_ROW, N, nseg, 0, 3, 0.01, act=ops.ACT_GELU))
