@@ -108,6 +108,11 @@ OFQ_API int ofq_gemm_ex(int kind, const ofq_operand_t* A, const ofq_operand_t* B
 OFQ_API int ofq_statsq_codes(const float* w, int rows, int cols, long long ldw, int bits, int8_t* codes,
                              long long ldq, float* colscale, float* sf, const float* aft, const float* bias,
                              float* colterm, int* kminmax, float* inv_colscale, void* stream);
+/* Same, plus an optional exact 16-bit copy codes16 [rows][cols] (OFQ_FMT_BF16 / _F16) of the codes: the B operand of
+ * the layer's dX GEMM in the backward, written while the codes are in registers. */
+OFQ_API int ofq_statsq_codes_ex(const float* w, int rows, int cols, long long ldw, int bits, int8_t* codes,
+                                long long ldq, float* colscale, float* sf, const float* aft, const float* bias,
+                                float* colterm, int* kminmax, float* inv_colscale, void* codes16, int fmt16, void* stream);
 
 /* LSQ effective step size (lsq.py:593): out[i] = (a - a*g) + a*g with a = alpha[i] > 1e-5 ? alpha[i] : 1e-5,
  * evaluated in fp32 exactly as grad_scale(clip(alpha)) does. out_recip (optional) receives 1 / out[i]. */
@@ -296,7 +301,9 @@ OFQ_API int ofq_wqk_compose_bwd(const float* dwqk, const float* wq, const float*
 typedef struct {
     const float* w; const float* aft; const float* bias;       /* aft / bias may be NULL (see ofq_statsq_codes) */
     int8_t* codes; float* colscale; float* inv_colscale; float* colterm;   /* inv_colscale / colterm may be NULL */
+    void* codes16;                                                         /* optional exact 16-bit copy of the codes */
     long long ldw; int rows, cols; float n_levels; int first_block;        /* n_levels = 2^(bits-1); codes pitch = cols */
+    int f16; int pad;                                                      /* codes16 format: 1 = fp16, 0 = bf16 */
 } ofq_statsq_job_t;
 typedef struct {
     const float* alpha; float* out; float* out_recip;          /* out_recip may be NULL */
@@ -345,6 +352,13 @@ OFQ_API int ofq_layernorm_bwd(const float* dy, const float* x, const float* gamm
 OFQ_API int ofq_layernorm_bwd_res(const float* dy, const float* x, const float* gamma, const float* mean,
                                   const float* rstd, long long rows, int cols, const float* res, float* dx,
                                   float* dgamma, float* dbeta, float* workspace, void* stream);
+/* Same, plus blockmax [ofq_layernorm_bwd_nmax(rows, cols)] = per-CTA max |dx| (cols <= 512 only): dx is the residual-stream
+ * gradient that the previous proj / fc2 layer's backward consumes as dY, whose fp16 range scale then needs no pass over it
+ * (ofq_scale_from_max). */
+OFQ_API long long ofq_layernorm_bwd_nmax(long long rows, int cols);
+OFQ_API int ofq_layernorm_bwd_max(const float* dy, const float* x, const float* gamma, const float* mean,
+                                  const float* rstd, long long rows, int cols, const float* res, float* dx,
+                                  float* dgamma, float* dbeta, float* workspace, float* blockmax, void* stream);
 
 #ifdef __cplusplus
 }

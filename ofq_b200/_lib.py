@@ -44,6 +44,7 @@ SIGNATURES = {
     "ofq_gemm_ex": (_i, [_i, C.POINTER(Operand), C.POINTER(Operand), C.POINTER(GemmOut), _i, _i, _i, _i, _i, _i, _i,
                          C.POINTER(Vec), C.POINTER(Vec), C.POINTER(Vec), C.POINTER(Vec), _p, _p]),
     "ofq_statsq_codes": (_i, [_p, _i, _i, _ll, _i, _p, _ll, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ofq_statsq_codes_ex": (_i, [_p, _i, _i, _ll, _i, _p, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p]),
     "ofq_statsq_codes_multi": (_i, [_p, _i, _i, _p]),
     "ofq_lsq_effective_scale_multi": (_i, [_p, _i, _i, _p]),
     "ofq_wqk_compose_multi": (_i, [_p, _i, _i, _i, _i, _p]),
@@ -78,6 +79,8 @@ SIGNATURES = {
     "ofq_layernorm_fwd": (_i, [_p, _ll, _i, _p, _p, _f, _p, _p, _p, _p]),
     "ofq_layernorm_bwd_workspace": (_ll, [_ll, _i]),
     "ofq_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _ll, _i, _p, _p, _p, _p, _p]),
+    "ofq_layernorm_bwd_nmax": (_ll, [_ll, _i]),
+    "ofq_layernorm_bwd_max": (_i, [_p, _p, _p, _p, _p, _ll, _i, _p, _p, _p, _p, _p, _p, _p]),
     "ofq_layernorm_bwd_res": (_i, [_p, _p, _p, _p, _p, _ll, _i, _p, _p, _p, _p, _p, _p]),
     "ofq_adamw_multi": (_i, [_p, _i, _i, _i, _d, _d, _d, _d, _p, _p]),
 }

@@ -58,8 +58,11 @@ template <bool ONE_CHUNK>
 __global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, long long rows, int cols,
-                     const float* __restrict__ res, float* __restrict__ dx, float* __restrict__ part) {
+                     const float* __restrict__ res, float* __restrict__ dx, float* __restrict__ part,
+                     float* __restrict__ blockmax) {
     __shared__ float col_s[2][kChunk];
+    __shared__ float bmax_s[8];
+    float tmax = 0.f;             // max |dx| written by this thread: the fp16 range scale of the next GEMM operand needs no pass
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long rpb = (rows + gridDim.x - 1) / gridDim.x;
     const long long r0 = (long long)blockIdx.x * rpb, r1 = min(rows, r0 + rpb);
@@ -129,6 +132,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
                     const float4 r4 = __ldg(reinterpret_cast<const float4*>(res + r * cols) + p * 32 + lane);
                     o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
                 }
+                tmax = fmaxf(fmaxf(tmax, fmaxf(fabsf(o[0]), fabsf(o[1]))), fmaxf(fabsf(o[2]), fabsf(o[3])));
                 reinterpret_cast<float4*>(dx + r * cols)[p * 32 + lane] = make_float4(o[0], o[1], o[2], o[3]);
             }
         }
@@ -178,6 +182,18 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
                 atomicAdd(&col_s[1][si], a_b[p][e]);
             }
     __syncthreads();
+    if (blockmax && ONE_CHUNK) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        if (lane == 0) bmax_s[warp] = tmax;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float m = bmax_s[0];
+#pragma unroll
+            for (int w2 = 1; w2 < 8; ++w2) m = fmaxf(m, bmax_s[w2]);
+            blockmax[blockIdx.x] = m;
+        }
+    }
     float* pp = part + (long long)blockIdx.x * 2 * cols;
     for (int i = threadIdx.x; i < kChunk; i += blockDim.x)
         if (cbase + i < cols) {
@@ -230,6 +246,14 @@ extern "C" long long ofq_layernorm_bwd_workspace(long long rows, int cols) { ret
 extern "C" int ofq_layernorm_bwd_res(const float* dy, const float* x, const float* gamma, const float* mean,
                                      const float* rstd, long long rows, int cols, const float* res, float* dx,
                                      float* dgamma, float* dbeta, float* workspace, void* stream) {
+    return ofq_layernorm_bwd_max(dy, x, gamma, mean, rstd, rows, cols, res, dx, dgamma, dbeta, workspace, nullptr, stream);
+}
+
+extern "C" long long ofq_layernorm_bwd_nmax(long long rows, int cols) { return cols <= kChunk ? ln_nblk(rows) : 0; }
+
+extern "C" int ofq_layernorm_bwd_max(const float* dy, const float* x, const float* gamma, const float* mean,
+                                     const float* rstd, long long rows, int cols, const float* res, float* dx,
+                                     float* dgamma, float* dbeta, float* workspace, float* blockmax, void* stream) {
     OFQ_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && workspace && rows > 0 && cols > 0,
                 "ofq_layernorm_bwd: bad argument");
     OFQ_REQUIRE(cols % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)dy % 16 == 0 && (uintptr_t)dx % 16 == 0 &&
@@ -239,8 +263,9 @@ extern "C" int ofq_layernorm_bwd_res(const float* dy, const float* x, const floa
     cudaStream_t st = (cudaStream_t)stream;
     const long long nblk = ln_nblk(rows);
     dim3 grid((unsigned)nblk, (cols + kChunk - 1) / kChunk);
-    if (grid.y == 1) layernorm_bwd_kernel<true><<<grid, 256, 0, st>>>(dy, x, gamma, mean, rstd, rows, cols, res, dx, workspace);
-    else layernorm_bwd_kernel<false><<<grid, 256, 0, st>>>(dy, x, gamma, mean, rstd, rows, cols, res, dx, workspace);
+    OFQ_REQUIRE(!blockmax || grid.y == 1, "ofq_layernorm_bwd_max: block maxima are produced for rows of at most 512 columns");
+    if (grid.y == 1) layernorm_bwd_kernel<true><<<grid, 256, 0, st>>>(dy, x, gamma, mean, rstd, rows, cols, res, dx, workspace, blockmax);
+    else layernorm_bwd_kernel<false><<<grid, 256, 0, st>>>(dy, x, gamma, mean, rstd, rows, cols, res, dx, workspace, nullptr);
     dim3 g2((cols + 31) / 32, 2);
     colpart_reduce2_kernel<<<g2, 1024, 0, st>>>(workspace, cols, nblk, dgamma, dbeta);
     OFQ_CUDA(cudaGetLastError());

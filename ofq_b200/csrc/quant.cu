@@ -37,7 +37,8 @@ __device__ __forceinline__ void
 statsq_row(const float* __restrict__ w, int row, int cols, long long ldw, float n_levels,
            int8_t* __restrict__ codes, long long ldq, float* __restrict__ colscale,
            float* __restrict__ sf_out, const float* __restrict__ aft, const float* __restrict__ bias,
-           float* __restrict__ colterm, int* __restrict__ kminmax, float* __restrict__ inv_colscale, int lane) {
+           float* __restrict__ colterm, int* __restrict__ kminmax, float* __restrict__ inv_colscale, int lane,
+           uint16_t* __restrict__ codes16 = nullptr, int f16 = 1) {
     const float* wr = w + (long long)row * ldw;
     double acc = 0.0;
     for (int c = lane; c < cols; c += 32) acc += (double)fabsf(__ldg(wr + c));
@@ -55,6 +56,12 @@ statsq_row(const float* __restrict__ w, int row, int cols, long long ldw, float 
         const int ki = (int)k;
         const int code = 2 * ki + 1;
         qr[c] = (int8_t)code;
+        if (codes16) {      // exact 16-bit copy (pitch = cols): the B operand of the layer's dX GEMM in the backward
+            uint32_t h;
+            if (f16) asm("cvt.rn.f16x2.f32 %0, %1, %2;\n" : "=r"(h) : "f"(0.f), "f"((float)code));
+            else     asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(h) : "f"(0.f), "f"((float)code));
+            codes16[(long long)row * cols + c] = (uint16_t)(h & 0xffffu);
+        }
         if (aft) dot = fmaf(__ldg(aft + c), (float)code, dot);
         kmin = min(kmin, ki);
         kmax = max(kmax, ki);
@@ -86,19 +93,20 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 statsq_codes_kernel(const float* __restrict__ w, int rows, int cols, long long ldw, float n_levels,
                     int8_t* __restrict__ codes, long long ldq, float* __restrict__ colscale,
                     float* __restrict__ sf_out, const float* __restrict__ aft, const float* __restrict__ bias,
-                    float* __restrict__ colterm, int* __restrict__ kminmax, float* __restrict__ inv_colscale) {
+                    float* __restrict__ colterm, int* __restrict__ kminmax, float* __restrict__ inv_colscale,
+                    uint16_t* __restrict__ codes16, int f16) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * kWarpsPerBlock + warp;
     if (row >= rows) return;
-    statsq_row(w, row, cols, ldw, n_levels, codes, ldq, colscale, sf_out, aft, bias, colterm, kminmax, inv_colscale, lane);
+    statsq_row(w, row, cols, ldw, n_levels, codes, ldq, colscale, sf_out, aft, bias, colterm, kminmax, inv_colscale, lane, codes16, f16);
 }
 
 // Multi-tensor variants (one launch for every quantized weight / every LSQ step size of a model): the jobs live in a device
 // table, a CTA finds its job by binary search over first_block. Layouts are part of the C-ABI (include/ofq_b200.h).
 struct StatsqJob {
     const float* w; const float* aft; const float* bias;
-    int8_t* codes; float* colscale; float* inv_colscale; float* colterm;
-    long long ldw; int rows, cols; float n_levels; int first_block;
+    int8_t* codes; float* colscale; float* inv_colscale; float* colterm; uint16_t* codes16;
+    long long ldw; int rows, cols; float n_levels; int first_block; int f16; int pad;
 };
 struct ScaleJob {
     const float* alpha; float* out; float* out_recip;
@@ -120,7 +128,7 @@ statsq_codes_multi_kernel(const StatsqJob* __restrict__ table, int n_jobs) {
     const int row = ((int)blockIdx.x - j.first_block) * kWarpsPerBlock + warp;
     if (row >= j.rows) return;
     statsq_row(j.w, row, j.cols, j.ldw, j.n_levels, j.codes, j.cols, j.colscale, nullptr, j.aft, j.bias, j.colterm, nullptr,
-               j.inv_colscale, lane);
+               j.inv_colscale, lane, j.codes16, j.f16);
 }
 
 // ------------------------------------------------------------------------------------------- LSQ scale
@@ -1227,20 +1235,29 @@ extern "C" int ofq_codes_rowdot(const int8_t* codes, long long rows, int cols, l
 extern "C" int ofq_statsq_codes(const float* w, int rows, int cols, long long ldw, int bits, int8_t* codes,
                                 long long ldq, float* colscale, float* sf, const float* aft, const float* bias,
                                 float* colterm, int* kminmax, float* inv_colscale, void* stream) {
+    return ofq_statsq_codes_ex(w, rows, cols, ldw, bits, codes, ldq, colscale, sf, aft, bias, colterm, kminmax, inv_colscale,
+                               nullptr, OFQ_FMT_F16, stream);
+}
+
+extern "C" int ofq_statsq_codes_ex(const float* w, int rows, int cols, long long ldw, int bits, int8_t* codes,
+                                   long long ldq, float* colscale, float* sf, const float* aft, const float* bias,
+                                   float* colterm, int* kminmax, float* inv_colscale, void* codes16, int fmt16, void* stream) {
     OFQ_REQUIRE(w && codes && colscale, "ofq_statsq_codes: null pointer");
+    OFQ_REQUIRE(!codes16 || fmt16 == OFQ_FMT_BF16 || fmt16 == OFQ_FMT_F16, "ofq_statsq_codes: bad 16-bit format");
     OFQ_REQUIRE(rows > 0 && cols > 0 && bits >= 2 && bits <= 7, "ofq_statsq_codes: bad shape or bits (2..7)");
     OFQ_CHECK_ARCH();
     const float n = (float)(1 << (bits - 1));
     const int grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
     statsq_codes_kernel<<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-        w, rows, cols, ldw, n, codes, ldq, colscale, sf, aft, bias, colterm, kminmax, inv_colscale);
+        w, rows, cols, ldw, n, codes, ldq, colscale, sf, aft, bias, colterm, kminmax, inv_colscale, (uint16_t*)codes16,
+        fmt16 == OFQ_FMT_F16);
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }
 
 extern "C" int ofq_statsq_codes_multi(const void* table, int n_jobs, int total_blocks, void* stream) {
     OFQ_REQUIRE(table && n_jobs > 0 && total_blocks > 0, "ofq_statsq_codes_multi: bad argument");
-    static_assert(sizeof(StatsqJob) == 80, "StatsqJob layout is part of the C-ABI");
+    static_assert(sizeof(StatsqJob) == 96, "StatsqJob layout is part of the C-ABI");
     OFQ_CHECK_ARCH();
     statsq_codes_multi_kernel<<<total_blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>((const StatsqJob*)table, n_jobs);
     OFQ_CUDA(cudaGetLastError());

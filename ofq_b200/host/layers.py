@@ -19,7 +19,7 @@ class _LayerNormFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x2d, weight, mean, rstd = ctx.saved_tensors
-        dx, dg, db = ops.layernorm_bwd(dy.contiguous().view_as(x2d), x2d, weight, mean, rstd)
+        dx, dg, db = ops.layernorm_bwd(dy.contiguous().view_as(x2d), x2d, weight, mean, rstd, want_max=True)
         return dx.view_as(dy), dg, db, None
 
 
@@ -43,7 +43,7 @@ class _LayerNormResFn(torch.autograd.Function):
         if dy is None:
             return dres, None, None, None
         res2d = dres.contiguous().view_as(x2d) if dres is not None else None
-        dx, dg, db = ops.layernorm_bwd(dy.contiguous().view_as(x2d), x2d, weight, mean, rstd, res2d)
+        dx, dg, db = ops.layernorm_bwd(dy.contiguous().view_as(x2d), x2d, weight, mean, rstd, res2d, want_max=True)
         return dx.view_as(dy), dg, db, None
 
 

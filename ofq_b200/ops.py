@@ -88,25 +88,27 @@ def gemm(kind: int, a: torch.Tensor, a_strides, b: torch.Tensor, b_strides, out:
 
 # ------------------------------------------------------------------------------------------------ quantizers
 def statsq_codes(w: torch.Tensor, bits: int, aft: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
-                 want_minmax: bool = False, want_inv: bool = False, want_sf: bool = False):
+                 want_minmax: bool = False, want_inv: bool = False, want_sf: bool = False, fmt16: Optional[int] = None):
     """StatsQ codes of a 2-D fp32 weight. Returns (codes int8 [R,C], colscale [R], sf [R] | None, colterm [R] | None,
     kminmax int32[2] | None [, 1/colscale [R] if want_inv]). sf is only guaranteed with want_sf (the step prologue does
-    not produce it)."""
+    not produce it). fmt16: a further last element, the exact 16-bit copy [R,C] of the codes."""
     _cuda(w)
     assert w.dim() == 2 and w.dtype == torch.float32 and w.stride(1) == 1
     R, Cc = w.shape
     from . import prologue
     pro = prologue.ACTIVE if prologue.ENABLED else None
-    job = None
+    c16 = None
     if pro is not None and not want_minmax and not want_sf:
-        job, ready = pro.get_statsq(w, bits, aft, bias)     # persistent outputs; `ready`: already produced by the step prologue
-        codes, cs2, colterm = job.out["codes"], job.out["cs2"], job.out["colterm"]
+        job, ready = pro.get_statsq(w, bits, aft, bias, fmt16)   # persistent outputs; `ready`: produced by the step prologue
+        codes, cs2, colterm, c16 = job.out["codes"], job.out["cs2"], job.out["colterm"], job.out["codes16"]
         if ready:
-            return (codes, cs2[0], None, colterm, None, cs2[1]) if want_inv else (codes, cs2[0], None, colterm, None)
+            res = (codes, cs2[0], None, colterm, None) + ((cs2[1],) if want_inv else ())
+            return res + ((c16,) if fmt16 is not None else ())
     else:
         codes = torch.empty((R, Cc), dtype=torch.int8, device=w.device)
         cs2 = torch.empty((2, R), dtype=torch.float32, device=w.device)
         colterm = torch.empty(R, dtype=torch.float32, device=w.device) if (aft is not None or bias is not None) else None
+        c16 = torch.empty((R, Cc), dtype=_T16[fmt16], device=w.device) if fmt16 is not None else None
     colscale = cs2[0]
     sf = torch.empty(R, dtype=torch.float32, device=w.device)
     mm = None
@@ -114,12 +116,11 @@ def statsq_codes(w: torch.Tensor, bits: int, aft: Optional[torch.Tensor] = None,
         mm = torch.tensor([2 ** 31 - 1, -2 ** 31], dtype=torch.int32, device=w.device)
     if colterm is not None and aft is None:
         aft = torch.zeros(Cc, dtype=torch.float32, device=w.device)
-    _call("statsq", 1, 5.0 * R * Cc, 0, _lib.load().ofq_statsq_codes, w.data_ptr(), R, Cc, w.stride(0), bits,
+    _call("statsq", 1, 5.0 * R * Cc, 0, _lib.load().ofq_statsq_codes_ex, w.data_ptr(), R, Cc, w.stride(0), bits,
           codes.data_ptr(), Cc, colscale.data_ptr(), sf.data_ptr(), _ptr(aft), _ptr(bias), _ptr(colterm), _ptr(mm),
-          cs2[1].data_ptr(), _st())
-    if want_inv:
-        return codes, colscale, sf, colterm, mm, cs2[1]
-    return codes, colscale, sf, colterm, mm
+          cs2[1].data_ptr(), _ptr(c16), fmt16 if fmt16 is not None else FMT_F16, _st())
+    res = (codes, colscale, sf, colterm, mm) + ((cs2[1],) if want_inv else ())
+    return res + ((c16,) if fmt16 is not None else ())
 
 
 def lsq_effective_scale(alpha: torch.Tensor, g: float, recip: bool = False):
@@ -464,7 +465,13 @@ def layernorm_fwd(x2d: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, ep
     return y, mean, rstd
 
 
-def layernorm_bwd(dy2d, x2d, gamma, mean, rstd, res2d=None):
+# The latest residual-stream gradient an ofq_b200 LayerNorm backward produced, with the per-CTA maxima of |dx|: the proj / fc2
+# backward that consumes exactly this tensor as dY derives its fp16 range scale from them (no absmax pass). The strong
+# reference keeps the storage alive, so a matching data_ptr really is this tensor.
+RESIDUAL_MAX = {"dx": None, "bmax": None}
+
+
+def layernorm_bwd(dy2d, x2d, gamma, mean, rstd, res2d=None, want_max: bool = False):
     """dx = LayerNorm'(dy) (+ res2d: the gradient arriving over the residual connection, added in the same pass)."""
     rows, cols = x2d.shape
     lib = _lib.load()
@@ -472,7 +479,19 @@ def layernorm_bwd(dy2d, x2d, gamma, mean, rstd, res2d=None):
     dx = torch.empty_like(x2d)
     dgamma = torch.empty(cols, dtype=torch.float32, device=x2d.device)
     dbeta = torch.empty(cols, dtype=torch.float32, device=x2d.device)
-    _call("layernorm_bwd", 2, (12.0 + (4 if res2d is not None else 0)) * rows * cols, 0, lib.ofq_layernorm_bwd_res, dy2d.data_ptr(),
+    nmax = lib.ofq_layernorm_bwd_nmax(rows, cols) if want_max else 0
+    bmax = torch.empty(nmax, dtype=torch.float32, device=x2d.device) if nmax > 0 else None
+    _call("layernorm_bwd", 2, (12.0 + (4 if res2d is not None else 0)) * rows * cols, 0, lib.ofq_layernorm_bwd_max, dy2d.data_ptr(),
           x2d.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, cols, _ptr(res2d), dx.data_ptr(),
-          dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), _st())
+          dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), _ptr(bmax), _st())
+    if bmax is not None:
+        RESIDUAL_MAX["dx"], RESIDUAL_MAX["bmax"] = dx, bmax
     return dx, dgamma, dbeta
+
+
+def residual_max_for(t: torch.Tensor):
+    """Block maxima of |t| if t is (a view of the whole of) the latest LayerNorm-backward output, else None."""
+    dx = RESIDUAL_MAX["dx"]
+    if dx is not None and t.data_ptr() == dx.data_ptr() and t.numel() == dx.numel() and t.is_contiguous():
+        return RESIDUAL_MAX["bmax"]
+    return None

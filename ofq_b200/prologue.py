@@ -54,16 +54,19 @@ class StepPrologue:
         job.used = True
         return job, self.fresh
 
-    def get_statsq(self, w, bits, aft, bias):
+    def get_statsq(self, w, bits, aft, bias, fmt16=None):
         R, Cc = w.shape
-        key = (w.data_ptr(), R, Cc, int(bits), 0 if aft is None else aft.data_ptr(), 0 if bias is None else bias.data_ptr())
+        key = (w.data_ptr(), R, Cc, int(bits), 0 if aft is None else aft.data_ptr(), 0 if bias is None else bias.data_ptr(),
+               fmt16)
         job = self.statsq.get(key)
         if job is None:
             dev = w.device
             out = dict(codes=torch.empty((R, Cc), dtype=torch.int8, device=dev),
                        cs2=torch.empty((2, R), dtype=torch.float32, device=dev),
-                       colterm=torch.empty(R, dtype=torch.float32, device=dev) if (aft is not None or bias is not None) else None)
-            job = self.statsq[key] = _Job(key, (w, aft, bias), out, meta=int(bits))
+                       colterm=torch.empty(R, dtype=torch.float32, device=dev) if (aft is not None or bias is not None) else None,
+                       codes16=None if fmt16 is None else torch.empty((R, Cc), device=dev,
+                                                                      dtype=torch.float16 if fmt16 == 1 else torch.bfloat16))
+            job = self.statsq[key] = _Job(key, (w, aft, bias), out, meta=(int(bits), fmt16))
             self.dirty = True
             return job, False
         job.used = True
@@ -112,10 +115,12 @@ class StepPrologue:
                 w, aft, bias = j.tensors
                 R, Cc = w.shape
                 o = j.out
-                blob += struct.pack("<QQQQQQQqiifi", w.data_ptr(), 0 if aft is None else aft.data_ptr(),
+                bits, fmt16 = j.meta
+                blob += struct.pack("<QQQQQQQQqiifiii", w.data_ptr(), 0 if aft is None else aft.data_ptr(),
                                     0 if bias is None else bias.data_ptr(), o["codes"].data_ptr(), o["cs2"][0].data_ptr(),
                                     o["cs2"][1].data_ptr(), 0 if o["colterm"] is None else o["colterm"].data_ptr(),
-                                    w.stride(0), R, Cc, float(1 << (j.meta - 1)), first)
+                                    0 if o["codes16"] is None else o["codes16"].data_ptr(),
+                                    w.stride(0), R, Cc, float(1 << (bits - 1)), first, 1 if fmt16 == 1 else 0, 0)
                 first += (R + 7) // 8
             tb["statsq"] = (self._upload(blob, dev), len(self.statsq), first)
         if self.scale:

@@ -67,7 +67,7 @@ def _scalar(sc):
 
 
 def _linear_backward_f16(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulate_dx: bool, qx16=None, sc=None, a16=None,
-                         colsum=None, amax_dx=None):
+                         colsum=None, amax_dx=None, wc16=None):
     """fp16 backward of out = x_hat @ W_hat^T (+bias) with ONE range-scaled copy of the gradient,
     A16[t,n] = fp16(dY[t,n] * colscale[n] * se_x[t] * sc), read K-major by the dX GEMM and MN-major by the dW GEMM; the
     code operands stay exact and un-transposed (MN-major B), the folded scale vectors are undone per output row:
@@ -80,11 +80,16 @@ def _linear_backward_f16(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulat
     Nout = wc.shape[0]
     if a16 is None:
         if sc is None:
+            bmax = ops.residual_max_for(dY2d)       # dY straight out of an ofq_b200 LayerNorm backward: maxima already known
+            if bmax is not None:
+                sc = ops.scale_from_max(bmax, v1=cs2[0], v2=se2[0], product=True)
+        if sc is None:
             sc = ops.absmax_scale(dY2d, 1, M, Nout, dY2d.stride(0), 0, cs=cs2[0], rs=se2[0], rs_period=period, product=True)
         prep = ops.grad_prep(dY2d, 1, M, Nout, dY2d.stride(0), 0, cs=cs2[0], rs=se2[0], rs_period=period, want_rm=True,
                              want_colsum=True, fmt=FMT, scale4=sc, rm_rowscale=True)
         a16, colsum = prep["rm"], prep["colsum"]
-    wc16 = ops.codes_to_bf16(wc, 1, Nout, K, K, 0, False, FMT)           # [1, Nout, K]
+    if wc16 is None:
+        wc16 = ops.codes_to_bf16(wc, 1, Nout, K, K, 0, False, FMT)       # [1, Nout, K]
     ops.gemm(GEMM_BWD, a16, (Nout, 0, 0, 0), wc16, (K, 0, 0, 0), dxhat, (K, 0, 0), M, K, Nout, b_mn=True,
              accumulate=accumulate_dx, rs=vec(se2[1], period), cs=_scalar(sc), amax=amax_dx)
     if qx16 is None:
@@ -164,20 +169,23 @@ class QLinearFn(torch.autograd.Function):
             qx, qx16 = ops.lsq_quant(x2d, b4, se, PER_ROW, P, 1, lo, hi, act=act, fmt16=FMT)
         else:
             qx = ops.lsq_quant(x2d, b4, se, PER_ROW, P, 1, lo, hi, act=act)
-        wc, colscale, _, colterm, _, inv_cs = ops.statsq_codes(weight, wbits, aft=aft, bias=bias, want_inv=True)
+        w16 = FMT if (F16 and any(ctx.needs_input_grad)) else None
+        wc, colscale, _, colterm, _, inv_cs, *wc16 = ops.statsq_codes(weight, wbits, aft=aft, bias=bias, want_inv=True, fmt16=w16)
+        wc16 = wc16[0] if wc16 else None
         out = torch.empty((M, Nout), dtype=torch.float32, device=x.device)
         ops.gemm(GEMM_I8, qx, (K, 0, 0, 0), wc, (K, 0, 0, 0), out, (Nout, 0, 0), M, Nout, K,
                  rs=vec(se, P), cs=vec(colscale), ct=vec(colterm))
         if link is not None and role == 1:
             link.cs, link.se, link.sc = colscale, se, None
-        ctx.save_for_backward(xc, qx, wc, colscale, inv_cs, se2, b4, aft, qx16)
+        ctx.save_for_backward(xc, qx, wc, colscale, inv_cs, se2, b4, aft, qx16, wc16)
         ctx.cfg = (P, lo, hi, g, bias is not None, act, link, role)
         return out.view(*x.shape[:-1], Nout)
 
     @staticmethod
     def backward(ctx, dY):
-        xc, qx, wc, colscale, inv_cs, se2, b4, aft, qx16 = ctx.saved_tensors
+        xc, qx, wc, colscale, inv_cs, se2, b4, aft, qx16, wc16 = ctx.saved_tensors
         P, lo, hi, g, has_bias, act, link, role = ctx.cfg
+        wkw = {"wc16": wc16} if (F16 and wc16 is not None) else {}
         K = xc.shape[-1]
         x2d = xc.view(-1, K)
         M = x2d.shape[0]
@@ -187,7 +195,7 @@ class QLinearFn(torch.autograd.Function):
             # fc1 of a fused QMLP: fc2's backward already wrote this layer's fp16 gradient operand and colsum(dY); the dY
             # tensor that arrived through autograd is a placeholder
             dW, dbias, _ = _linear_backward_f16(None, qx, wc, (colscale, inv_cs), se2, P, aft, dxhat, False, qx16, sc=link.sc,
-                                                a16=link.a16, colsum=link.colsum)
+                                                a16=link.a16, colsum=link.colsum, **wkw)
             link.a16 = link.colsum = None
         else:
             sc = link.sc if (link is not None and role == 1) else None
@@ -195,7 +203,7 @@ class QLinearFn(torch.autograd.Function):
                          and link.cs.shape[0] == K and K % 4 == 0 and M % link.se.numel() == 0)
             amax = torch.zeros(1, dtype=torch.float32, device=dY.device) if fuse_next else None
             dW, dbias, _ = _linear_backward(dY2d, qx, wc, (colscale, inv_cs), se2, P, aft, dxhat, False, qx16, sc=sc,
-                                            **({"amax_dx": amax} if fuse_next else {}))
+                                            **({"amax_dx": amax} if fuse_next else {}), **wkw)
             if fuse_next:
                 # the producer (fc1) only needs fp16(dx * colscale1[c] * se1[r] * sc) and colsum(dx): written by this pass
                 # |dx| <= |dxhat| * max GELU' (1.13)
@@ -368,7 +376,8 @@ class QKRAttnCoreFn(torch.autograd.Function):
         if f16 is not None:
             qx, qx16 = qx
         # --- V branch (attention.py:179-186)
-        wvc, cs_v, _, ct_v, _, ics_v = ops.statsq_codes(wv, wbits, aft=x_aft, bias=bv, want_inv=True)
+        wvc, cs_v, _, ct_v, _, ics_v, *wv16 = ops.statsq_codes(wv, wbits, aft=x_aft, bias=bv, want_inv=True, fmt16=f16)
+        wv16 = wv16[0] if wv16 else None
         v_out = torch.empty((M, C), dtype=torch.float32, device=dev)
         ops.gemm(GEMM_I8, qx, (C, 0, 0, 0), wvc, (C, 0, 0, 0), v_out, (C, 0, 0), M, C, C,
                  rs=vec(se_x, N), cs=vec(cs_v), ct=vec(ct_v))
@@ -380,7 +389,8 @@ class QKRAttnCoreFn(torch.autograd.Function):
             qv, qv16 = qv
         # --- QK branch: one StatsQ on the per-head product W_q^T W_k (attention.py:190-196)
         wqk = ops.wqk_compose(wq, wk, H)
-        wqkc, cs_qk, _, ct_qk, _, ics_qk = ops.statsq_codes(wqk, wbits, aft=x_aft, want_inv=True)
+        wqkc, cs_qk, _, ct_qk, _, ics_qk, *wqk16 = ops.statsq_codes(wqk, wbits, aft=x_aft, want_inv=True, fmt16=f16)
+        wqk16 = wqk16[0] if wqk16 else None
         qkx = torch.empty((M, H * C), dtype=torch.float32, device=dev)
         ops.gemm(GEMM_I8, qx, (C, 0, 0, 0), wqkc, (C, 0, 0, 0), qkx, (H * C, 0, 0), M, H * C, C,
                  rs=vec(se_x, N), cs=vec(cs_qk), ct=vec(ct_qk))
@@ -415,7 +425,7 @@ class QKRAttnCoreFn(torch.autograd.Function):
         del S
         out = _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C)
         ctx.save_for_backward(xc, wq, wk, x_b4, x_aft, v_b4, v_aft, k_b4, k_aft, qx, sx2, wvc, cs_v, ics_v, v_out, qv, sv2,
-                              wqkc, cs_qk, ics_qk, qkx, qk, sk2, sk2_hn, P, qp, sp2, qx16, qv16, qk16, qp16)
+                              wqkc, cs_qk, ics_qk, qkx, qk, sk2, sk2_hn, P, qp, sp2, qx16, qv16, qk16, qp16, wv16, wqk16)
         ctx.cfg = (B, N, C, H, lo, hi, hiu, scale, g_x, g_v, g_k, g_p, ldS, ldq, bv is not None,
                    attn_bias is not None, link)
         if link is not None:
@@ -425,7 +435,7 @@ class QKRAttnCoreFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dO):
         (xc, wq, wk, x_b4, x_aft, v_b4, v_aft, k_b4, k_aft, qx, sx2, wvc, cs_v, ics_v, v_out, qv, sv2, wqkc, cs_qk, ics_qk,
-         qkx, qk, sk2, sk2_hn, P, qp, sp2, qx16, qv16, qk16, qp16) = ctx.saved_tensors
+         qkx, qk, sk2, sk2_hn, P, qp, sp2, qx16, qv16, qk16, qp16, wv16, wqk16) = ctx.saved_tensors
         B, N, C, H, lo, hi, hiu, scale, g_x, g_v, g_k, g_p, ldS, ldq, has_bv, has_bias, link = ctx.cfg
         se_x, se_v, se_k, se_p, se_k_hn = sx2[0], sv2[0], sk2[0], sp2[0], sk2_hn[0]
         M = B * N
@@ -446,12 +456,12 @@ class QKRAttnCoreFn(torch.autograd.Function):
             _, ds_v, dvb4, dvaft, a16_v = ops.lsq_bwd(dvhat.view(M, C), v_out, v_b4, se_v, PER_COL, 1, 1, lo, hi, g_v,
                                                       out16=(FMT, cs_v, se_x, N, sc_v), want_dx=False)
             dWv, dbv, qx_op = _linear_backward_f16(None, qx, wvc, (cs_v, ics_v), sx2, N, x_aft, dxhat, False, qx16, sc=sc_v,
-                                                   a16=a16_v, colsum=dvb4)
+                                                   a16=a16_v, colsum=dvb4, wc16=wv16)
         else:
             dv_out, ds_v, dvb4, dvaft, *sc_v = ops.lsq_bwd(dvhat.view(M, C), v_out, v_b4, se_v, PER_COL, 1, 1, lo, hi, g_v,
                                                            next_scale=(cs_v, se_x, 1.0, True) if F16 else None)
             dWv, dbv, qx_op = _linear_backward(dv_out, qx, wvc, (cs_v, ics_v), sx2, N, x_aft, dxhat, False, qx16,
-                                               sc=sc_v[0] if sc_v else None)
+                                               sc=sc_v[0] if sc_v else None, **({"wc16": wv16} if F16 else {}))
         # --- softmax + probability quantizer, then the two score GEMMs
         if F16:
             # |dS| = |alpha P (dP - sum P dP)| <= 2 alpha max|dPq|; ONE copy dS16[b,h,n,d] = fp16(dS se_k[h,d] se_x[n] sc)
@@ -505,13 +515,13 @@ class QKRAttnCoreFn(torch.autograd.Function):
             # colsum(d qkx) = sum over rows of the masked gradient = d(move_qkx_b4) (its zero-sum form differs from the plain
             # sum by sum_rows d k_hat, which is analytically zero)
             dWqk, _, _ = _linear_backward_f16(None, qx, wqkc, (cs_qk, ics_qk), sx2, N, x_aft, dxhat, True, qx_op, sc=sc_k,
-                                              a16=a16_k, colsum=dkb4)
+                                              a16=a16_k, colsum=dkb4, wc16=wqk16)
         else:
             dqkx, ds_k, dkb4, _, *sc_k = ops.lsq_bwd(dkhat, qkx, k_b4, se_k, PER_ROW, N, H, lo, hi, g_k, want_aft=False,
                                                      zero_sum=True, next_scale=(cs_qk, se_x, 1.0, True) if F16 else None)
             del dkhat
             dWqk, _, _ = _linear_backward(dqkx, qx, wqkc, (cs_qk, ics_qk), sx2, N, x_aft, dxhat, True, qx_op,
-                                          sc=sc_k[0] if sc_k else None)
+                                          sc=sc_k[0] if sc_k else None, **({"wc16": wqk16} if F16 else {}))
         dwq, dwk = ops.wqk_compose_bwd(dWqk, wq, wk, H)
         # --- shared input quantizer
         dx, ds_x, dxb4, dxaft = ops.lsq_bwd(dxhat, xc.view(M, C), x_b4, se_x, PER_ROW, N, 1, lo, hi, g_x)
