@@ -44,6 +44,7 @@ struct GemmParams {
     int ab_fmt;              // 16-bit kinds: UMMA a/b format field (0 = F16, 1 = BF16)
     int a_mn, b_mn;          // 16-bit kinds: operand is MN-major (rows contiguous, K strided) instead of K-major
     unsigned int* amax;      // optional: max |output| over the whole problem (bits of a non-negative float, atomicMax)
+    int debug_nostore;       // measurement only (OFQ_GEMM_NOSTORE=1): run the epilogue but do not issue the stores
 };
 
 // NA: A tiles per pipeline stage. NA = 2 ("dual-A") loads the bf16 hi and lo planes of a gradient operand together with
@@ -286,7 +287,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) {
+                if (lane == 0 && !p.debug_nostore) {
                     if (p.atomic)
                         tma_reduce_add_5d(&tmC, buf, c.n0 + c0, c.m0 + q * 32, 0, c.b1 * p.c_b1, c.b2 * p.c_b2);
                     else
@@ -532,7 +533,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) {
+                if (lane == 0 && !p.debug_nostore) {
                     if (p.atomic)
                         tma_reduce_add_5d(&tmC, buf, c.n0 + c0, m0 + q * 32, 0, c.b1 * p.c_b1, c.b2 * p.c_b2);
                     else
@@ -732,6 +733,8 @@ extern "C" int ofq_gemm_ex(int kind, const ofq_operand_t* A, const ofq_operand_t
         return OFQ_ERR_ARG;
     }
     p.amax = reinterpret_cast<unsigned int*>(out_absmax);
+    static const int nostore = [] { const char* e = getenv("OFQ_GEMM_NOSTORE"); return e ? atoi(e) : 0; }();
+    p.debug_nostore = nostore;
     if (out_absmax && (p.atomic || splits > 1)) {
         ofq_set_error("ofq_gemm: the output maximum is tracked for plain (non-accumulating, unsplit) stores only");
         return OFQ_ERR_ARG;
@@ -740,13 +743,13 @@ extern "C" int ofq_gemm_ex(int kind, const ofq_operand_t* A, const ofq_operand_t
         ofq_set_error("ofq_gemm: split-K requires an accumulating (pre-zeroed) output");
         return OFQ_ERR_ARG;
     }
-    // CTA pairs (cta_group::2, 256-row tiles) for the long-K / wide-N problems with many row blocks, where the third less
-    // operand traffic per CTA pays (measured on B200, tools/gemm_sweep.py and the per-site bench table: +4..14 % there,
-    // -3..15 % on the 198-row attention batches and the K = 384 layers, which stay on the single-CTA kernel).
+    // CTA pairs (cta_group::2, 256-row tiles) for the wide-N problems with many row blocks, where the third less operand
+    // traffic per CTA pays (measured on B200, tools/gemm_sweep.py and the per-site bench table: +4..14 % at N >= 1024;
+    // the N = 384 layers and the 198-row attention batches are faster on the single-CTA kernel with its 4-stage ring).
     // OFQ_GEMM_PAIR=0 / 2 forces the single-CTA / the pair kernel wherever it is legal (A/B measurements, tests).
     static const int pair_mode = [] { const char* e = getenv("OFQ_GEMM_PAIR"); return e ? atoi(e) : 1; }();
     const bool pair_legal = A->dual_delta == 0 && M > BM;
-    const bool pair = pair_legal && (pair_mode == 2 || (pair_mode == 1 && M >= 4 * BM && ((long long)K * k2 >= 1024 || N >= 1024)));
+    const bool pair = pair_legal && (pair_mode == 2 || (pair_mode == 1 && M >= 4 * BM && N >= 1024));
     // tile width: minimise (number of N tiles) x (per-tile fixed cost + tile width); the fixed cost (pipeline fill,
     // barrier round trips, epilogue start-up) is worth about 128 columns of MMA/epilogue work
     static const int widths[] = {256, 224, 192, 128, 64, 32};
@@ -780,11 +783,16 @@ extern "C" int ofq_gemm_ex(int kind, const ofq_operand_t* A, const ofq_operand_t
         if (kind == OFQ_GEMM_I8) { OFQ_DISPATCH_PAIR(0) } else { OFQ_DISPATCH_PAIR(1) }
 #undef OFQ_DISPATCH_PAIR
     }
+    // long K loops: a 4-stage operand ring with one store staging buffer per epilogue warp (5-10 % faster from K ~ 1024);
+    // short ones (the K = 384 layers) are epilogue-paced and keep two staging buffers and 3 stages
+    const bool deep = (long long)p.kblocks * k2 / splits >= 8;
 #define OFQ_DISPATCH(KIND)                                                   \
     switch (bn) {                                                            \
         case 256: return launch_gemm<KIND, 256, 3>(tmA, tmB, tmC, p, st);    \
-        case 224: return launch_gemm<KIND, 224, 3>(tmA, tmB, tmC, p, st);    \
-        case 192: return launch_gemm<KIND, 192, 3>(tmA, tmB, tmC, p, st);    \
+        case 224: return deep ? launch_gemm<KIND, 224, 4, 1, 1>(tmA, tmB, tmC, p, st)   \
+                              : launch_gemm<KIND, 224, 3>(tmA, tmB, tmC, p, st);         \
+        case 192: return deep ? launch_gemm<KIND, 192, 4, 1, 1>(tmA, tmB, tmC, p, st)   \
+                              : launch_gemm<KIND, 192, 3>(tmA, tmB, tmC, p, st);         \
         case 128: return launch_gemm<KIND, 128, 4>(tmA, tmB, tmC, p, st);    \
         case 64:  return launch_gemm<KIND, 64, 6>(tmA, tmB, tmC, p, st);     \
         default:  return launch_gemm<KIND, 32, 6>(tmA, tmB, tmC, p, st);     \
