@@ -44,7 +44,7 @@ struct GemmParams {
     int ab_fmt;              // 16-bit kinds: UMMA a/b format field (0 = F16, 1 = BF16)
     int a_mn, b_mn;          // 16-bit kinds: operand is MN-major (rows contiguous, K strided) instead of K-major
     unsigned int* amax;      // optional: max |output| over the whole problem (bits of a non-negative float, atomicMax)
-    int debug_nostore;       // measurement only (OFQ_GEMM_NOSTORE=1): run the epilogue but do not issue the stores
+    int debug_nostore;       // measurement only (OFQ_GEMM_NOSTORE bits): 1 = epilogue without stores, 2 = no operand loads, 4 = no epilogue work (single-CTA kernel)
 };
 
 // NA: A tiles per pipeline stage. NA = 2 ("dual-A") loads the bf16 hi and lo planes of a gradient operand together with
@@ -81,6 +81,94 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t, int
     c.it_begin = (int)((long long)total_it * c.split / p.splits);
     c.nit = (int)((long long)total_it * (c.split + 1) / p.splits) - c.it_begin;
     return c;
+}
+
+// ------------------------------------------------------------------------------------------ epilogue (shared)
+// One 32 x 32 chunk of the accumulator: o = acc * rs[m] * cs[n] + rt[m] * ct[n] -> 128B-swizzled staging row `lane`.
+// R1 / TRACK are warp-uniform facts lifted to template parameters: without the rank-1 term the ct vector is never read,
+// without an amax request no maxima are formed; the register buffer is a compile-time array, so the eight float4 groups
+// carry no branches and the scheduler can interleave them (the epilogue is latency-bound: 2 warps per scheduler).
+template <int KIND, bool R1, bool TRACK>
+__device__ __forceinline__ void epi_math(const uint32_t (&r)[32], const float rsv, const float rtv,
+                                         const float* __restrict__ cs_c, const float* __restrict__ ct_c,
+                                         float4* __restrict__ rowp, const int lane, float& omax) {
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 cs4 = *reinterpret_cast<const float4*>(cs_c + 4 * j4);
+        float4 ct4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (R1) ct4 = *reinterpret_cast<const float4*>(ct_c + 4 * j4);
+        const float csv[4] = {cs4.x, cs4.y, cs4.z, cs4.w};
+        const float ctv[4] = {ct4.x, ct4.y, ct4.z, ct4.w};
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const uint32_t raw = r[4 * j4 + e];
+            const float acc = KIND == 0 ? static_cast<float>(static_cast<int32_t>(raw)) : __uint_as_float(raw);
+            o[e] = acc * rsv * csv[e] + rtv * ctv[e];    // R1 == false: rtv = 0 and ctv = 0, the term folds away exactly
+            if (TRACK) omax = fmaxf(omax, fabsf(o[e]));  // rows / columns outside the matrix carry exact zeros
+        }
+        rowp[j4 ^ (lane & 7)] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// All chunks a warp owns of one output tile: TMEM loads one chunk ahead into two compile-time register buffers, scale /
+// offset math, swizzled staging, TMA store (or reduce-add). `have` = the tile has an accumulator at all (nit > 0).
+template <int KIND, int OUT_BUFS>
+__device__ __forceinline__ void epi_tile(const CUtensorMap* tmC, const GemmParams& p, const TileCoord& c, const int m_row0,
+                                         const uint32_t tmem_acc, const bool have, const int nvalid, const int half,
+                                         const bool rank1, const float rsv, const float rtv, const float* cs_s,
+                                         const float* ct_s, uint8_t* stage_base, uint32_t& chunk, const int lane,
+                                         float& omax) {
+    uint32_t r0[32], r1[32];
+    const bool track = p.amax != nullptr;
+    auto fetch = [&](int cc, uint32_t (&rr)[32]) {
+        if (have) {
+            tmem_ld_32x32(tmem_acc + cc * 32, rr);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) rr[j] = 0u;
+        }
+    };
+    auto emit = [&](const uint32_t (&rr)[32], int cc) {
+        const int c0 = cc * 32;
+        uint8_t* buf = stage_base + (chunk % OUT_BUFS) * 4096;
+        if (chunk >= OUT_BUFS) {  // the staging buffer used OUT_BUFS chunks ago must have been read by TMA
+            if (lane == 0) tma_store_wait_read<OUT_BUFS - 1>();
+            __syncwarp();
+        }
+        ++chunk;
+        // row `lane` of the 32x32 fp32 box, 128B-swizzled: 16-byte chunk j lands at j ^ (lane % 8)
+        float4* rowp = reinterpret_cast<float4*>(buf + lane * 128);
+        if (rank1) {
+            if (track) epi_math<KIND, true, true>(rr, rsv, rtv, cs_s + c0, ct_s + c0, rowp, lane, omax);
+            else       epi_math<KIND, true, false>(rr, rsv, rtv, cs_s + c0, ct_s + c0, rowp, lane, omax);
+        } else {
+            if (track) epi_math<KIND, false, true>(rr, rsv, rtv, cs_s + c0, ct_s + c0, rowp, lane, omax);
+            else       epi_math<KIND, false, false>(rr, rsv, rtv, cs_s + c0, ct_s + c0, rowp, lane, omax);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && !(p.debug_nostore & 1)) {
+            if (p.atomic)
+                tma_reduce_add_5d(tmC, buf, c.n0 + c0, m_row0, 0, c.b1 * p.c_b1, c.b2 * p.c_b2);
+            else
+                tma_store_5d(tmC, buf, c.n0 + c0, m_row0, 0, c.b1 * p.c_b1, c.b2 * p.c_b2);
+            tma_store_commit();
+        }
+    };
+    int ci = half;
+    if (ci < nvalid) fetch(ci, r0);
+#pragma unroll 1
+    for (; ci < nvalid; ci += 4) {
+        if (have) { tmem_ld_wait(); tmem_ld_pin(r0); }        // chunk ci is in r0
+        if (ci + 2 < nvalid) fetch(ci + 2, r1);               // prefetch the next owned chunk
+        emit(r0, ci);
+        if (ci + 2 < nvalid) {
+            if (have) { tmem_ld_wait(); tmem_ld_pin(r1); }
+            if (ci + 4 < nvalid) fetch(ci + 4, r0);
+            emit(r1, ci + 2);
+        }
+    }
 }
 
 // Persistent, warp-specialised: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The smem ring runs
@@ -152,6 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int k2i = g / p.kblocks, kb = g % p.kblocks;
                     uint8_t* sa = smem + s * STAGE_BYTES;
                     uint8_t* sb = sa + NA * A_BYTES;
+                    if (p.debug_nostore & 2) { mbar_arrive(&full_bar[s]); continue; }   // probe: no operand loads
                     mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
                     if (KIND != 0 && p.a_mn) {   // MN-major: 64-row x 64-k boxes, one 8 KB swizzle-atom column each
                         for (int j = 0; j < BM / 64; ++j)
@@ -245,56 +334,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t tmem_acc = tmem_base + as * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
             // number of chunks this warp owns inside the valid column range (warp-uniform)
             int nvalid = (min(BN, p.N - c.n0) + 31) / 32;
-            uint32_t r[2][32];
-            int ci = half;
-            if (ci < nvalid && c.nit > 0) tmem_ld_32x32(tmem_acc + ci * 32, r[0]);
-            int buf_sel = 0;
-#pragma unroll 1
-            for (; ci < nvalid; ci += 2, buf_sel ^= 1) {
-                const int c0 = ci * 32;
-                if (c.nit > 0) {
-                    tmem_ld_wait();                                          // chunk ci is in r[buf_sel]
-                    if (buf_sel == 0) tmem_ld_pin(r[0]); else tmem_ld_pin(r[1]);
-                    if (ci + 2 < nvalid) {                                   // prefetch the next owned chunk
-                        if (buf_sel == 0) tmem_ld_32x32(tmem_acc + (ci + 2) * 32, r[1]);
-                        else              tmem_ld_32x32(tmem_acc + (ci + 2) * 32, r[0]);
-                    }
-                }
-                uint8_t* buf = stage_base + (chunk % OUT_BUFS) * 4096;
-                if (chunk >= OUT_BUFS) {  // the staging buffer used OUT_BUFS chunks ago must have been read by TMA
-                    if (lane == 0) tma_store_wait_read<OUT_BUFS - 1>();
-                    __syncwarp();
-                }
-                ++chunk;
-                // row `lane` of the 32x32 fp32 box, 128B-swizzled: 16-byte chunk j lands at j ^ (lane % 8)
-                float4* rowp = reinterpret_cast<float4*>(buf + lane * 128);
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 cs4 = *reinterpret_cast<const float4*>(cs_s + c0 + 4 * j4);
-                    const float4 ct4 = *reinterpret_cast<const float4*>(ct_s + c0 + 4 * j4);
-                    const float csv[4] = {cs4.x, cs4.y, cs4.z, cs4.w};
-                    const float ctv[4] = {ct4.x, ct4.y, ct4.z, ct4.w};
-                    float o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int j = 4 * j4 + e;
-                        const uint32_t raw = c.nit > 0 ? (buf_sel == 0 ? r[0][j] : r[1][j]) : 0u;
-                        const float acc = KIND == 0 ? static_cast<float>(static_cast<int32_t>(raw)) : __uint_as_float(raw);
-                        o[e] = acc * rsv * csv[e] + rtv * ctv[e];
-                        omax = fmaxf(omax, fabsf(o[e]));    // rows / columns outside the matrix carry exact zeros
-                    }
-                    rowp[j4 ^ (lane & 7)] = make_float4(o[0], o[1], o[2], o[3]);
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0 && !p.debug_nostore) {
-                    if (p.atomic)
-                        tma_reduce_add_5d(&tmC, buf, c.n0 + c0, c.m0 + q * 32, 0, c.b1 * p.c_b1, c.b2 * p.c_b2);
-                    else
-                        tma_store_5d(&tmC, buf, c.n0 + c0, c.m0 + q * 32, 0, c.b1 * p.c_b1, c.b2 * p.c_b2);
-                    tma_store_commit();
-                }
-            }
+            if (p.debug_nostore & 4) nvalid = 0;                               // probe: no epilogue work at all
+            epi_tile<KIND, OUT_BUFS>(&tmC, p, c, c.m0 + q * 32, tmem_acc, c.nit > 0, nvalid, half, rank1, rsv, rtv, cs_s, ct_s,
+                                     stage_base, chunk, lane, omax);
             // all TMEM reads of this tile are complete: hand the accumulator stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -492,55 +534,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t tmem_acc = tmem_base + as * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
             int nvalid = (min(BN, p.N - c.n0) + 31) / 32;
             if (m0 >= p.M) nvalid = 0;                 // this CTA's half of the pair tile lies entirely below the matrix
-            uint32_t r[2][32];
-            int ci = half;
-            if (ci < nvalid && c.nit > 0) tmem_ld_32x32(tmem_acc + ci * 32, r[0]);
-            int buf_sel = 0;
-#pragma unroll 1
-            for (; ci < nvalid; ci += 2, buf_sel ^= 1) {
-                const int c0 = ci * 32;
-                if (c.nit > 0) {
-                    tmem_ld_wait();
-                    if (buf_sel == 0) tmem_ld_pin(r[0]); else tmem_ld_pin(r[1]);
-                    if (ci + 2 < nvalid) {
-                        if (buf_sel == 0) tmem_ld_32x32(tmem_acc + (ci + 2) * 32, r[1]);
-                        else              tmem_ld_32x32(tmem_acc + (ci + 2) * 32, r[0]);
-                    }
-                }
-                uint8_t* buf = stage_base + (chunk % OUT_BUFS) * 4096;
-                if (chunk >= OUT_BUFS) {
-                    if (lane == 0) tma_store_wait_read<OUT_BUFS - 1>();
-                    __syncwarp();
-                }
-                ++chunk;
-                float4* rowp = reinterpret_cast<float4*>(buf + lane * 128);
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 cs4 = *reinterpret_cast<const float4*>(cs_s + c0 + 4 * j4);
-                    const float4 ct4 = *reinterpret_cast<const float4*>(ct_s + c0 + 4 * j4);
-                    const float csv[4] = {cs4.x, cs4.y, cs4.z, cs4.w};
-                    const float ctv[4] = {ct4.x, ct4.y, ct4.z, ct4.w};
-                    float o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int j = 4 * j4 + e;
-                        const uint32_t raw = c.nit > 0 ? (buf_sel == 0 ? r[0][j] : r[1][j]) : 0u;
-                        const float acc = KIND == 0 ? static_cast<float>(static_cast<int32_t>(raw)) : __uint_as_float(raw);
-                        o[e] = acc * rsv * csv[e] + rtv * ctv[e];
-                        omax = fmaxf(omax, fabsf(o[e]));    // rows / columns outside the matrix carry exact zeros
-                    }
-                    rowp[j4 ^ (lane & 7)] = make_float4(o[0], o[1], o[2], o[3]);
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0 && !p.debug_nostore) {
-                    if (p.atomic)
-                        tma_reduce_add_5d(&tmC, buf, c.n0 + c0, m0 + q * 32, 0, c.b1 * p.c_b1, c.b2 * p.c_b2);
-                    else
-                        tma_store_5d(&tmC, buf, c.n0 + c0, m0 + q * 32, 0, c.b1 * p.c_b1, c.b2 * p.c_b2);
-                    tma_store_commit();
-                }
-            }
+            epi_tile<KIND, OUT_BUFS>(&tmC, p, c, m0 + q * 32, tmem_acc, c.nit > 0, nvalid, half, rank1, rsv, rtv, cs_s, ct_s,
+                                     stage_base, chunk, lane, omax);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[as]), 0));

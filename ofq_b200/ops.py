@@ -6,6 +6,7 @@ sm_100a kernel on torch's current stream.  No function here computes anything it
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -39,6 +40,55 @@ def _call(family: str, nkernels: int, alg_bytes: float, alg_flops: float, fn, *a
     e1.record()
     check(rc)
     PROFILE.append((family, e0, e1, alg_bytes, alg_flops, tag))
+
+
+# ------------------------------------------------------------------------------------------------ side stream
+# Weight-gradient work (the split-K dW GEMMs, the W_qk product backward) does not feed the activation-gradient chain of a
+# layer: inside one autograd backward it is queued on a second stream, where the tensor-bound GEMM overlaps the HBM-bound
+# STE / LayerNorm passes of the main chain, and joined before the backward returns (so autograd, DDP and the optimizer
+# only ever see completed gradients on the current stream). Works the same under CUDA-graph capture (fork / join edges).
+SIDE_ENABLED = os.environ.get("OFQ_SIDE_STREAM", "1") != "0"
+_SIDE = {}
+_SIDE_KEEP = []
+
+
+class side_stream:
+    """`with ops.side_stream(t0, t1, ...):` launches issued inside run on the side stream after everything already queued
+    on the current stream; the tensors named are kept alive until `side_join()` (the caching allocator must not hand
+    their storage to later work of the current stream while the side stream still reads it)."""
+
+    def __init__(self, *keep):
+        self.keep = keep
+        self.ctx = None
+
+    def __enter__(self):
+        if not SIDE_ENABLED:
+            return self
+        cur = torch.cuda.current_stream()
+        side = _SIDE.get(cur.device)
+        if side is None:
+            # higher priority: when both become runnable the one-CTA-per-SM GEMM is placed first and the streaming
+            # kernel of the main chain fills the rest of each SM (the other order would serialise them)
+            side = _SIDE[cur.device] = torch.cuda.Stream(device=cur.device, priority=int(os.environ.get("OFQ_SIDE_PRIO", "-1")))
+        side.wait_stream(cur)
+        _SIDE_KEEP.append((cur, side, self.keep))
+        self.ctx = torch.cuda.stream(side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def side_join() -> None:
+    """The current stream waits for everything forked with `side_stream` since the last join."""
+    if not _SIDE_KEEP:
+        return
+    cur, side, _ = _SIDE_KEEP[-1]
+    cur.wait_stream(side)
+    _SIDE_KEEP.clear()
 
 
 def _cuda(*ts):
@@ -375,11 +425,10 @@ def wqk_compose(wq: torch.Tensor, wk: torch.Tensor, H: int) -> torch.Tensor:
     return out
 
 
-def wqk_compose_bwd(dwqk: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, H: int):
+def wqk_compose_bwd(dwqk: torch.Tensor, wq: torch.Tensor, wk: torch.Tensor, H: int, out=None):
     Cc = wq.shape[1]
     hd = wq.shape[0] // H
-    dwq = torch.empty_like(wq)
-    dwk = torch.empty_like(wk)
+    dwq, dwk = out if out is not None else (torch.empty_like(wq), torch.empty_like(wk))
     _call("wqk_compose_bwd", 1, 4.0 * (4 * H * hd * Cc + 2 * H * Cc * Cc), 4.0 * H * hd * Cc * Cc,
           _lib.load().ofq_wqk_compose_bwd, dwqk.data_ptr(), wq.data_ptr(), wk.data_ptr(), H, hd, Cc, dwq.data_ptr(),
           dwk.data_ptr(), _st())

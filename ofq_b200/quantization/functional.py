@@ -97,8 +97,10 @@ def _linear_backward_f16(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulat
     dW = torch.zeros((Nout, K), dtype=torch.float32, device=a16.device)
     tiles = ((Nout + 127) // 128) * ((K + 127) // 128)
     splits = _splits_for(tiles, (M + 63) // 64)
-    ops.gemm(GEMM_BWD, a16, (Nout, 0, 0, 0), qx16, (K, 0, 0, 0), dW, (K, 0, 0), Nout, K, M, a_mn=True, b_mn=True,
-             splits=splits, accumulate=True, rs=vec(cs2[1]), cs=_scalar(sc), rt=vec(colsum), ct=vec(x_aft))
+    # the weight gradient is off the activation-gradient chain: side stream, joined before the backward returns
+    with ops.side_stream(a16, qx16, dW, cs2, sc, colsum, x_aft):
+        ops.gemm(GEMM_BWD, a16, (Nout, 0, 0, 0), qx16, (K, 0, 0, 0), dW, (K, 0, 0), Nout, K, M, a_mn=True, b_mn=True,
+                 splits=splits, accumulate=True, rs=vec(cs2[1]), cs=_scalar(sc), rt=vec(colsum), ct=vec(x_aft))
     return dW, colsum, qx16
 
 
@@ -213,6 +215,7 @@ class QLinearFn(torch.autograd.Function):
                                                           want_colsum=True)
                 link.sc, link.a16, link.colsum = sc1, a16, csum
                 dx = torch.empty_like(xc)         # placeholder: never read (see MlpLink.fuse)
+                ops.side_join()
                 return dx, dW, (dbias if has_bias else None), db4, daft, ds, None, None, None, None, None, None
         nxt = None
         if F16 and link is not None and role == 2 and link.cs is not None and link.cs.shape[0] == K:
@@ -220,6 +223,7 @@ class QLinearFn(torch.autograd.Function):
         dx, ds, db4, daft, *scn = ops.lsq_bwd(dxhat, x2d, b4, se2[0], PER_ROW, P, 1, lo, hi, g, act=act, next_scale=nxt)
         if nxt is not None:
             link.sc = scn[0]
+        ops.side_join()
         return dx.view_as(xc), dW, (dbias if has_bias else None), db4, daft, ds, None, None, None, None, None, None
 
 
@@ -522,12 +526,15 @@ class QKRAttnCoreFn(torch.autograd.Function):
             del dkhat
             dWqk, _, _ = _linear_backward(dqkx, qx, wqkc, (cs_qk, ics_qk), sx2, N, x_aft, dxhat, True, qx_op,
                                           sc=sc_k[0] if sc_k else None, **({"wc16": wqk16} if F16 else {}))
-        dwq, dwk = ops.wqk_compose_bwd(dWqk, wq, wk, H)
+        dwq, dwk = torch.empty_like(wq), torch.empty_like(wk)
+        with ops.side_stream(dWqk, wq, wk, dwq, dwk):      # ordered after the dW_qk GEMM on the side stream
+            ops.wqk_compose_bwd(dWqk, wq, wk, H, out=(dwq, dwk))
         # --- shared input quantizer
         dx, ds_x, dxb4, dxaft = ops.lsq_bwd(dxhat, xc.view(M, C), x_b4, se_x, PER_ROW, N, 1, lo, hi, g_x)
         dbias = None
         if has_bias:
             dbias = dS32[..., :N].reshape(B, H, N, N).sum(0)
+        ops.side_join()
         return (dx.view(B, N, C), dwq, dwk, dWv, (dbv if has_bv else None), dxb4, dxaft, ds_x, dvb4, dvaft, ds_v,
                 dkb4, dkaft, ds_k, ds_p, dbias, None, None, None, None, None, None)
 

@@ -2,6 +2,9 @@
 usage: python tools/summarize_launches.py gpurun_out/r01_launches.csv profiles/r01_launches_summary.md [profiles/traffic.json]"""
 import collections, csv, json, re, sys
 
+one_step = "--one-step" in sys.argv
+if one_step:
+    sys.argv.remove("--one-step")
 src, dst = sys.argv[1], sys.argv[2]
 lines = [l for l in open(src) if not l.startswith("==")]
 cur = {}
@@ -25,6 +28,12 @@ def family(k):
     m = re.search(r"(?:void )?([\w:]+)", k)
     return "torch " + (m.group(1) if m else k)[:50]
 
+if one_step:   # keep exactly one QAT step: the launches between the last AdamW launch of one step and of the next
+    keys = sorted(cur, key=lambda ik: int(ik[0]))
+    opt = [i for i, ik in enumerate(keys) if "adamw" in ik[1]]
+    ends = [i for j, i in enumerate(opt) if j + 1 == len(opt) or opt[j + 1] - i > 50]
+    assert len(ends) >= 2, "the capture does not hold a whole step"
+    cur = {ik: cur[ik] for ik in keys[ends[-2] + 1: ends[-1] + 1]}
 per = collections.defaultdict(lambda: dict(n=0, ns=0.0, rd=0.0, wr=0.0))
 for (_, k), d in cur.items():
     p = per[family(k)]
@@ -40,12 +49,12 @@ with open(dst, "w") as f:
     f.write(f"{len(cur)} launches, {tot / 1e6:.2f} ms of kernel time (cold-cache, serialised under ncu: compare SHARES, not absolutes).\n")
     f.write(f"ofq_b200 kernels: {100 * ofq / tot:.1f} % of the captured kernel time; the rest is torch glue (LayerNorm, GELU, residual adds, fills, heads, patch embed).\n\n")
     f.write("| kernel family | launches | total ms | share % | avg us | DRAM MB / launch (read+write) |\n|---|---:|---:|---:|---:|---:|\n")
-    for k, p in rows[:40]:
+    for k, p in rows[:60]:
         f.write(f"| {k} | {p['n']} | {p['ns'] / 1e6:.3f} | {100 * p['ns'] / tot:.2f} | {p['ns'] / p['n'] / 1e3:.1f} | {(p['rd'] + p['wr']) / p['n'] / 1e6:.2f} |\n")
-print(open(dst).read()[:3500])
+print(open(dst).read()[:7000])
 if len(sys.argv) > 3:
-    fam_map = {"gemm_bf16": "gemm_tc_kernel<16-bit", "gemm_f16": "gemm_tc_kernel<16-bit", "absmax_scale": "ofq absmax_scale_kernel", "gemm_i8": "gemm_tc_kernel<i8", "lsq_bwd": "ofq lsq_bwd_kernel", "lsq_quant": "ofq lsq_quant_kernel",
-               "grad_prep": "ofq grad_prep_kernel", "softmax_quant": "ofq softmax_quant_kernel", "softmax_quant_bwd": "ofq softmax_quant_bwd_kernel",
+    fam_map = {"gemm_bf16": "gemm_tc_kernel<16-bit", "gemm_f16": "gemm_tc_kernel<16-bit", "absmax_scale": "ofq absmax_scale_kernel", "gemm_i8": "gemm_tc_kernel<i8", "lsq_bwd": "ofq lsq_bwd_stream_kernel", "lsq_quant": "ofq lsq_quant_vec_kernel",
+               "grad_prep": "ofq grad_prep_stream_kernel", "softmax_quant": "ofq softmax_quant_vec_kernel", "softmax_quant_bwd": "ofq softmax_quant_bwd_vec_kernel", "layernorm_bwd": "ofq layernorm_bwd_kernel", "layernorm_fwd": "ofq layernorm_fwd_kernel",
                "codes_to_bf16": "ofq codes_convert_kernel"}
     out = {}
     for name, pat in fam_map.items():
