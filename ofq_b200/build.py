@@ -21,7 +21,7 @@ LIB = ROOT / "libofq_b200.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-          "--expt-relaxed-constexpr", "-I", str(INCLUDE), "-I", str(CSRC)]
+          "--expt-relaxed-constexpr", "-I", str(INCLUDE), "-I", str(CSRC)] + os.environ.get("OFQ_NVCC_FLAGS", "").split()
 
 
 def sources() -> list[Path]:

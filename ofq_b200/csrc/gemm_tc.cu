@@ -12,6 +12,7 @@
 // read the accumulator back with tcgen05.ld and apply the rank-1 scale/offset epilogue straight to HBM.
 // Quantizer scales never touch the operands: per-row (token) scales, per-column (StatsQ channel) scales
 // and the affine "move_aft" shift all live in the epilogue vectors, so the MMA itself is exact.
+#include <cstdio>
 #include <cstdlib>
 #include "ofq_b200.h"
 #include "ptx.cuh"
@@ -24,10 +25,32 @@ constexpr int KBYTES = 128;      // one 128B swizzle atom of K per stage
 constexpr int EPI_WARPS = 8;      // two warps per TMEM lane quarter, interleaved over the 32-column chunks
 constexpr int NUM_THREADS = 64 + EPI_WARPS * 32; // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 
+// Division / remainder of a non-negative int (< 2^31) by a run-time constant as multiply-high + shift: the tile decode and
+// the wrapped epilogue-vector indices sit on the serial path of every tile, where a hardware-emulated integer division
+// costs ~100 dependent cycles each.  q = (umulhi(n, mul) + n) >> shr with mul = floor(2^32 (2^shr - d) / d) + 1.
+struct FastDiv {
+    uint32_t d, mul, shr;
+    __device__ __forceinline__ int div(int n) const { return (int)((__umulhi((uint32_t)n, mul) + (uint32_t)n) >> shr); }
+    __device__ __forceinline__ int mod(int n) const { return n - div(n) * (int)d; }
+};
+static FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    f.d = (uint32_t)(d < 1 ? 1 : d);
+    uint32_t s = 0;
+    while (s < 31 && (1u << s) < f.d) ++s;
+    f.shr = s;
+    f.mul = (uint32_t)((((unsigned long long)1 << 32) * (((unsigned long long)1 << s) - f.d)) / f.d + 1);
+    return f;
+}
+
+// 32-column chunks of a BN-wide tile owned by one epilogue warp (the two warps of a lane quarter take even / odd chunks)
+constexpr int epi_nch(int bn) { return (bn / 32 + 1) / 2; }
+
 struct VecRef {
     const float* p;   // nullptr -> 1.0
     int period;       // rs / rt / cs: index = i % period (ct is never wrapped)
     long long bs1, bs2;
+    FastDiv fd;       // of `period`
 };
 
 struct GemmParams {
@@ -44,6 +67,7 @@ struct GemmParams {
     int ab_fmt;              // 16-bit kinds: UMMA a/b format field (0 = F16, 1 = BF16)
     int a_mn, b_mn;          // 16-bit kinds: operand is MN-major (rows contiguous, K strided) instead of K-major
     unsigned int* amax;      // optional: max |output| over the whole problem (bits of a non-negative float, atomicMax)
+    FastDiv fd_ntiles, fd_mtiles, fd_nbatch, fd_nb1, fd_splits, fd_kblocks, fd_ak2mod, fd_bk2mod;   // set by the launchers
     int debug_nostore;       // measurement only (OFQ_GEMM_NOSTORE bits): 1 = epilogue without stores, 2 = no operand loads, 4 = no epilogue work (single-CTA kernel)
 };
 
@@ -57,8 +81,8 @@ struct SmemLayout {
     static constexpr uint32_t STAGE_BYTES = NA * A_BYTES + B_BYTES;
     static constexpr uint32_t OUT_OFF = STAGES * STAGE_BYTES;          // 4 warps x OUT_BUFS x (32 x 128 B), swizzled
     static constexpr uint32_t OUT_BYTES = EPI_WARPS * OUT_BUFS * 4096;
-    static constexpr uint32_t VEC_OFF = OUT_OFF + OUT_BYTES;            // 2 x {cs[BN], ct[BN]} (double buffered)
-    static constexpr uint32_t BAR_OFF = VEC_OFF + 2 * 2 * BN * 4;
+    static constexpr uint32_t VEC_OFF = OUT_OFF + OUT_BYTES;            // per epilogue warp: {cs[32], ct[32]} per owned chunk
+    static constexpr uint32_t BAR_OFF = VEC_OFF + EPI_WARPS * epi_nch(BN) * 64 * 4;
     static constexpr uint32_t TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
     static constexpr size_t DYN_BYTES = TOTAL + 1024;                   // slack for 1024 B alignment
 };
@@ -70,18 +94,32 @@ struct TileCoord {
 // tile index -> coordinates; consecutive indices share the A (row) block so that it is re-read from L2
 __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t, int BN_, int mtiles, int ntiles) {
     TileCoord c;
-    const int nb = t % ntiles; t /= ntiles;
-    const int mb = t % mtiles; t /= mtiles;
-    const int nbatch = p.nb1 * p.nb2;
-    const int z = t % nbatch;
-    c.split = t / nbatch;
-    c.b1 = z % p.nb1; c.b2 = z / p.nb1;
+    int q = p.fd_ntiles.div(t);
+    const int nb = t - q * ntiles; t = q;
+    q = p.fd_mtiles.div(t);
+    const int mb = t - q * mtiles; t = q;
+    c.split = p.fd_nbatch.div(t);
+    const int z = t - c.split * (p.nb1 * p.nb2);
+    c.b2 = p.fd_nb1.div(z); c.b1 = z - c.b2 * p.nb1;
     c.m0 = mb * BM; c.n0 = nb * BN_;
-    const int total_it = p.k2 * p.kblocks;
-    c.it_begin = (int)((long long)total_it * c.split / p.splits);
-    c.nit = (int)((long long)total_it * (c.split + 1) / p.splits) - c.it_begin;
+    const int total_it = p.k2 * p.kblocks;            // total_it * (splits + 1) < 2^31 (checked on the host)
+    c.it_begin = p.fd_splits.div(total_it * c.split);
+    c.nit = p.fd_splits.div(total_it * (c.split + 1)) - c.it_begin;
     return c;
 }
+
+// OFQ_GEMM_TRACE (measurement builds only, OFQ_NVCC_FLAGS=-DOFQ_GEMM_TRACE): per-phase clock64 totals of the first epilogue
+// warp and the MMA thread of CTA 0, printed at kernel exit.
+#ifdef OFQ_GEMM_TRACE
+#define TR_DECL(n) long long n = 0
+#define TR_T0(t) const long long t = clock64()
+#define TR_ADD(n, t) n += clock64() - t
+#else
+#define TR_DECL(n)
+#define TR_T0(t)
+#define TR_ADD(n, t)
+#endif
+struct EpiTrace { long long ldwait, rdwait, math, fence; };
 
 // ------------------------------------------------------------------------------------------ epilogue (shared)
 // One 32 x 32 chunk of the accumulator: o = acc * rs[m] * cs[n] + rt[m] * ct[n] -> 128B-swizzled staging row `lane`.
@@ -92,23 +130,82 @@ template <int KIND, bool R1, bool TRACK>
 __device__ __forceinline__ void epi_math(const uint32_t (&r)[32], const float rsv, const float rtv,
                                          const float* __restrict__ cs_c, const float* __restrict__ ct_c,
                                          float4* __restrict__ rowp, const int lane, float& omax) {
+    // two columns per instruction (FMUL2 / FFMA2): same roundings as fmaf(acc * rs, cs, rt * ct) per element.
+    // Shared-memory traffic goes through volatile asm without memory clobbers, in two batches of four 16-byte groups: all
+    // vector loads of a batch are issued before its first staging store. As plain C++ accesses every store would pin the
+    // following loads behind it (neither nvvm nor ptxas can prove that the staging buffer and the vectors do not alias),
+    // which serialised the eight groups on the shared-memory latency. The fence.proxy.async after the chunk is a volatile
+    // asm with a memory clobber and stays behind these stores.
+    const float2 rs2 = make_float2(rsv, rsv), rt2 = make_float2(rtv, rtv);
 #pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 cs4 = *reinterpret_cast<const float4*>(cs_c + 4 * j4);
-        float4 ct4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (R1) ct4 = *reinterpret_cast<const float4*>(ct_c + 4 * j4);
-        const float csv[4] = {cs4.x, cs4.y, cs4.z, cs4.w};
-        const float ctv[4] = {ct4.x, ct4.y, ct4.z, ct4.w};
-        float o[4];
+    for (int b = 0; b < 2; ++b) {
+        float4 cs4[4], ct4[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const uint32_t raw = r[4 * j4 + e];
-            const float acc = KIND == 0 ? static_cast<float>(static_cast<int32_t>(raw)) : __uint_as_float(raw);
-            o[e] = acc * rsv * csv[e] + rtv * ctv[e];    // R1 == false: rtv = 0 and ctv = 0, the term folds away exactly
-            if (TRACK) omax = fmaxf(omax, fabsf(o[e]));  // rows / columns outside the matrix carry exact zeros
+        for (int g = 0; g < 4; ++g) {
+            cs4[g] = ld_shared_v4_nc(cs_c + 16 * b + 4 * g);
+            if (R1) ct4[g] = ld_shared_v4_nc(ct_c + 16 * b + 4 * g);
         }
-        rowp[j4 ^ (lane & 7)] = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int j4 = 4 * b + g;
+            float2 o[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t ra = r[4 * j4 + 2 * h], rb = r[4 * j4 + 2 * h + 1];
+                const float2 acc = KIND == 0 ? make_float2(static_cast<float>(static_cast<int32_t>(ra)), static_cast<float>(static_cast<int32_t>(rb)))
+                                             : make_float2(__uint_as_float(ra), __uint_as_float(rb));
+                const float2 cs2 = h == 0 ? make_float2(cs4[g].x, cs4[g].y) : make_float2(cs4[g].z, cs4[g].w);
+                const float2 t = __fmul2_rn(acc, rs2);
+                if (R1) {
+                    const float2 ct2 = h == 0 ? make_float2(ct4[g].x, ct4[g].y) : make_float2(ct4[g].z, ct4[g].w);
+                    o[h] = __ffma2_rn(t, cs2, __fmul2_rn(rt2, ct2));
+                } else {
+                    o[h] = __fmul2_rn(t, cs2);
+                }
+                if (TRACK) omax = fmaxf(omax, fmaxf(fabsf(o[h].x), fabsf(o[h].y)));   // rows / columns outside the matrix carry exact zeros
+            }
+            st_shared_v4_nc(rowp + (j4 ^ (lane & 7)), o[0].x, o[0].y, o[1].x, o[1].y);
+        }
     }
+}
+
+// The epilogue vectors of one tile as per-lane registers: lane l holds cs / ct of column l of every chunk its warp owns,
+// plus rs / rt of its row. Loaded one tile ahead (the global-load latency hides behind the chunk work of the current tile)
+// and published to a warp-private staging area: no CTA-wide barrier, no coupling between the epilogue warps.
+template <int NCH>
+struct EpiVecs {
+    float cs[NCH], ct[NCH];
+    float rsv, rtv;
+    bool rank1;
+};
+template <int NCH>
+__device__ __forceinline__ void epi_vec_load(const GemmParams& p, const TileCoord& c, const int m, const int half,
+                                             const int lane, EpiVecs<NCH>& v) {
+    v.rank1 = p.has_rank1 && c.split == 0;
+    const long long cs_off = (long long)c.b1 * p.cs.bs1 + (long long)c.b2 * p.cs.bs2;
+    const long long ct_off = (long long)c.b1 * p.ct.bs1 + (long long)c.b2 * p.ct.bs2;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        const int n = c.n0 + (half + 2 * k) * 32 + lane;
+        const bool ok = n < p.N;
+        v.cs[k] = ok ? (p.cs.p ? __ldg(p.cs.p + cs_off + p.cs.fd.mod(n)) : 1.0f) : 0.f;
+        v.ct[k] = (ok && v.rank1) ? (p.ct.p ? __ldg(p.ct.p + ct_off + n) : 1.0f) : 0.f;
+    }
+    const bool row_ok = m < p.M;
+    const long long rs_off = (long long)c.b1 * p.rs.bs1 + (long long)c.b2 * p.rs.bs2;
+    const long long rt_off = (long long)c.b1 * p.rt.bs1 + (long long)c.b2 * p.rt.bs2;
+    v.rsv = row_ok ? (p.rs.p ? __ldg(p.rs.p + rs_off + p.rs.fd.mod(m)) : 1.0f) : 0.f;
+    v.rtv = (row_ok && v.rank1) ? (p.rt.p ? __ldg(p.rt.p + rt_off + p.rt.fd.mod(m)) : 1.0f) : 0.f;
+}
+template <int NCH>
+__device__ __forceinline__ void epi_vec_publish(const EpiVecs<NCH>& v, float* myvec, const int lane) {
+    __syncwarp();                      // every lane is done reading the previous tile's vectors
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        myvec[k * 64 + lane] = v.cs[k];
+        myvec[k * 64 + 32 + lane] = v.ct[k];
+    }
+    __syncwarp();
 }
 
 // All chunks a warp owns of one output tile: TMEM loads one chunk ahead into two compile-time register buffers, scale /
@@ -116,9 +213,9 @@ __device__ __forceinline__ void epi_math(const uint32_t (&r)[32], const float rs
 template <int KIND, int OUT_BUFS>
 __device__ __forceinline__ void epi_tile(const CUtensorMap* tmC, const GemmParams& p, const TileCoord& c, const int m_row0,
                                          const uint32_t tmem_acc, const bool have, const int nvalid, const int half,
-                                         const bool rank1, const float rsv, const float rtv, const float* cs_s,
-                                         const float* ct_s, uint8_t* stage_base, uint32_t& chunk, const int lane,
-                                         float& omax) {
+                                         const bool rank1, const float rsv, const float rtv, const float* myvec,
+                                         uint8_t* stage_base, uint32_t& chunk, const int lane,
+                                         float& omax, EpiTrace* tr = nullptr) {
     uint32_t r0[32], r1[32];
     const bool track = p.amax != nullptr;
     auto fetch = [&](int cc, uint32_t (&rr)[32]) {
@@ -131,21 +228,32 @@ __device__ __forceinline__ void epi_tile(const CUtensorMap* tmC, const GemmParam
     };
     auto emit = [&](const uint32_t (&rr)[32], int cc) {
         const int c0 = cc * 32;
+        const float* cs_c = myvec + ((cc - half) >> 1) * 64;       // {cs[32], ct[32]} of this owned chunk
+        const float* ct_c = cs_c + 32;
         uint8_t* buf = stage_base + (chunk % OUT_BUFS) * 4096;
+        TR_T0(t_a);
         if (chunk >= OUT_BUFS) {  // the staging buffer used OUT_BUFS chunks ago must have been read by TMA
             if (lane == 0) tma_store_wait_read<OUT_BUFS - 1>();
             __syncwarp();
         }
         ++chunk;
+#ifdef OFQ_GEMM_TRACE
+        if (tr) TR_ADD(tr->rdwait, t_a);
+#endif
+        TR_T0(t_b);
         // row `lane` of the 32x32 fp32 box, 128B-swizzled: 16-byte chunk j lands at j ^ (lane % 8)
         float4* rowp = reinterpret_cast<float4*>(buf + lane * 128);
         if (rank1) {
-            if (track) epi_math<KIND, true, true>(rr, rsv, rtv, cs_s + c0, ct_s + c0, rowp, lane, omax);
-            else       epi_math<KIND, true, false>(rr, rsv, rtv, cs_s + c0, ct_s + c0, rowp, lane, omax);
+            if (track) epi_math<KIND, true, true>(rr, rsv, rtv, cs_c, ct_c, rowp, lane, omax);
+            else       epi_math<KIND, true, false>(rr, rsv, rtv, cs_c, ct_c, rowp, lane, omax);
         } else {
-            if (track) epi_math<KIND, false, true>(rr, rsv, rtv, cs_s + c0, ct_s + c0, rowp, lane, omax);
-            else       epi_math<KIND, false, false>(rr, rsv, rtv, cs_s + c0, ct_s + c0, rowp, lane, omax);
+            if (track) epi_math<KIND, false, true>(rr, rsv, rtv, cs_c, ct_c, rowp, lane, omax);
+            else       epi_math<KIND, false, false>(rr, rsv, rtv, cs_c, ct_c, rowp, lane, omax);
         }
+#ifdef OFQ_GEMM_TRACE
+        if (tr) TR_ADD(tr->math, t_b);
+#endif
+        TR_T0(t_c);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0 && !(p.debug_nostore & 1)) {
@@ -155,16 +263,27 @@ __device__ __forceinline__ void epi_tile(const CUtensorMap* tmC, const GemmParam
                 tma_store_5d(tmC, buf, c.n0 + c0, m_row0, 0, c.b1 * p.c_b1, c.b2 * p.c_b2);
             tma_store_commit();
         }
+#ifdef OFQ_GEMM_TRACE
+        if (tr) TR_ADD(tr->fence, t_c);
+#endif
     };
     int ci = half;
     if (ci < nvalid) fetch(ci, r0);
 #pragma unroll 1
     for (; ci < nvalid; ci += 4) {
+        TR_T0(t_l0);
         if (have) { tmem_ld_wait(); tmem_ld_pin(r0); }        // chunk ci is in r0
+#ifdef OFQ_GEMM_TRACE
+        if (tr) TR_ADD(tr->ldwait, t_l0);
+#endif
         if (ci + 2 < nvalid) fetch(ci + 2, r1);               // prefetch the next owned chunk
         emit(r0, ci);
         if (ci + 2 < nvalid) {
+            TR_T0(t_l1);
             if (have) { tmem_ld_wait(); tmem_ld_pin(r1); }
+#ifdef OFQ_GEMM_TRACE
+            if (tr) TR_ADD(tr->ldwait, t_l1);
+#endif
             if (ci + 4 < nvalid) fetch(ci + 4, r0);
             emit(r1, ci + 2);
         }
@@ -237,24 +356,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     const int g = c.it_begin + i;
-                    const int k2i = g / p.kblocks, kb = g % p.kblocks;
+                    const int k2i = p.fd_kblocks.div(g), kb = g - k2i * p.kblocks;
                     uint8_t* sa = smem + s * STAGE_BYTES;
                     uint8_t* sb = sa + NA * A_BYTES;
                     if (p.debug_nostore & 2) { mbar_arrive(&full_bar[s]); continue; }   // probe: no operand loads
                     mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
                     if (KIND != 0 && p.a_mn) {   // MN-major: 64-row x 64-k boxes, one 8 KB swizzle-atom column each
                         for (int j = 0; j < BM / 64; ++j)
-                            tma_load_5d(sa + j * 8192, &tmA, &full_bar[s], c.m0 + 64 * j, kb * kelem, (k2i % p.a_k2mod) * p.a_k2, c.b1 * p.a_b1, c.b2 * p.a_b2);
+                            tma_load_5d(sa + j * 8192, &tmA, &full_bar[s], c.m0 + 64 * j, kb * kelem, p.fd_ak2mod.mod(k2i) * p.a_k2, c.b1 * p.a_b1, c.b2 * p.a_b2);
                     } else {
-                        tma_load_5d(sa, &tmA, &full_bar[s], kb * kelem, c.m0, (k2i % p.a_k2mod) * p.a_k2, c.b1 * p.a_b1, c.b2 * p.a_b2);
+                        tma_load_5d(sa, &tmA, &full_bar[s], kb * kelem, c.m0, p.fd_ak2mod.mod(k2i) * p.a_k2, c.b1 * p.a_b1, c.b2 * p.a_b2);
                         if (NA == 2)
                             tma_load_5d(sa + A_BYTES, &tmA, &full_bar[s], kb * kelem, c.m0, k2i + p.a_dual_delta, c.b1 * p.a_b1, c.b2 * p.a_b2);
                     }
                     if (KIND != 0 && p.b_mn) {
                         for (int j = 0; j < BN / 64; ++j)
-                            tma_load_5d(sb + j * 8192, &tmB, &full_bar[s], c.n0 + 64 * j, kb * kelem, (k2i % p.b_k2mod) * p.b_k2, c.b1 * p.b_b1, c.b2 * p.b_b2);
+                            tma_load_5d(sb + j * 8192, &tmB, &full_bar[s], c.n0 + 64 * j, kb * kelem, p.fd_bk2mod.mod(k2i) * p.b_k2, c.b1 * p.b_b1, c.b2 * p.b_b2);
                     } else {
-                        tma_load_5d(sb, &tmB, &full_bar[s], kb * kelem, c.n0, (k2i % p.b_k2mod) * p.b_k2, c.b1 * p.b_b1, c.b2 * p.b_b2);
+                        tma_load_5d(sb, &tmB, &full_bar[s], kb * kelem, c.n0, p.fd_bk2mod.mod(k2i) * p.b_k2, c.b1 * p.b_b1, c.b2 * p.b_b2);
                     }
                 }
             }
@@ -262,16 +381,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         if (elect_one()) {
             uint32_t it = 0, tc = 0;
+            TR_DECL(tm_acc); TR_DECL(tm_full);
+            TR_T0(tm_begin);
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tc) {
                 const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);
                 const uint32_t as = tc & 1, aph = (tc >> 1) & 1;
+                TR_T0(t_e);
                 mbar_wait(&acc_empty[as], aph ^ 1);       // epilogue has drained this accumulator stage
+                TR_ADD(tm_acc, t_e);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * ACC_COLS;
                 for (int i = 0; i < c.nit; ++i, ++it) {
                     const uint32_t s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
+                    TR_T0(t_f);
                     mbar_wait(&full_bar[s], ph);
+                    TR_ADD(tm_full, t_f);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                     // K-major: one MMA consumes 32 bytes of the 128-byte K row. MN-major (16-bit): 16 k-rows of 128 bytes.
@@ -294,6 +419,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 tc_commit(&acc_full[as]);          // accumulator of this tile complete
             }
+#ifdef OFQ_GEMM_TRACE
+            if (blockIdx.x == 0)
+                printf("mma thread: tiles %u total %lld | wait acc_empty %lld wait full %lld\n", tc, clock64() - tm_begin, tm_acc, tm_full);
+#endif
         }
     } else {
         // ---- epilogue: warps 2..9. TMEM lane quarter = warp % 4 (hardware restriction); the two warps of a quarter
@@ -303,40 +432,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* stage_base = smem + L::OUT_OFF + (warp - 2) * OUT_BUFS * 4096;
         uint32_t tc = 0, chunk = 0;
         float omax = 0.f;                          // max |output| seen by this thread (p.amax)
+        TR_DECL(tr_vec); TR_DECL(tr_wait); TR_DECL(tr_work);
+        EpiTrace etr = {0, 0, 0, 0};
+        TR_T0(tr_begin);
+        constexpr int NCH = epi_nch(BN);
+        float* myvec = vec_s + (warp - 2) * NCH * 64;
+        EpiVecs<NCH> nv;                           // vectors of the NEXT tile, loaded one tile ahead
+        TileCoord cn;
+        if ((int)blockIdx.x < num_tiles) {
+            cn = decode_tile(p, blockIdx.x, BN, mtiles, ntiles);
+            epi_vec_load<NCH>(p, cn, cn.m0 + q * 32 + lane, half, lane, nv);
+        }
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tc) {
-            const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);
+            TR_T0(t_v);
+            const TileCoord c = cn;
             const uint32_t as = tc & 1, aph = (tc >> 1) & 1;
-            const bool rank1 = p.has_rank1 && c.split == 0;
-            float* cs_s = vec_s + as * 2 * BN;
-            float* ct_s = cs_s + BN;
-            {   // stage the column vectors of this tile (double buffered by accumulator stage)
-                const long long cs_off = (long long)c.b1 * p.cs.bs1 + (long long)c.b2 * p.cs.bs2;
-                const long long ct_off = (long long)c.b1 * p.ct.bs1 + (long long)c.b2 * p.ct.bs2;
-                for (int j = threadIdx.x - 64; j < BN; j += EPI_WARPS * 32) {
-                    const int n = c.n0 + j;
-                    const bool ok = n < p.N;
-                    cs_s[j] = ok ? (p.cs.p ? __ldg(p.cs.p + cs_off + (n % p.cs.period)) : 1.0f) : 0.f;
-                    ct_s[j] = (ok && rank1) ? (p.ct.p ? __ldg(p.ct.p + ct_off + n) : 1.0f) : 0.f;
-                }
-                named_bar_sync(1, EPI_WARPS * 32);
+            const bool rank1 = nv.rank1;
+            const float rsv = nv.rsv, rtv = nv.rtv;
+            epi_vec_publish<NCH>(nv, myvec, lane);
+            if (t + (int)gridDim.x < num_tiles) {
+                cn = decode_tile(p, t + gridDim.x, BN, mtiles, ntiles);
+                epi_vec_load<NCH>(p, cn, cn.m0 + q * 32 + lane, half, lane, nv);
             }
-            const int m = c.m0 + q * 32 + lane;
-            const bool row_ok = m < p.M;
-            const long long rs_off = (long long)c.b1 * p.rs.bs1 + (long long)c.b2 * p.rs.bs2;
-            const long long rt_off = (long long)c.b1 * p.rt.bs1 + (long long)c.b2 * p.rt.bs2;
-            const float rsv = row_ok ? (p.rs.p ? __ldg(p.rs.p + rs_off + (m % p.rs.period)) : 1.0f) : 0.f;
-            const float rtv = (row_ok && rank1) ? (p.rt.p ? __ldg(p.rt.p + rt_off + (m % p.rt.period)) : 1.0f) : 0.f;
 
+            TR_ADD(tr_vec, t_v);
+            TR_T0(t_w);
             if (c.nit > 0) {
                 mbar_wait(&acc_full[as], aph);
                 tc_fence_after();
             }
+            TR_ADD(tr_wait, t_w);
+            TR_T0(t_k);
             const uint32_t tmem_acc = tmem_base + as * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
             // number of chunks this warp owns inside the valid column range (warp-uniform)
             int nvalid = (min(BN, p.N - c.n0) + 31) / 32;
             if (p.debug_nostore & 4) nvalid = 0;                               // probe: no epilogue work at all
-            epi_tile<KIND, OUT_BUFS>(&tmC, p, c, c.m0 + q * 32, tmem_acc, c.nit > 0, nvalid, half, rank1, rsv, rtv, cs_s, ct_s,
-                                     stage_base, chunk, lane, omax);
+            epi_tile<KIND, OUT_BUFS>(&tmC, p, c, c.m0 + q * 32, tmem_acc, c.nit > 0, nvalid, half, rank1, rsv, rtv, myvec,
+                                     stage_base, chunk, lane, omax, &etr);
+            TR_ADD(tr_work, t_k);
             // all TMEM reads of this tile are complete: hand the accumulator stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -347,6 +480,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int o2 = 16; o2 > 0; o2 >>= 1) omax = fmaxf(omax, __shfl_xor_sync(0xffffffffu, omax, o2));
             if (lane == 0) atomicMax(p.amax, __float_as_uint(omax));
         }
+#ifdef OFQ_GEMM_TRACE
+        if (blockIdx.x == 0 && threadIdx.x == 64)
+            printf("epi warp: tiles %u total %lld | vec %lld accwait %lld work %lld | ldwait %lld rdwait %lld math %lld fence+store %lld\n",
+                   tc, clock64() - tr_begin, tr_vec, tr_wait, tr_work, etr.ldwait, etr.rdwait, etr.math, etr.fence);
+#endif
         if (lane == 0) tma_store_wait_all<0>();
     }
     __syncthreads();
@@ -373,7 +511,7 @@ struct SmemLayout2 {
     static constexpr uint32_t OUT_OFF = STAGES * STAGE_BYTES;
     static constexpr uint32_t OUT_BYTES = EPI_WARPS * OUT_BUFS * 4096;
     static constexpr uint32_t VEC_OFF = OUT_OFF + OUT_BYTES;
-    static constexpr uint32_t BAR_OFF = VEC_OFF + 2 * 2 * BN * 4;
+    static constexpr uint32_t BAR_OFF = VEC_OFF + EPI_WARPS * epi_nch(BN) * 64 * 4;
     static constexpr uint32_t TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
     static constexpr size_t DYN_BYTES = TOTAL + 1024;
 };
@@ -444,22 +582,22 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     const int g = c.it_begin + i;
-                    const int k2i = g / p.kblocks, kb = g % p.kblocks;
+                    const int k2i = p.fd_kblocks.div(g), kb = g - k2i * p.kblocks;
                     uint8_t* sa = smem + s * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
                     const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
                     if (KIND != 0 && p.a_mn) {
                         for (int j = 0; j < BM / 64; ++j)
-                            tma_load_5d_pair(sa + j * 8192, &tmA, bar, m0 + 64 * j, kb * kelem, (k2i % p.a_k2mod) * p.a_k2, c.b1 * p.a_b1, c.b2 * p.a_b2);
+                            tma_load_5d_pair(sa + j * 8192, &tmA, bar, m0 + 64 * j, kb * kelem, p.fd_ak2mod.mod(k2i) * p.a_k2, c.b1 * p.a_b1, c.b2 * p.a_b2);
                     } else {
-                        tma_load_5d_pair(sa, &tmA, bar, kb * kelem, m0, (k2i % p.a_k2mod) * p.a_k2, c.b1 * p.a_b1, c.b2 * p.a_b2);
+                        tma_load_5d_pair(sa, &tmA, bar, kb * kelem, m0, p.fd_ak2mod.mod(k2i) * p.a_k2, c.b1 * p.a_b1, c.b2 * p.a_b2);
                     }
                     if (KIND != 0 && p.b_mn) {
                         for (int j = 0; j < BNH / 64; ++j)
-                            tma_load_5d_pair(sb + j * 8192, &tmB, bar, n0 + 64 * j, kb * kelem, (k2i % p.b_k2mod) * p.b_k2, c.b1 * p.b_b1, c.b2 * p.b_b2);
+                            tma_load_5d_pair(sb + j * 8192, &tmB, bar, n0 + 64 * j, kb * kelem, p.fd_bk2mod.mod(k2i) * p.b_k2, c.b1 * p.b_b1, c.b2 * p.b_b2);
                     } else {
-                        tma_load_5d_pair(sb, &tmB, bar, kb * kelem, n0, (k2i % p.b_k2mod) * p.b_k2, c.b1 * p.b_b1, c.b2 * p.b_b2);
+                        tma_load_5d_pair(sb, &tmB, bar, kb * kelem, n0, p.fd_bk2mod.mod(k2i) * p.b_k2, c.b1 * p.b_b1, c.b2 * p.b_b2);
                     }
                 }
             }
@@ -502,30 +640,25 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint8_t* stage_base = smem + L::OUT_OFF + (warp - 2) * OUT_BUFS * 4096;
         uint32_t tc = 0, chunk = 0;
         float omax = 0.f;                          // max |output| seen by this thread (p.amax)
+        constexpr int NCH = epi_nch(BN);
+        float* myvec = vec_s + (warp - 2) * NCH * 64;
+        EpiVecs<NCH> nv;                           // vectors of the NEXT tile, loaded one tile ahead
+        TileCoord cn;
+        if (pair < num_tiles) {
+            cn = decode_tile(p, pair, BN, mtiles, ntiles);
+            epi_vec_load<NCH>(p, cn, 2 * cn.m0 + (int)rank * BM + q * 32 + lane, half, lane, nv);
+        }
         for (int t = pair; t < num_tiles; t += npairs, ++tc) {
-            const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);
+            const TileCoord c = cn;
             const int m0 = 2 * c.m0 + (int)rank * BM;
             const uint32_t as = tc & 1, aph = (tc >> 1) & 1;
-            const bool rank1 = p.has_rank1 && c.split == 0;
-            float* cs_s = vec_s + as * 2 * BN;
-            float* ct_s = cs_s + BN;
-            {
-                const long long cs_off = (long long)c.b1 * p.cs.bs1 + (long long)c.b2 * p.cs.bs2;
-                const long long ct_off = (long long)c.b1 * p.ct.bs1 + (long long)c.b2 * p.ct.bs2;
-                for (int j = threadIdx.x - 64; j < BN; j += EPI_WARPS * 32) {
-                    const int n = c.n0 + j;
-                    const bool ok = n < p.N;
-                    cs_s[j] = ok ? (p.cs.p ? __ldg(p.cs.p + cs_off + (n % p.cs.period)) : 1.0f) : 0.f;
-                    ct_s[j] = (ok && rank1) ? (p.ct.p ? __ldg(p.ct.p + ct_off + n) : 1.0f) : 0.f;
-                }
-                named_bar_sync(1, EPI_WARPS * 32);
+            const bool rank1 = nv.rank1;
+            const float rsv = nv.rsv, rtv = nv.rtv;
+            epi_vec_publish<NCH>(nv, myvec, lane);
+            if (t + npairs < num_tiles) {
+                cn = decode_tile(p, t + npairs, BN, mtiles, ntiles);
+                epi_vec_load<NCH>(p, cn, 2 * cn.m0 + (int)rank * BM + q * 32 + lane, half, lane, nv);
             }
-            const int m = m0 + q * 32 + lane;
-            const bool row_ok = m < p.M;
-            const long long rs_off = (long long)c.b1 * p.rs.bs1 + (long long)c.b2 * p.rs.bs2;
-            const long long rt_off = (long long)c.b1 * p.rt.bs1 + (long long)c.b2 * p.rt.bs2;
-            const float rsv = row_ok ? (p.rs.p ? __ldg(p.rs.p + rs_off + (m % p.rs.period)) : 1.0f) : 0.f;
-            const float rtv = (row_ok && rank1) ? (p.rt.p ? __ldg(p.rt.p + rt_off + (m % p.rt.period)) : 1.0f) : 0.f;
 
             if (c.nit > 0) {
                 mbar_wait(&acc_full[as], aph);
@@ -534,7 +667,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t tmem_acc = tmem_base + as * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
             int nvalid = (min(BN, p.N - c.n0) + 31) / 32;
             if (m0 >= p.M) nvalid = 0;                 // this CTA's half of the pair tile lies entirely below the matrix
-            epi_tile<KIND, OUT_BUFS>(&tmC, p, c, m0 + q * 32, tmem_acc, c.nit > 0, nvalid, half, rank1, rsv, rtv, cs_s, ct_s,
+            epi_tile<KIND, OUT_BUFS>(&tmC, p, c, m0 + q * 32, tmem_acc, c.nit > 0, nvalid, half, rank1, rsv, rtv, myvec,
                                      stage_base, chunk, lane, omax);
             tc_fence_before();
             __syncwarp();
@@ -559,7 +692,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ------------------------------------------------------------------------------------------ host side
 template <int KIND, int BN, int STAGES, int NA = 1, int OUT_BUFS = 2>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-                       const GemmParams& p, cudaStream_t stream) {
+                       GemmParams p, cudaStream_t stream) {
     constexpr size_t smem = SmemLayout<BN, STAGES, NA, OUT_BUFS>::DYN_BYTES;
     static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
     auto kern = gemm_tc_kernel<KIND, BN, STAGES, NA, OUT_BUFS>;
@@ -569,6 +702,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
         configured = true;
     }
     const int mtiles = (p.M + BM - 1) / BM, ntiles = (p.N + BN - 1) / BN;
+    p.fd_ntiles = make_fastdiv(ntiles); p.fd_mtiles = make_fastdiv(mtiles);
     const long long tiles = (long long)mtiles * ntiles * p.nb1 * p.nb2 * p.splits;
     if (tiles > 0x7fffffff) {
         ofq_set_error("ofq_gemm: too many tiles");
@@ -584,7 +718,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 // Largest number of co-resident CTA pairs for an instantiation (clusters need two free SMs of one TPC).
 template <int KIND, int BN, int STAGES, int OUT_BUFS = 2>
 static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-                            const GemmParams& p, cudaStream_t stream) {
+                            GemmParams p, cudaStream_t stream) {
     constexpr size_t smem = SmemLayout2<BN, STAGES, OUT_BUFS>::DYN_BYTES;
     static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
     auto kern = gemm_tc_pair_kernel<KIND, BN, STAGES, OUT_BUFS>;
@@ -605,6 +739,7 @@ static int launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
         max_pairs = n < ofq_num_sms() / 2 ? n : ofq_num_sms() / 2;
     }
     const int mtiles = (p.M + 2 * BM - 1) / (2 * BM), ntiles = (p.N + BN - 1) / BN;
+    p.fd_ntiles = make_fastdiv(ntiles); p.fd_mtiles = make_fastdiv(mtiles);
     const long long tiles = (long long)mtiles * ntiles * p.nb1 * p.nb2 * p.splits;
     if (tiles > 0x7fffffff) {
         ofq_set_error("ofq_gemm: too many tiles");
@@ -628,6 +763,7 @@ static VecRef make_vec(const ofq_vec_t* v) {
     VecRef r;
     r.p = v ? v->ptr : nullptr;
     r.period = (v && v->period > 0) ? v->period : 0x7fffffff;
+    r.fd = make_fastdiv(r.period);
     r.bs1 = v ? v->bstride1 : 0;
     r.bs2 = v ? v->bstride2 : 0;
     return r;
@@ -717,6 +853,12 @@ extern "C" int ofq_gemm_ex(int kind, const ofq_operand_t* A, const ofq_operand_t
     p.a_dual_delta = A->dual_delta;
     p.a_k2mod = A->k2_mod > 0 ? A->k2_mod : 0x7fffffff;
     p.b_k2mod = B->k2_mod > 0 ? B->k2_mod : 0x7fffffff;
+    p.fd_nbatch = make_fastdiv(nb1 * nb2); p.fd_nb1 = make_fastdiv(nb1); p.fd_splits = make_fastdiv(splits);
+    p.fd_kblocks = make_fastdiv(p.kblocks); p.fd_ak2mod = make_fastdiv(p.a_k2mod); p.fd_bk2mod = make_fastdiv(p.b_k2mod);
+    if ((long long)p.kblocks * k2 * (splits + 1) > 0x7fffffffLL || (long long)nb1 * nb2 > 0x7fffffffLL) {
+        ofq_set_error("ofq_gemm: k-block count x splits (or the batch count) does not fit 31 bits");
+        return OFQ_ERR_ARG;
+    }
     p.c_b1 = out->bstride1 != 0; p.c_b2 = out->bstride2 != 0;
     p.rs = make_vec(rs); p.cs = make_vec(cs); p.rt = make_vec(rt); p.ct = make_vec(ct);
     p.has_rank1 = (rt && rt->ptr) || (ct && ct->ptr);
@@ -802,7 +944,7 @@ extern "C" int ofq_gemm_ex(int kind, const ofq_operand_t* A, const ofq_operand_t
             case 224: return launch_gemm<1, 224, 3, 2, 1>(tmA, tmB, tmC, p, st);
             case 192: return launch_gemm<1, 192, 3, 2, 1>(tmA, tmB, tmC, p, st);
             case 128: return launch_gemm<1, 128, 3, 2, 2>(tmA, tmB, tmC, p, st);
-            case 64:  return launch_gemm<1, 64, 4, 2, 2>(tmA, tmB, tmC, p, st);
+            case 64:  return launch_gemm<1, 64, 3, 2, 2>(tmA, tmB, tmC, p, st);
             default:  return launch_gemm<1, 32, 4, 2, 2>(tmA, tmB, tmC, p, st);
         }
     }

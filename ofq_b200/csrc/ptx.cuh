@@ -35,6 +35,15 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 }
+// 16-byte shared-memory accesses in volatile-asm order without memory clobbers (see the GEMM epilogue).
+__device__ __forceinline__ float4 ld_shared_v4_nc(const void* src) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(src)));
+    return v;
+}
+__device__ __forceinline__ void st_shared_v4_nc(void* dst, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(smem_u32(dst)), "f"(a), "f"(b), "f"(c), "f"(d));
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)),
                  "r"(bytes)
