@@ -40,7 +40,8 @@ OFQ_API int ofq_device_ok(void);
  * kind BF16 / F16: bf16 / fp16 operands, fp32 accumulation. Strides are in elements; a batch stride of 0 means the
  * operand is shared across that batch axis. Row/k2/batch strides must be multiples of 16 bytes.
  * NULL vectors read as 1; the rank-1 term is added only when rt or ct is non-NULL.
- * With splits > 1 (split-K) the output must be pre-zeroed and `accumulate` set (fp32 atomics).
+ * With splits > 1 (split-K) the output must be pre-zeroed and `accumulate` set (fp32 atomics). splits = 0: the library
+ * chooses (split-K only for accumulating outputs), from the tile count, the K extent and the number of SMs.
  */
 #define OFQ_GEMM_I8   0
 #define OFQ_GEMM_BF16 1

@@ -835,7 +835,7 @@ extern "C" int ofq_gemm_ex(int kind, const ofq_operand_t* A, const ofq_operand_t
         ofq_set_error("ofq_gemm: unknown kind %d", kind);
         return OFQ_ERR_ARG;
     }
-    if (M <= 0 || N <= 0 || K <= 0 || k2 <= 0 || nb1 <= 0 || nb2 <= 0 || splits <= 0) {
+    if (M <= 0 || N <= 0 || K <= 0 || k2 <= 0 || nb1 <= 0 || nb2 <= 0 || splits < 0) {
         ofq_set_error("ofq_gemm: non-positive extent");
         return OFQ_ERR_ARG;
     }
@@ -853,10 +853,10 @@ extern "C" int ofq_gemm_ex(int kind, const ofq_operand_t* A, const ofq_operand_t
     p.a_dual_delta = A->dual_delta;
     p.a_k2mod = A->k2_mod > 0 ? A->k2_mod : 0x7fffffff;
     p.b_k2mod = B->k2_mod > 0 ? B->k2_mod : 0x7fffffff;
-    p.fd_nbatch = make_fastdiv(nb1 * nb2); p.fd_nb1 = make_fastdiv(nb1); p.fd_splits = make_fastdiv(splits);
+    p.fd_nbatch = make_fastdiv(nb1 * nb2); p.fd_nb1 = make_fastdiv(nb1);
     p.fd_kblocks = make_fastdiv(p.kblocks); p.fd_ak2mod = make_fastdiv(p.a_k2mod); p.fd_bk2mod = make_fastdiv(p.b_k2mod);
-    if ((long long)p.kblocks * k2 * (splits + 1) > 0x7fffffffLL || (long long)nb1 * nb2 > 0x7fffffffLL) {
-        ofq_set_error("ofq_gemm: k-block count x splits (or the batch count) does not fit 31 bits");
+    if ((long long)p.kblocks * k2 * 65 > 0x7fffffffLL || splits > 64 || (long long)nb1 * nb2 > 0x7fffffffLL) {
+        ofq_set_error("ofq_gemm: at most 64 splits; k-block count x 65 and the batch count must fit 31 bits");
         return OFQ_ERR_ARG;
     }
     p.c_b1 = out->bstride1 != 0; p.c_b2 = out->bstride2 != 0;
@@ -898,6 +898,31 @@ extern "C" int ofq_gemm_ex(int kind, const ofq_operand_t* A, const ofq_operand_t
         const long long nt = (N + w - 1) / w;
         const long long cost = nt * (128 + w);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; bn = w; }
+    }
+    if (splits == 0) {
+        // auto split-K (accumulating outputs only): work items = tiles x splits are dealt round-robin to one CTA (pair) per
+        // SM, so the launch takes ceil(items / slots) rounds of (k-blocks per split + a fixed per-item cost: pipeline fill,
+        // epilogue, reduce-add ~ 6 k-blocks); take the split count with the cheapest total.
+        splits = 1;
+        if (p.atomic) {
+            const long long mt = pair ? (M + 2 * BM - 1) / (2 * BM) : (M + BM - 1) / BM, nt = (N + bn - 1) / bn;
+            const long long T = mt * nt * nb1 * nb2;
+            const long long slots = pair ? ofq_num_sms() / 2 : ofq_num_sms();
+            const long long KB = (long long)p.kblocks * k2;
+            static const double fixed = [] { const char* e = getenv("OFQ_GEMM_SPLIT_COST"); return e ? atof(e) : 6.0; }();
+            double best = -1.0;
+            for (int sp = 1; sp <= 64 && sp <= (KB / 4 > 1 ? KB / 4 : 1); ++sp) {
+                const long long rounds = (T * sp + slots - 1) / slots;
+                const double cost = (double)rounds * ((double)((KB + sp - 1) / sp) + fixed);
+                if (best < 0 || cost < best * 0.98) { best = cost; splits = sp; }      // ties / near-ties: fewer splits
+            }
+        }
+    }
+    p.splits = splits;
+    p.fd_splits = make_fastdiv(splits);
+    if (out_absmax && splits > 1) {
+        ofq_set_error("ofq_gemm: the output maximum is tracked for plain (non-accumulating, unsplit) stores only");
+        return OFQ_ERR_ARG;
     }
     CUtensorMap tmA, tmB, tmC;
     int rc = make_operand_map(&tmA, A, eb, M, K, k2, nb1, nb2, BM, kind == OFQ_GEMM_F16);

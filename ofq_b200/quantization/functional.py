@@ -95,12 +95,10 @@ def _linear_backward_f16(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulat
     if qx16 is None:
         qx16 = ops.codes_to_bf16(qx, 1, M, K, K, 0, False, FMT)          # [1, M, K]
     dW = torch.zeros((Nout, K), dtype=torch.float32, device=a16.device)
-    tiles = ((Nout + 127) // 128) * ((K + 127) // 128)
-    splits = _splits_for(tiles, (M + 63) // 64)
     # the weight gradient is off the activation-gradient chain: side stream, joined before the backward returns
     with ops.side_stream(a16, qx16, dW, cs2, sc, colsum, x_aft):
         ops.gemm(GEMM_BWD, a16, (Nout, 0, 0, 0), qx16, (K, 0, 0, 0), dW, (K, 0, 0), Nout, K, M, a_mn=True, b_mn=True,
-                 splits=splits, accumulate=True, rs=vec(cs2[1]), cs=_scalar(sc), rt=vec(colsum), ct=vec(x_aft))
+                 splits=0, accumulate=True, rs=vec(cs2[1]), cs=_scalar(sc), rt=vec(colsum), ct=vec(x_aft))
     return dW, colsum, qx16
 
 
