@@ -466,6 +466,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t tmem_acc = tmem_base + as * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
             // number of chunks this warp owns inside the valid column range (warp-uniform)
             int nvalid = (min(BN, p.N - c.n0) + 31) / 32;
+            if (c.m0 + q * 32 >= p.M) nvalid = 0;      // this warp's 32 rows lie entirely below the matrix (ragged last row block)
             if (p.debug_nostore & 4) nvalid = 0;                               // probe: no epilogue work at all
             epi_tile<KIND, OUT_BUFS>(&tmC, p, c, c.m0 + q * 32, tmem_acc, c.nit > 0, nvalid, half, rank1, rsv, rtv, myvec,
                                      stage_base, chunk, lane, omax, &etr);
@@ -666,7 +667,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             const uint32_t tmem_acc = tmem_base + as * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
             int nvalid = (min(BN, p.N - c.n0) + 31) / 32;
-            if (m0 >= p.M) nvalid = 0;                 // this CTA's half of the pair tile lies entirely below the matrix
+            if (m0 + q * 32 >= p.M) nvalid = 0;        // this warp's 32 rows (or the CTA's whole half) lie below the matrix
             epi_tile<KIND, OUT_BUFS>(&tmC, p, c, m0 + q * 32, tmem_acc, c.nit > 0, nvalid, half, rank1, rsv, rtv, myvec,
                                      stage_base, chunk, lane, omax);
             tc_fence_before();

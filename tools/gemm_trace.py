@@ -19,3 +19,15 @@ for N in [int(a) for a in sys.argv[1:]] or [2304, 384]:
         print(f"--- i8 M={M} N={N} K={K} launch {i}", flush=True)
         ops.gemm(GEMM_I8, A, (K, 0, 0, 0), B, (K, 0, 0, 0), out, (N, 0, 0), M, N, K, rs=vec(rs, 198), cs=vec(cs), ct=vec(ct))
         torch.cuda.synchronize()
+
+# weight-gradient shape (both operands MN-major, auto split-K): dW[Mo, No] = A16[T, Mo]^T @ Q16[T, No]
+T = 25344
+for Mo, No in ((384, 1536), (2304, 384)):
+    a16 = torch.randn(T, Mo, device=dev).half()
+    q16 = torch.randint(-2, 2, (T, No), device=dev).half()
+    dW = torch.zeros(Mo, No, device=dev)
+    for i in range(2):
+        print(f"--- f16 dW M={Mo} N={No} K={T} launch {i}", flush=True)
+        ops.gemm(GEMM_F16, a16, (Mo, 0, 0, 0), q16, (No, 0, 0, 0), dW, (No, 0, 0), Mo, No, T, a_mn=True, b_mn=True,
+                 splits=0, accumulate=True)
+        torch.cuda.synchronize()
