@@ -182,6 +182,9 @@ def main():
     import torch.distributed as dist
     import torch.nn.functional as F
 
+    if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+        # the step is captured on a side stream; AccumulateGrad nodes created during the eager warm-up live on the default one
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
     import ofq_b200.quantization as Q
     from ofq_b200 import _lib, ops
     from ofq_b200.cga import CGAAdamW, cga_masked_parameter_names, param_groups_weight_decay
@@ -231,8 +234,8 @@ def main():
     def step(img, lbl):
         if a.mode == "eval":
             with torch.no_grad():
-                (cls, dst), _ = model(img)
-            return cls.float().mean()
+                out, _ = model(img)              # eval: the mean of the two heads (deit.py:60-67)
+            return out.float().mean()
         if ddp is None:
             opt.zero_grad(set_to_none=True)
         else:

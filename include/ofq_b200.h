@@ -344,6 +344,11 @@ OFQ_API int ofq_adamw_multi(const void* table, int n_entries, int total_blocks, 
  * mean / rstd [rows] are saved for the backward. workspace: float[ofq_layernorm_bwd_workspace(rows, cols)]. */
 OFQ_API int ofq_layernorm_fwd(const float* x, long long rows, int cols, const float* gamma, const float* beta,
                               float eps, float* y, float* mean, float* rstd, void* stream);
+/* xsum = x + add and y = LayerNorm(xsum) in one pass (cols <= 512): the residual add in front of a pre-norm LayerNorm
+ * (x = x + attn(...); mlp(norm2(x)), deit_vision_transformer.py:156-163). Bit-identical to a separate add + ofq_layernorm_fwd. */
+OFQ_API int ofq_layernorm_fwd_add(const float* x, const float* add, long long rows, int cols, const float* gamma,
+                                  const float* beta, float eps, float* xsum, float* y, float* mean, float* rstd,
+                                  void* stream);
 OFQ_API long long ofq_layernorm_bwd_workspace(long long rows, int cols);
 OFQ_API int ofq_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
                               const float* rstd, long long rows, int cols, float* dx, float* dgamma, float* dbeta,

@@ -77,6 +77,7 @@ SIGNATURES = {
     "ofq_cga_adamw": (_i, [_p, _p, _p, _p, _ll, _i, _i, _i, _d, _d, _d, _d, _d, _i, _d, _p, _p, _p, _p, _p]),
     "ofq_counter_increment": (_i, [_p, _p]),
     "ofq_layernorm_fwd": (_i, [_p, _ll, _i, _p, _p, _f, _p, _p, _p, _p]),
+    "ofq_layernorm_fwd_add": (_i, [_p, _p, _ll, _i, _p, _p, _f, _p, _p, _p, _p, _p]),
     "ofq_layernorm_bwd_workspace": (_ll, [_ll, _i]),
     "ofq_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _ll, _i, _p, _p, _p, _p, _p]),
     "ofq_layernorm_bwd_nmax": (_ll, [_ll, _i]),

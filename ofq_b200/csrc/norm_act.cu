@@ -50,6 +50,62 @@ layernorm_fwd_kernel(const float* __restrict__ x, long long rows, int cols, cons
     }
 }
 
+// x_new = x + add (the residual add in front of a pre-norm LayerNorm, deit_vision_transformer.py:156-163) and
+// y = LayerNorm(x_new) in ONE pass: rows of at most 512 columns stay in registers (4 x 16 B per lane), so the sum is read
+// once and never re-read. Same summation order as layernorm_fwd_kernel: identical statistics and outputs.
+__global__ void __launch_bounds__(256)
+layernorm_fwd_add_kernel(const float* __restrict__ x, const float* __restrict__ add, long long rows, int cols,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                         float* __restrict__ xsum, float* __restrict__ y, float* __restrict__ mean_out,
+                         float* __restrict__ rstd_out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + warp;
+    if (row >= rows) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * cols);
+    const float4* ar = reinterpret_cast<const float4*>(add + row * cols);
+    float4* sr = reinterpret_cast<float4*>(xsum + row * cols);
+    const int c4 = cols >> 2;
+    float4 v[4];
+    float s = 0.f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int i = lane + 32 * p;
+        v[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < c4) {
+            const float4 a = __ldg(xr + i), b = __ldg(ar + i);
+            v[p] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+            sr[i] = v[p];
+            s += (v[p].x + v[p].y) + (v[p].z + v[p].w);
+        }
+    }
+    const float mean = wsum(s) / (float)cols;
+    float q = 0.f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        if (lane + 32 * p < c4) {
+            const float a = v[p].x - mean, b = v[p].y - mean, c = v[p].z - mean, d = v[p].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    const float rstd = rsqrtf(wsum(q) / (float)cols + eps);
+    float4* yr = reinterpret_cast<float4*>(y + row * cols);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int i = lane + 32 * p;
+        if (i < c4) {
+            const float4 g = __ldg(g4 + i), b = __ldg(b4 + i);
+            yr[i] = make_float4((v[p].x - mean) * rstd * g.x + b.x, (v[p].y - mean) * rstd * g.y + b.y,
+                                (v[p].z - mean) * rstd * g.z + b.z, (v[p].w - mean) * rstd * g.w + b.w);
+        }
+    }
+    if (lane == 0) {
+        mean_out[row] = mean;
+        rstd_out[row] = rstd;
+    }
+}
+
 constexpr int kChunk = 512;
 constexpr int kMaxBlocks = 4 * 148;
 
@@ -237,6 +293,20 @@ extern "C" int ofq_layernorm_fwd(const float* x, long long rows, int cols, const
                 (uintptr_t)beta % 16 == 0, "ofq_layernorm_fwd: cols must be a multiple of 4 and pointers 16-byte aligned");
     OFQ_CHECK_ARCH();
     layernorm_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, gamma, beta, eps, y, mean, rstd);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ofq_layernorm_fwd_add(const float* x, const float* add, long long rows, int cols, const float* gamma,
+                                     const float* beta, float eps, float* xsum, float* y, float* mean, float* rstd,
+                                     void* stream) {
+    OFQ_REQUIRE(x && add && gamma && beta && xsum && y && mean && rstd && rows > 0 && cols > 0, "ofq_layernorm_fwd_add: bad argument");
+    OFQ_REQUIRE(cols % 4 == 0 && cols <= 512, "ofq_layernorm_fwd_add: rows of at most 512 columns, a multiple of 4");
+    OFQ_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)add % 16 == 0 && (uintptr_t)xsum % 16 == 0 && (uintptr_t)y % 16 == 0 &&
+                (uintptr_t)gamma % 16 == 0 && (uintptr_t)beta % 16 == 0, "ofq_layernorm_fwd_add: pointers must be 16-byte aligned");
+    OFQ_CHECK_ARCH();
+    layernorm_fwd_add_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, add, rows, cols, gamma, beta, eps,
+                                                                                         xsum, y, mean, rstd);
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }

@@ -82,16 +82,30 @@ class Block(nn.Module):
         self.drop_path = nn.Identity()
         self.norm2 = norm_layer(dim)
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+        self._defer = False       # set by the host model: hand the MLP branch to the next block instead of adding it here
 
-    def forward(self, x):
-        res = getattr(self.norm1, "forward_res", None)       # ofq_b200 LayerNorm: residual gradient summed in its backward kernel
-        x, y = res(x) if res is not None else (x, self.norm1(x))
+    def forward(self, x, pending=None):
+        """pending: the MLP branch of the previous block, not yet added to x (forward_pending): the add is fused into norm1."""
+        # ofq_b200 LayerNorm: residual gradient summed in its backward kernel, residual add fused into the forward one
+        res, res_add = getattr(self.norm1, "forward_res", None), getattr(self.norm1, "forward_res_add", None)
+        if pending is not None:
+            x, y = res_add(x, pending) if res_add is not None else (x + pending, None)
+            if y is None:
+                x, y = res(x) if res is not None else (x, self.norm1(x))
+        else:
+            x, y = res(x) if res is not None else (x, self.norm1(x))
         a, _ = self.attn(y)
-        x = x + self.drop_path(a)
-        res = getattr(self.norm2, "forward_res", None)
-        x, y = res(x) if res is not None else (x, self.norm2(x))
-        x = x + self.drop_path(self.mlp(y))
-        return x, None
+        a = self.drop_path(a)
+        res, res_add = getattr(self.norm2, "forward_res", None), getattr(self.norm2, "forward_res_add", None)
+        if res_add is not None:
+            x, y = res_add(x, a)
+        else:
+            x = x + a
+            x, y = res(x) if res is not None else (x, self.norm2(x))
+        m = self.drop_path(self.mlp(y))
+        if self._defer:
+            return x, m
+        return x + m, None
 
 
 class DistilledVisionTransformer(nn.Module):
@@ -138,9 +152,14 @@ class DistilledVisionTransformer(nn.Module):
         B = x.shape[0]
         x = torch.cat((self.cls_token.expand(B, -1, -1), self.dist_token.expand(B, -1, -1), x), dim=1)
         x = self.pos_drop(x + self.pos_embed)
-        for blk in self.blocks:
-            x, _ = blk(x)
-        x = self.norm(x)
+        # the residual add that closes a block is fused into the first LayerNorm of the next one
+        pending = None
+        last = len(self.blocks) - 1
+        for i, blk in enumerate(self.blocks):
+            blk._defer = i < last
+            x, pending = blk(x, pending)
+        # only the class and distillation tokens reach the heads: LayerNorm is per token, so normalise just those two
+        x = self.norm(x[:, :2])
         return x[:, 0], x[:, 1]
 
     def forward(self, x):

@@ -47,6 +47,30 @@ class _LayerNormResFn(torch.autograd.Function):
         return dx.view_as(dy), dg, db, None
 
 
+class _LayerNormAddFn(torch.autograd.Function):
+    """(x + a, LayerNorm(x + a)) in one kernel: the residual add of the previous branch fused into the pre-norm LayerNorm of
+    the next one. Backward as _LayerNormResFn; the summed gradient goes to both addends."""
+
+    @staticmethod
+    def forward(ctx, x, a, weight, bias, eps):
+        xc, ac = x.contiguous(), a.contiguous()
+        C = xc.shape[-1]
+        xsum, y, mean, rstd = ops.layernorm_fwd(xc.view(-1, C), weight, bias, eps, add=ac.view(-1, C))
+        ctx.save_for_backward(xsum, weight, mean, rstd)
+        ctx.set_materialize_grads(False)
+        return xsum.view_as(xc), y.view_as(xc)
+
+    @staticmethod
+    def backward(ctx, dres, dy):
+        x2d, weight, mean, rstd = ctx.saved_tensors
+        if dy is None:
+            return dres, dres, None, None, None
+        res2d = dres.contiguous().view_as(x2d) if dres is not None else None
+        dx, dg, db = ops.layernorm_bwd(dy.contiguous().view_as(x2d), x2d, weight, mean, rstd, res2d, want_max=True)
+        dx = dx.view_as(dy)
+        return dx, dx, dg, db, None
+
+
 class LayerNorm(nn.LayerNorm):
     """nn.LayerNorm over the last dimension with the same parameters / state-dict keys; fp32 CUDA inputs take the
     ofq_b200 kernels (forward ~HBM roofline, backward 4-5x faster than ATen's for 384-wide rows), anything else falls
@@ -60,6 +84,13 @@ class LayerNorm(nn.LayerNorm):
         if self._native(x):
             return _LayerNormFn.apply(x, self.weight, self.bias, self.eps)
         return super().forward(x)
+
+    def forward_res_add(self, x, a):
+        """(x + a, LayerNorm(x + a)): the residual add and the normalisation of its result in one pass."""
+        if (self._native(x) and a.dtype == x.dtype and a.shape == x.shape and x.shape[-1] <= 512 and torch.is_grad_enabled()
+                and (x.requires_grad or a.requires_grad)):
+            return _LayerNormAddFn.apply(x, a, self.weight, self.bias, self.eps)
+        return self.forward_res(x + a)
 
     def forward_res(self, x):
         """(x, LayerNorm(x)): use the returned x in the residual add around the normalised branch."""

@@ -503,12 +503,22 @@ def adamw_multi_(table, n_entries: int, total_blocks: int, total_numel: int, ste
 
 
 # ------------------------------------------------------------------------------------------------ LayerNorm
-def layernorm_fwd(x2d: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float):
+def layernorm_fwd(x2d: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, add: Optional[torch.Tensor] = None):
+    """(y, mean, rstd) of nn.LayerNorm over the rows of x2d; with `add` [rows, cols] (cols <= 512): (x2d + add, y, mean, rstd),
+    the residual sum formed and normalised in one pass."""
     _cuda(x2d, gamma, beta)
     rows, cols = x2d.shape
     y = torch.empty_like(x2d)
     mean = torch.empty(rows, dtype=torch.float32, device=x2d.device)
     rstd = torch.empty(rows, dtype=torch.float32, device=x2d.device)
+    if add is not None:
+        _cuda(add)
+        assert add.shape == x2d.shape and add.is_contiguous() and x2d.is_contiguous()
+        xsum = torch.empty_like(x2d)
+        _call("layernorm_fwd", 1, 16.0 * rows * cols, 0, _lib.load().ofq_layernorm_fwd_add, x2d.data_ptr(), add.data_ptr(), rows,
+              cols, gamma.data_ptr(), beta.data_ptr(), float(eps), xsum.data_ptr(), y.data_ptr(), mean.data_ptr(),
+              rstd.data_ptr(), _st())
+        return xsum, y, mean, rstd
     _call("layernorm_fwd", 1, 8.0 * rows * cols, 0, _lib.load().ofq_layernorm_fwd, x2d.data_ptr(), rows, cols,
           gamma.data_ptr(), beta.data_ptr(), float(eps), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _st())
     return y, mean, rstd

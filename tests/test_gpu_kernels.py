@@ -711,6 +711,47 @@ def test_layernorm_residual_module(ops):
         assert rel_err(a, b) < 1e-6
 
 
+@pytest.mark.parametrize("rows,cols", [(25344, 384), (396, 192), (77, 96), (130, 512)])
+def test_layernorm_fwd_add(ops, rows, cols):
+    """x + a and LayerNorm(x + a) in one pass: bit-identical to the separate add + ofq_layernorm_fwd."""
+    torch.manual_seed(19)
+    x = torch.randn(rows, cols, device="cuda") * 2 + 0.5
+    a = torch.randn(rows, cols, device="cuda")
+    g = torch.rand(cols, device="cuda") + 0.5
+    b = torch.randn(cols, device="cuda")
+    xs, y, mean, rstd = ops.layernorm_fwd(x, g, b, 1e-6, add=a)
+    y0, mean0, rstd0 = ops.layernorm_fwd(x + a, g, b, 1e-6)
+    assert torch.equal(xs, x + a) and torch.equal(y, y0) and torch.equal(mean, mean0) and torch.equal(rstd, rstd0)
+
+
+def test_layernorm_add_module(ops):
+    """LayerNorm.forward_res_add(x, a) equals x + a followed by forward_res (values bit-identical, gradients equal)."""
+    from ofq_b200.host.layers import LayerNorm
+    torch.manual_seed(20)
+    ln = LayerNorm(384, eps=1e-6).cuda()
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.normal_()
+    x0 = torch.randn(4, 50, 384, device="cuda")
+    a0 = torch.randn(4, 50, 384, device="cuda")
+    w = torch.randn(384, 384, device="cuda") * 0.05
+    outs = []
+    for fused in (True, False):
+        x = x0.clone().requires_grad_(True)
+        a = a0.clone().requires_grad_(True)
+        ln.zero_grad()
+        if fused:
+            r, y = ln.forward_res_add(x * 1.5, a * 0.5)
+        else:
+            r, y = ln.forward_res(x * 1.5 + a * 0.5)
+        out = r + torch.tanh(y @ w)
+        out.square().sum().backward()
+        outs.append((out.detach(), x.grad.clone(), a.grad.clone(), ln.weight.grad.clone(), ln.bias.grad.clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for u, v in zip(*outs):
+        assert rel_err(u, v) < 1e-6
+
+
 def test_gemm_pair_kernel_forced(ops):
     """The CTA-pair (cta_group::2) kernel is chosen by a shape heuristic; OFQ_GEMM_PAIR=2 forces it wherever it is legal
     (M > 128, no dual-A), so the whole GEMM test matrix (int8 exact, fp16 / bf16, MN-major, batched, split-K, outer-K) runs
