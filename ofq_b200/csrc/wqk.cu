@@ -16,12 +16,15 @@ struct SgemmProblem {
 };
 struct SgemmPair { SgemmProblem p[2]; };
 
-template <int TM>
+// BK: k-extent of a shared-memory tile. The loop is not double buffered, so every tile exposes one global-load round trip:
+// the small backward products (16-row tiles, K = 384) take 64-deep tiles (6 round trips instead of 24, 20 loads in flight
+// per thread).
+template <int TM, int BK>
 __global__ void __launch_bounds__(256)
 sgemm_strided_kernel(const SgemmPair pair, int nb, int M, int N, int K) {
     constexpr int RM = TM / 16;
-    __shared__ float As[16][TM + 4];
-    __shared__ float Bs[16][64 + 4];
+    __shared__ float As[BK][TM + 4];
+    __shared__ float Bs[BK][64 + 4];
     const SgemmProblem& q = pair.p[blockIdx.z / nb];
     const int b = blockIdx.z % nb;
     const int m0 = blockIdx.y * TM, n0 = blockIdx.x * 64;
@@ -30,27 +33,29 @@ sgemm_strided_kernel(const SgemmPair pair, int nb, int M, int N, int K) {
     const float* Bb = q.B + b * q.bsB;
     const long long sAk = q.sAk, sAm = q.sAm, sBk = q.sBk, sBn = q.sBn;
     float acc[RM][4] = {};
-    for (int k0 = 0; k0 < K; k0 += 16) {
-        for (int i = t; i < 16 * TM; i += 256) {
+    for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll 4
+        for (int i = t; i < BK * TM; i += 256) {
             int kk, mm;
-            if (sAm == 1) { kk = i / TM; mm = i % TM; } else { kk = i & 15; mm = i >> 4; }
+            if (sAm == 1) { kk = i / TM; mm = i % TM; } else { kk = i % BK; mm = i / BK; }
             const int k = k0 + kk, m = m0 + mm;
             As[kk][mm] = (k < K && m < M) ? __ldg(Ab + k * sAk + m * sAm) : 0.f;
         }
-        for (int i = t; i < 16 * 64; i += 256) {
+#pragma unroll 4
+        for (int i = t; i < BK * 64; i += 256) {
             int kb, nn;
-            if (sBn == 1) { kb = i >> 6; nn = i & 63; } else { kb = i & 15; nn = i >> 4; }
+            if (sBn == 1) { kb = i >> 6; nn = i & 63; } else { kb = i % BK; nn = i / BK; }
             const int k2 = k0 + kb, n = n0 + nn;
             Bs[kb][nn] = (k2 < K && n < N) ? __ldg(Bb + k2 * sBk + n * sBn) : 0.f;
         }
         __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
+#pragma unroll 16
+        for (int kk = 0; kk < BK; ++kk) {
             float a[RM], bb[4];
 #pragma unroll
             for (int i = 0; i < RM; ++i) a[i] = As[kk][ty * RM + i];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) bb[j] = Bs[kk][tx * 4 + j];
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            bb[0] = b4.x; bb[1] = b4.y; bb[2] = b4.z; bb[3] = b4.w;
 #pragma unroll
             for (int i = 0; i < RM; ++i)
 #pragma unroll
@@ -136,13 +141,13 @@ int launch(const SgemmPair& pair, int nprob, int M, int N, int K, int nb, cudaSt
     const long long tiles32 = (long long)((N + 63) / 64) * ((M + 31) / 32) * nb * nprob;
     if (tiles64 >= 148) {
         dim3 grid((N + 63) / 64, (M + 63) / 64, nb * nprob);
-        sgemm_strided_kernel<64><<<grid, 256, 0, st>>>(pair, nb, M, N, K);
+        sgemm_strided_kernel<64, 16><<<grid, 256, 0, st>>>(pair, nb, M, N, K);
     } else if (false && tiles32 >= 128) {   // measured slower than the 16-row tiles on B200 (67 vs 58 us): kept for reference   // the backward pair of a DeiT-S layer: 144 CTAs of 32 x 64 (2 x 4 outputs per thread)
         dim3 grid((N + 63) / 64, (M + 31) / 32, nb * nprob);
-        sgemm_strided_kernel<32><<<grid, 256, 0, st>>>(pair, nb, M, N, K);
+        sgemm_strided_kernel<32, 32><<<grid, 256, 0, st>>>(pair, nb, M, N, K);
     } else {
         dim3 grid((N + 63) / 64, (M + 15) / 16, nb * nprob);
-        sgemm_strided_kernel<16><<<grid, 256, 0, st>>>(pair, nb, M, N, K);
+        sgemm_strided_kernel<16, 64><<<grid, 256, 0, st>>>(pair, nb, M, N, K);
     }
     OFQ_CUDA(cudaGetLastError());
     return 0;

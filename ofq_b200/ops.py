@@ -44,10 +44,12 @@ def _call(family: str, nkernels: int, alg_bytes: float, alg_flops: float, fn, *a
 
 # ------------------------------------------------------------------------------------------------ side stream
 # Weight-gradient work (the split-K dW GEMMs, the W_qk product backward) does not feed the activation-gradient chain of a
-# layer: inside one autograd backward it is queued on a second stream, where the tensor-bound GEMM overlaps the HBM-bound
-# STE / LayerNorm passes of the main chain, and joined before the backward returns (so autograd, DDP and the optimizer
-# only ever see completed gradients on the current stream). Works the same under CUDA-graph capture (fork / join edges).
-SIDE_ENABLED = os.environ.get("OFQ_SIDE_STREAM", "1") != "0"
+# layer: inside one autograd backward it can be queued on a second stream and joined before the backward returns (so
+# autograd, DDP and the optimizer only ever see completed gradients on the current stream; works the same under CUDA-graph
+# capture: fork / join edges). OFF by default (OFQ_SIDE_STREAM=1 turns it on): measured on B200, the persistent GEMM CTAs
+# (168 registers x 320 threads, ~200 KB of shared memory) leave no room for a streaming CTA on the same SM, so the two
+# streams only take SMs from each other: 22.9 ms per step with the side stream against 22.3 ms without.
+SIDE_ENABLED = os.environ.get("OFQ_SIDE_STREAM", "0") == "1"
 _SIDE = {}
 _SIDE_KEEP = []
 
