@@ -717,7 +717,6 @@ lsq_bwd_finalize_cols(const float* __restrict__ colpart, int cols, long long nbl
 __device__ __forceinline__ void
 lsq_bwd_finalize_rows(const float* __restrict__ rowpart, long long total, long long nscale, float g,
                       float* __restrict__ d_s, int bx) {
-    __shared__ float red[8][33];
     if (nscale < 32) {
         // few scales, many partials each (the per-channel step sizes of the image quantizer: 3 scales, 10^5 partials):
         // all threads stride over the partials with a stride that is a multiple of nscale, so a thread stays on one scale
@@ -735,17 +734,20 @@ lsq_bwd_finalize_rows(const float* __restrict__ rowpart, long long total, long l
         }
         return;
     }
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const long long i = (long long)bx * 32 + tx;
+    // block = 8 scales x 32 slices of the reduction axis (a warp reads four 32-byte runs per load): four times the CTAs of a
+    // 32 x 8 split, which matters for the 198-scale quantizers whose partials (1.2 MB for fc2) were summed by 7 CTAs
+    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+    const long long i = (long long)bx * 8 + tx;
     float acc = 0.f;
     if (i < nscale)
-        for (long long j = i + (long long)ty * nscale; j < total; j += 8 * nscale) acc += rowpart[j];
-    red[ty][tx] = acc;
+        for (long long j = i + (long long)ty * nscale; j < total; j += 32 * nscale) acc += rowpart[j];
+    __shared__ float red2[32][9];
+    red2[ty][tx] = acc;
     __syncthreads();
     if (ty == 0 && i < nscale) {
         float s = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s += red[k][tx];
+        for (int k = 0; k < 32; ++k) s += red2[k][tx];
         d_s[i] = g * s;
     }
 }
@@ -1480,7 +1482,7 @@ static int lsq_bwd_finalize_impl(const float* workspace, long long rows, int col
     a.v1 = v1; a.n1 = n1; a.v2 = v2; a.n2 = n2; a.mult = mult; a.product = product; a.out4 = out4;
     a.ncx = (cols + 31) / 32;
     a.ncb = 3 * a.ncx;
-    a.nrb = (d_s && scale_mode == OFQ_SCALE_PER_ROW) ? (int)((a.nscale + 31) / 32) : 0;
+    a.nrb = (d_s && scale_mode == OFQ_SCALE_PER_ROW) ? (a.nscale < 32 ? 1 : (int)((a.nscale + 7) / 8)) : 0;
     lsq_bwd_finalize_kernel<<<(unsigned)(a.ncb + a.nrb + (out4 ? 1 : 0)), 256, 0, (cudaStream_t)stream>>>(a);
     OFQ_CUDA(cudaGetLastError());
     return 0;
