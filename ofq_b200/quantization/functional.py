@@ -291,6 +291,77 @@ class ImgLsqFn(torch.autograd.Function):
         return (dx.view_as(xc) if ctx.needs_input_grad[0] else None), db4, daft, ds, None, None
 
 
+class PatchEmbedFn(torch.autograd.Function):
+    """The 8-bit patch-embedding convolution (qlinear.py:138-191) with stride = kernel as integer GEMMs on the tensor cores:
+    move_b4 -> LsqQuantizer4img -> move_aft on the image (lsq.py:306-382, qbias.py:15-23), im2col of the int8 CODES, and
+
+        out[b,p,n] = sum_c (s_c se_w[n]) sum_{ij} q[b,p,c,ij] qw[n,c,ij]  +  sum_{c,ij} aft[p,ij] W_hat[n,c,ij]  +  bias[n]
+
+    one exact int8 GEMM per input channel (the per-channel step size s_c is constant inside it), accumulated in fp32 on top
+    of the batch-independent shift term. `what` is the already fake-quantized weight (LsqQuantizer4Conv2d keeps its torch
+    autograd: this node hands back d what), `se_w` its effective per-output-channel step (no gradient through it here).
+    Backward (fp16 range-scaled operand like every other backward GEMM): d x_hat = col2im(dY W_hat) -> the LSQ backward of
+    the image quantizer; d what = dY^T x_hat with the integer part on the tensor cores and the shift part as a small GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, b4, aft, s_img, what, se_w, bias, lo: int, hi: int):
+        B, Cin, H, W = x.shape
+        Cout, _, kh, kw = what.shape
+        gh, gw = H // kh, W // kw
+        P, KK = gh * gw, kh * kw
+        K, M = Cin * KK, B * P
+        xc = x.contiguous()
+        x2d = xc.view(B * Cin, H * W)
+        g = grad_scale_factor(hi, B * H * W)
+        se = ops.lsq_effective_scale(s_img, g)                       # [Cin]
+        codes = ops.lsq_quant(x2d, b4, se, PER_ROW, Cin, 1, lo, hi)  # int8 [B*Cin, H*W]
+        qcols = codes.view(B, Cin, gh, kh, gw, kw).permute(0, 2, 4, 1, 3, 5).contiguous().view(M, K)
+        w2d = what.detach().reshape(Cout, K)
+        qw = torch.round(w2d / se_w.view(-1, 1)).to(torch.int8)      # exact: what = code * se_w
+        aftcols = aft.detach().view(gh, kh, gw, kw).permute(0, 2, 1, 3).reshape(P, KK)
+        shift = torch.addmm(bias.detach(), aftcols, w2d.view(Cout, Cin, KK).sum(1).t())          # [P, Cout]
+        out = shift.unsqueeze(0).expand(B, P, Cout).contiguous().view(M, Cout)
+        csw = (se.view(-1, 1) * se_w.view(1, -1)).contiguous()       # [Cin, Cout]
+        for c in range(Cin):
+            ops.gemm(GEMM_I8, qcols[:, c * KK:], (K, 0, 0, 0), qw[:, c * KK:], (K, 0, 0, 0), out, (Cout, 0, 0), M, Cout, KK,
+                     accumulate=True, cs=vec(csw[c]))
+        ctx.save_for_backward(xc, b4, se, qcols, qw, se_w, aftcols)
+        ctx.cfg = (lo, hi, g, B, Cin, H, W, Cout, kh, kw)
+        return out.view(B, gh, gw, Cout).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dout):
+        xc, b4, se, qcols, qw, se_w, aftcols = ctx.saved_tensors
+        lo, hi, g, B, Cin, H, W, Cout, kh, kw = ctx.cfg
+        gh, gw = H // kh, W // kw
+        P, KK = gh * gw, kh * kw
+        K, M = Cin * KK, B * P
+        dY = dout.permute(0, 2, 3, 1).reshape(M, Cout)
+        if not dY.is_contiguous():
+            dY = dY.contiguous()
+        # ONE fp16 copy A16[m,n] = fp16(dY se_w[n] sc), K-major for d x_hat and MN-major for d what
+        sc = ops.absmax_scale(dY, 1, M, Cout, Cout, 0, cs=se_w)
+        prep = ops.grad_prep(dY, 1, M, Cout, Cout, 0, cs=se_w, want_rm=True, want_colsum=True, fmt=FMT, scale4=sc)
+        a16, dbias = prep["rm"], prep["colsum"]
+        qw16 = ops.codes_to_bf16(qw, 1, Cout, K, K, 0, False, FMT)
+        dxcols = torch.empty((M, K), dtype=torch.float32, device=dY.device)
+        ops.gemm(GEMM_BWD, a16, (Cout, 0, 0, 0), qw16, (K, 0, 0, 0), dxcols, (K, 0, 0), M, K, Cout, b_mn=True, cs=_scalar(sc))
+        # d what[n,k] = s_c(k) / (se_w[n] sc) sum_m A16[m,n] q[m,k]  +  sum_p (sum_b dY[b,p,n]) aft[p, k % KK]
+        q16 = ops.codes_to_bf16(qcols, 1, M, K, K, 0, False, FMT)
+        colscale = (se.repeat_interleave(KK) * sc[1]).contiguous()
+        inv_sew = (1.0 / se_w).contiguous()
+        dwhat = torch.zeros((Cout, K), dtype=torch.float32, device=dY.device)
+        ops.gemm(GEMM_BWD, a16, (Cout, 0, 0, 0), q16, (K, 0, 0, 0), dwhat, (K, 0, 0), Cout, K, M, a_mn=True, b_mn=True, splits=0,
+                 accumulate=True, rs=vec(inv_sew), cs=vec(colscale))
+        dysum = dY.view(B, P, Cout).sum(0)                           # [P, Cout]
+        dwhat.view(Cout, Cin, KK).add_((dysum.t() @ aftcols).unsqueeze(1))
+        # d x_hat back in image layout, then the image quantizer's straight-through / scale / shift gradients
+        dxhat = dxcols.view(B, gh, gw, Cin, kh, kw).permute(0, 3, 1, 4, 2, 5).contiguous().view(B * Cin, H * W)
+        dx, ds, db4, daft = ops.lsq_bwd(dxhat, xc.view(B * Cin, H * W), b4, se, PER_ROW, Cin, 1, lo, hi, g)
+        return ((dx.view_as(xc) if ctx.needs_input_grad[0] else None), db4, daft, ds, dwhat.view(Cout, Cin, kh, kw), None,
+                dbias, None, None)
+
+
 # ====================================================================================== attention core
 def _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C):
     """out[b,n,h*hd+j] = se_p[n] * (se_v[hj] * sum_d qp[z,n,d] qv[b,d,hj] + v_aft[hj] * sum_d qp[z,n,d])."""

@@ -8,7 +8,9 @@ import torch.nn.functional as F
 
 from ...host.deit import Mlp
 from ...ops import ACT_GELU, ACT_NONE
-from ..functional import MlpLink, QLinearFn
+from ..functional import F16 as F16_BWD
+from ..functional import MlpLink, PatchEmbedFn, QLinearFn
+from ..quantizer.lsq import _eff_scale
 from ..quantizer.lsq import (LsqQuantizer, LsqQuantizer4Conv2d, LsqQuantizer4head_input, LsqQuantizer4img,
                              LsqQuantizerWeight)
 from ..quantizer.statsq import StatsQuantizer
@@ -138,8 +140,18 @@ class LSQ_QConv2d(nn.Conv2d):
 
     def forward(self, input):
         weight = self.lsqw_fn(self.weight)
-        input = self.input_quant_fn.forward_with_shifts(input, self.move_b4, self.move_aft)
         kh, kw = self.kernel_size
+        q = self.input_quant_fn
+        patchify = (tuple(self.stride) == (kh, kw) and tuple(self.padding) == (0, 0) and tuple(self.dilation) == (1, 1)
+                    and self.groups == 1 and input.shape[-2] % kh == 0 and input.shape[-1] % kw == 0)
+        if (patchify and F16_BWD and q.fused_ready(input, self.move_b4, self.move_aft) and (kh * kw) % 16 == 0
+                and self.lsqw_fn.initialized_alpha and self.bias is not None):
+            # integer codes of image and weight straight into int8 tensor-core GEMMs (functional.PatchEmbedFn)
+            w = self.lsqw_fn
+            se_w = _eff_scale(w.s.detach(), 1.0 / ((w.thd_pos * weight[0].numel()) ** 0.5))
+            return PatchEmbedFn.apply(input, self.move_b4.bias, self.move_aft.bias, q.s, weight, se_w, self.bias,
+                                      -(2 ** (q.bit - 1)), 2 ** (q.bit - 1) - 1)
+        input = self.input_quant_fn.forward_with_shifts(input, self.move_b4, self.move_aft)
         if (tuple(self.stride) == (kh, kw) and tuple(self.padding) == (0, 0) and tuple(self.dilation) == (1, 1)
                 and self.groups == 1 and input.shape[-2] % kh == 0 and input.shape[-1] % kw == 0):
             # patchify convolution == one GEMM over unfolded patches; done as a true-fp32 matmul because cuDNN

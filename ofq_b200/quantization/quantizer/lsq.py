@@ -159,12 +159,19 @@ class LsqQuantizer4img(_Lsq8):
             self._set_s(f * x.detach().abs().mean(dim=-1).mean(dim=-1).mean(dim=0) / (self.thd_pos ** 0.5))
         return self._quant(x, self.s.view(1, -1, 1, 1), x.shape[0] * x.shape[2] * x.shape[3])
 
+    def fused_ready(self, x, move_b4, move_aft) -> bool:
+        """The step size exists, the data is known to be signed (8-bit codes in [-128, 127]) and the image is an fp32 CUDA
+        batch whose pixels match the per-pixel shifts: the hot-path LSQ kernels apply in the [B*Cin, H*W] view."""
+        if x.dim() != 4:
+            return False
+        H, W = x.shape[-2], x.shape[-1]
+        return bool(self.initialized_alpha and self._signed_host == 1 and x.is_cuda and x.dtype == torch.float32
+                    and H == W and move_b4.bias.numel() == H * W and move_aft.bias.numel() == H * W and (H * W) % 4 == 0
+                    and self.bit <= 8 and x.shape[1] == self.s.numel())
+
     def forward_with_shifts(self, x, move_b4, move_aft):
         """move_aft(self(move_b4(x))) (qlinear.py:171). Once the step size exists and the data is known to be signed (8-bit
         codes in [-128, 127]), fp32 CUDA images take ONE fused kernel per direction (functional.ImgLsqFn)."""
-        H, W = x.shape[-2], x.shape[-1]
-        if (self.initialized_alpha and self._signed_host == 1 and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
-                and H == W and move_b4.bias.numel() == H * W and move_aft.bias.numel() == H * W and (H * W) % 4 == 0
-                and self.bit <= 8 and x.shape[1] == self.s.numel()):
+        if self.fused_ready(x, move_b4, move_aft):
             return ImgLsqFn.apply(x, move_b4.bias, move_aft.bias, self.s, -(2 ** (self.bit - 1)), 2 ** (self.bit - 1) - 1)
         return move_aft(self(move_b4(x)))

@@ -5,6 +5,11 @@ import collections, csv, json, re, sys
 one_step = "--one-step" in sys.argv
 if one_step:
     sys.argv.remove("--one-step")
+rng = None          # --range a:b keeps launches a <= index < b of the capture (in launch order)
+for a in list(sys.argv):
+    if a.startswith("--range="):
+        rng = tuple(int(v) for v in a[8:].split(":"))
+        sys.argv.remove(a)
 src, dst = sys.argv[1], sys.argv[2]
 lines = [l for l in open(src) if not l.startswith("==")]
 cur = {}
@@ -34,6 +39,9 @@ if one_step:   # keep exactly one QAT step: the launches between the last AdamW 
     ends = [i for j, i in enumerate(opt) if j + 1 == len(opt) or opt[j + 1] - i > 50]
     assert len(ends) >= 2, "the capture does not hold a whole step"
     cur = {ik: cur[ik] for ik in keys[ends[-2] + 1: ends[-1] + 1]}
+if rng is not None:
+    keys = sorted(cur, key=lambda ik: int(ik[0]))
+    cur = {ik: cur[ik] for ik in keys[rng[0]:rng[1]]}
 per = collections.defaultdict(lambda: dict(n=0, ns=0.0, rd=0.0, wr=0.0))
 for (_, k), d in cur.items():
     p = per[family(k)]
