@@ -283,3 +283,40 @@ def test_step_prologue_matches_per_layer_path(Q):
         for n in g_b:
             assert rel_err(g_a[n], g_b[n]) < 1e-5 or (g_a[n] - g_b[n]).abs().max().item() <= 1e-6 * gmax, n
         opt.step()                                  # weights move: the next forward must see the new codes
+
+
+@pytest.mark.parametrize("patch,cout", [(16, 64), (32, 96)])
+def test_patch_embed_int8_path_matches_torch_composition(Q, patch, cout):
+    """LSQ_QConv2d (8-bit patch embedding): the int8 tensor-core path (functional.PatchEmbedFn) against the op-for-op torch
+    composition of qlinear.py:138-191 that it replaces: output <= 1e-5, every gradient (image, per-pixel shifts, the three
+    image step sizes, conv weight, weight step sizes, bias) <= 1e-3 (the backward GEMM operand is fp16 range-scaled)."""
+    from ofq_b200.quantization.modules import qlinear as QL
+    torch.manual_seed(43)
+    conv = nn.Conv2d(3, cout, patch, patch)
+    mod = QL.LSQ_QConv2d(m=conv, pretrained_initialized=True).cuda()
+    with torch.no_grad():
+        mod.move_b4.bias.normal_(0, 0.05)
+        mod.move_aft.bias.normal_(0, 0.05)
+    x0 = torch.randn(4, 3, 224, 224, device="cuda")
+    with torch.no_grad():
+        mod(x0)                                       # creates the step sizes and latches the sign (torch path)
+    gout = torch.randn(4, cout, 224 // patch, 224 // patch, device="cuda")
+    res = []
+    for fused in (True, False):
+        x = x0.clone().requires_grad_(True)
+        mod.zero_grad(set_to_none=True)
+        saved = QL.F16_BWD
+        QL.F16_BWD = saved and fused                  # the switch that routes LSQ_QConv2d.forward to PatchEmbedFn
+        try:
+            out = mod(x)
+        finally:
+            QL.F16_BWD = saved
+        assert (type(out.grad_fn).__name__ == "PatchEmbedFnBackward") == fused
+        (out * gout).sum().backward()
+        res.append((out.detach(), x.grad.clone(), {n: p.grad.clone() for n, p in mod.named_parameters()}))
+    (o1, dx1, g1), (o0, dx0, g0) = res
+    assert rel_err(o1, o0) < 1e-5
+    assert rel_err(dx1, dx0) < GRAD_TOL
+    assert set(g1) == set(g0)
+    for n in g0:
+        assert rel_err(g1[n], g0[n]) < GRAD_TOL, n
