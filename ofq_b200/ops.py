@@ -492,7 +492,7 @@ def build_adamw_table(entries, device) -> tuple:
         first += (n + 1023) // 1024
         total += n
     # pinned staging + async copy: legal inside CUDA-graph capture (the caller keeps `host` alive with the table)
-    host = torch.frombuffer(bytes(blob), dtype=torch.uint8).clone().pin_memory()
+    host = torch.frombuffer(blob, dtype=torch.uint8).clone().pin_memory()      # bytearray: writable, no aliasing warning
     t = host.to(device, non_blocking=True)
     t._ofq_host = host
     return t, len(entries), first, total
