@@ -181,6 +181,28 @@ __device__ __forceinline__ int lsq_code_fast(float x, float b4, float s, float i
     if (fabsf(v - r) > 0.4998f) r = rintf(fminf(fmaxf(__fdiv_rn(a, s), qlo), qhi));
     return __float2int_rn(fminf(fmaxf(r, qlo), qhi));      // rint(clamp(v)) == clamp(rint(v)) for integer bounds
 }
+// Four codes at once: the cheap quotients and roundings carry no branch; ONE (rare) branch redoes all four with the IEEE
+// division when any of them sits near a rounding boundary (same codes wherever it did not), so the common path of the
+// instruction-bound variants (GELU, fp16 copy, code dot) is straight-line code.
+__device__ __forceinline__ void lsq_code4_fast(const float4 x, const float4 b4, const float4 s, const float4 inv_s, float qlo,
+                                               float qhi, int* q) {
+    const float a[4] = {__fadd_rn(x.x, b4.x), __fadd_rn(x.y, b4.y), __fadd_rn(x.z, b4.z), __fadd_rn(x.w, b4.w)};
+    const float sv[4] = {s.x, s.y, s.z, s.w}, iv[4] = {inv_s.x, inv_s.y, inv_s.z, inv_s.w};
+    float r[4];
+    bool redo = false;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float v = __fmul_rn(a[e], iv[e]);
+        r[e] = rintf(v);
+        redo |= fabsf(v - r[e]) > 0.4998f;
+    }
+    if (redo) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r[e] = rintf(fminf(fmaxf(__fdiv_rn(a[e], sv[e]), qlo), qhi));
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) q[e] = __float2int_rn(fminf(fmaxf(r[e], qlo), qhi));   // rint(clamp(v)) == clamp(rint(v)) for integer bounds
+}
 // {a, b, c, d} -> four saturated int8 bytes, a in the lowest byte
 __device__ __forceinline__ uint32_t pack4_i8(int a, int b, int c, int d) {
     uint32_t hi, r;
@@ -296,10 +318,9 @@ lsq_quant_vec_kernel(const float* __restrict__ x, uint32_t rows, int cols, long 
             }
             if (ACT == OFQ_ACT_GELU)
                 xv[u] = make_float4(gelu_fwd(xv[u].x), gelu_fwd(xv[u].y), gelu_fwd(xv[u].z), gelu_fwd(xv[u].w));
-            const int q0 = lsq_code_fast(xv[u].x, b.x, s4.x, i4.x, qlo, qhi);
-            const int q1 = lsq_code_fast(xv[u].y, b.y, s4.y, i4.y, qlo, qhi);
-            const int q2 = lsq_code_fast(xv[u].z, b.z, s4.z, i4.z, qlo, qhi);
-            const int q3 = lsq_code_fast(xv[u].w, b.w, s4.w, i4.w, qlo, qhi);
+            int qv[4];
+            lsq_code4_fast(xv[u], b, s4, i4, qlo, qhi, qv);
+            const int q0 = qv[0], q1 = qv[1], q2 = qv[2], q3 = qv[3];
             *reinterpret_cast<uint32_t*>(cp + (long long)r * ldq) = pack4_i8(q0, q1, q2, q3);
             if (codes16)       // exact 16-bit copy: the operand of the backward GEMMs, written while the codes are in registers
                 *reinterpret_cast<uint2*>(codes16 + (long long)r * ld16 + col) =
