@@ -203,6 +203,10 @@ __device__ __forceinline__ void lsq_code4_fast(const float4 x, const float4 b4, 
 #pragma unroll
     for (int e = 0; e < 4; ++e) q[e] = __float2int_rn(fminf(fmaxf(r[e], qlo), qhi));   // rint(clamp(v)) == clamp(rint(v)) for integer bounds
 }
+// Codes of Q(GELU(x) + b4): GELU_fast and the cheap quotient on the straight-line path, the band around the rounding
+// boundaries widened by the error bound of GELU_fast; the rare fallback evaluates erff and the IEEE quotient for all four.
+__device__ __forceinline__ void lsq_code4_gelu(const float4 x, const float4 b4, const float4 s, const float4 inv_s, float qlo,
+                                               float qhi, int* q);
 // {a, b, c, d} -> four saturated int8 bytes, a in the lowest byte
 __device__ __forceinline__ uint32_t pack4_i8(int a, int b, int c, int d) {
     uint32_t hi, r;
@@ -230,6 +234,50 @@ __device__ __forceinline__ void gelu_both(float x, float* a, float* d) {
     *a = __fmul_rn(__fmul_rn(x, 0.5f), e1);
     *d = fmaf(x, __expf(-0.5f * x * x) * 0.39894228040143267794f, 0.5f * e1);
 }
+// Fast GELU for the instruction-bound fused variants: erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 in exact
+// arithmetic, ~5e-7 with rcp.approx / ex2.approx and fp32 rounding), branch-free, one MUFU.RCP + one MUFU.EX2 instead of
+// erff's two-regime evaluation. |GELU_fast(x) - GELU(x)| <= 0.5 |x| 5e-7. It never decides a code or a straight-through
+// mask on its own: wherever the quotient (GELU(x) + b4) / s comes within kGeluGuard |x| / s of a rounding boundary or a
+// clamp bound, the element is redone with gelu_fwd (erff) and, in the forward, the IEEE division. *gauss receives
+// exp(-x^2 / 2), which the derivative needs anyway.
+constexpr float kGeluGuard = 4e-6f;      // 16x the error bound of GELU_fast, relative to |x|
+__device__ __forceinline__ float gelu_fast(float x, float* gauss, float* one_plus_erf) {
+    const float z = x * 0.70710678118654752440f;
+    const float az = fabsf(z);
+    const float t = rcp_approx(fmaf(0.3275911f, az, 1.0f));
+    float poly = fmaf(t, 1.061405429f, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float e = __expf(-az * az);
+    *gauss = e;
+    const float e1 = 1.0f + copysignf(fmaf(-poly * t, e, 1.0f), z);
+    *one_plus_erf = e1;
+    return (x * 0.5f) * e1;
+}
+
+__device__ __forceinline__ void lsq_code4_gelu(const float4 x, const float4 b4, const float4 s, const float4 inv_s, float qlo,
+                                               float qhi, int* q) {
+    const float xv[4] = {x.x, x.y, x.z, x.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+    const float sv[4] = {s.x, s.y, s.z, s.w}, iv[4] = {inv_s.x, inv_s.y, inv_s.z, inv_s.w};
+    float r[4];
+    bool redo = false;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        float gauss, e1;
+        const float v = __fmul_rn(__fadd_rn(gelu_fast(xv[e], &gauss, &e1), bv[e]), iv[e]);
+        r[e] = rintf(v);
+        redo |= fabsf(v - r[e]) > 0.4998f - kGeluGuard * fabsf(xv[e] * iv[e]);
+    }
+    if (redo) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            r[e] = rintf(fminf(fmaxf(__fdiv_rn(__fadd_rn(gelu_fwd(xv[e]), bv[e]), sv[e]), qlo), qhi));
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) q[e] = __float2int_rn(fminf(fmaxf(r[e], qlo), qhi));
+}
+
 // two floats -> packed fp16 / bf16 pair (round to nearest), first in the low half
 __device__ __forceinline__ uint32_t pack_rn16(float a, float b, bool f16) {
     uint32_t r;
@@ -316,10 +364,9 @@ lsq_quant_vec_kernel(const float* __restrict__ x, uint32_t rows, int cols, long 
                 s4 = make_float4(sv[u], sv[u], sv[u], sv[u]);
                 i4 = make_float4(iv, iv, iv, iv);
             }
-            if (ACT == OFQ_ACT_GELU)
-                xv[u] = make_float4(gelu_fwd(xv[u].x), gelu_fwd(xv[u].y), gelu_fwd(xv[u].z), gelu_fwd(xv[u].w));
             int qv[4];
-            lsq_code4_fast(xv[u], b, s4, i4, qlo, qhi, qv);
+            if (ACT == OFQ_ACT_GELU) lsq_code4_gelu(xv[u], b, s4, i4, qlo, qhi, qv);
+            else lsq_code4_fast(xv[u], b, s4, i4, qlo, qhi, qv);
             const int q0 = qv[0], q1 = qv[1], q2 = qv[2], q3 = qv[3];
             *reinterpret_cast<uint32_t*>(cp + (long long)r * ldq) = pack4_i8(q0, q1, q2, q3);
             if (codes16)       // exact 16-bit copy: the operand of the backward GEMMs, written while the codes are in registers
