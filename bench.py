@@ -24,9 +24,10 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "QAT images/sec, DeiT-S W2A2 attn_q (QKR) step, synthetic 224x224"
 UNIT = "images/s"
-MODELS = {"deit_small": dict(embed_dim=384, depth=12, num_heads=6), "deit_tiny": dict(embed_dim=192, depth=12, num_heads=3)}
+MODELS = {"deit_small": dict(embed_dim=384, depth=12, num_heads=6), "deit_tiny": dict(embed_dim=192, depth=12, num_heads=3),
+          "swin_tiny": None}      # BASELINE.json config 4 (W3A3: --bits 3): quantized shifted-window attention, host/swin.py
 # forward GFLOP per image in the quantized GEMMs of the hot path; a QAT step is 3x
-GFLOP_FWD_PER_IMG = {"deit_small": 13.74, "deit_tiny": 3.00}
+GFLOP_FWD_PER_IMG = {"deit_small": 13.74, "deit_tiny": 3.00, "swin_tiny": 16.5}
 
 
 BWD_DTYPE = {"f16": "range-scaled fp16", "bf16x2": "bf16 hi+lo", "bf16": "bf16"}
@@ -65,7 +66,7 @@ T0 = time.perf_counter()
 def workload_name(a):
     what = {"qat": "QAT step (fwd+bwd+AdamW)", "cga": "CGA fine-tune step (fwd+bwd+freeze-masked AdamW)",
             "eval": "eval forward (no grad)"}[getattr(a, "mode", "qat")]
-    return (f"{a.model.replace('_', '-')} distilled W{a.bits}A{a.bits} attn_q {'plain' if a.no_qkr else 'QKR'} {what}, "
+    return (f"{a.model.replace('_', '-')}{'' if a.model.startswith('swin') else ' distilled'} W{a.bits}A{a.bits} attn_q {'plain' if a.no_qkr else 'QKR'} {what}, "
             f"batch {a.batch}/GPU, synthetic 224x224, random init")
 
 
@@ -204,10 +205,18 @@ def main():
     from ofq_b200.quantization.functional import BWD_MODE as bwd_mode
     cfg = MODELS[a.model]
     torch.manual_seed(0)                      # identical initial weights on every rank
-    model = DistilledVisionTransformer(num_classes=1000, **cfg)
-    names = Q.deit_qmodule_names(cfg["depth"])
-    model = Q.replace_module_by_qmodule_deit(model, Q.make_qconfigs(names, a.bits, a.bits), pretrained_initialized=True,
-                                             qk_reparam=not a.no_qkr, qk_reparam_type=1 if a.mode == "cga" else 0).to(dev)
+    swin = a.model.startswith("swin")
+    if swin:
+        from ofq_b200.host.swin import swin_t
+        model = swin_t(num_classes=1000)
+        model = Q.replace_module_by_qmodule_swin(model, Q.make_qconfigs(Q.swin_qmodule_names(), a.bits, a.bits),
+                                                 pretrained_initialized=True, qk_reparam=not a.no_qkr,
+                                                 qk_reparam_type=1 if a.mode == "cga" else 0).to(dev)
+    else:
+        model = DistilledVisionTransformer(num_classes=1000, **cfg)
+        names = Q.deit_qmodule_names(cfg["depth"])
+        model = Q.replace_module_by_qmodule_deit(model, Q.make_qconfigs(names, a.bits, a.bits), pretrained_initialized=True,
+                                                 qk_reparam=not a.no_qkr, qk_reparam_type=1 if a.mode == "cga" else 0).to(dev)
     gen = torch.Generator().manual_seed(1234 + rank)
     B = a.batch
     h_img = torch.randn(B, 3, 224, 224, generator=gen).pin_memory()
@@ -223,10 +232,10 @@ def main():
     if a.mode == "cga":       # cga.py:953-1013: every StatsQ-quantized block weight is freeze-masked inside the AdamW kernel
         pd = dict(model.named_parameters())
         masked = [pd[n] for n in cga_masked_parameter_names(model, qk_reparam=not a.no_qkr)]
-        opt = CGAAdamW(param_groups_weight_decay(model, 0.05, model.no_weight_decay()), lr=1e-5, masked=masked,
+        opt = CGAAdamW(param_groups_weight_decay(model, 0.05, getattr(model, 'no_weight_decay', lambda: set())()), lr=1e-5, masked=masked,
                        wq_bitw=a.bits, boundary_range=0.005)
     else:
-        opt = CGAAdamW(param_groups_weight_decay(model, 0.05, model.no_weight_decay()), lr=5.47e-4)
+        opt = CGAAdamW(param_groups_weight_decay(model, 0.05, getattr(model, 'no_weight_decay', lambda: set())()), lr=5.47e-4)
     # data-parallel gradient exchange (ofq_b200/ddp.py): ONE NCCL all-reduce (mean) of a flat fp32 gradient buffer
     ddp = FlatGradAllReduce(model.parameters(), world) if world > 1 else None
     flat = ddp.flat if ddp is not None else None
@@ -240,8 +249,12 @@ def main():
             opt.zero_grad(set_to_none=True)
         else:
             ddp.zero()
-        (cls, dst), _ = model(img)
-        loss = F.cross_entropy(cls, lbl) + F.cross_entropy(dst, lbl)
+        if swin:
+            logits, _ = model(img)
+            loss = F.cross_entropy(logits, lbl)
+        else:
+            (cls, dst), _ = model(img)
+            loss = F.cross_entropy(cls, lbl) + F.cross_entropy(dst, lbl)
         (ddp.scale_loss(loss) if ddp is not None else loss).backward()
         if ddp is not None:
             ddp.reduce()
@@ -409,7 +422,7 @@ def main():
     if rank != 0:
         return finish()
     cpu = None
-    if world == 1 and not a.no_cpu_baseline:
+    if world == 1 and not a.no_cpu_baseline and not swin:
         threads = os.cpu_count() or 1
         ips, sec = cpu_step_rate(a, 4, 1, threads)
         cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
