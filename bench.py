@@ -146,18 +146,39 @@ class ClockSampler:
 
     def _run(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        # NVML directly when the bindings are there (a query takes microseconds: tens of samples inside a half-second timed
+        # region); otherwise the nvidia-smi line of the profiling recipe (~0.2 s per query)
+        nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            nv = (pynvml, h, bits, get_reasons)
+        except Exception:
+            nv = None
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for n, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(n)
+                if nv is not None:
+                    pynvml, h, bits, get_reasons = nv
+                    self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    r = int(get_reasons(h))
+                    for n, b in bits.items():
+                        if r & b:
+                            self.reasons.add(n)
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                    self.samples.append(float(out[0]))
+                    self.max_mhz = float(out[1])
+                    for n, v in zip(names, out[2:]):
+                        if v.strip().lower().startswith("active"):
+                            self.reasons.add(n)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.02 if nv is not None else 0.2)
 
     def __enter__(self):
         self.t.start()
