@@ -40,6 +40,9 @@ K2P = 1 if DUAL else PLANES          # outer-K slices still looped over
 DD = 1 if DUAL else 0                # dual_delta for operands laid out [plane][...]
 # fp16 mode: let the LSQ backward of the V / qkx quantizers write the fp16 GEMM operand directly (tests toggle this)
 FUSED16 = os.environ.get("OFQ_FUSED16", "1") != "0"
+# Debug tap (parity tests): when a list, every forward of the autograd functions below appends (kind, {name: tensor}) with
+# the integer codes and the pre-quantizer values of each of its quantizers, in call order. None in production.
+TAP = None
 
 
 def levels(bit: int, all_positive: bool):
@@ -177,6 +180,8 @@ class QLinearFn(torch.autograd.Function):
                  rs=vec(se, P), cs=vec(colscale), ct=vec(colterm))
         if link is not None and role == 1:
             link.cs, link.se, link.sc = colscale, se, None
+        if TAP is not None:
+            TAP.append(("qlinear", dict(x=x2d, b4=b4, se=se, period=P, act=act, qx=qx, wc=wc, colscale=colscale, out=out)))
         ctx.save_for_backward(xc, qx, wc, colscale, inv_cs, se2, b4, aft, qx16, wc16)
         ctx.cfg = (P, lo, hi, g, bias is not None, act, link, role)
         return out.view(*x.shape[:-1], Nout)
@@ -497,6 +502,9 @@ class QKRAttnCoreFn(torch.autograd.Function):
         ldq = qp.shape[-1]
         del S
         out = _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C)
+        if TAP is not None:
+            TAP.append(("qkr", dict(x=x2d, x_b4=x_b4, se_x=se_x, qx=qx, wvc=wvc, v_out=v_out, v_b4=v_b4, se_v=se_v, qv=qv, wqkc=wqkc,
+                                    qkx=qkx, k_b4=k_b4, se_k=se_k, qk=qk, P=P, se_p=se_p, qp=qp, out=out, B=B, N=N, H=H, C=C)))
         ctx.save_for_backward(xc, wq, wk, x_b4, x_aft, v_b4, v_aft, k_b4, k_aft, qx, sx2, wvc, cs_v, ics_v, v_out, qv, sv2,
                               wqkc, cs_qk, ics_qk, qkx, qk, sk2, sk2_hn, P, qp, sp2, qx16, qv16, qk16, qp16, wv16, wqk16)
         ctx.cfg = (B, N, C, H, lo, hi, hiu, scale, g_x, g_v, g_k, g_p, ldS, ldq, bv is not None,
@@ -650,6 +658,9 @@ class QAttnCoreFn(torch.autograd.Function):
         ldq = qp.shape[-1]
         del S
         out = _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C)
+        if TAP is not None:
+            TAP.append(("attn", dict(qkv=q2d, b4=b4, se_q=se_q, se_k=se_k, se_v=se_v, qq=qq, qk=qk, qv=qv, P=P, se_p=se_p, qp=qp,
+                                     out=out, B=B, N=N, H=H, C=C)))
         ctx.save_for_backward(qkvc, b4, q_aft, k_aft, v_aft, qq, qk, qv, sq2, sk2, sv2, P, qp, sp2)
         ctx.cfg = (B, N, C, H, lo, hi, hiu, scale, g_qk, g_v, g_p, ldS, ldq, attn_bias is not None, link)
         if link is not None:

@@ -25,6 +25,16 @@ Params = Dict[str, Tensor]
 
 EPS_FLOOR = 1e-5  # lsq.py:593 `clip(alpha, 1e-5)`
 
+# Test instrumentation: when a dict, every LSQ quantizer call made through the layer functions below records
+# {"x": its input, "se": the effective step size, "codes": the integer codes} under the reference's module name
+# (e.g. "blocks.0.attn.quan_a_qkx_fn"), and the layers record a few named intermediates ("<module>.@v_out", ...).
+TAPS: Optional[dict] = None
+
+
+def _tap(name: Optional[str], **kw) -> None:
+    if TAPS is not None and name is not None:
+        TAPS[name] = {k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in kw.items()}
+
 
 # ------------------------------------------------------------------------------------------ STE helpers
 def ste_round(x: Tensor) -> Tensor:
@@ -108,17 +118,19 @@ def lsq_init_cols(x: Tensor, hi: int, all_positive: bool) -> Tensor:
     return f * a / (hi ** 0.5)
 
 
-def _lsq_core(x: Tensor, alpha: Tensor, g: float, lo: int, hi: int, bit: int, all_positive: bool) -> Tensor:
+def _lsq_core(x: Tensor, alpha: Tensor, g: float, lo: int, hi: int, bit: int, all_positive: bool,
+              tap: Optional[str] = None) -> Tensor:
     s = grad_scaled(floor_clip(alpha), g)
     v = x / s
     if bit == 1 and not all_positive:
         v = torch.sign(v)
     else:
         v = ste_round(torch.clamp(v, lo, hi))
+    _tap(tap, x=x, se=s, codes=v.detach().to(torch.int8))
     return v * s
 
 
-def lsq_rows(x: Tensor, s: Tensor, bit: int, all_positive: bool) -> Tensor:
+def lsq_rows(x: Tensor, s: Tensor, bit: int, all_positive: bool, tap: Optional[str] = None) -> Tensor:
     """LsqQuantizer.forward (per_channel=True), lsq.py:571-602: scale indexed by dim -2."""
     lo, hi = lsq_levels(bit, all_positive)
     if x.dim() == 3:
@@ -128,10 +140,10 @@ def lsq_rows(x: Tensor, s: Tensor, bit: int, all_positive: bool) -> Tensor:
     else:
         assert x.dim() == 4
         g = 1.0 / ((hi * x.shape[0] * x.shape[1] * x.shape[-1]) ** 0.5)
-    return _lsq_core(x, s.unsqueeze(-1), g, lo, hi, bit, all_positive)
+    return _lsq_core(x, s.unsqueeze(-1), g, lo, hi, bit, all_positive, tap)
 
 
-def lsq_cols(x: Tensor, s: Tensor, bit: int, all_positive: bool) -> Tensor:
+def lsq_cols(x: Tensor, s: Tensor, bit: int, all_positive: bool, tap: Optional[str] = None) -> Tensor:
     """LsqQuantizer4v.forward, lsq.py:757-790: scale indexed by the last dim."""
     lo, hi = lsq_levels(bit, all_positive)
     if x.dim() == 3:
@@ -141,7 +153,7 @@ def lsq_cols(x: Tensor, s: Tensor, bit: int, all_positive: bool) -> Tensor:
         assert x.dim() == 4
         g = 1.0 / ((hi * x.shape[0] * x.shape[1] * x.shape[2]) ** 0.5)
         a = s.unsqueeze(0).unsqueeze(1).unsqueeze(2)
-    return _lsq_core(x, a, g, lo, hi, bit, all_positive)
+    return _lsq_core(x, a, g, lo, hi, bit, all_positive, tap)
 
 
 def lsq_codes_rows(x: Tensor, s: Tensor, bit: int, all_positive: bool) -> Tensor:
@@ -172,7 +184,7 @@ def lsq_input(x: Tensor, P: Params, pre: str, bit: int, all_positive: bool = Fal
     _, hi = lsq_levels(bit, all_positive)
     x = x + P[pre + "move_b4.bias"].expand_as(x)
     s = _get_scale(P, pre + "input_quant_fn.s", lambda: lsq_init_rows(x, hi, all_positive))
-    x = lsq_rows(x, s, bit, all_positive)
+    x = lsq_rows(x, s, bit, all_positive, tap=pre + "input_quant_fn")
     return x + P[pre + "move_aft.bias"].expand_as(x)
 
 
@@ -182,6 +194,7 @@ def qlinear(x: Tensor, P: Params, pre: str, wbits: int, abits: int, symmetric: b
     xq = lsq_input(x, P, pre, abits, all_positive=not symmetric)
     out = F.linear(xq, w)
     out = out + P[pre + "bias"].view(1, -1).expand_as(out)
+    _tap(pre + "@out", out=out)
     return out
 
 
@@ -196,7 +209,7 @@ def _softmax_quant(attn: Tensor, P: Params, pre: str, abits: int) -> Tensor:
     _, hi = lsq_levels(abits, True)
     prob = F.softmax(attn, dim=-1)
     s = _get_scale(P, pre + "quan_a_softmax_fn.s", lambda: lsq_init_rows(prob, hi, True))
-    return lsq_rows(prob, s, abits, True)
+    return lsq_rows(prob, s, abits, True, tap=pre + "quan_a_softmax_fn")
 
 
 def qattention(x: Tensor, P: Params, pre: str, heads: int, wbits: int, abits: int,
@@ -211,12 +224,12 @@ def qattention(x: Tensor, P: Params, pre: str, heads: int, wbits: int, abits: in
     qkv = qkv.reshape(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0], qkv[1], qkv[2]
     sq = _get_scale(P, pre + "quan_a_q_fn.s", lambda: lsq_init_rows(q, hi, False))
-    q = lsq_rows(q, sq, abits, False)
+    q = lsq_rows(q, sq, abits, False, tap=pre + "quan_a_q_fn")
     sk = _get_scale(P, pre + "quan_a_k_fn.s", lambda: lsq_init_rows(k, hi, False))
-    k = lsq_rows(k, sk, abits, False)
+    k = lsq_rows(k, sk, abits, False, tap=pre + "quan_a_k_fn")
     v = v.permute(0, 2, 1, 3).reshape(B, N, C)
     sv = _get_scale(P, pre + "quan_a_v_fn.s", lambda: lsq_init_cols(v, hi, False))
-    v = lsq_cols(v, sv, abits, False)
+    v = lsq_cols(v, sv, abits, False, tap=pre + "quan_a_v_fn")
     q = q.permute(0, 2, 1, 3).reshape(B, N, C) + P[pre + "move_q_aft.bias"]
     k = k.permute(0, 2, 1, 3).reshape(B, N, C) + P[pre + "move_k_aft.bias"]
     v = v + P[pre + "move_v_aft.bias"]
@@ -228,6 +241,7 @@ def qattention(x: Tensor, P: Params, pre: str, heads: int, wbits: int, abits: in
         attn = attn + bias
     prob = _softmax_quant(attn, P, pre, abits)
     out = (prob @ v).transpose(1, 2).reshape(B, N, C)
+    _tap(pre + "@core_out", out=out)
     return qlinear(out, P, pre + "proj.", wbits, abits, symmetric=True)
 
 
@@ -253,7 +267,7 @@ def qattention_qkr(x: Tensor, P: Params, pre: str, heads: int, wbits: int, abits
     v = v + P[pre + "v.bias"].view(1, -1).expand_as(v)
     v = v + P[pre + "move_v_b4.bias"]
     sv = _get_scale(P, pre + "quan_a_v_fn.s", lambda: lsq_init_cols(v, hi, False))
-    v = lsq_cols(v, sv, abits, False)
+    v = lsq_cols(v, sv, abits, False, tap=pre + "quan_a_v_fn")
     v = v + P[pre + "move_v_aft.bias"]
     v = v.reshape(B, N, heads, hd).permute(0, 2, 1, 3)
     # QK branch: one StatsQ on the per-head product
@@ -263,7 +277,7 @@ def qattention_qkr(x: Tensor, P: Params, pre: str, heads: int, wbits: int, abits
     qkx = qkx + P[pre + "move_qkx_b4.bias"]
     qkx = qkx.reshape(B, N * heads, C)
     sk = _get_scale(P, pre + "quan_a_qkx_fn.s", lambda: lsq_init_rows(qkx, hi, False))
-    qkx = lsq_rows(qkx, sk, abits, False)
+    qkx = lsq_rows(qkx, sk, abits, False, tap=pre + "quan_a_qkx_fn")
     qkx = qkx.reshape(B, N, heads * C) + P[pre + "move_qkx_aft.bias"]
     qkx = qkx.reshape(B, N, heads, -1).permute(0, 2, 3, 1)
     attn = torch.einsum("BNC,BHCD -> BHND", xq, qkx) * (hd ** -0.5)
@@ -271,6 +285,7 @@ def qattention_qkr(x: Tensor, P: Params, pre: str, heads: int, wbits: int, abits
         attn = attn + bias
     prob = _softmax_quant(attn, P, pre, abits)
     out = (prob @ v).transpose(1, 2).reshape(B, N, C)
+    _tap(pre + "@core_out", out=out)
     return qlinear(out, P, pre + "proj.", wbits, abits, symmetric=True)
 
 
@@ -319,11 +334,14 @@ def head_q(x: Tensor, P: Params, pre: str) -> Tensor:
 def deit_block(x: Tensor, P: Params, pre: str, heads: int, wbits: int, abits: int, qkr: bool) -> Tensor:
     """Block.forward, deit_vision_transformer.py:154-164 (LayerNorm eps 1e-6, deit.py:75)."""
     C = x.shape[-1]
+    _tap(pre + "@in", x=x)
     h = F.layer_norm(x, (C,), P[pre + "norm1.weight"], P[pre + "norm1.bias"], 1e-6)
     attn = (qattention_qkr if qkr else qattention)(h, P, pre + "attn.", heads, wbits, abits)
     x = x + attn
     h = F.layer_norm(x, (C,), P[pre + "norm2.weight"], P[pre + "norm2.bias"], 1e-6)
-    return x + qmlp(h, P, pre + "mlp.", wbits, abits)
+    x = x + qmlp(h, P, pre + "mlp.", wbits, abits)
+    _tap(pre + "@out", out=x)
+    return x
 
 
 def deit_forward(img: Tensor, P: Params, depth: int, heads: int, wbits: int, abits: int, qkr: bool,
@@ -411,11 +429,13 @@ def swin_forward(img: Tensor, P: Params, depths, heads, wbits: int, abits: int, 
         for j in range(depth):
             pre = f"features.{2 * i + 1}.{j}."
             C = x.shape[-1]
+            _tap(pre + "@in", x=x)
             h = F.layer_norm(x, (C,), P[pre + "norm1.weight"], P[pre + "norm1.bias"], 1e-5)
             shift = (0, 0) if j % 2 == 0 else (window[0] // 2, window[1] // 2)
             x = x + swin_window_attention(h, P, pre + "attn.", heads[i], wbits, abits, qkr, window, shift)
             h = F.layer_norm(x, (C,), P[pre + "norm2.weight"], P[pre + "norm2.bias"], 1e-5)
             x = x + qmlp(h, P, pre + "mlp.", wbits, abits)
+            _tap(pre + "@out", out=x)
         if i < len(depths) - 1:                                                 # PatchMerging, src/swin.py:40-59
             pre = f"features.{2 * i + 2}."
             Hh, Ww, _ = x.shape[-3:]
