@@ -51,7 +51,15 @@ def parse():
                          "freeze mask fused into AdamW for every StatsQ weight, boundaryRange 0.005, lr 1e-5). eval: no-grad "
                          "inference forward (eval_scripts/deit_s/w2a2.sh uses batch 200)")
     ap.add_argument("--graph", default="on", choices=["on", "off"],
-                    help="capture the whole QAT step (fwd+bwd+all-reduce+AdamW) in one CUDA graph and replay it")
+                    help="capture the whole QAT step (fwd+bwd+all-reduce+AdamW) in one CUDA graph and replay it "
+                         "(ofq_b200.step_graph.CapturedStep); off = the eager Python loop the reference's train.py runs")
+    ap.add_argument("--host-model", default="fused", choices=["fused", "plain"],
+                    help="fused: the repo's host model (ofq_b200 LayerNorm kernels, residual add folded into the next norm). "
+                         "plain: a timm-style host with torch LayerNorm and un-fused residuals (ofq_b200/host/plain.py), i.e. "
+                         "the quantized modules dropped into somebody else's model, as into the reference's")
+    ap.add_argument("--ddp", default="bucketed", choices=["flat", "bucketed"],
+                    help="gradient exchange for N > 1: one flat all-reduce after backward, or ~25 MB buckets reduced on a "
+                         "communication stream while the backward is still running (torch DDP semantics, train.py:727)")
     return ap.parse_args()
 
 
@@ -210,8 +218,10 @@ def main():
     import ofq_b200.quantization as Q
     from ofq_b200 import _lib, ops
     from ofq_b200.cga import CGAAdamW, cga_masked_parameter_names, param_groups_weight_decay
-    from ofq_b200.ddp import FlatGradAllReduce, broadcast_parameters
+    from ofq_b200.ddp import BucketedGradAllReduce, FlatGradAllReduce, broadcast_parameters
     from ofq_b200.host.deit import DistilledVisionTransformer
+    from ofq_b200.host.plain import PlainDistilledViT
+    from ofq_b200.step_graph import CapturedStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -234,7 +244,7 @@ def main():
                                                  pretrained_initialized=True, qk_reparam=not a.no_qkr,
                                                  qk_reparam_type=1 if a.mode == "cga" else 0).to(dev)
     else:
-        model = DistilledVisionTransformer(num_classes=1000, **cfg)
+        model = (PlainDistilledViT if a.host_model == "plain" else DistilledVisionTransformer)(num_classes=1000, **cfg)
         names = Q.deit_qmodule_names(cfg["depth"])
         model = Q.replace_module_by_qmodule_deit(model, Q.make_qconfigs(names, a.bits, a.bits), pretrained_initialized=True,
                                                  qk_reparam=not a.no_qkr, qk_reparam_type=1 if a.mode == "cga" else 0).to(dev)
@@ -258,7 +268,9 @@ def main():
     else:
         opt = CGAAdamW(param_groups_weight_decay(model, 0.05, getattr(model, 'no_weight_decay', lambda: set())()), lr=5.47e-4)
     # data-parallel gradient exchange (ofq_b200/ddp.py): ONE NCCL all-reduce (mean) of a flat fp32 gradient buffer
-    ddp = FlatGradAllReduce(model.parameters(), world) if world > 1 else None
+    ddp = None
+    if world > 1:
+        ddp = BucketedGradAllReduce(model, world) if a.ddp == "bucketed" else FlatGradAllReduce(model.parameters(), world)
     flat = ddp.flat if ddp is not None else None
 
     def step(img, lbl):
@@ -295,21 +307,18 @@ def main():
     run = step
     launches_per_step = None
     if a.graph == "on":
-        static_img, static_lbl = d_img.clone(), d_lbl.clone()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                step(static_img, static_lbl)
-        torch.cuda.current_stream().wait_stream(side)
-        barrier()
-        if flat is None:
-            opt.zero_grad(set_to_none=True)
-        graph = torch.cuda.CUDAGraph()
-        l0 = ops.LAUNCHES
-        with torch.cuda.graph(graph):
-            static_loss = step(static_img, static_lbl)
-        launches_per_step = ops.LAUNCHES - l0
+        counted = {}
+
+        def pre_capture():
+            barrier()
+            if flat is None:
+                opt.zero_grad(set_to_none=True)
+            counted["l0"] = ops.LAUNCHES
+
+        captured = CapturedStep(step, (d_img, d_lbl), warmup=2, pre_capture=pre_capture)
+        graph, static_loss = captured.graph, captured.static_output
+        static_img, static_lbl = captured.static_inputs
+        launches_per_step = ops.LAUNCHES - counted["l0"]
         note("graph captured")
         barrier()
 
@@ -460,7 +469,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": B * world, "parallelism": f"dp{world}",
                    "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush",
-                   "optimizer": {"qat": "fused AdamW lr 5.47e-4 wd 0.05", "cga": "fused CGA-masked AdamW lr 1e-5 wd 0.05 BR 0.005", "eval": "none"}[a.mode], "cuda_graph": a.graph == "on", "host_enqueue_ms_per_step": host_enqueue_ms, "bwd_mode": bwd_mode,
+                   "optimizer": {"qat": "fused AdamW lr 5.47e-4 wd 0.05", "cga": "fused CGA-masked AdamW lr 1e-5 wd 0.05 BR 0.005", "eval": "none"}[a.mode], "cuda_graph": a.graph == "on", "host_model": a.host_model, "ddp": (a.ddp if world > 1 else None), "host_enqueue_ms_per_step": host_enqueue_ms, "bwd_mode": bwd_mode,
                    "quantized_gemm_tflops_per_gpu": flops_step / (ms_total / a.steps * 1e-3) / 1e12},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": (h_img.numel() * 4 + h_lbl.numel() * 8) * world,
                 "d2h_bytes_per_step": 4 * world, "last_loss": last},

@@ -62,12 +62,31 @@ class CGAAdamW(torch.optim.Optimizer):
         self._step_dev = None      # device-resident step counter: the whole step can be captured in a CUDA graph
         self._tables = {}          # per param-group pointer tables of the multi-tensor kernel
 
+    # The kernels take the bias-correction step t from a device counter (so that a captured CUDA graph can be replayed);
+    # it is part of the optimizer state: saved under "ofq_step" and restored (or re-seeded from the per-parameter
+    # `step` entries of a torch.optim.AdamW checkpoint) by load_state_dict.
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["ofq_step"] = int(getattr(self, "_host_step", 0))
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        step = state_dict.pop("ofq_step", None)
+        super().load_state_dict(state_dict)
+        if step is None:
+            steps = [int(st["step"]) for st in self.state.values() if "step" in st]
+            step = max(steps) if steps else 0
+        self._host_step = int(step)
+        self._step_dev = None          # re-created on the parameters' device with the restored count at the next step
+        self._tables = {}
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         if self._step_dev is None:
             dev = next(p for g in self.param_groups for p in g["params"]).device
-            self._step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._step_dev = torch.full((1,), int(getattr(self, "_host_step", 0)), dtype=torch.int32, device=dev)
         ops.counter_increment_(self._step_dev)
         self._host_step = getattr(self, "_host_step", 0) + 1
         for gi, group in enumerate(self.param_groups):
@@ -79,6 +98,8 @@ class CGAAdamW(torch.optim.Optimizer):
                 st = self.state[p]
                 if not st:
                     st["step"] = 0
+                elif torch.is_tensor(st.get("step")):
+                    st["step"] = int(st["step"].item())          # a torch.optim.AdamW checkpoint keeps the step as a tensor
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 st["step"] += 1

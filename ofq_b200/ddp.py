@@ -64,3 +64,101 @@ def broadcast_parameters(model: torch.nn.Module, src: int = 0) -> None:
     identical on every rank."""
     for t in list(model.parameters()) + list(model.buffers()):
         dist.broadcast(t.data, src)
+
+
+class BucketedGradAllReduce:
+    """torch-DDP-style exchange (train.py:727): gradients are reduced in a few buckets WHILE the backward is still running.
+
+    Parameters are grouped, in reverse registration order (the order the backward produces their gradients), into buckets
+    of ~`bucket_mb`; each bucket is a slice of one flat fp32 buffer. A post-accumulate hook per parameter counts a bucket
+    down; when its last gradient has arrived the bucket's gradients are gathered into the slice (one multi-tensor copy on
+    the compute stream) and its NCCL all-reduce is queued on a communication stream behind an event, so the collective
+    of bucket i overlaps the backward kernels of the layers below it. `reduce()` joins the communication stream (and
+    handles buckets whose parameters took no part in the step). Event fork / join edges are legal inside CUDA-graph capture,
+    so the whole step can still be captured as one graph. Same interface as FlatGradAllReduce."""
+
+    def __init__(self, params_or_model, world_size: int, bucket_mb: float = 25.0):
+        params = params_or_model.parameters() if isinstance(params_or_model, torch.nn.Module) else params_or_model
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        self.world_size = world_size
+        dev = self.params[0].device
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+        self.comm = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        limit = int(bucket_mb * (1 << 20) / 4)
+        self.buckets = []            # dicts: params, views, flat slice, pending count
+        self._bucket_of = {}
+        off = self.flat.numel()
+        cur = None
+        for p in reversed(self.params):
+            if cur is None or cur["numel"] + p.numel() > limit:
+                cur = {"params": [], "views": [], "numel": 0, "hi": off}
+                self.buckets.append(cur)
+            off -= p.numel()
+            cur["params"].append(p)
+            cur["views"].append(self.flat[off:off + p.numel()].view_as(p))
+            cur["numel"] += p.numel()
+            cur["lo"] = off
+            self._bucket_of[id(p)] = cur
+        for b in self.buckets:
+            b["flat"] = self.flat[b["lo"]:b["hi"]]
+            b["pending"] = len(b["params"])
+            b["done"] = False
+        self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+
+    @property
+    def nbytes(self) -> int:
+        return self.flat.numel() * 4
+
+    def zero(self) -> None:
+        """Start of a step, on the stream the step runs on: the bucket gathers are queued on THAT stream (the gradients are
+        produced there), whatever stream autograd happens to run a parameter's AccumulateGrad node on."""
+        for p in self.params:
+            p.grad = None
+        for b in self.buckets:
+            b["pending"], b["done"] = len(b["params"]), False
+        self._main = torch.cuda.current_stream() if self.comm is not None else None
+
+    def scale_loss(self, loss: torch.Tensor) -> torch.Tensor:
+        return loss / self.world_size if self.world_size > 1 else loss
+
+    def _on_grad(self, p) -> None:
+        b = self._bucket_of[id(p)]
+        b["pending"] -= 1
+        if b["pending"] == 0 and not b["done"]:
+            self._launch(b)
+
+    def _gather(self, b) -> None:
+        grads, views = [], []
+        for p, v in zip(b["params"], b["views"]):
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                grads.append(p.grad)
+                views.append(v)
+        if grads:
+            torch._foreach_copy_(views, grads)
+        for p, v in zip(b["params"], b["views"]):
+            p.grad = v
+        b["done"] = True
+
+    def _launch(self, b) -> None:
+        main = getattr(self, "_main", None)
+        if self.comm is None or main is None:
+            self._gather(b)
+            if self.world_size > 1:
+                dist.all_reduce(b["flat"])
+            return
+        with torch.cuda.stream(main):
+            self._gather(b)
+            if self.world_size > 1:
+                self.comm.wait_event(main.record_event())
+        if self.world_size > 1:
+            with torch.cuda.stream(self.comm):
+                dist.all_reduce(b["flat"])
+
+    def reduce(self) -> None:
+        for b in self.buckets:
+            if not b["done"]:
+                self._launch(b)
+        if self.comm is not None and self.world_size > 1:
+            torch.cuda.current_stream().wait_stream(self.comm)

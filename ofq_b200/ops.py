@@ -529,7 +529,7 @@ def layernorm_fwd(x2d: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, ep
 # The latest residual-stream gradient an ofq_b200 LayerNorm backward produced, with the per-CTA maxima of |dx|: the proj / fc2
 # backward that consumes exactly this tensor as dY derives its fp16 range scale from them (no absmax pass). The strong
 # reference keeps the storage alive, so a matching data_ptr really is this tensor.
-RESIDUAL_MAX = {"dx": None, "bmax": None}
+RESIDUAL_MAX = {"dx": None, "bmax": None, "version": -1}
 
 
 def layernorm_bwd(dy2d, x2d, gamma, mean, rstd, res2d=None, want_max: bool = False):
@@ -546,13 +546,18 @@ def layernorm_bwd(dy2d, x2d, gamma, mean, rstd, res2d=None, want_max: bool = Fal
           x2d.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, cols, _ptr(res2d), dx.data_ptr(),
           dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), _ptr(bmax), _st())
     if bmax is not None:
-        RESIDUAL_MAX["dx"], RESIDUAL_MAX["bmax"] = dx, bmax
+        import weakref
+        # weak reference: the maxima are only trusted while this very tensor is alive (so no other tensor can own its
+        # address) and unmodified (version counter); nothing is kept alive past the backward
+        RESIDUAL_MAX["dx"], RESIDUAL_MAX["bmax"], RESIDUAL_MAX["version"] = weakref.ref(dx), bmax, dx._version
     return dx, dgamma, dbeta
 
 
 def residual_max_for(t: torch.Tensor):
     """Block maxima of |t| if t is (a view of the whole of) the latest LayerNorm-backward output, else None."""
-    dx = RESIDUAL_MAX["dx"]
-    if dx is not None and t.data_ptr() == dx.data_ptr() and t.numel() == dx.numel() and t.is_contiguous():
+    ref = RESIDUAL_MAX["dx"]
+    dx = ref() if ref is not None else None
+    if (dx is not None and t.data_ptr() == dx.data_ptr() and t.numel() == dx.numel() and t.is_contiguous()
+            and dx._version == RESIDUAL_MAX["version"] and t._version == dx._version):
         return RESIDUAL_MAX["bmax"]
     return None

@@ -42,6 +42,11 @@ class StepPrologue:
         self.tables = None
         self.launches = 0
 
+    def __deepcopy__(self, memo):
+        # copy.deepcopy(model) (e.g. timm's ModelEmaV2): the copy gets a prologue of its own; jobs hold raw pointers of
+        # the original's parameters and must not travel
+        return StepPrologue()
+
     # ------------------------------------------------------------------ registration / lookup (called from ops)
     def get_scale(self, alpha: torch.Tensor, g: float, recip: bool):
         key = (alpha.data_ptr(), alpha.numel(), float(g), bool(recip))
@@ -185,6 +190,19 @@ def install(model: torch.nn.Module) -> StepPrologue:
         return pro
     pro = StepPrologue()
     model._ofq_prologue = pro
-    model.register_forward_pre_hook(lambda m, inp: pro.begin() if (inp and torch.is_tensor(inp[0]) and inp[0].is_cuda) else None)
-    model.register_forward_hook(lambda m, inp, out: pro.end(), always_call=True)
+    # the hooks look the prologue up on the module they fire for: a deep copy of the model runs its own
+    model.register_forward_pre_hook(_begin_hook)
+    model.register_forward_hook(_end_hook, always_call=True)
     return pro
+
+
+def _begin_hook(m, inp):
+    pro = getattr(m, "_ofq_prologue", None)
+    if pro is not None and inp and torch.is_tensor(inp[0]) and inp[0].is_cuda:
+        pro.begin()
+
+
+def _end_hook(m, inp, out):
+    pro = getattr(m, "_ofq_prologue", None)
+    if pro is not None:
+        pro.end()

@@ -17,7 +17,12 @@ import torch
 from .. import ops
 from ..ops import ACT_GELU, ACT_NONE, FMT_BF16, FMT_F16, GEMM_BF16, GEMM_F16, GEMM_I8, PER_COL, PER_ROW, round_up, vec
 
-NUM_SMS = 148
+
+
+def _num_sms() -> int:
+    """SM count of the current device (split-K heuristic of the bf16 modes; the fp16 default lets the library choose)."""
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+
 # Number format of the real-valued (gradient) operand of every backward GEMM; the integer-code operand is exact in all:
 #   "f16"    one fp16 plane (11 significant bits, ~2e-4 gradient error), range-scaled per tensor by a power of two
 #            from an absmax pass (ops.absmax_scale) and un-scaled in the GEMM epilogue              [default]
@@ -60,7 +65,7 @@ def grad_scale_factor(hi: int, count: int) -> float:
 
 
 def _splits_for(tiles: int, kblocks: int) -> int:
-    s = max(1, min((2 * NUM_SMS + tiles - 1) // tiles, max(1, kblocks // 4)))
+    s = max(1, min((2 * _num_sms() + tiles - 1) // tiles, max(1, kblocks // 4)))
     return min(s, 64)
 
 
@@ -132,6 +137,24 @@ def _linear_backward(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulate_dx
     return dW, prep["colsum"], qxT_all
 
 
+_ZERO = {}
+
+
+def _placeholder_grad(like: torch.Tensor) -> torch.Tensor:
+    """A gradient-shaped, zero-stride view of ONE cached zero: what a node returns for an input whose real gradient
+    travels another way (MlpLink.fuse). It costs no memory and no launch, reads as exact zeros (never as uninitialised
+    memory) and is recognisable by its data pointer."""
+    z = _ZERO.get(like.device)
+    if z is None:
+        z = _ZERO[like.device] = torch.zeros((), dtype=like.dtype, device=like.device)
+    return z.expand(like.shape)
+
+
+def _is_placeholder_grad(t: torch.Tensor) -> bool:
+    z = _ZERO.get(t.device)
+    return z is not None and t.data_ptr() == z.data_ptr() and all(s == 0 for s in t.stride())
+
+
 # ====================================================================================== QLinear
 class MlpLink:
     """Side channel between a producer node and the QLinearFn that consumes its output (fc1 -> fc2 of a QMLP, attention
@@ -142,7 +165,9 @@ class MlpLink:
 
     def __init__(self, fuse: bool = False):
         # fuse: the consumer's LSQ backward writes the producer's fp16 gradient operand (a16) and colsum(dY) itself; the
-        # fp32 gradient tensor handed back through autograd is then an uninitialised placeholder that the producer ignores
+        # fp32 gradient handed back through autograd is then a zero placeholder (_placeholder_grad) that the producer
+        # recognises and ignores. Anything else that consumed the producer's output (a hook, a second use) would add its
+        # own gradient to the placeholder: the producer detects that and fails loudly instead of dropping it
         self.cs = self.se = self.sc = self.a16 = self.colsum = None
         self.fuse = fuse
 
@@ -198,7 +223,10 @@ class QLinearFn(torch.autograd.Function):
         dxhat = torch.empty((M, K), dtype=torch.float32, device=dY.device)
         if link is not None and role == 1 and link.a16 is not None:
             # fc1 of a fused QMLP: fc2's backward already wrote this layer's fp16 gradient operand and colsum(dY); the dY
-            # tensor that arrived through autograd is a placeholder
+            # tensor that arrived through autograd is the zero placeholder
+            if not _is_placeholder_grad(dY):
+                raise RuntimeError("fused QMLP: the fc1 output received a gradient from something other than fc2 (a hook, "
+                                   "retain_grad or a second consumer); run the MLP un-fused (OFQ_FUSED16=0) for such graphs")
             dW, dbias, _ = _linear_backward_f16(None, qx, wc, (colscale, inv_cs), se2, P, aft, dxhat, False, qx16, sc=link.sc,
                                                 a16=link.a16, colsum=link.colsum, **wkw)
             link.a16 = link.colsum = None
@@ -217,7 +245,7 @@ class QLinearFn(torch.autograd.Function):
                                                           out16=(FMT, link.cs, link.se, link.se.numel(), sc1), want_dx=False,
                                                           want_colsum=True)
                 link.sc, link.a16, link.colsum = sc1, a16, csum
-                dx = torch.empty_like(xc)         # placeholder: never read (see MlpLink.fuse)
+                dx = _placeholder_grad(xc)        # exact zeros, recognised by fc1's backward (see MlpLink.fuse)
                 ops.side_join()
                 return dx, dW, (dbias if has_bias else None), db4, daft, ds, None, None, None, None, None, None
         nxt = None

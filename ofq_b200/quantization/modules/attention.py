@@ -16,6 +16,17 @@ from .qbias import LearnableBias
 from .qlinear import LSQ_input, QLinear
 
 
+def _check_attention_like(m):
+    """The registry hands over the host model's attention module (modules/utils.py:21-44). Any module with the timm / DeiT
+    attention interface is accepted - the repo's own host class, the reference's src.deit_vision_transformer.Attention, or
+    timm's - not one particular class (the reference asserts `type(m) == deit_attention`, attention.py:17, because its
+    registry is keyed on its own class)."""
+    for attr in ("qkv", "proj", "num_heads", "attn_drop", "proj_drop"):
+        if not hasattr(m, attr):
+            raise TypeError(f"{type(m).__name__} does not look like a DeiT attention module: no `{attr}`")
+    return m
+
+
 def _qlinear_kwargs(weight_bits, input_bits, weight_channelwise, input_channelwise, weight_quant_method,
                     input_quant_method, aq_learnable, wq_learnable, pretrained_initialized):
     return dict(weight_bits=weight_bits, input_bits=input_bits, weight_channelwise=weight_channelwise,
@@ -30,9 +41,9 @@ class QAttention(deit_attention):
     def __init__(self, m: deit_attention, weight_bits=8, input_bits=8, aq_learnable=True, wq_learnable=True,
                  weight_channelwise=True, input_channelwise=True, weight_quant_method="statsq", input_quant_method="lsq",
                  pretrained_initialized=False, **kwargs):
-        assert isinstance(m, deit_attention)
+        _check_attention_like(m)
         super().__init__(dim=m.qkv.in_features, num_heads=m.num_heads, attn_drop=m.attn_drop.p, proj_drop=m.proj_drop.p,
-                         qqkkvv=m.qqkkvv)
+                         qqkkvv=getattr(m, "qqkkvv", False))
         self.weight_bits = weight_bits
         self.input_bits = input_bits
         self.input_channelwise = input_channelwise
@@ -105,9 +116,9 @@ class QAttention_qkreparam(deit_attention):
     def __init__(self, m: deit_attention, weight_bits=8, input_bits=8, aq_learnable=True, wq_learnable=True,
                  weight_channelwise=True, input_channelwise=True, weight_quant_method="statsq", input_quant_method="lsq",
                  pretrained_initialized=False, **kwargs):
-        assert isinstance(m, deit_attention)
+        _check_attention_like(m)
         super().__init__(dim=m.qkv.in_features, num_heads=m.num_heads, attn_drop=m.attn_drop.p, proj_drop=m.proj_drop.p,
-                         qqkkvv=m.qqkkvv)
+                         qqkkvv=getattr(m, "qqkkvv", False))
         dim = m.qkv.in_features
         self.weight_bits = weight_bits
         self.input_bits = input_bits

@@ -88,7 +88,12 @@ class QMLP(Mlp):
     def __init__(self, *kargs, m: Mlp, weight_bits=8, input_bits=8, aq_learnable=True, wq_learnable=True,
                  weight_channelwise=True, input_channelwise=True, weight_quant_method="statsq", input_quant_method="lsq",
                  act_layer=nn.GELU, pretrained_initialized=False, **kwargs):
-        super().__init__(in_features=m.in_features, hidden_features=m.hidden_features, out_features=m.out_features, drop=m.drop)
+        # any Mlp-like host module (fc1 / fc2 Linears): the repo's, the reference's (deit_vision_transformer.py:53-83), timm's
+        drop = getattr(m, "drop", None)
+        drop = drop.p if isinstance(drop, nn.Dropout) else (drop if isinstance(drop, (int, float)) else getattr(getattr(m, "drop1", None), "p", 0.0))
+        super().__init__(in_features=getattr(m, "in_features", m.fc1.in_features),
+                         hidden_features=getattr(m, "hidden_features", None) or m.fc1.out_features,
+                         out_features=getattr(m, "out_features", None) or m.fc2.out_features, drop=drop)
         common = dict(weight_bits=weight_bits, input_bits=input_bits, aq_learnable=aq_learnable, wq_learnable=wq_learnable,
                       weight_channelwise=weight_channelwise, input_channelwise=input_channelwise,
                       weight_quant_method=weight_quant_method, input_quant_method=input_quant_method,

@@ -16,6 +16,17 @@ from .qbias import LearnableBias
 from .qlinear import LSQ_input, QLinear, qmlp_forward
 
 
+def _check_window_attention_like(m):
+    """Any module with the torchvision / reference ShiftedWindowAttention interface is accepted (the reference asserts
+    `type(m) == ShiftedWindowAttention`, swin_attention_and_mlp.py:71, because its registry is keyed on its own class)."""
+    for attr in ("qkv", "proj", "num_heads", "window_size", "shift_size"):
+        if not hasattr(m, attr):
+            raise TypeError(f"{type(m).__name__} does not look like a shifted-window attention module: no `{attr}`")
+    if not hasattr(m, "dim"):
+        m.dim = m.qkv.in_features
+    return m
+
+
 class QMLP_swin(nn.Module):
     """swin_attention_and_mlp.py:24-63: fc1 (signed input) -> GELU -> fc2 (unsigned input)."""
 
@@ -60,9 +71,9 @@ class QAttention_swin(_SwinWindows, ShiftedWindowAttention):
     def __init__(self, m: ShiftedWindowAttention, weight_bits=8, input_bits=8, aq_learnable=True, wq_learnable=True,
                  weight_channelwise=True, input_channelwise=True, weight_quant_method="statsq", input_quant_method="lsq",
                  pretrained_initialized=False, **kwargs):
-        assert isinstance(m, ShiftedWindowAttention)
+        _check_window_attention_like(m)
         super().__init__(dim=m.dim, window_size=m.window_size, shift_size=m.shift_size, num_heads=m.num_heads, qkv_bias=True,
-                         proj_bias=True, attention_dropout=0.0, dropout=0.0, qqkkvv=m.qqkkvv)
+                         proj_bias=True, attention_dropout=0.0, dropout=0.0, qqkkvv=getattr(m, "qqkkvv", False))
         self.weight_bits, self.input_bits, self.input_channelwise = weight_bits, input_bits, input_channelwise
         self.scale = (m.dim // m.num_heads) ** -0.5
         kw = _qlinear_kwargs(weight_bits, input_bits, weight_channelwise, input_channelwise, weight_quant_method,
@@ -93,9 +104,9 @@ class QAttention_swin_qkreparam(_SwinWindows, ShiftedWindowAttention):
     def __init__(self, m: ShiftedWindowAttention, weight_bits=8, input_bits=8, aq_learnable=True, wq_learnable=True,
                  symmetric=True, weight_channelwise=True, input_channelwise=True, weight_quant_method="statsq",
                  input_quant_method="lsq", pretrained_initialized=False, **kwargs):
-        assert isinstance(m, ShiftedWindowAttention)
+        _check_window_attention_like(m)
         super().__init__(dim=m.dim, window_size=m.window_size, shift_size=m.shift_size, num_heads=m.num_heads, qkv_bias=True,
-                         proj_bias=True, attention_dropout=0.0, dropout=0.0, qqkkvv=m.qqkkvv)
+                         proj_bias=True, attention_dropout=0.0, dropout=0.0, qqkkvv=getattr(m, "qqkkvv", False))
         if symmetric is False:
             raise NotImplementedError("unsigned input quantization of the shared attention input is not used by any recipe")
         self.weight_bits, self.input_bits, self.input_channelwise = weight_bits, input_bits, input_channelwise

@@ -36,6 +36,26 @@ QMODULE_MAPPINGS_QK_REPARAM_SWIN = [
 ]
 
 
+def _qclass_for(mapping, module, swin=False):
+    """The quantized class for a host module. Exact type first (the reference's registry, utils.py:21-44, is keyed on ITS
+    host classes); otherwise by interface, so that the reference's own `src.deit_vision_transformer.Attention / Mlp`,
+    `src.swin.ShiftedWindowAttention`, torchvision's `MLP` or timm's layers are swapped exactly like the repo's host classes."""
+    cls = mapping.get(type(module))
+    if cls is not None:
+        return cls
+    if isinstance(module, torch.nn.Linear):
+        return mapping[torch.nn.Linear]
+    attn_key, mlp_key = (ShiftedWindowAttention, swin_MLP) if swin else (deit_attention, Mlp)
+    if all(hasattr(module, a) for a in ("qkv", "proj", "num_heads")):
+        return mapping[attn_key]
+    if all(hasattr(module, a) for a in ("fc1", "fc2")):
+        return mapping[mlp_key]
+    if swin and isinstance(module, torch.nn.Sequential) and len(module) >= 5 and isinstance(module[0], torch.nn.Linear) \
+            and isinstance(module[3], torch.nn.Linear):
+        return mapping[mlp_key]                      # torchvision.ops.MLP: Sequential(Linear, act, Dropout, Linear, Dropout)
+    raise KeyError(f"no quantized module is registered for {type(module).__module__}.{type(module).__name__}")
+
+
 def get_module_by_name(model, module_name):
     module = model
     for name in module_name.split("."):
@@ -70,7 +90,7 @@ def replace_module_by_qmodule_deit(model, qconfigs, pretrained_initialized=False
             qmodule = LSQ_QLinear4head(m=module, symmetric=True, **_eight_bit_kwargs(cfg, pretrained_initialized))
         else:
             extra = {"boundaryRange": boundaryRange} if (qk_reparam and qk_reparam_type == 1) else {}
-            qmodule = mapping[type(module)](
+            qmodule = _qclass_for(mapping, module)(
                 m=module, weight_bits=cfg["weight"]["bit"], input_bits=cfg["act"]["bit"],
                 weight_channelwise=cfg["weight"]["per_channel"], input_channelwise=cfg["act"]["per_channel"],
                 weight_quant_method=cfg["weight"]["mode"], input_quant_method=cfg["act"]["mode"],
@@ -93,7 +113,7 @@ def replace_module_by_qmodule_swin(model, qconfigs, pretrained_initialized=False
         elif name == "head":
             qmodule = LSQ_QLinear4head(m=module, symmetric=True, **_eight_bit_kwargs(cfg, pretrained_initialized))
         else:
-            qmodule = mapping[type(module)](
+            qmodule = _qclass_for(mapping, module, swin=True)(
                 m=module, weight_bits=cfg["weight"]["bit"], input_bits=cfg["act"]["bit"],
                 weight_channelwise=cfg["weight"]["per_channel"], input_channelwise=cfg["act"]["per_channel"],
                 weight_quant_method=cfg["weight"]["mode"], input_quant_method=cfg["act"]["mode"],

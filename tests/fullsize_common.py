@@ -68,8 +68,9 @@ def key_seed(key: str) -> int:
 
 
 def is_regenerated(key: str, t: torch.Tensor) -> bool:
-    """Everything is regenerated except data-derived LSQ step sizes (`.s`), the frozen StatsQ `clip_val` and integer buffers."""
-    return t.is_floating_point() and not key.endswith(".s") and not key.endswith("clip_val")
+    """Everything is regenerated except data-derived LSQ step sizes (`.s`), the frozen StatsQ `clip_val`, the sign latch of
+    the image quantizer and integer buffers."""
+    return t.is_floating_point() and not key.endswith((".s", "clip_val", ".signed"))
 
 
 def det_value(key: str, shape) -> torch.Tensor:

@@ -20,17 +20,18 @@ def _model():
     return torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.GELU(), torch.nn.LayerNorm(32), torch.nn.Linear(32, 5))
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, bucketed=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from ofq_b200.ddp import FlatGradAllReduce, broadcast_parameters
+    from ofq_b200.ddp import BucketedGradAllReduce, FlatGradAllReduce, broadcast_parameters
     model = _model()
     if rank == 1:                                   # deliberately different start: the broadcast must fix it
         with torch.no_grad():
             for p in model.parameters():
                 p.add_(1.0)
     broadcast_parameters(model, 0)
-    ddp = FlatGradAllReduce(model.parameters(), world)
+    # tiny buckets: the four parameter tensors fall into several of them
+    ddp = BucketedGradAllReduce(model, world, bucket_mb=0.001) if bucketed else FlatGradAllReduce(model.parameters(), world)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-2)
     g = torch.Generator().manual_seed(100)
     x = torch.randn(8, 16, generator=g)
@@ -47,12 +48,13 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_flat_allreduce_matches_single_process():
+@pytest.mark.parametrize("bucketed", [False, True])
+def test_flat_allreduce_matches_single_process(bucketed):
     world = 2
     port = _free_port()
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, out, bucketed), nprocs=world, join=True)
     # single-process reference on the full batch
     model = _model()
     opt = torch.optim.AdamW(model.parameters(), lr=1e-2)
