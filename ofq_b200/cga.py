@@ -98,10 +98,10 @@ class CGAAdamW(torch.optim.Optimizer):
                 st = self.state[p]
                 if not st:
                     st["step"] = 0
-                elif torch.is_tensor(st.get("step")):
-                    st["step"] = int(st["step"].item())          # a torch.optim.AdamW checkpoint keeps the step as a tensor
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                elif torch.is_tensor(st.get("step")):
+                    st["step"] = int(st["step"].item())          # a torch.optim.AdamW checkpoint keeps the step as a tensor
                 st["step"] += 1
                 masked = id(p) in self._masked
                 if not masked and p.is_contiguous() and p.grad.is_contiguous():

@@ -200,3 +200,65 @@ def oracle_forward(cfg_name: str, P, img, signed: int):
         return (O.swin_forward(img, P, (2, 2, 6, 2), (3, 6, 12, 24), wb, ab, qkr, state),)
     dims = MODEL_DIMS[model_name]
     return O.deit_forward(img, P, dims["depth"], dims["num_heads"], wb, ab, qkr, state)
+
+
+# ------------------------------------------------------------------------------------------------ code comparison
+TIE_TOL = 2e-5     # relative (to max(1, |v|)) window in which two pre-round values count as the same value up to GEMM round-off
+
+
+def compare_codes(mine, v_mine, ref, v_ref=None):
+    """Mismatch statistics of one integer code tensor against a reference one. With the pre-round values v = x / s of both
+    sides, a mismatch is a PROVEN TIE when the two values differ by no more than TIE_TOL * max(1, |v|): both are then within
+    that distance of the rounding boundary that separates the two codes."""
+    mine = mine.detach().cpu().to(torch.int16).reshape(ref.shape)
+    bad = mine != ref.to(torch.int16)
+    n = int(bad.sum())
+    r = {"numel": ref.numel(), "mismatches": n}
+    if v_ref is not None:
+        vm = v_mine.detach().cpu().reshape(ref.shape).float()
+        v_ref = v_ref.float()
+        d = (vm - v_ref).abs()
+        inside = v_ref.abs() < 1e3
+        r["max_pre_round_diff"] = float((d[inside] / v_ref[inside].abs().clamp_min(1.0)).max()) if bool(inside.any()) else 0.0
+        if n:
+            ties = d[bad] <= TIE_TOL * v_ref[bad].abs().clamp_min(1.0)
+            r["ties"] = int(ties.sum())
+            r["not_ties"] = n - int(ties.sum())
+        else:
+            r["ties"] = r["not_ties"] = 0
+    return r
+
+
+def oracle_block(cfg_name: str, P, pre: str, x, bi: int):
+    """One host block (pre-norm attention + MLP with residuals) of a CONFIGS entry, evaluated by the oracle."""
+    import torch.nn.functional as F
+    from oracle import ofq_oracle as O
+    model_name, wb, ab, qkr, _, _ = CONFIGS[cfg_name]
+    if model_name != "swin_tiny":
+        return O.deit_block(x, P, pre, MODEL_DIMS[model_name]["num_heads"], wb, ab, qkr)
+    stage = next(i for i, e in enumerate((2, 4, 10, 12)) if bi < e)
+    j = bi - (0, 2, 4, 10)[stage]
+    heads = (3, 6, 12, 24)[stage]
+    C = x.shape[-1]
+    h = F.layer_norm(x, (C,), P[pre + "norm1.weight"], P[pre + "norm1.bias"], 1e-5)
+    shift = (0, 0) if j % 2 == 0 else (3, 3)
+    x = x + O.swin_window_attention(h, P, pre + "attn.", heads, wb, ab, qkr, (7, 7), shift)
+    h = F.layer_norm(x, (C,), P[pre + "norm2.weight"], P[pre + "norm2.bias"], 1e-5)
+    return x + O.qmlp(h, P, pre + "mlp.", wb, ab)
+
+
+def lsq_sites(taps: dict, pre: str):
+    """[(site name relative to the block, tap)] of the LSQ quantizer calls of one block, in forward order."""
+    return [(k[len(pre):], v) for k, v in taps.items() if k.startswith(pre) and "codes" in v]
+
+
+def weight_of_site(P, pre: str, name: str):
+    """The fp32 weight a StatsQ quantizer of a block sees, by the reference's quantizer name (relative to the block)."""
+    from oracle import ofq_oracle as O
+    if name.endswith("qk_quant"):
+        a = pre + name[: -len("qk_quant")]
+        heads = P[a + "quan_a_qkx_fn.s"].numel() // P[a + "quant_x_4_qkv.input_quant_fn.s"].numel()
+        return O.wqk_compose(P[a + "q.weight"].detach(), P[a + "k.weight"].detach(), heads)
+    if name.endswith("v_quant"):
+        return P[pre + name[: -len("v_quant")] + "v.weight"].detach()
+    return P[pre + name[: -len("statsq_fn")] + "weight"].detach()

@@ -81,3 +81,72 @@ def test_oracle_matches_reference_fullsize(cfg):
         assert rel_err(mine, ref) < 2e-5 or (mine - ref).abs().max().item() <= 1e-6 * gmax, f"{k}: {rel_err(mine, ref):.2e}"
         n += 1
     assert n > 100
+
+
+@pytest.mark.parametrize("cfg", [c for c in FC.CONFIGS if FC.CONFIGS[c][4] == 0])
+def test_exact_gemm_oracle_differs_from_the_reference_only_by_proven_ties(cfg):
+    """The oracle's EXACT_GEMM mode (matrix products accumulated in float64, rounded once) is what the CUDA path is compared
+    with on the GPU. Here it is pinned to the reference arithmetic (fp32 sgemm mode, bit-identical to the reference): every
+    block of the model is evaluated in both modes ON THE SAME block input (taken from the fp32 run); at every quantizer
+    that is not downstream of an already flipped code of that block, the codes must agree except for PROVEN TIES (pre-round
+    values within 2e-5 * max(1, |v|) of each other, i.e. the reference's own sgemm round-off decided the rounding)."""
+    torch.set_num_threads(8)
+    g = load_golden(f"full_{cfg}")
+    model_name = FC.CONFIGS[cfg][0]
+    P = FC.oracle_params(cfg, g, requires_grad=False)
+    img = FC.det_images()
+    O.TAPS = {}
+    try:
+        with torch.no_grad():
+            FC.oracle_forward(cfg, P, img, int(g["signed"]))
+        free = O.TAPS
+    finally:
+        O.TAPS = None
+    prefixes = FC.block_prefixes(model_name)
+    total_sites = flips = contaminated_sites = 0
+    worst_clean_out = 0.0
+    for bi, pre in enumerate(prefixes):
+        x_in = free[pre + "@in"]["x"]
+        res = {}
+        for exact in (False, True):
+            O.TAPS, O.EXACT_GEMM = {}, exact
+            try:
+                with torch.no_grad():
+                    out = FC.oracle_block(cfg, P, pre, x_in, bi)
+                res[exact] = (out, O.TAPS)
+            finally:
+                O.TAPS, O.EXACT_GEMM = None, False
+        dirty = 0
+        # the only weight whose codes depend on a matrix product: StatsQ of W_q^T W_k (QKR). A flipped WEIGHT code changes a
+        # whole column of qkx: it must itself be a proven tie, and everything after it in the block is downstream of it
+        wq_flips = 0
+        if pre + "attn.q.weight" in P:
+            codes = {}
+            for exact in (False, True):
+                O.EXACT_GEMM = exact
+                try:
+                    w = FC.weight_of_site(P, pre, "attn.qk_quant")
+                finally:
+                    O.EXACT_GEMM = False
+                codes[exact] = (O.statsq_codes(w, FC.CONFIGS[cfg][1])[0], O.statsq_pre_round(w, FC.CONFIGS[cfg][1])[0])
+            bad = codes[True][0] != codes[False][0]
+            wq_flips = int(bad.sum())
+            if wq_flips:
+                assert bool(((codes[True][1][bad] - codes[False][1][bad]).abs() <= FC.TIE_TOL).all()), (cfg, bi, "qk_quant")
+            flips += wq_flips
+        for (name, a), (_, b) in zip(FC.lsq_sites(res[False][1], pre), FC.lsq_sites(res[True][1], pre)):
+            if name.endswith("quan_a_qkx_fn"):
+                dirty += wq_flips
+            r = FC.compare_codes(b["codes"], b["x"] / b["se"], a["codes"], a["x"] / a["se"])
+            total_sites += 1
+            if dirty == 0:
+                assert r["not_ties"] == 0, (cfg, bi, name, r)
+            else:
+                contaminated_sites += 1
+            dirty += r["mismatches"]
+            flips += r["mismatches"]
+        if dirty == 0:
+            worst_clean_out = max(worst_clean_out, rel_err(res[True][0], res[False][0]))
+    print(f"{cfg}: {flips} flipped codes in {total_sites} quantizer calls ({contaminated_sites} downstream of a flip); "
+          f"blocks without a flip agree to {worst_clean_out:.1e}")
+    assert worst_clean_out < 1e-5
