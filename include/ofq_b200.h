@@ -316,6 +316,25 @@ OFQ_API int ofq_lsq_effective_scale_multi(const void* table, int n_jobs, int tot
 OFQ_API int ofq_wqk_compose_multi(const void* table, int n_jobs, int H, int hd, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K5  Fused quantized attention forward, query-key-reparameterised path (attention.py:210-219): ONE kernel computes
+ *   S = x_hat k_hat^T * hd^-1/2 (int8 tcgen05 MMA, K = C, accumulator in TMEM) -> softmax (registers / TMEM) -> unsigned LSQ
+ *   probability codes -> P_hat V_hat (second int8 MMA from a shared-memory P operand) -> out [B, N, C] fp32.
+ * The logits never exist in HBM. Replaces ofq_gemm(I8 scores) + ofq_softmax_quant + ofq_gemm(I8 P.V) bit for bit.
+ *   qx   int8 [B, N, C]      codes of the shared quantized input x_hat
+ *   qk   int8 [B, N, H, C]   codes of k_hat = Q(W_qk x): key d of head h at ((b*N + d)*H + h)*C
+ *   qvT  int8 [B, C, ldv]    codes of v_hat, transposed (keys contiguous, zero padded to ldv, a multiple of 16)
+ *   se_x [N], se_k [N*H] (index d*H + h), se_p [N], se_v [C]: effective step sizes; ctS [B*N, H]: code row-dots
+ *   sum_c x_aft[c] qk[b,d,h,c] (the logit term of the input shift); v_aft [C]: shift of v_hat; scale = hd^-1/2.
+ *   qp   int8 [B*H, N, ldq]  out: probability codes (ldq >= 208, multiple of 16; keys >= N hold 0)
+ *   P    optional out: probabilities fp32 [B*H, N, ldS]; qp16 optional out: exact 16-bit copy of the codes (pitch ldq);
+ *   rowsum optional out [B*H, N]: se_p[n] * sum_d qp[n, d].
+ * Limits: head dimension 64 (C = 64 H), N <= 208 tokens, C <= 384. */
+OFQ_API int ofq_qkr_attn_fwd(const int8_t* qx, const int8_t* qk, const int8_t* qvT, long long ldv, int B, int N, int H, int C,
+                             const float* se_x, const float* se_k, const float* ctS, float scale, const float* se_p,
+                             int qhi, const float* se_v, const float* v_aft, int8_t* qp, long long ldq, float* out,
+                             float* P, long long ldS, void* qp16, int fmt16, float* rowsum, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K7  CGA: freeze mask (cga.py:450-469) and the masked AdamW step (cga.py:953-1013 + torch.optim.AdamW).
  * ofq_cga_mask writes 1 for frozen, 0 for trainable (the reference's `freeze_idx`).
  * ofq_cga_adamw updates p, exp_avg, exp_avg_sq in place in ONE pass: frozen elements see a zero gradient

@@ -1,0 +1,623 @@
+// Fused quantized attention forward for the query-key-reparameterised path (reference attention.py:210-219):
+//
+//   S[b,h,n,d] = (x_hat[b,n,:] . k_hat[b,d,h,:]) * hd^-1/2        int8 codes x int8 codes -> exact int32 in TMEM (K = C)
+//   P = softmax_d(S)                                               fp32, in registers / TMEM, never in HBM as logits
+//   Qp = round(clamp(P / s_p[n], 0, 2^b - 1))                      unsigned LSQ codes (attention.py:215)
+//   O[b,n,h*hd+j] = s_p[n] (s_v[hj] sum_d Qp[n,d] Qv[b,d,hj] + v_aft[hj] sum_d Qp[n,d])      second int8 MMA (K = keys)
+//
+// One persistent CTA per SM walks (batch, head) units. Per unit the key operand k_hat (N x C codes) and the value operand
+// (hd x N codes, transposed) are staged ONCE in shared memory by TMA and serve both 128-row query tiles of the unit.
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected lane), warps 4-7 and 8-11 =
+// two softmax warpgroups; warpgroup g owns query tile g of every unit, its own TMEM accumulator (S, later reused for O)
+// and its own shared-memory P operand, so that the softmax of one tile overlaps the MMAs / loads / epilogue of the other.
+// Thread i of a warpgroup owns query row i: tcgen05.ld 32x32b hands it its row of the accumulator, the softmax needs no
+// cross-thread reduction at all. Three passes over the row, all on chip: (1) scaled logits + running maximum, logits
+// written back to TMEM; (2) exp and row sum, exponentials written back to TMEM; (3) probabilities, codes -> shared-memory
+// P operand (128B-swizzled K-major, the layout the UMMA descriptor expects) and -> HBM.
+//
+// Arithmetic is bit-identical to the three-kernel path it replaces (ofq_gemm I8 -> ofq_softmax_quant vectorised kernel ->
+// ofq_gemm I8): the logits are fmaf(acc * se_x[n], cs[d], ct[d]) exactly as the GEMM epilogue forms them, the row sum is
+// accumulated in the same order as that kernel's per-lane partial sums + xor-shuffle tree, quotients and codes use the
+// same Markstein / guarded-reciprocal sequences. tests/test_gpu_attn_fused.py asserts torch.equal on every output.
+#include <cstdint>
+#include <cmath>
+#include "ofq_b200.h"
+#include "ptx.cuh"
+#include "host_util.h"
+
+namespace ofq {
+namespace attn {
+
+constexpr int BM = 128;             // query rows per tile (UMMA M)
+constexpr int BN = 208;             // keys, padded to a multiple of 16 (UMMA N of the score product)
+constexpr int HD = 64;              // head dimension (UMMA N of the P V product)
+constexpr int MAXKB = 3;            // 128-byte K blocks of the score product: C <= 384
+constexpr int NTHREADS = 384;
+constexpr uint32_t K_BLOCK = BN * 128;          // 26 624 B
+constexpr uint32_t Q_BLOCK = BM * 128;          // 16 384 B
+constexpr uint32_t V_BLOCK = HD * 128;          //  8 192 B
+constexpr uint32_t P_BLOCK = BM * 128;          // 16 384 B
+constexpr uint32_t OFF_K = 0;
+constexpr uint32_t OFF_Q = OFF_K + MAXKB * K_BLOCK;
+constexpr uint32_t OFF_V = OFF_Q + MAXKB * Q_BLOCK;
+constexpr uint32_t OFF_P = OFF_V + 2 * V_BLOCK;                 // [warpgroup][2 blocks]
+constexpr uint32_t OFF_VEC = OFF_P + 2 * 2 * P_BLOCK;           // [warpgroup][parity]{cs[208], ct[208], sev[64], vaft[64]}
+constexpr int VEC_FLOATS = 2 * BN + 2 * HD;                      // 544
+constexpr uint32_t OFF_BAR = OFF_VEC + 2 * 2 * VEC_FLOATS * 4;
+constexpr int NBAR = 14;
+constexpr uint32_t SMEM_TOTAL = OFF_BAR + NBAR * 8 + 16;
+constexpr size_t DYN_BYTES = SMEM_TOTAL + 1024;
+static_assert(DYN_BYTES <= 227 * 1024, "shared memory budget exceeded");
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t S_COL_STRIDE = 256;          // accumulator of warpgroup g at column 256 g (208 columns; 0..63 are reused for O)
+
+struct Params {
+    int B, N, H, C, kblocks, units;
+    const float* se_x;      // [N]      effective step of the shared input quantizer
+    const float* se_k;      // [N * H]  effective step of the qkx quantizer, index d * H + h
+    const float* ctS;       // [B * N, H] code row-dots sum_c x_aft[c] qk[b,d,h,c]
+    float scale;
+    const float* se_p;      // [N]      effective step of the probability quantizer (per query row)
+    float qhi;
+    const float* se_v;      // [C]
+    const float* v_aft;     // [C]
+    int8_t* qp; long long ldq;          // out: probability codes [B*H, N, ldq]
+    float* out;                          // out: [B, N, C]
+    float* P; long long ldS;            // optional out: probabilities [B*H, N, ldS]
+    uint16_t* qp16; int f16;            // optional out: exact 16-bit copy of the codes, pitch ldq
+    float* rowsum;                       // optional out: s_p[n] * sum_d Qp[n,d], [B*H, N]
+};
+
+__device__ __forceinline__ float rcp_fast(float s) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(r) : "f"(s));
+    return r;
+}
+// exact rint(clamp(p / s, 0, qhi)) with a cheap quotient (same sequence as softmax_quant.cu prob_code)
+__device__ __forceinline__ float prob_code(float p, float s, float inv_s, float qhi) {
+    float v = __fmul_rn(p, inv_s);
+    float r = rintf(v);
+    const float dv = fabsf(v - r);
+    if (dv > 0.4998f || (dv < 2e-4f && r == qhi)) {
+        v = __fdiv_rn(p, s);
+        r = rintf(v);
+    }
+    return fminf(r, qhi);
+}
+// The conversion pipe (XU: I2F, F2I, FRND, MUFU) runs at a quarter of the FP32 rate and was 81 % busy in the first version
+// of this kernel (ncu, profiles/r02_ncu_attn_fwd.md). Everything but the one MUFU.EX2 per probability now stays on the
+// FMA / ALU pipes through the 1.5 * 2^23 trick: for |x| < 2^22, x + MAGIC has the integer rint(x) in its low mantissa bits.
+constexpr float MAGIC = 12582912.f;                 // 0x4B400000
+__device__ __forceinline__ float i2f_small(uint32_t acc) {      // exact (float)(int32_t)acc for |acc| < 2^22
+    return __fadd_rn(__uint_as_float(acc + 0x4B400000u), -MAGIC);
+}
+__device__ __forceinline__ float rint_small(float v) {          // rintf(v) (ties to even) for |v| < 2^22
+    return __fadd_rn(__fadd_rn(v, MAGIC), -MAGIC);
+}
+__device__ __forceinline__ uint32_t pack4_u8(float a, float b, float c, float d) {
+    return (uint32_t)(int)a | ((uint32_t)(int)b << 8) | ((uint32_t)(int)c << 16) | ((uint32_t)(int)d << 24);
+}
+// four small non-negative integer-valued floats -> packed bytes without a float->int conversion: q + MAGIC carries q in its low byte
+__device__ __forceinline__ uint32_t pack4_codes(float a, float b, float c, float d) {
+    const uint32_t x = __float_as_uint(__fadd_rn(a, MAGIC)), y = __float_as_uint(__fadd_rn(b, MAGIC));
+    const uint32_t z = __float_as_uint(__fadd_rn(c, MAGIC)), w = __float_as_uint(__fadd_rn(d, MAGIC));
+    return __byte_perm(__byte_perm(x, y, 0x0040), __byte_perm(z, w, 0x0040), 0x5410);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+// All per-row work walks the accumulator in chunks of 16 columns inside ROLLED loops: the three passes together are ~1 000
+// instructions. (Fully unrolled over the 208 columns the kernel was 13 000 instructions = 208 KB of straight-line code that
+// eight warps streamed through per tile: instruction fetch, not issue slots, set the pace - 302 us per layer.)
+__device__ __forceinline__ void ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+// all outstanding TMEM loads of this thread have landed; ties the registers to this point of the volatile-asm order
+__device__ __forceinline__ void ld16_done(uint32_t (&r)[16]) {
+    tmem_ld_wait();
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                      "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]) :: "memory");
+}
+__device__ __forceinline__ void ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    ld16_issue(taddr, r);
+    ld16_done(r);
+}
+__device__ __forceinline__ void st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+
+// pass 1: scaled logits s = fmaf(acc * rs, cs[d], ct[d]) (the GEMM epilogue's formula), running maximum; logits -> TMEM
+__device__ __forceinline__ void pass1_math(uint32_t (&r)[16], const float* cs, const float* ct, float rs, float& m) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+        const float4 c4 = *reinterpret_cast<const float4*>(cs + j);
+        const float4 t4 = *reinterpret_cast<const float4*>(ct + j);
+        const float s0 = fmaf(__fmul_rn(i2f_small(r[j + 0]), rs), c4.x, t4.x);
+        const float s1 = fmaf(__fmul_rn(i2f_small(r[j + 1]), rs), c4.y, t4.y);
+        const float s2 = fmaf(__fmul_rn(i2f_small(r[j + 2]), rs), c4.z, t4.z);
+        const float s3 = fmaf(__fmul_rn(i2f_small(r[j + 3]), rs), c4.w, t4.w);
+        m = fmaxf(m, fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)));
+        r[j + 0] = __float_as_uint(s0); r[j + 1] = __float_as_uint(s1);
+        r[j + 2] = __float_as_uint(s2); r[j + 3] = __float_as_uint(s3);
+    }
+}
+
+// pass 2: e = exp(s - m) for 16 columns = four "lanes" of the vectorised softmax kernel, whose lane l owns the columns
+// {4l..4l+3, 128+4l..128+4l+3} and adds them left to right: acc.{x,y,z,w} are the running sums of the four lanes
+__device__ __forceinline__ void pass2_math(uint32_t (&r)[16], float m, float4& acc) {
+    float e[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        e[j] = softmax_exp(__uint_as_float(r[j]) - m);
+        r[j] = __float_as_uint(e[j]);
+    }
+    acc.x += e[0];  acc.x += e[1];  acc.x += e[2];  acc.x += e[3];
+    acc.y += e[4];  acc.y += e[5];  acc.y += e[6];  acc.y += e[7];
+    acc.z += e[8];  acc.z += e[9];  acc.z += e[10]; acc.z += e[11];
+    acc.w += e[12]; acc.w += e[13]; acc.w += e[14]; acc.w += e[15];
+}
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+struct RowOut {
+    float* P;            // optional per-row outputs (nullptr: not requested / row outside the matrix)
+    uint16_t* qp16;
+    int f16;
+    int ldS;
+};
+
+// pass 3: probabilities and codes of 16 columns starting at key `col0`; codes -> the swizzled K-major P operand in shared
+// memory (from where the tensor core reads them and a TMA store writes them to HBM)
+__device__ __forceinline__ void pass3_math(uint32_t (&r)[16], int col0, float sum, float rinv, float s, float inv_s, float qhi,
+                                           uint8_t* prow_smem, int r7, const RowOut& o, uint32_t& csum) {
+    // codes = min(rint(p / s), qhi) with the quotient p * (1/s); the IEEE quotient decides wherever the product lies within
+    // 2e-4 of a rounding boundary (same decisions as prob_code / the unfused kernel). The boundary test is one running
+    // maximum per element and ONE branch per 16 columns instead of a branch per element.
+    float q[16];
+    float maxdv = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float e = __uint_as_float(r[j]);
+        float p = __fmul_rn(e, rinv);
+        p = fmaf(fmaf(-sum, p, e), rinv, p);                 // Markstein correction of the quotient e / sum
+        r[j] = __float_as_uint(p);
+        const float v = __fmul_rn(p, inv_s);
+        const float rr = rint_small(v);
+        maxdv = fmaxf(maxdv, fabsf(v - rr));
+        q[j] = fminf(rr, qhi);
+    }
+    if (maxdv > 0.4998f) {                                   // rare (a few percent of the chunks)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float p = __uint_as_float(r[j]);
+            const float v = __fmul_rn(p, inv_s);
+            if (fabsf(v - rint_small(v)) > 0.4998f) q[j] = fminf(rintf(__fdiv_rn(p, s)), qhi);
+        }
+    }
+    uint4 pk;
+    pk.x = pack4_codes(q[0], q[1], q[2], q[3]);
+    pk.y = pack4_codes(q[4], q[5], q[6], q[7]);
+    pk.z = pack4_codes(q[8], q[9], q[10], q[11]);
+    pk.w = pack4_codes(q[12], q[13], q[14], q[15]);
+    csum = __dp4a(pk.x, 0x01010101u, csum);                  // running integer sum of the row's codes
+    csum = __dp4a(pk.y, 0x01010101u, csum);
+    csum = __dp4a(pk.z, 0x01010101u, csum);
+    csum = __dp4a(pk.w, 0x01010101u, csum);
+    const int kb = col0 >> 7, c16 = (col0 & 127) >> 4;
+    *reinterpret_cast<uint4*>(prow_smem + kb * P_BLOCK + ((c16 ^ r7) << 4)) = pk;
+    if (o.qp16) {
+        uint4 h0, h1;
+        if (o.f16) {
+            h0.x = pack_f16x2(q[0], q[1]);   h0.y = pack_f16x2(q[2], q[3]);   h0.z = pack_f16x2(q[4], q[5]);   h0.w = pack_f16x2(q[6], q[7]);
+            h1.x = pack_f16x2(q[8], q[9]);   h1.y = pack_f16x2(q[10], q[11]); h1.z = pack_f16x2(q[12], q[13]); h1.w = pack_f16x2(q[14], q[15]);
+        } else {
+            h0.x = pack_bf16x2(q[0], q[1]);   h0.y = pack_bf16x2(q[2], q[3]);   h0.z = pack_bf16x2(q[4], q[5]);   h0.w = pack_bf16x2(q[6], q[7]);
+            h1.x = pack_bf16x2(q[8], q[9]);   h1.y = pack_bf16x2(q[10], q[11]); h1.z = pack_bf16x2(q[12], q[13]); h1.w = pack_bf16x2(q[14], q[15]);
+        }
+        uint4* hp = reinterpret_cast<uint4*>(o.qp16 + col0);
+        hp[0] = h0; hp[1] = h1;
+    }
+    if (o.P) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+            if (col0 + j < o.ldS)         // the pitch padding (keys N .. ldS-1) receives exact zeros, as in the unfused kernel
+                *reinterpret_cast<float4*>(o.P + col0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                        __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+qkr_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmP, const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* k_full = bars + 0;  uint64_t* k_empty = bars + 1;
+    uint64_t* q_full = bars + 2;  uint64_t* q_empty = bars + 3;
+    uint64_t* v_full = bars + 4;  uint64_t* v_empty = bars + 5;
+    uint64_t* s_full = bars + 6;      // [2]  MMA -> warpgroup: scores of its tile are in TMEM
+    uint64_t* s_free = bars + 8;      // [2]  warpgroup -> MMA: accumulator (O read out) may be overwritten
+    uint64_t* p_ready = bars + 10;    // [2]  warpgroup -> MMA: P operand written
+    uint64_t* o_full = bars + 12;     // [2]  MMA -> warpgroup: P V product complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nunits = ((int)blockIdx.x < p.units) ? (p.units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmP);
+        mbar_init(k_full, 1); mbar_init(k_empty, 1);
+        mbar_init(q_full, 1); mbar_init(q_empty, 1);
+        mbar_init(v_full, 1); mbar_init(v_empty, 1);
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(&s_full[g], 1); mbar_init(&s_free[g], 4);
+            mbar_init(&p_ready[g], 4); mbar_init(&o_full[g], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t kbytes = (uint32_t)p.kblocks;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------------------------------ TMA producer
+        if (elect_one()) {
+            for (int i = 0; i < nunits; ++i) {
+                const int u = blockIdx.x + i * gridDim.x, b = u / p.H, h = u - b * p.H;
+                // keys of (b, h): rows d of k_hat[b, d, h, :]; query tile 0
+                mbar_wait(k_empty, (i & 1) ^ 1);
+                mbar_arrive_expect_tx(k_full, kbytes * K_BLOCK);
+                for (int kb = 0; kb < p.kblocks; ++kb)
+                    tma_load_5d(smem + OFF_K + kb * K_BLOCK, &tmK, k_full, kb * 128, 0, h, b, 0);
+                mbar_wait(q_empty, 1);                    // Q uses 2i (tile 0) and 2i + 1 (tile 1): parity (use & 1) ^ 1
+                mbar_arrive_expect_tx(q_full, kbytes * Q_BLOCK);
+                for (int kb = 0; kb < p.kblocks; ++kb)
+                    tma_load_5d(smem + OFF_Q + kb * Q_BLOCK, &tmQ, q_full, kb * 128, 0, b, 0, 0);
+                // values of (b, h), transposed: rows hj, K = keys
+                mbar_wait(v_empty, (i & 1) ^ 1);
+                mbar_arrive_expect_tx(v_full, 2 * V_BLOCK);
+                for (int kb = 0; kb < 2; ++kb)
+                    tma_load_5d(smem + OFF_V + kb * V_BLOCK, &tmV, v_full, kb * 128, h * HD, b, 0, 0);
+                // query tile 1
+                mbar_wait(q_empty, 0);
+                mbar_arrive_expect_tx(q_full, kbytes * Q_BLOCK);
+                for (int kb = 0; kb < p.kblocks; ++kb)
+                    tma_load_5d(smem + OFF_Q + kb * Q_BLOCK, &tmQ, q_full, kb * 128, BM, b, 0, 0);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------------------------------ MMA issuer
+        if (elect_one()) {
+            const uint32_t IDESC_S = umma_idesc(2u, 1u, BM, BN);      // S32 accumulate, signed int8 operands
+            const uint32_t IDESC_O = umma_idesc(2u, 1u, BM, HD);
+            const uint32_t sK = smem_u32(smem + OFF_K), sQ = smem_u32(smem + OFF_Q), sV = smem_u32(smem + OFF_V);
+            auto scores = [&](int g) {
+                const uint32_t d = tmem_base + g * S_COL_STRIDE;
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    const uint64_t ad = umma_desc_kmajor_sw128(sQ + kb * Q_BLOCK);
+                    const uint64_t bd = umma_desc_kmajor_sw128(sK + kb * K_BLOCK);
+#pragma unroll
+                    for (uint32_t kk = 0; kk < 4; ++kk) umma_i8(d, ad + kk * 2, bd + kk * 2, IDESC_S, (kb | kk) != 0);
+                }
+            };
+            auto pv = [&](int g) {
+                const uint32_t d = tmem_base + g * S_COL_STRIDE;
+                const uint32_t sP = smem_u32(smem + OFF_P + g * 2 * P_BLOCK);
+#pragma unroll
+                for (uint32_t k = 0; k < 7; ++k) {                     // 7 x 32 = 224 >= 208 keys (columns 208..223 hold zeros)
+                    const uint32_t kb = k >> 2, kk = k & 3;
+                    umma_i8(d, umma_desc_kmajor_sw128(sP + kb * P_BLOCK) + kk * 2, umma_desc_kmajor_sw128(sV + kb * V_BLOCK) + kk * 2,
+                            IDESC_O, k != 0);
+                }
+            };
+            for (int i = 0; i < nunits; ++i) {
+                // scores of tile 0
+                mbar_wait(k_full, i & 1);
+                mbar_wait(q_full, 0);
+                mbar_wait(&s_free[0], (i & 1) ^ 1);
+                tc_fence_after();
+                scores(0);
+                tc_commit(q_empty);
+                tc_commit(&s_full[0]);
+                // P V of tile 1 of the previous unit
+                if (i > 0) {
+                    mbar_wait(&p_ready[1], (i - 1) & 1);
+                    tc_fence_after();
+                    pv(1);
+                    tc_commit(v_empty);
+                    tc_commit(&o_full[1]);
+                }
+                // scores of tile 1
+                mbar_wait(q_full, 1);
+                mbar_wait(&s_free[1], (i & 1) ^ 1);
+                tc_fence_after();
+                scores(1);
+                tc_commit(q_empty);
+                tc_commit(k_empty);
+                tc_commit(&s_full[1]);
+                // P V of tile 0
+                mbar_wait(v_full, i & 1);
+                mbar_wait(&p_ready[0], i & 1);
+                tc_fence_after();
+                pv(0);
+                tc_commit(&o_full[0]);
+            }
+            if (nunits > 0) {
+                mbar_wait(&p_ready[1], (nunits - 1) & 1);
+                tc_fence_after();
+                pv(1);
+                tc_commit(v_empty);
+                tc_commit(&o_full[1]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------------------------------ softmax warpgroups
+        const int g = (warp - 4) >> 2;               // warpgroup = query tile of every unit
+        const int q = warp & 3;                      // TMEM lane quarter of this warp
+        const int t = threadIdx.x - 128 - g * 128;   // 0..127: row inside the tile
+        const int n = g * BM + t;                    // query row
+        const bool row_ok = n < p.N;
+        const bool warp_ok = g * BM + q * 32 < p.N;  // warp-uniform: at least one valid row
+        const uint32_t trow = tmem_base + g * S_COL_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
+        uint8_t* pbase = smem + OFF_P + g * 2 * P_BLOCK;
+        uint8_t* prow = pbase + t * 128;
+        const int r7 = t & 7;
+        // keys 208..223 of the P operand are read by the last MMA and never written by data: zero them once
+        *reinterpret_cast<uint4*>(prow + P_BLOCK + ((5 ^ r7) << 4)) = make_uint4(0, 0, 0, 0);
+        fence_proxy_async_smem();
+        const float rs = row_ok ? __ldg(p.se_x + n) : 0.f;
+        const float s_p = row_ok ? __ldg(p.se_p + n) : 1.f;
+        const float inv_s = rcp_fast(s_p);
+        float* vecs = reinterpret_cast<float*>(smem + OFF_VEC) + g * 2 * VEC_FLOATS;
+        // vector entries this thread stages per unit: keys t and t + 128, and one of se_v / v_aft
+        auto load_vecs = [&](int u, float (&v)[5]) {
+            const int b = u / p.H, h = u - b * p.H;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int d = t + 128 * k;
+                float cs = 0.f, ct = -INFINITY;       // keys beyond N: logit -inf -> probability 0 -> code 0
+                if (d < p.N) {
+                    cs = __fmul_rn(__ldg(p.se_k + (long long)d * p.H + h), p.scale);
+                    ct = __fmul_rn(__ldg(p.ctS + ((long long)b * p.N + d) * p.H + h), cs);
+                }
+                v[2 * k] = cs; v[2 * k + 1] = ct;
+            }
+            v[4] = t < HD ? __ldg(p.se_v + h * HD + t) : __ldg(p.v_aft + h * HD + (t - HD));
+        };
+        float nv[5];
+        if (nunits > 0) load_vecs(blockIdx.x, nv);
+        for (int i = 0; i < nunits; ++i) {
+            const int u = blockIdx.x + i * gridDim.x, b = u / p.H, h = u - b * p.H;
+            const long long z = u;                   // (b, h) slab index = b * H + h
+            float* vb = vecs + (i & 1) * VEC_FLOATS;
+            if (t == 0) tma_store_wait_read<0>();     // last unit's code stores have read the P operand (ordered by the barrier below)
+            vb[t] = nv[0]; vb[BN + t] = nv[1];
+            if (t + 128 < BN) { vb[t + 128] = nv[2]; vb[BN + t + 128] = nv[3]; }
+            vb[2 * BN + t] = nv[4];
+            named_bar_sync(1 + g, 128);
+            if (i + 1 < nunits) load_vecs(u + gridDim.x, nv);      // next unit's vectors: latency hidden behind this tile
+            const float* cs = vb;
+            const float* ct = vb + BN;
+            const float* sev = vb + 2 * BN;
+            const float* vaft = sev + HD;
+
+            mbar_wait(&s_full[g], i & 1);
+            tc_fence_after();
+            float r_s = 0.f;                         // s_p * sum of the row's codes (rank-1 term of the P V epilogue)
+            if (warp_ok) {
+                // TMEM loads run one chunk ahead of the arithmetic (two register buffers, loops rolled in pairs)
+                constexpr int NCH = BN / 16;                      // 13 chunks of 16 columns
+                uint32_t ra[16], rb[16];
+                float m = -INFINITY;
+                ld16_issue(trow, ra);
+#pragma unroll 1
+                for (int c = 0; c < NCH; c += 2) {
+                    ld16_done(ra);
+                    if (c + 1 < NCH) ld16_issue(trow + 16 * (c + 1), rb);
+                    pass1_math(ra, cs + 16 * c, ct + 16 * c, rs, m);
+                    st16(trow + 16 * c, ra);
+                    if (c + 1 < NCH) {
+                        ld16_done(rb);
+                        if (c + 2 < NCH) ld16_issue(trow + 16 * (c + 2), ra);
+                        pass1_math(rb, cs + 16 * (c + 1), ct + 16 * (c + 1), rs, m);
+                        st16(trow + 16 * (c + 1), rb);
+                    }
+                }
+                tmem_st_wait();
+                // exp + row sum in the summation order of the vectorised softmax kernel: lane sums p[l] of its 32 lanes (columns
+                // 4l..4l+3 then 128+4l..128+4l+3), then the xor-shuffle tree p[l] + p[l^16], ... Four lanes per 16-column chunk;
+                // chunk order: for c4 = 0..3: lanes 4c4.. (first, second halves), lanes 16+4c4.. (first halves, second: c4 = 0 only)
+                float4 a[4];
+                {
+                    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+                    ld16_issue(trow, ra);
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        // ra: columns 16 c4 (issued)
+                        ld16_done(ra); ld16_issue(trow + 128 + 16 * c4, rb);
+                        pass2_math(ra, m, lo); st16(trow + 16 * c4, ra);
+                        ld16_done(rb); ld16_issue(trow + 64 + 16 * c4, ra);
+                        pass2_math(rb, m, lo); st16(trow + 128 + 16 * c4, rb);
+                        ld16_done(ra);
+                        if (c4 == 0) ld16_issue(trow + 192, rb); else if (c4 < 3) ld16_issue(trow + 16 * (c4 + 1), rb);
+                        pass2_math(ra, m, hi); st16(trow + 64 + 16 * c4, ra);
+                        if (c4 == 0) {
+                            ld16_done(rb); ld16_issue(trow + 16, ra);
+                            pass2_math(rb, m, hi); st16(trow + 192, rb);
+                        } else if (c4 < 3) {
+                            ld16_done(rb);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) ra[j] = rb[j];      // next iteration expects its first chunk in ra
+                        }
+                        a[c4] = add4(lo, hi);                                // p[l] + p[l + 16]
+                        lo = make_float4(0.f, 0.f, 0.f, 0.f); hi = lo;
+                    }
+                }
+                tmem_st_wait();
+                const float4 b0 = add4(a[0], a[2]), b1 = add4(a[1], a[3]);           // offset 8
+                const float4 c0 = add4(b0, b1);                                      // offset 4
+                const float sum = (c0.x + c0.z) + (c0.y + c0.w);                     // offsets 2, 1
+                float rinv = rcp_fast(sum);
+                rinv = fmaf(rinv, fmaf(-sum, rinv, 1.0f), rinv);
+                RowOut ro;
+                ro.P = (row_ok && p.P) ? p.P + (z * p.N + n) * p.ldS : nullptr;
+                ro.qp16 = (row_ok && p.qp16) ? p.qp16 + (z * p.N + n) * p.ldq : nullptr;
+                ro.f16 = p.f16;
+                ro.ldS = (int)p.ldS;
+                uint32_t csum = 0u;
+                ld16_issue(trow, ra);
+#pragma unroll 1
+                for (int c = 0; c < NCH; c += 2) {
+                    ld16_done(ra);
+                    if (c + 1 < NCH) ld16_issue(trow + 16 * (c + 1), rb);
+                    pass3_math(ra, 16 * c, sum, rinv, s_p, inv_s, p.qhi, prow, r7, ro, csum);
+                    if (c + 1 < NCH) {
+                        ld16_done(rb);
+                        if (c + 2 < NCH) ld16_issue(trow + 16 * (c + 2), ra);
+                        pass3_math(rb, 16 * (c + 1), sum, rinv, s_p, inv_s, p.qhi, prow, r7, ro, csum);
+                    }
+                }
+                r_s = __fmul_rn(s_p, (float)csum);
+                if (row_ok && p.rowsum) p.rowsum[z * p.N + n] = r_s;
+            }
+            // P operand (generic-proxy stores) -> visible to the async proxy (tensor core, TMA); all TMEM reads of S are done
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_ready[g]);
+            // the codes leave for HBM straight from the P operand: two TMA stores (128 queries x 128 keys each; rows >= N and
+            // keys >= ldq are clipped by the tensor map) instead of 13 scattered 16-byte stores per thread
+            named_bar_sync(3 + g, 128);
+            if (t == 0) {
+                tma_store_5d(&tmP, pbase, 0, g * BM, (int)z, 0, 0);
+                tma_store_5d(&tmP, pbase + P_BLOCK, 128, g * BM, (int)z, 0, 0);
+                tma_store_commit();
+            }
+
+            mbar_wait(&o_full[g], i & 1);
+            tc_fence_after();
+            if (warp_ok) {
+#pragma unroll 1
+                for (int c = 0; c < HD / 16; ++c) {
+                    uint32_t r[16];
+                    ld16(trow + 16 * c, r);
+                    if (row_ok) {
+                        float* orow = p.out + ((long long)b * p.N + n) * p.C + h * HD + 16 * c;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 sv = *reinterpret_cast<const float4*>(sev + 16 * c + j);
+                            const float4 va = *reinterpret_cast<const float4*>(vaft + 16 * c + j);
+                            float4 o4;
+                            o4.x = fmaf(__fmul_rn(i2f_small(r[j + 0]), s_p), sv.x, __fmul_rn(r_s, va.x));
+                            o4.y = fmaf(__fmul_rn(i2f_small(r[j + 1]), s_p), sv.y, __fmul_rn(r_s, va.y));
+                            o4.z = fmaf(__fmul_rn(i2f_small(r[j + 2]), s_p), sv.z, __fmul_rn(r_s, va.z));
+                            o4.w = fmaf(__fmul_rn(i2f_small(r[j + 3]), s_p), sv.w, __fmul_rn(r_s, va.w));
+                            *reinterpret_cast<float4*>(orow + j) = o4;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[g]);
+        }
+        if (t == 0) tma_store_wait_all<0>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace attn
+}  // namespace ofq
+
+using namespace ofq;
+
+static int make_map_u8(CUtensorMap* tm, const void* ptr, const cuuint64_t (&dims)[5], const cuuint64_t (&strides)[4],
+                       cuuint32_t box_rows) {
+    cuuint32_t box[5] = {128, box_rows, 1, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return ofq_encode_tensor_map(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<void*>(ptr), dims, strides, box, estr);
+}
+
+extern "C" int ofq_qkr_attn_fwd(const int8_t* qx, const int8_t* qk, const int8_t* qvT, long long ldv, int B, int N, int H, int C,
+                                const float* se_x, const float* se_k, const float* ctS, float scale, const float* se_p,
+                                int qhi, const float* se_v, const float* v_aft, int8_t* qp, long long ldq, float* out,
+                                float* P, long long ldS, void* qp16, int fmt16, float* rowsum, void* stream) {
+    OFQ_REQUIRE(qx && qk && qvT && se_x && se_k && ctS && se_p && se_v && v_aft && qp && out, "ofq_qkr_attn_fwd: null argument");
+    OFQ_REQUIRE(B > 0 && H > 0 && N > 0 && N <= attn::BN && C == H * attn::HD && C % 16 == 0 && C <= 128 * attn::MAXKB,
+                "ofq_qkr_attn_fwd: needs head dim 64, at most 208 tokens and C <= 384 (got N=%d H=%d C=%d)", N, H, C);
+    OFQ_REQUIRE(ldq >= attn::BN && ldq % 16 == 0 && ldv % 16 == 0 && ldv >= N && (!P || (ldS % 4 == 0 && ldS >= N)),
+                "ofq_qkr_attn_fwd: code pitch must be a multiple of 16 and >= 208, probability pitch a multiple of 4");
+    OFQ_REQUIRE(((uintptr_t)qx | (uintptr_t)qk | (uintptr_t)qvT | (uintptr_t)qp | (uintptr_t)out | (uintptr_t)P | (uintptr_t)qp16) % 16 == 0,
+                "ofq_qkr_attn_fwd: tensors must be 16-byte aligned");
+    OFQ_REQUIRE(qhi > 0 && qhi <= 127, "ofq_qkr_attn_fwd: bad level count");
+    OFQ_REQUIRE(!qp16 || fmt16 == OFQ_FMT_BF16 || fmt16 == OFQ_FMT_F16, "ofq_qkr_attn_fwd: bad 16-bit format");
+    OFQ_CHECK_ARCH();
+    CUtensorMap tmQ, tmK, tmV;
+    {   // x_hat codes [B, N, C]
+        const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)B, 1, 1};
+        const cuuint64_t st[4] = {(cuuint64_t)C, (cuuint64_t)N * C, (cuuint64_t)N * C, (cuuint64_t)N * C};
+        int rc = make_map_u8(&tmQ, qx, dims, st, attn::BM);
+        if (rc) return rc;
+    }
+    {   // k_hat codes [B, N, H, C]: rows = keys d (stride H*C), then head, then batch
+        const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)H, (cuuint64_t)B, 1};
+        const cuuint64_t st[4] = {(cuuint64_t)H * C, (cuuint64_t)C, (cuuint64_t)N * H * C, (cuuint64_t)N * H * C};
+        int rc = make_map_u8(&tmK, qk, dims, st, attn::BN);
+        if (rc) return rc;
+    }
+    {   // v_hat codes transposed [B, C, ldv] (keys contiguous, zero padded)
+        const cuuint64_t dims[5] = {(cuuint64_t)ldv, (cuuint64_t)C, (cuuint64_t)B, 1, 1};
+        const cuuint64_t st[4] = {(cuuint64_t)ldv, (cuuint64_t)C * ldv, (cuuint64_t)C * ldv, (cuuint64_t)C * ldv};
+        int rc = make_map_u8(&tmV, qvT, dims, st, attn::HD);
+        if (rc) return rc;
+    }
+    CUtensorMap tmP;
+    {   // probability codes [B*H, N, ldq]: written by TMA from the shared-memory P operand
+        const cuuint64_t dims[5] = {(cuuint64_t)ldq, (cuuint64_t)N, (cuuint64_t)B * H, 1, 1};
+        const cuuint64_t st[4] = {(cuuint64_t)ldq, (cuuint64_t)N * ldq, (cuuint64_t)N * ldq, (cuuint64_t)N * ldq};
+        int rc = make_map_u8(&tmP, qp, dims, st, attn::BM);
+        if (rc) return rc;
+    }
+    attn::Params p;
+    p.B = B; p.N = N; p.H = H; p.C = C; p.kblocks = (C + 127) / 128; p.units = B * H;
+    p.se_x = se_x; p.se_k = se_k; p.ctS = ctS; p.scale = scale; p.se_p = se_p; p.qhi = (float)qhi;
+    p.se_v = se_v; p.v_aft = v_aft; p.qp = qp; p.ldq = ldq; p.out = out; p.P = P; p.ldS = P ? ldS : 0;
+    p.qp16 = (uint16_t*)qp16; p.f16 = fmt16 == OFQ_FMT_F16; p.rowsum = rowsum;
+    static bool configured = false;
+    if (!configured) {
+        OFQ_CUDA(cudaFuncSetAttribute(attn::qkr_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::DYN_BYTES));
+        configured = true;
+    }
+    const int grid = p.units < ofq_num_sms() ? p.units : ofq_num_sms();
+    attn::qkr_attn_fwd_kernel<<<grid, attn::NTHREADS, attn::DYN_BYTES, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmP, p);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -3,6 +3,7 @@
 // (N <= 256 keys: DeiT 197/198, Swin 49), values live in registers, reductions are warp shuffles.
 #include "host_util.h"
 #include "ofq_b200.h"
+#include "ptx.cuh"
 #include <cstdint>
 
 namespace {
@@ -284,7 +285,7 @@ softmax_quant_vec_kernel(const float* __restrict__ S, long long rows, int N, lon
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int col = 4 * (e < 4 ? j0 : j1) + (e & 3);
-            x[e] = col < N ? expf(x[e] - m) : 0.f;
+            x[e] = col < N ? ofq::softmax_exp(x[e] - m) : 0.f;
             sum += x[e];
         }
         sum = wsum(sum);

@@ -408,6 +408,30 @@ def softmax_quant_bwd(dPq: torch.Tensor, P: torch.Tensor, N: int, H: int, s_eff:
     return out_a, out_bt, ldo, colsum, d_s, ds32
 
 
+def qkr_attn_fwd(qx: torch.Tensor, qk: torch.Tensor, qvT: torch.Tensor, B: int, N: int, H: int, Cc: int, se_x, se_k, ctS,
+                 scale: float, se_p, qhi: int, se_v, v_aft, *, save_p: bool = False, fmt16: Optional[int] = None,
+                 want_rowsum: bool = False):
+    """Fused QKR attention forward (ofq_qkr_attn_fwd): scores, softmax, probability codes and P.V in ONE kernel.
+    qx int8 [B*N, C], qk int8 [B*N, H*C], qvT int8 [B, C, ldv] (codes_transpose). Returns (out fp32 [B, N, C],
+    qp int8 [B*H, N, ldq], P fp32 [B*H, N, ldS] | None, qp16 | None, rowsum | None)."""
+    _cuda(qx, qk, qvT)
+    dev = qx.device
+    ldq = max(round_up(N, 16), 208)
+    ldS = round_up(N, 4)
+    out = torch.empty((B, N, Cc), dtype=torch.float32, device=dev)
+    qp = torch.empty((B * H, N, ldq), dtype=torch.int8, device=dev)
+    P = torch.empty((B * H, N, ldS), dtype=torch.float32, device=dev) if save_p else None
+    qp16 = torch.empty((B * H, N, ldq), dtype=_T16[fmt16], device=dev) if fmt16 is not None else None
+    rowsum = torch.empty((B * H, N), dtype=torch.float32, device=dev) if want_rowsum else None
+    nbytes = (B * N * Cc * (1.0 + H + 1.0 + 4.0) + B * H * N * (ldq * (1.0 + (2.0 if fmt16 is not None else 0.0)) + (4.0 * ldS if save_p else 0.0)))
+    flops = 2.0 * B * H * N * N * (Cc + Cc // H)
+    _call("qkr_attn_fwd", 1, nbytes, flops, _lib.load().ofq_qkr_attn_fwd, qx.data_ptr(), qk.data_ptr(), qvT.data_ptr(), qvT.shape[-1],
+          B, N, H, Cc, se_x.data_ptr(), se_k.data_ptr(), ctS.data_ptr(), float(scale), se_p.data_ptr(), int(qhi), se_v.data_ptr(),
+          v_aft.data_ptr(), qp.data_ptr(), ldq, out.data_ptr(), _ptr(P), ldS, _ptr(qp16), fmt16 if fmt16 is not None else FMT_F16,
+          _ptr(rowsum), _st())
+    return out, qp, P, qp16, rowsum
+
+
 # ------------------------------------------------------------------------------------------------ W_qk
 def wqk_compose(wq: torch.Tensor, wk: torch.Tensor, H: int) -> torch.Tensor:
     _cuda(wq, wk)

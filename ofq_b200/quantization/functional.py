@@ -45,6 +45,10 @@ K2P = 1 if DUAL else PLANES          # outer-K slices still looped over
 DD = 1 if DUAL else 0                # dual_delta for operands laid out [plane][...]
 # fp16 mode: let the LSQ backward of the V / qkx quantizers write the fp16 GEMM operand directly (tests toggle this)
 FUSED16 = os.environ.get("OFQ_FUSED16", "1") != "0"
+# Fused attention forward (ofq_qkr_attn_fwd: scores -> softmax -> probability codes -> P.V in one kernel, logits never in HBM)
+# for the QKR path wherever its shape limits hold (head dim 64, <= 208 tokens, C <= 384: DeiT-T / DeiT-S); OFQ_FUSED_ATTN=0
+# keeps the three-kernel path (A/B measurements, bit-identity tests).
+FUSED_ATTN = os.environ.get("OFQ_FUSED_ATTN", "1") != "0"
 # Debug tap (parity tests): when a list, every forward of the autograd functions below appends (kind, {name: tensor}) with
 # the integer codes and the pre-quantizer values of each of its quantizers, in call order. None in production.
 TAP = None
@@ -219,9 +223,10 @@ class QLinearFn(torch.autograd.Function):
         K = xc.shape[-1]
         x2d = xc.view(-1, K)
         M = x2d.shape[0]
-        dY2d = dY.contiguous().view(M, -1)
         dxhat = torch.empty((M, K), dtype=torch.float32, device=dY.device)
-        if link is not None and role == 1 and link.a16 is not None:
+        fused_in = link is not None and role == 1 and link.a16 is not None
+        dY2d = None if fused_in else dY.contiguous().view(M, -1)      # (never materialise the zero-stride placeholder)
+        if fused_in:
             # fc1 of a fused QMLP: fc2's backward already wrote this layer's fp16 gradient operand and colsum(dY); the dY
             # tensor that arrived through autograd is the zero placeholder
             if not _is_placeholder_grad(dY):
@@ -513,23 +518,32 @@ class QKRAttnCoreFn(torch.autograd.Function):
             qk, ctS = r
         sk2_hn = sk2.view(2, N, H).transpose(1, 2).contiguous()      # [2, H, N]
         se_k_hn = sk2_hn[0]
-        cs_S = se_k_hn * scale
-        ct_S = (ctS.view(B, N, H).permute(0, 2, 1) * cs_S.unsqueeze(0)).contiguous()   # [B, H, N]
         ldS = round_up(N, 4)
-        S = torch.empty((B * H, N, ldS), dtype=torch.float32, device=dev)
-        ops.gemm(GEMM_I8, qx, (C, 0, 0, N * C), qk, (H * C, 0, C, N * H * C), S, (ldS, N * ldS, H * N * ldS),
-                 N, N, C, nb1=H, nb2=B, rs=vec(se_x, N), cs=vec(cs_S, 0, N), ct=vec(ct_S, 0, N, H * N))
-        # --- softmax + probability quantizer (attention.py:213-215)
         g_p = grad_scale_factor(hiu, B * H * N)
         sp2 = ops.lsq_effective_scale(s_p, g_p, recip=True)
         se_p = sp2[0]
-        if f16 is not None and attn_bias is None and attn_mask is None:
-            P, qp, rowsum, qp16 = ops.softmax_quant(S, N, H, se_p, hiu, save_p=need_grad, fmt16=f16)
+        fused_attn = (FUSED_ATTN and attn_bias is None and attn_mask is None and hd == 64 and N <= 208 and C <= 384
+                      and (f16 is not None or not need_grad))
+        if fused_attn:
+            # --- scores, softmax, probability quantizer and P.V in one kernel (attention.py:210-219)
+            qvT = ops.codes_transpose(qv, B, N, C, C, N * C)
+            out, qp, P, qp16, _ = ops.qkr_attn_fwd(qx, qk, qvT, B, N, H, C, se_x, se_k, ctS, scale, se_p, hiu, se_v, v_aft,
+                                                   save_p=need_grad, fmt16=f16 if need_grad else None)
+            ldq = qp.shape[-1]
         else:
-            P, qp, rowsum = ops.softmax_quant(S, N, H, se_p, hiu, bias=attn_bias, mask=attn_mask, nW=nW, save_p=need_grad)
-        ldq = qp.shape[-1]
-        del S
-        out = _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C)
+            cs_S = se_k_hn * scale
+            ct_S = (ctS.view(B, N, H).permute(0, 2, 1) * cs_S.unsqueeze(0)).contiguous()   # [B, H, N]
+            S = torch.empty((B * H, N, ldS), dtype=torch.float32, device=dev)
+            ops.gemm(GEMM_I8, qx, (C, 0, 0, N * C), qk, (H * C, 0, C, N * H * C), S, (ldS, N * ldS, H * N * ldS),
+                     N, N, C, nb1=H, nb2=B, rs=vec(se_x, N), cs=vec(cs_S, 0, N), ct=vec(ct_S, 0, N, H * N))
+            # --- softmax + probability quantizer (attention.py:213-215)
+            if f16 is not None and attn_bias is None and attn_mask is None:
+                P, qp, rowsum, qp16 = ops.softmax_quant(S, N, H, se_p, hiu, save_p=need_grad, fmt16=f16)
+            else:
+                P, qp, rowsum = ops.softmax_quant(S, N, H, se_p, hiu, bias=attn_bias, mask=attn_mask, nW=nW, save_p=need_grad)
+            ldq = qp.shape[-1]
+            del S
+            out = _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C)
         if TAP is not None:
             TAP.append(("qkr", dict(x=x2d, x_b4=x_b4, se_x=se_x, qx=qx, wvc=wvc, v_out=v_out, v_b4=v_b4, se_v=se_v, qv=qv, wqkc=wqkc,
                                     qkx=qkx, k_b4=k_b4, se_k=se_k, qk=qk, P=P, se_p=se_p, qp=qp, out=out, B=B, N=N, H=H, C=C)))

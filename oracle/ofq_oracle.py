@@ -152,7 +152,7 @@ def _lsq_core(x: Tensor, alpha: Tensor, g: float, lo: int, hi: int, bit: int, al
         v = torch.sign(v)
     else:
         v = ste_round(torch.clamp(v, lo, hi))
-    _tap(tap, x=x, se=s, codes=v.detach().to(torch.int8))
+    _tap(tap, x=x, se=s, codes=v.detach().to(torch.int8), lo=lo, hi=hi)
     return v * s
 
 

@@ -206,10 +206,12 @@ def oracle_forward(cfg_name: str, P, img, signed: int):
 TIE_TOL = 2e-5     # relative (to max(1, |v|)) window in which two pre-round values count as the same value up to GEMM round-off
 
 
-def compare_codes(mine, v_mine, ref, v_ref=None):
+def compare_codes(mine, v_mine, ref, v_ref=None, lo=None, hi=None):
     """Mismatch statistics of one integer code tensor against a reference one. With the pre-round values v = x / s of both
     sides, a mismatch is a PROVEN TIE when the two values differ by no more than TIE_TOL * max(1, |v|): both are then within
-    that distance of the rounding boundary that separates the two codes."""
+    that distance of the rounding boundary that separates the two codes. With the clamp bounds [lo, hi] also the
+    straight-through mask 1[lo <= v <= hi] of the backward is compared ("mask_flips": same code, but the two pre-round values
+    lie on different sides of a clamp bound - the tie class of the gradient; lsq.py:595-599)."""
     mine = mine.detach().cpu().to(torch.int16).reshape(ref.shape)
     bad = mine != ref.to(torch.int16)
     n = int(bad.sum())
@@ -226,6 +228,10 @@ def compare_codes(mine, v_mine, ref, v_ref=None):
             r["not_ties"] = n - int(ties.sum())
         else:
             r["ties"] = r["not_ties"] = 0
+        if lo is not None:
+            flip = ((vm >= lo) & (vm <= hi)) != ((v_ref >= lo) & (v_ref <= hi))
+            r["mask_flips"] = int(flip.sum())
+            r["mask_not_ties"] = int((d[flip] > TIE_TOL * v_ref[flip].abs().clamp_min(1.0)).sum()) if r["mask_flips"] else 0
     return r
 
 

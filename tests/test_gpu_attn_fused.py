@@ -1,0 +1,122 @@
+"""The fused QKR attention forward (ofq_qkr_attn_fwd: scores -> softmax -> probability codes -> P.V in ONE tcgen05 kernel,
+logits never in HBM; reference attention.py:210-219) against the three-kernel path it replaces (int8 score GEMM ->
+ofq_softmax_quant -> int8 P.V GEMM), which the golden / oracle tests pin to the reference: every output must be
+BIT-IDENTICAL (the fused kernel reproduces the same fp32 operation order), at the DeiT-S / DeiT-T shapes and at ragged ones."""
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from ofq_b200 import _lib, ops
+    from ofq_b200.quantization import functional as Fn
+    assert _lib.load().ofq_device_ok() == 1
+    return ops, Fn
+
+
+def _unfused(ops, Fn, qx, qk, qv, B, N, H, C, se_x, se_k, ctS, scale, se_p, qhi, se_v, v_aft, fmt16):
+    from ofq_b200.ops import GEMM_I8, round_up, vec
+    se_k_hn = se_k.view(N, H).t().contiguous()
+    cs_S = se_k_hn * scale
+    ct_S = (ctS.view(B, N, H).permute(0, 2, 1) * cs_S.unsqueeze(0)).contiguous()
+    ldS = round_up(N, 4)
+    S = torch.empty((B * H, N, ldS), dtype=torch.float32, device=qx.device)
+    ops.gemm(GEMM_I8, qx, (C, 0, 0, N * C), qk, (H * C, 0, C, N * H * C), S, (ldS, N * ldS, H * N * ldS),
+             N, N, C, nb1=H, nb2=B, rs=vec(se_x, N), cs=vec(cs_S, 0, N), ct=vec(ct_S, 0, N, H * N))
+    P, qp, rowsum, qp16 = ops.softmax_quant(S, N, H, se_p, qhi, save_p=True, fmt16=fmt16)
+    out = Fn._pv_forward(qp, qp.shape[-1], rowsum, qv, se_p, se_v, v_aft, B, N, H, C)
+    return out, qp, P, qp16, rowsum
+
+
+@pytest.mark.parametrize("B,N,H,bits", [(3, 198, 6, 2), (5, 198, 3, 2), (2, 198, 6, 4), (2, 40, 2, 3), (1, 129, 1, 2),
+                                        (150, 198, 6, 2), (7, 208, 4, 2), (2, 128, 2, 2), (3, 17, 5, 4)])
+def test_fused_forward_bit_identical_to_three_kernel_path(mods, B, N, H, bits):
+    ops, Fn = mods
+    C = 64 * H
+    torch.manual_seed(B * 1000 + N + H)
+    dev = "cuda"
+    lo, hi = -(2 ** (bits - 1)), 2 ** (bits - 1) - 1
+    qhi = 2 ** bits - 1
+    qx = torch.randint(lo, hi + 1, (B * N, C), dtype=torch.int8, device=dev)
+    qk = torch.randint(lo, hi + 1, (B * N, H * C), dtype=torch.int8, device=dev)
+    qv = torch.randint(lo, hi + 1, (B * N, C), dtype=torch.int8, device=dev)
+    se_x = torch.rand(N, device=dev) * 0.5 + 0.5
+    se_k = (torch.rand(N * H, device=dev) * 0.5 + 0.5) * (2.0 / (C ** 0.5) / max(1, 2 ** (bits - 2)) ** 2)
+    ctS = torch.randn(B * N, H, device=dev)
+    se_p = torch.rand(N, device=dev) * (0.5 / qhi) + 0.2 / qhi
+    se_v = torch.rand(C, device=dev) * 0.1 + 0.05
+    v_aft = torch.randn(C, device=dev) * 0.02
+    scale = 64 ** -0.5
+    for fmt16 in (ops.FMT_F16, ops.FMT_BF16):
+        ref = _unfused(ops, Fn, qx, qk, qv, B, N, H, C, se_x, se_k, ctS, scale, se_p, qhi, se_v, v_aft, fmt16)
+        qvT = ops.codes_transpose(qv, B, N, C, C, N * C)
+        out, qp, P, qp16, rowsum = ops.qkr_attn_fwd(qx, qk, qvT, B, N, H, C, se_x, se_k, ctS, scale, se_p, qhi, se_v, v_aft,
+                                                    save_p=True, fmt16=fmt16, want_rowsum=True)
+        torch.cuda.synchronize()
+        o_r, qp_r, P_r, qp16_r, rs_r = ref
+        w = qp_r.shape[-1]
+        assert int(qp.max()) <= qhi and int(qp.min()) >= 0
+        assert torch.equal(qp[..., :w], qp_r), f"codes differ in {int((qp[..., :w] != qp_r).sum())} places"
+        assert bool((qp[..., N:] == 0).all())
+        assert torch.equal(P[..., :N], P_r[..., :N])
+        assert torch.equal(qp16[..., :w], qp16_r)
+        assert torch.equal(rowsum, rs_r)
+        assert torch.equal(out, o_r), f"out differs: {rel_err(out, o_r):.2e}"
+        # the probabilities are a softmax: rows sum to one, and the codes are their correctly rounded quantization
+        assert torch.allclose(P[..., :N].sum(-1), torch.ones(B * H, N, device=dev), atol=1e-5)
+    # no optional outputs (eval): same codes and output
+    out2, qp2, P2, qp16_2, _ = ops.qkr_attn_fwd(qx, qk, qvT, B, N, H, C, se_x, se_k, ctS, scale, se_p, qhi, se_v, v_aft)
+    assert P2 is None and qp16_2 is None and torch.equal(out2, out) and torch.equal(qp2, qp)
+
+
+@pytest.mark.parametrize("C,H,N,B", [(384, 6, 198, 4), (192, 3, 198, 3), (128, 2, 40, 3)])
+def test_module_forward_backward_identical_with_and_without_fusion(mods, C, H, N, B):
+    ops, Fn = mods
+    import ofq_b200.quantization as Q
+    from ofq_b200.host.deit import Attention
+    torch.manual_seed(5)
+    mod = Q.QAttention_qkreparam(Attention(C, H, qkv_bias=True), weight_bits=2, input_bits=2, pretrained_initialized=True)
+    with torch.no_grad():
+        for n, p in mod.named_parameters():
+            if n.endswith(".bias") and p.dim() == 1:
+                p.copy_(torch.randn(p.shape) * 0.02)
+    mod = mod.cuda().train()
+    x0 = torch.randn(B, N, C, device="cuda")
+    go = torch.randn(B, N, C, device="cuda")
+    with torch.no_grad():
+        mod(x0)
+    res = {}
+    for fused in (True, False):
+        Fn.FUSED_ATTN = fused
+        try:
+            mod.zero_grad(set_to_none=True)
+            x = x0.clone().requires_grad_(True)
+            l0 = ops.LAUNCHES
+            y, _ = mod(x)
+            nfwd = ops.LAUNCHES - l0
+            y.backward(go)
+        finally:
+            Fn.FUSED_ATTN = True
+        res[fused] = (y.detach(), x.grad.clone(), {n: p.grad.clone() for n, p in mod.named_parameters() if p.grad is not None}, nfwd)
+    assert res[True][3] < res[False][3]                       # fewer launches: the fused path really ran
+    assert torch.equal(res[True][0], res[False][0])
+    assert torch.equal(res[True][1], res[False][1])
+    for n in res[False][2]:
+        a, b = res[True][2][n], res[False][2][n]
+        assert torch.equal(a, b) or rel_err(a, b) < 1e-5, n   # (split-K atomics of the dW GEMMs are order dependent)
+    mod.eval()
+    outs = []
+    for fused in (True, False):
+        Fn.FUSED_ATTN = fused
+        try:
+            with torch.no_grad():
+                outs.append(mod(x0)[0])
+        finally:
+            Fn.FUSED_ATTN = True
+    assert rel_err(outs[0], outs[1]) < 1e-6                   # eval: the unfused path takes the scalar softmax kernel (ulp-level ties)

@@ -100,6 +100,7 @@ def test_cga_loop_of_the_reference_runs_unchanged_and_fused_optimizer_agrees(Q):
                          boundary_range=br)
     for step in range(3):
         before = {n: p.detach().clone() for n, p in model.named_parameters()}
+        before_fused = {n: p.detach().clone() for n, p in fused.named_parameters()}
         for m, opt in ((model, opt_ref), (fused, opt_fused)):
             opt.zero_grad(set_to_none=True)
             (cls, dst), _ = m(img)
@@ -115,10 +116,14 @@ def test_cga_loop_of_the_reference_runs_unchanged_and_fused_optimizer_agrees(Q):
             nfrozen += int(frozen.sum())
         assert nfrozen > 0
         for (n, p), (_, q) in zip(model.named_parameters(), fused.named_parameters()):
-            assert rel_err(q.detach(), p.detach()) < 1e-6, f"step {step} {n}: {rel_err(q.detach(), p.detach()):.2e}"
+            # (the two replicas run their own backward: split-K atomics order the gradient sums differently, and AdamW's
+            # first steps g / (|g| + eps) amplify that for gradients of the size of eps)
+            assert rel_err(q.detach(), p.detach()) < 1e-4, f"step {step} {n}: {rel_err(q.detach(), p.detach()):.2e}"
             if any(n == k + ".weight" for k in masks):
-                frozen = masks[n[: -len(".weight")]].bool()
-                assert torch.equal(q.detach()[frozen], before[n][frozen]), n     # fused path: frozen weights untouched bit for bit
+                # fused path: what ITS mask (the reference's formula on the replica's own weights) froze is untouched bit for bit
+                frozen = O.cga_freeze_mask(before_fused[n], bits, br).bool()
+                assert torch.equal(q.detach()[frozen], before_fused[n][frozen]), n
+                assert bool((q.detach()[~frozen] != before_fused[n][~frozen]).any()), n
 
 
 def test_cga_adamw_state_dict_round_trip_matches_torch_adamw(Q):

@@ -317,7 +317,7 @@ def test_teacher_forced_every_block_against_exact_oracle(Fn, cfg):
         finally:
             O.EXACT_GEMM = False
         sites, _ = _sites_of_block(taps, qkr, swin)
-        dirty = 0
+        dirty = mask_flips = 0
         for name, codes, v in sites:
             if name.endswith(("quan_a_qkx_fn", "quan_a_q_fn")):
                 dirty += sum(n for k, n in wflips.items() if k.startswith("attn.") and not k.endswith("proj.statsq_fn"))
@@ -326,13 +326,14 @@ def test_teacher_forced_every_block_against_exact_oracle(Fn, cfg):
             elif name.endswith("fc2.input_quant_fn"):
                 dirty += wflips.get("mlp.fc1.statsq_fn", 0)
             o = otaps[pre + name]
-            r = _compare_codes(codes, v, o["codes"], (o["x"] / o["se"]).float())
-            if r["mismatches"] or dirty:
+            r = _compare_codes(codes, v, o["codes"], (o["x"] / o["se"]).float(), o["lo"], o["hi"])
+            if r["mismatches"] or r["mask_flips"] or dirty:
                 r["downstream_of_flipped_tie"] = dirty > 0
                 rep[f"{key}.{name}"] = r
             if dirty == 0:
-                assert r["not_ties"] == 0, (cfg, key, name, r)
+                assert r["not_ties"] == 0 and r["mask_not_ties"] == 0, (cfg, key, name, r)
             dirty += r["mismatches"]
+            mask_flips += r["mask_flips"]
         dirty += wflips.get("mlp.fc2.statsq_fn", 0)
         rep["flipped_ties"] += dirty
         # ---- values and gradients
@@ -352,8 +353,9 @@ def test_teacher_forced_every_block_against_exact_oracle(Fn, cfg):
             if (m_ - r_).abs().max().item() > 1e-5 * gmax and e > worst:
                 worst, worst_name = e, name
         if dirty == 0:
-            rep["blocks_clean"] += 1
             assert e_out < 1e-5, (cfg, key, e_out)
+        if dirty == 0 and mask_flips == 0:      # gradients: also no straight-through mask decided by a clamp-bound tie
+            rep["blocks_clean"] += 1
             assert worst < GRAD_TOL, (cfg, key, worst_name, worst)
             if e_out > rep["worst_clean_block_out"]:
                 rep["worst_clean_block_out"] = e_out
@@ -361,7 +363,10 @@ def test_teacher_forced_every_block_against_exact_oracle(Fn, cfg):
                 rep["worst_clean_grad"], rep["worst_clean_grad_name"] = worst, f"{key}.{worst_name}"
         else:
             rep["blocks_with_flipped_tie"] += 1
-            rep[f"{key}.contaminated"] = {"block_out_rel_err": e_out, "worst_grad_rel_err": worst, "flipped": dirty}
+            rep[f"{key}.contaminated"] = {"block_out_rel_err": e_out, "worst_grad_rel_err": worst, "worst_grad": worst_name,
+                                          "flipped_codes": dirty, "flipped_masks": mask_flips}
     from ofq_b200.quantization.functional import BWD_MODE
     _report(cfg, f"teacher_forced[{BWD_MODE}]", rep)
-    assert rep["blocks_clean"] >= len(blocks) // 2, rep          # ties are rare: most blocks must be strictly checked
+    # ties are rare events per code, but a block of Swin-T's last stage quantizes 14 M W_qk weights: a good part of the
+    # blocks must still be free of any flipped tie and therefore strictly checked
+    assert rep["blocks_clean"] >= len(blocks) // 4, rep
