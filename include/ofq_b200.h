@@ -327,12 +327,26 @@ OFQ_API int ofq_wqk_compose_multi(const void* table, int n_jobs, int H, int hd, 
  *   sum_c x_aft[c] qk[b,d,h,c] (the logit term of the input shift); v_aft [C]: shift of v_hat; scale = hd^-1/2.
  *   qp   int8 [B*H, N, ldq]  out: probability codes (ldq >= 208, multiple of 16; keys >= N hold 0)
  *   P    optional out: probabilities fp32 [B*H, N, ldS]; qp16 optional out: exact 16-bit copy of the codes (pitch ldq);
- *   rowsum optional out [B*H, N]: se_p[n] * sum_d qp[n, d].
+ *   rowsum optional out [B*H, N]: se_p[n] * sum_d qp[n, d]; rowstat optional out [B*H, N, 2]: (row maximum of the scaled
+ *   logits, sum of exp) - what ofq_qkr_attn_bwd needs to recompute the probabilities bit for bit.
  * Limits: head dimension 64 (C = 64 H), N <= 208 tokens, C <= 384. */
 OFQ_API int ofq_qkr_attn_fwd(const int8_t* qx, const int8_t* qk, const int8_t* qvT, long long ldv, int B, int N, int H, int C,
                              const float* se_x, const float* se_k, const float* ctS, float scale, const float* se_p,
                              int qhi, const float* se_v, const float* v_aft, int8_t* qp, long long ldq, float* out,
-                             float* P, long long ldS, void* qp16, int fmt16, float* rowsum, void* stream);
+                             float* P, long long ldS, void* qp16, int fmt16, float* rowsum, float* rowstat, void* stream);
+/* Backward of softmax + probability quantizer fused with the GEMMs that feed it (autograd of attention.py:210-216): the
+ * logits are recomputed (int8 MMA), dP = dO v_hat^T is a 16-bit MMA, both stay in TMEM; out come the ONE 16-bit operand of the
+ * two score-gradient GEMMs, dS16[b,h,n,d] = rn16(dS * se_k[d*H+h] * se_x[n] * sc_out[0]) (pitch ldo, a multiple of 8),
+ * colsum[z,d] = sum_n dS[n,d], the step-size gradient d_s[n] of the probability quantizer (ds_part [B*H, N] is scratch) and
+ * sc_out[2] = {range scale of dS16, its reciprocal} (an a-priori power-of-two bound).
+ *   a16  16-bit [B, N, C]: dO * se_v[c] * se_p[n] * sc_in[0] (ofq_grad_prep), qv16 16-bit [B, N, C]: codes of v_hat,
+ *   rowdot [B, H, N]: sum_j dO[b,n,hj] v_aft[hj], rowstat from the forward, sc_in[2] = {scale of a16, reciprocal},
+ *   qmax_v = largest |code| of v_hat, g_s = gradient scale of the probability quantizer's step size (lsq.py:582-591). */
+OFQ_API int ofq_qkr_attn_bwd(const int8_t* qx, const int8_t* qk, const void* a16, const void* qv16, int fmt16, int B, int N,
+                             int H, int C, const float* se_x, const float* se_k, const float* ctS, float scale,
+                             const float* se_p, const float* inv_se_p, int qhi, const float* rowstat, const float* rowdot,
+                             const float* sc_in, const float* se_v, const float* v_aft, int qmax_v, float g_s, void* dS16,
+                             long long ldo, float* colsum, float* ds_part, float* d_s, float* sc_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K7  CGA: freeze mask (cga.py:450-469) and the masked AdamW step (cga.py:953-1013 + torch.optim.AdamW).

@@ -71,7 +71,9 @@ SIGNATURES = {
     "ofq_softmax_quant_ex": (_i, [_p, _i, _i, _ll, _i, _p, _p, _i, _p, _i, _p, _p, _ll, _p, _p, _i, _p]),
     "ofq_softmax_quant_bwd": (_i, [_p, _p, _i, _i, _ll, _i, _p, _i, _f, _f, _p, _i, _p, _i, _p, _p, _ll, _p, _p, _p, _i, _p, _i, _p]),
     "ofq_softmax_quant_bwd_ex": (_i, [_p, _p, _i, _i, _ll, _i, _p, _i, _f, _f, _p, _i, _p, _i, _p, _p, _ll, _p, _p, _p, _i, _p, _i, _p, _p]),
-    "ofq_qkr_attn_fwd": (_i, [_p, _p, _p, _ll, _i, _i, _i, _i, _p, _p, _p, _f, _p, _i, _p, _p, _p, _ll, _p, _p, _ll, _p, _i, _p, _p]),
+    "ofq_qkr_attn_fwd": (_i, [_p, _p, _p, _ll, _i, _i, _i, _i, _p, _p, _p, _f, _p, _i, _p, _p, _p, _ll, _p, _p, _ll, _p, _i, _p, _p, _p]),
+    "ofq_qkr_attn_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _f, _p, _p, _i, _p, _p, _p, _p, _p, _i, _f, _p, _ll, _p, _p, _p,
+                              _p, _p]),
     "ofq_wqk_compose": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "ofq_wqk_compose_bwd": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "ofq_cga_mask": (_i, [_p, _i, _i, _i, _d, _p, _p, _p, _p]),

@@ -66,6 +66,8 @@ struct Params {
     float* P; long long ldS;            // optional out: probabilities [B*H, N, ldS]
     uint16_t* qp16; int f16;            // optional out: exact 16-bit copy of the codes, pitch ldq
     float* rowsum;                       // optional out: s_p[n] * sum_d Qp[n,d], [B*H, N]
+    float2* rowstat;                     // optional out: (row maximum of the scaled logits, sum of exp) [B*H, N]: lets the
+                                         // backward recompute the probabilities bit for bit from the codes alone
 };
 
 __device__ __forceinline__ float rcp_fast(float s) {
@@ -502,6 +504,7 @@ qkr_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 }
                 r_s = __fmul_rn(s_p, (float)csum);
                 if (row_ok && p.rowsum) p.rowsum[z * p.N + n] = r_s;
+                if (row_ok && p.rowstat) p.rowstat[z * p.N + n] = make_float2(m, sum);
             }
             // P operand (generic-proxy stores) -> visible to the async proxy (tensor core, TMA); all TMEM reads of S are done
             fence_proxy_async_smem();
@@ -554,6 +557,380 @@ qkr_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
 }
 
+
+// =====================================================================================================================
+// Backward of softmax + probability quantizer, fused with the two GEMMs that feed it (autograd of attention.py:210-216):
+//
+//   S  = x_hat k_hat^T * hd^-1/2                      recomputed: int8 MMA into TMEM, as in the forward
+//   dP = dO v_hat^T                                    fp16 MMA into TMEM (A16 = dO * se_v[c] * se_p[n] * sc, codes of v)
+//   P  = softmax(S) recomputed bit for bit from the forward's row statistics (max, sum of exp)
+//   straight-through mask of the probability quantizer, ds_p partial sums, dS = alpha P (dP_masked - <P, dP_masked>)
+//   -> dS16[b,h,n,d] = fp16(dS * se_k[h,d] * se_x[n] * sc2)   the ONE operand both score-gradient GEMMs read
+//   -> colsum[z,d] = sum_n dS[n,d] (rank-1 term of d k_hat), ds_part[z,n] (step-size gradient of the quantizer)
+//
+// Neither the logits S, nor the probabilities P, nor dP ever exist in HBM (the three-kernel path wrote dP in fp32, and read
+// it and P back: 366 MB per layer at DeiT-S / batch 128). One accumulator pair (S at TMEM column 0, dP at 256) per CTA:
+// all eight compute warps work on the same 128-query tile, warpgroup 0 on keys 0..127, warpgroup 1 on keys 128..207; the
+// two row-wise scalars a thread needs from the other half (<P, dP> and the ds_p term) cross through shared memory.
+constexpr uint32_t B_OFF_K = 0;
+constexpr uint32_t B_OFF_Q = B_OFF_K + MAXKB * K_BLOCK;
+constexpr uint32_t B_OFF_A = B_OFF_Q + MAXKB * Q_BLOCK;            // A16 tile: 128 queries x 64 channels of the head (16-bit)
+constexpr uint32_t B_OFF_V = B_OFF_A + Q_BLOCK;                    // v codes (16-bit): 208 keys x 64 channels
+constexpr uint32_t B_OFF_VEC = B_OFF_V + K_BLOCK;                  // [parity]{cs[208], ct[208], ca[208]}
+constexpr int B_VEC_FLOATS = 3 * BN;
+constexpr uint32_t B_OFF_RED = B_OFF_VEC + 2 * B_VEC_FLOATS * 4;   // [2 halves][2]{dot, dsp}[128 rows]
+constexpr uint32_t B_OFF_COL = B_OFF_RED + 2 * 2 * BM * 4;         // [4 lane quarters][208 keys] column sums of dS
+constexpr uint32_t B_OFF_BAR = B_OFF_COL + 4 * BN * 4;
+constexpr int B_NBAR = 6;
+constexpr size_t B_DYN_BYTES = B_OFF_BAR + B_NBAR * 8 + 16 + 1024;
+static_assert(B_DYN_BYTES <= 227 * 1024, "shared memory budget exceeded");
+constexpr uint32_t DP_COL = 256;
+
+struct BwdParams {
+    int B, N, H, C, kblocks, units;
+    const float* se_x; const float* se_k; const float* ctS; float scale;
+    const float* se_p; const float* inv_se_p; float qhi;
+    const float2* rowstat;      // [B*H, N] (max, sum) from the forward
+    const float* rowdot;        // [B, H, N] sum_j dO[b,n,hj] v_aft[hj]
+    const float* sc_in;         // [2] range scale of A16 and its reciprocal
+    const float* sc_out;        // [2] range scale of dS16 (ofq attn_bwd_scale_kernel) and its reciprocal
+    uint16_t* dS16; long long ldo; int f16;
+    float* colsum;              // [B*H, N]
+    float* ds_part;             // [B*H, N]
+};
+
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16(float lo, float hi) { return F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+
+template <bool F16>
+__global__ void __launch_bounds__(NTHREADS, 1)
+qkr_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmV, const BwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF_BAR);
+    uint64_t* kv_full = bars + 0;  uint64_t* kv_empty = bars + 1;     // keys + values of a unit
+    uint64_t* qa_full = bars + 2;  uint64_t* qa_empty = bars + 3;     // queries + gradient operand of a tile
+    uint64_t* acc_full = bars + 4; uint64_t* acc_free = bars + 5;     // S and dP of a tile in TMEM / read out
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_NBAR);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nunits = ((int)blockIdx.x < p.units) ? (p.units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmV);
+        mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
+        mbar_init(qa_full, 1); mbar_init(qa_empty, 1);
+        mbar_init(acc_full, 1); mbar_init(acc_free, 8);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t kbytes = (uint32_t)p.kblocks;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int i = 0; i < nunits; ++i) {
+                const int u = blockIdx.x + i * gridDim.x, b = u / p.H, h = u - b * p.H;
+                mbar_wait(kv_empty, (i & 1) ^ 1);
+                mbar_arrive_expect_tx(kv_full, kbytes * K_BLOCK + K_BLOCK);
+                for (int kb = 0; kb < p.kblocks; ++kb)
+                    tma_load_5d(smem + B_OFF_K + kb * K_BLOCK, &tmK, kv_full, kb * 128, 0, h, b, 0);
+                tma_load_5d(smem + B_OFF_V, &tmV, kv_full, h * HD, 0, b, 0, 0);
+                for (int tile = 0; tile < 2; ++tile) {
+                    const int use = 2 * i + tile;
+                    mbar_wait(qa_empty, (use & 1) ^ 1);
+                    mbar_arrive_expect_tx(qa_full, kbytes * Q_BLOCK + Q_BLOCK);
+                    for (int kb = 0; kb < p.kblocks; ++kb)
+                        tma_load_5d(smem + B_OFF_Q + kb * Q_BLOCK, &tmQ, qa_full, kb * 128, tile * BM, b, 0, 0);
+                    tma_load_5d(smem + B_OFF_A, &tmA, qa_full, h * HD, tile * BM, b, 0, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t IDESC_S = umma_idesc(2u, 1u, BM, BN);
+            const uint32_t IDESC_D = umma_idesc(1u, F16 ? 0u : 1u, BM, BN);      // F32 accumulate, fp16 / bf16 operands
+            const uint32_t sK = smem_u32(smem + B_OFF_K), sQ = smem_u32(smem + B_OFF_Q);
+            const uint64_t adD = umma_desc_kmajor_sw128(smem_u32(smem + B_OFF_A));
+            const uint64_t bdD = umma_desc_kmajor_sw128(smem_u32(smem + B_OFF_V));
+            for (int i = 0; i < nunits; ++i) {
+                for (int tile = 0; tile < 2; ++tile) {
+                    const int use = 2 * i + tile;
+                    if (tile == 0) mbar_wait(kv_full, i & 1);
+                    mbar_wait(qa_full, use & 1);
+                    mbar_wait(acc_free, (use & 1) ^ 1);
+                    tc_fence_after();
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        const uint64_t ad = umma_desc_kmajor_sw128(sQ + kb * Q_BLOCK);
+                        const uint64_t bd = umma_desc_kmajor_sw128(sK + kb * K_BLOCK);
+#pragma unroll
+                        for (uint32_t kk = 0; kk < 4; ++kk) umma_i8(tmem_base, ad + kk * 2, bd + kk * 2, IDESC_S, (kb | kk) != 0);
+                    }
+#pragma unroll
+                    for (uint32_t kk = 0; kk < 4; ++kk) umma_f16(tmem_base + DP_COL, adD + kk * 2, bdD + kk * 2, IDESC_D, kk != 0);
+                    tc_commit(qa_empty);
+                    if (tile == 1) tc_commit(kv_empty);
+                    tc_commit(acc_full);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int g = (warp - 4) >> 2;               // key half: 0 -> chunks 0..7 (keys 0..127), 1 -> chunks 8..12 (keys 128..207)
+        const int q = warp & 3;
+        const int t = (threadIdx.x - 128) & 127;     // row inside the tile
+        const int c_lo = g ? 8 : 0, c_hi = g ? BN / 16 : 8;
+        const uint32_t trS = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const uint32_t trD = trS + DP_COL;
+        float* vecs = reinterpret_cast<float*>(smem + B_OFF_VEC);
+        float* red = reinterpret_cast<float*>(smem + B_OFF_RED);          // [half][{dot, dsp}][row]
+        float* colpart = reinterpret_cast<float*>(smem + B_OFF_COL);      // [quarter][key]
+        const int tid = threadIdx.x - 128;            // 0..255
+        const float inv_sc_in = __ldg(p.sc_in + 1);
+        const float sc_out = __ldg(p.sc_out);
+        // column this lane ends up with after the halving reduction over the warp's 32 rows (bits 4..1 of the lane)
+        const int mycol = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        auto load_vecs = [&](int u, float (&v)[3]) {
+            const int b = u / p.H, h = u - b * p.H;
+            v[0] = 0.f; v[1] = -INFINITY; v[2] = 0.f;
+            if (tid < BN && tid < p.N) {
+                const float ca = __ldg(p.se_k + (long long)tid * p.H + h);
+                v[2] = ca;
+                v[0] = __fmul_rn(ca, p.scale);
+                v[1] = __fmul_rn(__ldg(p.ctS + ((long long)b * p.N + tid) * p.H + h), v[0]);
+            }
+        };
+        float nv[3];
+        if (nunits > 0) load_vecs(blockIdx.x, nv);
+        for (int k = tid; k < 4 * BN; k += 256) colpart[k] = 0.f;      // (ordered before its first use by the barrier below)
+        for (int i = 0; i < nunits; ++i) {
+            const int u = blockIdx.x + i * gridDim.x, b = u / p.H, h = u - b * p.H;
+            const long long z = u;
+            float* vb = vecs + (i & 1) * B_VEC_FLOATS;
+            if (tid < BN) { vb[tid] = nv[0]; vb[BN + tid] = nv[1]; vb[2 * BN + tid] = nv[2]; }
+            named_bar_sync(1, 256);
+            if (i + 1 < nunits) load_vecs(u + gridDim.x, nv);
+            const float* cs = vb;
+            const float* ct = vb + BN;
+            const float* ca = vb + 2 * BN;
+            for (int tile = 0; tile < 2; ++tile) {
+                const int use = 2 * i + tile;
+                const int n = tile * BM + t;
+                const bool row_ok = n < p.N;
+                const bool warp_ok = tile * BM + q * 32 < p.N;
+                float rs = 0.f, s_p = 1.f, inv_sep = 0.f, m = 0.f, sum = 1.f, rdot = 0.f, sca_row = 0.f;
+                if (row_ok) {
+                    rs = __ldg(p.se_x + n); s_p = __ldg(p.se_p + n); inv_sep = __ldg(p.inv_se_p + n);
+                    const float2 st = __ldg(p.rowstat + z * p.N + n);
+                    m = st.x; sum = st.y;
+                    rdot = __ldg(p.rowdot + ((long long)b * p.H + h) * p.N + n);
+                    sca_row = __fmul_rn(sc_out, rs);
+                }
+                const float inv_s = rcp_fast(s_p);
+                float rinv = rcp_fast(sum);
+                rinv = fmaf(rinv, fmaf(-sum, rinv, 1.0f), rinv);
+                mbar_wait(acc_full, use & 1);
+                tc_fence_after();
+                float dot = 0.f, dsp = 0.f;
+                if (warp_ok) {
+                    // ---- pass 1: probabilities, codes, straight-through mask; P -> S columns, masked dP -> dP columns
+#pragma unroll 1
+                    for (int c = c_lo; c < c_hi; ++c) {
+                        uint32_t rS[16], rD[16];
+                        ld16_issue(trS + 16 * c, rS);
+                        ld16_issue(trD + 16 * c, rD);
+                        ld16_done(rS);
+                        ld16_done(rD);
+                        float pr[16], vq[16];
+                        float flag = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 c4 = *reinterpret_cast<const float4*>(cs + 16 * c + j);
+                            const float4 t4 = *reinterpret_cast<const float4*>(ct + 16 * c + j);
+                            const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float sl = fmaf(__fmul_rn(i2f_small(rS[j + k]), rs), cc[k], tt[k]);
+                                const float e = softmax_exp(sl - m);
+                                float pp = __fmul_rn(e, rinv);
+                                pp = fmaf(fmaf(-sum, pp, e), rinv, pp);
+                                pr[j + k] = pp;
+                                const float v = __fmul_rn(pp, inv_s);
+                                vq[j + k] = v;
+                                const float rr = rint_small(v);
+                                const float dv = fabsf(v - rr);
+                                // rounding boundary, or the clamp bound itself (it decides the straight-through mask)
+                                flag = fmaxf(flag, (dv > 0.4998f || (dv < 2e-4f && rr == p.qhi)) ? 1.f : 0.f);
+                            }
+                        }
+                        if (flag != 0.f) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float rr = rint_small(vq[j]);
+                                const float dv = fabsf(vq[j] - rr);
+                                if (dv > 0.4998f || (dv < 2e-4f && rr == p.qhi)) vq[j] = __fdiv_rn(pr[j], s_p);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float v = vq[j];
+                            const float qq = fminf(rint_small(v), p.qhi);
+                            const bool inside = v <= p.qhi;                   // v >= 0 always holds for probabilities
+                            const float gq = fmaf(__fmul_rn(__uint_as_float(rD[j]), inv_sep), inv_sc_in, rdot);
+                            dsp = fmaf(gq, inside ? (qq - v) : qq, dsp);
+                            const float dp = inside ? gq : 0.f;
+                            dot = fmaf(pr[j], dp, dot);
+                            rS[j] = __float_as_uint(pr[j]);
+                            rD[j] = __float_as_uint(dp);
+                        }
+                        st16(trS + 16 * c, rS);
+                        st16(trD + 16 * c, rD);
+                    }
+                    tmem_st_wait();
+                }
+                red[(g * 2 + 0) * BM + t] = dot;
+                red[(g * 2 + 1) * BM + t] = dsp;
+                named_bar_sync(2, 256);
+                dot = red[(0 * 2 + 0) * BM + t] + red[(1 * 2 + 0) * BM + t];
+                if (g == 0 && row_ok) p.ds_part[z * p.N + n] = red[(0 * 2 + 1) * BM + t] + red[(1 * 2 + 1) * BM + t];
+                if (warp_ok) {
+                    // ---- pass 2: dS = alpha P (dP - <P, dP>); scaled 16-bit copy -> HBM; column sums over the warp's rows
+                    uint16_t* orow = p.dS16 + (z * p.N + n) * p.ldo;
+#pragma unroll 1
+                    for (int c = c_lo; c < c_hi; ++c) {
+                        uint32_t rS[16], rD[16];
+                        ld16_issue(trS + 16 * c, rS);
+                        ld16_issue(trD + 16 * c, rD);
+                        ld16_done(rS);
+                        ld16_done(rD);
+                        float ds[16];
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 a4 = *reinterpret_cast<const float4*>(ca + 16 * c + j);
+                            const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
+                            float va[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float raw = __uint_as_float(rS[j + k]) * (__uint_as_float(rD[j + k]) - dot);
+                                ds[j + k] = row_ok ? p.scale * raw : 0.f;
+                                va[k] = ds[j + k] * aa[k] * sca_row;
+                            }
+                            pk[j / 2] = pack16<F16>(va[0], va[1]);
+                            pk[j / 2 + 1] = pack16<F16>(va[2], va[3]);
+                        }
+                        if (row_ok) {
+                            const int d0 = 16 * c;
+                            if (d0 < p.ldo) *reinterpret_cast<uint4*>(orow + d0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            if (d0 + 8 < p.ldo) *reinterpret_cast<uint4*>(orow + d0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        }
+                        // sum of each of the 16 columns over the warp's 32 rows: recursive halving (16 shuffles instead of 80)
+                        float w8[8], w4[4], w2[2], w1;
+                        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float send = h16 ? ds[k] : ds[k + 8], keep = h16 ? ds[k + 8] : ds[k];
+                            w8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float send = h8 ? w8[k] : w8[k + 4], keep = h8 ? w8[k + 4] : w8[k];
+                            w4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const float send = h4 ? w4[k] : w4[k + 2], keep = h4 ? w4[k + 2] : w4[k];
+                            w2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                        }
+                        {
+                            const float send = h2 ? w2[0] : w2[1], keep = h2 ? w2[1] : w2[0];
+                            w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                        }
+                        w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+                        if ((lane & 1) == 0) colpart[q * BN + 16 * c + mycol] += w1;     // one lane per (quarter, key): no race
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_free);
+            }
+            // column sums of the unit: the four lane quarters in a fixed order (quarters without rows in tile 1 added nothing)
+            named_bar_sync(3, 256);
+            if (tid < p.N) {
+                float a = colpart[tid];
+                colpart[tid] = 0.f;                          // each reader clears exactly what it read, for the next unit
+#pragma unroll
+                for (int qq = 1; qq < 4; ++qq) { a += colpart[qq * BN + tid]; colpart[qq * BN + tid] = 0.f; }
+                p.colsum[z * p.N + tid] = a;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// fp16 range scale of dS16 from an a-priori bound (the maximum of dP is not known before the fused kernel has run):
+//   |dO| <= 2^15 / (sc_in min se_v min se_p),  |dP| <= 64 max|dO| (max se_v qmax_v + max|v_aft|),
+//   |dS se_k se_x| <= 2 alpha max|dP| max se_k max se_x;   sc = 2^k with bound * sc in [2^14, 2^15).
+// The bound is loose (a few binades): with 5 exponent bits that costs range at the bottom, where gradients do not matter.
+__global__ void __launch_bounds__(256)
+attn_bwd_scale_kernel(const float* __restrict__ sc_in, const float* __restrict__ se_v, const float* __restrict__ v_aft, int C,
+                      const float* __restrict__ se_p, const float* __restrict__ se_x, int N, const float* __restrict__ se_k, int NH,
+                      float qmax_v, float alpha, float* __restrict__ out2) {
+    __shared__ float red[6][8];
+    float mn_v = INFINITY, mx_v = 0.f, mx_a = 0.f, mn_p = INFINITY, mx_x = 0.f, mx_k = 0.f;
+    for (int i = threadIdx.x; i < C; i += 256) { const float a = fabsf(se_v[i]); mn_v = fminf(mn_v, a); mx_v = fmaxf(mx_v, a); mx_a = fmaxf(mx_a, fabsf(v_aft[i])); }
+    for (int i = threadIdx.x; i < N; i += 256) { mn_p = fminf(mn_p, fabsf(se_p[i])); mx_x = fmaxf(mx_x, fabsf(se_x[i])); }
+    for (int i = threadIdx.x; i < NH; i += 256) mx_k = fmaxf(mx_k, fabsf(se_k[i]));
+    float v[6] = {-mn_v, mx_v, mx_a, -mn_p, mx_x, mx_k};          // minima as maxima of the negated values
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] = fmaxf(v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 6; ++k) { float a = red[k][0]; for (int w = 1; w < 8; ++w) a = fmaxf(a, red[k][w]); v[k] = a; }
+        const float max_dO = 32768.f / (sc_in[0] * fmaxf(-v[0], 1e-30f) * fmaxf(-v[3], 1e-30f));
+        const float max_dP = 64.f * max_dO * (v[1] * qmax_v + v[2]);
+        float bound = 2.f * alpha * max_dP * v[5] * v[4];
+        if (!(bound > 0.f) || !isfinite(bound)) bound = 1.f;
+        int e;
+        frexpf(bound, &e);                            // bound = f * 2^e, f in [0.5, 1)  ->  bound * 2^(15 - e) in [2^14, 2^15)
+        const float sc = ldexpf(1.f, 15 - e);
+        out2[0] = sc;
+        out2[1] = 1.f / sc;
+    }
+}
+
+// d_s[n] = g_s * sum_z part[z][n] in a fixed order (deterministic)
+__global__ void __launch_bounds__(256)
+attn_ds_reduce_kernel(const float* __restrict__ part, int nz, int N, float g_s, float* __restrict__ d_s) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + tx;
+    float acc = 0.f;
+    if (n < N)
+        for (int z = ty; z < nz; z += 8) acc += part[(long long)z * N + n];
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && n < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][tx];
+        d_s[n] = g_s * s;
+    }
+}
+
 }  // namespace attn
 }  // namespace ofq
 
@@ -569,7 +946,7 @@ static int make_map_u8(CUtensorMap* tm, const void* ptr, const cuuint64_t (&dims
 extern "C" int ofq_qkr_attn_fwd(const int8_t* qx, const int8_t* qk, const int8_t* qvT, long long ldv, int B, int N, int H, int C,
                                 const float* se_x, const float* se_k, const float* ctS, float scale, const float* se_p,
                                 int qhi, const float* se_v, const float* v_aft, int8_t* qp, long long ldq, float* out,
-                                float* P, long long ldS, void* qp16, int fmt16, float* rowsum, void* stream) {
+                                float* P, long long ldS, void* qp16, int fmt16, float* rowsum, float* rowstat, void* stream) {
     OFQ_REQUIRE(qx && qk && qvT && se_x && se_k && ctS && se_p && se_v && v_aft && qp && out, "ofq_qkr_attn_fwd: null argument");
     OFQ_REQUIRE(B > 0 && H > 0 && N > 0 && N <= attn::BN && C == H * attn::HD && C % 16 == 0 && C <= 128 * attn::MAXKB,
                 "ofq_qkr_attn_fwd: needs head dim 64, at most 208 tokens and C <= 384 (got N=%d H=%d C=%d)", N, H, C);
@@ -610,7 +987,7 @@ extern "C" int ofq_qkr_attn_fwd(const int8_t* qx, const int8_t* qk, const int8_t
     p.B = B; p.N = N; p.H = H; p.C = C; p.kblocks = (C + 127) / 128; p.units = B * H;
     p.se_x = se_x; p.se_k = se_k; p.ctS = ctS; p.scale = scale; p.se_p = se_p; p.qhi = (float)qhi;
     p.se_v = se_v; p.v_aft = v_aft; p.qp = qp; p.ldq = ldq; p.out = out; p.P = P; p.ldS = P ? ldS : 0;
-    p.qp16 = (uint16_t*)qp16; p.f16 = fmt16 == OFQ_FMT_F16; p.rowsum = rowsum;
+    p.qp16 = (uint16_t*)qp16; p.f16 = fmt16 == OFQ_FMT_F16; p.rowsum = rowsum; p.rowstat = reinterpret_cast<float2*>(rowstat);
     static bool configured = false;
     if (!configured) {
         OFQ_CUDA(cudaFuncSetAttribute(attn::qkr_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::DYN_BYTES));
@@ -618,6 +995,72 @@ extern "C" int ofq_qkr_attn_fwd(const int8_t* qx, const int8_t* qk, const int8_t
     }
     const int grid = p.units < ofq_num_sms() ? p.units : ofq_num_sms();
     attn::qkr_attn_fwd_kernel<<<grid, attn::NTHREADS, attn::DYN_BYTES, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmP, p);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+
+static int make_map_16(CUtensorMap* tm, const void* ptr, const cuuint64_t (&dims)[5], const cuuint64_t (&strides)[4],
+                       cuuint32_t box_rows, bool f16) {
+    cuuint32_t box[5] = {64, box_rows, 1, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return ofq_encode_tensor_map(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
+                                 const_cast<void*>(ptr), dims, strides, box, estr);
+}
+
+extern "C" int ofq_qkr_attn_bwd(const int8_t* qx, const int8_t* qk, const void* a16, const void* qv16, int fmt16, int B, int N,
+                                int H, int C, const float* se_x, const float* se_k, const float* ctS, float scale,
+                                const float* se_p, const float* inv_se_p, int qhi, const float* rowstat, const float* rowdot,
+                                const float* sc_in, const float* se_v, const float* v_aft, int qmax_v, float g_s, void* dS16,
+                                long long ldo, float* colsum, float* ds_part, float* d_s, float* sc_out, void* stream) {
+    OFQ_REQUIRE(qx && qk && a16 && qv16 && se_x && se_k && ctS && se_p && inv_se_p && rowstat && rowdot && sc_in && se_v && v_aft &&
+                dS16 && colsum && ds_part && d_s && sc_out, "ofq_qkr_attn_bwd: null argument");
+    OFQ_REQUIRE(B > 0 && H > 0 && N > 0 && N <= attn::BN && C == H * attn::HD && C <= 128 * attn::MAXKB,
+                "ofq_qkr_attn_bwd: needs head dim 64, at most 208 tokens and C <= 384 (got N=%d H=%d C=%d)", N, H, C);
+    OFQ_REQUIRE(fmt16 == OFQ_FMT_BF16 || fmt16 == OFQ_FMT_F16, "ofq_qkr_attn_bwd: bad 16-bit format");
+    OFQ_REQUIRE(ldo % 8 == 0 && ldo >= N, "ofq_qkr_attn_bwd: output pitch must be a multiple of 8 and >= N");
+    OFQ_REQUIRE(((uintptr_t)qx | (uintptr_t)qk | (uintptr_t)a16 | (uintptr_t)qv16 | (uintptr_t)dS16) % 16 == 0 && (uintptr_t)rowstat % 8 == 0,
+                "ofq_qkr_attn_bwd: tensors must be 16-byte aligned");
+    OFQ_CHECK_ARCH();
+    const bool f16 = fmt16 == OFQ_FMT_F16;
+    CUtensorMap tmQ, tmK, tmA, tmV;
+    {
+        const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)B, 1, 1};
+        const cuuint64_t st[4] = {(cuuint64_t)C, (cuuint64_t)N * C, (cuuint64_t)N * C, (cuuint64_t)N * C};
+        int rc = make_map_u8(&tmQ, qx, dims, st, attn::BM);
+        if (rc) return rc;
+    }
+    {
+        const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)H, (cuuint64_t)B, 1};
+        const cuuint64_t st[4] = {(cuuint64_t)H * C, (cuuint64_t)C, (cuuint64_t)N * H * C, (cuuint64_t)N * H * C};
+        int rc = make_map_u8(&tmK, qk, dims, st, attn::BN);
+        if (rc) return rc;
+    }
+    {   // 16-bit tensors [B, N, C]: one 64-channel (128-byte) slice of a head per box row
+        const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)B, 1, 1};
+        const cuuint64_t st[4] = {(cuuint64_t)C * 2, (cuuint64_t)N * C * 2, (cuuint64_t)N * C * 2, (cuuint64_t)N * C * 2};
+        int rc = make_map_16(&tmA, a16, dims, st, attn::BM, f16);
+        if (rc) return rc;
+        rc = make_map_16(&tmV, qv16, dims, st, attn::BN, f16);
+        if (rc) return rc;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    attn::attn_bwd_scale_kernel<<<1, 256, 0, st>>>(sc_in, se_v, v_aft, C, se_p, se_x, N, se_k, N * H, (float)qmax_v, scale, sc_out);
+    attn::BwdParams p;
+    p.B = B; p.N = N; p.H = H; p.C = C; p.kblocks = (C + 127) / 128; p.units = B * H;
+    p.se_x = se_x; p.se_k = se_k; p.ctS = ctS; p.scale = scale; p.se_p = se_p; p.inv_se_p = inv_se_p; p.qhi = (float)qhi;
+    p.rowstat = reinterpret_cast<const float2*>(rowstat); p.rowdot = rowdot; p.sc_in = sc_in; p.sc_out = sc_out;
+    p.dS16 = (uint16_t*)dS16; p.ldo = ldo; p.f16 = f16; p.colsum = colsum; p.ds_part = ds_part;
+    static bool configured = false;
+    if (!configured) {
+        OFQ_CUDA(cudaFuncSetAttribute(attn::qkr_attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::B_DYN_BYTES));
+        OFQ_CUDA(cudaFuncSetAttribute(attn::qkr_attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::B_DYN_BYTES));
+        configured = true;
+    }
+    const int grid = p.units < ofq_num_sms() ? p.units : ofq_num_sms();
+    if (f16) attn::qkr_attn_bwd_kernel<true><<<grid, attn::NTHREADS, attn::B_DYN_BYTES, st>>>(tmQ, tmK, tmA, tmV, p);
+    else attn::qkr_attn_bwd_kernel<false><<<grid, attn::NTHREADS, attn::B_DYN_BYTES, st>>>(tmQ, tmK, tmA, tmV, p);
+    attn::attn_ds_reduce_kernel<<<(N + 31) / 32, 256, 0, st>>>(ds_part, B * H, N, g_s, d_s);
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }

@@ -410,10 +410,10 @@ def softmax_quant_bwd(dPq: torch.Tensor, P: torch.Tensor, N: int, H: int, s_eff:
 
 def qkr_attn_fwd(qx: torch.Tensor, qk: torch.Tensor, qvT: torch.Tensor, B: int, N: int, H: int, Cc: int, se_x, se_k, ctS,
                  scale: float, se_p, qhi: int, se_v, v_aft, *, save_p: bool = False, fmt16: Optional[int] = None,
-                 want_rowsum: bool = False):
+                 want_rowsum: bool = False, want_rowstat: bool = False):
     """Fused QKR attention forward (ofq_qkr_attn_fwd): scores, softmax, probability codes and P.V in ONE kernel.
     qx int8 [B*N, C], qk int8 [B*N, H*C], qvT int8 [B, C, ldv] (codes_transpose). Returns (out fp32 [B, N, C],
-    qp int8 [B*H, N, ldq], P fp32 [B*H, N, ldS] | None, qp16 | None, rowsum | None)."""
+    qp int8 [B*H, N, ldq], P fp32 [B*H, N, ldS] | None, qp16 | None, rowsum | None[, rowstat [B*H, N, 2] with want_rowstat])."""
     _cuda(qx, qk, qvT)
     dev = qx.device
     ldq = max(round_up(N, 16), 208)
@@ -423,13 +423,38 @@ def qkr_attn_fwd(qx: torch.Tensor, qk: torch.Tensor, qvT: torch.Tensor, B: int, 
     P = torch.empty((B * H, N, ldS), dtype=torch.float32, device=dev) if save_p else None
     qp16 = torch.empty((B * H, N, ldq), dtype=_T16[fmt16], device=dev) if fmt16 is not None else None
     rowsum = torch.empty((B * H, N), dtype=torch.float32, device=dev) if want_rowsum else None
+    rowstat = torch.empty((B * H, N, 2), dtype=torch.float32, device=dev) if want_rowstat else None
     nbytes = (B * N * Cc * (1.0 + H + 1.0 + 4.0) + B * H * N * (ldq * (1.0 + (2.0 if fmt16 is not None else 0.0)) + (4.0 * ldS if save_p else 0.0)))
     flops = 2.0 * B * H * N * N * (Cc + Cc // H)
     _call("qkr_attn_fwd", 1, nbytes, flops, _lib.load().ofq_qkr_attn_fwd, qx.data_ptr(), qk.data_ptr(), qvT.data_ptr(), qvT.shape[-1],
           B, N, H, Cc, se_x.data_ptr(), se_k.data_ptr(), ctS.data_ptr(), float(scale), se_p.data_ptr(), int(qhi), se_v.data_ptr(),
           v_aft.data_ptr(), qp.data_ptr(), ldq, out.data_ptr(), _ptr(P), ldS, _ptr(qp16), fmt16 if fmt16 is not None else FMT_F16,
-          _ptr(rowsum), _st())
+          _ptr(rowsum), _ptr(rowstat), _st())
+    if want_rowstat:
+        return out, qp, P, qp16, rowsum, rowstat
     return out, qp, P, qp16, rowsum
+
+
+def qkr_attn_bwd(qx, qk, a16, qv16, fmt16: int, B: int, N: int, H: int, Cc: int, se_x, se_k, ctS, scale: float, sp2, qhi: int,
+                 rowstat, rowdot, sc_in, se_v, v_aft, qmax_v: int, g_s: float):
+    """Fused backward of softmax + probability quantizer with the score recomputation and dP = dO v^T (ofq_qkr_attn_bwd).
+    sp2 = [se_p, 1/se_p]. Returns (dS16 [B, 1, H, N, ldo], ldo, colsum [B*H, N], d_s [N], sc4 = [scale of dS16, 1/scale, 0, 0])."""
+    _cuda(qx, qk, a16, qv16)
+    dev = qx.device
+    ldo = round_up(N, 8)
+    # (zero-filled: the pitch padding is read by the GEMMs' TMA boxes)
+    dS16 = torch.zeros((B, 1, H, N, ldo), dtype=_T16[fmt16], device=dev) if ldo > round_up(N, 8) else torch.empty((B, 1, H, N, ldo), dtype=_T16[fmt16], device=dev)
+    colsum = torch.empty((B * H, N), dtype=torch.float32, device=dev)
+    ds_part = torch.empty((B * H, N), dtype=torch.float32, device=dev)
+    d_s = torch.empty(N, dtype=torch.float32, device=dev)
+    sc4 = torch.zeros(4, dtype=torch.float32, device=dev)
+    nbytes = B * N * Cc * (1.0 + H + 2.0 + 2.0) + B * H * N * (2.0 * ldo + 16.0)
+    flops = 2.0 * B * H * N * N * (Cc + Cc // H)
+    _call("qkr_attn_bwd", 3, nbytes, flops, _lib.load().ofq_qkr_attn_bwd, qx.data_ptr(), qk.data_ptr(), a16.data_ptr(), qv16.data_ptr(),
+          fmt16, B, N, H, Cc, se_x.data_ptr(), se_k.data_ptr(), ctS.data_ptr(), float(scale), sp2[0].data_ptr(), sp2[1].data_ptr(),
+          int(qhi), rowstat.data_ptr(), rowdot.data_ptr(), sc_in.data_ptr(), se_v.data_ptr(), v_aft.data_ptr(), int(qmax_v), float(g_s),
+          dS16.data_ptr(), ldo, colsum.data_ptr(), ds_part.data_ptr(), d_s.data_ptr(), sc4.data_ptr(), _st())
+    return dS16, ldo, colsum, d_s, sc4
 
 
 # ------------------------------------------------------------------------------------------------ W_qk

@@ -49,6 +49,9 @@ FUSED16 = os.environ.get("OFQ_FUSED16", "1") != "0"
 # for the QKR path wherever its shape limits hold (head dim 64, <= 208 tokens, C <= 384: DeiT-T / DeiT-S); OFQ_FUSED_ATTN=0
 # keeps the three-kernel path (A/B measurements, bit-identity tests).
 FUSED_ATTN = os.environ.get("OFQ_FUSED_ATTN", "1") != "0"
+# ... and its backward (ofq_qkr_attn_bwd: logits recomputed, dP = dO v^T, softmax / quantizer backward in one kernel; neither P
+# nor dP in HBM). fp16 mode only; OFQ_FUSED_ATTN_BWD=0 keeps dP GEMM + ofq_softmax_quant_bwd on the saved probabilities.
+FUSED_ATTN_BWD = os.environ.get("OFQ_FUSED_ATTN_BWD", "1") != "0"
 # Debug tap (parity tests): when a list, every forward of the autograd functions below appends (kind, {name: tensor}) with
 # the integer codes and the pre-quantizer values of each of its quantizers, in call order. None in production.
 TAP = None
@@ -414,7 +417,7 @@ def _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C):
 
 
 def _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=None, qp16=None, sc=None, amax_dv=None,
-                     amax_dp=None):
+                     amax_dp=None, skip_dp=False):
     """fp16 backward of P_hat V_hat with ONE copy A16[b,n,c] = fp16(dO * se_v[c] * se_p[n] * sc):
         dP_hat[z,n,d]  = 1/(se_p[n] sc) * sum_j A16[b,n,hj] qv[b,d,hj] + sum_j dO[b,n,hj] v_aft[hj]
         dv_hat[b,d,hj] = 1/(se_v[hj] sc) * sum_n qp[z,n,d] A16[b,n,hj]                    (both operands MN-major)"""
@@ -426,14 +429,18 @@ def _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=Non
     a16 = prep["rm"]                                                     # [1, B, N, C]
     if qv16 is None:
         qv16 = ops.codes_to_bf16(qv, B, N, C, C, N * C, False, FMT)      # [B, N, C]
-    dPq = torch.empty((B * H, N, ldS), dtype=torch.float32, device=dO.device)
-    ops.gemm(GEMM_BWD, a16, (C, 0, hd, N * C), qv16, (C, 0, hd, N * C), dPq, (ldS, N * ldS, H * N * ldS), N, N, hd,
-             nb1=H, nb2=B, rs=vec(sp2[1], N), cs=_scalar(sc), rt=vec(prep["rowdot"], 0, N, H * N), amax=amax_dp)
+    dPq = None
+    if not skip_dp:
+        dPq = torch.empty((B * H, N, ldS), dtype=torch.float32, device=dO.device)
+        ops.gemm(GEMM_BWD, a16, (C, 0, hd, N * C), qv16, (C, 0, hd, N * C), dPq, (ldS, N * ldS, H * N * ldS), N, N, hd,
+                 nb1=H, nb2=B, rs=vec(sp2[1], N), cs=_scalar(sc), rt=vec(prep["rowdot"], 0, N, H * N), amax=amax_dp)
     if qp16 is None:
         qp16 = ops.codes_to_bf16(qp, B * H, N, ldq, ldq, N * ldq, False, FMT)    # [B*H, N, ldq]
     dvhat = torch.empty((B, N, C), dtype=torch.float32, device=dO.device)
     ops.gemm(GEMM_BWD, qp16, (ldq, 0, N * ldq, H * N * ldq), a16, (C, 0, hd, N * C), dvhat, (C, hd, N * C), N, hd, N,
              nb1=H, nb2=B, a_mn=True, b_mn=True, rs=_scalar(sc), cs=vec(sv2[1], 0, hd), amax=amax_dv)
+    if skip_dp:       # the fused attention backward forms dP itself: hand it the operand, the rank-1 term and the range scale
+        return (a16, prep["rowdot"], sc, qv16), dvhat
     return dPq, dvhat
 
 
@@ -524,11 +531,15 @@ class QKRAttnCoreFn(torch.autograd.Function):
         se_p = sp2[0]
         fused_attn = (FUSED_ATTN and attn_bias is None and attn_mask is None and hd == 64 and N <= 208 and C <= 384
                       and (f16 is not None or not need_grad))
+        rowstat = None
         if fused_attn:
             # --- scores, softmax, probability quantizer and P.V in one kernel (attention.py:210-219)
             qvT = ops.codes_transpose(qv, B, N, C, C, N * C)
-            out, qp, P, qp16, _ = ops.qkr_attn_fwd(qx, qk, qvT, B, N, H, C, se_x, se_k, ctS, scale, se_p, hiu, se_v, v_aft,
-                                                   save_p=need_grad, fmt16=f16 if need_grad else None)
+            fused_bwd = need_grad and FUSED_ATTN_BWD and F16
+            res = ops.qkr_attn_fwd(qx, qk, qvT, B, N, H, C, se_x, se_k, ctS, scale, se_p, hiu, se_v, v_aft,
+                                   save_p=need_grad and not fused_bwd, fmt16=f16 if need_grad else None, want_rowstat=fused_bwd)
+            out, qp, P, qp16 = res[:4]
+            rowstat = res[5] if fused_bwd else None
             ldq = qp.shape[-1]
         else:
             cs_S = se_k_hn * scale
@@ -545,10 +556,14 @@ class QKRAttnCoreFn(torch.autograd.Function):
             del S
             out = _pv_forward(qp, ldq, rowsum, qv, se_p, se_v, v_aft, B, N, H, C)
         if TAP is not None:
+            P_tap = P
+            if P_tap is None and fused_attn:      # debug only: the probabilities of the fused kernel (bit-identical re-run)
+                P_tap = ops.qkr_attn_fwd(qx, qk, qvT, B, N, H, C, se_x, se_k, ctS, scale, se_p, hiu, se_v, v_aft, save_p=True)[2]
             TAP.append(("qkr", dict(x=x2d, x_b4=x_b4, se_x=se_x, qx=qx, wvc=wvc, v_out=v_out, v_b4=v_b4, se_v=se_v, qv=qv, wqkc=wqkc,
-                                    qkx=qkx, k_b4=k_b4, se_k=se_k, qk=qk, P=P, se_p=se_p, qp=qp, out=out, B=B, N=N, H=H, C=C)))
+                                    qkx=qkx, k_b4=k_b4, se_k=se_k, qk=qk, P=P_tap, se_p=se_p, qp=qp, out=out, B=B, N=N, H=H, C=C)))
         ctx.save_for_backward(xc, wq, wk, x_b4, x_aft, v_b4, v_aft, k_b4, k_aft, qx, sx2, wvc, cs_v, ics_v, v_out, qv, sv2,
-                              wqkc, cs_qk, ics_qk, qkx, qk, sk2, sk2_hn, P, qp, sp2, qx16, qv16, qk16, qp16, wv16, wqk16)
+                              wqkc, cs_qk, ics_qk, qkx, qk, sk2, sk2_hn, P, qp, sp2, qx16, qv16, qk16, qp16, wv16, wqk16,
+                              rowstat, ctS if rowstat is not None else None)
         ctx.cfg = (B, N, C, H, lo, hi, hiu, scale, g_x, g_v, g_k, g_p, ldS, ldq, bv is not None,
                    attn_bias is not None, link)
         if link is not None:
@@ -558,7 +573,7 @@ class QKRAttnCoreFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dO):
         (xc, wq, wk, x_b4, x_aft, v_b4, v_aft, k_b4, k_aft, qx, sx2, wvc, cs_v, ics_v, v_out, qv, sv2, wqkc, cs_qk, ics_qk,
-         qkx, qk, sk2, sk2_hn, P, qp, sp2, qx16, qv16, qk16, qp16, wv16, wqk16) = ctx.saved_tensors
+         qkx, qk, sk2, sk2_hn, P, qp, sp2, qx16, qv16, qk16, qp16, wv16, wqk16, rowstat, ctS) = ctx.saved_tensors
         B, N, C, H, lo, hi, hiu, scale, g_x, g_v, g_k, g_p, ldS, ldq, has_bv, has_bias, link = ctx.cfg
         se_x, se_v, se_k, se_p, se_k_hn = sx2[0], sv2[0], sk2[0], sp2[0], sk2_hn[0]
         M = B * N
@@ -569,9 +584,15 @@ class QKRAttnCoreFn(torch.autograd.Function):
         # (range scale from that bound), so d v_out / d qkx never exist in fp32 and ofq_grad_prep is not needed there
         fused16 = F16 and FUSED16 and C % 128 == 0      # streaming layout of the (token, head)-segmented qkx pass
         amax = torch.zeros(3, dtype=torch.float32, device=dev) if F16 else None      # max |d v_hat|, |d k_hat|, |dP_hat|
-        dPq, dvhat = _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16, qp16,
-                                  link.sc if link is not None else None, amax_dv=amax[0:1] if fused16 else None,
-                                  amax_dp=amax[2:3] if F16 else None)
+        fused_bwd = rowstat is not None
+        if fused_bwd:
+            (a16_o, rowdot, sc_o, qv16), dvhat = _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16, qp16,
+                                                                 link.sc if link is not None else None,
+                                                                 amax_dv=amax[0:1] if fused16 else None, skip_dp=True)
+        else:
+            dPq, dvhat = _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16, qp16,
+                                      link.sc if link is not None else None, amax_dv=amax[0:1] if fused16 else None,
+                                      amax_dp=amax[2:3] if F16 else None)
         # --- V quantizer and V linear
         dxhat = torch.empty((M, C), dtype=torch.float32, device=dev)
         if fused16:
@@ -587,14 +608,20 @@ class QKRAttnCoreFn(torch.autograd.Function):
                                                sc=sc_v[0] if sc_v else None, **({"wc16": wv16} if F16 else {}))
         # --- softmax + probability quantizer, then the two score GEMMs
         if F16:
-            # |dS| = |alpha P (dP - sum P dP)| <= 2 alpha max|dPq|; ONE copy dS16[b,h,n,d] = fp16(dS se_k[h,d] se_x[n] sc)
-            # (max |dP_hat| comes from the epilogue of the GEMM that produced it: no pass over dP_hat)
-            sc = ops.scale_from_max(amax[2:3], v1=se_k_hn, v2=se_x, mult=2.0 * scale, product=True)
-            dS16, _, ldo, colsum_dS, ds_p, dS32 = ops.softmax_quant_bwd(dPq, P, N, H, se_p, hiu, scale, g_p, se_k_hn, True,
-                                                                      se_x, want_ds32=has_bias, fmt=FMT, scale4=sc,
-                                                                      single=True)
+            if fused_bwd:
+                # logits recomputed from the codes, dP = dO v^T, softmax / quantizer backward: one kernel, nothing of it in HBM
+                dS16, ldo, colsum_dS, ds_p, sc = ops.qkr_attn_bwd(qx, qk, a16_o, qv16, FMT, B, N, H, C, se_x, se_k, ctS, scale, sp2, hiu,
+                                                                rowstat, rowdot, sc_o, se_v, v_aft, -lo, g_p)
+                dS32 = None
+            else:
+                # |dS| = |alpha P (dP - sum P dP)| <= 2 alpha max|dPq|; ONE copy dS16[b,h,n,d] = fp16(dS se_k[h,d] se_x[n] sc)
+                # (max |dP_hat| comes from the epilogue of the GEMM that produced it: no pass over dP_hat)
+                sc = ops.scale_from_max(amax[2:3], v1=se_k_hn, v2=se_x, mult=2.0 * scale, product=True)
+                dS16, _, ldo, colsum_dS, ds_p, dS32 = ops.softmax_quant_bwd(dPq, P, N, H, se_p, hiu, scale, g_p, se_k_hn, True,
+                                                                          se_x, want_ds32=has_bias, fmt=FMT, scale4=sc,
+                                                                          single=True)
+                del dPq
             slab = N * ldo
-            del dPq
             # d x_hat[b,n,c] += 1/(se_x[n] sc) sum_h sum_d dS16[b,h,n,d] qk[b,d,h,c]      (heads = outer-K, B MN-major)
             if qk16 is None:
                 qk16 = ops.codes_to_bf16(qk, 1, M, H * C, H * C, 0, False, FMT)     # [1, M, H*C] = [b][d][h][c]

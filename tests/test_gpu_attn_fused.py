@@ -92,8 +92,8 @@ def test_module_forward_backward_identical_with_and_without_fusion(mods, C, H, N
     with torch.no_grad():
         mod(x0)
     res = {}
-    for fused in (True, False):
-        Fn.FUSED_ATTN = fused
+    for mode in ("fused", "fused_fwd", "unfused"):
+        Fn.FUSED_ATTN, Fn.FUSED_ATTN_BWD = mode != "unfused", mode == "fused"
         try:
             mod.zero_grad(set_to_none=True)
             x = x0.clone().requires_grad_(True)
@@ -101,15 +101,24 @@ def test_module_forward_backward_identical_with_and_without_fusion(mods, C, H, N
             y, _ = mod(x)
             nfwd = ops.LAUNCHES - l0
             y.backward(go)
+            nall = ops.LAUNCHES - l0
         finally:
-            Fn.FUSED_ATTN = True
-        res[fused] = (y.detach(), x.grad.clone(), {n: p.grad.clone() for n, p in mod.named_parameters() if p.grad is not None}, nfwd)
-    assert res[True][3] < res[False][3]                       # fewer launches: the fused path really ran
-    assert torch.equal(res[True][0], res[False][0])
-    assert torch.equal(res[True][1], res[False][1])
-    for n in res[False][2]:
-        a, b = res[True][2][n], res[False][2][n]
+            Fn.FUSED_ATTN = Fn.FUSED_ATTN_BWD = True
+        res[mode] = (y.detach(), x.grad.clone(), {n: p.grad.clone() for n, p in mod.named_parameters() if p.grad is not None}, nfwd, nall)
+    assert res["fused"][3] < res["unfused"][3] and res["fused"][4] < res["fused_fwd"][4]     # the fused kernels really ran
+    assert torch.equal(res["fused"][0], res["unfused"][0]) and torch.equal(res["fused_fwd"][0], res["unfused"][0])
+    # fused forward + three-kernel backward on the saved probabilities: the same numbers as the unfused path
+    assert torch.equal(res["fused_fwd"][1], res["unfused"][1])
+    for n in res["unfused"][2]:
+        a, b = res["fused_fwd"][2][n], res["unfused"][2][n]
         assert torch.equal(a, b) or rel_err(a, b) < 1e-5, n   # (split-K atomics of the dW GEMMs are order dependent)
+    # fused backward: same mathematics, another power-of-two range scale of the 16-bit dS operand (a-priori bound instead of the
+    # measured maximum of dP): agreement at the rounding level of the fp16 operands
+    gmax = max(v.abs().max().item() for v in res["unfused"][2].values())
+    assert rel_err(res["fused"][1], res["unfused"][1]) < 1e-3
+    for n in res["unfused"][2]:
+        a, b = res["fused"][2][n], res["unfused"][2][n]
+        assert rel_err(a, b) < 1e-3 or (a - b).abs().max().item() <= 1e-5 * gmax, f"{n}: {rel_err(a, b):.2e}"
     mod.eval()
     outs = []
     for fused in (True, False):
@@ -120,3 +129,56 @@ def test_module_forward_backward_identical_with_and_without_fusion(mods, C, H, N
         finally:
             Fn.FUSED_ATTN = True
     assert rel_err(outs[0], outs[1]) < 1e-6                   # eval: the unfused path takes the scalar softmax kernel (ulp-level ties)
+
+
+@pytest.mark.parametrize("B,N,H,bits", [(3, 198, 6, 2), (4, 198, 3, 4), (2, 40, 2, 3), (150, 198, 6, 2), (2, 129, 1, 2)])
+def test_fused_backward_against_three_kernel_path(mods, B, N, H, bits):
+    """ofq_qkr_attn_bwd (logits recomputed, dP in TMEM, softmax / quantizer backward in the same kernel) against
+    dP GEMM -> ofq_softmax_quant_bwd on stored probabilities: dS (un-scaled), its column sums and the step-size gradient."""
+    ops, Fn = mods
+    from ofq_b200.ops import GEMM_F16, FMT_F16, vec
+    C = 64 * H
+    torch.manual_seed(B * 77 + N + H)
+    dev = "cuda"
+    lo, hi = -(2 ** (bits - 1)), 2 ** (bits - 1) - 1
+    qhi = 2 ** bits - 1
+    qx = torch.randint(lo, hi + 1, (B * N, C), dtype=torch.int8, device=dev)
+    qk = torch.randint(lo, hi + 1, (B * N, H * C), dtype=torch.int8, device=dev)
+    qv = torch.randint(lo, hi + 1, (B * N, C), dtype=torch.int8, device=dev)
+    se_x = torch.rand(N, device=dev) * 0.5 + 0.5
+    se_k = (torch.rand(N * H, device=dev) * 0.5 + 0.5) * (2.0 / (C ** 0.5) / max(1, 2 ** (bits - 2)) ** 2)
+    ctS = torch.randn(B * N, H, device=dev)
+    se_p = torch.rand(N, device=dev) * (0.5 / qhi) + 0.2 / qhi
+    sp2 = torch.stack((se_p, 1.0 / se_p)).contiguous()
+    se_v = torch.rand(C, device=dev) * 0.1 + 0.05
+    sv2 = torch.stack((se_v, 1.0 / se_v)).contiguous()
+    v_aft = torch.randn(C, device=dev) * 0.02
+    scale, g_p = 64 ** -0.5, 1.0 / ((qhi * B * H * N) ** 0.5)
+    dO = torch.randn(B, N, C, device=dev) * 1e-3
+    qvT = ops.codes_transpose(qv, B, N, C, C, N * C)
+    fwd = ops.qkr_attn_fwd(qx, qk, qvT, B, N, H, C, se_x, se_k, ctS, scale, se_p, qhi, se_v, v_aft, save_p=True, fmt16=FMT_F16,
+                           want_rowstat=True)
+    out, qp, P, qp16, _, rowstat = fwd
+    ldq, ldS = qp.shape[-1], P.shape[-1]
+    # ---- three-kernel reference
+    amax = torch.zeros(1, device=dev)
+    dPq, dvhat = Fn._pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, None, qp16, None, amax_dp=amax)
+    se_k_hn = se_k.view(N, H).t().contiguous()
+    sc = ops.scale_from_max(amax, v1=se_k_hn, v2=se_x, mult=2.0 * scale, product=True)
+    dS16_r, _, ldo, colsum_r, ds_r, _ = ops.softmax_quant_bwd(dPq, P, N, H, se_p, qhi, scale, g_p, se_k_hn, True, se_x, fmt=FMT_F16,
+                                                               scale4=sc, single=True)
+    # ---- fused
+    (a16, rowdot, sc_in, qv16), dvhat2 = Fn._pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, None, qp16, None, skip_dp=True)
+    dS16, ldo2, colsum, ds, sc2 = ops.qkr_attn_bwd(qx, qk, a16, qv16, FMT_F16, B, N, H, C, se_x, se_k, ctS, scale, sp2, qhi, rowstat, rowdot,
+                                                   sc_in, se_v, v_aft, -lo, g_p)
+    torch.cuda.synchronize()
+    assert ldo2 == ldo and torch.equal(dvhat, dvhat2)
+    s_r, s_f = float(sc[0]), float(sc2[0])
+    assert s_f > 0 and s_f <= s_r * 1.0001 and s_f >= s_r / 4096          # a-priori bound: never tighter than the measured one, a few binades looser
+    a = dS16.float()[..., :N] / s_f
+    b = dS16_r.float()[..., :N] / s_r
+    assert not torch.isinf(dS16.float()).any() and not torch.isnan(a).any()
+    assert rel_err(a, b) < 2e-3, rel_err(a, b)                            # two fp16 roundings at different scales
+    assert bool((dS16.float()[..., N:] == 0).all())
+    assert rel_err(colsum, colsum_r) < 1e-4
+    assert rel_err(ds, ds_r) < 1e-4
