@@ -101,9 +101,9 @@ __device__ __forceinline__ uint32_t pack4_u8(float a, float b, float c, float d)
 }
 // four small non-negative integer-valued floats -> packed bytes without a float->int conversion: q + MAGIC carries q in its low byte
 __device__ __forceinline__ uint32_t pack4_codes(float a, float b, float c, float d) {
-    const uint32_t x = __float_as_uint(__fadd_rn(a, MAGIC)), y = __float_as_uint(__fadd_rn(b, MAGIC));
-    const uint32_t z = __float_as_uint(__fadd_rn(c, MAGIC)), w = __float_as_uint(__fadd_rn(d, MAGIC));
-    return __byte_perm(__byte_perm(x, y, 0x0040), __byte_perm(z, w, 0x0040), 0x5410);
+    const float2 xy = __fadd2_rn(make_float2(a, b), make_float2(MAGIC, MAGIC)), zw = __fadd2_rn(make_float2(c, d), make_float2(MAGIC, MAGIC));
+    return __byte_perm(__byte_perm(__float_as_uint(xy.x), __float_as_uint(xy.y), 0x0040),
+                       __byte_perm(__float_as_uint(zw.x), __float_as_uint(zw.y), 0x0040), 0x5410);
 }
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
     uint32_t r;
@@ -147,18 +147,24 @@ __device__ __forceinline__ void st16(uint32_t taddr, const uint32_t (&r)[16]) {
 }
 
 // pass 1: scaled logits s = fmaf(acc * rs, cs[d], ct[d]) (the GEMM epilogue's formula), running maximum; logits -> TMEM
+// Packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2: two IEEE operations per issue slot) throughout: the kernel is bound by
+// instruction issue and dependency latency, not by any memory system.
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 i2f_small2(uint32_t a, uint32_t b) {      // exact int32 -> fp32 for |x| < 2^22, no conversion pipe
+    return __fadd2_rn(f2(__uint_as_float(a + 0x4B400000u), __uint_as_float(b + 0x4B400000u)), f2(-MAGIC));
+}
 __device__ __forceinline__ void pass1_math(uint32_t (&r)[16], const float* cs, const float* ct, float rs, float& m) {
+    const float2 rs2 = f2(rs);
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
         const float4 c4 = *reinterpret_cast<const float4*>(cs + j);
         const float4 t4 = *reinterpret_cast<const float4*>(ct + j);
-        const float s0 = fmaf(__fmul_rn(i2f_small(r[j + 0]), rs), c4.x, t4.x);
-        const float s1 = fmaf(__fmul_rn(i2f_small(r[j + 1]), rs), c4.y, t4.y);
-        const float s2 = fmaf(__fmul_rn(i2f_small(r[j + 2]), rs), c4.z, t4.z);
-        const float s3 = fmaf(__fmul_rn(i2f_small(r[j + 3]), rs), c4.w, t4.w);
-        m = fmaxf(m, fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)));
-        r[j + 0] = __float_as_uint(s0); r[j + 1] = __float_as_uint(s1);
-        r[j + 2] = __float_as_uint(s2); r[j + 3] = __float_as_uint(s3);
+        const float2 s01 = __ffma2_rn(__fmul2_rn(i2f_small2(r[j + 0], r[j + 1]), rs2), f2(c4.x, c4.y), f2(t4.x, t4.y));
+        const float2 s23 = __ffma2_rn(__fmul2_rn(i2f_small2(r[j + 2], r[j + 3]), rs2), f2(c4.z, c4.w), f2(t4.z, t4.w));
+        m = fmaxf(m, fmaxf(fmaxf(s01.x, s01.y), fmaxf(s23.x, s23.y)));
+        r[j + 0] = __float_as_uint(s01.x); r[j + 1] = __float_as_uint(s01.y);
+        r[j + 2] = __float_as_uint(s23.x); r[j + 3] = __float_as_uint(s23.y);
     }
 }
 
@@ -166,10 +172,15 @@ __device__ __forceinline__ void pass1_math(uint32_t (&r)[16], const float* cs, c
 // {4l..4l+3, 128+4l..128+4l+3} and adds them left to right: acc.{x,y,z,w} are the running sums of the four lanes
 __device__ __forceinline__ void pass2_math(uint32_t (&r)[16], float m, float4& acc) {
     float e[16];
+    const float2 nm = f2(-m), l2e = f2(1.4426950408889634f);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        e[j] = softmax_exp(__uint_as_float(r[j]) - m);
+    for (int j = 0; j < 16; j += 2) {
+        // softmax_exp(s - m) = ex2(rn((s - m) * log2 e)) on two columns at a time
+        const float2 t = __fmul2_rn(__fadd2_rn(f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), nm), l2e);
+        asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(e[j]) : "f"(t.x));
+        asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(e[j + 1]) : "f"(t.y));
         r[j] = __float_as_uint(e[j]);
+        r[j + 1] = __float_as_uint(e[j + 1]);
     }
     acc.x += e[0];  acc.x += e[1];  acc.x += e[2];  acc.x += e[3];
     acc.y += e[4];  acc.y += e[5];  acc.y += e[6];  acc.y += e[7];
@@ -194,16 +205,19 @@ __device__ __forceinline__ void pass3_math(uint32_t (&r)[16], int col0, float su
     // maximum per element and ONE branch per 16 columns instead of a branch per element.
     float q[16];
     float maxdv = 0.f;
+    const float2 rinv2 = f2(rinv), nsum2 = f2(-sum), is2 = f2(inv_s), mg = f2(MAGIC), nmg = f2(-MAGIC), m1 = f2(-1.f);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const float e = __uint_as_float(r[j]);
-        float p = __fmul_rn(e, rinv);
-        p = fmaf(fmaf(-sum, p, e), rinv, p);                 // Markstein correction of the quotient e / sum
-        r[j] = __float_as_uint(p);
-        const float v = __fmul_rn(p, inv_s);
-        const float rr = rint_small(v);
-        maxdv = fmaxf(maxdv, fabsf(v - rr));
-        q[j] = fminf(rr, qhi);
+    for (int j = 0; j < 16; j += 2) {
+        const float2 e = f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+        float2 p = __fmul2_rn(e, rinv2);
+        p = __ffma2_rn(__ffma2_rn(nsum2, p, e), rinv2, p);   // Markstein correction of the quotient e / sum
+        r[j] = __float_as_uint(p.x); r[j + 1] = __float_as_uint(p.y);
+        const float2 v = __fmul2_rn(p, is2);
+        const float2 rr = __fadd2_rn(__fadd2_rn(v, mg), nmg);            // rint (ties to even) without the conversion pipe
+        const float2 dv = __ffma2_rn(rr, m1, v);                         // v - rr (exact)
+        maxdv = fmaxf(maxdv, fmaxf(fabsf(dv.x), fabsf(dv.y)));
+        q[j] = fminf(rr.x, qhi);
+        q[j + 1] = fminf(rr.y, qhi);
     }
     if (maxdv > 0.4998f) {                                   // rare (a few percent of the chunks)
 #pragma unroll
@@ -533,12 +547,11 @@ qkr_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         for (int j = 0; j < 16; j += 4) {
                             const float4 sv = *reinterpret_cast<const float4*>(sev + 16 * c + j);
                             const float4 va = *reinterpret_cast<const float4*>(vaft + 16 * c + j);
-                            float4 o4;
-                            o4.x = fmaf(__fmul_rn(i2f_small(r[j + 0]), s_p), sv.x, __fmul_rn(r_s, va.x));
-                            o4.y = fmaf(__fmul_rn(i2f_small(r[j + 1]), s_p), sv.y, __fmul_rn(r_s, va.y));
-                            o4.z = fmaf(__fmul_rn(i2f_small(r[j + 2]), s_p), sv.z, __fmul_rn(r_s, va.z));
-                            o4.w = fmaf(__fmul_rn(i2f_small(r[j + 3]), s_p), sv.w, __fmul_rn(r_s, va.w));
-                            *reinterpret_cast<float4*>(orow + j) = o4;
+                            const float2 o01 = __ffma2_rn(__fmul2_rn(i2f_small2(r[j + 0], r[j + 1]), f2(s_p)), f2(sv.x, sv.y),
+                                                          __fmul2_rn(f2(r_s), f2(va.x, va.y)));
+                            const float2 o23 = __ffma2_rn(__fmul2_rn(i2f_small2(r[j + 2], r[j + 3]), f2(s_p)), f2(sv.z, sv.w),
+                                                          __fmul2_rn(f2(r_s), f2(va.z, va.w)));
+                            *reinterpret_cast<float4*>(orow + j) = make_float4(o01.x, o01.y, o23.x, o23.y);
                         }
                     }
                 }
@@ -753,18 +766,23 @@ qkr_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                             const float4 t4 = *reinterpret_cast<const float4*>(ct + 16 * c + j);
                             const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const float sl = fmaf(__fmul_rn(i2f_small(rS[j + k]), rs), cc[k], tt[k]);
-                                const float e = softmax_exp(sl - m);
-                                float pp = __fmul_rn(e, rinv);
-                                pp = fmaf(fmaf(-sum, pp, e), rinv, pp);
-                                pr[j + k] = pp;
-                                const float v = __fmul_rn(pp, inv_s);
-                                vq[j + k] = v;
-                                const float rr = rint_small(v);
-                                const float dv = fabsf(v - rr);
+                            for (int k = 0; k < 4; k += 2) {
+                                const float2 sl = __ffma2_rn(__fmul2_rn(i2f_small2(rS[j + k], rS[j + k + 1]), f2(rs)), f2(cc[k], cc[k + 1]),
+                                                             f2(tt[k], tt[k + 1]));
+                                const float2 tx = __fmul2_rn(__fadd2_rn(sl, f2(-m)), f2(1.4426950408889634f));
+                                float2 e;
+                                asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(e.x) : "f"(tx.x));
+                                asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(e.y) : "f"(tx.y));
+                                float2 pp = __fmul2_rn(e, f2(rinv));
+                                pp = __ffma2_rn(__ffma2_rn(f2(-sum), pp, e), f2(rinv), pp);
+                                pr[j + k] = pp.x; pr[j + k + 1] = pp.y;
+                                const float2 v = __fmul2_rn(pp, f2(inv_s));
+                                vq[j + k] = v.x; vq[j + k + 1] = v.y;
+                                const float2 rr = __fadd2_rn(__fadd2_rn(v, f2(MAGIC)), f2(-MAGIC));
+                                const float2 dv = __ffma2_rn(rr, f2(-1.f), v);
                                 // rounding boundary, or the clamp bound itself (it decides the straight-through mask)
-                                flag = fmaxf(flag, (dv > 0.4998f || (dv < 2e-4f && rr == p.qhi)) ? 1.f : 0.f);
+                                flag = fmaxf(flag, (fabsf(dv.x) > 0.4998f || (fabsf(dv.x) < 2e-4f && rr.x == p.qhi)) ? 1.f : 0.f);
+                                flag = fmaxf(flag, (fabsf(dv.y) > 0.4998f || (fabsf(dv.y) < 2e-4f && rr.y == p.qhi)) ? 1.f : 0.f);
                             }
                         }
                         if (flag != 0.f) {

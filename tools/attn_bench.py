@@ -51,3 +51,31 @@ for name, kw in (("codes + out only (eval)", {}), ("+ qp16", dict(fmt16=ops.FMT_
     print(f"fused   {t:8.1f} us  {name}")
 t = timeit(lambda: _unfused(ops, Fn, qx, qk, qv, B, N, H, C, se_x, se_k, ctS, scale, se_p, qhi, se_v, v_aft, ops.FMT_F16))
 print(f"unfused {t:8.1f} us  score GEMM + softmax_quant (P, codes, qp16) + codes_transpose + P.V GEMM")
+
+# ---- backward: fused kernel against dP GEMM + softmax_quant_bwd
+from ofq_b200.ops import FMT_F16  # noqa: E402
+sp2 = torch.stack((se_p, 1.0 / se_p)).contiguous()
+sv2 = torch.stack((se_v, 1.0 / se_v)).contiguous()
+g_p = 1.0 / ((qhi * B * H * N) ** 0.5)
+dO = torch.randn(B, N, C, device=dev) * 1e-3
+out, qp, P, qp16, _, rowstat = ops.qkr_attn_fwd(qx, qk, qvT, B, N, H, C, se_x, se_k, ctS, scale, se_p, qhi, se_v, v_aft, save_p=True,
+                                                fmt16=FMT_F16, want_rowstat=True)
+ldq, ldS = qp.shape[-1], P.shape[-1]
+(a16, rowdot, sc_in, qv16), _ = Fn._pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, None, qp16, None, skip_dp=True)
+se_k_hn = se_k.view(N, H).t().contiguous()
+t = timeit(lambda: ops.qkr_attn_bwd(qx, qk, a16, qv16, FMT_F16, B, N, H, C, se_x, se_k, ctS, scale, sp2, qhi, rowstat, rowdot, sc_in,
+                                    se_v, v_aft, 2, g_p))
+print(f"fused   {t:8.1f} us  backward: S recompute + dP + softmax / quantizer backward -> dS16, colsum, ds")
+
+
+def unfused_bwd():
+    amax = torch.zeros(1, device=dev)
+    dPq = torch.empty((B * H, N, ldS), dtype=torch.float32, device=dev)
+    ops.gemm(ops.GEMM_F16, a16, (C, 0, 64, N * C), qv16, (C, 0, 64, N * C), dPq, (ldS, N * ldS, H * N * ldS), N, N, 64, nb1=H, nb2=B,
+             rs=ops.vec(sp2[1], N), cs=ops.vec(sc_in[1:2], 1), rt=ops.vec(rowdot, 0, N, H * N), amax=amax)
+    sc = ops.scale_from_max(amax, v1=se_k_hn, v2=se_x, mult=2.0 * scale, product=True)
+    ops.softmax_quant_bwd(dPq, P, N, H, se_p, qhi, scale, g_p, se_k_hn, True, se_x, fmt=FMT_F16, scale4=sc, single=True)
+
+
+t = timeit(unfused_bwd)
+print(f"unfused {t:8.1f} us  backward: dP GEMM (fp32 out) + scale + softmax_quant_bwd on stored P")
