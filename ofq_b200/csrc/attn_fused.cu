@@ -20,6 +20,7 @@
 // accumulated in the same order as that kernel's per-lane partial sums + xor-shuffle tree, quotients and codes use the
 // same Markstein / guarded-reciprocal sequences. tests/test_gpu_attn_fused.py asserts torch.equal on every output.
 #include <cstdint>
+#include <cstdlib>
 #include <cmath>
 #include "ofq_b200.h"
 #include "ptx.cuh"
@@ -66,6 +67,7 @@ struct Params {
     float* P; long long ldS;            // optional out: probabilities [B*H, N, ldS]
     uint16_t* qp16; int f16;            // optional out: exact 16-bit copy of the codes, pitch ldq
     float* rowsum;                       // optional out: s_p[n] * sum_d Qp[n,d], [B*H, N]
+    int debug;                           // measurement only (OFQ_ATTN_DEBUG bits): knock out parts of the softmax warps' work
     float2* rowstat;                     // optional out: (row maximum of the scaled logits, sum of exp) [B*H, N]: lets the
                                          // backward recompute the probabilities bit for bit from the codes alone
 };
@@ -571,6 +573,414 @@ qkr_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }
 
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Forward, 16 softmax warps (the version the library dispatches). ncu of the 8-warp kernel above: 38 % issue-slot
+// utilisation, ~300 cycles of exposed latency per TMEM access (one 16-column load or store per ~100 instructions, two
+// warps per scheduler to cover it): the kernel is bound by TMEM round-trip latency, not by issue slots (halving the
+// instruction count with packed math did not move it). Here every 128-query tile is shared by TWO warpgroups, which take
+// the first / second 8 columns of every 16-column group (the two column sets are the lanes with bit 1 clear / set of the
+// vectorised softmax kernel, so its summation tree splits cleanly: each side produces two of the four partial sums c[0..3]
+// and only those, the row maximum and the code sums cross through shared memory). Four warps per scheduler, half the
+// TMEM accesses per warp.
+#ifdef OFQ_ATTN_TRACE
+#define ATR_T(t) const long long t = clock64()
+#define ATR_ADD(k, t) atr[k] += clock64() - t
+#else
+#define ATR_T(t)
+#define ATR_ADD(k, t)
+#endif
+constexpr int NTHREADS16 = 576;                 // warp 0 TMA, warp 1 MMA, warps 2..17 softmax
+constexpr uint32_t OFF_X16 = OFF_BAR + NBAR * 8 + 16;              // exchange area: [tile][half][128 rows] x {max, c_lo, c_hi, csum}
+constexpr size_t DYN_BYTES16 = OFF_X16 + 2 * 2 * BM * 4 * 4 + 1024;
+static_assert(DYN_BYTES16 <= 227 * 1024, "shared memory budget exceeded");
+
+__device__ __forceinline__ void ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    tmem_ld_wait();
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]) :: "memory");
+}
+__device__ __forceinline__ void st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
+                 "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+// exponentials of 8 columns = two lanes of the vectorised kernel (4 columns each), accumulated left to right
+__device__ __forceinline__ void exp8(uint32_t taddr, float m, float2& acc) {
+    uint32_t r[8];
+    ld8(taddr, r);
+    float e[8];
+    const float2 nm = f2(-m), l2e = f2(1.4426950408889634f);
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        const float2 t = __fmul2_rn(__fadd2_rn(f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), nm), l2e);
+        asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(e[j]) : "f"(t.x));
+        asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(e[j + 1]) : "f"(t.y));
+        r[j] = __float_as_uint(e[j]);
+        r[j + 1] = __float_as_uint(e[j + 1]);
+    }
+    acc.x += e[0]; acc.x += e[1]; acc.x += e[2]; acc.x += e[3];
+    acc.y += e[4]; acc.y += e[5]; acc.y += e[6]; acc.y += e[7];
+    st8(taddr, r);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+
+__global__ void __launch_bounds__(NTHREADS16, 1)
+qkr_attn_fwd16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmP, const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* k_full = bars + 0;  uint64_t* k_empty = bars + 1;
+    uint64_t* q_full = bars + 2;  uint64_t* q_empty = bars + 3;
+    uint64_t* v_full = bars + 4;  uint64_t* v_empty = bars + 5;
+    uint64_t* s_full = bars + 6;
+    uint64_t* s_free = bars + 8;
+    uint64_t* p_ready = bars + 10;
+    uint64_t* o_full = bars + 12;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nunits = ((int)blockIdx.x < p.units) ? (p.units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmP);
+        mbar_init(k_full, 1); mbar_init(k_empty, 1);
+        mbar_init(q_full, 1); mbar_init(q_empty, 1);
+        mbar_init(v_full, 1); mbar_init(v_empty, 1);
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(&s_full[g], 1); mbar_init(&s_free[g], 8);
+            mbar_init(&p_ready[g], 8); mbar_init(&o_full[g], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t kbytes = (uint32_t)p.kblocks;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int i = 0; i < nunits; ++i) {
+                const int u = blockIdx.x + i * gridDim.x, b = u / p.H, h = u - b * p.H;
+                mbar_wait(k_empty, (i & 1) ^ 1);
+                mbar_arrive_expect_tx(k_full, kbytes * K_BLOCK);
+                for (int kb = 0; kb < p.kblocks; ++kb)
+                    tma_load_5d(smem + OFF_K + kb * K_BLOCK, &tmK, k_full, kb * 128, 0, h, b, 0);
+                mbar_wait(q_empty, 1);
+                mbar_arrive_expect_tx(q_full, kbytes * Q_BLOCK);
+                for (int kb = 0; kb < p.kblocks; ++kb)
+                    tma_load_5d(smem + OFF_Q + kb * Q_BLOCK, &tmQ, q_full, kb * 128, 0, b, 0, 0);
+                mbar_wait(v_empty, (i & 1) ^ 1);
+                mbar_arrive_expect_tx(v_full, 2 * V_BLOCK);
+                for (int kb = 0; kb < 2; ++kb)
+                    tma_load_5d(smem + OFF_V + kb * V_BLOCK, &tmV, v_full, kb * 128, h * HD, b, 0, 0);
+                mbar_wait(q_empty, 0);
+                mbar_arrive_expect_tx(q_full, kbytes * Q_BLOCK);
+                for (int kb = 0; kb < p.kblocks; ++kb)
+                    tma_load_5d(smem + OFF_Q + kb * Q_BLOCK, &tmQ, q_full, kb * 128, BM, b, 0, 0);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t IDESC_S = umma_idesc(2u, 1u, BM, BN);
+            const uint32_t IDESC_O = umma_idesc(2u, 1u, BM, HD);
+            const uint32_t sK = smem_u32(smem + OFF_K), sQ = smem_u32(smem + OFF_Q), sV = smem_u32(smem + OFF_V);
+            auto scores = [&](int g) {
+                const uint32_t d = tmem_base + g * S_COL_STRIDE;
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    const uint64_t ad = umma_desc_kmajor_sw128(sQ + kb * Q_BLOCK);
+                    const uint64_t bd = umma_desc_kmajor_sw128(sK + kb * K_BLOCK);
+#pragma unroll
+                    for (uint32_t kk = 0; kk < 4; ++kk) umma_i8(d, ad + kk * 2, bd + kk * 2, IDESC_S, (kb | kk) != 0);
+                }
+            };
+            auto pv = [&](int g) {
+                const uint32_t d = tmem_base + g * S_COL_STRIDE;
+                const uint32_t sP = smem_u32(smem + OFF_P + g * 2 * P_BLOCK);
+#pragma unroll
+                for (uint32_t k = 0; k < 7; ++k) {
+                    const uint32_t kb = k >> 2, kk = k & 3;
+                    umma_i8(d, umma_desc_kmajor_sw128(sP + kb * P_BLOCK) + kk * 2, umma_desc_kmajor_sw128(sV + kb * V_BLOCK) + kk * 2,
+                            IDESC_O, k != 0);
+                }
+            };
+            for (int i = 0; i < nunits; ++i) {
+                mbar_wait(k_full, i & 1);
+                mbar_wait(q_full, 0);
+                mbar_wait(&s_free[0], (i & 1) ^ 1);
+                tc_fence_after();
+                scores(0);
+                tc_commit(q_empty);
+                tc_commit(&s_full[0]);
+                if (i > 0) {
+                    mbar_wait(&p_ready[1], (i - 1) & 1);
+                    tc_fence_after();
+                    pv(1);
+                    tc_commit(v_empty);
+                    tc_commit(&o_full[1]);
+                }
+                mbar_wait(q_full, 1);
+                mbar_wait(&s_free[1], (i & 1) ^ 1);
+                tc_fence_after();
+                scores(1);
+                tc_commit(q_empty);
+                tc_commit(k_empty);
+                tc_commit(&s_full[1]);
+                mbar_wait(v_full, i & 1);
+                mbar_wait(&p_ready[0], i & 1);
+                tc_fence_after();
+                pv(0);
+                tc_commit(&o_full[0]);
+            }
+            if (nunits > 0) {
+                mbar_wait(&p_ready[1], (nunits - 1) & 1);
+                tc_fence_after();
+                pv(1);
+                tc_commit(v_empty);
+                tc_commit(&o_full[1]);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------------------------------ softmax warps 2..17
+        const int cw = warp - 2;
+        const int g = cw >> 3;                       // query tile of every unit
+        const int hf = (cw >> 2) & 1;                // first / second 8 columns of every 16-column group
+        const int q = warp & 3;                      // TMEM lane quarter of this warp (hardware: warp id mod 4)
+        const int t = q * 32 + lane;                 // row inside the tile
+        const int pt = hf * BM + t;                  // thread index inside the tile's pair of warpgroups (0..255)
+        const int n = g * BM + t;
+        const bool row_ok = n < p.N;
+        const bool warp_ok = g * BM + q * 32 < p.N;
+        const uint32_t trow = tmem_base + g * S_COL_STRIDE + (static_cast<uint32_t>(q * 32) << 16) + 8 * hf;
+        uint8_t* pbase = smem + OFF_P + g * 2 * P_BLOCK;
+        uint8_t* prow = pbase + t * 128;
+        const int r7 = t & 7;
+        if (hf == 0) *reinterpret_cast<uint4*>(prow + P_BLOCK + ((5 ^ r7) << 4)) = make_uint4(0, 0, 0, 0);   // keys 208..223: zeros
+        fence_proxy_async_smem();
+        const float rs = row_ok ? __ldg(p.se_x + n) : 0.f;
+        const float s_p = row_ok ? __ldg(p.se_p + n) : 1.f;
+        const float inv_s = rcp_fast(s_p);
+        float* vecs = reinterpret_cast<float*>(smem + OFF_VEC) + g * 2 * VEC_FLOATS;
+        float* xch = reinterpret_cast<float*>(smem + OFF_X16) + g * (2 * BM * 4);      // [half][row][4]
+        float* xmine = xch + (hf * BM + t) * 4;
+        const float* xother = xch + ((hf ^ 1) * BM + t) * 4;
+        auto load_vecs = [&](int u, float (&v)[3]) {      // key pt (< 208): cs, ct; one of se_v / v_aft for pt < 128
+            const int b = u / p.H, h = u - b * p.H;
+            v[0] = 0.f; v[1] = -INFINITY; v[2] = 0.f;
+            if (pt < p.N) {
+                v[0] = __fmul_rn(__ldg(p.se_k + (long long)pt * p.H + h), p.scale);
+                v[1] = __fmul_rn(__ldg(p.ctS + ((long long)b * p.N + pt) * p.H + h), v[0]);
+            }
+            if (pt < 2 * HD) v[2] = pt < HD ? __ldg(p.se_v + h * HD + pt) : __ldg(p.v_aft + h * HD + (pt - HD));
+        };
+        float nv[3];
+        if (nunits > 0) load_vecs(blockIdx.x, nv);
+#ifdef OFQ_ATTN_TRACE
+        long long atr[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+        for (int i = 0; i < nunits; ++i) {
+            const int u = blockIdx.x + i * gridDim.x, b = u / p.H, h = u - b * p.H;
+            const long long z = u;
+            float* vb = vecs + (i & 1) * VEC_FLOATS;
+            if (pt == 0) tma_store_wait_read<0>();    // last unit's code stores have read the P operand (ordered by the barrier below)
+            if (pt < BN) { vb[pt] = nv[0]; vb[BN + pt] = nv[1]; }
+            if (pt < 2 * HD) vb[2 * BN + pt] = nv[2];
+            named_bar_sync(1 + g, 256);
+            if (i + 1 < nunits) load_vecs(u + gridDim.x, nv);
+            const float* cs = vb + 8 * hf;
+            const float* ct = vb + BN + 8 * hf;
+            const float* sev = vb + 2 * BN;
+            const float* vaft = sev + HD;
+
+            ATR_T(t0);
+            mbar_wait(&s_full[g], i & 1);
+            tc_fence_after();
+            ATR_ADD(0, t0);
+            ATR_T(t1);
+            float m = -INFINITY;
+            if (warp_ok && !(p.debug & 1)) {
+                // ---- pass 1: scaled logits of this side's 104 columns, maximum; logits -> TMEM
+#pragma unroll 1
+                for (int c = 0; c < BN / 16; ++c) {
+                    uint32_t r[8];
+                    ld8(trow + 16 * c, r);
+                    const float4 c0 = *reinterpret_cast<const float4*>(cs + 16 * c), c1 = *reinterpret_cast<const float4*>(cs + 16 * c + 4);
+                    const float4 t0 = *reinterpret_cast<const float4*>(ct + 16 * c), t1 = *reinterpret_cast<const float4*>(ct + 16 * c + 4);
+                    const float2 rs2 = f2(rs);
+                    const float2 s01 = __ffma2_rn(__fmul2_rn(i2f_small2(r[0], r[1]), rs2), f2(c0.x, c0.y), f2(t0.x, t0.y));
+                    const float2 s23 = __ffma2_rn(__fmul2_rn(i2f_small2(r[2], r[3]), rs2), f2(c0.z, c0.w), f2(t0.z, t0.w));
+                    const float2 s45 = __ffma2_rn(__fmul2_rn(i2f_small2(r[4], r[5]), rs2), f2(c1.x, c1.y), f2(t1.x, t1.y));
+                    const float2 s67 = __ffma2_rn(__fmul2_rn(i2f_small2(r[6], r[7]), rs2), f2(c1.z, c1.w), f2(t1.z, t1.w));
+                    m = fmaxf(m, fmaxf(fmaxf(fmaxf(s01.x, s01.y), fmaxf(s23.x, s23.y)), fmaxf(fmaxf(s45.x, s45.y), fmaxf(s67.x, s67.y))));
+                    r[0] = __float_as_uint(s01.x); r[1] = __float_as_uint(s01.y); r[2] = __float_as_uint(s23.x); r[3] = __float_as_uint(s23.y);
+                    r[4] = __float_as_uint(s45.x); r[5] = __float_as_uint(s45.y); r[6] = __float_as_uint(s67.x); r[7] = __float_as_uint(s67.y);
+                    st8(trow + 16 * c, r);
+                }
+                tmem_st_wait();
+            }
+            ATR_ADD(1, t1);
+            ATR_T(t2);
+            xmine[0] = m;
+            named_bar_sync(1 + g, 256);
+            m = fmaxf(m, xother[0]);
+            ATR_ADD(2, t2);
+            ATR_T(t3);
+            float2 cc = f2(0.f);
+            if (warp_ok && !(p.debug & 2)) {
+                // ---- pass 2: exponentials; this side owns the lanes 4k + 2 hf, 4k + 2 hf + 1 (k = 0..7) of the vectorised kernel:
+                //      lane sums P[k] (first half: columns 16 k + 8 hf .., second half: 128 + 16 k + 8 hf .. while < 208), then its
+                //      xor tree: offset 16 pairs k with k + 4, offset 8 k with k + 2, offset 4 k with k + 1 -> c[2 hf], c[2 hf + 1]
+                float2 P8[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    P8[k] = f2(0.f);
+                    exp8(trow + 16 * k, m, P8[k]);
+                    if (128 + 16 * k < BN) exp8(trow + 128 + 16 * k, m, P8[k]);
+                }
+                tmem_st_wait();
+                const float2 a0 = add2(P8[0], P8[4]), a1 = add2(P8[1], P8[5]), a2 = add2(P8[2], P8[6]), a3 = add2(P8[3], P8[7]);
+                cc = add2(add2(a0, a2), add2(a1, a3));
+            }
+            ATR_ADD(3, t3);
+            ATR_T(t4);
+            xmine[1] = cc.x; xmine[2] = cc.y;
+            named_bar_sync(1 + g, 256);
+            ATR_ADD(4, t4);
+            ATR_T(t5);
+            const float2 co = f2(xother[1], xother[2]);
+            const float2 clo = hf ? co : cc, chi = hf ? cc : co;            // (c[0], c[1]) and (c[2], c[3])
+            const float sum = (clo.x + chi.x) + (clo.y + chi.y);          // offsets 2, 1 of the tree
+            float rinv = rcp_fast(sum);
+            rinv = fmaf(rinv, fmaf(-sum, rinv, 1.0f), rinv);
+            uint32_t csum = 0u;
+            if (warp_ok && !(p.debug & 4)) {
+                // ---- pass 3: probabilities and codes of this side's columns
+                float* Prow = (row_ok && p.P) ? p.P + (z * p.N + n) * p.ldS : nullptr;
+                uint16_t* hrow = (row_ok && p.qp16) ? p.qp16 + (z * p.N + n) * p.ldq : nullptr;
+#pragma unroll 1
+                for (int c = 0; c < BN / 16; ++c) {
+                    uint32_t r[8];
+                    ld8(trow + 16 * c, r);
+                    float q8[8];
+                    float maxdv = 0.f;
+                    const float2 rinv2 = f2(rinv), nsum2 = f2(-sum), is2 = f2(inv_s), mg = f2(MAGIC), nmg = f2(-MAGIC), m1 = f2(-1.f);
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        const float2 e = f2(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+                        float2 pp = __fmul2_rn(e, rinv2);
+                        pp = __ffma2_rn(__ffma2_rn(nsum2, pp, e), rinv2, pp);
+                        r[j] = __float_as_uint(pp.x); r[j + 1] = __float_as_uint(pp.y);
+                        const float2 v = __fmul2_rn(pp, is2);
+                        const float2 rr = __fadd2_rn(__fadd2_rn(v, mg), nmg);
+                        const float2 dv = __ffma2_rn(rr, m1, v);
+                        maxdv = fmaxf(maxdv, fmaxf(fabsf(dv.x), fabsf(dv.y)));
+                        q8[j] = fminf(rr.x, p.qhi);
+                        q8[j + 1] = fminf(rr.y, p.qhi);
+                    }
+                    if (maxdv > 0.4998f) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float pp = __uint_as_float(r[j]);
+                            const float v = __fmul_rn(pp, inv_s);
+                            if (fabsf(v - rint_small(v)) > 0.4998f) q8[j] = fminf(rintf(__fdiv_rn(pp, s_p)), p.qhi);
+                        }
+                    }
+                    uint2 pk;
+                    pk.x = pack4_codes(q8[0], q8[1], q8[2], q8[3]);
+                    pk.y = pack4_codes(q8[4], q8[5], q8[6], q8[7]);
+                    csum = __dp4a(pk.x, 0x01010101u, csum);
+                    csum = __dp4a(pk.y, 0x01010101u, csum);
+                    const int col0 = 16 * c;
+                    const int kb = col0 >> 7, c16 = (col0 & 127) >> 4;
+                    *reinterpret_cast<uint2*>(prow + kb * P_BLOCK + ((c16 ^ r7) << 4) + 8 * hf) = pk;
+                    if (hrow) {
+                        uint4 h4;
+                        if (p.f16) { h4.x = pack_f16x2(q8[0], q8[1]); h4.y = pack_f16x2(q8[2], q8[3]); h4.z = pack_f16x2(q8[4], q8[5]); h4.w = pack_f16x2(q8[6], q8[7]); }
+                        else { h4.x = pack_bf16x2(q8[0], q8[1]); h4.y = pack_bf16x2(q8[2], q8[3]); h4.z = pack_bf16x2(q8[4], q8[5]); h4.w = pack_bf16x2(q8[6], q8[7]); }
+                        *reinterpret_cast<uint4*>(hrow + col0 + 8 * hf) = h4;
+                    }
+                    if (Prow) {
+                        const int d0 = col0 + 8 * hf;
+                        if (d0 < (int)p.ldS) *reinterpret_cast<float4*>(Prow + d0) = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+                        if (d0 + 4 < (int)p.ldS) *reinterpret_cast<float4*>(Prow + d0 + 4) = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+                    }
+                }
+            }
+            ATR_ADD(5, t5);
+            ATR_T(t6);
+            xmine[3] = __uint_as_float(csum);
+            // P operand (generic-proxy stores) -> visible to the async proxy (tensor core, TMA); all TMEM reads of S are done
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_ready[g]);
+            named_bar_sync(1 + g, 256);
+            if (pt == 0 && !(p.debug & 32)) {
+                tma_store_5d(&tmP, pbase, 0, g * BM, (int)z, 0, 0);
+                tma_store_5d(&tmP, pbase + P_BLOCK, 128, g * BM, (int)z, 0, 0);
+                tma_store_commit();
+            }
+            const float r_s = __fmul_rn(s_p, (float)(csum + __float_as_uint(xother[3])));
+            if (hf == 0 && row_ok) {
+                if (p.rowsum) p.rowsum[z * p.N + n] = r_s;
+                if (p.rowstat) p.rowstat[z * p.N + n] = make_float2(m, sum);
+            }
+
+            ATR_ADD(6, t6);
+            ATR_T(t7);
+            mbar_wait(&o_full[g], i & 1);
+            tc_fence_after();
+            ATR_ADD(7, t7);
+            ATR_T(t8);
+            if (warp_ok && !(p.debug & 8)) {
+                // ---- P V epilogue: this side takes 32 of the head's 64 channels
+                const uint32_t orow_t = tmem_base + g * S_COL_STRIDE + (static_cast<uint32_t>(q * 32) << 16) + 32 * hf;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[8];
+                    ld8(orow_t + 8 * c, r);
+                    if (row_ok) {
+                        const int j0 = 32 * hf + 8 * c;
+                        float* orow = p.out + ((long long)b * p.N + n) * p.C + h * HD + j0;
+#pragma unroll
+                        for (int j = 0; j < 8; j += 4) {
+                            const float4 sv = *reinterpret_cast<const float4*>(sev + j0 + j);
+                            const float4 va = *reinterpret_cast<const float4*>(vaft + j0 + j);
+                            const float2 o01 = __ffma2_rn(__fmul2_rn(i2f_small2(r[j + 0], r[j + 1]), f2(s_p)), f2(sv.x, sv.y),
+                                                          __fmul2_rn(f2(r_s), f2(va.x, va.y)));
+                            const float2 o23 = __ffma2_rn(__fmul2_rn(i2f_small2(r[j + 2], r[j + 3]), f2(s_p)), f2(sv.z, sv.w),
+                                                          __fmul2_rn(f2(r_s), f2(va.z, va.w)));
+                            *reinterpret_cast<float4*>(orow + j) = make_float4(o01.x, o01.y, o23.x, o23.y);
+                        }
+                    }
+                }
+            }
+            ATR_ADD(8, t8);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[g]);
+        }
+#ifdef OFQ_ATTN_TRACE
+        if (blockIdx.x == 0 && lane == 0 && (cw == 0 || cw == 4 || cw == 8))
+            printf("attn fwd16 warp %d (tile %d half %d): units %d | wait S %lld pass1 %lld bar %lld pass2 %lld bar %lld pass3 %lld fence+bar %lld wait O %lld epilogue %lld\n",
+                   warp, g, hf, nunits, atr[0], atr[1], atr[2], atr[3], atr[4], atr[5], atr[6], atr[7], atr[8]);
+#endif
+        if (pt == 0) tma_store_wait_all<0>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 // =====================================================================================================================
 // Backward of softmax + probability quantizer, fused with the two GEMMs that feed it (autograd of attention.py:210-216):
 //
@@ -591,8 +1001,8 @@ constexpr uint32_t B_OFF_A = B_OFF_Q + MAXKB * Q_BLOCK;            // A16 tile: 
 constexpr uint32_t B_OFF_V = B_OFF_A + Q_BLOCK;                    // v codes (16-bit): 208 keys x 64 channels
 constexpr uint32_t B_OFF_VEC = B_OFF_V + K_BLOCK;                  // [parity]{cs[208], ct[208], ca[208]}
 constexpr int B_VEC_FLOATS = 3 * BN;
-constexpr uint32_t B_OFF_RED = B_OFF_VEC + 2 * B_VEC_FLOATS * 4;   // [2 halves][2]{dot, dsp}[128 rows]
-constexpr uint32_t B_OFF_COL = B_OFF_RED + 2 * 2 * BM * 4;         // [4 lane quarters][208 keys] column sums of dS
+constexpr uint32_t B_OFF_RED = B_OFF_VEC + 2 * B_VEC_FLOATS * 4;   // [4 column parts][2]{dot, dsp}[128 rows]
+constexpr uint32_t B_OFF_COL = B_OFF_RED + 4 * 2 * BM * 4;         // [4 lane quarters][208 keys] column sums of dS
 constexpr uint32_t B_OFF_BAR = B_OFF_COL + 4 * BN * 4;
 constexpr int B_NBAR = 6;
 constexpr size_t B_DYN_BYTES = B_OFF_BAR + B_NBAR * 8 + 16 + 1024;
@@ -616,7 +1026,7 @@ template <bool F16>
 __device__ __forceinline__ uint32_t pack16(float lo, float hi) { return F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
 
 template <bool F16>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS16, 1)
 qkr_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmV, const BwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -632,7 +1042,7 @@ qkr_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmV);
         mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
         mbar_init(qa_full, 1); mbar_init(qa_empty, 1);
-        mbar_init(acc_full, 1); mbar_init(acc_free, 8);
+        mbar_init(acc_full, 1); mbar_init(acc_free, 16);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -692,21 +1102,22 @@ qkr_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 }
             }
         }
-    } else if (warp >= 4) {
-        const int g = (warp - 4) >> 2;               // key half: 0 -> chunks 0..7 (keys 0..127), 1 -> chunks 8..12 (keys 128..207)
+    } else {
+        // 16 compute warps on one tile: part = 0..3 takes the 8-key groups part, part + 4, part + 8, ... (26 groups of the 208 keys)
+        const int cw = warp - 2;
+        const int part = cw >> 2;
         const int q = warp & 3;
-        const int t = (threadIdx.x - 128) & 127;     // row inside the tile
-        const int c_lo = g ? 8 : 0, c_hi = g ? BN / 16 : 8;
+        const int t = q * 32 + lane;                 // row inside the tile
+        const int tid = threadIdx.x - 64;             // 0..511
         const uint32_t trS = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const uint32_t trD = trS + DP_COL;
         float* vecs = reinterpret_cast<float*>(smem + B_OFF_VEC);
-        float* red = reinterpret_cast<float*>(smem + B_OFF_RED);          // [half][{dot, dsp}][row]
+        float* red = reinterpret_cast<float*>(smem + B_OFF_RED);          // [part][{dot, dsp}][row]
         float* colpart = reinterpret_cast<float*>(smem + B_OFF_COL);      // [quarter][key]
-        const int tid = threadIdx.x - 128;            // 0..255
         const float inv_sc_in = __ldg(p.sc_in + 1);
         const float sc_out = __ldg(p.sc_out);
-        // column this lane ends up with after the halving reduction over the warp's 32 rows (bits 4..1 of the lane)
-        const int mycol = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        // key (inside an 8-key group) this lane ends up with after the halving reduction over the warp's 32 rows
+        const int mycol = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
         auto load_vecs = [&](int u, float (&v)[3]) {
             const int b = u / p.H, h = u - b * p.H;
             v[0] = 0.f; v[1] = -INFINITY; v[2] = 0.f;
@@ -719,13 +1130,13 @@ qkr_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         };
         float nv[3];
         if (nunits > 0) load_vecs(blockIdx.x, nv);
-        for (int k = tid; k < 4 * BN; k += 256) colpart[k] = 0.f;      // (ordered before its first use by the barrier below)
+        for (int k = tid; k < 4 * BN; k += 512) colpart[k] = 0.f;      // (ordered before its first use by the barrier below)
         for (int i = 0; i < nunits; ++i) {
             const int u = blockIdx.x + i * gridDim.x, b = u / p.H, h = u - b * p.H;
             const long long z = u;
             float* vb = vecs + (i & 1) * B_VEC_FLOATS;
             if (tid < BN) { vb[tid] = nv[0]; vb[BN + tid] = nv[1]; vb[2 * BN + tid] = nv[2]; }
-            named_bar_sync(1, 256);
+            named_bar_sync(1, 512);
             if (i + 1 < nunits) load_vecs(u + gridDim.x, nv);
             const float* cs = vb;
             const float* ct = vb + BN;
@@ -752,49 +1163,45 @@ qkr_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 if (warp_ok) {
                     // ---- pass 1: probabilities, codes, straight-through mask; P -> S columns, masked dP -> dP columns
 #pragma unroll 1
-                    for (int c = c_lo; c < c_hi; ++c) {
-                        uint32_t rS[16], rD[16];
-                        ld16_issue(trS + 16 * c, rS);
-                        ld16_issue(trD + 16 * c, rD);
-                        ld16_done(rS);
-                        ld16_done(rD);
-                        float pr[16], vq[16];
+                    for (int gi = part; gi < BN / 8; gi += 4) {
+                        const int d0 = 8 * gi;
+                        uint32_t rS[8], rD[8];
+                        ld8(trS + d0, rS);
+                        ld8(trD + d0, rD);
+                        float pr[8], vq[8];
                         float flag = 0.f;
+                        const float4 c0 = *reinterpret_cast<const float4*>(cs + d0), c1 = *reinterpret_cast<const float4*>(cs + d0 + 4);
+                        const float4 t0 = *reinterpret_cast<const float4*>(ct + d0), t1 = *reinterpret_cast<const float4*>(ct + d0 + 4);
+                        const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                        const float tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const float4 c4 = *reinterpret_cast<const float4*>(cs + 16 * c + j);
-                            const float4 t4 = *reinterpret_cast<const float4*>(ct + 16 * c + j);
-                            const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, tt[4] = {t4.x, t4.y, t4.z, t4.w};
-#pragma unroll
-                            for (int k = 0; k < 4; k += 2) {
-                                const float2 sl = __ffma2_rn(__fmul2_rn(i2f_small2(rS[j + k], rS[j + k + 1]), f2(rs)), f2(cc[k], cc[k + 1]),
-                                                             f2(tt[k], tt[k + 1]));
-                                const float2 tx = __fmul2_rn(__fadd2_rn(sl, f2(-m)), f2(1.4426950408889634f));
-                                float2 e;
-                                asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(e.x) : "f"(tx.x));
-                                asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(e.y) : "f"(tx.y));
-                                float2 pp = __fmul2_rn(e, f2(rinv));
-                                pp = __ffma2_rn(__ffma2_rn(f2(-sum), pp, e), f2(rinv), pp);
-                                pr[j + k] = pp.x; pr[j + k + 1] = pp.y;
-                                const float2 v = __fmul2_rn(pp, f2(inv_s));
-                                vq[j + k] = v.x; vq[j + k + 1] = v.y;
-                                const float2 rr = __fadd2_rn(__fadd2_rn(v, f2(MAGIC)), f2(-MAGIC));
-                                const float2 dv = __ffma2_rn(rr, f2(-1.f), v);
-                                // rounding boundary, or the clamp bound itself (it decides the straight-through mask)
-                                flag = fmaxf(flag, (fabsf(dv.x) > 0.4998f || (fabsf(dv.x) < 2e-4f && rr.x == p.qhi)) ? 1.f : 0.f);
-                                flag = fmaxf(flag, (fabsf(dv.y) > 0.4998f || (fabsf(dv.y) < 2e-4f && rr.y == p.qhi)) ? 1.f : 0.f);
-                            }
+                        for (int k = 0; k < 8; k += 2) {
+                            const float2 sl = __ffma2_rn(__fmul2_rn(i2f_small2(rS[k], rS[k + 1]), f2(rs)), f2(cc[k], cc[k + 1]), f2(tt[k], tt[k + 1]));
+                            const float2 tx = __fmul2_rn(__fadd2_rn(sl, f2(-m)), f2(1.4426950408889634f));
+                            float2 e;
+                            asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(e.x) : "f"(tx.x));
+                            asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(e.y) : "f"(tx.y));
+                            float2 pp = __fmul2_rn(e, f2(rinv));
+                            pp = __ffma2_rn(__ffma2_rn(f2(-sum), pp, e), f2(rinv), pp);
+                            pr[k] = pp.x; pr[k + 1] = pp.y;
+                            const float2 v = __fmul2_rn(pp, f2(inv_s));
+                            vq[k] = v.x; vq[k + 1] = v.y;
+                            const float2 rr = __fadd2_rn(__fadd2_rn(v, f2(MAGIC)), f2(-MAGIC));
+                            const float2 dv = __ffma2_rn(rr, f2(-1.f), v);
+                            // rounding boundary, or the clamp bound itself (it decides the straight-through mask)
+                            flag = fmaxf(flag, (fabsf(dv.x) > 0.4998f || (fabsf(dv.x) < 2e-4f && rr.x == p.qhi)) ? 1.f : 0.f);
+                            flag = fmaxf(flag, (fabsf(dv.y) > 0.4998f || (fabsf(dv.y) < 2e-4f && rr.y == p.qhi)) ? 1.f : 0.f);
                         }
                         if (flag != 0.f) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
+                            for (int j = 0; j < 8; ++j) {
                                 const float rr = rint_small(vq[j]);
                                 const float dv = fabsf(vq[j] - rr);
                                 if (dv > 0.4998f || (dv < 2e-4f && rr == p.qhi)) vq[j] = __fdiv_rn(pr[j], s_p);
                             }
                         }
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
+                        for (int j = 0; j < 8; ++j) {
                             const float v = vq[j];
                             const float qq = fminf(rint_small(v), p.qhi);
                             const bool inside = v <= p.qhi;                   // v >= 0 always holds for probabilities
@@ -805,71 +1212,59 @@ qkr_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                             rS[j] = __float_as_uint(pr[j]);
                             rD[j] = __float_as_uint(dp);
                         }
-                        st16(trS + 16 * c, rS);
-                        st16(trD + 16 * c, rD);
+                        st8(trS + d0, rS);
+                        st8(trD + d0, rD);
                     }
                     tmem_st_wait();
                 }
-                red[(g * 2 + 0) * BM + t] = dot;
-                red[(g * 2 + 1) * BM + t] = dsp;
-                named_bar_sync(2, 256);
-                dot = red[(0 * 2 + 0) * BM + t] + red[(1 * 2 + 0) * BM + t];
-                if (g == 0 && row_ok) p.ds_part[z * p.N + n] = red[(0 * 2 + 1) * BM + t] + red[(1 * 2 + 1) * BM + t];
+                red[(part * 2 + 0) * BM + t] = dot;
+                red[(part * 2 + 1) * BM + t] = dsp;
+                named_bar_sync(2, 512);
+                dot = (red[(0 * 2 + 0) * BM + t] + red[(1 * 2 + 0) * BM + t]) + (red[(2 * 2 + 0) * BM + t] + red[(3 * 2 + 0) * BM + t]);
+                if (part == 0 && row_ok)
+                    p.ds_part[z * p.N + n] = (red[(0 * 2 + 1) * BM + t] + red[(1 * 2 + 1) * BM + t]) + (red[(2 * 2 + 1) * BM + t] + red[(3 * 2 + 1) * BM + t]);
                 if (warp_ok) {
                     // ---- pass 2: dS = alpha P (dP - <P, dP>); scaled 16-bit copy -> HBM; column sums over the warp's rows
                     uint16_t* orow = p.dS16 + (z * p.N + n) * p.ldo;
 #pragma unroll 1
-                    for (int c = c_lo; c < c_hi; ++c) {
-                        uint32_t rS[16], rD[16];
-                        ld16_issue(trS + 16 * c, rS);
-                        ld16_issue(trD + 16 * c, rD);
-                        ld16_done(rS);
-                        ld16_done(rD);
-                        float ds[16];
-                        uint32_t pk[8];
+                    for (int gi = part; gi < BN / 8; gi += 4) {
+                        const int d0 = 8 * gi;
+                        uint32_t rS[8], rD[8];
+                        ld8(trS + d0, rS);
+                        ld8(trD + d0, rD);
+                        float ds[8];
+                        uint32_t pk[4];
+                        const float4 a0 = *reinterpret_cast<const float4*>(ca + d0), a1 = *reinterpret_cast<const float4*>(ca + d0 + 4);
+                        const float aa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const float4 a4 = *reinterpret_cast<const float4*>(ca + 16 * c + j);
-                            const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
-                            float va[4];
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const float raw = __uint_as_float(rS[j + k]) * (__uint_as_float(rD[j + k]) - dot);
-                                ds[j + k] = row_ok ? p.scale * raw : 0.f;
-                                va[k] = ds[j + k] * aa[k] * sca_row;
-                            }
-                            pk[j / 2] = pack16<F16>(va[0], va[1]);
-                            pk[j / 2 + 1] = pack16<F16>(va[2], va[3]);
+                        for (int k = 0; k < 8; k += 2) {
+                            const float r0 = __uint_as_float(rS[k]) * (__uint_as_float(rD[k]) - dot);
+                            const float r1 = __uint_as_float(rS[k + 1]) * (__uint_as_float(rD[k + 1]) - dot);
+                            ds[k] = row_ok ? p.scale * r0 : 0.f;
+                            ds[k + 1] = row_ok ? p.scale * r1 : 0.f;
+                            pk[k / 2] = pack16<F16>(ds[k] * aa[k] * sca_row, ds[k + 1] * aa[k + 1] * sca_row);
                         }
-                        if (row_ok) {
-                            const int d0 = 16 * c;
-                            if (d0 < p.ldo) *reinterpret_cast<uint4*>(orow + d0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                            if (d0 + 8 < p.ldo) *reinterpret_cast<uint4*>(orow + d0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                        }
-                        // sum of each of the 16 columns over the warp's 32 rows: recursive halving (16 shuffles instead of 80)
-                        float w8[8], w4[4], w2[2], w1;
-                        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const float send = h16 ? ds[k] : ds[k + 8], keep = h16 ? ds[k + 8] : ds[k];
-                            w8[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                        }
+                        if (row_ok && d0 < p.ldo) *reinterpret_cast<uint4*>(orow + d0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        // sum of each of the 8 keys over the warp's 32 rows: recursive halving (9 shuffles instead of 40)
+                        float w4[4], w2[2], w1;
+                        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const float send = h8 ? w8[k] : w8[k + 4], keep = h8 ? w8[k + 4] : w8[k];
-                            w4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                            const float send = h16 ? ds[k] : ds[k + 4], keep = h16 ? ds[k + 4] : ds[k];
+                            w4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
                         }
 #pragma unroll
                         for (int k = 0; k < 2; ++k) {
-                            const float send = h4 ? w4[k] : w4[k + 2], keep = h4 ? w4[k + 2] : w4[k];
-                            w2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                            const float send = h8 ? w4[k] : w4[k + 2], keep = h8 ? w4[k + 2] : w4[k];
+                            w2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
                         }
                         {
-                            const float send = h2 ? w2[0] : w2[1], keep = h2 ? w2[1] : w2[0];
-                            w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                            const float send = h4 ? w2[0] : w2[1], keep = h4 ? w2[1] : w2[0];
+                            w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
                         }
+                        w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
                         w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
-                        if ((lane & 1) == 0) colpart[q * BN + 16 * c + mycol] += w1;     // one lane per (quarter, key): no race
+                        if ((lane & 3) == 0) colpart[q * BN + d0 + mycol] += w1;      // one lane per (quarter, key): no race
                     }
                 }
                 tc_fence_before();
@@ -877,7 +1272,7 @@ qkr_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 if (lane == 0) mbar_arrive(acc_free);
             }
             // column sums of the unit: the four lane quarters in a fixed order (quarters without rows in tile 1 added nothing)
-            named_bar_sync(3, 256);
+            named_bar_sync(3, 512);
             if (tid < p.N) {
                 float a = colpart[tid];
                 colpart[tid] = 0.f;                          // each reader clears exactly what it read, for the next unit
@@ -1005,6 +1400,8 @@ extern "C" int ofq_qkr_attn_fwd(const int8_t* qx, const int8_t* qk, const int8_t
     p.B = B; p.N = N; p.H = H; p.C = C; p.kblocks = (C + 127) / 128; p.units = B * H;
     p.se_x = se_x; p.se_k = se_k; p.ctS = ctS; p.scale = scale; p.se_p = se_p; p.qhi = (float)qhi;
     p.se_v = se_v; p.v_aft = v_aft; p.qp = qp; p.ldq = ldq; p.out = out; p.P = P; p.ldS = P ? ldS : 0;
+    static const int dbg = [] { const char* e = getenv("OFQ_ATTN_DEBUG"); return e ? atoi(e) : 0; }();
+    p.debug = dbg;
     p.qp16 = (uint16_t*)qp16; p.f16 = fmt16 == OFQ_FMT_F16; p.rowsum = rowsum; p.rowstat = reinterpret_cast<float2*>(rowstat);
     static bool configured = false;
     if (!configured) {
@@ -1012,7 +1409,18 @@ extern "C" int ofq_qkr_attn_fwd(const int8_t* qx, const int8_t* qk, const int8_t
         configured = true;
     }
     const int grid = p.units < ofq_num_sms() ? p.units : ofq_num_sms();
-    attn::qkr_attn_fwd_kernel<<<grid, attn::NTHREADS, attn::DYN_BYTES, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmP, p);
+    // 16 softmax warps by default; OFQ_ATTN_WARPS=8 keeps the first (8-warp) kernel for A/B measurements
+    static const int warps = [] { const char* e = getenv("OFQ_ATTN_WARPS"); return e ? atoi(e) : 16; }();
+    if (warps == 8) {
+        attn::qkr_attn_fwd_kernel<<<grid, attn::NTHREADS, attn::DYN_BYTES, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmP, p);
+    } else {
+        static bool configured16 = false;
+        if (!configured16) {
+            OFQ_CUDA(cudaFuncSetAttribute(attn::qkr_attn_fwd16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn::DYN_BYTES16));
+            configured16 = true;
+        }
+        attn::qkr_attn_fwd16_kernel<<<grid, attn::NTHREADS16, attn::DYN_BYTES16, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmP, p);
+    }
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1076,8 +1484,8 @@ extern "C" int ofq_qkr_attn_bwd(const int8_t* qx, const int8_t* qk, const void* 
         configured = true;
     }
     const int grid = p.units < ofq_num_sms() ? p.units : ofq_num_sms();
-    if (f16) attn::qkr_attn_bwd_kernel<true><<<grid, attn::NTHREADS, attn::B_DYN_BYTES, st>>>(tmQ, tmK, tmA, tmV, p);
-    else attn::qkr_attn_bwd_kernel<false><<<grid, attn::NTHREADS, attn::B_DYN_BYTES, st>>>(tmQ, tmK, tmA, tmV, p);
+    if (f16) attn::qkr_attn_bwd_kernel<true><<<grid, attn::NTHREADS16, attn::B_DYN_BYTES, st>>>(tmQ, tmK, tmA, tmV, p);
+    else attn::qkr_attn_bwd_kernel<false><<<grid, attn::NTHREADS16, attn::B_DYN_BYTES, st>>>(tmQ, tmK, tmA, tmV, p);
     attn::attn_ds_reduce_kernel<<<(N + 31) / 32, 256, 0, st>>>(ds_part, B * H, N, g_s, d_s);
     OFQ_CUDA(cudaGetLastError());
     return 0;
