@@ -57,9 +57,11 @@ def parse():
                     help="fused: the repo's host model (ofq_b200 LayerNorm kernels, residual add folded into the next norm). "
                          "plain: a timm-style host with torch LayerNorm and un-fused residuals (ofq_b200/host/plain.py), i.e. "
                          "the quantized modules dropped into somebody else's model, as into the reference's")
-    ap.add_argument("--ddp", default="bucketed", choices=["flat", "bucketed"],
-                    help="gradient exchange for N > 1: one flat all-reduce after backward, or ~25 MB buckets reduced on a "
-                         "communication stream while the backward is still running (torch DDP semantics, train.py:727)")
+    ap.add_argument("--ddp", default="flat", choices=["flat", "bucketed"],
+                    help="gradient exchange for N > 1: one flat all-reduce after backward (default: measured faster on B200, "
+                         "20.87 against 21.28 ms per step at N = 2 - the persistent one-CTA-per-SM GEMMs leave the NCCL kernels "
+                         "of an overlapped exchange no SM to run on, the two only take SMs from each other), or ~25 MB buckets "
+                         "reduced on a communication stream while the backward is still running (torch DDP semantics, train.py:727)")
     return ap.parse_args()
 
 

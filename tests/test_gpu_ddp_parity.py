@@ -1,11 +1,13 @@
 """N-GPU data-parallel gradients == 1-GPU gradients of the concatenated batch, on a real multi-GPU box:
-depth-12 DeiT-T W2A2 QKR, global batch 8 split over 2 ranks, NCCL, ofq_b200.ddp (flat and bucketed / overlapped exchange).
+DeiT-T width (192, 3 heads) W2A2 QKR, two blocks (low-bit QAT is chaotic in the last bit - see test_gpu_fullsize_parity.py -
+and the two runs quantize with step sizes whose last bit depends on the local batch size, lsq.py:6-9), global batch 8 split
+over 2 ranks, NCCL, ofq_b200.ddp (flat and bucketed / overlapped exchange).
 Skipped on a single-GPU box (the driver's round-end `-m gpu` run); run with `gpurun --gpus 2`, result recorded in profiles/.
 
 Every gradient must agree to the fp16-operand tolerance of the backward (1e-3). The LSQ step-size gradients carry the
 reference's own batch dependence: their gradient scale is 1/sqrt(thd_pos * elements-per-scale) of the LOCAL batch
-(lsq.py:582-591), so a rank with B/W images produces sqrt(W) times the 1-GPU value before the mean over ranks (torch DDP
-around the reference behaves identically); the test accounts for exactly that factor."""
+(lsq.py:582-591): 1/sqrt(B/W) instead of 1/sqrt(B), so the reduced step-size gradient is sqrt(W) times the 1-GPU value (torch
+DDP around the reference behaves identically); the test accounts for exactly that factor."""
 import os
 import socket
 
@@ -17,7 +19,22 @@ import fullsize_common as FC
 from conftest import load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
-CFG = "deit_tiny_qkr_w2a2"
+DEPTH = 2
+
+
+def _model():
+    import ofq_b200.quantization as Q
+    from ofq_b200.host.deit import DistilledVisionTransformer
+    model = DistilledVisionTransformer(num_classes=1000, embed_dim=192, depth=DEPTH, num_heads=3)
+    model = Q.replace_module_by_qmodule_deit(model, Q.make_qconfigs(FC.deit_names(DEPTH), 2, 2), pretrained_initialized=True,
+                                             qk_reparam=True)
+    values, _ = FC.fill_state(model.state_dict())
+    FC.apply_state(model, values)
+    model = model.cuda()
+    model.eval()
+    with torch.no_grad():
+        model(FC.det_images().cuda())             # setup_alpha on the full batch: identical step sizes everywhere
+    return model.train()
 
 
 def _free_port():
@@ -41,8 +58,7 @@ def _worker(rank, world, port, mode, out):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from ofq_b200 import ddp as D
-    g = load_golden(f"full_{CFG}")
-    model = FC.load_repo_model(CFG, g).cuda().train()
+    model = _model()
     D.broadcast_parameters(model, 0)
     per = FC.BATCH // world
     img = FC.det_images()[rank * per:(rank + 1) * per].cuda()
@@ -66,19 +82,21 @@ def test_two_gpu_gradients_match_single_gpu(mode):
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), mode, out), nprocs=world, join=True)
-    g = load_golden(f"full_{CFG}")
-    model = FC.load_repo_model(CFG, g).cuda().train()
+    model = _model()
     ref = _grads(model, FC.det_images().cuda(), FC.det_labels(FC.BATCH, 1000).cuda())
     gmax = max(v.abs().max().item() for v in ref.values())
     worst = 0.0
+    bad = []
     for n, r in ref.items():
         for rank in range(world):
             mine = out[rank][n]
             if n.endswith(".s") and "lsqw_fn" not in n:          # activation step sizes: local-batch gradient scale
-                mine = mine * (world ** 0.5)
+                mine = mine / (world ** 0.5)
             e = rel_err(mine, r)
             ok = e < 2e-3 or (mine - r).abs().max().item() <= 2e-5 * gmax
-            assert ok, f"{n} rank {rank}: {e:.2e}"
+            if not ok:
+                bad.append((n, rank, e))
             worst = max(worst, e if (mine - r).abs().max().item() > 2e-5 * gmax else 0.0)
         assert torch.equal(out[0][n], out[1][n]), n          # both ranks hold the same reduced gradient
-    print(f"2-GPU vs 1-GPU gradient parity ({mode}): worst rel err {worst:.2e}")
+    print(f"2-GPU vs 1-GPU gradient parity ({mode}): worst rel err {worst:.2e}; outside tolerance: {bad[:6]}")
+    assert not bad, bad[:10]
