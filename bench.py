@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=8, help="images per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sites", default="", help="write a per-call-site kernel timing table of the instrumented steps here")
+    ap.add_argument("--grad-buffer", default="flat", choices=["flat", "none"],
+                    help="flat: gradients live in one flat fp32 buffer (ofq_b200.ddp.FlatGradAllReduce, also at N = 1)")
     ap.add_argument("--mode", default="qat", choices=["qat", "cga", "eval"],
                     help="qat: the headline QAT step. cga: BASELINE.json config 5, the CGA fine-tune step (qk_reparam_type=1, "
                          "freeze mask fused into AdamW for every StatsQ weight, boundaryRange 0.005, lr 1e-5). eval: no-grad "
@@ -270,9 +272,11 @@ def main():
     else:
         opt = CGAAdamW(param_groups_weight_decay(model, 0.05, getattr(model, 'no_weight_decay', lambda: set())()), lr=5.47e-4)
     # data-parallel gradient exchange (ofq_b200/ddp.py): ONE NCCL all-reduce (mean) of a flat fp32 gradient buffer
+    # (also at N = 1: the flat buffer is the gradient arena - the dW GEMMs accumulate straight into their slices after ONE
+    # memset, instead of one zero fill per weight; `--grad-buffer none` keeps per-parameter gradient tensors)
     ddp = None
-    if world > 1:
-        ddp = BucketedGradAllReduce(model, world) if a.ddp == "bucketed" else FlatGradAllReduce(model.parameters(), world)
+    if a.mode != "eval" and (world > 1 or a.grad_buffer == "flat"):
+        ddp = BucketedGradAllReduce(model, world) if (a.ddp == "bucketed" and world > 1) else FlatGradAllReduce(model.parameters(), world)
     flat = ddp.flat if ddp is not None else None
 
     def step(img, lbl):
@@ -471,7 +475,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": B * world, "parallelism": f"dp{world}",
                    "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush",
-                   "optimizer": {"qat": "fused AdamW lr 5.47e-4 wd 0.05", "cga": "fused CGA-masked AdamW lr 1e-5 wd 0.05 BR 0.005", "eval": "none"}[a.mode], "cuda_graph": a.graph == "on", "host_model": a.host_model, "ddp": (a.ddp if world > 1 else None), "host_enqueue_ms_per_step": host_enqueue_ms, "bwd_mode": bwd_mode,
+                   "optimizer": {"qat": "fused AdamW lr 5.47e-4 wd 0.05", "cga": "fused CGA-masked AdamW lr 1e-5 wd 0.05 BR 0.005", "eval": "none"}[a.mode], "cuda_graph": a.graph == "on", "host_model": a.host_model, "ddp": (a.ddp if world > 1 else None), "grad_buffer": a.grad_buffer, "host_enqueue_ms_per_step": host_enqueue_ms, "bwd_mode": bwd_mode,
                    "quantized_gemm_tflops_per_gpu": flops_step / (ms_total / a.steps * 1e-3) / 1e12},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": (h_img.numel() * 4 + h_lbl.numel() * 8) * world,
                 "d2h_bytes_per_step": 4 * world, "last_loss": last},

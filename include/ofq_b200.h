@@ -366,10 +366,19 @@ OFQ_API int ofq_cga_adamw(float* p, const float* grad, float* exp_avg, float* ex
 OFQ_API int ofq_counter_increment(int* counter, void* stream);
 /* Multi-tensor plain AdamW (all un-masked parameters of one learning-rate group in ONE launch).
  * table: device array of n_entries 48-byte records
- *   { float* p; const float* g; float* m; float* v; int64 numel; float decay (= 1 - lr*wd); int32 first_block; }
+ *   { float* p; const float* g; float* m; float* v; int64 numel; float wd (weight decay; 1 - lr*wd is formed in the kernel); int32 first_block; }
  * where first_block is the running sum of ceil(numel / 1024) and total_blocks the final sum. */
 OFQ_API int ofq_adamw_multi(const void* table, int n_entries, int total_blocks, int step, double lr, double beta1,
                             double beta2, double eps, const int* step_dev, void* stream);
+/* Multi-tensor CGA-masked AdamW: every freeze-masked weight in THREE launches (scratch init, per-row StatsQ statistics and
+ * rounding-level range, masked update) instead of three per weight. table: device array of n_entries 72-byte records
+ *   { float* p; const float* g; float* m; float* v; float* rowstat (scratch [rows]); int32* kminmax (scratch [2]);
+ *     int32 rows, cols; float wd; int32 first_block; int32 first_rowblock; int32 pad }
+ * first_block = running sum of ceil(rows*cols / 1024) (total_blocks the final sum), first_rowblock = running sum of
+ * ceil(rows / 8) (total_rowblocks the final sum). Same arithmetic per element as ofq_cga_adamw. */
+OFQ_API int ofq_cga_adamw_multi(const void* table, int n_entries, int total_blocks, int total_rowblocks, int step, double lr,
+                                double beta1, double beta2, double eps, int bits, double boundary_range, const int* step_dev,
+                                void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Host glue around the quantized layers: fp32 LayerNorm (nn.LayerNorm semantics: biased

@@ -91,7 +91,7 @@ class CGAAdamW(torch.optim.Optimizer):
         self._host_step = getattr(self, "_host_step", 0) + 1
         for gi, group in enumerate(self.param_groups):
             b1, b2 = group["betas"]
-            plain = []
+            plain, masked_list = [], []
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -104,12 +104,17 @@ class CGAAdamW(torch.optim.Optimizer):
                     st["step"] = int(st["step"].item())          # a torch.optim.AdamW checkpoint keeps the step as a tensor
                 st["step"] += 1
                 masked = id(p) in self._masked
-                if not masked and p.is_contiguous() and p.grad.is_contiguous():
-                    plain.append(p)
-                    continue
                 if masked and "scratch" not in st:
                     st["scratch"] = (torch.empty(p.shape[0], dtype=torch.float32, device=p.device),
                                      torch.empty(2, dtype=torch.int32, device=p.device))
+                dense = p.is_contiguous() and p.grad.is_contiguous()
+                if dense and not masked:
+                    plain.append(p)
+                    continue
+                if dense and not self.keep_masks:
+                    masked_list.append(p)
+                    continue
+                # odd layouts and the mask-recording debug mode: one parameter at a time
                 mask_out = None
                 if masked and self.keep_masks:
                     mask_out = torch.empty(p.shape, dtype=torch.uint8, device=p.device)
@@ -120,18 +125,31 @@ class CGAAdamW(torch.optim.Optimizer):
                                boundary_range=self.boundary_range, scratch=st.get("scratch"), mask_out=mask_out,
                                step_dev=self._step_dev)
                 self.launches += 3 if masked else 1
+            # Multi-tensor launches. The pointer tables are rebuilt only when a buffer moved (never under CUDA-graph
+            # replay or with persistent .grad buffers); lr is a launch argument and weight decay a table field the kernel
+            # turns into 1 - lr * wd, so a learning-rate schedule does not touch the tables.
             if plain:
-                # every un-masked parameter of the group in ONE launch; the pointer table is rebuilt only when a
-                # gradient buffer moved (it never does under CUDA-graph replay or with persistent .grad buffers)
-                key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in plain) + (group["lr"], group["weight_decay"])
-                cache = self._tables.get(gi)
+                key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in plain) + (group["weight_decay"],)
+                cache = self._tables.get((gi, "plain"))
                 if cache is None or cache[0] != key:
-                    decay = 1.0 - group["lr"] * group["weight_decay"]
-                    entries = [(p.data, p.grad, self.state[p]["exp_avg"], self.state[p]["exp_avg_sq"], decay) for p in plain]
+                    entries = [(p.data, p.grad, self.state[p]["exp_avg"], self.state[p]["exp_avg_sq"], group["weight_decay"])
+                               for p in plain]
                     cache = (key,) + ops.build_adamw_table(entries, plain[0].device)
-                    self._tables[gi] = cache
+                    self._tables[(gi, "plain")] = cache
                 _, table, n, blocks, numel = cache
                 ops.adamw_multi_(table, n, blocks, numel, self._host_step, group["lr"], b1, b2, group["eps"],
                                  step_dev=self._step_dev)
                 self.launches += 1
+            if masked_list:
+                key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in masked_list) + (group["weight_decay"],)
+                cache = self._tables.get((gi, "masked"))
+                if cache is None or cache[0] != key:
+                    entries = [(p.data, p.grad, self.state[p]["exp_avg"], self.state[p]["exp_avg_sq"]) + self.state[p]["scratch"]
+                               + (group["weight_decay"],) for p in masked_list]
+                    cache = (key,) + ops.build_cga_table(entries, masked_list[0].device)
+                    self._tables[(gi, "masked")] = cache
+                _, table, n, blocks, rowblocks, numel = cache
+                ops.cga_adamw_multi_(table, n, blocks, rowblocks, numel, self._host_step, group["lr"], b1, b2, group["eps"],
+                                     self.wq_bitw, self.boundary_range, step_dev=self._step_dev)
+                self.launches += 3
         return loss

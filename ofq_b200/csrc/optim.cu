@@ -163,9 +163,40 @@ struct AdamWEntry {
     float* m;
     float* v;
     long long numel;
-    float decay;       // 1 - lr * wd of this parameter's group
+    float wd;          // weight decay of this parameter's group (the decay factor 1 - lr * wd is formed in the kernel: the
+                       // table does not change with the learning-rate schedule)
     int first_block;   // first CTA that works on this entry
 };
+
+// Multi-tensor CGA: every freeze-masked weight of the model in ONE pre-pass launch and ONE update launch.
+struct CgaEntry {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    float* rowstat;    // [rows] scratch: per-row StatsQ scale
+    int* kminmax;      // [2] scratch: global min / max rounding level of this weight
+    int rows, cols;
+    float wd;
+    int first_block;   // update kernel: running sum of ceil(rows * cols / 1024)
+    int first_rowblock;// pre-pass kernel: running sum of ceil(rows / 8)
+    int pad;
+};
+
+template <typename E>
+__device__ __forceinline__ int find_entry(const E* table, int n_entries, int block, int E::*first) {
+    int lo = 0, hi = n_entries - 1;                 // last entry whose first block <= block
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (table[mid].*first <= block) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void cga_init_multi_kernel(const CgaEntry* __restrict__ table, int n_entries) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_entries) { table[i].kminmax[0] = INT_MAX; table[i].kminmax[1] = INT_MIN; }
+}
 
 __global__ void __launch_bounds__(256)
 adamw_multi_kernel(const AdamWEntry* __restrict__ table, int n_entries, AdamScalars a, const int* __restrict__ step_dev) {
@@ -191,7 +222,7 @@ adamw_multi_kernel(const AdamWEntry* __restrict__ table, int n_entries, AdamScal
     a.step_size = bc[0];
     a.bc2_sqrt = bc[1];
     const AdamWEntry e = table[entry_s];
-    a.decay = e.decay;
+    a.decay = (float)(1.0 - a.lr * (double)e.wd);
     const long long base = ((long long)(blockIdx.x - e.first_block) * blockDim.x + threadIdx.x) * 4;
     if (base >= e.numel) return;
     if (base + 4 <= e.numel && (((uintptr_t)e.p | (uintptr_t)e.g | (uintptr_t)e.m | (uintptr_t)e.v) & 15) == 0) {
@@ -209,6 +240,86 @@ adamw_multi_kernel(const AdamWEntry* __restrict__ table, int n_entries, AdamScal
         for (long long i = base; i < e.numel && i < base + 4; ++i) {
             float pv = e.p[i], mv = e.m[i], vv = e.v[i];
             adamw_elem(pv, e.g[i], mv, vv, a, false);
+            e.p[i] = pv; e.m[i] = mv; e.v[i] = vv;
+        }
+    }
+}
+
+// pre-pass of all masked weights: block = 8 rows of one entry (cga_rowstat_kernel's work per row)
+__global__ void __launch_bounds__(256)
+cga_rowstat_multi_kernel(const CgaEntry* __restrict__ table, int n_entries, float n_levels) {
+    __shared__ int entry_s;
+    if (threadIdx.x == 0) entry_s = find_entry(table, n_entries, (int)blockIdx.x, &CgaEntry::first_rowblock);
+    __syncthreads();
+    const CgaEntry e = table[entry_s];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = ((int)blockIdx.x - e.first_rowblock) * 8 + warp;
+    if (row >= e.rows) return;
+    const float* wr = e.p + (long long)row * e.cols;
+    double acc = 0.0;
+    for (int c = lane; c < e.cols; c += 32) acc += (double)fabsf(__ldg(wr + c));
+    acc = warp_sum_d(acc);
+    const float sf = __fmul_rn(2.0f, __fdiv_rn((float)acc, (float)e.cols));
+    int kmin = INT_MAX, kmax = INT_MIN;
+    for (int c = lane; c < e.cols; c += 32) {
+        const int k = (int)rintf(statsq_b4(__ldg(wr + c), sf, n_levels));
+        kmin = min(kmin, k);
+        kmax = max(kmax, k);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if (lane == 0) {
+        e.rowstat[row] = sf;
+        atomicMin(e.kminmax, kmin);
+        atomicMax(e.kminmax + 1, kmax);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+cga_adamw_multi_kernel(const CgaEntry* __restrict__ table, int n_entries, float n_levels, float lo_thr, float hi_thr,
+                       AdamScalars a, const int* __restrict__ step_dev) {
+    __shared__ float bc[2];
+    __shared__ int entry_s;
+    if (threadIdx.x == 0) {
+        if (step_dev) {
+            const double t = (double)(*step_dev);
+            bc[0] = (float)(a.lr / (1.0 - pow(a.beta1_d, t)));
+            bc[1] = (float)sqrt(1.0 - pow(a.beta2_d, t));
+        } else {
+            bc[0] = a.step_size;
+            bc[1] = a.bc2_sqrt;
+        }
+        entry_s = find_entry(table, n_entries, (int)blockIdx.x, &CgaEntry::first_block);
+    }
+    __syncthreads();
+    a.step_size = bc[0];
+    a.bc2_sqrt = bc[1];
+    const CgaEntry e = table[entry_s];
+    a.decay = (float)(1.0 - a.lr * (double)e.wd);
+    const long long numel = (long long)e.rows * e.cols;
+    const long long base = ((long long)((int)blockIdx.x - e.first_block) * blockDim.x + threadIdx.x) * 4;
+    if (base >= numel) return;
+    const int kmin = e.kminmax[0], kmax = e.kminmax[1];
+    if (base + 4 <= numel && e.cols % 4 == 0) {
+        float4 pp = *reinterpret_cast<float4*>(e.p + base);
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(e.g + base));
+        float4 mm = *reinterpret_cast<float4*>(e.m + base);
+        float4 vv = *reinterpret_cast<float4*>(e.v + base);
+        float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+        const float sf = __ldg(e.rowstat + base / e.cols);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            adamw_elem(pa[k], ga[k], ma[k], va[k], a, cga_frozen(pa[k], sf, n_levels, kmin, kmax, lo_thr, hi_thr));
+        *reinterpret_cast<float4*>(e.p + base) = pp;
+        *reinterpret_cast<float4*>(e.m + base) = mm;
+        *reinterpret_cast<float4*>(e.v + base) = vv;
+    } else {
+        for (long long i = base; i < numel && i < base + 4; ++i) {
+            float pv = e.p[i], mv = e.m[i], vv = e.v[i];
+            adamw_elem(pv, e.g[i], mv, vv, a, cga_frozen(pv, __ldg(e.rowstat + i / e.cols), n_levels, kmin, kmax, lo_thr, hi_thr));
             e.p[i] = pv; e.m[i] = mv; e.v[i] = vv;
         }
     }
@@ -301,6 +412,39 @@ extern "C" int ofq_adamw_multi(const void* table, int n_entries, int total_block
     a.eps = (float)eps;
     a.lr = lr; a.beta1_d = beta1; a.beta2_d = beta2;
     adamw_multi_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>((const AdamWEntry*)table, n_entries, a, step_dev);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// table: device array of n_entries 72-byte CgaEntry records
+//   { float* p; const float* g; float* m; float* v; float* rowstat; int32* kminmax; int32 rows, cols; float wd;
+//     int32 first_block (running sum of ceil(rows*cols / 1024)); int32 first_rowblock (running sum of ceil(rows / 8)); int32 pad }
+// Three launches for ALL freeze-masked weights of a model (scratch init, per-row statistics + level range, masked update)
+// instead of three per weight.
+extern "C" int ofq_cga_adamw_multi(const void* table, int n_entries, int total_blocks, int total_rowblocks, int step, double lr,
+                                   double beta1, double beta2, double eps, int bits, double boundary_range, const int* step_dev,
+                                   void* stream) {
+    OFQ_REQUIRE(table && n_entries > 0 && total_blocks > 0 && total_rowblocks > 0 && (step >= 1 || step_dev) && bits >= 2 && bits <= 7,
+                "ofq_cga_adamw_multi: bad argument");
+    static_assert(sizeof(CgaEntry) == 72, "CgaEntry layout is part of the C-ABI");
+    OFQ_CHECK_ARCH();
+    if (step < 1) step = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    AdamScalars a;
+    a.decay = 1.f;
+    a.one_m_b1 = (float)(1.0 - beta1);
+    a.beta2 = (float)beta2;
+    a.one_m_b2 = (float)(1.0 - beta2);
+    a.step_size = (float)(lr / (1.0 - std::pow(beta1, (double)step)));
+    a.bc2_sqrt = (float)std::sqrt(1.0 - std::pow(beta2, (double)step));
+    a.eps = (float)eps;
+    a.lr = lr; a.beta1_d = beta1; a.beta2_d = beta2;
+    const CgaEntry* t = (const CgaEntry*)table;
+    const float n_levels = (float)(1 << (bits - 1));
+    cga_init_multi_kernel<<<(n_entries + 127) / 128, 128, 0, st>>>(t, n_entries);
+    cga_rowstat_multi_kernel<<<total_rowblocks, 256, 0, st>>>(t, n_entries, n_levels);
+    cga_adamw_multi_kernel<<<total_blocks, 256, 0, st>>>(t, n_entries, n_levels, (float)(0.5 - boundary_range), (float)(0.5 + boundary_range),
+                                                         a, step_dev);
     OFQ_CUDA(cudaGetLastError());
     return 0;
 }

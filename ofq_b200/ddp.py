@@ -18,9 +18,16 @@ import torch.distributed as dist
 
 
 class FlatGradAllReduce:
-    def __init__(self, params: Iterable[torch.nn.Parameter], world_size: int):
+    """`direct=True` (default): the weight-gradient GEMMs of the ofq_b200 layers write straight into the parameter's slice
+    of the flat buffer (functional.GRAD_SLOTS -> take()): the slice is handed out as a fresh view that autograd adopts as
+    `.grad`, so ~94 % of the gradient bytes are never copied, and the per-weight zero fills (split-K outputs accumulate)
+    become the one memset of zero(). Everything else (biases, norms, step sizes) is gathered by the multi-tensor copy."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], world_size: int, direct: bool = True):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.world_size = world_size
+        self.direct = direct
+        self._taken = set()
         dev = self.params[0].device
         self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
         self.views = []
@@ -30,6 +37,8 @@ class FlatGradAllReduce:
             off += p.numel()
         for p, v in zip(self.params, self.views):
             p.grad = v
+        self._slot = {p.data_ptr(): i for i, p in enumerate(self.params)}
+        self.direct_hits = 0
 
     @property
     def nbytes(self) -> int:
@@ -39,6 +48,23 @@ class FlatGradAllReduce:
         """Start of a step: backward writes fresh gradient tensors (no accumulate kernels); reduce() gathers them."""
         for p in self.params:
             p.grad = None
+        if self.direct:
+            from .quantization import functional
+            self.flat.zero_()
+            self._taken.clear()
+            functional.GRAD_SLOTS = self
+
+    def take(self, w: torch.Tensor):
+        """A fresh zeroed view of `w`'s slice of the flat buffer for the layer's backward to accumulate dW into, once per
+        step and parameter (a weight used twice in one forward gets an ordinary buffer the second time: autograd sums)."""
+        i = self._slot.get(w.data_ptr())
+        if i is None or i in self._taken or self.params[i].grad is not None:
+            return None
+        self._taken.add(i)
+        self.direct_hits += 1
+        p = self.params[i]
+        off = self.views[i].storage_offset()
+        return self.flat[off:off + p.numel()].view_as(p)
 
     def scale_loss(self, loss: torch.Tensor) -> torch.Tensor:
         return loss / self.world_size if self.world_size > 1 else loss
@@ -55,6 +81,10 @@ class FlatGradAllReduce:
             torch._foreach_copy_(views, grads)              # a handful of multi-tensor kernels
         for p, v in zip(self.params, self.views):
             p.grad = v
+        if self.direct:
+            from .quantization import functional
+            if functional.GRAD_SLOTS is self:
+                functional.GRAD_SLOTS = None
         if self.world_size > 1:
             dist.all_reduce(self.flat)
 

@@ -103,6 +103,48 @@ def _st():
     return torch.cuda.current_stream().cuda_stream
 
 
+# ------------------------------------------------------------------------------------------------ zero arena
+# The backward of every layer needs a few tiny pre-zeroed scratch vectors (running maxima for the fp16 range scales, scale
+# quadruples, atomic accumulators): as `torch.zeros` each is a fill launch of its own - ~70 per DeiT-S step. They are carved
+# from ONE persistent buffer per device instead, zeroed by a single memset when the step begins (StepPrologue.begin).
+# Only for scratch that lives and dies inside one autograd-node call: nothing carved here may be returned as a gradient or
+# saved for the backward (the next step's memset would clear it).
+_ARENA = {}
+_ARENA_FLOATS = 1 << 14
+
+
+class _ZeroArena:
+    __slots__ = ("buf", "cursor", "live", "carved", "missed")
+
+    def __init__(self, device):
+        self.buf = torch.zeros(_ARENA_FLOATS, dtype=torch.float32, device=device)
+        self.cursor, self.live, self.carved, self.missed = 0, False, 0, 0
+
+
+def arena_begin(device) -> None:
+    """Start of a step on `device`: one memset clears every scratch vector the step will carve."""
+    a = _ARENA.get(device)
+    if a is None:
+        a = _ARENA[device] = _ZeroArena(device)
+    a.buf.zero_()
+    a.cursor, a.live = 0, True
+
+
+def scratch_zeros(n: int, device, dtype=torch.float32) -> torch.Tensor:
+    """`n` zeroed 4-byte elements of call-local scratch (see above); falls back to torch.zeros outside a step or when the
+    arena is exhausted."""
+    a = _ARENA.get(device)
+    need = (n + 3) & ~3                                  # keep every carve 16-byte aligned
+    if a is None or not a.live or a.cursor + need > _ARENA_FLOATS:
+        if a is not None:
+            a.missed += 1
+        return torch.zeros(n, dtype=dtype, device=device)
+    t = a.buf[a.cursor:a.cursor + n]
+    a.cursor += need
+    a.carved += 1
+    return t if dtype == torch.float32 else t.view(dtype)
+
+
 def _ptr(t):
     return None if t is None else t.data_ptr()
 
@@ -447,7 +489,7 @@ def qkr_attn_bwd(qx, qk, a16, qv16, fmt16: int, B: int, N: int, H: int, Cc: int,
     colsum = torch.empty((B * H, N), dtype=torch.float32, device=dev)
     ds_part = torch.empty((B * H, N), dtype=torch.float32, device=dev)
     d_s = torch.empty(N, dtype=torch.float32, device=dev)
-    sc4 = torch.zeros(4, dtype=torch.float32, device=dev)
+    sc4 = scratch_zeros(4, dev)
     nbytes = B * N * Cc * (1.0 + H + 2.0 + 2.0) + B * H * N * (2.0 * ldo + 16.0)
     flops = 2.0 * B * H * N * N * (Cc + Cc // H)
     _call("qkr_attn_bwd", 3, nbytes, flops, _lib.load().ofq_qkr_attn_bwd, qx.data_ptr(), qk.data_ptr(), a16.data_ptr(), qv16.data_ptr(),
@@ -529,15 +571,16 @@ def counter_increment_(counter: torch.Tensor) -> None:
 
 
 def build_adamw_table(entries, device) -> tuple:
-    """entries: list of (p, grad, exp_avg, exp_avg_sq, decay). Returns (device uint8 table, n_entries, total_blocks,
-    total_numel). The table holds raw pointers: it is valid as long as those tensors keep their storage."""
+    """entries: list of (p, grad, exp_avg, exp_avg_sq, weight_decay). Returns (device uint8 table, n_entries, total_blocks,
+    total_numel). The table holds raw pointers: it is valid as long as those tensors keep their storage (the learning
+    rate is a launch argument, not part of the table)."""
     import struct
     blob = bytearray()
     first = 0
     total = 0
-    for p, g, m, v, decay in entries:
+    for p, g, m, v, wd in entries:
         n = p.numel()
-        blob += struct.pack("<QQQQqfi", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, float(decay), first)
+        blob += struct.pack("<QQQQqfi", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, float(wd), first)
         first += (n + 1023) // 1024
         total += n
     # pinned staging + async copy: legal inside CUDA-graph capture (the caller keeps `host` alive with the table)
@@ -551,6 +594,33 @@ def adamw_multi_(table, n_entries: int, total_blocks: int, total_numel: int, ste
                  beta2: float, eps: float, step_dev: Optional[torch.Tensor] = None) -> None:
     _call("adamw_multi", 1, 28.0 * total_numel, 0, _lib.load().ofq_adamw_multi, table.data_ptr(), n_entries,
           total_blocks, step, lr, beta1, beta2, eps, _ptr(step_dev), _st())
+
+
+def build_cga_table(entries, device) -> tuple:
+    """entries: list of (p [rows, cols], grad, exp_avg, exp_avg_sq, rowstat scratch [rows], kminmax scratch [2], weight_decay).
+    Returns (device table, n_entries, total_blocks, total_rowblocks, total_numel) for cga_adamw_multi_."""
+    import struct
+    blob = bytearray()
+    first = first_row = total = 0
+    for p, g, m, v, rowstat, mm, wd in entries:
+        rows, cols = p.shape
+        blob += struct.pack("<QQQQQQiifiii", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), rowstat.data_ptr(),
+                            mm.data_ptr(), rows, cols, float(wd), first, first_row, 0)
+        first += (rows * cols + 1023) // 1024
+        first_row += (rows + 7) // 8
+        total += rows * cols
+    host = torch.frombuffer(blob, dtype=torch.uint8).clone().pin_memory()
+    t = host.to(device, non_blocking=True)
+    t._ofq_host = host
+    return t, len(entries), first, first_row, total
+
+
+def cga_adamw_multi_(table, n_entries: int, total_blocks: int, total_rowblocks: int, total_numel: int, step: int, lr: float,
+                     beta1: float, beta2: float, eps: float, bits: int, boundary_range: float,
+                     step_dev: Optional[torch.Tensor] = None) -> None:
+    """CGA-masked AdamW on every weight of the table: 3 launches (scratch init, row statistics, masked update)."""
+    _call("cga_adamw", 3, 32.0 * total_numel, 0, _lib.load().ofq_cga_adamw_multi, table.data_ptr(), n_entries, total_blocks,
+          total_rowblocks, step, lr, beta1, beta2, eps, bits, float(boundary_range), _ptr(step_dev), _st())
 
 
 # ------------------------------------------------------------------------------------------------ LayerNorm

@@ -141,11 +141,13 @@ class StepPrologue:
         self.tables = tb
         self.dirty = False
 
-    def begin(self):
+    def begin(self, device=None):
         """Root forward pre-hook: run the registered work (if any) and make it available to the layers."""
         global ACTIVE
         ACTIVE = self
         self.fresh = False
+        from . import ops
+        ops.arena_begin(torch.cuda.current_device() if device is None else device)
         if not ENABLED or not (self.scale or self.statsq or self.wqk):
             return
         for d in (self.scale, self.statsq, self.wqk):       # a job must still describe live storage of the same layout
@@ -153,7 +155,6 @@ class StepPrologue:
                 j.used = False
         if self.dirty:
             self._build()
-        from . import ops
         lib = _lib.load()
         st = torch.cuda.current_stream().cuda_stream
         tb = self.tables
@@ -199,7 +200,7 @@ def install(model: torch.nn.Module) -> StepPrologue:
 def _begin_hook(m, inp):
     pro = getattr(m, "_ofq_prologue", None)
     if pro is not None and inp and torch.is_tensor(inp[0]) and inp[0].is_cuda:
-        pro.begin()
+        pro.begin(inp[0].device)
 
 
 def _end_hook(m, inp, out):

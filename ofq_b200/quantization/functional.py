@@ -81,8 +81,21 @@ def _scalar(sc):
     return vec(sc[1:2], 1)
 
 
+# Set by ddp.FlatGradAllReduce.zero() for the duration of a step: `.take(weight)` hands out the weight's (zeroed) slice of
+# the flat gradient buffer, so the dW GEMM accumulates in place and no gather copy / per-weight fill is needed.
+GRAD_SLOTS = None
+
+
+def _dw_buffer(w, Nout: int, K: int, device) -> torch.Tensor:
+    if GRAD_SLOTS is not None and w is not None and tuple(w.shape) == (Nout, K):
+        v = GRAD_SLOTS.take(w)
+        if v is not None:
+            return v
+    return torch.zeros((Nout, K), dtype=torch.float32, device=device)
+
+
 def _linear_backward_f16(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulate_dx: bool, qx16=None, sc=None, a16=None,
-                         colsum=None, amax_dx=None, wc16=None):
+                         colsum=None, amax_dx=None, wc16=None, dw_for=None):
     """fp16 backward of out = x_hat @ W_hat^T (+bias) with ONE range-scaled copy of the gradient,
     A16[t,n] = fp16(dY[t,n] * colscale[n] * se_x[t] * sc), read K-major by the dX GEMM and MN-major by the dW GEMM; the
     code operands stay exact and un-transposed (MN-major B), the folded scale vectors are undone per output row:
@@ -109,7 +122,7 @@ def _linear_backward_f16(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulat
              accumulate=accumulate_dx, rs=vec(se2[1], period), cs=_scalar(sc), amax=amax_dx)
     if qx16 is None:
         qx16 = ops.codes_to_bf16(qx, 1, M, K, K, 0, False, FMT)          # [1, M, K]
-    dW = torch.zeros((Nout, K), dtype=torch.float32, device=a16.device)
+    dW = _dw_buffer(dw_for, Nout, K, a16.device)
     # the weight gradient is off the activation-gradient chain: side stream, joined before the backward returns
     with ops.side_stream(a16, qx16, dW, cs2, sc, colsum, x_aft):
         ops.gemm(GEMM_BWD, a16, (Nout, 0, 0, 0), qx16, (K, 0, 0, 0), dW, (K, 0, 0), Nout, K, M, a_mn=True, b_mn=True,
@@ -136,7 +149,7 @@ def _linear_backward(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulate_dx
     # dW[Nout,K] = (dY * se_x)^T[Nout,M] @ qx[M,K]  + colsum(dY)[Nout] x aft[K]
     if qxT_all is None:
         qxT_all = ops.codes_to_bf16(qx, 1, M, K, K, 0, True, FMT)  # [1, K, m_pad]
-    dW = torch.zeros((Nout, K), dtype=torch.float32, device=dY2d.device)
+    dW = _dw_buffer(f16kw.get("dw_for"), Nout, K, dY2d.device)
     tiles = ((Nout + 127) // 128) * ((K + 127) // 128)
     splits = _splits_for(tiles, K2P * ((M + 63) // 64))
     ops.gemm(GEMM_BWD, prep["t"], (m_pad, Nout * m_pad, 0, 0), qxT_all, (m_pad, 0, 0, 0), dW, (K, 0, 0), Nout, K, M,
@@ -214,15 +227,16 @@ class QLinearFn(torch.autograd.Function):
             link.cs, link.se, link.sc = colscale, se, None
         if TAP is not None:
             TAP.append(("qlinear", dict(x=x2d, b4=b4, se=se, period=P, act=act, qx=qx, wc=wc, colscale=colscale, out=out)))
-        ctx.save_for_backward(xc, qx, wc, colscale, inv_cs, se2, b4, aft, qx16, wc16)
+        ctx.save_for_backward(xc, qx, wc, colscale, inv_cs, se2, b4, aft, qx16, wc16, weight)
         ctx.cfg = (P, lo, hi, g, bias is not None, act, link, role)
         return out.view(*x.shape[:-1], Nout)
 
     @staticmethod
     def backward(ctx, dY):
-        xc, qx, wc, colscale, inv_cs, se2, b4, aft, qx16, wc16 = ctx.saved_tensors
+        xc, qx, wc, colscale, inv_cs, se2, b4, aft, qx16, wc16, weight = ctx.saved_tensors
         P, lo, hi, g, has_bias, act, link, role = ctx.cfg
         wkw = {"wc16": wc16} if (F16 and wc16 is not None) else {}
+        wkw["dw_for"] = weight
         K = xc.shape[-1]
         x2d = xc.view(-1, K)
         M = x2d.shape[0]
@@ -242,7 +256,7 @@ class QLinearFn(torch.autograd.Function):
             sc = link.sc if (link is not None and role == 1) else None
             fuse_next = (F16 and FUSED16 and link is not None and role == 2 and link.fuse and link.cs is not None
                          and link.cs.shape[0] == K and K % 4 == 0 and M % link.se.numel() == 0)
-            amax = torch.zeros(1, dtype=torch.float32, device=dY.device) if fuse_next else None
+            amax = ops.scratch_zeros(1, dY.device) if fuse_next else None
             dW, dbias, _ = _linear_backward(dY2d, qx, wc, (colscale, inv_cs), se2, P, aft, dxhat, False, qx16, sc=sc,
                                             **({"amax_dx": amax} if fuse_next else {}), **wkw)
             if fuse_next:
@@ -563,7 +577,7 @@ class QKRAttnCoreFn(torch.autograd.Function):
                                     qkx=qkx, k_b4=k_b4, se_k=se_k, qk=qk, P=P_tap, se_p=se_p, qp=qp, out=out, B=B, N=N, H=H, C=C)))
         ctx.save_for_backward(xc, wq, wk, x_b4, x_aft, v_b4, v_aft, k_b4, k_aft, qx, sx2, wvc, cs_v, ics_v, v_out, qv, sv2,
                               wqkc, cs_qk, ics_qk, qkx, qk, sk2, sk2_hn, P, qp, sp2, qx16, qv16, qk16, qp16, wv16, wqk16,
-                              rowstat, ctS if rowstat is not None else None)
+                              rowstat, ctS if rowstat is not None else None, wv)
         ctx.cfg = (B, N, C, H, lo, hi, hiu, scale, g_x, g_v, g_k, g_p, ldS, ldq, bv is not None,
                    attn_bias is not None, link)
         if link is not None:
@@ -573,7 +587,7 @@ class QKRAttnCoreFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dO):
         (xc, wq, wk, x_b4, x_aft, v_b4, v_aft, k_b4, k_aft, qx, sx2, wvc, cs_v, ics_v, v_out, qv, sv2, wqkc, cs_qk, ics_qk,
-         qkx, qk, sk2, sk2_hn, P, qp, sp2, qx16, qv16, qk16, qp16, wv16, wqk16, rowstat, ctS) = ctx.saved_tensors
+         qkx, qk, sk2, sk2_hn, P, qp, sp2, qx16, qv16, qk16, qp16, wv16, wqk16, rowstat, ctS, wv) = ctx.saved_tensors
         B, N, C, H, lo, hi, hiu, scale, g_x, g_v, g_k, g_p, ldS, ldq, has_bv, has_bias, link = ctx.cfg
         se_x, se_v, se_k, se_p, se_k_hn = sx2[0], sv2[0], sk2[0], sp2[0], sk2_hn[0]
         M = B * N
@@ -583,7 +597,7 @@ class QKRAttnCoreFn(torch.autograd.Function):
         # of the V and qkx quantizers then write the fp16 operand of the next linear layer's backward GEMMs directly
         # (range scale from that bound), so d v_out / d qkx never exist in fp32 and ofq_grad_prep is not needed there
         fused16 = F16 and FUSED16 and C % 128 == 0      # streaming layout of the (token, head)-segmented qkx pass
-        amax = torch.zeros(3, dtype=torch.float32, device=dev) if F16 else None      # max |d v_hat|, |d k_hat|, |dP_hat|
+        amax = ops.scratch_zeros(3, dev) if F16 else None      # max |d v_hat|, |d k_hat|, |dP_hat|
         fused_bwd = rowstat is not None
         if fused_bwd:
             (a16_o, rowdot, sc_o, qv16), dvhat = _pv_backward_f16(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16, qp16,
@@ -600,12 +614,12 @@ class QKRAttnCoreFn(torch.autograd.Function):
             _, ds_v, dvb4, dvaft, a16_v = ops.lsq_bwd(dvhat.view(M, C), v_out, v_b4, se_v, PER_COL, 1, 1, lo, hi, g_v,
                                                       out16=(FMT, cs_v, se_x, N, sc_v), want_dx=False)
             dWv, dbv, qx_op = _linear_backward_f16(None, qx, wvc, (cs_v, ics_v), sx2, N, x_aft, dxhat, False, qx16, sc=sc_v,
-                                                   a16=a16_v, colsum=dvb4, wc16=wv16)
+                                                   a16=a16_v, colsum=dvb4, wc16=wv16, dw_for=wv)
         else:
             dv_out, ds_v, dvb4, dvaft, *sc_v = ops.lsq_bwd(dvhat.view(M, C), v_out, v_b4, se_v, PER_COL, 1, 1, lo, hi, g_v,
                                                            next_scale=(cs_v, se_x, 1.0, True) if F16 else None)
             dWv, dbv, qx_op = _linear_backward(dv_out, qx, wvc, (cs_v, ics_v), sx2, N, x_aft, dxhat, False, qx16,
-                                               sc=sc_v[0] if sc_v else None, **({"wc16": wv16} if F16 else {}))
+                                               sc=sc_v[0] if sc_v else None, dw_for=wv, **({"wc16": wv16} if F16 else {}))
         # --- softmax + probability quantizer, then the two score GEMMs
         if F16:
             if fused_bwd:

@@ -664,6 +664,49 @@ def test_adamw_multi_tensor(ops):
         assert rel_err(p.detach().cpu(), r.detach()) < 1e-6
 
 
+def test_cga_adamw_multi_tensor_is_the_per_tensor_kernel(ops):
+    """CGAAdamW's three-launch multi-tensor masked step == ofq_cga_adamw on each weight, bit for bit (weights, both
+    moments), over steps with a changing learning rate (lr is a launch argument: the pointer tables must survive it)."""
+    from ofq_b200.cga import CGAAdamW
+    torch.manual_seed(18)
+    shapes = [(384, 384), (1536, 384), (384, 1536), (1152, 384), (96, 100), (10, 7), (384,), (1000, 384)]
+    ps = [torch.nn.Parameter(torch.nn.init.trunc_normal_(torch.empty(s), std=0.02).cuda()) for s in shapes]
+    masked = [p for p in ps[:6]]
+    groups = [{"params": [p for p in ps if p.ndim <= 1], "weight_decay": 0.0},
+              {"params": [p for p in ps if p.ndim > 1], "weight_decay": 0.05}]
+    opt = CGAAdamW(groups, lr=1e-3, masked=masked, wq_bitw=2, boundary_range=0.05)
+    ref = [p.detach().clone() for p in ps]
+    rm = [torch.zeros_like(p) for p in ps]
+    rv = [torch.zeros_like(p) for p in ps]
+    tables = None
+    for step in range(4):
+        lr = 1e-3 * (1.0 - 0.2 * step)
+        for g in opt.param_groups:
+            g["lr"] = lr
+        grads = [torch.randn_like(p) * 1e-3 for p in ps]
+        for p, g in zip(ps, grads):
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)                                           # persistent gradient buffers, as under the captured step
+        before = opt.launches
+        opt.step()
+        assert opt.launches - before == 2 + 3                             # one plain launch per group + the masked trio
+        if tables is None:
+            tables = {k: v[1].data_ptr() for k, v in opt._tables.items()}
+        else:
+            assert tables == {k: v[1].data_ptr() for k, v in opt._tables.items()}      # not rebuilt when lr changed
+        sd = torch.full((1,), step + 1, dtype=torch.int32, device="cuda")     # both sides form the bias corrections on the device
+        for i, (r, g) in enumerate(zip(ref, grads)):
+            is_masked = i < 6
+            ops.cga_adamw_(r, g, rm[i], rv[i], step + 1, lr, 0.9, 0.999, 1e-8, 0.05 if r.ndim > 1 else 0.0,
+                           bits=2 if is_masked else 0, boundary_range=0.05, step_dev=sd)
+        for i, (p, r) in enumerate(zip(ps, ref)):
+            assert torch.equal(p.detach(), r), (step, i)
+            assert torch.equal(opt.state[p]["exp_avg"], rm[i]), (step, i)
+            assert torch.equal(opt.state[p]["exp_avg_sq"], rv[i]), (step, i)
+
+
 @pytest.mark.parametrize("rows,cols", [(25344, 384), (1000, 1536), (396, 64), (77, 96)])
 def test_layernorm_fwd_bwd(ops, rows, cols):
     """Host-glue LayerNorm kernels vs torch.nn.functional.layer_norm (fp64 reference)."""

@@ -285,6 +285,56 @@ def test_step_prologue_matches_per_layer_path(Q):
         opt.step()                                  # weights move: the next forward must see the new codes
 
 
+def test_flat_gradient_buffer_direct_slots_and_zero_arena(Q):
+    """ddp.FlatGradAllReduce(direct=True): the dW GEMMs of the quantized layers accumulate straight into the flat gradient
+    buffer (autograd adopts the slice as .grad: no gather copy, no per-weight zero fill), and the tiny scratch vectors of the
+    backward come from the per-step zero arena. Pure re-plumbing: every gradient equals the plain path's."""
+    from ofq_b200 import ops
+    from ofq_b200.ddp import FlatGradAllReduce
+    from ofq_b200.host.deit import DistilledVisionTransformer
+    from ofq_b200.quantization import functional as Fn
+    torch.manual_seed(44)
+    depth = 2
+    model = DistilledVisionTransformer(embed_dim=128, depth=depth, num_heads=2, num_classes=10)
+    model = Q.replace_module_by_qmodule_deit(model, Q.make_qconfigs(Q.deit_qmodule_names(depth), 2, 2),
+                                             pretrained_initialized=True, qk_reparam=True).cuda()
+    img = torch.randn(3, 3, 224, 224, device="cuda")
+    lbl = torch.tensor([1, 5, 7], device="cuda")
+    model.eval()
+    with torch.no_grad():
+        model(img)
+    model.train()
+
+    def fwd_bwd():
+        (cls, dst), _ = model(img)
+        (F.cross_entropy(cls, lbl) + F.cross_entropy(dst, lbl)).backward()
+
+    model.zero_grad(set_to_none=True)
+    fwd_bwd()
+    ref = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    arena = ops._ARENA[img.device]
+    assert arena.carved > 0                                       # the backward scratch came from the arena ...
+    ddp = FlatGradAllReduce(model.parameters(), 1)
+    for _ in range(2):                                            # twice: the second step re-uses the slots after zero()
+        ddp.zero()
+        assert Fn.GRAD_SLOTS is ddp
+        hits0 = ddp.direct_hits
+        fwd_bwd()
+        weights = [(n, p) for n, p in model.named_parameters() if p.ndim == 2 and ".blocks." in "." + n and n.endswith(".weight")
+                   and not n.endswith(("q.weight", "k.weight"))]
+        assert ddp.direct_hits - hits0 == len(weights) == 4 * depth          # v, proj, fc1, fc2 of every block
+        views = {id(p): v for p, v in zip(ddp.params, ddp.views)}
+        for n, p in weights:
+            assert p.grad.data_ptr() == views[id(p)].data_ptr(), n           # adopted, not copied
+        ddp.reduce()
+        assert Fn.GRAD_SLOTS is None
+        for n, p in model.named_parameters():
+            if n in ref:
+                assert p.grad.data_ptr() == views[id(p)].data_ptr()
+                # (split-K weight gradients are summed by atomics in arrival order: equal up to fp32 summation order)
+                assert torch.equal(p.grad, ref[n]) or rel_err(p.grad, ref[n]) < 1e-5, n
+
+
 @pytest.mark.parametrize("patch,cout", [(16, 64), (32, 96)])
 def test_patch_embed_int8_path_matches_torch_composition(Q, patch, cout):
     """LSQ_QConv2d (8-bit patch embedding): the int8 tensor-core path (functional.PatchEmbedFn) against the op-for-op torch
