@@ -46,8 +46,9 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=8, help="images per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sites", default="", help="write a per-call-site kernel timing table of the instrumented steps here")
-    ap.add_argument("--grad-buffer", default="flat", choices=["flat", "none"],
-                    help="flat: gradients live in one flat fp32 buffer (ofq_b200.ddp.FlatGradAllReduce, also at N = 1)")
+    ap.add_argument("--grad-buffer", default="none", choices=["flat", "none"],
+                    help="N = 1 only (N > 1 always exchanges through the flat buffer). flat: gradients live in one flat fp32 buffer "
+                         "(ofq_b200.ddp.FlatGradAllReduce); measured no faster than per-parameter gradients at N = 1 (6207 vs 6214-6302 img/s)")
     ap.add_argument("--mode", default="qat", choices=["qat", "cga", "eval"],
                     help="qat: the headline QAT step. cga: BASELINE.json config 5, the CGA fine-tune step (qk_reparam_type=1, "
                          "freeze mask fused into AdamW for every StatsQ weight, boundaryRange 0.005, lr 1e-5). eval: no-grad "
@@ -272,8 +273,7 @@ def main():
     else:
         opt = CGAAdamW(param_groups_weight_decay(model, 0.05, getattr(model, 'no_weight_decay', lambda: set())()), lr=5.47e-4)
     # data-parallel gradient exchange (ofq_b200/ddp.py): ONE NCCL all-reduce (mean) of a flat fp32 gradient buffer
-    # (also at N = 1: the flat buffer is the gradient arena - the dW GEMMs accumulate straight into their slices after ONE
-    # memset, instead of one zero fill per weight; `--grad-buffer none` keeps per-parameter gradient tensors)
+    # (`--grad-buffer flat` uses the same flat buffer as the gradient arena at N = 1)
     ddp = None
     if a.mode != "eval" and (world > 1 or a.grad_buffer == "flat"):
         ddp = BucketedGradAllReduce(model, world) if (a.ddp == "bucketed" and world > 1) else FlatGradAllReduce(model.parameters(), world)

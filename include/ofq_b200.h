@@ -94,6 +94,37 @@ OFQ_API int ofq_gemm_ex(int kind, const ofq_operand_t* A, const ofq_operand_t* B
              const ofq_vec_t* rs, const ofq_vec_t* cs, const ofq_vec_t* rt, const ofq_vec_t* ct,
              float* out_absmax, void* stream);
 
+/* int8 GEMM whose epilogue IS the LSQ quantizer of its output (reference attention.py:200-207: qkx = Linear(x_hat) ->
+ * move_qkx_b4 -> LsqQuantizer): y = acc * rs[m] * cs[n] + rt[m] * ct[n] exactly as ofq_gemm forms it, then
+ *   v = (y + b4[n]) / s,  s = s_eff[(m % period) * nseg + n / seg_len],  q = rint(clamp(v, qlo, qhi))
+ * with the same guarded quotient as ofq_lsq_quant (codes bit-identical to ofq_gemm followed by ofq_lsq_quant_ex).
+ * The fp32 product is never written. Outputs (each optional except codes):
+ *   codes   int8 [M, N]                 the operand of the next integer GEMM
+ *   codes16 fp16 / bf16 [M, N]          exact copy for the 16-bit backward GEMMs
+ *   res16   fp16 [M, N]                 what the quantizer's backward needs instead of y: q - v where qlo <= v <= qhi (the
+ *                                       straight-through region; v = (y + b4) * inv_s as ofq_lsq_bwd evaluates it), -2 where v < qlo,
+ *                                       +2 where v > qhi (|q - v| <= 1/2, so the three cases cannot be confused)
+ *   rowdot  fp32 [M, nseg]              sum over the segment's columns of dot_u[n] * q (the column term of the attention logits)
+ * seg_len % 32 == 0; N % 16 == 0; leading dimensions multiples of 16 elements. workspace: M * ceil(N / 32) floats when
+ * rowdot is requested. */
+typedef struct {
+    int8_t* codes;      long long ld_codes;
+    void* codes16;      long long ld_codes16;  int fmt16;     /* OFQ_FMT_F16 / OFQ_FMT_BF16 */
+    void* res16;        long long ld_res16;
+    const float* b4;        /* [N] or NULL */
+    const float* s_eff;     /* [period * nseg] */
+    const float* inv_s;     /* [period * nseg], 1.0f / s_eff */
+    int period, nseg, seg_len;
+    float qlo, qhi;
+    const float* dot_u;     /* [N] or NULL */
+    float* rowdot;          /* [M, nseg] or NULL */
+    float* workspace;
+} ofq_gemm_lsq_t;
+
+OFQ_API int ofq_gemm_lsq(const ofq_operand_t* A, const ofq_operand_t* B, int M, int N, int K,
+                         const ofq_vec_t* rs, const ofq_vec_t* cs, const ofq_vec_t* rt, const ofq_vec_t* ct,
+                         const ofq_gemm_lsq_t* q, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K1  StatsQuantizer.forward as integer codes (reference statsq.py:133-150).
  *   sf[r]       = 2 * mean_c |w[r][c]|                       (row sum accumulated in fp64, then fp32 ops)
@@ -132,6 +163,7 @@ OFQ_API int ofq_lsq_effective_scale(const float* alpha, int n, float g, float* o
 #define OFQ_SCALE_PER_COL 1
 #define OFQ_ACT_NONE 0
 #define OFQ_ACT_GELU 1   /* nn.GELU() (erf form) applied to x before the shift: the fc2 input of QMLP (qlinear.py:123-136) */
+#define OFQ_ACT_RES16 2   /* ofq_lsq_bwd_ex only: `x` is the fp16 residual plane written by ofq_gemm_lsq (pitch ldx in halves), not the input */
 OFQ_API int ofq_lsq_quant(const float* x, long long rows, int cols, long long ldx, const float* b4,
                           const float* s_eff, int scale_mode, int period, int nseg, int qlo, int qhi,
                           int8_t* codes, long long ldq, void* stream);

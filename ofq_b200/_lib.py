@@ -32,6 +32,13 @@ class GemmOut(C.Structure):
                 ("bstride2", C.c_longlong), ("accumulate", C.c_int)]
 
 
+class GemmLsq(C.Structure):
+    _fields_ = [("codes", C.c_void_p), ("ld_codes", C.c_longlong), ("codes16", C.c_void_p), ("ld_codes16", C.c_longlong),
+                ("fmt16", C.c_int), ("res16", C.c_void_p), ("ld_res16", C.c_longlong), ("b4", C.c_void_p), ("s_eff", C.c_void_p),
+                ("inv_s", C.c_void_p), ("period", C.c_int), ("nseg", C.c_int), ("seg_len", C.c_int), ("qlo", C.c_float),
+                ("qhi", C.c_float), ("dot_u", C.c_void_p), ("rowdot", C.c_void_p), ("workspace", C.c_void_p)]
+
+
 _p, _i, _ll, _f, _d = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
 
 # name -> (restype, argtypes); must list every symbol include/ofq_b200.h declares (tests/test_abi.py checks)
@@ -43,6 +50,8 @@ SIGNATURES = {
                       C.POINTER(Vec), C.POINTER(Vec), C.POINTER(Vec), C.POINTER(Vec), _p]),
     "ofq_gemm_ex": (_i, [_i, C.POINTER(Operand), C.POINTER(Operand), C.POINTER(GemmOut), _i, _i, _i, _i, _i, _i, _i,
                          C.POINTER(Vec), C.POINTER(Vec), C.POINTER(Vec), C.POINTER(Vec), _p, _p]),
+    "ofq_gemm_lsq": (_i, [C.POINTER(Operand), C.POINTER(Operand), _i, _i, _i, C.POINTER(Vec), C.POINTER(Vec), C.POINTER(Vec),
+                          C.POINTER(Vec), C.POINTER(GemmLsq), _p]),
     "ofq_statsq_codes": (_i, [_p, _i, _i, _ll, _i, _p, _ll, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ofq_statsq_codes_ex": (_i, [_p, _i, _i, _ll, _i, _p, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p]),
     "ofq_statsq_codes_multi": (_i, [_p, _i, _i, _p]),

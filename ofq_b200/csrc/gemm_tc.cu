@@ -690,6 +690,363 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------ LSQ-quantizing epilogue
+// ofq_gemm_lsq: the int8 GEMM of a linear layer whose output goes straight into an LSQ quantizer (qkx of the query-key
+// reparameterisation, attention.py:200-207). Mainloop, ring and accumulator hand-off as gemm_tc_kernel<0, BN, STAGES>; the
+// epilogue forms y = acc * rs * cs + rt * ct with the SAME roundings, then the quantizer: codes (int8), their exact 16-bit copy
+// and the fp16 backward residual leave through three TMA stores per 32 x 32 chunk, the fp32 product is never written.
+struct LsqEpi {
+    const float* b4; const float* s_eff; const float* inv_s; const float* dot_u;
+    float* part; int ld_part;          // [M, ceil(N / 32)] per-chunk partial row dots (summed in fixed order afterwards)
+    int nseg, seg_len;
+    FastDiv fd_period, fd_seglen;
+    float qlo, qhi;
+    int has16, has_res, f16;
+};
+
+template <int BN, int STAGES>
+struct LsqSmem {
+    static constexpr uint32_t A_BYTES = BM * KBYTES;
+    static constexpr uint32_t STAGE_BYTES = A_BYTES + BN * KBYTES;
+    static constexpr uint32_t CHUNK_BYTES = 5120;                      // codes 1 KB (32B swizzle) | codes16 2 KB | res16 2 KB (64B swizzle)
+    static constexpr uint32_t OUT_OFF = STAGES * STAGE_BYTES;
+    static constexpr uint32_t OUT_BYTES = EPI_WARPS * 2 * CHUNK_BYTES;
+    static constexpr uint32_t VEC_OFF = OUT_OFF + OUT_BYTES;           // per warp and owned chunk: cs | ct | b4 | u (32 floats each)
+    static constexpr uint32_t BAR_OFF = VEC_OFF + EPI_WARPS * epi_nch(BN) * 128 * 4;
+    static constexpr uint32_t TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
+    static constexpr size_t DYN_BYTES = TOTAL + 1024;
+};
+
+__device__ __forceinline__ void st_shared_v4_b32(void* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(smem_u32(dst)), "r"(a), "r"(b), "r"(c), "r"(d));
+}
+__device__ __forceinline__ uint32_t cvt_pack16(float lo, float hi, bool f16) {
+    uint32_t r;
+    if (f16) asm("cvt.rn.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+    else     asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+__device__ __forceinline__ void tmem_ld_32x32_x8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_pin8(uint32_t (&r)[8]) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]) : : "memory");
+}
+
+// Eight columns (piece `sub` of a 32 x 32 chunk) of row `lane`: y, quantizer, outputs into the swizzled staging rows.
+// MODE 0: codes only; 1: + 16-bit copy; 2: + fp16 residual. Returns sum_j u[j] * q[j] over the piece.
+// Kept small and called from a rolled loop: a fully unrolled chunk (x 2 register buffers x variants) did not fit the
+// instruction cache and ran at a third of this speed.
+template <int MODE, bool RT1>
+__device__ __forceinline__ float lsq_piece(const uint32_t (&rr)[8], const float rsv, const float rtv, const float* __restrict__ vec,
+                                           const float se, const float inv, const float qlo, const float qhi, const bool f16,
+                                           uint8_t* __restrict__ row8, uint8_t* __restrict__ row16, uint8_t* __restrict__ rowr,
+                                           const int sw8, const int sw16, const int sub) {
+    constexpr float MAGIC = 12582912.f;                 // 1.5 * 2^23: (t + MAGIC) - MAGIC = rint(t) for |t| < 2^22; low byte of the sum's bits = the code
+    const float* vp = vec + 8 * sub;
+    const float4 csA = ld_shared_v4_nc(vp), csB = ld_shared_v4_nc(vp + 4);
+    const float4 ctA = ld_shared_v4_nc(vp + 32), ctB = ld_shared_v4_nc(vp + 36);
+    const float4 b4A = ld_shared_v4_nc(vp + 64), b4B = ld_shared_v4_nc(vp + 68);
+    const float4 uA = ld_shared_v4_nc(vp + 96), uB = ld_shared_v4_nc(vp + 100);
+    const float csv[8] = {csA.x, csA.y, csA.z, csA.w, csB.x, csB.y, csB.z, csB.w};
+    const float ctv[8] = {ctA.x, ctA.y, ctA.z, ctA.w, ctB.x, ctB.y, ctB.z, ctB.w};
+    const float b4v[8] = {b4A.x, b4A.y, b4A.z, b4A.w, b4B.x, b4B.y, b4B.z, b4B.w};
+    const float uv[8] = {uA.x, uA.y, uA.z, uA.w, uB.x, uB.y, uB.z, uB.w};
+    // Packed fp32x2 arithmetic (FMUL2 / FFMA2 / FADD2: two columns per instruction, the same roundings per element): this
+    // epilogue is bound by instruction issue, not by memory. The accumulators are small integers (|acc| < 2^22): int -> float
+    // through the magic constant (integer add + FADD2) instead of I2F.
+    const float2 rs2 = make_float2(rsv, rsv), rt2 = make_float2(rtv, rtv), inv2 = make_float2(inv, inv);
+    const float2 magic2 = make_float2(MAGIC, MAGIC), nmagic2 = make_float2(-MAGIC, -MAGIC);
+    float2 a2[4], v2[4], t2[4], mg2[4], r2[4];
+    bool redo = false;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        const float2 acc = __fadd2_rn(make_float2(__uint_as_float(rr[2 * h] + 0x4B400000u), __uint_as_float(rr[2 * h + 1] + 0x4B400000u)), nmagic2);
+        const float2 t0 = __fmul2_rn(acc, rs2);
+        const float2 y = __ffma2_rn(t0, make_float2(csv[2 * h], csv[2 * h + 1]),
+                                    RT1 ? make_float2(ctv[2 * h], ctv[2 * h + 1]) : __fmul2_rn(rt2, make_float2(ctv[2 * h], ctv[2 * h + 1])));
+        a2[h] = __fadd2_rn(y, make_float2(b4v[2 * h], b4v[2 * h + 1]));
+        v2[h] = __fmul2_rn(a2[h], inv2);
+        t2[h] = make_float2(fminf(fmaxf(v2[h].x, qlo), qhi), fminf(fmaxf(v2[h].y, qlo), qhi));
+        mg2[h] = __fadd2_rn(t2[h], magic2);
+        r2[h] = __fadd2_rn(mg2[h], nmagic2);
+        const float2 d = __fadd2_rn(t2[h], make_float2(-r2[h].x, -r2[h].y));
+        redo |= fmaxf(fabsf(d.x), fabsf(d.y)) > 0.4998f;
+    }
+    if (redo) {                                         // a quotient near a rounding boundary: IEEE division for the piece (rare)
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            r2[h] = make_float2(rintf(fminf(fmaxf(__fdiv_rn(a2[h].x, se), qlo), qhi)), rintf(fminf(fmaxf(__fdiv_rn(a2[h].y, se), qlo), qhi)));
+            mg2[h] = __fadd2_rn(r2[h], magic2);
+        }
+    }
+    float2 dot2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) dot2 = __ffma2_rn(make_float2(uv[2 * h], uv[2 * h + 1]), r2[h], dot2);
+    const float dot = dot2.x + dot2.y;
+    // eight int8 codes: the low bytes of the magic sums
+    uint32_t c8[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t lo2 = __byte_perm(__float_as_uint(mg2[2 * h].x), __float_as_uint(mg2[2 * h].y), 0x0040);
+        const uint32_t hi2 = __byte_perm(__float_as_uint(mg2[2 * h + 1].x), __float_as_uint(mg2[2 * h + 1].y), 0x0040);
+        c8[h] = __byte_perm(lo2, hi2, 0x5410);
+    }
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};\n" ::"r"(smem_u32(row8 + (((sub >> 1) ^ sw8) << 4) + ((sub & 1) << 3))), "r"(c8[0]), "r"(c8[1]));
+    if (MODE >= 1)
+        st_shared_v4_b32(row16 + ((sub ^ sw16) << 4), cvt_pack16(r2[0].x, r2[0].y, f16), cvt_pack16(r2[1].x, r2[1].y, f16),
+                         cvt_pack16(r2[2].x, r2[2].y, f16), cvt_pack16(r2[3].x, r2[3].y, f16));
+    if (MODE >= 2) {
+        // inside the clamp range <=> the clamp changed nothing; outside, the sign of v tells the side (qlo <= 0 <= qhi)
+        uint32_t w[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const float2 dv = __fadd2_rn(r2[h], make_float2(-v2[h].x, -v2[h].y));
+            const float rx = t2[h].x == v2[h].x ? dv.x : copysignf(2.f, v2[h].x);
+            const float ry = t2[h].y == v2[h].y ? dv.y : copysignf(2.f, v2[h].y);
+            w[h] = cvt_pack16(rx, ry, true);
+        }
+        st_shared_v4_b32(rowr + ((sub ^ sw16) << 4), w[0], w[1], w[2], w[3]);
+    }
+    return dot;
+}
+
+__device__ __forceinline__ void tmem_ld_32x32_x16r(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_pin16(uint32_t (&r)[16]) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                      "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]) : : "memory");
+}
+// sixteen columns = two 8-column pieces
+template <int MODE, bool RT1>
+__device__ __forceinline__ float lsq_piece16(const uint32_t (&rr)[16], const float rsv, const float rtv, const float* __restrict__ vec,
+                                             const float se, const float inv, const float qlo, const float qhi, const bool f16,
+                                             uint8_t* __restrict__ row8, uint8_t* __restrict__ row16, uint8_t* __restrict__ rowr,
+                                             const int sw8, const int sw16, const int sub) {
+    const uint32_t lo[8] = {rr[0], rr[1], rr[2], rr[3], rr[4], rr[5], rr[6], rr[7]};
+    const uint32_t hi[8] = {rr[8], rr[9], rr[10], rr[11], rr[12], rr[13], rr[14], rr[15]};
+    const float d0 = lsq_piece<MODE, RT1>(lo, rsv, rtv, vec, se, inv, qlo, qhi, f16, row8, row16, rowr, sw8, sw16, sub);
+    const float d1 = lsq_piece<MODE, RT1>(hi, rsv, rtv, vec, se, inv, qlo, qhi, f16, row8, row16, rowr, sw8, sw16, sub + 1);
+    return d0 + d1;
+}
+
+template <int BN, int STAGES, int MODE, bool RT1>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_lsq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmQ8, const __grid_constant__ CUtensorMap tmQ16,
+                const __grid_constant__ CUtensorMap tmR16, const GemmParams p, const LsqEpi e, const int num_tiles,
+                const int mtiles, const int ntiles) {
+    using L = LsqSmem<BN, STAGES>;
+    constexpr uint32_t A_BYTES = L::A_BYTES;
+    constexpr uint32_t STAGE_BYTES = L::STAGE_BYTES;
+    constexpr uint32_t ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+    constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
+    constexpr uint32_t UMMA_K_BYTES = 32;
+    const uint32_t IDESC = umma_idesc(2u, 1u, BM, BN);
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_full = empty_bar + STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* vec_s = reinterpret_cast<float*>(smem + L::VEC_OFF);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmQ8);
+        tma_prefetch_desc(&tmQ16); tma_prefetch_desc(&tmR16);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_WARPS); }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);
+                for (int i = 0; i < c.nit; ++i, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* sa = smem + s * STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                    tma_load_5d(sa, &tmA, &full_bar[s], (c.it_begin + i) * KBYTES, c.m0, 0, 0, 0);
+                    tma_load_5d(sa + A_BYTES, &tmB, &full_bar[s], (c.it_begin + i) * KBYTES, c.n0, 0, 0, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            uint32_t it = 0, tc = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tc) {
+                const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);
+                const uint32_t as = tc & 1, aph = (tc >> 1) & 1;
+                mbar_wait(&acc_empty[as], aph ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * ACC_COLS;
+                for (int i = 0; i < c.nit; ++i, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t adesc = umma_desc_kmajor_sw128(sa), bdesc = umma_desc_kmajor_sw128(sa + A_BYTES);
+#pragma unroll
+                    for (uint32_t kk = 0; kk < KBYTES / UMMA_K_BYTES; ++kk)
+                        umma_i8(tmem_d, adesc + kk * (UMMA_K_BYTES >> 4), bdesc + kk * (UMMA_K_BYTES >> 4), IDESC, (i | kk) != 0);
+                    tc_commit(&empty_bar[s]);
+                }
+                tc_commit(&acc_full[as]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int NCH = epi_nch(BN);
+        uint8_t* stage_base = smem + L::OUT_OFF + (warp - 2) * 2 * L::CHUNK_BYTES;
+        float* myvec = vec_s + (warp - 2) * NCH * 128;
+        uint32_t tc = 0, chunk = 0;
+        const float qlo = e.qlo, qhi = e.qhi;
+        const bool f16 = e.f16 != 0;
+        // vectors of the NEXT tile, loaded one tile ahead: column `lane` of every owned chunk, the row's rs / rt and the step
+        // sizes of the (at most two: BN <= seg_len) segments the tile touches
+        float n_cs[NCH], n_ct[NCH], n_b4[NCH], n_u[NCH], n_rs = 0.f, n_rt = 0.f, n_se[2] = {1.f, 1.f}, n_inv[2] = {1.f, 1.f};
+        TileCoord cn;
+        auto load_vecs = [&](const TileCoord& c) {
+            const int m = c.m0 + q * 32 + lane;
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                const int n = c.n0 + (half + 2 * k) * 32 + lane;
+                const bool ok = n < p.N;
+                n_cs[k] = ok ? (p.cs.p ? __ldg(p.cs.p + p.cs.fd.mod(n)) : 1.0f) : 0.f;
+                n_ct[k] = (ok && p.has_rank1) ? (p.ct.p ? __ldg(p.ct.p + n) : 1.0f) : 0.f;
+                n_b4[k] = (ok && e.b4) ? __ldg(e.b4 + n) : 0.f;
+                n_u[k] = (ok && e.dot_u) ? __ldg(e.dot_u + n) : 0.f;
+            }
+            const bool row_ok = m < p.M;
+            n_rs = row_ok ? (p.rs.p ? __ldg(p.rs.p + p.rs.fd.mod(m)) : 1.0f) : 0.f;
+            n_rt = (row_ok && p.has_rank1) ? (p.rt.p ? __ldg(p.rt.p + p.rt.fd.mod(m)) : 1.0f) : 0.f;
+            const int seg0 = e.fd_seglen.div(c.n0);
+            const int mp = e.fd_period.mod(row_ok ? m : 0);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int sg = min(seg0 + k, e.nseg - 1);
+                n_se[k] = __ldg(e.s_eff + mp * e.nseg + sg);
+                n_inv[k] = __ldg(e.inv_s + mp * e.nseg + sg);
+            }
+        };
+        if ((int)blockIdx.x < num_tiles) {
+            cn = decode_tile(p, blockIdx.x, BN, mtiles, ntiles);
+            load_vecs(cn);
+        }
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tc) {
+            const TileCoord c = cn;
+            const uint32_t as = tc & 1, aph = (tc >> 1) & 1;
+            const float rsv = n_rs, rtv = n_rt;
+            const float se_a = n_se[0], se_b = n_se[1], inv_a = n_inv[0], inv_b = n_inv[1];
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                myvec[k * 128 + lane] = n_cs[k];
+                myvec[k * 128 + 32 + lane] = n_ct[k];
+                myvec[k * 128 + 64 + lane] = n_b4[k];
+                myvec[k * 128 + 96 + lane] = n_u[k];
+            }
+            __syncwarp();
+            if (t + (int)gridDim.x < num_tiles) {
+                cn = decode_tile(p, t + gridDim.x, BN, mtiles, ntiles);
+                load_vecs(cn);
+            }
+            if (c.nit > 0) {
+                mbar_wait(&acc_full[as], aph);
+                tc_fence_after();
+            }
+            const uint32_t tmem_acc = tmem_base + as * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+            int nvalid = (min(BN, p.N - c.n0) + 31) / 32;
+            const int m_row0 = c.m0 + q * 32;
+            if (m_row0 >= p.M) nvalid = 0;
+            const int seg_first = e.fd_seglen.div(c.n0);
+            const int seg_switch = (seg_first + 1) * e.seg_len;          // first column of the tile's second segment
+            // this warp's chunks (half, half + 2, ...), each as two 16-column pieces; the TMEM loads ping-pong between two
+            // 16-register buffers one piece ahead (also across chunk boundaries). ROLLED loop over the chunks: a fully unrolled
+            // tile did not fit the instruction cache.
+            const int nown = nvalid > half ? (nvalid - half + 1) >> 1 : 0;
+            uint32_t ra[16], rb[16];
+            if (nown > 0) tmem_ld_32x32_x16r(tmem_acc + (uint32_t)(half * 32), ra);
+            const int sw8 = (lane >> 2) & 1, sw16 = (lane >> 1) & 3;
+#pragma unroll 1
+            for (int k = 0; k < nown; ++k) {
+                const int cc = half + 2 * k, n_c = c.n0 + cc * 32;
+                const float* vec = myvec + k * 128;
+                uint8_t* buf = stage_base + (chunk & 1) * L::CHUNK_BYTES;
+                if (chunk >= 2) {              // the staging buffer used two chunks ago must have been read by TMA
+                    if (lane == 0) tma_store_wait_read<1>();
+                    __syncwarp();
+                }
+                ++chunk;
+                const bool second = n_c >= seg_switch;
+                const float se = second ? se_b : se_a, inv = second ? inv_b : inv_a;
+                uint8_t* row8 = buf + lane * 32;
+                uint8_t* row16 = buf + 1024 + lane * 64;
+                uint8_t* rowr = buf + 3072 + lane * 64;
+                float dot = 0.f;
+                tmem_ld_wait(); tmem_ld_pin16(ra);
+                tmem_ld_32x32_x16r(tmem_acc + (uint32_t)(cc * 32 + 16), rb);
+                if (!(p.debug_nostore & 2)) dot += lsq_piece16<MODE, RT1>(ra, rsv, rtv, vec, se, inv, qlo, qhi, f16, row8, row16, rowr, sw8, sw16, 0);
+                tmem_ld_wait(); tmem_ld_pin16(rb);
+                if (k + 1 < nown) tmem_ld_32x32_x16r(tmem_acc + (uint32_t)((cc + 2) * 32), ra);
+                if (!(p.debug_nostore & 2)) dot += lsq_piece16<MODE, RT1>(rb, rsv, rtv, vec, se, inv, qlo, qhi, f16, row8, row16, rowr, sw8, sw16, 2);
+                if (e.part && m_row0 + lane < p.M && !(p.debug_nostore & 8)) e.part[(long long)(m_row0 + lane) * e.ld_part + (n_c >> 5)] = dot;
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && !(p.debug_nostore & 1)) {
+                    tma_store_5d(&tmQ8, buf, n_c, m_row0, 0, 0, 0);
+                    if (MODE >= 1) tma_store_5d(&tmQ16, buf + 1024, n_c, m_row0, 0, 0, 0);
+                    if (MODE >= 2) tma_store_5d(&tmR16, buf + 3072, n_c, m_row0, 0, 0, 0);
+                    tma_store_commit();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// rowdot[m, s] = sum of the per-chunk partials of segment s, in column order (deterministic)
+__global__ void __launch_bounds__(256)
+rowdot_reduce_kernel(const float* __restrict__ part, int ld_part, long long M, int nseg, int chunks_per_seg, float* __restrict__ rowdot) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * nseg) return;
+    const long long m = i / nseg;
+    const int sg = (int)(i - m * nseg);
+    const float* pp = part + m * ld_part + (long long)sg * chunks_per_seg;
+    float a = 0.f;
+    for (int j = 0; j < chunks_per_seg; ++j) a += pp[j];
+    rowdot[i] = a;
+}
+
 // ------------------------------------------------------------------------------------------ host side
 template <int KIND, int BN, int STAGES, int NA = 1, int OUT_BUFS = 2>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
@@ -976,4 +1333,113 @@ extern "C" int ofq_gemm_ex(int kind, const ofq_operand_t* A, const ofq_operand_t
     }
     if (kind == OFQ_GEMM_I8) { OFQ_DISPATCH(0) } else { OFQ_DISPATCH(1) }
 #undef OFQ_DISPATCH
+}
+
+// ------------------------------------------------------------------------------------------ ofq_gemm_lsq
+template <int BN, int STAGES, int MODE, bool RT1>
+static int launch_gemm_lsq(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmQ8, const CUtensorMap& tmQ16,
+                           const CUtensorMap& tmR16, GemmParams p, const LsqEpi& e, cudaStream_t stream) {
+    constexpr size_t smem = LsqSmem<BN, STAGES>::DYN_BYTES;
+    static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
+    auto kern = gemm_lsq_kernel<BN, STAGES, MODE, RT1>;
+    static bool configured = false;
+    if (!configured) {
+        OFQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int mtiles = (p.M + BM - 1) / BM, ntiles = (p.N + BN - 1) / BN;
+    p.fd_ntiles = make_fastdiv(ntiles); p.fd_mtiles = make_fastdiv(mtiles);
+    const long long tiles = (long long)mtiles * ntiles;
+    OFQ_REQUIRE(tiles <= 0x7fffffff, "ofq_gemm_lsq: too many tiles");
+    const int grid = (int)(tiles < ofq_num_sms() ? tiles : ofq_num_sms());
+    kern<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, tmQ8, tmQ16, tmR16, p, e, (int)tiles, mtiles, ntiles);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// {N, M, 1, 1, 1} map of a quantizer output with a 32-column x 32-row box
+static int make_q_map(CUtensorMap* tm, void* ptr, long long ld, int elem_bytes, bool f16, int M, int N) {
+    OFQ_REQUIRE(reinterpret_cast<uintptr_t>(ptr) % 16 == 0 && (ld * elem_bytes) % 16 == 0,
+                "ofq_gemm_lsq: outputs must be 16-byte aligned with 16-byte-multiple row pitches");
+    const cuuint64_t row_b = (cuuint64_t)ld * elem_bytes;
+    cuuint64_t dims[5] = {(cuuint64_t)N, (cuuint64_t)M, 1, 1, 1};
+    cuuint64_t strides[4] = {row_b, row_b, row_b, row_b};
+    cuuint32_t box[5] = {32, 32, 1, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return ofq_encode_tensor_map_sw(tm, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                    : (f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16),
+                                    5, ptr, dims, strides, box, estr,
+                                    elem_bytes == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+extern "C" int ofq_gemm_lsq(const ofq_operand_t* A, const ofq_operand_t* B, int M, int N, int K, const ofq_vec_t* rs,
+                            const ofq_vec_t* cs, const ofq_vec_t* rt, const ofq_vec_t* ct, const ofq_gemm_lsq_t* q, void* stream) {
+    OFQ_REQUIRE(A && B && q && q->codes && q->s_eff && q->inv_s, "ofq_gemm_lsq: null argument");
+    OFQ_REQUIRE(M > 0 && N > 0 && K > 0 && N % 16 == 0, "ofq_gemm_lsq: extents must be positive, N a multiple of 16");
+    OFQ_REQUIRE(q->period > 0 && q->nseg > 0 && q->seg_len > 0 && q->seg_len % 32 == 0 && (long long)q->nseg * q->seg_len >= N,
+                "ofq_gemm_lsq: segments must be multiples of 32 columns and cover N");
+    OFQ_REQUIRE(!q->rowdot || (q->dot_u && q->workspace), "ofq_gemm_lsq: rowdot needs dot_u and a workspace");
+    OFQ_REQUIRE(A->dual_delta == 0 && !A->mn_major && !B->mn_major, "ofq_gemm_lsq: K-major int8 operands only");
+    OFQ_CHECK_ARCH();
+    GemmParams p;
+    p.M = M; p.N = N;
+    p.kblocks = (K + KBYTES - 1) / KBYTES;
+    p.k2 = 1; p.splits = 1; p.nb1 = p.nb2 = 1;
+    p.a_b1 = p.a_b2 = p.b_b1 = p.b_b2 = p.c_b1 = p.c_b2 = 0;
+    p.a_k2 = p.b_k2 = 0; p.a_dual_delta = 0;
+    p.a_k2mod = p.b_k2mod = 0x7fffffff;
+    p.fd_nbatch = make_fastdiv(1); p.fd_nb1 = make_fastdiv(1); p.fd_splits = make_fastdiv(1);
+    p.fd_kblocks = make_fastdiv(p.kblocks); p.fd_ak2mod = make_fastdiv(p.a_k2mod); p.fd_bk2mod = make_fastdiv(p.b_k2mod);
+    p.rs = make_vec(rs); p.cs = make_vec(cs); p.rt = make_vec(rt); p.ct = make_vec(ct);
+    p.has_rank1 = (rt && rt->ptr) || (ct && ct->ptr);
+    p.atomic = 0; p.ab_fmt = 0; p.a_mn = p.b_mn = 0; p.amax = nullptr;
+    static const int nostore = [] { const char* ev = getenv("OFQ_GEMM_NOSTORE"); return ev ? atoi(ev) : 0; }();
+    p.debug_nostore = nostore;      // measurement only: 1 = no TMA stores, 2 = no epilogue math, 8 = no row-dot partial stores
+    LsqEpi e;
+    e.b4 = q->b4; e.s_eff = q->s_eff; e.inv_s = q->inv_s; e.dot_u = q->rowdot ? q->dot_u : nullptr;
+    e.part = q->rowdot ? q->workspace : nullptr;
+    e.ld_part = (N + 31) / 32;
+    e.nseg = q->nseg; e.seg_len = q->seg_len;
+    e.fd_period = make_fastdiv(q->period); e.fd_seglen = make_fastdiv(q->seg_len);
+    e.qlo = q->qlo; e.qhi = q->qhi;
+    e.has_res = q->res16 != nullptr;
+    e.has16 = q->codes16 != nullptr;
+    e.f16 = q->fmt16 == OFQ_FMT_F16;
+    OFQ_REQUIRE(!e.has_res || e.has16, "ofq_gemm_lsq: the residual is produced together with the 16-bit copy of the codes");
+    // tile width: at most one segment boundary per tile
+    int bn = q->seg_len >= 192 ? 192 : (q->seg_len >= 128 ? 128 : 64);
+    if (N <= 64) bn = 64; else if (N <= 128 && bn > 128) bn = 128;
+    CUtensorMap tmA, tmB, tmQ8, tmQ16, tmR16;
+    int rc = make_operand_map(&tmA, A, 1, M, K, 1, 1, 1, BM);
+    if (rc) return rc;
+    rc = make_operand_map(&tmB, B, 1, N, K, 1, 1, 1, bn);
+    if (rc) return rc;
+    rc = make_q_map(&tmQ8, q->codes, q->ld_codes, 1, false, M, N);
+    if (rc) return rc;
+    tmQ16 = tmQ8; tmR16 = tmQ8;
+    if (e.has16) { rc = make_q_map(&tmQ16, q->codes16, q->ld_codes16, 2, e.f16 != 0, M, N); if (rc) return rc; }
+    if (e.has_res) { rc = make_q_map(&tmR16, q->res16, q->ld_res16, 2, true, M, N); if (rc) return rc; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int mode = e.has_res ? 2 : (e.has16 ? 1 : 0);
+#define OFQ_LSQ_DISPATCH2(BN_, ST_, RT1_)                                                                  \
+    (mode == 2 ? launch_gemm_lsq<BN_, ST_, 2, RT1_>(tmA, tmB, tmQ8, tmQ16, tmR16, p, e, st)                \
+               : (mode == 1 ? launch_gemm_lsq<BN_, ST_, 1, RT1_>(tmA, tmB, tmQ8, tmQ16, tmR16, p, e, st)   \
+                            : launch_gemm_lsq<BN_, ST_, 0, RT1_>(tmA, tmB, tmQ8, tmQ16, tmR16, p, e, st)))
+    // RT1: no per-row offset vector (rt = 1): the rank-1 term is ct[n] itself, one multiply less per element
+#define OFQ_LSQ_DISPATCH(BN_, ST_) (rt1 ? OFQ_LSQ_DISPATCH2(BN_, ST_, true) : OFQ_LSQ_DISPATCH2(BN_, ST_, false))
+    const bool rt1 = !(rt && rt->ptr);
+    switch (bn) {
+        case 192: rc = OFQ_LSQ_DISPATCH(192, 3); break;
+        case 128: rc = OFQ_LSQ_DISPATCH(128, 3); break;
+        default:  rc = OFQ_LSQ_DISPATCH(64, 4); break;
+    }
+#undef OFQ_LSQ_DISPATCH2
+#undef OFQ_LSQ_DISPATCH
+    if (rc) return rc;
+    if (q->rowdot) {
+        const long long n = (long long)M * q->nseg;
+        rowdot_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(e.part, e.ld_part, M, q->nseg, q->seg_len / 32, q->rowdot);
+        OFQ_CUDA(cudaGetLastError());
+    }
+    return 0;
 }

@@ -57,6 +57,12 @@ static std::once_flag g_encode_once;
 int ofq_encode_tensor_map(CUtensorMap* tm, CUtensorMapDataType dtype, int rank, void* addr,
                           const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
                           const cuuint32_t* estr) {
+    return ofq_encode_tensor_map_sw(tm, dtype, rank, addr, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int ofq_encode_tensor_map_sw(CUtensorMap* tm, CUtensorMapDataType dtype, int rank, void* addr,
+                             const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
+                             const cuuint32_t* estr, CUtensorMapSwizzle swizzle) {
     std::call_once(g_encode_once, [] {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -69,7 +75,7 @@ int ofq_encode_tensor_map(CUtensorMap* tm, CUtensorMapDataType dtype, int rank, 
         return OFQ_ERR_CUDA;
     }
     CUresult r = g_encode(tm, dtype, rank, addr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         ofq_set_error("cuTensorMapEncodeTiled failed with CUresult %d (dims %llu,%llu,%llu,%llu,%llu strides %llu,%llu,%llu,%llu box %u,%u)",

@@ -11,6 +11,9 @@ int ofq_check_arch();  // 0 if current device is sm_100, else OFQ_ERR_ARCH (mess
 int ofq_encode_tensor_map(CUtensorMap* tm, CUtensorMapDataType dtype, int rank, void* addr,
                           const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
                           const cuuint32_t* estr);
+int ofq_encode_tensor_map_sw(CUtensorMap* tm, CUtensorMapDataType dtype, int rank, void* addr,
+                             const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
+                             const cuuint32_t* estr, CUtensorMapSwizzle swizzle);
 int ofq_num_sms();
 
 #define OFQ_CUDA(expr)                                                                       \

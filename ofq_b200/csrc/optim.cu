@@ -97,11 +97,12 @@ __global__ void counter_increment_kernel(int* c) { *c += 1; }
 // torch/optim/adamw.py::_single_tensor_adamw element-wise math.
 __device__ __forceinline__ void adamw_elem(float& p, float g, float& m, float& v, const AdamScalars& a, bool frozen) {
     if (frozen) g = 0.f;                                    // cga.py:958 grad * freeze_idx * 0
-    const float p_new0 = p * a.decay;                       // param.mul_(1 - lr * wd)
+    const float p_new0 = __fmul_rn(p, a.decay);             // param.mul_(1 - lr * wd): a rounded product of its own (never
+                                                            // contracted into the update below, in any of the kernels)
     m = fmaf(a.one_m_b1, g - m, m);                         // exp_avg.lerp_(grad, 1 - beta1)
     v = fmaf(a.one_m_b2 * g, g, v * a.beta2);               // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
     const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
-    const float p_new = p_new0 - a.step_size * (m / denom); // param.addcdiv_(exp_avg, denom, value=-step_size)
+    const float p_new = __fmaf_rn(-a.step_size, __fdiv_rn(m, denom), p_new0);   // param.addcdiv_(exp_avg, denom, value=-step_size)
     if (!frozen) p = p_new;                                 // cga.py:1002-1005 restores frozen weights bit-for-bit
 }
 

@@ -3,6 +3,7 @@
 // Every arithmetic step that decides an integer code uses explicit round-to-nearest intrinsics
 // (__fdiv_rn / __fmul_rn / __fsub_rn / __fadd_rn, rintf) so that nvcc cannot contract it into FMAs:
 // codes must be bit-identical to the reference's fp32 op sequence.
+#include <cuda_fp16.h>
 #include "host_util.h"
 #include "ofq_b200.h"
 #include <climits>
@@ -669,7 +670,14 @@ lsq_bwd_stream_kernel(const float* __restrict__ dy, long long lddy, const float*
             if (r < rows) {
                 if (act) {
                     g4[u] = __ldg(reinterpret_cast<const float4*>(dy + (long long)r * lddy + col));
-                    x4[u] = __ldg(reinterpret_cast<const float4*>(x + (long long)r * ldx + col));
+                    if (ACT == OFQ_ACT_RES16) {     // x is the fp16 residual plane of ofq_gemm_lsq: q - v, or -2 / +2 where v was clipped
+                        const uint2 h = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(x) + (long long)r * ldx + col));
+                        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+                        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+                        x4[u] = make_float4(a.x, a.y, c.x, c.y);
+                    } else {
+                        x4[u] = __ldg(reinterpret_cast<const float4*>(x + (long long)r * ldx + col));
+                    }
                 }
                 if (MODE == OFQ_SCALE_PER_ROW) isv[u] = __ldg(s_eff + n * nseg + seg);
                 if (OUT16) r16[u] = o16.rs ? __ldg(o16.rs + n16) : 1.f;
@@ -698,10 +706,17 @@ lsq_bwd_stream_kernel(const float* __restrict__ dy, long long lddy, const float*
             for (int e = 0; e < 4; ++e) {
                 float xa = xx[e], dact = 1.f;
                 if (ACT == OFQ_ACT_GELU) gelu_both(xx[e], &xa, &dact);               // the quantizer saw act(x)
-                const float v = (xa + bb[e]) * ii[e];
-                const bool inside = (v >= qlo) && (v <= qhi);
-                const float q = rintf(fminf(fmaxf(v, qlo), qhi));
-                const float t = gg[e] * (inside ? (q - v) : q);
+                bool inside;
+                float t;
+                if (ACT == OFQ_ACT_RES16) {
+                    inside = fabsf(xa) <= 1.f;
+                    t = gg[e] * (inside ? xa : (xa < 0.f ? qlo : qhi));
+                } else {
+                    const float v = (xa + bb[e]) * ii[e];
+                    inside = (v >= qlo) && (v <= qhi);
+                    const float q = rintf(fminf(fmaxf(v, qlo), qhi));
+                    t = gg[e] * (inside ? (q - v) : q);
+                }
                 o[e] = inside ? gg[e] : 0.f;
                 aft[e] += gg[e];
                 ab4[e] += o[e];
@@ -1480,7 +1495,9 @@ extern "C" int ofq_lsq_bwd_ex(const float* dy, long long lddy, const float* x, l
                 "ofq_lsq_bwd: the fused 16-bit operand needs the streaming layout (columns % 4 == 0, 128-column segment multiples), "
                 "an 8-byte aligned output with a pitch that is a multiple of 4 and a 16-byte aligned cs16");
     OFQ_REQUIRE(!out16 || !rs16 || rs16_period >= rows || rows % rs16_period == 0, "ofq_lsq_bwd: rows must be a multiple of rs16_period");
-    OFQ_REQUIRE(act == OFQ_ACT_NONE || act == OFQ_ACT_GELU, "ofq_lsq_bwd: unknown activation");
+    OFQ_REQUIRE(act == OFQ_ACT_NONE || act == OFQ_ACT_GELU || act == OFQ_ACT_RES16, "ofq_lsq_bwd: unknown activation");
+    OFQ_REQUIRE(act != OFQ_ACT_RES16 || (lsq_bwd_streaming(cols, nseg) && scale_mode == OFQ_SCALE_PER_ROW),
+                "ofq_lsq_bwd: the fp16-residual input is for per-row scales in the streaming layout");
     OFQ_REQUIRE(rows > 0 && cols > 0 && nseg > 0 && cols % nseg == 0 && period > 0, "ofq_lsq_bwd: bad shape");
     const int seg_len = cols / nseg;
     OFQ_REQUIRE(cols % 4 == 0 && seg_len % 4 == 0 && lddy % 4 == 0 && ldx % 4 == 0 && lddx % 4 == 0,
@@ -1511,6 +1528,7 @@ extern "C" int ofq_lsq_bwd_ex(const float* dy, long long lddy, const float* x, l
     } while (0)
         if (scale_mode == OFQ_SCALE_PER_ROW) {
             if (act == OFQ_ACT_GELU) OFQ_LSQ_BWD_STREAM(OFQ_SCALE_PER_ROW, OFQ_ACT_GELU, (uint32_t)period);
+            else if (act == OFQ_ACT_RES16) OFQ_LSQ_BWD_STREAM(OFQ_SCALE_PER_ROW, OFQ_ACT_RES16, (uint32_t)period);
             else OFQ_LSQ_BWD_STREAM(OFQ_SCALE_PER_ROW, OFQ_ACT_NONE, (uint32_t)period);
         } else {
             if (act == OFQ_ACT_GELU) OFQ_LSQ_BWD_STREAM(OFQ_SCALE_PER_COL, OFQ_ACT_GELU, 1u);

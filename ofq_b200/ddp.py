@@ -17,6 +17,9 @@ import torch
 import torch.distributed as dist
 
 
+_ALIGN = 32          # floats
+
+
 class FlatGradAllReduce:
     """`direct=True` (default): the weight-gradient GEMMs of the ofq_b200 layers write straight into the parameter's slice
     of the flat buffer (functional.GRAD_SLOTS -> take()): the slice is handed out as a fresh view that autograd adopts as
@@ -29,12 +32,13 @@ class FlatGradAllReduce:
         self.direct = direct
         self._taken = set()
         dev = self.params[0].device
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
-        self.views = []
-        off = 0
+        # every slice starts on a 128-byte boundary (the dW GEMMs store through TMA: 16-byte aligned rows at least)
+        offs, off = [], 0
         for p in self.params:
-            self.views.append(self.flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+            offs.append(off)
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(offs, self.params)]
         for p, v in zip(self.params, self.views):
             p.grad = v
         self._slot = {p.data_ptr(): i for i, p in enumerate(self.params)}

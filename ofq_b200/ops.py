@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import GemmOut, Operand, Vec, check
+from ._lib import GemmLsq, GemmOut, Operand, Vec, check
 
 GEMM_I8, GEMM_BF16, GEMM_F16 = 0, 1, 2
 FMT_BF16, FMT_F16 = 0, 1
@@ -180,6 +180,30 @@ def gemm(kind: int, a: torch.Tensor, a_strides, b: torch.Tensor, b_strides, out:
           C.byref(A), C.byref(B), C.byref(O), M, N, K, k2, nb1, nb2, splits, rs, cs, rt, ct, _ptr(amax), _st(), tag=tag)
 
 
+def gemm_lsq(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, b4: Optional[torch.Tensor], s2: torch.Tensor, period: int,
+             nseg: int, qlo: int, qhi: int, *, rs=None, cs=None, rt=None, ct=None, fmt16: Optional[int] = None,
+             want_res: bool = False, dot_u: Optional[torch.Tensor] = None):
+    """int8 GEMM a [M, K] x b [N, K]^T whose epilogue is the LSQ quantizer of the product (ofq_gemm_lsq): the fp32 output never
+    exists. s2 = [s_eff, 1 / s_eff] with index (m % period) * nseg + n // (N // nseg). Returns (codes int8 [M, N],
+    codes16 | None, res16 | None, rowdot [M, nseg] | None); res16 is the fp16 residual plane lsq_bwd(act=ACT_RES16) reads."""
+    _cuda(a, b, s2)
+    assert a.dtype == torch.int8 and b.dtype == torch.int8 and a.stride(1) == 1 and b.stride(1) == 1 and N % nseg == 0
+    dev = a.device
+    codes = torch.empty((M, N), dtype=torch.int8, device=dev)
+    c16 = torch.empty((M, N), dtype=_T16[fmt16], device=dev) if fmt16 is not None else None
+    res = torch.empty((M, N), dtype=torch.float16, device=dev) if want_res else None
+    rowdot = torch.empty((M, nseg), dtype=torch.float32, device=dev) if dot_u is not None else None
+    ws = torch.empty((M, (N + 31) // 32), dtype=torch.float32, device=dev) if dot_u is not None else None
+    A = Operand(a.data_ptr(), a.stride(0), 0, 0, 0, 0, 0, 0)
+    B = Operand(b.data_ptr(), b.stride(0), 0, 0, 0, 0, 0, 0)
+    q = GemmLsq(codes.data_ptr(), N, _ptr(c16), N, fmt16 if fmt16 is not None else FMT_F16, _ptr(res), N, _ptr(b4), s2[0].data_ptr(),
+                s2[1].data_ptr(), period, nseg, N // nseg, float(qlo), float(qhi), _ptr(dot_u), _ptr(rowdot), _ptr(ws))
+    nbytes = float(M * K + N * K) + M * N * (1.0 + (2 if c16 is not None else 0) + (2 if res is not None else 0))
+    _call("gemm_lsq", 2 if dot_u is not None else 1, nbytes, 2.0 * M * N * K, _lib.load().ofq_gemm_lsq, C.byref(A), C.byref(B), M, N, K,
+          rs, cs, rt, ct, C.byref(q), _st(), tag=f"M{M} N{N} K{K} lsq")
+    return codes, c16, res, rowdot
+
+
 # ------------------------------------------------------------------------------------------------ quantizers
 def statsq_codes(w: torch.Tensor, bits: int, aft: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
                  want_minmax: bool = False, want_inv: bool = False, want_sf: bool = False, fmt16: Optional[int] = None):
@@ -240,7 +264,7 @@ def lsq_effective_scale(alpha: torch.Tensor, g: float, recip: bool = False):
     return out
 
 
-ACT_NONE, ACT_GELU = 0, 1
+ACT_NONE, ACT_GELU, ACT_RES16 = 0, 1, 2      # ACT_RES16 (lsq_bwd with out16 only): x2d is gemm_lsq's fp16 residual plane
 
 
 def lsq_quant(x2d: torch.Tensor, b4: torch.Tensor, s_eff: torch.Tensor, mode: int, period: int, nseg: int,

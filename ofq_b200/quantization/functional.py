@@ -49,6 +49,8 @@ FUSED16 = os.environ.get("OFQ_FUSED16", "1") != "0"
 # for the QKR path wherever its shape limits hold (head dim 64, <= 208 tokens, C <= 384: DeiT-T / DeiT-S); OFQ_FUSED_ATTN=0
 # keeps the three-kernel path (A/B measurements, bit-identity tests).
 FUSED_ATTN = os.environ.get("OFQ_FUSED_ATTN", "1") != "0"
+# the qkx quantizer as the epilogue of the qkx GEMM (ofq_gemm_lsq); 0 = GEMM -> fp32 qkx -> ofq_lsq_quant (A/B measurements, tests)
+FUSED_QKX = os.environ.get("OFQ_FUSED_QKX", "1") != "0"
 # ... and its backward (ofq_qkr_attn_bwd: logits recomputed, dP = dO v^T, softmax / quantizer backward in one kernel; neither P
 # nor dP in HBM). fp16 mode only; OFQ_FUSED_ATTN_BWD=0 keeps dP GEMM + ofq_softmax_quant_bwd on the saved probabilities.
 FUSED_ATTN_BWD = os.environ.get("OFQ_FUSED_ATTN_BWD", "1") != "0"
@@ -523,20 +525,29 @@ class QKRAttnCoreFn(torch.autograd.Function):
         wqk = ops.wqk_compose(wq, wk, H)
         wqkc, cs_qk, _, ct_qk, _, ics_qk, *wqk16 = ops.statsq_codes(wqk, wbits, aft=x_aft, want_inv=True, fmt16=f16)
         wqk16 = wqk16[0] if wqk16 else None
-        qkx = torch.empty((M, H * C), dtype=torch.float32, device=dev)
-        ops.gemm(GEMM_I8, qx, (C, 0, 0, 0), wqkc, (C, 0, 0, 0), qkx, (H * C, 0, 0), M, H * C, C,
-                 rs=vec(se_x, N), cs=vec(cs_qk), ct=vec(ct_qk))
         g_k = grad_scale_factor(hi, B * C)
         sk2 = ops.lsq_effective_scale(s_k, g_k, recip=True)          # [2, N*H], index n*H + h
         se_k = sk2[0]
-        # ... and, in the same pass, the column term of the logits sum_c x_aft[c] qk[b,d,h,c]  ([M, H]; attention.py:210-213:
-        # S = x_hat . k_hat^T * scale; terms constant along the softmax axis are dropped, they cancel exactly in softmax
-        # and in its gradient)
-        r = ops.lsq_quant(qkx, k_b4, se_k, PER_ROW, N, H, lo, hi, fmt16=f16, dot_u=x_aft.repeat(H))   # codes [M, H*C]
-        if f16 is not None:
-            qk, qk16, ctS = r
+        # The quantizer of qkx, and in the same pass the column term of the logits sum_c x_aft[c] qk[b,d,h,c]  ([M, H];
+        # attention.py:210-213: S = x_hat . k_hat^T * scale; terms constant along the softmax axis are dropped, they cancel
+        # exactly in softmax and in its gradient).
+        fused_qkx = (FUSED_QKX and C % 32 == 0 and TAP is None
+                     and (not need_grad or (f16 is not None and FUSED16 and C % 128 == 0)))       # backward: the streaming fp16 pass
+        qkx = qkx_res = None
+        if fused_qkx:
+            # ... as the EPILOGUE of the qkx GEMM: codes, their fp16 copy and the fp16 residual the backward needs leave the
+            # kernel, the fp32 product x_hat W_qk^T (233 MB per DeiT-S block) is never written or re-read
+            qk, qk16, qkx_res, ctS = ops.gemm_lsq(qx, wqkc, M, H * C, C, k_b4, sk2, N, H, lo, hi, rs=vec(se_x, N), cs=vec(cs_qk),
+                                                  ct=vec(ct_qk), fmt16=f16, want_res=f16 is not None, dot_u=x_aft.repeat(H))
         else:
-            qk, ctS = r
+            qkx = torch.empty((M, H * C), dtype=torch.float32, device=dev)
+            ops.gemm(GEMM_I8, qx, (C, 0, 0, 0), wqkc, (C, 0, 0, 0), qkx, (H * C, 0, 0), M, H * C, C,
+                     rs=vec(se_x, N), cs=vec(cs_qk), ct=vec(ct_qk))
+            r = ops.lsq_quant(qkx, k_b4, se_k, PER_ROW, N, H, lo, hi, fmt16=f16, dot_u=x_aft.repeat(H))   # codes [M, H*C]
+            if f16 is not None:
+                qk, qk16, ctS = r
+            else:
+                qk, ctS = r
         sk2_hn = sk2.view(2, N, H).transpose(1, 2).contiguous()      # [2, H, N]
         se_k_hn = sk2_hn[0]
         ldS = round_up(N, 4)
@@ -576,7 +587,7 @@ class QKRAttnCoreFn(torch.autograd.Function):
             TAP.append(("qkr", dict(x=x2d, x_b4=x_b4, se_x=se_x, qx=qx, wvc=wvc, v_out=v_out, v_b4=v_b4, se_v=se_v, qv=qv, wqkc=wqkc,
                                     qkx=qkx, k_b4=k_b4, se_k=se_k, qk=qk, P=P_tap, se_p=se_p, qp=qp, out=out, B=B, N=N, H=H, C=C)))
         ctx.save_for_backward(xc, wq, wk, x_b4, x_aft, v_b4, v_aft, k_b4, k_aft, qx, sx2, wvc, cs_v, ics_v, v_out, qv, sv2,
-                              wqkc, cs_qk, ics_qk, qkx, qk, sk2, sk2_hn, P, qp, sp2, qx16, qv16, qk16, qp16, wv16, wqk16,
+                              wqkc, cs_qk, ics_qk, qkx if qkx is not None else qkx_res, qk, sk2, sk2_hn, P, qp, sp2, qx16, qv16, qk16, qp16, wv16, wqk16,
                               rowstat, ctS if rowstat is not None else None, wv)
         ctx.cfg = (B, N, C, H, lo, hi, hiu, scale, g_x, g_v, g_k, g_p, ldS, ldq, bv is not None,
                    attn_bias is not None, link)
@@ -673,8 +684,10 @@ class QKRAttnCoreFn(torch.autograd.Function):
         dkaft = torch.zeros_like(k_aft)
         if fused16:
             sc_k = ops.scale_from_max(amax[1:2], v1=cs_qk, v2=se_x, product=True)
+            # (qkx is the fp16 residual plane when the forward quantized in the GEMM epilogue)
             _, ds_k, dkb4, _, a16_k = ops.lsq_bwd(dkhat, qkx, k_b4, se_k, PER_ROW, N, H, lo, hi, g_k, want_aft=False, zero_sum=True,
-                                                  out16=(FMT, cs_qk, se_x, N, sc_k), want_dx=False)
+                                                  out16=(FMT, cs_qk, se_x, N, sc_k), want_dx=False,
+                                                  act=ops.ACT_RES16 if qkx.dtype == torch.float16 else ops.ACT_NONE)
             del dkhat
             # colsum(d qkx) = sum over rows of the masked gradient = d(move_qkx_b4) (its zero-sum form differs from the plain
             # sum by sum_rows d k_hat, which is analytically zero)

@@ -131,6 +131,50 @@ def test_module_forward_backward_identical_with_and_without_fusion(mods, C, H, N
     assert rel_err(outs[0], outs[1]) < 1e-6                   # eval: the unfused path takes the scalar softmax kernel (ulp-level ties)
 
 
+@pytest.mark.parametrize("C,H,N,B", [(384, 6, 198, 4), (128, 2, 40, 3)])
+def test_module_with_quantizing_qkx_epilogue(mods, C, H, N, B):
+    """QAttention_qkreparam with the qkx quantizer as the epilogue of the qkx GEMM (ofq_gemm_lsq, fp16 residual plane for the
+    backward) against GEMM -> fp32 qkx -> quantizer pass: same codes, so the same output up to the summation order of the logits'
+    column term; gradients agree at the rounding level of the fp16 residual (step sizes) and exactly in the mask."""
+    ops, Fn = mods
+    import ofq_b200.quantization as Q
+    from ofq_b200.host.deit import Attention
+    torch.manual_seed(6)
+    mod = Q.QAttention_qkreparam(Attention(C, H, qkv_bias=True), weight_bits=2, input_bits=2, pretrained_initialized=True)
+    with torch.no_grad():
+        for n, p in mod.named_parameters():
+            if n.endswith(".bias") and p.dim() == 1:
+                p.copy_(torch.randn(p.shape) * 0.02)
+    mod = mod.cuda().train()
+    x0 = torch.randn(B, N, C, device="cuda")
+    go = torch.randn(B, N, C, device="cuda")
+    with torch.no_grad():
+        mod(x0)
+    res = {}
+    for fused in (True, False):
+        Fn.FUSED_QKX = fused
+        try:
+            mod.zero_grad(set_to_none=True)
+            x = x0.clone().requires_grad_(True)
+            ops.PROFILE = []
+            y, _ = mod(x)
+            fams = [r[0] for r in ops.PROFILE]
+            ops.PROFILE = None
+            y.backward(go)
+        finally:
+            Fn.FUSED_QKX = True
+            ops.PROFILE = None
+        res[fused] = (y.detach(), x.grad.clone(), {n: p.grad.clone() for n, p in mod.named_parameters() if p.grad is not None}, fams)
+    assert "gemm_lsq" in res[True][3] and "gemm_lsq" not in res[False][3]   # the quantizing epilogue really ran
+    assert res[True][3].count("lsq_quant") == res[False][3].count("lsq_quant") - 1
+    assert rel_err(res[True][0], res[False][0]) < 1e-5
+    gmax = max(v.abs().max().item() for v in res[False][2].values())
+    assert rel_err(res[True][1], res[False][1]) < 1e-4
+    for n in res[False][2]:
+        a, b = res[True][2][n], res[False][2][n]
+        assert rel_err(a, b) < 1e-4 or (a - b).abs().max().item() <= 1e-5 * gmax, f"{n}: {rel_err(a, b):.2e}"
+
+
 @pytest.mark.parametrize("B,N,H,bits", [(3, 198, 6, 2), (4, 198, 3, 4), (2, 40, 2, 3), (150, 198, 6, 2), (2, 129, 1, 2)])
 def test_fused_backward_against_three_kernel_path(mods, B, N, H, bits):
     """ofq_qkr_attn_bwd (logits recomputed, dP in TMEM, softmax / quantizer backward in the same kernel) against

@@ -590,6 +590,62 @@ def test_wqk_compose(ops):
     assert rel_err(dwq.cpu(), wq_.grad) < 1e-6 and rel_err(dwk.cpu(), wk_.grad) < 1e-6
 
 
+# ------------------------------------------------------------------------------------------------ quantizing GEMM epilogue
+@pytest.mark.parametrize("Bt,N,C,H,bits", [(16, 198, 384, 6, 2), (8, 198, 192, 3, 4), (37, 49, 96, 3, 3), (3, 198, 384, 6, 2),
+                                          (1, 50, 128, 2, 2)])
+def test_gemm_lsq_epilogue_is_gemm_then_quantizer(ops, Bt, N, C, H, bits):
+    """ofq_gemm_lsq (the qkx GEMM with the LSQ quantizer as its epilogue, attention.py:200-207) against ofq_gemm followed by
+    ofq_lsq_quant_ex on the fp32 product: codes and their 16-bit copy bit-identical, the logits' column term equal up to fp32
+    summation order, the fp16 residual plane == what the backward formula makes from the fp32 product, and the LSQ backward
+    fed with that plane == the backward fed with the product (same straight-through mask, same gradients)."""
+    torch.manual_seed(100 + C + Bt)
+    M = Bt * N
+    lo, hi = -(1 << (bits - 1)), (1 << (bits - 1)) - 1
+    qx = torch.randint(lo, hi + 1, (M, C), dtype=torch.int8, device="cuda")
+    wc = (torch.randint(lo, hi + 1, (H * C, C), device="cuda") * 2 + 1).to(torch.int8)            # odd StatsQ codes
+    se_x = torch.rand(N, device="cuda") * 0.2 + 0.1
+    cs = torch.rand(H * C, device="cuda") * 0.02 + 0.01
+    ct = torch.randn(H * C, device="cuda") * 0.05
+    b4 = torch.randn(H * C, device="cuda") * 0.05
+    u = torch.randn(H * C, device="cuda") * 0.1
+    alpha = torch.rand(N * H, device="cuda") * 0.5 + 0.2
+    s2 = ops.lsq_effective_scale(alpha, 0.01, recip=True)
+    vec = ops.vec
+    # reference path: GEMM -> fp32 -> quantizer pass
+    y = torch.empty((M, H * C), dtype=torch.float32, device="cuda")
+    ops.gemm(ops.GEMM_I8, qx, (C, 0, 0, 0), wc, (C, 0, 0, 0), y, (H * C, 0, 0), M, H * C, C, rs=vec(se_x, N), cs=vec(cs), ct=vec(ct))
+    fused_dot_ok = C % 128 == 0
+    codes_r, c16_r, dot_r = ops.lsq_quant(y, b4, s2[0], ops.PER_ROW, N, H, lo, hi, fmt16=ops.FMT_F16, dot_u=u)
+    codes, c16, res, dot = ops.gemm_lsq(qx, wc, M, H * C, C, b4, s2, N, H, lo, hi, rs=vec(se_x, N), cs=vec(cs), ct=vec(ct),
+                                        fmt16=ops.FMT_F16, want_res=True, dot_u=u)
+    assert torch.equal(codes, codes_r)
+    assert torch.equal(c16, c16_r) and torch.equal(c16.float(), codes.float())
+    assert rel_err(dot, dot_r) < 1e-5
+    # codes only (the eval path) and bf16 copy
+    codes_e, c16_e, res_e, dot_e = ops.gemm_lsq(qx, wc, M, H * C, C, b4, s2, N, H, lo, hi, rs=vec(se_x, N), cs=vec(cs), ct=vec(ct), dot_u=u)
+    assert torch.equal(codes_e, codes) and c16_e is None and res_e is None and torch.equal(dot_e, dot)
+    c16_b = ops.gemm_lsq(qx, wc, M, H * C, C, b4, s2, N, H, lo, hi, rs=vec(se_x, N), cs=vec(cs), ct=vec(ct), fmt16=ops.FMT_BF16)[1]
+    assert c16_b.dtype == torch.bfloat16 and torch.equal(c16_b.float(), codes.float())
+    # residual plane: q - v inside the clamp range, -2 / +2 outside, v = (y + b4) * (1 / s) as the backward evaluates it
+    inv = s2[1].view(N, H).repeat(Bt, 1).repeat_interleave(C, dim=1)
+    v = (y + b4) * inv
+    inside = (v >= lo) & (v <= hi)
+    expect = torch.where(inside, codes.float() - v, torch.where(v < lo, torch.full_like(v, -2.0), torch.full_like(v, 2.0)))
+    assert torch.equal(res, expect.half())
+    assert 0.005 < (~inside).float().mean().item() < 0.995                   # both regions are exercised
+    # backward through the quantizer from the plane == from the fp32 product
+    if C % 128 == 0:
+        dy = torch.randn(M, H * C, device="cuda")
+        sc4 = torch.tensor([64.0, 1 / 64.0, 0.0, 0.0], device="cuda")
+        o16 = (ops.FMT_F16, cs, se_x, N, sc4)
+        _, ds_a, db4_a, _, a16_a = ops.lsq_bwd(dy, y, b4, s2[0], ops.PER_ROW, N, H, lo, hi, 0.01, want_aft=False, out16=o16, want_dx=False)
+        _, ds_b, db4_b, _, a16_b = ops.lsq_bwd(dy, res, b4, s2[0], ops.PER_ROW, N, H, lo, hi, 0.01, want_aft=False, out16=o16,
+                                               want_dx=False, act=ops.ACT_RES16)
+        assert torch.equal(a16_a, a16_b) and torch.equal(db4_a, db4_b)
+        # step-size gradient: sum of dy * (q - v) with q - v rounded to fp16 (|error| <= 2^-13 per element, no bias)
+        assert rel_err(ds_b, ds_a) < 3e-4
+
+
 # ------------------------------------------------------------------------------------------------ CGA
 @pytest.mark.parametrize("bits,br", [(2, 0.005), (3, 0.005), (4, 0.05)])
 def test_cga_mask_bit_exact(ops, bits, br):
