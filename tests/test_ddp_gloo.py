@@ -42,7 +42,8 @@ def _worker(rank, world, port, out, bucketed=False):
         loss = torch.nn.functional.cross_entropy(model(xs), ys)
         ddp.scale_loss(loss).backward()
         ddp.reduce()
-        grads = ddp.flat.clone()
+        assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(ddp.params, getattr(ddp, 'views', [p.grad for p in ddp.params])))
+        grads = torch.cat([p.grad.flatten() for p in model.parameters()])   # (the flat buffer pads every slice to 128 bytes)
         opt.step()
     out[rank] = (grads, torch.cat([p.detach().flatten() for p in model.parameters()]))
     dist.destroy_process_group()
