@@ -531,7 +531,7 @@ class QKRAttnCoreFn(torch.autograd.Function):
         # The quantizer of qkx, and in the same pass the column term of the logits sum_c x_aft[c] qk[b,d,h,c]  ([M, H];
         # attention.py:210-213: S = x_hat . k_hat^T * scale; terms constant along the softmax axis are dropped, they cancel
         # exactly in softmax and in its gradient).
-        fused_qkx = (FUSED_QKX and C % 32 == 0 and TAP is None
+        fused_qkx = (FUSED_QKX and C % 32 == 0
                      and (not need_grad or (f16 is not None and FUSED16 and C % 128 == 0)))       # backward: the streaming fp16 pass
         qkx = qkx_res = None
         if fused_qkx:
@@ -584,8 +584,13 @@ class QKRAttnCoreFn(torch.autograd.Function):
             P_tap = P
             if P_tap is None and fused_attn:      # debug only: the probabilities of the fused kernel (bit-identical re-run)
                 P_tap = ops.qkr_attn_fwd(qx, qk, qvT, B, N, H, C, se_x, se_k, ctS, scale, se_p, hiu, se_v, v_aft, save_p=True)[2]
+            qkx_tap = qkx
+            if qkx_tap is None:                   # debug only: the product the quantizing epilogue never wrote
+                qkx_tap = torch.empty((M, H * C), dtype=torch.float32, device=dev)
+                ops.gemm(GEMM_I8, qx, (C, 0, 0, 0), wqkc, (C, 0, 0, 0), qkx_tap, (H * C, 0, 0), M, H * C, C,
+                         rs=vec(se_x, N), cs=vec(cs_qk), ct=vec(ct_qk))
             TAP.append(("qkr", dict(x=x2d, x_b4=x_b4, se_x=se_x, qx=qx, wvc=wvc, v_out=v_out, v_b4=v_b4, se_v=se_v, qv=qv, wqkc=wqkc,
-                                    qkx=qkx, k_b4=k_b4, se_k=se_k, qk=qk, P=P_tap, se_p=se_p, qp=qp, out=out, B=B, N=N, H=H, C=C)))
+                                    qkx=qkx_tap, k_b4=k_b4, se_k=se_k, qk=qk, P=P_tap, se_p=se_p, qp=qp, out=out, B=B, N=N, H=H, C=C)))
         ctx.save_for_backward(xc, wq, wk, x_b4, x_aft, v_b4, v_aft, k_b4, k_aft, qx, sx2, wvc, cs_v, ics_v, v_out, qv, sv2,
                               wqkc, cs_qk, ics_qk, qkx if qkx is not None else qkx_res, qk, sk2, sk2_hn, P, qp, sp2, qx16, qv16, qk16, qp16, wv16, wqk16,
                               rowstat, ctS if rowstat is not None else None, wv)

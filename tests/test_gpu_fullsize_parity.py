@@ -370,3 +370,18 @@ def test_teacher_forced_every_block_against_exact_oracle(Fn, cfg):
     # ties are rare events per code, but a block of Swin-T's last stage quantizes 14 M W_qk weights: a good part of the
     # blocks must still be free of any flipped tie and therefore strictly checked
     assert rep["blocks_clean"] >= len(blocks) // 4, rep
+
+
+@pytest.mark.skipif(os.environ.get("OFQ_PARITY_CHILD") == "1", reason="already the bf16x2 child run")
+def test_teacher_forced_parity_with_bf16x2_backward_operands():
+    """The same per-block parity run with the backward GEMM operands as two bf16 planes (OFQ_BWD_MODE=bf16x2, the
+    pre-fp16 default: no range scaling, ~16 mantissa bits) instead of range-scaled fp16. The mode is read at import, so the
+    run happens in a child interpreter; its per-block report lands next to the fp16 one (teacher_forced[bf16x2])."""
+    import subprocess
+    import sys
+    env = dict(os.environ, OFQ_BWD_MODE="bf16x2", OFQ_PARITY_CHILD="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", str(Path(__file__)), "-x", "-q", "-m", "gpu", "-k",
+                        "teacher_forced_every_block and (deit_tiny_qkr_w2a2 or deit_small_qkr_w2a2)"],
+                       env=env, cwd=str(ROOT), capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "2 passed" in r.stdout, r.stdout[-1000:]
