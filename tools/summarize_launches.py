@@ -21,7 +21,10 @@ def family(k):
     m = re.search(r"gemm_tc_kernel<(\d), (\d+), (\d+)(?:, (\d+), (\d+))?>", k)
     if m:
         return f"ofq gemm_tc_kernel<{'i8' if m.group(1) == '0' else '16-bit'}, BN={m.group(2)}{', dual-A' if m.group(4) == '2' else ''}>"
-    m = re.search(r"ofq::(\w+)", k)
+    m = re.search(r"ofq::(?:attn::)?(\w+)", k)
+    if m:
+        return "ofq " + m.group(1)
+    m = re.search(r"attn::(\w+_kernel)", k)
     if m:
         return "ofq " + m.group(1)
     m = re.search(r"<unnamed>::(\w+)", k)
