@@ -21,6 +21,9 @@ def family(k):
     m = re.search(r"gemm_tc_kernel<(\d), (\d+), (\d+)(?:, (\d+), (\d+))?>", k)
     if m:
         return f"ofq gemm_tc_kernel<{'i8' if m.group(1) == '0' else '16-bit'}, BN={m.group(2)}{', dual-A' if m.group(4) == '2' else ''}>"
+    m = re.search(r"gemm_tc_pair_kernel<(\d), (\d+)", k)
+    if m:
+        return f"ofq gemm_tc_pair_kernel<{'i8' if m.group(1) == '0' else '16-bit'}, BN={m.group(2)}>"
     m = re.search(r"ofq::(?:attn::)?(\w+)", k)
     if m:
         return "ofq " + m.group(1)
@@ -64,7 +67,8 @@ with open(dst, "w") as f:
         f.write(f"| {k} | {p['n']} | {p['ns'] / 1e6:.3f} | {100 * p['ns'] / tot:.2f} | {p['ns'] / p['n'] / 1e3:.1f} | {(p['rd'] + p['wr']) / p['n'] / 1e6:.2f} |\n")
 print(open(dst).read()[:7000])
 if len(sys.argv) > 3:
-    fam_map = {"gemm_bf16": "gemm_tc_kernel<16-bit", "gemm_f16": "gemm_tc_kernel<16-bit", "absmax_scale": "ofq absmax_scale_kernel", "gemm_i8": "gemm_tc_kernel<i8", "lsq_bwd": "ofq lsq_bwd_stream_kernel", "lsq_quant": "ofq lsq_quant_vec_kernel",
+    fam_map = {"gemm_bf16": "_kernel<16-bit", "gemm_f16": "_kernel<16-bit", "absmax_scale": "ofq absmax_scale_kernel", "gemm_i8": "_kernel<i8",
+               "qkr_attn_fwd": "ofq qkr_attn_fwd", "qkr_attn_bwd": "ofq qkr_attn_bwd_kernel", "gemm_lsq": "ofq gemm_lsq_kernel", "cga_adamw": "ofq cga_adamw", "adamw_multi": "ofq adamw_multi_kernel", "lsq_bwd": "ofq lsq_bwd_stream_kernel", "lsq_quant": "ofq lsq_quant_vec_kernel",
                "grad_prep": "ofq grad_prep_stream_kernel", "softmax_quant": "ofq softmax_quant_vec_kernel", "softmax_quant_bwd": "ofq softmax_quant_bwd_vec_kernel", "layernorm_bwd": "ofq layernorm_bwd_kernel", "layernorm_fwd": "ofq layernorm_fwd_kernel",
                "codes_to_bf16": "ofq codes_convert_kernel"}
     out = {}
