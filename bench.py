@@ -49,6 +49,10 @@ def parse():
     ap.add_argument("--grad-buffer", default="none", choices=["flat", "none"],
                     help="N = 1 only (N > 1 always exchanges through the flat buffer). flat: gradients live in one flat fp32 buffer "
                          "(ofq_b200.ddp.FlatGradAllReduce); measured no faster than per-parameter gradients at N = 1 (6207 vs 6214-6302 img/s)")
+    ap.add_argument("--kd", default="off", choices=["off", "fp32", "bf16"],
+                    help="knowledge distillation as every reference script trains (--use-kd --kd_hard_and_soft 1, train.py:896-910): a "
+                         "frozen unquantized teacher of the same architecture runs under no_grad (ofq_b200.kd.Teacher; fp32, or bf16 "
+                         "autocast) and the loss is the fused KDLossSoftandHard. Not the headline workload (BASELINE's metric is the QAT step).")
     ap.add_argument("--mode", default="qat", choices=["qat", "cga", "eval"],
                     help="qat: the headline QAT step. cga: BASELINE.json config 5, the CGA fine-tune step (qk_reparam_type=1, "
                          "freeze mask fused into AdamW for every StatsQ weight, boundaryRange 0.005, lr 1e-5). eval: no-grad "
@@ -253,6 +257,12 @@ def main():
         names = Q.deit_qmodule_names(cfg["depth"])
         model = Q.replace_module_by_qmodule_deit(model, Q.make_qconfigs(names, a.bits, a.bits), pretrained_initialized=True,
                                                  qk_reparam=not a.no_qkr, qk_reparam_type=1 if a.mode == "cga" else 0).to(dev)
+    def make_fp_model():          # the KD teacher: the unquantized network of the same architecture (train.py:428-442)
+        if swin:
+            from ofq_b200.host.swin import swin_t
+            return swin_t(num_classes=1000)
+        return DistilledVisionTransformer(num_classes=1000, **cfg)
+
     gen = torch.Generator().manual_seed(1234 + rank)
     B = a.batch
     h_img = torch.randn(B, 3, 224, 224, generator=gen).pin_memory()
@@ -278,6 +288,13 @@ def main():
     if a.mode != "eval" and (world > 1 or a.grad_buffer == "flat"):
         ddp = BucketedGradAllReduce(model, world) if (a.ddp == "bucketed" and world > 1) else FlatGradAllReduce(model.parameters(), world)
     flat = ddp.flat if ddp is not None else None
+    teacher = kd_loss_fn = None
+    if a.kd != "off" and a.mode != "eval":
+        from ofq_b200.kd import Teacher
+        from ofq_b200.quantization.utils import KDLossSoftandHard
+        torch.manual_seed(1234)
+        teacher = Teacher(make_fp_model().to(dev), dtype=torch.bfloat16 if a.kd == "bf16" else None)
+        kd_loss_fn = KDLossSoftandHard()
 
     def step(img, lbl):
         if a.mode == "eval":
@@ -288,7 +305,10 @@ def main():
             opt.zero_grad(set_to_none=True)
         else:
             ddp.zero()
-        if swin:
+        if teacher is not None:
+            out, _ = model(img)
+            loss = kd_loss_fn(out, lbl, teacher(img))
+        elif swin:
             logits, _ = model(img)
             loss = F.cross_entropy(logits, lbl)
         else:
@@ -475,7 +495,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": B * world, "parallelism": f"dp{world}",
                    "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush",
-                   "optimizer": {"qat": "fused AdamW lr 5.47e-4 wd 0.05", "cga": "fused CGA-masked AdamW lr 1e-5 wd 0.05 BR 0.005", "eval": "none"}[a.mode], "cuda_graph": a.graph == "on", "host_model": a.host_model, "ddp": (a.ddp if world > 1 else None), "grad_buffer": a.grad_buffer, "host_enqueue_ms_per_step": host_enqueue_ms, "bwd_mode": bwd_mode,
+                   "optimizer": {"qat": "fused AdamW lr 5.47e-4 wd 0.05", "cga": "fused CGA-masked AdamW lr 1e-5 wd 0.05 BR 0.005", "eval": "none"}[a.mode], "cuda_graph": a.graph == "on", "host_model": a.host_model, "ddp": (a.ddp if world > 1 else None), "grad_buffer": a.grad_buffer, "kd": a.kd, "host_enqueue_ms_per_step": host_enqueue_ms, "bwd_mode": bwd_mode,
                    "quantized_gemm_tflops_per_gpu": flops_step / (ms_total / a.steps * 1e-3) / 1e12},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": (h_img.numel() * 4 + h_lbl.numel() * 8) * world,
                 "d2h_bytes_per_step": 4 * world, "last_loss": last},

@@ -395,6 +395,17 @@ OFQ_API int ofq_cga_adamw(float* p, const float* grad, float* exp_avg, float* ex
                           int rows, int cols, int step, double lr, double beta1, double beta2, double eps,
                           double weight_decay, int bits, double boundary_range, float* rowstat, int* kminmax,
                           uint8_t* mask_out, const int* step_dev, void* stream);
+/* KD losses of the training recipe (reference src/quantization/utils.py:44-77 KLLossSoft / KDLossSoftandHard; train.py:896-910)
+ * and their gradients in one pass over the logits:
+ *   row_loss[b] = CE(z_hard[b], target[b])                                  (z_hard != NULL; nn.CrossEntropyLoss, class indices)
+ *               - sum_k softmax(teacher[b] / T)_k * log_softmax(z_soft[b] / T)_k   (teacher != NULL)
+ *   loss        = mean_b row_loss[b]       (summed in a fixed order)
+ *   dz_hard / dz_soft = d loss / d z_hard, d loss / d z_soft  [B, K]; when z_hard == z_soft (single-output student) the sum
+ *                       of both terms goes to dz_hard.
+ * All logits are dense [B, K] fp32 rows; target int64 [B]. */
+OFQ_API int ofq_kd_loss(const float* z_hard, const float* z_soft, const float* teacher, const long long* target, int B, int K,
+                        float T, float* row_loss, float* loss, float* dz_hard, float* dz_soft, void* stream);
+
 OFQ_API int ofq_counter_increment(int* counter, void* stream);
 /* Multi-tensor plain AdamW (all un-masked parameters of one learning-rate group in ONE launch).
  * table: device array of n_entries 48-byte records

@@ -96,6 +96,7 @@ SIGNATURES = {
     "ofq_layernorm_bwd_max": (_i, [_p, _p, _p, _p, _p, _ll, _i, _p, _p, _p, _p, _p, _p, _p]),
     "ofq_layernorm_bwd_res": (_i, [_p, _p, _p, _p, _p, _ll, _i, _p, _p, _p, _p, _p, _p]),
     "ofq_adamw_multi": (_i, [_p, _i, _i, _i, _d, _d, _d, _d, _p, _p]),
+    "ofq_kd_loss": (_i, [_p, _p, _p, _p, _i, _i, _f, _p, _p, _p, _p, _p]),
     "ofq_cga_adamw_multi": (_i, [_p, _i, _i, _i, _i, _d, _d, _d, _d, _i, _d, _p, _p]),
 }
 EXPORTS = list(SIGNATURES)

@@ -647,6 +647,30 @@ def cga_adamw_multi_(table, n_entries: int, total_blocks: int, total_rowblocks: 
           total_rowblocks, step, lr, beta1, beta2, eps, bits, float(boundary_range), _ptr(step_dev), _st())
 
 
+# ------------------------------------------------------------------------------------------------ KD losses
+def kd_loss(z_hard: Optional[torch.Tensor], z_soft: Optional[torch.Tensor], teacher: Optional[torch.Tensor],
+            target: Optional[torch.Tensor], T: float = 1.0):
+    """mean_b [ CE(z_hard, target) - sum softmax(teacher / T) log_softmax(z_soft / T) ] and its gradients (ofq_kd_loss).
+    Returns (loss scalar tensor, d loss / d z_hard | None, d loss / d z_soft | None); z_hard may be z_soft (single-output student:
+    the summed gradient is returned as the first)."""
+    ref = z_hard if z_hard is not None else z_soft
+    _cuda(ref, teacher)
+    B, K = ref.shape
+    dev = ref.device
+    same = z_hard is not None and z_soft is not None and z_hard.data_ptr() == z_soft.data_ptr()
+    row = torch.empty(B, dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    dzh = torch.empty((B, K), dtype=torch.float32, device=dev) if z_hard is not None else None
+    dzs = torch.empty((B, K), dtype=torch.float32, device=dev) if (teacher is not None and not same) else None
+    for t in (z_hard, z_soft, teacher):
+        assert t is None or (t.is_contiguous() and t.dtype == torch.float32 and tuple(t.shape) == (B, K))
+    assert target is None or (target.dtype == torch.int64 and target.is_contiguous() and target.numel() == B)
+    _call("kd_loss", 2, 4.0 * B * K * (int(z_hard is not None) * 2 + int(teacher is not None) * 3), 0, _lib.load().ofq_kd_loss,
+          _ptr(z_hard), _ptr(z_soft), _ptr(teacher), _ptr(target), B, K, float(T), row.data_ptr(), loss.data_ptr(), _ptr(dzh),
+          _ptr(dzs), _st())
+    return loss, dzh, dzs
+
+
 # ------------------------------------------------------------------------------------------------ LayerNorm
 def layernorm_fwd(x2d: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, add: Optional[torch.Tensor] = None):
     """(y, mean, rstd) of nn.LayerNorm over the rows of x2d; with `add` [rows, cols] (cols <= 512): (x2d + add, y, mean, rstd),

@@ -514,3 +514,22 @@ def cga_masked_step(w: Tensor, grad: Tensor, m: Tensor, v: Tensor, step: int, lr
         adamw_reference(w, g, m, v, step, lr, beta1, beta2, eps, wd)
         w.copy_(w * (1 - f) + stash)
         return f
+
+
+# ----------------------------------------------------------------------------------------------- KD losses (f2)
+def kl_loss_soft(output, target, T: float = 1.0, reduction: str = "mean"):
+    """KLLossSoft.forward (src/quantization/utils.py:44-58): soft-target cross entropy -sum softmax(t/T) * log_softmax(o/T);
+    tuples (the distilled student / the training-mode teacher) contribute their FIRST element."""
+    output = output[0] if isinstance(output, tuple) else output
+    target = target[0] if isinstance(target, tuple) else target
+    output, target = output / T, target / T
+    loss = -torch.sum(torch.softmax(target, dim=1) * torch.log_softmax(output, dim=1), dim=1)
+    return loss.mean() if reduction == "mean" else (loss.sum() if reduction == "sum" else loss)
+
+
+def kd_loss_soft_and_hard(output, hard_target, soft_target):
+    """KDLossSoftandHard.forward (src/quantization/utils.py:60-77): hard CE on the class head + soft CE of the distillation head
+    against the teacher (both on the same logits for a single-output student)."""
+    if isinstance(output, tuple):
+        return kl_loss_soft(output[1], soft_target) + torch.nn.functional.cross_entropy(output[0], hard_target)
+    return kl_loss_soft(output, soft_target) + torch.nn.functional.cross_entropy(output, hard_target)

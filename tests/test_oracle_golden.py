@@ -206,3 +206,27 @@ def test_swin_step(qkr):
         assert (mine - ref).abs().max().item() <= 1e-4 * scale + 1e-10, name
         n += 1
     assert n > 80
+
+
+# ------------------------------------------------------------------------------------------------ KD losses (f2)
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_kd_losses_match_reference_classes(tag):
+    """oracle.kl_loss_soft / kd_loss_soft_and_hard against the reference's KLLossSoft / KDLossSoftandHard
+    (src/quantization/utils.py:44-77), values and gradients (tests/golden/make_golden_kd.py)."""
+    g = load_golden("kd_loss")
+    cls = g[f"{tag}.cls"].clone().requires_grad_(True)
+    dist = g[f"{tag}.dist"].clone().requires_grad_(True)
+    teacher, teacher_dist, y = g[f"{tag}.teacher"], g[f"{tag}.teacher_dist"], g[f"{tag}.y"].long()
+    loss = O.kd_loss_soft_and_hard((cls, dist), y, (teacher, teacher_dist))
+    loss.backward()
+    assert torch.equal(loss.detach(), g[f"{tag}.sh_tuple.loss"])
+    assert torch.equal(cls.grad, g[f"{tag}.sh_tuple.dcls"]) and torch.equal(dist.grad, g[f"{tag}.sh_tuple.ddist"])
+    cls.grad = None
+    loss = O.kd_loss_soft_and_hard(cls, y, teacher)
+    loss.backward()
+    assert torch.equal(loss.detach(), g[f"{tag}.sh_single.loss"]) and torch.equal(cls.grad, g[f"{tag}.sh_single.dcls"])
+    for T in (1.0, 2.5):
+        cls.grad = None
+        loss = O.kl_loss_soft((cls, dist), (teacher, teacher_dist), T=T)
+        loss.backward()
+        assert torch.equal(loss.detach(), g[f"{tag}.soft_T{T}.loss"]) and torch.equal(cls.grad, g[f"{tag}.soft_T{T}.dcls"])
