@@ -152,4 +152,6 @@ class CGAAdamW(torch.optim.Optimizer):
                 ops.cga_adamw_multi_(table, n, blocks, rowblocks, numel, self._host_step, group["lr"], b1, b2, group["eps"],
                                      self.wq_bitw, self.boundary_range, step_dev=self._step_dev)
                 self.launches += 3
+        from . import prologue
+        prologue.weights_changed()         # the kernels wrote the parameters through raw pointers
         return loss

@@ -11,6 +11,7 @@ from functools import partial
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from .layers import LayerNorm
 
@@ -66,8 +67,9 @@ class Attention(nn.Module):
         B, N, C = x.shape
         qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
         q, k, v = qkv.unbind(0)
-        attn = self.attn_drop(((q @ k.transpose(-2, -1)) * self.scale).softmax(dim=-1))
-        x = (attn @ v).transpose(1, 2).reshape(B, N, C)
+        # unquantized attention (only the KD teacher and un-swapped hosts run it): the library's fused kernel
+        x = F.scaled_dot_product_attention(q, k, v, dropout_p=self.attn_drop.p if self.training else 0.0, scale=self.scale)
+        x = x.transpose(1, 2).reshape(B, N, C)
         return self.proj_drop(self.proj(x)), None
 
 

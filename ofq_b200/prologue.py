@@ -26,6 +26,30 @@ from . import _lib
 ACTIVE: Optional["StepPrologue"] = None
 ENABLED = os.environ.get("OFQ_PROLOGUE", "1") != "0"          # tests / A-B measurements switch the whole mechanism off here
 
+# Bumped by optimizers that write parameters through raw pointers (CGAAdamW: torch's per-tensor version counters do not see
+# those writes). Together with the version counters it forms the "weights changed" signature of a prologue.
+WEIGHT_EPOCH = 0
+
+
+def weights_changed() -> None:
+    """Tell every prologue that parameters were modified behind autograd's back (raw-pointer kernels, `p.data` tricks)."""
+    global WEIGHT_EPOCH
+    WEIGHT_EPOCH += 1
+
+
+def current_generation():
+    """(prologue, generation) when the running forward is being served from persistent prologue buffers, else None: what an
+    autograd node stores to detect, in its backward, that a later forward re-produced those buffers for OTHER weights."""
+    p = ACTIVE
+    return (p, p.generation) if (p is not None and p.fresh) else None
+
+
+def check_generation(token) -> None:
+    if token is not None and token[0].generation != token[1]:
+        raise RuntimeError("ofq_b200: this graph saved weight codes / step sizes that live in the step prologue's persistent buffers, "
+                           "and a later forward re-produced them after the weights changed; run backward before the next "
+                           "optimizer step + forward, or disable the prologue (OFQ_PROLOGUE=0) for such graphs")
+
 
 class _Job:
     __slots__ = ("key", "tensors", "out", "used", "meta")
@@ -41,6 +65,18 @@ class StepPrologue:
         self.dirty = True
         self.tables = None
         self.launches = 0
+        self.generation = 0        # bumped whenever the buffers are re-produced for changed weights
+        self._sig = None           # weights signature of the last production
+        self.cache_hits = 0
+
+    def _signature(self):
+        v = 0
+        for d in (self.scale, self.statsq, self.wqk):
+            for j in d.values():
+                for t in j.tensors:
+                    if t is not None:
+                        v += t._version
+        return (WEIGHT_EPOCH, v)
 
     def __deepcopy__(self, memo):
         # copy.deepcopy(model) (e.g. timm's ModelEmaV2): the copy gets a prologue of its own; jobs hold raw pointers of
@@ -153,8 +189,20 @@ class StepPrologue:
         for d in (self.scale, self.statsq, self.wqk):       # a job must still describe live storage of the same layout
             for j in d.values():
                 j.used = False
+        rebuilt = self.dirty
         if self.dirty:
             self._build()
+        sig = self._signature()
+        if sig != self._sig:
+            self.generation += 1
+        elif not rebuilt and not torch.is_grad_enabled():
+            # inference with unchanged weights (same optimizer epoch, same version counters, same registered jobs): the
+            # persistent buffers still hold this model's codes / W_qk / step sizes - nothing to launch. (Weights modified
+            # through `p.data` or foreign raw-pointer kernels are invisible to both counters: call weights_changed().)
+            self.cache_hits += 1
+            self.fresh = True
+            return
+        self._sig = sig
         lib = _lib.load()
         st = torch.cuda.current_stream().cuda_stream
         tb = self.tables

@@ -14,7 +14,7 @@ from typing import Optional
 
 import torch
 
-from .. import ops
+from .. import ops, prologue
 from ..ops import ACT_GELU, ACT_NONE, FMT_BF16, FMT_F16, GEMM_BF16, GEMM_F16, GEMM_I8, PER_COL, PER_ROW, round_up, vec
 
 
@@ -231,10 +231,12 @@ class QLinearFn(torch.autograd.Function):
             TAP.append(("qlinear", dict(x=x2d, b4=b4, se=se, period=P, act=act, qx=qx, wc=wc, colscale=colscale, out=out)))
         ctx.save_for_backward(xc, qx, wc, colscale, inv_cs, se2, b4, aft, qx16, wc16, weight)
         ctx.cfg = (P, lo, hi, g, bias is not None, act, link, role)
+        ctx.pro_gen = prologue.current_generation()
         return out.view(*x.shape[:-1], Nout)
 
     @staticmethod
     def backward(ctx, dY):
+        prologue.check_generation(ctx.pro_gen)
         xc, qx, wc, colscale, inv_cs, se2, b4, aft, qx16, wc16, weight = ctx.saved_tensors
         P, lo, hi, g, has_bias, act, link, role = ctx.cfg
         wkw = {"wc16": wc16} if (F16 and wc16 is not None) else {}
@@ -596,12 +598,14 @@ class QKRAttnCoreFn(torch.autograd.Function):
                               rowstat, ctS if rowstat is not None else None, wv)
         ctx.cfg = (B, N, C, H, lo, hi, hiu, scale, g_x, g_v, g_k, g_p, ldS, ldq, bv is not None,
                    attn_bias is not None, link)
+        ctx.pro_gen = prologue.current_generation()
         if link is not None:
             link.cs, link.se, link.sc = se_v, se_p, None
         return out
 
     @staticmethod
     def backward(ctx, dO):
+        prologue.check_generation(ctx.pro_gen)
         (xc, wq, wk, x_b4, x_aft, v_b4, v_aft, k_b4, k_aft, qx, sx2, wvc, cs_v, ics_v, v_out, qv, sv2, wqkc, cs_qk, ics_qk,
          qkx, qk, sk2, sk2_hn, P, qp, sp2, qx16, qv16, qk16, qp16, wv16, wqk16, rowstat, ctS, wv) = ctx.saved_tensors
         B, N, C, H, lo, hi, hiu, scale, g_x, g_v, g_k, g_p, ldS, ldq, has_bv, has_bias, link = ctx.cfg

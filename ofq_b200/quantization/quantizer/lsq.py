@@ -106,6 +106,12 @@ class _Lsq8(_LsqBase):
 class LsqQuantizerWeight(_Lsq8):
     """lsq.py:20-109: per-output-row learned step size of the 8-bit head weight."""
 
+    def __init__(self, bit=8, all_positive=False, per_channel=True, learnable=True, **kwargs):
+        if not per_channel or all_positive:
+            # the reference also has a scalar-step form and a 4x unsigned init (lsq.py:72-101); no OFQ recipe uses them
+            raise NotImplementedError("LsqQuantizerWeight: only the per-row signed form (per_channel=True, all_positive=False) is built")
+        super().__init__(bit, all_positive, per_channel, learnable)
+
     def forward(self, x):
         if not self.initialized_alpha:
             self._set_s(2 * x.detach().abs().mean(dim=-1) / (self.thd_pos ** 0.5))
@@ -125,6 +131,8 @@ class LsqQuantizer4Conv2d(_Lsq8):
     """lsq.py:384-446: per-output-channel step size of the 8-bit patch-embed conv weight."""
 
     def __init__(self, bit=8, all_positive=False, per_channel=True, learnable=True, **kwargs):
+        if not per_channel or all_positive:
+            raise NotImplementedError("LsqQuantizer4Conv2d: only the per-output-channel signed form is built (lsq.py:419-437)")
         super().__init__(bit, False, per_channel, learnable)
 
     def forward(self, x):

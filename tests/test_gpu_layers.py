@@ -285,6 +285,65 @@ def test_step_prologue_matches_per_layer_path(Q):
         opt.step()                                  # weights move: the next forward must see the new codes
 
 
+def test_prologue_inference_cache_and_stale_graph_detection(Q):
+    """(1) Inference with unchanged weights re-uses the prologue's persistent buffers (no StatsQ / W_qk / step-size launches);
+    an optimizer step (CGAAdamW writes through raw pointers and bumps prologue.WEIGHT_EPOCH; torch optimizers bump the
+    version counters) invalidates it. (2) A graph whose saved weight codes were overwritten by a later forward after the
+    weights changed refuses to run its backward instead of silently using the new codes."""
+    from ofq_b200 import ops
+    from ofq_b200.cga import CGAAdamW, param_groups_weight_decay
+    from ofq_b200.host.deit import DistilledVisionTransformer
+    torch.manual_seed(45)
+    depth = 2
+    model = DistilledVisionTransformer(embed_dim=128, depth=depth, num_heads=2, num_classes=10)
+    model = Q.replace_module_by_qmodule_deit(model, Q.make_qconfigs(Q.deit_qmodule_names(depth), 2, 2),
+                                             pretrained_initialized=True, qk_reparam=True).cuda()
+    img = torch.randn(3, 3, 224, 224, device="cuda")
+    lbl = torch.tensor([1, 5, 7], device="cuda")
+    model.eval()
+    pro = model._ofq_prologue
+
+    def infer():
+        l0 = ops.LAUNCHES
+        with torch.no_grad():
+            out = model(img)[0].clone()
+        return out, ops.LAUNCHES - l0
+
+    infer(); infer()                                   # creates the step sizes, registers the jobs
+    out_a, n_a = infer()
+    hits = pro.cache_hits
+    out_b, n_b = infer()
+    assert pro.cache_hits == hits + 1 and n_b <= n_a and torch.equal(out_a, out_b)
+    # a training step changes the weights: the next inference re-produces the codes and sees the new weights
+    model.train()
+    opt = CGAAdamW(param_groups_weight_decay(model, 0.05, model.no_weight_decay()), lr=1e-2)
+    (cls, dst), _ = model(img)
+    (F.cross_entropy(cls, lbl) + F.cross_entropy(dst, lbl)).backward()
+    opt.step()
+    model.eval()
+    hits = pro.cache_hits
+    out_c, n_c = infer()
+    assert pro.cache_hits == hits and n_c > n_b and not torch.equal(out_c, out_b)
+    out_d, _ = infer()
+    assert pro.cache_hits == hits + 1 and torch.equal(out_c, out_d)
+    with torch.no_grad():                              # a torch-side in-place update is seen through the version counters
+        model.blocks[0].mlp.fc1.weight.mul_(1.01)
+    hits = pro.cache_hits
+    infer()
+    assert pro.cache_hits == hits
+    # stale graph: forward, optimizer step, ANOTHER forward (re-produces the buffers), then the first graph's backward
+    model.train()
+    (cls, dst), _ = model(img)
+    loss_old = F.cross_entropy(cls, lbl) + F.cross_entropy(dst, lbl)
+    model.zero_grad(set_to_none=True)
+    (cls2, dst2), _ = model(img)
+    (F.cross_entropy(cls2, lbl) + F.cross_entropy(dst2, lbl)).backward()
+    opt.step()
+    model(img)
+    with pytest.raises(RuntimeError, match="step prologue"):
+        loss_old.backward()
+
+
 def test_flat_gradient_buffer_direct_slots_and_zero_arena(Q):
     """ddp.FlatGradAllReduce(direct=True): the dW GEMMs of the quantized layers accumulate straight into the flat gradient
     buffer (autograd adopts the slice as .grad: no gather copy, no per-weight zero fill), and the tiny scratch vectors of the
