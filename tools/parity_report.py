@@ -22,8 +22,9 @@ for f in sorted(glob.glob(str(src / "fullsize_parity_*.json"))):
                           f"{mism} of {numel} |")
         else:
             clean, dirty = v["blocks_clean"], v["blocks_with_flipped_tie"]
-            rows_t.append(f"| {cfg} | {mode} | {clean} / {clean + dirty} | {v['worst_clean_block_out']:.1e} | "
-                          (f"{v['worst_clean_grad']:.1e} ({v['worst_clean_grad_name']})" if v['worst_clean_grad_name'] else "every gradient within 1e-5 of max abs(g)") + f" | {v['flipped_ties']} |")
+            g = (f"{v['worst_clean_grad']:.1e} ({v['worst_clean_grad_name']})" if v["worst_clean_grad_name"]
+                 else "every gradient within 1e-5 of max abs(g)")
+            rows_t.append(f"| {cfg} | {mode} | {clean} / {clean + dirty} | {v['worst_clean_block_out']:.1e} | {g} | {v['flipped_ties']} |")
 md = ["# Full-size parity against the reference (depth-12 DeiT-T / DeiT-S, Swin-T real dims; batch 8 fixtures)\n",
       "Written by `tests/test_gpu_fullsize_parity.py` on a B200 (`gpurun_out/fullsize_parity_*.json`), tabulated by "
       "`tools/parity_report.py`. Goldens: `tests/golden/full_*.npz`, generated from the unmodified reference by "
