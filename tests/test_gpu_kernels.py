@@ -193,9 +193,15 @@ def test_lsq_gelu_fused_and_fp16_copy(ops, cols):
     a_gpu = torch.nn.functional.gelu(dev(h.detach())).cpu()
     ref_gpu = O.lsq_codes_rows(a_gpu + b4.detach(), s.detach(), bit, True)
     mine = codes.cpu().int().view(B, N, cols)
-    assert (mine != ref_gpu).float().mean() < 1e-5
-    ref_cpu = O.lsq_codes_rows(xs.detach(), s.detach(), bit, True)
-    assert (mine != ref_cpu).float().mean() < 1e-4
+    # ... every mismatch classified: the reference's own pre-round value sits within 2e-5 * max(1, |v|) of a rounding boundary
+    # k + 1/2 (a proven tie: erf / quotient evaluated in another order), nothing else may differ
+    s_rows = se.cpu().view(1, N, 1)                      # effective step sizes (bit-exact against the oracle, tested above)
+    for ref_codes, act_ref in ((ref_gpu, a_gpu), (O.lsq_codes_rows(xs.detach(), s.detach(), bit, True), a.detach())):
+        bad = mine != ref_codes
+        if bad.any():
+            v = ((act_ref + b4.detach()) / s_rows)[bad]
+            assert ((v - torch.floor(v) - 0.5).abs() <= 2e-5 * v.abs().clamp(min=1.0)).all(), "a code differs away from a rounding tie"
+            assert (mine[bad] - ref_codes[bad]).abs().max() <= 1
     cs = torch.rand(cols) + 0.5
     dx, ds, db4, daft, sc = ops.lsq_bwd(dev(dy).view(B * N, cols), hd, dev(b4.detach()), se, ops.PER_ROW, N, 1, lo, hi, g,
                                         act=ops.ACT_GELU, next_scale=(dev(cs), se, 1.0, True))
@@ -476,8 +482,8 @@ def test_softmax_quant_forward(ops, N, H, bit):
     if bad.any():
         se_c = se.cpu().view(1, 1, N, 1)
         v = (prob_ref / se_c)[bad]
-        assert ((v - torch.floor(v) - 0.5).abs() < 1e-4).all()
-    assert bad.float().mean() < 1e-4
+        assert ((v - torch.floor(v) - 0.5).abs() <= 2e-5 * v.abs().clamp(min=1.0)).all()     # proven ties only
+        assert (mine[bad] - ref2[bad]).abs().max() <= 1
     assert rel_err(rowsum.cpu().view(B, H, N), ref_codes.float().sum(-1) * se.cpu().view(1, 1, N)) < 1e-6
 
 
