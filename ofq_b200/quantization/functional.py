@@ -350,6 +350,60 @@ class ImgLsqFn(torch.autograd.Function):
         return (dx.view_as(xc) if ctx.needs_input_grad[0] else None), db4, daft, ds, None, None
 
 
+class HeadLinearFn(torch.autograd.Function):
+    """LSQ_QLinear4head.forward (qlinear.py:193-238), the 8-bit classifier heads, on the integer path:
+    move_b4 -> LsqQuantizer4head_input (ONE learned step, lsq.py:448-513) -> move_aft on the input, LsqQuantizerWeight (one
+    learned step per output row, lsq.py:20-109) on the weight, both as int8 codes, one exact int8 GEMM with the step sizes and
+    the folded shift / bias term in its epilogue. Backward: the fp16 (or bf16x2) GEMM pair of every other linear layer, then the
+    LSQ backward of both quantizers (straight-through masks, step-size gradients). Signed 8-bit only (codes must fit int8)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, b4, aft, s_x, s_w, bits: int):
+        Nout, K = weight.shape
+        xc = x.contiguous()
+        x2d = xc.view(-1, K)
+        M = x2d.shape[0]
+        lo, hi = levels(bits, False)
+        g_x = grad_scale_factor(hi, x2d.numel())
+        g_w = grad_scale_factor(hi, K)
+        sx2 = ops.lsq_effective_scale(s_x, g_x, recip=True)          # [2, 1]
+        sw2 = ops.lsq_effective_scale(s_w, g_w, recip=True)          # [2, Nout]
+        need_grad = any(ctx.needs_input_grad)
+        f16 = FMT if (F16 and need_grad) else None
+        qx16 = wc16 = None
+        r = ops.lsq_quant(x2d, b4, sx2[0], PER_ROW, 1, 1, lo, hi, fmt16=f16)
+        qx, qx16 = r if f16 is not None else (r, None)
+        zero_k = ops.scratch_zeros(K, x.device)
+        r = ops.lsq_quant(weight, zero_k, sw2[0], PER_ROW, Nout, 1, lo, hi, fmt16=f16)
+        wc, wc16 = r if f16 is not None else (r, None)
+        # out = se_x * se_w[n] * (qx . wc[n]) + se_w[n] * (aft . wc[n]) + bias[n]
+        colterm = torch.addcmul(bias, ops.codes_rowdot(wc, 1, aft).view(-1), sw2[0])
+        out = torch.empty((M, Nout), dtype=torch.float32, device=x.device)
+        ops.gemm(GEMM_I8, qx, (K, 0, 0, 0), wc, (K, 0, 0, 0), out, (Nout, 0, 0), M, Nout, K, rs=vec(sx2[0], 1), cs=vec(sw2[0]), ct=vec(colterm))
+        ctx.save_for_backward(xc, weight, b4, aft, qx, wc, sx2, sw2, qx16, wc16)
+        ctx.cfg = (lo, hi, g_x, g_w)
+        return out.view(*x.shape[:-1], Nout)
+
+    @staticmethod
+    def backward(ctx, dY):
+        xc, weight, b4, aft, qx, wc, sx2, sw2, qx16, wc16 = ctx.saved_tensors
+        lo, hi, g_x, g_w = ctx.cfg
+        Nout, K = weight.shape
+        x2d = xc.view(-1, K)
+        M = x2d.shape[0]
+        dY2d = dY.reshape(M, Nout)
+        if not dY2d.is_contiguous():
+            dY2d = dY2d.contiguous()
+        dxhat = torch.empty((M, K), dtype=torch.float32, device=dY.device)
+        dwhat, dbias, _ = _linear_backward(dY2d, qx, wc, (sw2[0], sw2[1]), sx2, 1, aft, dxhat, False, qx16,
+                                           **({"wc16": wc16} if (F16 and wc16 is not None) else {}))
+        dx, ds_x, db4, daft = ops.lsq_bwd(dxhat, x2d, b4, sx2[0], PER_ROW, 1, 1, lo, hi, g_x)
+        zero_k = ops.scratch_zeros(K, dY.device)
+        dW, ds_w, _, _ = ops.lsq_bwd(dwhat, weight, zero_k, sw2[0], PER_ROW, Nout, 1, lo, hi, g_w, want_aft=False)
+        ops.side_join()
+        return dx.view_as(xc), dW, dbias, db4, daft, ds_x, ds_w, None
+
+
 class PatchEmbedFn(torch.autograd.Function):
     """The 8-bit patch-embedding convolution (qlinear.py:138-191) with stride = kernel as integer GEMMs on the tensor cores:
     move_b4 -> LsqQuantizer4img -> move_aft on the image (lsq.py:306-382, qbias.py:15-23), im2col of the int8 CODES, and

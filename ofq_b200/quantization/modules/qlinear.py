@@ -170,7 +170,8 @@ class LSQ_QConv2d(nn.Conv2d):
 
 
 class LSQ_QLinear4head(nn.Linear):
-    """qlinear.py:193-252: the 8-bit classifier heads (torch-composed)."""
+    """qlinear.py:193-252: the 8-bit classifier heads: int8 tensor-core path once the step
+    sizes exist, the op-for-op torch composition for the initialising forward and for shapes / options outside that path."""
 
     def __init__(self, *kargs, m: nn.Linear, weight_bits=8, input_bits=8, aq_learnable=True, wq_learnable=True,
                  symmetric=True, weight_channelwise=True, input_channelwise=True, weight_quant_method="statsq",
@@ -192,7 +193,18 @@ class LSQ_QLinear4head(nn.Linear):
         self.move_b4 = LearnableBias(self.weight.shape[1])
         self.move_aft = LearnableBias(self.weight.shape[1])
 
+    def _native(self, input) -> bool:
+        """The int8 tensor-core path (functional.HeadLinearFn): CUDA fp32, signed 8-bit codes, both step sizes already created
+        (the first forward initialises them from the data, lsq.py:72-101 / 476-486) and TMA-legal pitches."""
+        return (input.is_cuda and input.dtype == torch.float32 and self.symmetric and self.weight_bits == 8 and self.input_bits == 8
+                and self.input_quant_fn.initialized_alpha and self.lsqw_fn.initialized_alpha
+                and self.weight.shape[0] % 8 == 0 and self.weight.shape[1] % 16 == 0 and input.shape[-1] == self.weight.shape[1])
+
     def forward(self, input):
+        if self._native(input):
+            from ..functional import HeadLinearFn
+            return HeadLinearFn.apply(input, self.weight, self.bias, self.move_b4.bias, self.move_aft.bias,
+                                      self.input_quant_fn.s, self.lsqw_fn.s, self.weight_bits)
         weight = self.lsqw_fn(self.weight)
         input = self.move_aft(self.input_quant_fn(self.move_b4(input)))
         out = F.linear(input, weight)

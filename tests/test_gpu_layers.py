@@ -344,6 +344,49 @@ def test_prologue_inference_cache_and_stale_graph_detection(Q):
         loss_old.backward()
 
 
+@pytest.mark.parametrize("B,K,Nout", [(16, 384, 1000), (128, 192, 1000), (3, 64, 24)])
+def test_head_int8_path_matches_torch_composition(Q, B, K, Nout):
+    """LSQ_QLinear4head (8-bit classifier head): the int8 tensor-core path (functional.HeadLinearFn) against the op-for-op torch
+    composition of qlinear.py:193-238 it replaces (which the tiny-DeiT goldens pin to the reference): output <= 1e-5, every
+    gradient (input, both shifts, the scalar input step, weight, per-row weight steps, bias) <= 1e-3."""
+    from ofq_b200 import ops
+    from ofq_b200.quantization.modules import qlinear as QL
+    torch.manual_seed(46)
+    lin = nn.Linear(K, Nout)
+    mod = QL.LSQ_QLinear4head(m=lin, weight_quant_method="lsq", pretrained_initialized=True).cuda()
+    with torch.no_grad():
+        mod.move_b4.bias.normal_(0, 0.05)
+        mod.move_aft.bias.normal_(0, 0.05)
+    x0 = torch.randn(B, K, device="cuda")
+    go = torch.randn(B, Nout, device="cuda")
+    with torch.no_grad():
+        mod(x0)                                        # creates both step sizes (torch composition)
+    assert mod._native(x0)
+    res = []
+    for native in (True, False):
+        mod.zero_grad(set_to_none=True)
+        x = x0.clone().requires_grad_(True)
+        l0 = ops.LAUNCHES
+        if native:
+            y = mod(x)
+        else:
+            w = mod.lsqw_fn(mod.weight)
+            y = F.linear(mod.move_aft(mod.input_quant_fn(mod.move_b4(x))), w) + mod.bias
+        n = ops.LAUNCHES - l0
+        y.backward(go)
+        res.append((y.detach(), x.grad.clone(), {k: p.grad.clone() for k, p in mod.named_parameters()}, n))
+    assert res[0][3] > 0 and res[1][3] == 0                        # the native path really ran the C-ABI kernels
+    assert rel_err(res[0][0], res[1][0]) < 1e-5
+    assert rel_err(res[0][1], res[1][1]) < 1e-3
+    # the scalar input step's gradient is ONE random-walk sum g * sum dx_hat * (q - v) over B*K elements: its error budget is 1e-3
+    # of the walk's own scale g * ||dx||_2 (the sum itself can come out arbitrarily close to zero)
+    walk = res[1][1].norm().item() / (127.0 * B * K) ** 0.5
+    for k, b in res[1][2].items():
+        a = res[0][2][k]
+        floor = 1e-3 * walk if k == "input_quant_fn.s" else 1e-6 * max(1.0, b.abs().max().item())
+        assert rel_err(a, b) < 1e-3 or (a - b).abs().max().item() <= floor, (k, rel_err(a, b))
+
+
 def test_flat_gradient_buffer_direct_slots_and_zero_arena(Q):
     """ddp.FlatGradAllReduce(direct=True): the dW GEMMs of the quantized layers accumulate straight into the flat gradient
     buffer (autograd adopts the slice as .grad: no gather copy, no per-weight zero fill), and the tiny scratch vectors of the
