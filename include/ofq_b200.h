@@ -395,6 +395,15 @@ OFQ_API int ofq_cga_adamw(float* p, const float* grad, float* exp_avg, float* ex
                           int rows, int cols, int step, double lr, double beta1, double beta2, double eps,
                           double weight_decay, int bits, double boundary_range, float* rowstat, int* kminmax,
                           uint8_t* mask_out, const int* step_dev, void* stream);
+/* Deployment export (the reference stops at fake-quant floats): StatsQ weight codes at their true width.
+ * A b-bit code 2k+1 (k in [-n, n-1], n = 2^(b-1); reference statsq.py:145-147) is stored as u = k + n in b bits, eight codes per
+ * b bytes in little-endian bit order; a row of `cols` codes takes ofq_packed_row_bytes(cols, bits) bytes. Round trip is exact. */
+OFQ_API long long ofq_packed_row_bytes(int cols, int bits);
+OFQ_API int ofq_pack_codes(const int8_t* codes, long long rows, int cols, long long ld, int bits, uint8_t* out, long long ld_out,
+                           void* stream);
+OFQ_API int ofq_unpack_codes(const uint8_t* in, long long ld_in, long long rows, int cols, int bits, int8_t* codes, long long ld,
+                             void* stream);
+
 /* KD losses of the training recipe (reference src/quantization/utils.py:44-77 KLLossSoft / KDLossSoftandHard; train.py:896-910)
  * and their gradients in one pass over the logits:
  *   row_loss[b] = CE(z_hard[b], target[b])                                  (z_hard != NULL; nn.CrossEntropyLoss, class indices)

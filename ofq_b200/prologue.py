@@ -65,6 +65,7 @@ class StepPrologue:
         self.dirty = True
         self.tables = None
         self.launches = 0
+        self.frozen = False        # export.load_packed: the buffers hold deployed codes, the weight-side kernels never run
         self.generation = 0        # bumped whenever the buffers are re-produced for changed weights
         self._sig = None           # weights signature of the last production
         self.cache_hits = 0
@@ -206,10 +207,10 @@ class StepPrologue:
         lib = _lib.load()
         st = torch.cuda.current_stream().cuda_stream
         tb = self.tables
-        for table, n, H, hd, Cc in tb.get("wqk", ()):
+        for table, n, H, hd, Cc in (() if self.frozen else tb.get("wqk", ())):
             ops._call("wqk_compose", 1, 4.0 * n * (2 * H * hd * Cc + H * Cc * Cc), 2.0 * n * H * hd * Cc * Cc, lib.ofq_wqk_compose_multi,
                       table.data_ptr(), n, H, hd, Cc, st)
-        if "statsq" in tb:
+        if "statsq" in tb and not self.frozen:
             table, n, blocks = tb["statsq"]
             nbytes = sum(5.0 * j.tensors[0].numel() for j in self.statsq.values())
             ops._call("statsq", 1, nbytes, 0, lib.ofq_statsq_codes_multi, table.data_ptr(), n, blocks, st)

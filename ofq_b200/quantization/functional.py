@@ -68,6 +68,12 @@ def levels(bit: int, all_positive: bool):
     return -(2 ** (bit - 1)), 2 ** (bit - 1) - 1
 
 
+def _need_grad(ctx) -> bool:
+    """Will this node ever run a backward? `ctx.needs_input_grad` alone says True under torch.no_grad() (it mirrors
+    `requires_grad` of the inputs): inference then produced fp16 operand copies and probabilities nobody reads."""
+    return torch.is_grad_enabled() and any(ctx.needs_input_grad)
+
+
 def grad_scale_factor(hi: int, count: int) -> float:
     """s_grad_scale of lsq.py:582-591 / 775-778: 1/sqrt(thd_pos * elements-per-scale)."""
     return 1.0 / ((hi * count) ** 0.5)
@@ -215,11 +221,11 @@ class QLinearFn(torch.autograd.Function):
         se2 = ops.lsq_effective_scale(s, g, recip=True)
         se = se2[0]
         qx16 = None
-        if F16 and any(ctx.needs_input_grad):
+        if F16 and _need_grad(ctx):
             qx, qx16 = ops.lsq_quant(x2d, b4, se, PER_ROW, P, 1, lo, hi, act=act, fmt16=FMT)
         else:
             qx = ops.lsq_quant(x2d, b4, se, PER_ROW, P, 1, lo, hi, act=act)
-        w16 = FMT if (F16 and any(ctx.needs_input_grad)) else None
+        w16 = FMT if (F16 and _need_grad(ctx)) else None
         wc, colscale, _, colterm, _, inv_cs, *wc16 = ops.statsq_codes(weight, wbits, aft=aft, bias=bias, want_inv=True, fmt16=w16)
         wc16 = wc16[0] if wc16 else None
         out = torch.empty((M, Nout), dtype=torch.float32, device=x.device)
@@ -368,7 +374,7 @@ class HeadLinearFn(torch.autograd.Function):
         g_w = grad_scale_factor(hi, K)
         sx2 = ops.lsq_effective_scale(s_x, g_x, recip=True)          # [2, 1]
         sw2 = ops.lsq_effective_scale(s_w, g_w, recip=True)          # [2, Nout]
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = _need_grad(ctx)
         f16 = FMT if (F16 and need_grad) else None
         qx16 = wc16 = None
         r = ops.lsq_quant(x2d, b4, sx2[0], PER_ROW, 1, 1, lo, hi, fmt16=f16)
@@ -559,7 +565,7 @@ class QKRAttnCoreFn(torch.autograd.Function):
         g_x = grad_scale_factor(hi, B * C)
         sx2 = ops.lsq_effective_scale(s_x, g_x, recip=True)
         se_x = sx2[0]
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = _need_grad(ctx)
         f16 = FMT if (F16 and need_grad) else None     # every quantizer pass also leaves the exact fp16 copy the backward GEMMs read
         qx16 = qv16 = qk16 = qp16 = None
         qx = ops.lsq_quant(x2d, x_b4, se_x, PER_ROW, N, 1, lo, hi, fmt16=f16)
@@ -812,7 +818,7 @@ class QAttnCoreFn(torch.autograd.Function):
         g_p = grad_scale_factor(hiu, B * H * N)
         sp2 = ops.lsq_effective_scale(s_p, g_p, recip=True)
         se_p = sp2[0]
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = _need_grad(ctx)
         P, qp, rowsum = ops.softmax_quant(S, N, H, se_p, hiu, bias=attn_bias, mask=attn_mask, nW=nW, save_p=need_grad)
         ldq = qp.shape[-1]
         del S
