@@ -395,6 +395,23 @@ OFQ_API int ofq_cga_adamw(float* p, const float* grad, float* exp_avg, float* ex
                           int rows, int cols, int step, double lr, double beta1, double beta2, double eps,
                           double weight_decay, int bits, double boundary_range, float* rowstat, int* kminmax,
                           uint8_t* mask_out, const int* step_dev, void* stream);
+/* dX GEMM of a quantized linear layer with the backward of the layer's INPUT quantizer as its epilogue (north star: STE mask and
+ * LSQ step-size gradient fused into the backward GEMM; autograd of reference lsq.py:571-602 on qlinear.py:58-73):
+ *   dxhat[m][n] = (sum_k A[m][k] B[n][k]) * rs[m % period] * cs[0]       (as ofq_gemm; never written)
+ *   v = (x[m][n] + b4[n]) * rs[m % period]        (rs = 1 / s_eff: the GEMM's row un-scale IS the quantizer's reciprocal step)
+ *   dx[m][n]    = dxhat if qlo <= v <= qhi else 0
+ *   d_s[i]      = g * sum_{m % period == i} sum_n dxhat * (q - v if inside else q),   q = rint(clamp(v, qlo, qhi))
+ *   d_b4[n]     = sum_m dx[m][n],   d_aft[n] = sum_m dxhat[m][n]            (deterministic: per-warp partials + one finalize)
+ * 16-bit kinds, plain (unbatched) operands, N % 64 == 0. workspace: ofq_gemm_dx_lsq_workspace(M, N) floats. */
+OFQ_API long long ofq_gemm_dx_lsq_workspace(int M, int N);
+OFQ_API int ofq_gemm_dx_lsq(int kind, const ofq_operand_t* A, const ofq_operand_t* B, int M, int N, int K, const ofq_vec_t* rs,
+                            const ofq_vec_t* cs, const float* x, long long ldx, const float* b4, int qlo, int qhi, float g,
+                            float* dx, long long lddx, float* d_s, float* d_b4, float* d_aft, float* workspace, void* stream);
+/* The finalize pass of the above on raw partials (colpart [nslots][3][cols], rowpart [planes][rows]). */
+OFQ_API int ofq_lsq_bwd_finalize_parts(const float* colpart, long long nslots, const float* rowpart, long long rowpart_total,
+                                       long long rows, int cols, int period, float g, float* d_s, float* d_b4, float* d_aft,
+                                       void* stream);
+
 /* Deployment export (the reference stops at fake-quant floats): StatsQ weight codes at their true width.
  * A b-bit code 2k+1 (k in [-n, n-1], n = 2^(b-1); reference statsq.py:145-147) is stored as u = k + n in b bits, eight codes per
  * b bytes in little-endian bit order; a row of `cols` codes takes ofq_packed_row_bytes(cols, bits) bytes. Round trip is exact. */

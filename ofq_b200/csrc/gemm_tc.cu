@@ -1034,6 +1034,275 @@ gemm_lsq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 }
 
+// ------------------------------------------------------------------------------------------ dX GEMM + LSQ backward epilogue
+// ofq_gemm_dx_lsq: dX_hat = A16 . W16 (the backward GEMM of a quantized linear layer, qlinear.py:58-73) whose epilogue IS the
+// backward of the layer's input quantizer (autograd of lsq.py:571-602): the x tile arrives by TMA beside the accumulator, the
+// epilogue applies the straight-through mask, stores dx, and leaves per-row partials of the step-size gradient and per-warp
+// column sums (d move_b4, d move_aft) for the ordinary finalize pass. dX_hat never exists in HBM.
+struct DxLsqEpi {
+    const float* b4;        // [N]
+    float* rowpart;         // [2 * ntiles][M]
+    float* colpart;         // [4 * mtiles][3][N]
+    float qlo, qhi;
+};
+
+template <int BN, int STAGES>
+struct DxLsqSmem {
+    static constexpr uint32_t A_BYTES = BM * KBYTES;
+    static constexpr uint32_t STAGE_BYTES = A_BYTES + BN * KBYTES;
+    static constexpr uint32_t WARP_BYTES = 3 * 4096;                  // x tile (double buffered) | dx staging, 32 x 128 B each, 128B swizzle
+    static constexpr uint32_t OUT_OFF = STAGES * STAGE_BYTES;
+    static constexpr uint32_t VEC_OFF = OUT_OFF + EPI_WARPS * WARP_BYTES;           // per warp and owned chunk: b4[32]
+    static constexpr uint32_t BAR_OFF = VEC_OFF + EPI_WARPS * epi_nch(BN) * 32 * 4;
+    static constexpr uint32_t TOTAL = BAR_OFF + (2 * STAGES + 4 + 2 * EPI_WARPS) * 8 + 16;
+    static constexpr size_t DYN_BYTES = TOTAL + 1024;
+};
+
+// column sums over the 32 rows (lanes) of a warp for 16 columns held one per register: lane l ends with column l & 15
+__device__ __forceinline__ float colsum16(float (&v)[16], const int lane) {
+#pragma unroll
+    for (int s = 8; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float keep = up ? v[i + s] : v[i];
+            const float send = up ? v[i] : v[i + s];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
+// sixteen columns (half `sub` of a 32 x 32 chunk) of row `lane`; returns the row's partial of dy * (q - v | q)
+__device__ __forceinline__ float dxlsq_piece(const uint32_t (&rr)[16], const float rsv, const float csv, const float* __restrict__ b4v,
+                                             const uint8_t* __restrict__ xrow, uint8_t* __restrict__ orow, const float qlo, const float qhi,
+                                             const int lane, const int sub, float* __restrict__ col_aft, float* __restrict__ col_b4) {
+    constexpr float MAGIC = 12582912.f;
+    const float2 rs2 = make_float2(rsv, rsv), cs2 = make_float2(csv, csv);
+    float ys[16], ds[16];
+    float2 part2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int j4 = sub * 4 + g;                                   // 16-byte group of the 128-byte row
+        const float4 x4 = ld_shared_v4_nc(xrow + ((j4 ^ (lane & 7)) << 4));
+        const float4 b44 = ld_shared_v4_nc(b4v + sub * 16 + 4 * g);
+        const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, bs[4] = {b44.x, b44.y, b44.z, b44.w};
+        float o[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = 4 * g + 2 * h;
+            const float2 y = __fmul2_rn(__fmul2_rn(make_float2(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1])), rs2), cs2);
+            const float2 v = __fmul2_rn(__fadd2_rn(make_float2(xs[2 * h], xs[2 * h + 1]), make_float2(bs[2 * h], bs[2 * h + 1])), rs2);
+            const float2 t = make_float2(fminf(fmaxf(v.x, qlo), qhi), fminf(fmaxf(v.y, qlo), qhi));
+            const float2 q = __fadd2_rn(__fadd2_rn(t, make_float2(MAGIC, MAGIC)), make_float2(-MAGIC, -MAGIC));
+            const float2 qv = __fadd2_rn(q, make_float2(-v.x, -v.y));
+            const bool in0 = t.x == v.x, in1 = t.y == v.y;            // inside the clamp range <=> the clamp changed nothing
+            part2 = __ffma2_rn(y, make_float2(in0 ? qv.x : q.x, in1 ? qv.y : q.y), part2);
+            o[2 * h] = in0 ? y.x : 0.f;
+            o[2 * h + 1] = in1 ? y.y : 0.f;
+            ys[j] = y.x; ys[j + 1] = y.y;
+            ds[j] = o[2 * h]; ds[j + 1] = o[2 * h + 1];
+        }
+        st_shared_v4_nc(orow + ((j4 ^ (lane & 7)) << 4), o[0], o[1], o[2], o[3]);
+    }
+    *col_aft = colsum16(ys, lane);
+    *col_b4 = colsum16(ds, lane);
+    return part2.x + part2.y;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_dxlsq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmC, const GemmParams p,
+                  const DxLsqEpi e, const int num_tiles, const int mtiles, const int ntiles) {
+    using L = DxLsqSmem<BN, STAGES>;
+    constexpr uint32_t A_BYTES = L::A_BYTES;
+    constexpr uint32_t STAGE_BYTES = L::STAGE_BYTES;
+    constexpr uint32_t ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+    constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
+    constexpr uint32_t UMMA_K_BYTES = 32;
+    const uint32_t IDESC = umma_idesc(1u, (uint32_t)p.ab_fmt, BM, BN) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16);
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_full = empty_bar + STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    uint64_t* x_bar = acc_empty + 2;             // [EPI_WARPS][2]: x tile of a chunk has landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_bar + 2 * EPI_WARPS);
+    float* vec_s = reinterpret_cast<float*>(smem + L::VEC_OFF);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmC);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_WARPS); }
+        for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(&x_bar[s], 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            constexpr int kelem = KBYTES / 2;
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);
+                for (int i = 0; i < c.nit; ++i, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    const int kb = c.it_begin + i;
+                    uint8_t* sa = smem + s * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                    if (p.a_mn) {
+                        for (int j = 0; j < BM / 64; ++j) tma_load_5d(sa + j * 8192, &tmA, &full_bar[s], c.m0 + 64 * j, kb * kelem, 0, 0, 0);
+                    } else {
+                        tma_load_5d(sa, &tmA, &full_bar[s], kb * kelem, c.m0, 0, 0, 0);
+                    }
+                    if (p.b_mn) {
+                        for (int j = 0; j < BN / 64; ++j) tma_load_5d(sb + j * 8192, &tmB, &full_bar[s], c.n0 + 64 * j, kb * kelem, 0, 0, 0);
+                    } else {
+                        tma_load_5d(sb, &tmB, &full_bar[s], kb * kelem, c.n0, 0, 0, 0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            uint32_t it = 0, tc = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tc) {
+                const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);
+                const uint32_t as = tc & 1, aph = (tc >> 1) & 1;
+                mbar_wait(&acc_empty[as], aph ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * ACC_COLS;
+                for (int i = 0; i < c.nit; ++i, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                    const bool bmn = p.b_mn != 0, amn = p.a_mn != 0;
+                    const uint64_t bdesc = bmn ? umma_desc_mnmajor_sw128(sa + A_BYTES) : umma_desc_kmajor_sw128(sa + A_BYTES);
+                    const uint64_t adesc = amn ? umma_desc_mnmajor_sw128(sa) : umma_desc_kmajor_sw128(sa);
+                    const uint64_t badv = bmn ? (2048u >> 4) : (UMMA_K_BYTES >> 4);
+                    const uint64_t aadv = amn ? (2048u >> 4) : (UMMA_K_BYTES >> 4);
+#pragma unroll
+                    for (uint32_t kk = 0; kk < KBYTES / UMMA_K_BYTES; ++kk)
+                        umma_f16(tmem_d, adesc + kk * aadv, bdesc + kk * badv, IDESC, (i | kk) != 0);
+                    tc_commit(&empty_bar[s]);
+                }
+                tc_commit(&acc_full[as]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int NCH = epi_nch(BN);
+        uint8_t* wbase = smem + L::OUT_OFF + (warp - 2) * L::WARP_BYTES;
+        uint8_t* obuf = wbase + 8192;
+        uint64_t* xb = x_bar + 2 * (warp - 2);
+        float* myvec = vec_s + (warp - 2) * NCH * 32;
+        const float qlo = e.qlo, qhi = e.qhi;
+        const float csv = p.cs.p ? __ldg(p.cs.p) : 1.0f;              // the range un-scale: one value for the whole problem
+        uint32_t tc = 0, nstore = 0, xdone = 0, xissued = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tc) {
+            const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);
+            const uint32_t as = tc & 1, aph = (tc >> 1) & 1;
+            const int m_row0 = c.m0 + q * 32, m = m_row0 + lane;
+            const bool row_ok = m < p.M;
+            const float rsv = row_ok ? (p.rs.p ? __ldg(p.rs.p + p.rs.fd.mod(m)) : 1.0f) : 0.f;
+            const int nvalid = (min(BN, p.N - c.n0) + 31) / 32;
+            const int nown = nvalid > half ? (nvalid - half + 1) >> 1 : 0;
+            // first x tile of this tile's chunks, and the b4 vectors of all owned chunks
+            if (nown > 0 && lane == 0) {
+                uint64_t* bar = &xb[xissued & 1];
+                mbar_arrive_expect_tx(bar, 4096);
+                tma_load_5d(wbase + (xissued & 1) * 4096, &tmX, bar, c.n0 + half * 32, m_row0, 0, 0, 0);
+            }
+            if (nown > 0) ++xissued;
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                const int n = c.n0 + (half + 2 * k) * 32 + lane;
+                myvec[k * 32 + lane] = (n < p.N && e.b4) ? __ldg(e.b4 + n) : 0.f;
+            }
+            __syncwarp();
+            mbar_wait(&acc_full[as], aph);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + as * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+            uint32_t ra[16], rb[16];
+            if (nown > 0) tmem_ld_32x32_x16r(tmem_acc + (uint32_t)(half * 32), ra);
+            float part = 0.f;
+#pragma unroll 1
+            for (int k = 0; k < nown; ++k) {
+                const int cc = half + 2 * k, n_c = c.n0 + cc * 32;
+                if (k + 1 < nown) {                  // x tile of the next chunk into the other buffer
+                    if (lane == 0) {
+                        uint64_t* bar = &xb[xissued & 1];
+                        mbar_arrive_expect_tx(bar, 4096);
+                        tma_load_5d(wbase + (xissued & 1) * 4096, &tmX, bar, n_c + 64, m_row0, 0, 0, 0);
+                    }
+                    ++xissued;
+                }
+                const uint32_t xslot = xdone & 1u;               // loads are consumed in issue order, alternating buffers
+                mbar_wait(&xb[xslot], (xdone >> 1) & 1u);
+                ++xdone;
+                if (nstore > 0) {                    // the staging buffer must have been read by the previous chunk's store
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+                }
+                const uint8_t* xrow = wbase + xslot * 4096 + lane * 128;
+                uint8_t* orow = obuf + lane * 128;
+                const float* b4v = myvec + k * 32;
+                float ca0, cb0, ca1, cb1;
+                tmem_ld_wait(); tmem_ld_pin16(ra);
+                tmem_ld_32x32_x16r(tmem_acc + (uint32_t)(cc * 32 + 16), rb);
+                part += dxlsq_piece(ra, rsv, csv, b4v, xrow, orow, qlo, qhi, lane, 0, &ca0, &cb0);
+                tmem_ld_wait(); tmem_ld_pin16(rb);
+                if (k + 1 < nown) tmem_ld_32x32_x16r(tmem_acc + (uint32_t)((cc + 2) * 32), ra);
+                part += dxlsq_piece(rb, rsv, csv, b4v, xrow, orow, qlo, qhi, lane, 1, &ca1, &cb1);
+                // per-warp column sums: slot = (row block, lane quarter); lanes 0..15 own the first, 16..31 the second piece
+                {
+                    const int col = n_c + lane;
+                    if (col < p.N) {
+                        const long long slot = (long long)(c.m0 / BM) * 4 + q;
+                        float* cp = e.colpart + slot * 3 * p.N + col;
+                        cp[0] = lane < 16 ? ca0 : ca1;
+                        cp[p.N] = lane < 16 ? cb0 : cb1;
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_5d(&tmC, obuf, n_c, m_row0, 0, 0, 0);
+                    tma_store_commit();
+                }
+                ++nstore;
+            }
+            if (row_ok && nown > 0) e.rowpart[(long long)((c.n0 / BN) * 2 + half) * p.M + m] = part;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 // rowdot[m, s] = sum of the per-chunk partials of segment s, in column order (deterministic)
 __global__ void __launch_bounds__(256)
 rowdot_reduce_kernel(const float* __restrict__ part, int ld_part, long long M, int nseg, int chunks_per_seg, float* __restrict__ rowdot) {
@@ -1442,4 +1711,84 @@ extern "C" int ofq_gemm_lsq(const ofq_operand_t* A, const ofq_operand_t* B, int 
         OFQ_CUDA(cudaGetLastError());
     }
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------ ofq_gemm_dx_lsq
+template <int BN, int STAGES>
+static int launch_gemm_dxlsq(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const CUtensorMap& tmC,
+                             GemmParams p, const DxLsqEpi& e, cudaStream_t stream) {
+    constexpr size_t smem = DxLsqSmem<BN, STAGES>::DYN_BYTES;
+    static_assert(smem <= 227 * 1024, "shared memory budget exceeded");
+    auto kern = gemm_dxlsq_kernel<BN, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        OFQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int mtiles = (p.M + BM - 1) / BM, ntiles = (p.N + BN - 1) / BN;
+    p.fd_ntiles = make_fastdiv(ntiles); p.fd_mtiles = make_fastdiv(mtiles);
+    const long long tiles = (long long)mtiles * ntiles;
+    OFQ_REQUIRE(tiles <= 0x7fffffff, "ofq_gemm_dx_lsq: too many tiles");
+    const int grid = (int)(tiles < ofq_num_sms() ? tiles : ofq_num_sms());
+    kern<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, tmX, tmC, p, e, (int)tiles, mtiles, ntiles);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int dxlsq_bn(int N) { return N % 192 == 0 ? 192 : (N % 128 == 0 ? 128 : 64); }
+
+extern "C" long long ofq_gemm_dx_lsq_workspace(int M, int N) {
+    const int bn = dxlsq_bn(N);
+    const long long ntiles = (N + bn - 1) / bn, mtiles = (M + BM - 1) / BM;
+    return 2 * ntiles * (long long)M + 4 * mtiles * 3 * (long long)N;
+}
+
+extern "C" int ofq_gemm_dx_lsq(int kind, const ofq_operand_t* A, const ofq_operand_t* B, int M, int N, int K, const ofq_vec_t* rs,
+                               const ofq_vec_t* cs, const float* x, long long ldx, const float* b4, int qlo, int qhi, float g,
+                               float* dx, long long lddx, float* d_s, float* d_b4, float* d_aft, float* workspace, void* stream) {
+    OFQ_REQUIRE(kind == OFQ_GEMM_BF16 || kind == OFQ_GEMM_F16, "ofq_gemm_dx_lsq: 16-bit kinds only");
+    OFQ_REQUIRE(A && B && rs && rs->ptr && rs->period > 0 && x && dx && workspace && d_b4, "ofq_gemm_dx_lsq: null argument");
+    OFQ_REQUIRE(M > 0 && N > 0 && K > 0 && N % 64 == 0, "ofq_gemm_dx_lsq: extents must be positive, N a multiple of 64");
+    OFQ_REQUIRE(M % rs->period == 0 || rs->period >= M, "ofq_gemm_dx_lsq: rows must be a multiple of the step-size period");
+    OFQ_REQUIRE(A->dual_delta == 0 && A->bstride1 == 0 && B->bstride1 == 0, "ofq_gemm_dx_lsq: plain (unbatched, single-plane) operands only");
+    OFQ_CHECK_ARCH();
+    const int kelem = KBYTES / 2;
+    GemmParams p;
+    p.M = M; p.N = N;
+    p.kblocks = (K + kelem - 1) / kelem;
+    p.k2 = 1; p.splits = 1; p.nb1 = p.nb2 = 1;
+    p.a_b1 = p.a_b2 = p.b_b1 = p.b_b2 = p.c_b1 = p.c_b2 = 0;
+    p.a_k2 = p.b_k2 = 0; p.a_dual_delta = 0;
+    p.a_k2mod = p.b_k2mod = 0x7fffffff;
+    p.fd_nbatch = make_fastdiv(1); p.fd_nb1 = make_fastdiv(1); p.fd_splits = make_fastdiv(1);
+    p.fd_kblocks = make_fastdiv(p.kblocks); p.fd_ak2mod = make_fastdiv(p.a_k2mod); p.fd_bk2mod = make_fastdiv(p.b_k2mod);
+    p.rs = make_vec(rs); p.cs = make_vec(cs); p.rt = make_vec(nullptr); p.ct = make_vec(nullptr);
+    p.has_rank1 = 0; p.atomic = 0;
+    p.ab_fmt = kind == OFQ_GEMM_F16 ? 0 : 1;
+    p.a_mn = A->mn_major != 0; p.b_mn = B->mn_major != 0;
+    p.amax = nullptr; p.debug_nostore = 0;
+    const int bn = dxlsq_bn(N);
+    OFQ_REQUIRE(!p.b_mn || bn % 64 == 0, "ofq_gemm_dx_lsq: tile width");
+    const long long ntiles = (N + bn - 1) / bn, mtiles = (M + BM - 1) / BM;
+    DxLsqEpi e;
+    e.b4 = b4; e.rowpart = workspace; e.colpart = workspace + 2 * ntiles * (long long)M;
+    e.qlo = (float)qlo; e.qhi = (float)qhi;
+    CUtensorMap tmA, tmB, tmX, tmC;
+    int rc = make_operand_map(&tmA, A, 2, M, K, 1, 1, 1, BM, kind == OFQ_GEMM_F16);
+    if (rc) return rc;
+    rc = make_operand_map(&tmB, B, 2, N, K, 1, 1, 1, bn, kind == OFQ_GEMM_F16);
+    if (rc) return rc;
+    ofq_gemm_out_t ox = {const_cast<float*>(x), ldx, 0, 0, 0}, oc = {dx, lddx, 0, 0, 0};
+    rc = make_out_map(&tmX, &ox, M, N, 1, 1);
+    if (rc) return rc;
+    rc = make_out_map(&tmC, &oc, M, N, 1, 1);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (bn) {
+        case 192: rc = launch_gemm_dxlsq<192, 3>(tmA, tmB, tmX, tmC, p, e, st); break;
+        case 128: rc = launch_gemm_dxlsq<128, 3>(tmA, tmB, tmX, tmC, p, e, st); break;
+        default:  rc = launch_gemm_dxlsq<64, 4>(tmA, tmB, tmX, tmC, p, e, st); break;
+    }
+    if (rc) return rc;
+    return ofq_lsq_bwd_finalize_parts(e.colpart, 4 * mtiles, e.rowpart, 2 * ntiles * (long long)M, M, N, rs->period, g, d_s, d_b4, d_aft, stream);
 }

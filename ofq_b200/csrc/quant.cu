@@ -1574,6 +1574,31 @@ static int lsq_bwd_finalize_impl(const float* workspace, long long rows, int col
     return 0;
 }
 
+// Finalize pass over partials produced by another kernel (the dX GEMM with the LSQ backward in its epilogue, ofq_gemm_dx_lsq):
+// colpart [nslots][3][cols] (vector 0: column sums of dy -> d_aft, 1: of the masked dy -> d_b4), rowpart [planes][rows] per-row
+// partials of dy * (q - v | q); per-row scales with `period`, one segment.
+extern "C" int ofq_lsq_bwd_finalize_parts(const float* colpart, long long nslots, const float* rowpart, long long rowpart_total,
+                                          long long rows, int cols, int period, float g, float* d_s, float* d_b4, float* d_aft,
+                                          void* stream) {
+    OFQ_REQUIRE(colpart && rowpart && nslots > 0 && rowpart_total > 0 && rows > 0 && cols > 0 && period > 0,
+                "ofq_lsq_bwd_finalize_parts: bad argument");
+    OFQ_REQUIRE(period >= rows || rows % period == 0, "ofq_lsq_bwd_finalize_parts: rows must be a multiple of the scale period");
+    OFQ_CHECK_ARCH();
+    FinalizeArgs a;
+    a.colpart = colpart; a.cols = cols; a.nslots = nslots; a.scale_mode = OFQ_SCALE_PER_ROW; a.g = g;
+    a.d_s = d_s; a.d_b4 = d_b4; a.d_aft = d_aft; a.zero_sum = 0; a.dx_colsum = nullptr;
+    a.rowpart = rowpart; a.total = rowpart_total;
+    a.nscale = (long long)(period < rows ? period : rows);
+    a.blockmax = nullptr; a.nblk = 0;
+    a.v1 = a.v2 = nullptr; a.n1 = a.n2 = 0; a.mult = 1.f; a.product = 0; a.out4 = nullptr;
+    a.ncx = (cols + 31) / 32;
+    a.ncb = 2 * a.ncx;                 // vectors 0 and 1 only
+    a.nrb = d_s ? (a.nscale < 32 ? 1 : (int)((a.nscale + 7) / 8)) : 0;
+    lsq_bwd_finalize_kernel<<<(unsigned)(a.ncb + a.nrb), 256, 0, (cudaStream_t)stream>>>(a);
+    OFQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int ofq_lsq_bwd_finalize(const float* workspace, long long rows, int cols, int scale_mode, int period,
                                     int nseg, float g, float* d_s, float* d_b4, float* d_aft, int zero_sum, void* stream) {
     return lsq_bwd_finalize_impl(workspace, rows, cols, scale_mode, period, nseg, g, d_s, d_b4, d_aft, zero_sum, nullptr, nullptr, 0,

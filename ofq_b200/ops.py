@@ -204,6 +204,28 @@ def gemm_lsq(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, b4: Optio
     return codes, c16, res, rowdot
 
 
+def gemm_dx_lsq(kind: int, a16: torch.Tensor, a_strides, b16: torch.Tensor, b_strides, M: int, N: int, K: int, *, rs, cs, x2d: torch.Tensor,
+                b4: torch.Tensor, period: int, qlo: int, qhi: int, g: float, a_mn: bool = False, b_mn: bool = False):
+    """dX GEMM of a quantized linear layer with the LSQ backward of its input quantizer as the epilogue (ofq_gemm_dx_lsq):
+    returns (dx [M, N] fp32, d_s [min(period, M)], d_b4 [N], d_aft [N]); dX_hat itself is never written. rs = vec(1 / s_eff, period)
+    is both the GEMM's row un-scale and the quantizer's reciprocal step; cs the period-1 range un-scale."""
+    _cuda(a16, b16, x2d, b4)
+    assert x2d.dtype == torch.float32 and x2d.stride(1) == 1 and tuple(x2d.shape) == (M, N)
+    dev = x2d.device
+    lib = _lib.load()
+    dx = torch.empty((M, N), dtype=torch.float32, device=dev)
+    d_s = torch.empty(min(period, M), dtype=torch.float32, device=dev)
+    d_b4 = torch.empty(N, dtype=torch.float32, device=dev)
+    d_aft = torch.empty(N, dtype=torch.float32, device=dev)
+    ws = torch.empty(lib.ofq_gemm_dx_lsq_workspace(M, N), dtype=torch.float32, device=dev)
+    A = Operand(a16.data_ptr(), a_strides[0], 0, 0, 0, 0, 0, int(a_mn))
+    B = Operand(b16.data_ptr(), b_strides[0], 0, 0, 0, 0, 0, int(b_mn))
+    _call("gemm_dx_lsq", 2, 2.0 * (M * K + N * K) + 8.0 * M * N, 2.0 * M * N * K, lib.ofq_gemm_dx_lsq, kind, C.byref(A), C.byref(B), M, N, K,
+          rs, cs, x2d.data_ptr(), x2d.stride(0), b4.data_ptr(), qlo, qhi, float(g), dx.data_ptr(), N, d_s.data_ptr(), d_b4.data_ptr(),
+          d_aft.data_ptr(), ws.data_ptr(), _st(), tag=f"M{M} N{N} K{K} dx+lsq")
+    return dx, d_s, d_b4, d_aft
+
+
 # ------------------------------------------------------------------------------------------------ quantizers
 def statsq_codes(w: torch.Tensor, bits: int, aft: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
                  want_minmax: bool = False, want_inv: bool = False, want_sf: bool = False, fmt16: Optional[int] = None):

@@ -51,6 +51,8 @@ FUSED16 = os.environ.get("OFQ_FUSED16", "1") != "0"
 FUSED_ATTN = os.environ.get("OFQ_FUSED_ATTN", "1") != "0"
 # the qkx quantizer as the epilogue of the qkx GEMM (ofq_gemm_lsq); 0 = GEMM -> fp32 qkx -> ofq_lsq_quant (A/B measurements, tests)
 FUSED_QKX = os.environ.get("OFQ_FUSED_QKX", "1") != "0"
+# the input quantizer's backward as the epilogue of the layer's dX GEMM (ofq_gemm_dx_lsq); 0 = GEMM -> fp32 dX_hat -> ofq_lsq_bwd
+FUSED_DX = os.environ.get("OFQ_FUSED_DX", "1") != "0"
 # ... and its backward (ofq_qkr_attn_bwd: logits recomputed, dP = dO v^T, softmax / quantizer backward in one kernel; neither P
 # nor dP in HBM). fp16 mode only; OFQ_FUSED_ATTN_BWD=0 keeps dP GEMM + ofq_softmax_quant_bwd on the saved probabilities.
 FUSED_ATTN_BWD = os.environ.get("OFQ_FUSED_ATTN_BWD", "1") != "0"
@@ -68,10 +70,29 @@ def levels(bit: int, all_positive: bool):
     return -(2 ** (bit - 1)), 2 ** (bit - 1) - 1
 
 
+_GRAD_AT_APPLY = True
+
+
+class _Fn(torch.autograd.Function):
+    """autograd.Function whose forward can tell whether a backward can ever follow. Inside `forward` grad mode is always off, and
+    `ctx.needs_input_grad` mirrors `requires_grad` of the inputs even under torch.no_grad(): neither says whether the caller is
+    building a graph. `apply` records the caller's grad mode for `_need_grad`."""
+
+    @classmethod
+    def apply(cls, *args, **kwargs):
+        global _GRAD_AT_APPLY
+        prev = _GRAD_AT_APPLY
+        _GRAD_AT_APPLY = torch.is_grad_enabled()
+        try:
+            return super().apply(*args, **kwargs)
+        finally:
+            _GRAD_AT_APPLY = prev
+
+
 def _need_grad(ctx) -> bool:
-    """Will this node ever run a backward? `ctx.needs_input_grad` alone says True under torch.no_grad() (it mirrors
-    `requires_grad` of the inputs): inference then produced fp16 operand copies and probabilities nobody reads."""
-    return torch.is_grad_enabled() and any(ctx.needs_input_grad)
+    """Will this node ever run a backward? (Under no_grad inference must not produce the fp16 operand copies, probabilities and
+    residual planes only a backward reads.)"""
+    return _GRAD_AT_APPLY and any(ctx.needs_input_grad)
 
 
 def grad_scale_factor(hi: int, count: int) -> float:
@@ -103,7 +124,7 @@ def _dw_buffer(w, Nout: int, K: int, device) -> torch.Tensor:
 
 
 def _linear_backward_f16(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulate_dx: bool, qx16=None, sc=None, a16=None,
-                         colsum=None, amax_dx=None, wc16=None, dw_for=None):
+                         colsum=None, amax_dx=None, wc16=None, dw_for=None, dx_lsq=None):
     """fp16 backward of out = x_hat @ W_hat^T (+bias) with ONE range-scaled copy of the gradient,
     A16[t,n] = fp16(dY[t,n] * colscale[n] * se_x[t] * sc), read K-major by the dX GEMM and MN-major by the dW GEMM; the
     code operands stay exact and un-transposed (MN-major B), the folded scale vectors are undone per output row:
@@ -126,8 +147,15 @@ def _linear_backward_f16(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulat
         a16, colsum = prep["rm"], prep["colsum"]
     if wc16 is None:
         wc16 = ops.codes_to_bf16(wc, 1, Nout, K, K, 0, False, FMT)       # [1, Nout, K]
-    ops.gemm(GEMM_BWD, a16, (Nout, 0, 0, 0), wc16, (K, 0, 0, 0), dxhat, (K, 0, 0), M, K, Nout, b_mn=True,
-             accumulate=accumulate_dx, rs=vec(se2[1], period), cs=_scalar(sc), amax=amax_dx)
+    lsq_grads = None
+    if dx_lsq is not None:
+        # the dX GEMM with the input quantizer's backward (STE mask, ds, db4, daft) as its epilogue: dX_hat is never written
+        x2d_, b4_, lo_, hi_, g_ = dx_lsq
+        lsq_grads = ops.gemm_dx_lsq(GEMM_BWD, a16, (Nout, 0, 0, 0), wc16, (K, 0, 0, 0), M, K, Nout, rs=vec(se2[1], period), cs=_scalar(sc),
+                                    x2d=x2d_, b4=b4_, period=period, qlo=lo_, qhi=hi_, g=g_, b_mn=True)
+    else:
+        ops.gemm(GEMM_BWD, a16, (Nout, 0, 0, 0), wc16, (K, 0, 0, 0), dxhat, (K, 0, 0), M, K, Nout, b_mn=True,
+                 accumulate=accumulate_dx, rs=vec(se2[1], period), cs=_scalar(sc), amax=amax_dx)
     if qx16 is None:
         qx16 = ops.codes_to_bf16(qx, 1, M, K, K, 0, False, FMT)          # [1, M, K]
     dW = _dw_buffer(dw_for, Nout, K, a16.device)
@@ -135,6 +163,8 @@ def _linear_backward_f16(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulat
     with ops.side_stream(a16, qx16, dW, cs2, sc, colsum, x_aft):
         ops.gemm(GEMM_BWD, a16, (Nout, 0, 0, 0), qx16, (K, 0, 0, 0), dW, (K, 0, 0), Nout, K, M, a_mn=True, b_mn=True,
                  splits=0, accumulate=True, rs=vec(cs2[1]), cs=_scalar(sc), rt=vec(colsum), ct=vec(x_aft))
+    if lsq_grads is not None:
+        return dW, colsum, qx16, lsq_grads
     return dW, colsum, qx16
 
 
@@ -200,7 +230,7 @@ class MlpLink:
         self.fuse = fuse
 
 
-class QLinearFn(torch.autograd.Function):
+class QLinearFn(_Fn):
     """QLinear.forward (qlinear.py:58-73): StatsQ weight codes, (move_b4 -> LSQ -> move_aft) input codes,
     int8 tcgen05 GEMM with the scales / shift / bias in the epilogue.
     act = ACT_GELU: the layer computes QLinear(GELU(x)) (fc2 of QMLP, qlinear.py:123-136) with the activation fused into
@@ -250,8 +280,13 @@ class QLinearFn(torch.autograd.Function):
         K = xc.shape[-1]
         x2d = xc.view(-1, K)
         M = x2d.shape[0]
-        dxhat = torch.empty((M, K), dtype=torch.float32, device=dY.device)
         fused_in = link is not None and role == 1 and link.a16 is not None
+        # single-producer input gradients that leave as fp32 dx (fc1 and proj inputs): the quantizer's backward runs as the
+        # epilogue of the dX GEMM (ofq_gemm_dx_lsq) and dX_hat never exists
+        fuse_dx = (F16 and FUSED_DX and act == ACT_NONE and K % 64 == 0 and M % P == 0 and x2d.stride(0) % 4 == 0
+                   and not (link is not None and role == 2))
+        dxkw = {"dx_lsq": (x2d, b4, lo, hi, g)} if fuse_dx else {}
+        dxhat = None if fuse_dx else torch.empty((M, K), dtype=torch.float32, device=dY.device)
         dY2d = None if fused_in else dY.contiguous().view(M, -1)      # (never materialise the zero-stride placeholder)
         if fused_in:
             # fc1 of a fused QMLP: fc2's backward already wrote this layer's fp16 gradient operand and colsum(dY); the dY
@@ -259,16 +294,16 @@ class QLinearFn(torch.autograd.Function):
             if not _is_placeholder_grad(dY):
                 raise RuntimeError("fused QMLP: the fc1 output received a gradient from something other than fc2 (a hook, "
                                    "retain_grad or a second consumer); run the MLP un-fused (OFQ_FUSED16=0) for such graphs")
-            dW, dbias, _ = _linear_backward_f16(None, qx, wc, (colscale, inv_cs), se2, P, aft, dxhat, False, qx16, sc=link.sc,
-                                                a16=link.a16, colsum=link.colsum, **wkw)
+            dW, dbias, _, *lsqg = _linear_backward_f16(None, qx, wc, (colscale, inv_cs), se2, P, aft, dxhat, False, qx16, sc=link.sc,
+                                                       a16=link.a16, colsum=link.colsum, **wkw, **dxkw)
             link.a16 = link.colsum = None
         else:
             sc = link.sc if (link is not None and role == 1) else None
             fuse_next = (F16 and FUSED16 and link is not None and role == 2 and link.fuse and link.cs is not None
                          and link.cs.shape[0] == K and K % 4 == 0 and M % link.se.numel() == 0)
             amax = ops.scratch_zeros(1, dY.device) if fuse_next else None
-            dW, dbias, _ = _linear_backward(dY2d, qx, wc, (colscale, inv_cs), se2, P, aft, dxhat, False, qx16, sc=sc,
-                                            **({"amax_dx": amax} if fuse_next else {}), **wkw)
+            dW, dbias, _, *lsqg = _linear_backward(dY2d, qx, wc, (colscale, inv_cs), se2, P, aft, dxhat, False, qx16, sc=sc,
+                                                   **({"amax_dx": amax} if fuse_next else {}), **wkw, **dxkw)
             if fuse_next:
                 # the producer (fc1) only needs fp16(dx * colscale1[c] * se1[r] * sc) and colsum(dx): written by this pass
                 # |dx| <= |dxhat| * max GELU' (1.13)
@@ -280,6 +315,10 @@ class QLinearFn(torch.autograd.Function):
                 dx = _placeholder_grad(xc)        # exact zeros, recognised by fc1's backward (see MlpLink.fuse)
                 ops.side_join()
                 return dx, dW, (dbias if has_bias else None), db4, daft, ds, None, None, None, None, None, None
+        if lsqg:
+            dx, ds, db4, daft = lsqg[0]
+            ops.side_join()
+            return dx.view_as(xc), dW, (dbias if has_bias else None), db4, daft, ds, None, None, None, None, None, None
         nxt = None
         if F16 and link is not None and role == 2 and link.cs is not None and link.cs.shape[0] == K:
             nxt = (link.cs, link.se, 1.0, True)
@@ -356,7 +395,7 @@ class ImgLsqFn(torch.autograd.Function):
         return (dx.view_as(xc) if ctx.needs_input_grad[0] else None), db4, daft, ds, None, None
 
 
-class HeadLinearFn(torch.autograd.Function):
+class HeadLinearFn(_Fn):
     """LSQ_QLinear4head.forward (qlinear.py:193-238), the 8-bit classifier heads, on the integer path:
     move_b4 -> LsqQuantizer4head_input (ONE learned step, lsq.py:448-513) -> move_aft on the input, LsqQuantizerWeight (one
     learned step per output row, lsq.py:20-109) on the weight, both as int8 codes, one exact int8 GEMM with the step sizes and
@@ -545,7 +584,7 @@ def _pv_backward(dO, qp, ldq, qv, sp2, sv2, v_aft, B, N, H, C, ldS, qv16=None, q
     return dPq, dvhat
 
 
-class QKRAttnCoreFn(torch.autograd.Function):
+class QKRAttnCoreFn(_Fn):
     """QAttention_qkreparam.forward up to (not including) proj (attention.py:174-219), and the Swin variant
     (swin_attention_and_mlp.py:168-229) through `attn_bias` / `attn_mask`.  x is [B, N, C]."""
 
@@ -781,7 +820,7 @@ class QKRAttnCoreFn(torch.autograd.Function):
                 dkb4, dkaft, ds_k, ds_p, dbias, None, None, None, None, None, None)
 
 
-class QAttnCoreFn(torch.autograd.Function):
+class QAttnCoreFn(_Fn):
     """QAttention.forward between the qkv QLinear and proj (attention.py:70-102) / QAttention_swin
     (swin_attention_and_mlp.py:172-229).  qkv is [B, N, 3C] laid out (3, H, hd) along the last dim."""
 

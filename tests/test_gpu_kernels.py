@@ -652,6 +652,34 @@ def test_gemm_lsq_epilogue_is_gemm_then_quantizer(ops, Bt, N, C, H, bits):
         assert rel_err(ds_b, ds_a) < 3e-4
 
 
+@pytest.mark.parametrize("Bt,N,K,Nout,bits", [(16, 198, 384, 384, 2), (8, 198, 384, 1536, 2), (5, 198, 192, 768, 4), (3, 50, 128, 256, 3),
+                                             (1, 40, 64, 64, 2)])
+def test_gemm_dx_lsq_epilogue_is_gemm_then_lsq_backward(ops, Bt, N, K, Nout, bits):
+    """ofq_gemm_dx_lsq (the dX GEMM of a quantized linear layer with the backward of its input quantizer as the epilogue) against
+    ofq_gemm followed by ofq_lsq_bwd on the fp32 dX_hat: dx bit-identical (same roundings, same straight-through mask), the
+    step-size / shift gradients equal up to fp32 summation order."""
+    torch.manual_seed(200 + K + Nout)
+    M = Bt * N
+    lo, hi = -(1 << (bits - 1)), (1 << (bits - 1)) - 1
+    a16 = (torch.randn(M, Nout, device="cuda") * 300).half()                   # range-scaled gradient operand
+    wc = (torch.randint(lo, hi + 1, (Nout, K), device="cuda") * 2 + 1).half()   # exact fp16 copy of StatsQ codes (MN-major B)
+    x = torch.randn(M, K, device="cuda") * 1.2
+    b4 = torch.randn(K, device="cuda") * 0.05
+    alpha = torch.rand(N, device="cuda") * 0.5 + 0.3
+    g = 0.01
+    s2 = ops.lsq_effective_scale(alpha, g, recip=True)
+    sc = torch.tensor([512.0, 1 / 512.0, 0.0, 0.0], device="cuda")
+    vec = ops.vec
+    dxhat = torch.empty((M, K), dtype=torch.float32, device="cuda")
+    ops.gemm(ops.GEMM_F16, a16, (Nout, 0, 0, 0), wc, (K, 0, 0, 0), dxhat, (K, 0, 0), M, K, Nout, b_mn=True, rs=vec(s2[1], N), cs=vec(sc[1:2], 1))
+    dx_r, ds_r, db4_r, daft_r = ops.lsq_bwd(dxhat, x, b4, s2[0], ops.PER_ROW, N, 1, lo, hi, g)
+    dx, ds, db4, daft = ops.gemm_dx_lsq(ops.GEMM_F16, a16, (Nout, 0, 0, 0), wc, (K, 0, 0, 0), M, K, Nout, rs=vec(s2[1], N), cs=vec(sc[1:2], 1),
+                                        x2d=x, b4=b4, period=N, qlo=lo, qhi=hi, g=g, b_mn=True)
+    assert torch.equal(dx, dx_r)
+    assert 0.002 < (dx == 0).float().mean().item() < 0.98                       # both sides of the mask are exercised
+    assert rel_err(ds, ds_r) < 1e-5 and rel_err(db4, db4_r) < 1e-5 and rel_err(daft, daft_r) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------------ CGA
 @pytest.mark.parametrize("bits,br", [(2, 0.005), (3, 0.005), (4, 0.05)])
 def test_cga_mask_bit_exact(ops, bits, br):

@@ -324,6 +324,8 @@ def test_prologue_inference_cache_and_stale_graph_detection(Q):
     hits = pro.cache_hits
     out_c, n_c = infer()
     assert pro.cache_hits == hits and n_c > n_b and not torch.equal(out_c, out_b)
+    infer()                                            # (drops the training-mode twins of the jobs: tables rebuilt once more)
+    hits = pro.cache_hits
     out_d, _ = infer()
     assert pro.cache_hits == hits + 1 and torch.equal(out_c, out_d)
     with torch.no_grad():                              # a torch-side in-place update is seen through the version counters
