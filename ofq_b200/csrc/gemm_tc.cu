@@ -496,6 +496,262 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 
+__device__ __forceinline__ void tmem_ld_32x32_x16r(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_pin16(uint32_t (&r)[16]) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                      "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]) : : "memory");
+}
+// ------------------------------------------------------------------------------------------ 16-epilogue-warp variant
+// Same mainloop; SIXTEEN epilogue warps (four per TMEM lane quarter, chunk j of a tile goes to warp j % 4 of its quarter), TMEM
+// read-out in 16-column pieces, one staging buffer per warp: 576 threads at <= 112 registers. The epilogue of this engine is
+// bound by latency chains (TMEM load -> math -> staging -> fence -> TMA store), not by issue slots: twice the warps per scheduler
+// hide twice the latency (the same observation that took the fused attention kernels from 8 to 16 softmax warps).
+#ifndef OFQ_GEMM_EPI16_DEFAULT
+#define OFQ_GEMM_EPI16_DEFAULT 0
+#endif
+constexpr int EPI_WARPS16 = 16;
+constexpr int NUM_THREADS16 = 64 + EPI_WARPS16 * 32;
+constexpr int epi_nch16(int bn) { return (bn / 32 + 3) / 4; }
+
+template <int BN, int STAGES>
+struct SmemLayout16 {
+    static constexpr uint32_t A_BYTES = BM * KBYTES;
+    static constexpr uint32_t STAGE_BYTES = A_BYTES + BN * KBYTES;
+    static constexpr uint32_t OUT_OFF = STAGES * STAGE_BYTES;
+    static constexpr uint32_t OUT_BYTES = EPI_WARPS16 * 4096;
+    static constexpr uint32_t VEC_OFF = OUT_OFF + OUT_BYTES;
+    static constexpr uint32_t BAR_OFF = VEC_OFF + EPI_WARPS16 * epi_nch16(BN) * 64 * 4;
+    static constexpr uint32_t TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
+    static constexpr size_t DYN_BYTES = TOTAL + 1024;
+};
+
+// sixteen columns (half `sub` of a chunk) of row `lane` into the swizzled staging row
+template <int KIND, bool R1, bool TRACK>
+__device__ __forceinline__ void epi_math16(const uint32_t (&r)[16], const float rsv, const float rtv, const float* __restrict__ cs_c,
+                                           const float* __restrict__ ct_c, uint8_t* __restrict__ rowp, const int lane, const int sub,
+                                           float& omax) {
+    const float2 rs2 = make_float2(rsv, rsv), rt2 = make_float2(rtv, rtv);
+    float4 cs4[4], ct4[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        cs4[g] = ld_shared_v4_nc(cs_c + 16 * sub + 4 * g);
+        if (R1) ct4[g] = ld_shared_v4_nc(ct_c + 16 * sub + 4 * g);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float2 o[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t ra = r[4 * g + 2 * h], rb = r[4 * g + 2 * h + 1];
+            const float2 acc = KIND == 0 ? make_float2(static_cast<float>(static_cast<int32_t>(ra)), static_cast<float>(static_cast<int32_t>(rb)))
+                                         : make_float2(__uint_as_float(ra), __uint_as_float(rb));
+            const float2 cs2 = h == 0 ? make_float2(cs4[g].x, cs4[g].y) : make_float2(cs4[g].z, cs4[g].w);
+            const float2 t = __fmul2_rn(acc, rs2);
+            if (R1) {
+                const float2 ct2 = h == 0 ? make_float2(ct4[g].x, ct4[g].y) : make_float2(ct4[g].z, ct4[g].w);
+                o[h] = __ffma2_rn(t, cs2, __fmul2_rn(rt2, ct2));
+            } else {
+                o[h] = __fmul2_rn(t, cs2);
+            }
+            if (TRACK) omax = fmaxf(omax, fmaxf(fabsf(o[h].x), fabsf(o[h].y)));
+        }
+        st_shared_v4_nc(rowp + (((sub * 4 + g) ^ (lane & 7)) << 4), o[0].x, o[0].y, o[1].x, o[1].y);
+    }
+}
+
+template <int KIND, int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS16, 1)
+gemm_tc16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const GemmParams p, const int num_tiles, const int mtiles, const int ntiles) {
+    using L = SmemLayout16<BN, STAGES>;
+    constexpr uint32_t A_BYTES = L::A_BYTES;
+    constexpr uint32_t STAGE_BYTES = L::STAGE_BYTES;
+    constexpr uint32_t ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+    constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
+    constexpr uint32_t UMMA_K_BYTES = 32;
+    const uint32_t IDESC = KIND == 0 ? umma_idesc(2u, 1u, BM, BN)
+                                     : (umma_idesc(1u, (uint32_t)p.ab_fmt, BM, BN) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16));
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_full = empty_bar + STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* vec_s = reinterpret_cast<float*>(smem + L::VEC_OFF);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_WARPS16); }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            const int kelem = KIND == 0 ? KBYTES : KBYTES / 2;
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);
+                for (int i = 0; i < c.nit; ++i, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    const int g = c.it_begin + i;
+                    const int k2i = p.fd_kblocks.div(g), kb = g - k2i * p.kblocks;
+                    uint8_t* sa = smem + s * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                    if (KIND != 0 && p.a_mn) {
+                        for (int j = 0; j < BM / 64; ++j)
+                            tma_load_5d(sa + j * 8192, &tmA, &full_bar[s], c.m0 + 64 * j, kb * kelem, p.fd_ak2mod.mod(k2i) * p.a_k2, c.b1 * p.a_b1, c.b2 * p.a_b2);
+                    } else {
+                        tma_load_5d(sa, &tmA, &full_bar[s], kb * kelem, c.m0, p.fd_ak2mod.mod(k2i) * p.a_k2, c.b1 * p.a_b1, c.b2 * p.a_b2);
+                    }
+                    if (KIND != 0 && p.b_mn) {
+                        for (int j = 0; j < BN / 64; ++j)
+                            tma_load_5d(sb + j * 8192, &tmB, &full_bar[s], c.n0 + 64 * j, kb * kelem, p.fd_bk2mod.mod(k2i) * p.b_k2, c.b1 * p.b_b1, c.b2 * p.b_b2);
+                    } else {
+                        tma_load_5d(sb, &tmB, &full_bar[s], kb * kelem, c.n0, p.fd_bk2mod.mod(k2i) * p.b_k2, c.b1 * p.b_b1, c.b2 * p.b_b2);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            uint32_t it = 0, tc = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tc) {
+                const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);
+                const uint32_t as = tc & 1, aph = (tc >> 1) & 1;
+                mbar_wait(&acc_empty[as], aph ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * ACC_COLS;
+                for (int i = 0; i < c.nit; ++i, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                    const bool bmn = KIND != 0 && p.b_mn, amn = KIND != 0 && p.a_mn;
+                    const uint64_t bdesc = bmn ? umma_desc_mnmajor_sw128(sa + A_BYTES) : umma_desc_kmajor_sw128(sa + A_BYTES);
+                    const uint64_t adesc = amn ? umma_desc_mnmajor_sw128(sa) : umma_desc_kmajor_sw128(sa);
+                    const uint64_t badv = bmn ? (2048u >> 4) : (UMMA_K_BYTES >> 4);
+                    const uint64_t aadv = amn ? (2048u >> 4) : (UMMA_K_BYTES >> 4);
+#pragma unroll
+                    for (uint32_t kk = 0; kk < KBYTES / UMMA_K_BYTES; ++kk) {
+                        if (KIND == 0) umma_i8(tmem_d, adesc + kk * aadv, bdesc + kk * badv, IDESC, (i | kk) != 0);
+                        else umma_f16(tmem_d, adesc + kk * aadv, bdesc + kk * badv, IDESC, (i | kk) != 0);
+                    }
+                    tc_commit(&empty_bar[s]);
+                }
+                tc_commit(&acc_full[as]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int jq = (warp - 2) >> 2;                      // 0..3: which of the quarter's four warps
+        constexpr int NCH = epi_nch16(BN);
+        uint8_t* buf = smem + L::OUT_OFF + (warp - 2) * 4096;
+        float* myvec = vec_s + (warp - 2) * NCH * 64;
+        const bool track = p.amax != nullptr;
+        uint32_t tc = 0, nstore = 0;
+        float omax = 0.f;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tc) {
+            const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);
+            const uint32_t as = tc & 1, aph = (tc >> 1) & 1;
+            const int m_row0 = c.m0 + q * 32, m = m_row0 + lane;
+            const bool rank1 = p.has_rank1 && c.split == 0;
+            const bool row_ok = m < p.M;
+            const float rsv = row_ok ? (p.rs.p ? __ldg(p.rs.p + (long long)c.b1 * p.rs.bs1 + (long long)c.b2 * p.rs.bs2 + p.rs.fd.mod(m)) : 1.0f) : 0.f;
+            const float rtv = (row_ok && rank1) ? (p.rt.p ? __ldg(p.rt.p + (long long)c.b1 * p.rt.bs1 + (long long)c.b2 * p.rt.bs2 + p.rt.fd.mod(m)) : 1.0f) : 0.f;
+            int nvalid = (min(BN, p.N - c.n0) + 31) / 32;
+            if (m_row0 >= p.M) nvalid = 0;
+            const int nown = nvalid > jq ? (nvalid - jq + 3) >> 2 : 0;
+            __syncwarp();
+            {
+                const long long cs_off = (long long)c.b1 * p.cs.bs1 + (long long)c.b2 * p.cs.bs2;
+                const long long ct_off = (long long)c.b1 * p.ct.bs1 + (long long)c.b2 * p.ct.bs2;
+#pragma unroll
+                for (int k = 0; k < NCH; ++k) {
+                    const int n = c.n0 + (jq + 4 * k) * 32 + lane;
+                    const bool ok = n < p.N;
+                    myvec[k * 64 + lane] = ok ? (p.cs.p ? __ldg(p.cs.p + cs_off + p.cs.fd.mod(n)) : 1.0f) : 0.f;
+                    myvec[k * 64 + 32 + lane] = (ok && rank1) ? (p.ct.p ? __ldg(p.ct.p + ct_off + n) : 1.0f) : 0.f;
+                }
+            }
+            __syncwarp();
+            const bool have = c.nit > 0;
+            if (have) {
+                mbar_wait(&acc_full[as], aph);
+                tc_fence_after();
+            }
+            const uint32_t tmem_acc = tmem_base + as * ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+            uint32_t ra[16], rb[16];
+            if (nown > 0 && have) tmem_ld_32x32_x16r(tmem_acc + (uint32_t)(jq * 32), ra);
+#pragma unroll 1
+            for (int k = 0; k < nown; ++k) {
+                const int cc = jq + 4 * k;
+                const float* cs_c = myvec + k * 64;
+                const float* ct_c = cs_c + 32;
+                if (nstore > 0) {                            // the staging buffer must have been read by the previous store
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+                }
+                uint8_t* rowp = buf + lane * 128;
+                if (have) {
+                    tmem_ld_wait(); tmem_ld_pin16(ra);
+                    tmem_ld_32x32_x16r(tmem_acc + (uint32_t)(cc * 32 + 16), rb);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { ra[j] = 0u; rb[j] = 0u; }
+                }
+                if (rank1) { if (track) epi_math16<KIND, true, true>(ra, rsv, rtv, cs_c, ct_c, rowp, lane, 0, omax); else epi_math16<KIND, true, false>(ra, rsv, rtv, cs_c, ct_c, rowp, lane, 0, omax); }
+                else       { if (track) epi_math16<KIND, false, true>(ra, rsv, rtv, cs_c, ct_c, rowp, lane, 0, omax); else epi_math16<KIND, false, false>(ra, rsv, rtv, cs_c, ct_c, rowp, lane, 0, omax); }
+                if (have) {
+                    tmem_ld_wait(); tmem_ld_pin16(rb);
+                    if (k + 1 < nown) tmem_ld_32x32_x16r(tmem_acc + (uint32_t)((cc + 4) * 32), ra);
+                }
+                if (rank1) { if (track) epi_math16<KIND, true, true>(rb, rsv, rtv, cs_c, ct_c, rowp, lane, 1, omax); else epi_math16<KIND, true, false>(rb, rsv, rtv, cs_c, ct_c, rowp, lane, 1, omax); }
+                else       { if (track) epi_math16<KIND, false, true>(rb, rsv, rtv, cs_c, ct_c, rowp, lane, 1, omax); else epi_math16<KIND, false, false>(rb, rsv, rtv, cs_c, ct_c, rowp, lane, 1, omax); }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (p.atomic) tma_reduce_add_5d(&tmC, buf, c.n0 + cc * 32, m_row0, 0, c.b1 * p.c_b1, c.b2 * p.c_b2);
+                    else          tma_store_5d(&tmC, buf, c.n0 + cc * 32, m_row0, 0, c.b1 * p.c_b1, c.b2 * p.c_b2);
+                    tma_store_commit();
+                }
+                ++nstore;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+        if (p.amax) {
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) omax = fmaxf(omax, __shfl_xor_sync(0xffffffffu, omax, o2));
+            if (lane == 0) atomicMax(p.amax, __float_as_uint(omax));
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ CTA-pair variant
 // Same pipeline on a 2-CTA cluster: one tcgen05.mma.cta_group::2 of M = 256 per instruction. CTA r of the pair owns rows
 // [m0 + 128 r, m0 + 128 r + 128) of the 256 x BN tile (its accumulator lives in its own TMEM) and stages its own A rows
@@ -813,15 +1069,6 @@ __device__ __forceinline__ float lsq_piece(const uint32_t (&rr)[8], const float 
     return dot;
 }
 
-__device__ __forceinline__ void tmem_ld_32x32_x16r(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_pin16(uint32_t (&r)[16]) {
-    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
-                      "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]) : : "memory");
-}
 // sixteen columns = two 8-column pieces
 template <int MODE, bool RT1>
 __device__ __forceinline__ float lsq_piece16(const uint32_t (&rr)[16], const float rsv, const float rtv, const float* __restrict__ vec,
@@ -1336,6 +1583,24 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
         return OFQ_ERR_ARG;
     }
     const int grid = (int)(tiles < ofq_num_sms() ? tiles : ofq_num_sms());   // one persistent CTA per SM
+    if constexpr (NA == 1 && BN >= 64) {
+        // 16-epilogue-warp variant (OFQ_GEMM_EPI16: 1 = on for every single-CTA launch, 0 = off)
+        static const int epi16 = [] { const char* e = getenv("OFQ_GEMM_EPI16"); return e ? atoi(e) : OFQ_GEMM_EPI16_DEFAULT; }();
+        if (epi16 && !p.debug_nostore) {
+            constexpr int ST16 = BN >= 192 ? (STAGES > 3 ? 3 : STAGES) : (STAGES > 4 ? 4 : STAGES);     // 64 KB of staging beside the ring
+            constexpr size_t smem16 = SmemLayout16<BN, ST16>::DYN_BYTES;
+            static_assert(smem16 <= 227 * 1024, "shared memory budget exceeded");
+            auto kern16 = gemm_tc16_kernel<KIND, BN, ST16>;
+            static bool configured16 = false;
+            if (!configured16) {
+                OFQ_CUDA(cudaFuncSetAttribute(kern16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+                configured16 = true;
+            }
+            kern16<<<grid, NUM_THREADS16, smem16, stream>>>(tmA, tmB, tmC, p, (int)tiles, mtiles, ntiles);
+            OFQ_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
     kern<<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, tmC, p, (int)tiles, mtiles, ntiles);
     OFQ_CUDA(cudaGetLastError());
     return 0;

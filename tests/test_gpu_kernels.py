@@ -894,6 +894,20 @@ def test_gemm_pair_kernel_forced(ops):
     import sys
     env = dict(os.environ, OFQ_GEMM_PAIR="2")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
-                        "gemm and not pair_kernel_forced", "-p", "no:cacheprovider"], env=env, capture_output=True, text=True,
+                        "gemm and not forced", "-p", "no:cacheprovider"], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_gemm_16_epilogue_warp_variant_forced(ops):
+    """gemm_tc16_kernel (16 epilogue warps, 16-column TMEM pieces, 96 registers) is a measured-and-not-adopted variant of the
+    single-CTA GEMM (no faster than 8 warps on B200: the store-heavy tiles are bound by shared-memory / L2 bandwidth, not by
+    epilogue latency); OFQ_GEMM_EPI16=1 selects it, and the whole GEMM test matrix must still hold on it."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, OFQ_GEMM_EPI16="1", OFQ_GEMM_PAIR="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                        "gemm and not forced", "-p", "no:cacheprovider"], env=env, capture_output=True, text=True,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
