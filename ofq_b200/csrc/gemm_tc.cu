@@ -1305,28 +1305,12 @@ struct DxLsqSmem {
     static constexpr size_t DYN_BYTES = TOTAL + 1024;
 };
 
-// column sums over the 32 rows (lanes) of a warp for 16 columns held one per register: lane l ends with column l & 15
-__device__ __forceinline__ float colsum16(float (&v)[16], const int lane) {
-#pragma unroll
-    for (int s = 8; s >= 1; s >>= 1) {
-        const bool up = (lane & s) != 0;
-#pragma unroll
-        for (int i = 0; i < s; ++i) {
-            const float keep = up ? v[i + s] : v[i];
-            const float send = up ? v[i] : v[i + s];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-        }
-    }
-    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
-}
-
 // sixteen columns (half `sub` of a 32 x 32 chunk) of row `lane`; returns the row's partial of dy * (q - v | q)
 __device__ __forceinline__ float dxlsq_piece(const uint32_t (&rr)[16], const float rsv, const float csv, const float* __restrict__ b4v,
                                              const uint8_t* __restrict__ xrow, uint8_t* __restrict__ orow, const float qlo, const float qhi,
-                                             const int lane, const int sub, float* __restrict__ col_aft, float* __restrict__ col_b4) {
+                                             const int lane, const int sub) {
     constexpr float MAGIC = 12582912.f;
     const float2 rs2 = make_float2(rsv, rsv), cs2 = make_float2(csv, csv);
-    float ys[16], ds[16];
     float2 part2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -1347,13 +1331,9 @@ __device__ __forceinline__ float dxlsq_piece(const uint32_t (&rr)[16], const flo
             part2 = __ffma2_rn(y, make_float2(in0 ? qv.x : q.x, in1 ? qv.y : q.y), part2);
             o[2 * h] = in0 ? y.x : 0.f;
             o[2 * h + 1] = in1 ? y.y : 0.f;
-            ys[j] = y.x; ys[j + 1] = y.y;
-            ds[j] = o[2 * h]; ds[j + 1] = o[2 * h + 1];
         }
         st_shared_v4_nc(orow + ((j4 ^ (lane & 7)) << 4), o[0], o[1], o[2], o[3]);
     }
-    *col_aft = colsum16(ys, lane);
-    *col_b4 = colsum16(ds, lane);
     return part2.x + part2.y;
 }
 
@@ -1511,25 +1491,25 @@ gemm_dxlsq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const uint8_t* xrow = wbase + xslot * 4096 + lane * 128;
                 uint8_t* orow = obuf + lane * 128;
                 const float* b4v = myvec + k * 32;
-                float ca0, cb0, ca1, cb1;
                 tmem_ld_wait(); tmem_ld_pin16(ra);
                 tmem_ld_32x32_x16r(tmem_acc + (uint32_t)(cc * 32 + 16), rb);
-                part += dxlsq_piece(ra, rsv, csv, b4v, xrow, orow, qlo, qhi, lane, 0, &ca0, &cb0);
+                part += dxlsq_piece(ra, rsv, csv, b4v, xrow, orow, qlo, qhi, lane, 0);
                 tmem_ld_wait(); tmem_ld_pin16(rb);
                 if (k + 1 < nown) tmem_ld_32x32_x16r(tmem_acc + (uint32_t)((cc + 2) * 32), ra);
-                part += dxlsq_piece(rb, rsv, csv, b4v, xrow, orow, qlo, qhi, lane, 1, &ca1, &cb1);
-                // per-warp column sums: slot = (row block, lane quarter); lanes 0..15 own the first, 16..31 the second piece
-                {
-                    const int col = n_c + lane;
-                    if (col < p.N) {
-                        const long long slot = (long long)(c.m0 / BM) * 4 + q;
-                        float* cp = e.colpart + slot * 3 * p.N + col;
-                        cp[0] = lane < 16 ? ca0 : ca1;
-                        cp[p.N] = lane < 16 ? cb0 : cb1;
-                    }
-                }
+                part += dxlsq_piece(rb, rsv, csv, b4v, xrow, orow, qlo, qhi, lane, 1);
                 fence_proxy_async_smem();
                 __syncwarp();
+                // d move_b4: column sums of the staged dx tile over this warp's 32 rows. Lane l walks column l down the rows
+                // (row r holds it in 16-byte group (l / 4) ^ (r % 8): one conflict-free 128-byte wavefront per row). d move_aft
+                // (the unmasked column sums) is not formed here at all: sum_m dX_hat = (colsum(dY) * colscale) . W_codes.
+                {
+                    float cb = 0.f;
+#pragma unroll 8
+                    for (int r = 0; r < 32; ++r)
+                        cb += *reinterpret_cast<const float*>(obuf + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+                    const int col = n_c + lane;
+                    if (col < p.N) e.colpart[((long long)(c.m0 / BM) * 4 + q) * 3 * p.N + p.N + col] = cb;
+                }
                 if (lane == 0) {
                     tma_store_5d(&tmC, obuf, n_c, m_row0, 0, 0, 0);
                     tma_store_commit();
@@ -1547,6 +1527,26 @@ gemm_dxlsq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// out[k] = sum_n u1[n] * u2[n] * codes[n][k]: d move_aft of a linear layer's input from colsum(dY) and the weight codes
+__global__ void __launch_bounds__(256)
+codes_vecmat_kernel(const int8_t* __restrict__ codes, int rows, int cols, long long ld, const float* __restrict__ u1,
+                    const float* __restrict__ u2, float* __restrict__ out) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + tx;
+    float acc = 0.f;
+    if (col < cols)
+        for (int n = ty; n < rows; n += 8) acc = fmaf(__ldg(u1 + n) * (u2 ? __ldg(u2 + n) : 1.f), (float)codes[(long long)n * ld + col], acc);
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && col < cols) {
+        float s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s2 += red[k][tx];
+        out[col] = s2;
     }
 }
 
@@ -2010,7 +2010,8 @@ extern "C" long long ofq_gemm_dx_lsq_workspace(int M, int N) {
 
 extern "C" int ofq_gemm_dx_lsq(int kind, const ofq_operand_t* A, const ofq_operand_t* B, int M, int N, int K, const ofq_vec_t* rs,
                                const ofq_vec_t* cs, const float* x, long long ldx, const float* b4, int qlo, int qhi, float g,
-                               float* dx, long long lddx, float* d_s, float* d_b4, float* d_aft, float* workspace, void* stream) {
+                               float* dx, long long lddx, float* d_s, float* d_b4, float* d_aft, const int8_t* w_codes,
+                               long long ld_codes, const float* dy_colsum, const float* colscale, float* workspace, void* stream) {
     OFQ_REQUIRE(kind == OFQ_GEMM_BF16 || kind == OFQ_GEMM_F16, "ofq_gemm_dx_lsq: 16-bit kinds only");
     OFQ_REQUIRE(A && B && rs && rs->ptr && rs->period > 0 && x && dx && workspace && d_b4, "ofq_gemm_dx_lsq: null argument");
     OFQ_REQUIRE(M > 0 && N > 0 && K > 0 && N % 64 == 0, "ofq_gemm_dx_lsq: extents must be positive, N a multiple of 64");
@@ -2055,5 +2056,11 @@ extern "C" int ofq_gemm_dx_lsq(int kind, const ofq_operand_t* A, const ofq_opera
         default:  rc = launch_gemm_dxlsq<64, 4>(tmA, tmB, tmX, tmC, p, e, st); break;
     }
     if (rc) return rc;
-    return ofq_lsq_bwd_finalize_parts(e.colpart, 4 * mtiles, e.rowpart, 2 * ntiles * (long long)M, M, N, rs->period, g, d_s, d_b4, d_aft, stream);
+    // d_aft[k] = sum_m dX_hat[m][k] = sum_n colsum(dY)[n] * colscale[n] * W_codes[n][k]  (exact identity; no pass over dX_hat)
+    if (d_aft) {
+        OFQ_REQUIRE(w_codes && dy_colsum, "ofq_gemm_dx_lsq: d_aft needs the int8 weight codes and colsum(dY)");
+        codes_vecmat_kernel<<<(N + 31) / 32, 256, 0, st>>>(w_codes, K, N, ld_codes, dy_colsum, colscale, d_aft);
+        OFQ_CUDA(cudaGetLastError());
+    }
+    return ofq_lsq_bwd_finalize_parts(e.colpart, 4 * mtiles, e.rowpart, 2 * ntiles * (long long)M, M, N, rs->period, g, d_s, d_b4, nullptr, stream);
 }

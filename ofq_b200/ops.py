@@ -205,10 +205,12 @@ def gemm_lsq(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, b4: Optio
 
 
 def gemm_dx_lsq(kind: int, a16: torch.Tensor, a_strides, b16: torch.Tensor, b_strides, M: int, N: int, K: int, *, rs, cs, x2d: torch.Tensor,
-                b4: torch.Tensor, period: int, qlo: int, qhi: int, g: float, a_mn: bool = False, b_mn: bool = False):
+                b4: torch.Tensor, period: int, qlo: int, qhi: int, g: float, w_codes: torch.Tensor, dy_colsum: torch.Tensor,
+                colscale: Optional[torch.Tensor] = None, a_mn: bool = False, b_mn: bool = False):
     """dX GEMM of a quantized linear layer with the LSQ backward of its input quantizer as the epilogue (ofq_gemm_dx_lsq):
     returns (dx [M, N] fp32, d_s [min(period, M)], d_b4 [N], d_aft [N]); dX_hat itself is never written. rs = vec(1 / s_eff, period)
-    is both the GEMM's row un-scale and the quantizer's reciprocal step; cs the period-1 range un-scale."""
+    is both the GEMM's row un-scale and the quantizer's reciprocal step; cs the period-1 range un-scale. d_aft comes from the
+    identity sum_m dX_hat = (colsum(dY) * colscale) . w_codes (w_codes int8 [K, N]: the layer's weight codes)."""
     _cuda(a16, b16, x2d, b4)
     assert x2d.dtype == torch.float32 and x2d.stride(1) == 1 and tuple(x2d.shape) == (M, N)
     dev = x2d.device
@@ -220,9 +222,11 @@ def gemm_dx_lsq(kind: int, a16: torch.Tensor, a_strides, b16: torch.Tensor, b_st
     ws = torch.empty(lib.ofq_gemm_dx_lsq_workspace(M, N), dtype=torch.float32, device=dev)
     A = Operand(a16.data_ptr(), a_strides[0], 0, 0, 0, 0, 0, int(a_mn))
     B = Operand(b16.data_ptr(), b_strides[0], 0, 0, 0, 0, 0, int(b_mn))
-    _call("gemm_dx_lsq", 2, 2.0 * (M * K + N * K) + 8.0 * M * N, 2.0 * M * N * K, lib.ofq_gemm_dx_lsq, kind, C.byref(A), C.byref(B), M, N, K,
+    assert w_codes.dtype == torch.int8 and tuple(w_codes.shape) == (K, N) and w_codes.stride(1) == 1 and dy_colsum.numel() == K
+    _call("gemm_dx_lsq", 3, 2.0 * (M * K + N * K) + 8.0 * M * N, 2.0 * M * N * K, lib.ofq_gemm_dx_lsq, kind, C.byref(A), C.byref(B), M, N, K,
           rs, cs, x2d.data_ptr(), x2d.stride(0), b4.data_ptr(), qlo, qhi, float(g), dx.data_ptr(), N, d_s.data_ptr(), d_b4.data_ptr(),
-          d_aft.data_ptr(), ws.data_ptr(), _st(), tag=f"M{M} N{N} K{K} dx+lsq")
+          d_aft.data_ptr(), w_codes.data_ptr(), w_codes.stride(0), dy_colsum.data_ptr(), _ptr(colscale), ws.data_ptr(), _st(),
+          tag=f"M{M} N{N} K{K} dx+lsq")
     return dx, d_s, d_b4, d_aft
 
 

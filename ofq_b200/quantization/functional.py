@@ -152,7 +152,8 @@ def _linear_backward_f16(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulat
         # the dX GEMM with the input quantizer's backward (STE mask, ds, db4, daft) as its epilogue: dX_hat is never written
         x2d_, b4_, lo_, hi_, g_ = dx_lsq
         lsq_grads = ops.gemm_dx_lsq(GEMM_BWD, a16, (Nout, 0, 0, 0), wc16, (K, 0, 0, 0), M, K, Nout, rs=vec(se2[1], period), cs=_scalar(sc),
-                                    x2d=x2d_, b4=b4_, period=period, qlo=lo_, qhi=hi_, g=g_, b_mn=True)
+                                    x2d=x2d_, b4=b4_, period=period, qlo=lo_, qhi=hi_, g=g_, w_codes=wc, dy_colsum=colsum,
+                                    colscale=cs2[0], b_mn=True)
     else:
         ops.gemm(GEMM_BWD, a16, (Nout, 0, 0, 0), wc16, (K, 0, 0, 0), dxhat, (K, 0, 0), M, K, Nout, b_mn=True,
                  accumulate=accumulate_dx, rs=vec(se2[1], period), cs=_scalar(sc), amax=amax_dx)

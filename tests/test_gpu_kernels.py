@@ -662,7 +662,8 @@ def test_gemm_dx_lsq_epilogue_is_gemm_then_lsq_backward(ops, Bt, N, K, Nout, bit
     M = Bt * N
     lo, hi = -(1 << (bits - 1)), (1 << (bits - 1)) - 1
     a16 = (torch.randn(M, Nout, device="cuda") * 300).half()                   # range-scaled gradient operand
-    wc = (torch.randint(lo, hi + 1, (Nout, K), device="cuda") * 2 + 1).half()   # exact fp16 copy of StatsQ codes (MN-major B)
+    wc8 = (torch.randint(lo, hi + 1, (Nout, K), device="cuda") * 2 + 1).to(torch.int8)
+    wc = wc8.half()                                                            # exact fp16 copy of StatsQ codes (MN-major B)
     x = torch.randn(M, K, device="cuda") * 1.2
     b4 = torch.randn(K, device="cuda") * 0.05
     alpha = torch.rand(N, device="cuda") * 0.5 + 0.3
@@ -674,7 +675,8 @@ def test_gemm_dx_lsq_epilogue_is_gemm_then_lsq_backward(ops, Bt, N, K, Nout, bit
     ops.gemm(ops.GEMM_F16, a16, (Nout, 0, 0, 0), wc, (K, 0, 0, 0), dxhat, (K, 0, 0), M, K, Nout, b_mn=True, rs=vec(s2[1], N), cs=vec(sc[1:2], 1))
     dx_r, ds_r, db4_r, daft_r = ops.lsq_bwd(dxhat, x, b4, s2[0], ops.PER_ROW, N, 1, lo, hi, g)
     dx, ds, db4, daft = ops.gemm_dx_lsq(ops.GEMM_F16, a16, (Nout, 0, 0, 0), wc, (K, 0, 0, 0), M, K, Nout, rs=vec(s2[1], N), cs=vec(sc[1:2], 1),
-                                        x2d=x, b4=b4, period=N, qlo=lo, qhi=hi, g=g, b_mn=True)
+                                        x2d=x, b4=b4, period=N, qlo=lo, qhi=hi, g=g, w_codes=wc8,
+                                        dy_colsum=(a16.float() * s2[1].repeat(Bt).view(-1, 1) * sc[1]).sum(0), b_mn=True)
     assert torch.equal(dx, dx_r)
     assert 0.002 < (dx == 0).float().mean().item() < 0.98                       # both sides of the mask are exercised
     assert rel_err(ds, ds_r) < 1e-5 and rel_err(db4, db4_r) < 1e-5 and rel_err(daft, daft_r) < 1e-5
