@@ -404,12 +404,14 @@ OFQ_API int ofq_cga_adamw(float* p, const float* grad, float* exp_avg, float* ex
  *   d_b4[n]     = sum_m dx[m][n]                                          (deterministic: per-warp partials + one finalize)
  *   d_aft[n]    = sum_m dxhat[m][n] = sum_k dy_colsum[k] * colscale[k] * w_codes[k][n]   (optional; exact identity, no pass
  *                 over dxhat: w_codes int8 [K, N] are the layer's weight codes, dy_colsum = colsum(dY), colscale may be NULL)
+ * dx_absmax (optional, one float PRE-SET to 0) receives max |dx| (the bound for the fp16 range scale of whatever consumes dx).
  * 16-bit kinds, plain (unbatched) operands, N % 64 == 0. workspace: ofq_gemm_dx_lsq_workspace(M, N) floats. */
 OFQ_API long long ofq_gemm_dx_lsq_workspace(int M, int N);
 OFQ_API int ofq_gemm_dx_lsq(int kind, const ofq_operand_t* A, const ofq_operand_t* B, int M, int N, int K, const ofq_vec_t* rs,
                             const ofq_vec_t* cs, const float* x, long long ldx, const float* b4, int qlo, int qhi, float g,
                             float* dx, long long lddx, float* d_s, float* d_b4, float* d_aft, const int8_t* w_codes,
-                            long long ld_codes, const float* dy_colsum, const float* colscale, float* workspace, void* stream);
+                            long long ld_codes, const float* dy_colsum, const float* colscale, float* dx_absmax, float* workspace,
+                            void* stream);
 /* The finalize pass of the above on raw partials (colpart [nslots][3][cols], rowpart [planes][rows]). */
 OFQ_API int ofq_lsq_bwd_finalize_parts(const float* colpart, long long nslots, const float* rowpart, long long rowpart_total,
                                        long long rows, int cols, int period, float g, float* d_s, float* d_b4, float* d_aft,

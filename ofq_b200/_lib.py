@@ -98,7 +98,7 @@ SIGNATURES = {
     "ofq_adamw_multi": (_i, [_p, _i, _i, _i, _d, _d, _d, _d, _p, _p]),
     "ofq_gemm_dx_lsq_workspace": (_ll, [_i, _i]),
     "ofq_gemm_dx_lsq": (_i, [_i, C.POINTER(Operand), C.POINTER(Operand), _i, _i, _i, C.POINTER(Vec), C.POINTER(Vec), _p, _ll, _p, _i, _i, _f,
-                             _p, _ll, _p, _p, _p, _p, _ll, _p, _p, _p, _p]),
+                             _p, _ll, _p, _p, _p, _p, _ll, _p, _p, _p, _p, _p]),
     "ofq_lsq_bwd_finalize_parts": (_i, [_p, _ll, _p, _ll, _ll, _i, _i, _f, _p, _p, _p, _p]),
     "ofq_packed_row_bytes": (_ll, [_i, _i]),
     "ofq_pack_codes": (_i, [_p, _ll, _i, _ll, _i, _p, _ll, _p]),

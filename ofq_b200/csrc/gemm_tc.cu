@@ -1287,6 +1287,7 @@ gemm_lsq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // epilogue applies the straight-through mask, stores dx, and leaves per-row partials of the step-size gradient and per-warp
 // column sums (d move_b4, d move_aft) for the ordinary finalize pass. dX_hat never exists in HBM.
 struct DxLsqEpi {
+    unsigned int* amax;     // optional: max |dx| over the whole problem (bits of a non-negative float, atomicMax; pre-set to 0)
     const float* b4;        // [N]
     float* rowpart;         // [2 * ntiles][M]
     float* colpart;         // [4 * mtiles][3][N]
@@ -1308,7 +1309,7 @@ struct DxLsqSmem {
 // sixteen columns (half `sub` of a 32 x 32 chunk) of row `lane`; returns the row's partial of dy * (q - v | q)
 __device__ __forceinline__ float dxlsq_piece(const uint32_t (&rr)[16], const float rsv, const float csv, const float* __restrict__ b4v,
                                              const uint8_t* __restrict__ xrow, uint8_t* __restrict__ orow, const float qlo, const float qhi,
-                                             const int lane, const int sub) {
+                                             const int lane, const int sub, float& omax) {
     constexpr float MAGIC = 12582912.f;
     const float2 rs2 = make_float2(rsv, rsv), cs2 = make_float2(csv, csv);
     float2 part2 = make_float2(0.f, 0.f);
@@ -1331,6 +1332,7 @@ __device__ __forceinline__ float dxlsq_piece(const uint32_t (&rr)[16], const flo
             part2 = __ffma2_rn(y, make_float2(in0 ? qv.x : q.x, in1 ? qv.y : q.y), part2);
             o[2 * h] = in0 ? y.x : 0.f;
             o[2 * h + 1] = in1 ? y.y : 0.f;
+            omax = fmaxf(omax, fmaxf(fabsf(o[2 * h]), fabsf(o[2 * h + 1])));
         }
         st_shared_v4_nc(orow + ((j4 ^ (lane & 7)) << 4), o[0], o[1], o[2], o[3]);
     }
@@ -1442,6 +1444,7 @@ gemm_dxlsq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const float qlo = e.qlo, qhi = e.qhi;
         const float csv = p.cs.p ? __ldg(p.cs.p) : 1.0f;              // the range un-scale: one value for the whole problem
         uint32_t tc = 0, nstore = 0, xdone = 0, xissued = 0;
+        float omax = 0.f;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tc) {
             const TileCoord c = decode_tile(p, t, BN, mtiles, ntiles);
             const uint32_t as = tc & 1, aph = (tc >> 1) & 1;
@@ -1493,10 +1496,10 @@ gemm_dxlsq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const float* b4v = myvec + k * 32;
                 tmem_ld_wait(); tmem_ld_pin16(ra);
                 tmem_ld_32x32_x16r(tmem_acc + (uint32_t)(cc * 32 + 16), rb);
-                part += dxlsq_piece(ra, rsv, csv, b4v, xrow, orow, qlo, qhi, lane, 0);
+                part += dxlsq_piece(ra, rsv, csv, b4v, xrow, orow, qlo, qhi, lane, 0, omax);
                 tmem_ld_wait(); tmem_ld_pin16(rb);
                 if (k + 1 < nown) tmem_ld_32x32_x16r(tmem_acc + (uint32_t)((cc + 2) * 32), ra);
-                part += dxlsq_piece(rb, rsv, csv, b4v, xrow, orow, qlo, qhi, lane, 1);
+                part += dxlsq_piece(rb, rsv, csv, b4v, xrow, orow, qlo, qhi, lane, 1, omax);
                 fence_proxy_async_smem();
                 __syncwarp();
                 // d move_b4: column sums of the staged dx tile over this warp's 32 rows. Lane l walks column l down the rows
@@ -1521,6 +1524,11 @@ gemm_dxlsq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[as]);
         }
+        if (e.amax) {
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) omax = fmaxf(omax, __shfl_xor_sync(0xffffffffu, omax, o2));
+            if (lane == 0) atomicMax(e.amax, __float_as_uint(omax));
+        }
         if (lane == 0) tma_store_wait_all<0>();
     }
     __syncthreads();
@@ -1530,23 +1538,16 @@ gemm_dxlsq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
-// out[k] = sum_n u1[n] * u2[n] * codes[n][k]: d move_aft of a linear layer's input from colsum(dY) and the weight codes
-__global__ void __launch_bounds__(256)
-codes_vecmat_kernel(const int8_t* __restrict__ codes, int rows, int cols, long long ld, const float* __restrict__ u1,
-                    const float* __restrict__ u2, float* __restrict__ out) {
-    __shared__ float red[8][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int col = blockIdx.x * 32 + tx;
-    float acc = 0.f;
-    if (col < cols)
-        for (int n = ty; n < rows; n += 8) acc = fmaf(__ldg(u1 + n) * (u2 ? __ldg(u2 + n) : 1.f), (float)codes[(long long)n * ld + col], acc);
-    red[ty][tx] = acc;
-    __syncthreads();
-    if (ty == 0 && col < cols) {
-        float s2 = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s2 += red[k][tx];
-        out[col] = s2;
+// d move_aft of a linear layer's input from colsum(dY) and the weight codes: sum_n u1[n] * u2[n] * codes[n][k], spread over the
+// `nslots` column-partial slots the finalize pass sums anyway (slot b takes rows b, b + nslots, ...; vector 0 of colpart)
+__global__ void __launch_bounds__(128)
+codes_vecmat_parts_kernel(const int8_t* __restrict__ codes, int rows, int cols, long long ld, const float* __restrict__ u1,
+                          const float* __restrict__ u2, float* __restrict__ colpart, int nslots) {
+    const int b = blockIdx.x;
+    for (int col = threadIdx.x; col < cols; col += blockDim.x) {
+        float acc = 0.f;
+        for (int n = b; n < rows; n += nslots) acc = fmaf(__ldg(u1 + n) * (u2 ? __ldg(u2 + n) : 1.f), (float)codes[(long long)n * ld + col], acc);
+        colpart[(long long)b * 3 * cols + col] = acc;
     }
 }
 
@@ -2011,7 +2012,8 @@ extern "C" long long ofq_gemm_dx_lsq_workspace(int M, int N) {
 extern "C" int ofq_gemm_dx_lsq(int kind, const ofq_operand_t* A, const ofq_operand_t* B, int M, int N, int K, const ofq_vec_t* rs,
                                const ofq_vec_t* cs, const float* x, long long ldx, const float* b4, int qlo, int qhi, float g,
                                float* dx, long long lddx, float* d_s, float* d_b4, float* d_aft, const int8_t* w_codes,
-                               long long ld_codes, const float* dy_colsum, const float* colscale, float* workspace, void* stream) {
+                               long long ld_codes, const float* dy_colsum, const float* colscale, float* dx_absmax, float* workspace,
+                               void* stream) {
     OFQ_REQUIRE(kind == OFQ_GEMM_BF16 || kind == OFQ_GEMM_F16, "ofq_gemm_dx_lsq: 16-bit kinds only");
     OFQ_REQUIRE(A && B && rs && rs->ptr && rs->period > 0 && x && dx && workspace && d_b4, "ofq_gemm_dx_lsq: null argument");
     OFQ_REQUIRE(M > 0 && N > 0 && K > 0 && N % 64 == 0, "ofq_gemm_dx_lsq: extents must be positive, N a multiple of 64");
@@ -2037,6 +2039,7 @@ extern "C" int ofq_gemm_dx_lsq(int kind, const ofq_operand_t* A, const ofq_opera
     OFQ_REQUIRE(!p.b_mn || bn % 64 == 0, "ofq_gemm_dx_lsq: tile width");
     const long long ntiles = (N + bn - 1) / bn, mtiles = (M + BM - 1) / BM;
     DxLsqEpi e;
+    e.amax = reinterpret_cast<unsigned int*>(dx_absmax);
     e.b4 = b4; e.rowpart = workspace; e.colpart = workspace + 2 * ntiles * (long long)M;
     e.qlo = (float)qlo; e.qhi = (float)qhi;
     CUtensorMap tmA, tmB, tmX, tmC;
@@ -2059,8 +2062,8 @@ extern "C" int ofq_gemm_dx_lsq(int kind, const ofq_operand_t* A, const ofq_opera
     // d_aft[k] = sum_m dX_hat[m][k] = sum_n colsum(dY)[n] * colscale[n] * W_codes[n][k]  (exact identity; no pass over dX_hat)
     if (d_aft) {
         OFQ_REQUIRE(w_codes && dy_colsum, "ofq_gemm_dx_lsq: d_aft needs the int8 weight codes and colsum(dY)");
-        codes_vecmat_kernel<<<(N + 31) / 32, 256, 0, st>>>(w_codes, K, N, ld_codes, dy_colsum, colscale, d_aft);
+        codes_vecmat_parts_kernel<<<(unsigned)(4 * mtiles), 128, 0, st>>>(w_codes, K, N, ld_codes, dy_colsum, colscale, e.colpart, (int)(4 * mtiles));
         OFQ_CUDA(cudaGetLastError());
     }
-    return ofq_lsq_bwd_finalize_parts(e.colpart, 4 * mtiles, e.rowpart, 2 * ntiles * (long long)M, M, N, rs->period, g, d_s, d_b4, nullptr, stream);
+    return ofq_lsq_bwd_finalize_parts(e.colpart, 4 * mtiles, e.rowpart, 2 * ntiles * (long long)M, M, N, rs->period, g, d_s, d_b4, d_aft, stream);
 }

@@ -206,7 +206,7 @@ def gemm_lsq(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, b4: Optio
 
 def gemm_dx_lsq(kind: int, a16: torch.Tensor, a_strides, b16: torch.Tensor, b_strides, M: int, N: int, K: int, *, rs, cs, x2d: torch.Tensor,
                 b4: torch.Tensor, period: int, qlo: int, qhi: int, g: float, w_codes: torch.Tensor, dy_colsum: torch.Tensor,
-                colscale: Optional[torch.Tensor] = None, a_mn: bool = False, b_mn: bool = False):
+                colscale: Optional[torch.Tensor] = None, a_mn: bool = False, b_mn: bool = False, amax: Optional[torch.Tensor] = None):
     """dX GEMM of a quantized linear layer with the LSQ backward of its input quantizer as the epilogue (ofq_gemm_dx_lsq):
     returns (dx [M, N] fp32, d_s [min(period, M)], d_b4 [N], d_aft [N]); dX_hat itself is never written. rs = vec(1 / s_eff, period)
     is both the GEMM's row un-scale and the quantizer's reciprocal step; cs the period-1 range un-scale. d_aft comes from the
@@ -225,7 +225,7 @@ def gemm_dx_lsq(kind: int, a16: torch.Tensor, a_strides, b16: torch.Tensor, b_st
     assert w_codes.dtype == torch.int8 and tuple(w_codes.shape) == (K, N) and w_codes.stride(1) == 1 and dy_colsum.numel() == K
     _call("gemm_dx_lsq", 3, 2.0 * (M * K + N * K) + 8.0 * M * N, 2.0 * M * N * K, lib.ofq_gemm_dx_lsq, kind, C.byref(A), C.byref(B), M, N, K,
           rs, cs, x2d.data_ptr(), x2d.stride(0), b4.data_ptr(), qlo, qhi, float(g), dx.data_ptr(), N, d_s.data_ptr(), d_b4.data_ptr(),
-          d_aft.data_ptr(), w_codes.data_ptr(), w_codes.stride(0), dy_colsum.data_ptr(), _ptr(colscale), ws.data_ptr(), _st(),
+          d_aft.data_ptr(), w_codes.data_ptr(), w_codes.stride(0), dy_colsum.data_ptr(), _ptr(colscale), _ptr(amax), ws.data_ptr(), _st(),
           tag=f"M{M} N{N} K{K} dx+lsq")
     return dx, d_s, d_b4, d_aft
 

@@ -150,10 +150,10 @@ def _linear_backward_f16(dY2d, qx, wc, cs2, se2, period, x_aft, dxhat, accumulat
     lsq_grads = None
     if dx_lsq is not None:
         # the dX GEMM with the input quantizer's backward (STE mask, ds, db4, daft) as its epilogue: dX_hat is never written
-        x2d_, b4_, lo_, hi_, g_ = dx_lsq
+        x2d_, b4_, lo_, hi_, g_, amax_ = dx_lsq
         lsq_grads = ops.gemm_dx_lsq(GEMM_BWD, a16, (Nout, 0, 0, 0), wc16, (K, 0, 0, 0), M, K, Nout, rs=vec(se2[1], period), cs=_scalar(sc),
                                     x2d=x2d_, b4=b4_, period=period, qlo=lo_, qhi=hi_, g=g_, w_codes=wc, dy_colsum=colsum,
-                                    colscale=cs2[0], b_mn=True)
+                                    colscale=cs2[0], b_mn=True, amax=amax_)
     else:
         ops.gemm(GEMM_BWD, a16, (Nout, 0, 0, 0), wc16, (K, 0, 0, 0), dxhat, (K, 0, 0), M, K, Nout, b_mn=True,
                  accumulate=accumulate_dx, rs=vec(se2[1], period), cs=_scalar(sc), amax=amax_dx)
@@ -285,8 +285,11 @@ class QLinearFn(_Fn):
         # single-producer input gradients that leave as fp32 dx (fc1 and proj inputs): the quantizer's backward runs as the
         # epilogue of the dX GEMM (ofq_gemm_dx_lsq) and dX_hat never exists
         fuse_dx = (F16 and FUSED_DX and act == ACT_NONE and K % 64 == 0 and M % P == 0 and x2d.stride(0) % 4 == 0
-                   and not (link is not None and role == 2))
-        dxkw = {"dx_lsq": (x2d, b4, lo, hi, g)} if fuse_dx else {}
+                   and not (link is not None and role == 2 and link.fuse))
+        # a consumer of dx that takes a range-scaled fp16 operand (the attention backward behind proj) needs max |dx|
+        want_max = fuse_dx and link is not None and role == 2 and link.cs is not None and link.cs.shape[0] == K
+        dx_amax = ops.scratch_zeros(1, dY.device) if want_max else None
+        dxkw = {"dx_lsq": (x2d, b4, lo, hi, g, dx_amax)} if fuse_dx else {}
         dxhat = None if fuse_dx else torch.empty((M, K), dtype=torch.float32, device=dY.device)
         dY2d = None if fused_in else dY.contiguous().view(M, -1)      # (never materialise the zero-stride placeholder)
         if fused_in:
@@ -318,6 +321,8 @@ class QLinearFn(_Fn):
                 return dx, dW, (dbias if has_bias else None), db4, daft, ds, None, None, None, None, None, None
         if lsqg:
             dx, ds, db4, daft = lsqg[0]
+            if want_max:
+                link.sc = ops.scale_from_max(dx_amax, v1=link.cs, v2=link.se, mult=1.0, product=True)
             ops.side_join()
             return dx.view_as(xc), dW, (dbias if has_bias else None), db4, daft, ds, None, None, None, None, None, None
         nxt = None

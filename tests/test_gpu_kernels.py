@@ -674,10 +674,12 @@ def test_gemm_dx_lsq_epilogue_is_gemm_then_lsq_backward(ops, Bt, N, K, Nout, bit
     dxhat = torch.empty((M, K), dtype=torch.float32, device="cuda")
     ops.gemm(ops.GEMM_F16, a16, (Nout, 0, 0, 0), wc, (K, 0, 0, 0), dxhat, (K, 0, 0), M, K, Nout, b_mn=True, rs=vec(s2[1], N), cs=vec(sc[1:2], 1))
     dx_r, ds_r, db4_r, daft_r = ops.lsq_bwd(dxhat, x, b4, s2[0], ops.PER_ROW, N, 1, lo, hi, g)
+    amax = torch.zeros(1, device="cuda")
     dx, ds, db4, daft = ops.gemm_dx_lsq(ops.GEMM_F16, a16, (Nout, 0, 0, 0), wc, (K, 0, 0, 0), M, K, Nout, rs=vec(s2[1], N), cs=vec(sc[1:2], 1),
                                         x2d=x, b4=b4, period=N, qlo=lo, qhi=hi, g=g, w_codes=wc8,
-                                        dy_colsum=(a16.float() * s2[1].repeat(Bt).view(-1, 1) * sc[1]).sum(0), b_mn=True)
+                                        dy_colsum=(a16.float() * s2[1].repeat(Bt).view(-1, 1) * sc[1]).sum(0), b_mn=True, amax=amax)
     assert torch.equal(dx, dx_r)
+    assert amax.item() == dx_r.abs().max().item()                               # max |dx| for the consumer's fp16 range scale
     assert 0.002 < (dx == 0).float().mean().item() < 0.98                       # both sides of the mask are exercised
     assert rel_err(ds, ds_r) < 1e-5 and rel_err(db4, db4_r) < 1e-5 and rel_err(daft, daft_r) < 1e-5
 
