@@ -218,6 +218,34 @@ def test_swin_window_attention(Q, shift, qkr):
     run_layer(mod, load_golden(f"qattention_swin_{'qkr' if qkr else 'plain'}_shift{shift}_w3a3"))
 
 
+@pytest.mark.parametrize("shift", [0, 3])
+def test_swin_window_attention_4_cga_class(Q, shift):
+    """QAttention_swin_qkreparam_4_cga (swin_attention_and_mlp.py:554-671): the CGA weight quantizer is value- and
+    gradient-identical to StatsQ, so the class must reproduce the QKR golden of the reference."""
+    from ofq_b200.host.swin import ShiftedWindowAttention
+    mod = Q.QAttention_swin_qkreparam_4_cga(ShiftedWindowAttention(32, [7, 7], [shift, shift], 2), weight_bits=3, input_bits=3,
+                                            boundaryRange=0.005)
+    run_layer(mod, load_golden(f"qattention_swin_qkr_shift{shift}_w3a3"))
+
+
+def test_patch_embed_against_reference_golden(Q):
+    """LSQ_QConv2d (8-bit patch embedding, qlinear.py:138-191) on the int8 tensor-core path against the REFERENCE's own module
+    (tests/golden/make_golden_ends.py): output, input gradient and every parameter gradient."""
+    from ofq_b200.quantization.modules import qlinear as QL
+    run_layer(QL.LSQ_QConv2d(m=nn.Conv2d(3, 64, 16, 16), pretrained_initialized=True), load_golden("qconv2d_patch16"))
+
+
+def test_head_against_reference_golden(Q):
+    """LSQ_QLinear4head (8-bit classifier head, qlinear.py:193-238) on the int8 tensor-core path (functional.HeadLinearFn) against
+    the REFERENCE's own module."""
+    from ofq_b200 import ops
+    from ofq_b200.quantization.modules import qlinear as QL
+    mod = QL.LSQ_QLinear4head(m=nn.Linear(192, 1000), weight_quant_method="lsq", pretrained_initialized=True)
+    l0 = ops.LAUNCHES
+    run_layer(mod, load_golden("qlinear4head"))
+    assert ops.LAUNCHES > l0                           # the step sizes came from the checkpoint: the native path ran
+
+
 @pytest.mark.parametrize("qkr", [False, True])
 def test_swin_step_against_reference(Q, qkr):
     """Two-stage Swin (depths 2+2, width 32/64, 7x7 windows, patch merging `reduction` QLinear), W3A3."""
