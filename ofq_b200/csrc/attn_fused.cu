@@ -1217,6 +1217,9 @@ qkr_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     }
                     tmem_st_wait();
                 }
+                // (write-after-read on `red` across tiles: the next tile's writes come after its acc_full, which the MMA warp
+                // can only signal once ALL sixteen warps have arrived on acc_free, i.e. after every read below - ordered
+                // through the mbarrier chain, which compute-sanitizer's racecheck does not follow and reports as a hazard)
                 red[(part * 2 + 0) * BM + t] = dot;
                 red[(part * 2 + 1) * BM + t] = dsp;
                 named_bar_sync(2, 512);
