@@ -779,10 +779,25 @@ lsq_bwd_finalize_cols(const float* __restrict__ colpart, int cols, long long nbl
     if (col < cols) {
         // zero_sum: sum_rows dy is analytically zero, so d_b4 = sum_inside dy = -sum_outside dy; subtracting the two
         // partial sums block by block cancels the (reduced-precision) noise carried by the un-clipped elements
-        if (zero_sum && vecid == 1)
-            for (long long b = ty; b < nblk; b += 8) acc += colpart[(b * 3 + 1) * cols + col] - colpart[(b * 3 + 0) * cols + col];
-        else
-            for (long long b = ty; b < nblk; b += 8) acc += colpart[(b * 3 + vecid) * cols + col];
+        // four independent partial sums: the loads of four slots are in flight together (the pass is latency-, not
+        // bandwidth-bound: ~25 dependent L2 round trips per thread otherwise); summed in a fixed order
+        float a4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (zero_sum && vecid == 1) {
+            long long b = ty;
+            for (; b + 24 < nblk; b += 32) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a4[u] += colpart[((b + 8 * u) * 3 + 1) * cols + col] - colpart[((b + 8 * u) * 3 + 0) * cols + col];
+            }
+            for (; b < nblk; b += 8) a4[0] += colpart[(b * 3 + 1) * cols + col] - colpart[(b * 3 + 0) * cols + col];
+        } else {
+            long long b = ty;
+            for (; b + 24 < nblk; b += 32) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a4[u] += colpart[((b + 8 * u) * 3 + vecid) * cols + col];
+            }
+            for (; b < nblk; b += 8) a4[0] += colpart[(b * 3 + vecid) * cols + col];
+        }
+        acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
     }
     red[ty][tx] = acc;
     __syncthreads();
@@ -822,8 +837,17 @@ lsq_bwd_finalize_rows(const float* __restrict__ rowpart, long long total, long l
     const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
     const long long i = (long long)bx * 8 + tx;
     float acc = 0.f;
-    if (i < nscale)
-        for (long long j = i + (long long)ty * nscale; j < total; j += 32 * nscale) acc += rowpart[j];
+    if (i < nscale) {
+        float a4[4] = {0.f, 0.f, 0.f, 0.f};
+        const long long step = 32 * nscale;
+        long long j = i + (long long)ty * nscale;
+        for (; j + 3 * step < total; j += 4 * step) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a4[u] += rowpart[j + u * step];
+        }
+        for (; j < total; j += step) a4[0] += rowpart[j];
+        acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+    }
     __shared__ float red2[32][9];
     red2[ty][tx] = acc;
     __syncthreads();
