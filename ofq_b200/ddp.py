@@ -22,9 +22,8 @@ _ALIGN = 32          # floats
 
 class FlatGradAllReduce:
     """`direct=True` (default): the weight-gradient GEMMs of the ofq_b200 layers write straight into the parameter's slice
-    of the flat buffer (functional.GRAD_SLOTS -> take()): the slice is handed out as a fresh view that autograd adopts as
-    `.grad`, so ~94 % of the gradient bytes are never copied, and the per-weight zero fills (split-K outputs accumulate)
-    become the one memset of zero(). Everything else (biases, norms, step sizes) is gathered by the multi-tensor copy."""
+    of the flat buffer (functional.GRAD_SLOTS -> take()): the slice is zeroed and handed out as a fresh view that autograd adopts
+    as `.grad`, so ~94 % of the gradient bytes are never copied. Everything else (biases, norms, step sizes) is gathered by the multi-tensor copy."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], world_size: int, direct: bool = True):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
@@ -54,7 +53,6 @@ class FlatGradAllReduce:
             p.grad = None
         if self.direct:
             from .quantization import functional
-            self.flat.zero_()
             self._taken.clear()
             functional.GRAD_SLOTS = self
 
@@ -68,7 +66,10 @@ class FlatGradAllReduce:
         self.direct_hits += 1
         p = self.params[i]
         off = self.views[i].storage_offset()
-        return self.flat[off:off + p.numel()].view_as(p)
+        v = self.flat[off:off + p.numel()].view_as(p)
+        # zeroed HERE, right before the GEMM that accumulates into it (not by one memset of the whole buffer at the start of the
+        # step: by the time a layer's backward runs those lines would have left L2 again and every reduce-add would go to HBM)
+        return v.zero_()
 
     def scale_loss(self, loss: torch.Tensor) -> torch.Tensor:
         return loss / self.world_size if self.world_size > 1 else loss
