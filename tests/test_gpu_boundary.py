@@ -156,3 +156,31 @@ def test_cga_adamw_state_dict_round_trip_matches_torch_adamw(Q):
             opt.step()
     for p, q in zip(ps2, pr):
         assert rel_err(p.detach(), q.detach()) < 1e-6
+
+
+def test_dispatcher_ops_run_the_c_abi_kernels():
+    """torch.ops.ofq_b200.*  are thin wrappers over the same launchers as ofq_b200.ops: identical results."""
+    import ofq_b200.torch_ops  # noqa: F401
+    from ofq_b200 import ops
+    torch.manual_seed(60)
+    w = torch.nn.init.trunc_normal_(torch.empty(96, 64), std=0.02).cuda()
+    codes, colscale = torch.ops.ofq_b200.statsq_codes(w, 2)
+    rc, rs = ops.statsq_codes(w, 2)[:2]
+    assert torch.equal(codes, rc) and torch.equal(colscale, rs)
+    assert torch.equal(torch.ops.ofq_b200.cga_mask(w, 2, 0.05), ops.cga_mask(w, 2, 0.05))
+    x = torch.randn(40, 64, device="cuda")
+    b4 = torch.randn(64, device="cuda") * 0.05
+    se = torch.ops.ofq_b200.lsq_effective_scale(torch.rand(10, device="cuda") * 0.5 + 0.2, 0.01)
+    qx = torch.ops.ofq_b200.lsq_quant(x, b4, se, False, 10, 1, -2, 1)
+    assert torch.equal(qx, ops.lsq_quant(x, b4, se, ops.PER_ROW, 10, 1, -2, 1))
+    out = torch.ops.ofq_b200.qgemm_fwd(qx, se, codes, colscale, None)
+    ref = (qx.float() * se.repeat(4).view(-1, 1)) @ (codes.float() * colscale.view(-1, 1)).t()
+    assert (out - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+    wq, wk = torch.randn(64, 64, device="cuda"), torch.randn(64, 64, device="cuda")
+    assert torch.equal(torch.ops.ofq_b200.wqk_compose(wq, wk, 2), ops.wqk_compose(wq, wk, 2))
+    p = torch.randn(96, 64, device="cuda")
+    ref_p, g = p.clone(), torch.randn_like(p)
+    m, v, rm, rv = torch.zeros_like(p), torch.zeros_like(p), torch.zeros_like(p), torch.zeros_like(p)
+    torch.ops.ofq_b200.cga_adamw_step(p, g, m, v, 1, 1e-3, 0.9, 0.999, 1e-8, 0.05, 2, 0.05)
+    ops.cga_adamw_(ref_p, g, rm, rv, 1, 1e-3, 0.9, 0.999, 1e-8, 0.05, bits=2, boundary_range=0.05)
+    assert torch.equal(p, ref_p) and torch.equal(m, rm) and torch.equal(v, rv)

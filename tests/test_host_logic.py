@@ -50,3 +50,24 @@ def test_auto_split_k_fills_whole_rounds_for_the_weight_gradient_shapes():
     for tiles, expect in ((36, 4), (18, 8), (24, 6), (6, 24)):       # dW_qk (18 x 2), fc1 (3 x 6), fc2 (12 x 2), v / proj (3 x 2)
         sp = choose_splits(tiles, 396)
         assert sp == expect and tiles * sp <= 148
+
+
+def test_dispatcher_ops_are_registered_with_schemas_and_no_cpu_kernel():
+    """the kernels are PyTorch dispatcher operators (`torch.ops.ofq_b200.*`); CUDA-only (calling one with CPU tensors
+    raises: no CPU fallback in the product path), with fake implementations for shape propagation."""
+    import torch
+    import ofq_b200.torch_ops as T
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    for n in T.OPS:
+        schema = str(getattr(torch.ops.ofq_b200, n).default._schema)
+        assert schema.startswith(f"ofq_b200::{n}("), schema
+    assert "Tensor(a0!) p" in str(torch.ops.ofq_b200.cga_adamw_step.default._schema)        # in-place update is declared
+    with FakeTensorMode():
+        w = torch.empty(8, 16, device="cuda")
+        codes, colscale = torch.ops.ofq_b200.statsq_codes(w, 2)
+        assert codes.shape == (8, 16) and codes.dtype == torch.int8 and colscale.shape == (8,)
+        out = torch.ops.ofq_b200.qgemm_fwd(codes, colscale, codes, colscale, None)
+        assert out.shape == (8, 8) and out.dtype == torch.float32
+    import pytest
+    with pytest.raises(NotImplementedError):
+        torch.ops.ofq_b200.cga_mask(torch.randn(4, 4), 2, 0.005)
