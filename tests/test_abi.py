@@ -55,6 +55,23 @@ def test_sass_is_blackwell_native():
     for mnem in ("UTCIMMA", "UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UTMAREDG"):
         assert mnem in sass, mnem
     assert "sm_100a" in sass
+    # per kernel: the round-2 kernels are tcgen05 / TMEM / TMA kernels themselves, not wrappers around the GEMM engine
+    per_fn, cur = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+            per_fn[cur] = []
+        elif cur is not None:
+            per_fn[cur].append(line)
+    want = {"qkr_attn_fwd16_kernel": ("UTCIMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG"),          # S and P.V MMAs, TMEM both ways
+            "qkr_attn_bwd_kernel": ("UTCIMMA", "UTCHMMA", "LDTM", "UTMALDG"),                    # int8 S recompute + fp16 dP
+            "gemm_lsq_kernel": ("UTCIMMA", "LDTM", "UTMALDG", "UTMASTG"),
+            "gemm_dxlsq_kernel": ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG")}
+    for frag, mnems in want.items():
+        bodies = ["\n".join(v) for k, v in per_fn.items() if frag in k]
+        assert bodies, frag
+        for m in mnems:
+            assert any(m in b for b in bodies), (frag, m)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a machine without a GPU")
